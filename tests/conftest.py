@@ -1,0 +1,36 @@
+import os
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def make_particles(x, mat_ids, n_grid, used=None, rho=None):
+    """Particle dict in the format OracleSim / the CUDA simulator build() expect (MPM:136-175)."""
+    from fluidlab_b200.macros import MU, LAMDA, RHO, MAT_CLASS
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x)
+    mat = np.broadcast_to(np.asarray(mat_ids, dtype=np.int32), (n,)).copy()
+    dx = 1.0 / n_grid
+    p_vol = (dx * 0.5) ** 2
+    rho = np.array([RHO[m] for m in mat], dtype=np.float64) if rho is None else np.asarray(rho, dtype=np.float64)
+    return dict(
+        x=x, mat=mat, used=np.ones(n, dtype=np.int32) if used is None else np.asarray(used, dtype=np.int32),
+        cls=np.array([MAT_CLASS[m] for m in mat], dtype=np.int32),
+        mu=np.array([MU[m] for m in mat], dtype=np.float32).astype(np.float64),
+        lam=np.array([LAMDA[m] for m in mat], dtype=np.float32).astype(np.float64),
+        rho=rho, body_id=np.zeros(n, dtype=np.int32), bodies={'n': 1},
+        mass=(np.float32(p_vol) * rho.astype(np.float32)).astype(np.float64),  # MPM:174 evaluates in f32
+    )
+
+
+@pytest.fixture
+def particles_factory():
+    return make_particles

@@ -1,0 +1,179 @@
+"""CPU tests of the oracle itself: SVD convention, conservation invariants, adjoint vs central
+finite differences in fp64 (SURVEY.md §8c substitute pins 1-3).  No GPU needed."""
+import numpy as np
+import pytest
+from conftest import make_particles
+from oracle import oracle as orc
+from fluidlab_b200 import macros as M
+
+
+def test_svd_convention_and_reconstruction():
+    rng = np.random.RandomState(0)
+    for prec, tol in ((64, 1e-12), (32, 2e-6)):
+        for it in range(200):
+            A = np.eye(3) + 0.3 * rng.randn(3, 3) if it % 2 else rng.randn(3, 3)
+            if it == 7:
+                A = np.eye(3) * 1.3  # fully degenerate
+            if it == 9:
+                A = np.diag([2.0, 2.0, 0.5])
+            if prec == 32:
+                A = A.astype(np.float32).astype(np.float64)
+            U, s, V = orc.svd3(A, prec)
+            assert np.allclose(U @ np.diag(s) @ V.T, A, atol=tol * max(1, np.abs(A).max()))
+            assert abs(np.linalg.det(U) - 1) < 10 * tol and abs(np.linalg.det(V) - 1) < 10 * tol
+            assert abs(s[0]) >= abs(s[1]) - tol and abs(s[1]) >= abs(s[2]) - tol
+            assert s[0] >= 0 and s[1] >= 0
+            assert np.sign(np.linalg.det(A)) == np.sign(s[2]) or abs(s[2]) < tol
+            ref = np.linalg.svd(A, compute_uv=False)
+            assert np.allclose(np.abs(s), ref, atol=tol * 10)
+
+
+def _cloud(n, rng, lo=0.35, hi=0.65):
+    return rng.uniform(lo, hi, size=(n, 3))
+
+
+def test_mass_momentum_conservation_p2g_g2p():
+    rng = np.random.RandomState(1)
+    n_grid = 16
+    P = make_particles(_cloud(300, rng), M.WATER, n_grid)
+    sim = orc.OracleSim(n_grid, P, gravity=(0, 0, 0), precision=64)
+    fr = sim.get_frame(0)
+    v0 = rng.randn(300, 3) * 0.1
+    sim.set_frame(0, fr['x'], v0, fr['C'], fr['F'], fr['used'])
+    L = sim.L
+    L.orc_phase_reset_grid(sim.h); L.orc_phase_p2g(sim.h, 0, 1)
+    vin, m, _ = sim.get_grid()
+    assert np.isclose(m.sum(), P['mass'].sum(), rtol=1e-12)
+    # F = I, C = 0 -> J = 1 -> zero stress -> grid momentum equals particle momentum
+    assert np.allclose(vin.sum(0), (P['mass'][:, None] * v0).sum(0), rtol=1e-10, atol=1e-14)
+    L.orc_phase_grid_op(sim.h, 0); L.orc_phase_g2p(sim.h, 0)
+    f1 = sim.get_frame(1)
+    assert np.allclose((P['mass'][:, None] * f1['v']).sum(0), (P['mass'][:, None] * v0).sum(0), rtol=1e-10, atol=1e-14)
+
+
+def test_apic_preserves_rigid_translation():
+    rng = np.random.RandomState(2)
+    n_grid = 16
+    P = make_particles(_cloud(400, rng), M.ELASTIC, n_grid)
+    sim = orc.OracleSim(n_grid, P, gravity=(0, 0, 0), precision=64)
+    fr = sim.get_frame(0)
+    v0 = np.tile(np.array([0.3, -0.2, 0.1]), (400, 1))
+    sim.set_frame(0, fr['x'], v0, fr['C'], fr['F'], fr['used'])
+    sim.substep(0)
+    f1 = sim.get_frame(1)
+    assert np.allclose(f1['v'], v0, atol=1e-12)
+    assert np.allclose(f1['C'], 0, atol=1e-9)
+    assert np.allclose(f1['x'], fr['x'] + 2e-4 * v0, atol=1e-14)
+
+
+def _random_state(sim, rng, amp_F=0.02, amp_C=5.0, amp_v=0.5):
+    N = sim.N
+    fr = sim.get_frame(0)
+    v = rng.randn(N, 3) * amp_v
+    Cm = rng.randn(N, 3, 3) * amp_C
+    F = np.eye(3)[None] + rng.randn(N, 3, 3) * amp_F
+    sim.set_frame(0, fr['x'], v, Cm, F, fr['used'])
+    return dict(x=fr['x'].copy(), v=v, C=Cm, F=F, used=fr['used'])
+
+
+def _run_loss(sim, st, n_sub, wts):
+    sim.set_frame(0, st['x'], st['v'], st['C'], st['F'], st['used'])
+    for f in range(n_sub):
+        sim.substep(f)
+    fr = sim.get_frame(n_sub)
+    return sum((wts[k] * fr[k]).sum() for k in ('x', 'v', 'C', 'F'))
+
+
+@pytest.mark.parametrize("mat", [M.WATER, M.ELASTIC, M.ICECREAM, M.MILK_VIS, M.PLASTIC_DEMO])
+@pytest.mark.parametrize("boundary", [None, dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.3, 0.7))])
+def test_substep_adjoint_matches_finite_differences(mat, boundary):
+    rng = np.random.RandomState(3)
+    n_grid, N, n_sub = 16, 120, 3
+    if boundary is None:
+        boundary = dict(type='cube', lower=(0.32, 0.32, 0.32), upper=(0.68, 0.68, 0.68))
+    P = make_particles(_cloud(N, rng, 0.36, 0.64), mat, n_grid)
+    sim = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=boundary, precision=64, max_substeps_local=10)
+    st = _random_state(sim, rng)
+    wts = {k: rng.randn(*st[k].shape) for k in ('x', 'v', 'C', 'F')}
+    _run_loss(sim, st, n_sub, wts)
+    sim.reset_grad()
+    sim.set_grad_frame(n_sub, wts['x'], wts['v'], wts['C'], wts['F'])
+    for f in reversed(range(n_sub)):
+        sim.substep_grad(f)
+    g = sim.get_grad_frame(0)
+    eps = 1e-6
+    checked = 0
+    for key in ('x', 'v', 'C', 'F'):
+        flat = st[key].reshape(-1)
+        for idx in rng.choice(flat.size, 6, replace=False):
+            old = flat[idx]
+            flat[idx] = old + eps; lp = _run_loss(sim, st, n_sub, wts)
+            flat[idx] = old - eps; lm = _run_loss(sim, st, n_sub, wts)
+            flat[idx] = old
+            fd = (lp - lm) / (2 * eps)
+            an = g[key].reshape(-1)[idx]
+            assert abs(fd - an) <= 2e-5 * max(1.0, abs(fd), abs(an)), (key, idx, fd, an)
+            checked += 1
+    assert checked == 24
+
+
+def _latte_like(precision, n_sub_steps, flux=2):
+    """tiny LatteArt-like scene: coffee pool + parked milk + injector (envs/latteart_env.py:54-74)."""
+    rng = np.random.RandomState(4)
+    n_grid = 16
+    n_coffee, n_milk = 150, 60
+    x = np.concatenate([np.tile(M.NOWHERE, (n_milk, 1)), rng.uniform((0.35, 0.36, 0.35), (0.65, 0.45, 0.65), size=(n_coffee, 3))])
+    mat = np.concatenate([np.full(n_milk, M.MILK), np.full(n_coffee, M.COFFEE)])
+    used = np.concatenate([np.zeros(n_milk), np.ones(n_coffee)]).astype(np.int32)
+    P = make_particles(x, mat, n_grid, used=used)
+    bnd = dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.34, 0.9))
+    sim = orc.OracleSim(n_grid, P, gravity=(0, -20, 0), boundary=bnd, precision=precision, max_substeps_local=20)
+    rv = np.random.RandomState(5).uniform(size=(20, flux, 3))
+    sim.add_effector(type=1, action_dim=3, boundary=dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.55, 0.55)),
+                     radius=0.0075, flux=flux, inject_v=(0, -3, 0), inject_p=(0, 0, 0), locally_random=True, random_vector=rv,
+                     act_range=np.where(used == 0)[0], max_action_steps=64)
+    return sim, P
+
+
+def _latte_loss(sim, P, actions, action_p, tgt, n_steps, weight=1.0):
+    fr = dict(x=P['x'], v=np.zeros_like(P['x']), C=np.zeros((len(P['x']), 3, 3)), F=np.tile(np.eye(3), (len(P['x']), 1, 1)), used=P['used'])
+    sim.enable_grad()
+    sim.set_frame(0, fr['x'], fr['v'], fr['C'], fr['F'], fr['used'])
+    sim.set_effector_state(0, 0, np.array([0.5, 0.55, 0.5, 1, 0, 0, 0, 0.0]))
+    sim.apply_action_p(action_p)
+    total = 0.0
+    for s in range(n_steps):
+        sim.step(actions[s])
+        total += sim.loss_value(sim.cur_substep_local, M.MILK, weight, tgt[s])
+    return total
+
+
+def test_dloss_daction_injector_chain_fd():
+    """End to end dLoss/dAction (velocity actions and the initial-position action) through the injector,
+    across a checkpointed chunk boundary (T=20, 3 steps = 30 substeps), vs central differences in fp64."""
+    n_steps = 3
+    sim, P = _latte_like(64, n_steps)
+    rng = np.random.RandomState(6)
+    actions = rng.uniform(-0.004, 0.004, size=(n_steps, 3))
+    action_p = np.array([0.47, 0.55, 0.52])
+    tgt = [P['x'] * 0 + rng.uniform(0.4, 0.6, size=P['x'].shape) for _ in range(n_steps)]
+    _latte_loss(sim, P, actions, action_p, tgt, n_steps)
+    sim.reset_grad()
+    for s in reversed(range(n_steps)):
+        sim.loss_seed(sim.cur_substep_local, M.MILK, 1.0, tgt[s])
+        sim.step_grad(actions[s])
+    sim.apply_action_p_grad()
+    g = sim.get_action_grad(n_steps)
+    assert g.shape == (n_steps + 1, 3)
+    eps = 1e-6
+    for (i, j) in [(0, 0), (0, 2), (1, 0), (2, 2), (3, 0), (3, 2)]:
+        def run(d):
+            a, ap = actions.copy(), action_p.copy()
+            if i < n_steps: a[i, j] += d
+            else: ap[j] += d
+            return _latte_loss(sim, P, a, ap, tgt, n_steps)
+        fd = (run(eps) - run(-eps)) / (2 * eps)
+        assert abs(fd - g[i, j]) <= 1e-5 * max(1.0, abs(fd)), (i, j, fd, g[i, j])
+    # y is pinned by the effector's own boundary (y_range lower == upper) -> zero gradient
+    assert np.allclose(g[:, 1], 0)
+    assert np.abs(g[:, [0, 2]]).max() > 1e-6
