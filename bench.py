@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — MPM substeps/s of the B200-native FluidEngine substep (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--bwd 1]
+
+A bench "step" is one simulator step = 10 MLS-MPM substeps (MPM:30,749-751) of the workload BASELINE.json's metric
+is quoted on: configs[1], single-material water block free fall, 1M particles, 128^3 grid, fp32, forward only
+(SURVEY.md §8d C2).  `value` = substeps/s with the state resident in HBM; `e2e` = the same through the public
+MPMSimulator API with host buffers (set_state from pinned host memory at every episode start, get_state_RL D2H every
+step, as envs/fluid_env.py:131-150 does).  `roofline` is for the dominant kernel (p2g); `cpu_baseline` times the CPU
+oracle (restatement of the reference algorithm; Taichi is not installable) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+N_PARTICLES = 1_000_000
+QUALITY = 2  # 128^3
+GRAVITY = (0.0, -10.0, 0.0)
+LO, HI = (0.25, 0.30, 0.25), (0.75, 0.54, 0.75)
+SUBSTEPS_PER_STEP = 10
+
+
+def workload_particles(n=N_PARTICLES, seed=0, lo=LO, hi=HI):
+    from fluidlab_b200 import macros as M
+    x = np.random.RandomState(seed).uniform(lo, hi, size=(n, 3))
+    return dict(x=x, mat=np.full(n, M.WATER, dtype=np.int32), used=np.ones(n, dtype=np.int32), rho=np.full(n, M.RHO[M.WATER]),
+                body_id=np.zeros(n, dtype=np.int32), bodies={'n': 1})
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True); self._t.start(); return self
+
+    def __exit__(self, *a):
+        self._stop.set(); self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace('.', '').isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(self.samples)}
+
+
+def cpu_baseline_run(n_particles, max_seconds=20.0, max_substeps=6, threads=None):
+    """Time the CPU oracle (restatement of mpm_simulator.py:515-533, fp32, OpenMP) on the same workload."""
+    from conftest import make_particles
+    from oracle import oracle as orc
+    from fluidlab_b200 import macros as M
+    wp = workload_particles(n_particles)
+    P = make_particles(wp['x'], M.WATER, 64 * QUALITY)
+    L = orc.lib()
+    if threads:
+        L.orc_set_threads(int(threads))
+    cores = L.orc_get_max_threads()
+    o = orc.OracleSim(64 * QUALITY, P, gravity=GRAVITY, max_substeps_local=2, precision=32)
+    o.substep(0)  # warm-up (page faults, thread pool)
+    t0, n = time.perf_counter(), 0
+    while n < max_substeps and (time.perf_counter() - t0) < max_seconds:
+        o.substep(n % 2); n += 1
+    dt = time.perf_counter() - t0
+    return dict(value=n / dt, unit='substeps/s', cores=int(cores), kind='port',
+                sample=f'{n} forward substeps of the full workload ({n_particles} particles, {64 * QUALITY}^3 grid) in {dt:.1f}s; '
+                       'C++/OpenMP restatement of the reference algorithm (Taichi ti.cpu is not installable)')
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path = oracle port, all host threads; each bench step is a bounded sample of
+    ONE substep of the workload (a full 10-substep step at 1M particles takes ~10 s of CPU)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from conftest import make_particles
+    from oracle import oracle as orc
+    from fluidlab_b200 import macros as M
+    wp = workload_particles(N_PARTICLES)
+    P = make_particles(wp['x'], M.WATER, 64 * QUALITY)
+    L = orc.lib()
+    cores = L.orc_get_max_threads()
+    o = orc.OracleSim(64 * QUALITY, P, gravity=GRAVITY, max_substeps_local=2, precision=32)
+    for _ in range(max(1, min(args.warmup, 2))):
+        o.substep(0)
+    K = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for i in range(K):
+        o.substep(i % 2)
+    dt = time.perf_counter() - t0
+    val = K / dt
+    line = {'metric': 'mpm_substeps_per_s_fwd', 'value': val, 'unit': 'substeps/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * dt / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'impl': 'reference',
+            'config': {'workload': 'C2 water block free fall, 1M particles, 128^3 grid, forward', 'step': '1 substep (bounded sample)'},
+            'cpu_baseline': {'value': val, 'unit': 'substeps/s', 'cores': int(cores), 'kind': 'port',
+                             'sample': f'{K} forward substeps, full workload, C++/OpenMP restatement of the reference (Taichi not installable)'},
+            'e2e': {'value': val, 'unit': 'substeps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--particles', type=int, default=N_PARTICLES)
+    ap.add_argument('--bwd', type=int, default=1, help='also time forward+backward (extra keys)')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--sort-every', type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from fluidlab_b200 import MPMSimulator
+
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    W = max(args.warmup, 3)
+    K = args.steps
+    T = 50
+    N = args.particles
+    sim = MPMSimulator(dim=3, quality=QUALITY, gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T, max_substeps_global=10 ** 7,
+                       ckpt_dest='gpu', device=dev, sort_every=args.sort_every)
+    parts = workload_particles(N, seed=rank)
+    sim.build(None, None, [], parts)
+    init = sim.get_state()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ------------------------------------------------------------------ device-resident throughput
+    for _ in range(W):
+        sim.step(None)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as cs:
+        e0.record()
+        for _ in range(K):
+            sim.step(None)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = cs.summary()
+    value = world * K * SUBSTEPS_PER_STEP / (ms * 1e-3)
+
+    # ------------------------------------------------------------------ per-kernel timing (roofline)
+    f = sim.cur_substep_local
+    if f >= T:
+        f = 0
+    used = int(sim.readframe_torch(f, ('used',))['used'].sum().item())
+
+    def time_phase(fn, n=20, pre=None):
+        tot = 0.0
+        for i in range(n + 3):
+            if pre:
+                pre()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            if i >= 3:
+                tot += a.elapsed_time(b)
+        return tot / n
+
+    t_p2g = time_phase(lambda: sim.phase('p2g', f, 0), pre=lambda: sim.phase('clear_grid', f))
+    sim.phase('clear_grid', f); sim.phase('p2g', f, 0)
+    g_t = int((sim._grid_pm[:, 3] > 0).sum().item())
+    t_gop = time_phase(lambda: sim.phase('grid_op', f, 0))
+    # g2p writes frame f+1: time it on a scratch frame pair (f -> f+1 is rewritten by the next step anyway)
+    t_g2p = time_phase(lambda: sim._ck(sim._lib.fmpm_g2p(sim._h, f, sim._stream()), 'g2p'))
+    sim.phase('clear_grid', f)
+    peak, peak_src = peaks()
+    p2g_bytes = 136 * used + 16 * g_t            # p2g particle bytes + accumulated grid write-back
+    g2p_bytes = 76 * used + 12 * g_t             # g2p(+advect)
+    roof = {'bound': 'hbm', 'kernel': 'k_p2g', 'achieved': p2g_bytes / (t_p2g * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+            'frac': p2g_bytes / (t_p2g * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+            'algorithmic_bytes_per_launch': p2g_bytes, 'launch_ms': t_p2g, 'n_used': used, 'touched_nodes': g_t}
+    roof_pair = {'kernels': 'k_p2g+k_g2p', 'achieved': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9,
+                 'frac': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9 / peak, 'p2g_ms': t_p2g, 'g2p_ms': t_g2p, 'grid_op_ms': t_gop,
+                 'bytes': p2g_bytes + g2p_bytes}
+
+    # ------------------------------------------------------------------ forward+backward (BASELINE metric, second half)
+    fb = None
+    if args.bwd:
+        import fluidlab_b200  # noqa
+        nfb = max(2, min(K, 10))
+        tgt = torch.zeros((N, 3), dtype=torch.float32, device=dev) + 0.5
+        mask = sim.material_row_mask(fluidlab_b200.macros.WATER)
+
+        def fwd_bwd():
+            sim.set_state(0, init); sim.enable_grad()
+            for _ in range(nfb):
+                sim.step(None)
+            sim.reset_grad()
+            sim.add_x_grad_chamfer(tgt, mask, 1.0)
+            for _ in range(nfb):
+                sim.step_grad(None)
+        fwd_bwd(); barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fwd_bwd(); b.record(); barrier()
+        fb_ms = max_over_ranks(a.elapsed_time(b))
+        fb = {'value': world * nfb * SUBSTEPS_PER_STEP / (fb_ms * 1e-3), 'unit': 'substeps/s (each = 1 forward + 1 backward substep, incl. chunk re-simulation and set_state)',
+              'steps': nfb}
+        sim.disable_grad()
+
+    # ------------------------------------------------------------------ end to end through the public API with host buffers
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in init.items() if k in ('x', 'v', 'C', 'F', 'used')}
+    EP = 10  # steps per episode
+    n_ep = max(1, K // EP)
+    h2d = sum(t.numel() * t.element_size() for t in pin.values()) / EP
+    d2h = N * (12 + 12 + 4)
+
+    def episode():
+        sim.cur_substep_global = 0
+        sim.set_state(0, pin)                      # H2D of the episode's initial state (pinned host)
+        out = None
+        for _ in range(EP):
+            sim.step(None)
+            out = sim.get_state_RL()               # D2H of x, v, used every step (FluidEnv._get_obs)
+        return out
+    episode(); barrier()
+    t0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n_ep):
+        episode()
+    b.record(); barrier()
+    e2e_ms = max_over_ranks(max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3))
+    e2e_val = world * n_ep * EP * SUBSTEPS_PER_STEP / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        cpu = None if args.no_cpu else cpu_baseline_run(N)
+        line = {
+            'metric': 'mpm_substeps_per_s_fwd', 'value': value, 'unit': 'substeps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'C2 water block free fall, {N} particles/GPU, 128^3 grid, fp32, forward (BASELINE.json configs[1])',
+                       'substeps_per_step': SUBSTEPS_PER_STEP, 'dt': 2e-4, 'gravity': GRAVITY, 'max_substeps_local': T,
+                       'cell_sort_every_steps': args.sort_every,
+                       'l2_policy': 'inputs larger than L2 (one substep touches >= 212 B x 1M particles = 212 MB > 126 MB L2)',
+                       'parallelism': 'single GPU' if world == 1 else f'{world} independent slabs-as-replicas (ghost exchange not built yet)'},
+            'clocks': clocks,
+            'e2e': {'value': e2e_val, 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},
+            'gpu_launches': K * (SUBSTEPS_PER_STEP * 3 + (2 if args.sort_every else 0)),
+            'roofline': roof, 'roofline_p2g_g2p': roof_pair,
+            'fwd_bwd': fb,
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,132 @@
+"""ctypes binding of libfluidmpm.so (C ABI in include/fluidmpm.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or no GPU is visible, loading
+fails loudly.  (`tests/` use `oracle/` as the checker; nothing here imports it.)
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfluidmpm.so")
+_LIB = None
+
+vp = C.c_void_p
+
+
+class FmpmConfig(C.Structure):
+    _fields_ = [
+        ("n_grid", C.c_int), ("n_particles", C.c_int), ("max_substeps_local", C.c_int), ("n_substeps", C.c_int),
+        ("dt", C.c_float), ("dx", C.c_float), ("inv_dx", C.c_float), ("p_vol", C.c_float),
+        ("k_stress", C.c_float),
+        ("gravity", C.c_float * 3),
+        ("boundary_type", C.c_int),
+        ("b_lower", C.c_float * 3), ("b_upper", C.c_float * 3),
+        ("cyl_center", C.c_float * 2), ("cyl_radius", C.c_float),
+        ("restitution", C.c_float),
+        ("lock_mask", C.c_int),
+        ("n_materials", C.c_int),
+        ("device", C.c_int),
+    ]
+
+
+class FmpmMaterial(C.Structure):
+    _fields_ = [("mu", C.c_float), ("lam", C.c_float), ("mass", C.c_float), ("cls", C.c_int)]
+
+
+class FmpmBuffers(C.Structure):
+    _fields_ = [
+        ("pa", vp), ("pf", vp), ("pf8", vp),
+        ("ga", vp), ("gf", vp), ("gf8", vp),
+        ("grid_pm", vp), ("grid_v", vp), ("ggrid_v", vp), ("ggrid_pm", vp),
+        ("materials", vp),
+        ("scratch_a", vp), ("scratch_f", vp), ("scratch_f8", vp),
+        ("sort_keys_in", vp), ("sort_keys_out", vp), ("sort_vals_in", vp), ("sort_vals_out", vp),
+        ("sort_tmp", vp), ("sort_tmp_bytes", C.c_ulonglong),
+    ]
+
+
+class FmpmEffector(C.Structure):
+    _fields_ = [
+        ("pos", vp), ("quat", vp), ("v", vp), ("w", vp),
+        ("gpos", vp), ("gquat", vp), ("gv", vp), ("gw", vp),
+        ("act", vp), ("gact", vp), ("act_p", vp), ("gact_p", vp),
+        ("action_dim", C.c_int),
+        ("scale_v", C.c_float * 6), ("scale_p", C.c_float * 6),
+        ("boundary_type", C.c_int), ("b_lower", C.c_float * 3), ("b_upper", C.c_float * 3),
+        ("cyl_center", C.c_float * 2), ("cyl_radius", C.c_float),
+    ]
+
+
+class FmpmInjector(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("flux", C.c_int), ("radius", C.c_float),
+        ("inject_v", C.c_float * 3), ("inject_p", C.c_float * 3),
+        ("random_vector", vp), ("act_range", vp), ("n_act_range", C.c_int),
+    ]
+
+
+_I, _F, _U = C.c_int, C.c_float, C.c_uint
+_PROTOS = {
+    "fmpm_create": (_I, [C.POINTER(FmpmConfig), C.POINTER(vp)]),
+    "fmpm_destroy": (None, [vp]),
+    "fmpm_bind": (_I, [vp, C.POINTER(FmpmBuffers)]),
+    "fmpm_last_error": (C.c_char_p, [vp]),
+    "fmpm_sort_workspace_bytes": (C.c_ulonglong, [vp]),
+    "fmpm_abi_version": (_I, []),
+    "fmpm_clear_grid": (_I, [vp, vp]),
+    "fmpm_p2g": (_I, [vp, _I, _I, vp]),
+    "fmpm_grid_op": (_I, [vp, _I, _I, vp]),
+    "fmpm_g2p": (_I, [vp, _I, vp]),
+    "fmpm_substep": (_I, [vp, _I, vp]),
+    "fmpm_inject": (_I, [vp, _I, C.POINTER(FmpmInjector), C.POINTER(FmpmEffector), _I, _I, vp, vp]),
+    "fmpm_substep_grad": (_I, [vp, _I, _I, _I, vp]),
+    "fmpm_g2p_grad_scatter": (_I, [vp, _I, _I, vp]),
+    "fmpm_grid_op_grad": (_I, [vp, _I, vp]),
+    "fmpm_particle_grad": (_I, [vp, _I, _I, _I, vp]),
+    "fmpm_inject_grad": (_I, [vp, _I, _I, C.POINTER(FmpmInjector), C.POINTER(FmpmEffector), _I, vp, vp]),
+    "fmpm_write_frame": (_I, [vp, _I, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "fmpm_read_frame": (_I, [vp, _I, vp, vp, vp, vp, vp, vp, vp]),
+    "fmpm_write_grad": (_I, [vp, _I, vp, vp, vp, vp, vp, vp]),
+    "fmpm_read_grad": (_I, [vp, _I, vp, vp, vp, vp, vp, vp]),
+    "fmpm_zero_grad": (_I, [vp, _I, vp]),
+    "fmpm_copy_frame": (_I, [vp, _I, _I, vp]),
+    "fmpm_permute_grad": (_I, [vp, _I, _I, vp, vp, vp]),
+    "fmpm_sort": (_I, [vp, _I, vp, vp, vp, vp]),
+    "fmpm_read_grid": (_I, [vp, vp, vp, vp, vp]),
+    "fmpm_read_grid_grad": (_I, [vp, vp, vp, vp, vp]),
+    "fmpm_write_grid_grad": (_I, [vp, vp, vp, vp, vp]),
+    "fmpm_effector_step": (_I, [vp, C.POINTER(FmpmEffector), _I, _I, vp, vp]),
+    "fmpm_effector_step_grad": (_I, [vp, C.POINTER(FmpmEffector), _I, _I, vp]),
+    "fmpm_effector_apply_action_p": (_I, [vp, C.POINTER(FmpmEffector), vp]),
+    "fmpm_effector_apply_action_p_grad": (_I, [vp, C.POINTER(FmpmEffector), vp]),
+    "fmpm_loss_chamfer": (_I, [vp, _I, vp, vp, _U, _F, vp, vp]),
+    "fmpm_loss_chamfer_grad": (_I, [vp, _I, _I, vp, vp, _U, _F, vp]),
+}
+EXPORTS = tuple(_PROTOS.keys())
+
+
+def load():
+    """dlopen libfluidmpm.so and attach prototypes.  Raises if the library has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python fluidlab_b200/csrc/build.py` (nvcc, sm_100a). "
+                "fluidlab_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+class FmpmError(RuntimeError):
+    pass
+
+
+def check(lib, handle, rc, what=""):
+    if rc != 0:
+        msg = lib.fmpm_last_error(handle)
+        raise FmpmError(f"{what}: {msg.decode() if msg else 'error %d' % rc}")

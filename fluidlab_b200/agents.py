@@ -1,0 +1,134 @@
+"""Agents: groups of effectors.  Mirrors fluidlab/fluidengine/agents/agent.py (`Agent` :9-152) and
+agents/agent_injector.py (`AgentInjector` :8-39).  `collide` of injector agents is the identity
+(agent_injector.py:34-36), so no collision kernel is involved for them."""
+import numpy as np
+from .effectors import Effector, Injector, BallInjector, Rigid  # noqa: F401 (names are eval'ed from yaml, agent.py:32)
+
+
+class Agent:
+    def __init__(self, max_substeps_local, max_substeps_global, max_action_steps_global, ckpt_dest, collide_type='particle'):
+        self.max_substeps_local = max_substeps_local
+        self.max_substeps_global = max_substeps_global
+        self.max_action_steps_global = max_action_steps_global
+        self.ckpt_dest = ckpt_dest
+        self.collide_type = collide_type
+        assert self.collide_type in ['particle', 'grid', 'both']
+        self.effectors = []
+        self.action_dims = [0]
+
+    def add_effector(self, type, params, mesh_cfg, boundary_cfg):
+        cls = eval(type) if isinstance(type, str) else type
+        effector = cls(max_substeps_local=self.max_substeps_local, max_substeps_global=self.max_substeps_global,
+                       max_action_steps_global=self.max_action_steps_global, ckpt_dest=self.ckpt_dest, **dict(params))
+        if mesh_cfg is not None:
+            effector.setup_mesh(**dict(mesh_cfg))
+        effector.setup_boundary(**dict(boundary_cfg))
+        self.effectors.append(effector)
+        self.action_dims.append(self.action_dims[-1] + effector.action_dim)
+
+    def build(self, sim):
+        self.n_effectors = len(self.effectors)
+        self.sim = sim
+        for effector in self.effectors:
+            effector.build(sim)
+
+    def reset_grad(self):
+        for e in self.effectors:
+            e.reset_grad()
+
+    def act(self, f, f_global):
+        return
+
+    def act_grad(self, f, f_global, gin=0):
+        return
+
+    @property
+    def action_dim(self):
+        return self.action_dims[-1]
+
+    @property
+    def state_dim(self):
+        return sum(e.state_dim for e in self.effectors)
+
+    def set_action(self, s, s_global, n_substeps, action):
+        action = np.asarray(action).reshape(-1)
+        assert len(action) == self.action_dims[-1], 'Action length does not match agent specifications.'
+        for i in range(self.n_effectors):
+            self.effectors[i].set_action(s, s_global, n_substeps, action[self.action_dims[i]:self.action_dims[i + 1]])
+
+    def set_action_grad(self, s, s_global, n_substeps, action):
+        action = np.asarray(action).reshape(-1)
+        assert len(action) == self.action_dims[-1]
+        for i in range(self.n_effectors - 1, -1, -1):
+            self.effectors[i].set_action_grad(s, s_global, n_substeps, action[self.action_dims[i]:self.action_dims[i + 1]])
+
+    def apply_action_p(self, action_p):
+        action_p = np.asarray(action_p).reshape(-1)
+        for i in range(self.n_effectors):
+            self.effectors[i].apply_action_p(action_p[self.action_dims[i]:self.action_dims[i + 1]])
+
+    def apply_action_p_grad(self, action_p):
+        action_p = np.asarray(action_p).reshape(-1)
+        for i in range(self.n_effectors - 1, -1, -1):
+            self.effectors[i].apply_action_p_grad(action_p[self.action_dims[i]:self.action_dims[i + 1]])
+
+    def get_grad(self, n):
+        grads = [g for g in (e.get_action_grad(0, n) for e in self.effectors) if g is not None]
+        return np.concatenate(grads, axis=1)
+
+    def move(self, f):
+        for e in self.effectors:
+            e.move(f)
+
+    def move_grad(self, f):
+        for e in reversed(self.effectors):
+            e.move_grad(f)
+
+    def get_state(self, f):
+        return [e.get_state(f) for e in self.effectors]
+
+    def set_state(self, f, state):
+        for e, s in zip(self.effectors, state):
+            e.set_state(f, s)
+
+    def copy_frame(self, source, target):
+        for e in self.effectors:
+            e.copy_frame(source, target)
+
+    def copy_grad(self, source, target):
+        for e in self.effectors:
+            e.copy_grad(source, target)
+
+    def reset_grad_till_frame(self, f):
+        for e in self.effectors:
+            e.reset_grad_till_frame(f)
+
+    def get_ckpt(self, ckpt_name=None):
+        return [e.get_ckpt() for e in self.effectors]
+
+    def set_ckpt(self, ckpt=None, ckpt_name=None):
+        for e, c in zip(self.effectors, ckpt):
+            e.set_ckpt(c)
+
+
+class AgentInjector(Agent):
+    """Agent with one Injector (agents/agent_injector.py)."""
+
+    def build(self, sim):
+        super().build(sim)
+        assert self.n_effectors == 1
+        assert isinstance(self.effectors[0], Injector)
+        self.injector = self.effectors[0]
+        self.injector.set_act_range(sim.get_used(0))
+        self.injector.finalize()
+
+    def act(self, f, f_global):
+        self.injector.act(f, f_global)
+
+    def act_grad(self, f, f_global, gin=0):
+        self.injector.act_grad(f, f_global, gin)
+
+
+class AgentRigid(Agent):
+    def build(self, sim):
+        raise NotImplementedError('AgentRigid needs the SDF collide kernels, not built yet (SURVEY.md §8 a9.3)')

@@ -1,0 +1,329 @@
+// fmpm_common.cuh — shared device helpers of libfluidmpm.so (sm_100a).
+// Data layout and material/boundary semantics follow the reference simulator
+// fluidlab/fluidengine/simulators/mpm_simulator.py (MPM) — see include/fluidmpm.h and DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/fluidmpm.h"
+
+#define FMPM_EPS 1e-12f  // configs/macros.py:213
+
+struct FmpmHandle {
+  FmpmConfig cfg;
+  FmpmBuffers buf;
+  bool bound;
+  char err[512];
+  int sm_count;
+};
+
+// kernel-side view (passed by value)
+struct KParams {
+  int N, n, G, T;
+  float dt, dx, inv_dx, k_stress;
+  float gx, gy, gz;
+  int boundary_type;
+  float lo[3], hi[3];
+  float cyl_cx, cyl_cz, cyl_r, restitution;
+  int lock_mask;
+  float4* pa; float4* pf; float* pf8;
+  float4* ga; float4* gf; float* gf8;
+  float4* grid_pm; float4* grid_v; float4* ggrid_v; float4* ggrid_pm;
+  const float4* mats;  // (mu, lam, mass, cls-as-int-bits)
+};
+
+static inline KParams make_kparams(const FmpmHandle* h) {
+  KParams P;
+  const FmpmConfig& c = h->cfg;
+  P.N = c.n_particles; P.n = c.n_grid; P.G = c.n_grid * c.n_grid * c.n_grid; P.T = c.max_substeps_local;
+  P.dt = c.dt; P.dx = c.dx; P.inv_dx = c.inv_dx; P.k_stress = c.k_stress;
+  P.gx = c.gravity[0]; P.gy = c.gravity[1]; P.gz = c.gravity[2];
+  P.boundary_type = c.boundary_type;
+  for (int i = 0; i < 3; i++) { P.lo[i] = c.b_lower[i]; P.hi[i] = c.b_upper[i]; }
+  P.cyl_cx = c.cyl_center[0]; P.cyl_cz = c.cyl_center[1]; P.cyl_r = c.cyl_radius; P.restitution = c.restitution;
+  P.lock_mask = c.lock_mask;
+  P.pa = (float4*)h->buf.pa; P.pf = (float4*)h->buf.pf; P.pf8 = (float*)h->buf.pf8;
+  P.ga = (float4*)h->buf.ga; P.gf = (float4*)h->buf.gf; P.gf8 = (float*)h->buf.gf8;
+  P.grid_pm = (float4*)h->buf.grid_pm; P.grid_v = (float4*)h->buf.grid_v;
+  P.ggrid_v = (float4*)h->buf.ggrid_v; P.ggrid_pm = (float4*)h->buf.ggrid_pm;
+  P.mats = (const float4*)h->buf.materials;
+  return P;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small 3x3 algebra (row-major float[9] in registers)
+// ---------------------------------------------------------------------------------------------
+struct Mat3 { float m[9]; };
+
+__device__ __forceinline__ Mat3 m3_mul(const Mat3& A, const Mat3& B) {
+  Mat3 C;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C.m[i * 3 + j] = A.m[i * 3] * B.m[j] + A.m[i * 3 + 1] * B.m[3 + j] + A.m[i * 3 + 2] * B.m[6 + j];
+  return C;
+}
+__device__ __forceinline__ Mat3 m3_mul_nt(const Mat3& A, const Mat3& B) {  // A * B^T
+  Mat3 C;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C.m[i * 3 + j] = A.m[i * 3] * B.m[j * 3] + A.m[i * 3 + 1] * B.m[j * 3 + 1] + A.m[i * 3 + 2] * B.m[j * 3 + 2];
+  return C;
+}
+__device__ __forceinline__ Mat3 m3_mul_tn(const Mat3& A, const Mat3& B) {  // A^T * B
+  Mat3 C;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C.m[i * 3 + j] = A.m[i] * B.m[j] + A.m[3 + i] * B.m[3 + j] + A.m[6 + i] * B.m[6 + j];
+  return C;
+}
+__device__ __forceinline__ Mat3 m3_tr(const Mat3& A) {
+  Mat3 C;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C.m[i * 3 + j] = A.m[j * 3 + i];
+  return C;
+}
+__device__ __forceinline__ Mat3 m3_add(const Mat3& A, const Mat3& B) { Mat3 C;
+#pragma unroll
+  for (int i = 0; i < 9; i++) C.m[i] = A.m[i] + B.m[i]; return C; }
+__device__ __forceinline__ Mat3 m3_sub(const Mat3& A, const Mat3& B) { Mat3 C;
+#pragma unroll
+  for (int i = 0; i < 9; i++) C.m[i] = A.m[i] - B.m[i]; return C; }
+__device__ __forceinline__ Mat3 m3_scale(const Mat3& A, float s) { Mat3 C;
+#pragma unroll
+  for (int i = 0; i < 9; i++) C.m[i] = A.m[i] * s; return C; }
+__device__ __forceinline__ Mat3 m3_zero() { Mat3 C;
+#pragma unroll
+  for (int i = 0; i < 9; i++) C.m[i] = 0.f; return C; }
+__device__ __forceinline__ float m3_det(const Mat3& A) {
+  return A.m[0] * (A.m[4] * A.m[8] - A.m[5] * A.m[7]) - A.m[1] * (A.m[3] * A.m[8] - A.m[5] * A.m[6]) +
+         A.m[2] * (A.m[3] * A.m[7] - A.m[4] * A.m[6]);
+}
+__device__ __forceinline__ float m3_trace(const Mat3& A) { return A.m[0] + A.m[4] + A.m[8]; }
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 SVD, one lane per matrix (the warp batches 32 of them): one-sided Jacobi with a fixed
+// number of sweeps (branch-light, no early exit -> no divergence), then sort + sign fix to the
+// ti.svd convention used at MPM:264 (det U = det V = +1, sigma descending, sign on the smallest).
+// ---------------------------------------------------------------------------------------------
+#define FMPM_SVD_SWEEPS 5
+__device__ __forceinline__ void svd_rot(float* B, float* V, const int p, const int q) {
+  float alpha = B[p] * B[p] + B[3 + p] * B[3 + p] + B[6 + p] * B[6 + p];
+  float beta = B[q] * B[q] + B[3 + q] * B[3 + q] + B[6 + q] * B[6 + q];
+  float gamma = B[p] * B[q] + B[3 + p] * B[3 + q] + B[6 + p] * B[6 + q];
+  float c = 1.f, s = 0.f;
+  if (fabsf(gamma) > 1e-20f && fabsf(gamma) > 2e-8f * sqrtf(alpha * beta)) {
+    float zeta = (beta - alpha) / (2.f * gamma);
+    float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+    c = rsqrtf(1.f + t * t);
+    s = c * t;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float bp = B[k * 3 + p], bq = B[k * 3 + q];
+    B[k * 3 + p] = c * bp - s * bq; B[k * 3 + q] = s * bp + c * bq;
+    float vp = V[k * 3 + p], vq = V[k * 3 + q];
+    V[k * 3 + p] = c * vp - s * vq; V[k * 3 + q] = s * vp + c * vq;
+  }
+}
+__device__ __forceinline__ void svd_swap_cols(float* B, float* V, float* n, const int i, const int j) {
+  // conditional swap so that n[i] >= n[j]; a swap negates column j to keep det V = +1 and B V^T unchanged
+  if (n[i] < n[j]) {
+    float t = n[i]; n[i] = n[j]; n[j] = t;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float b = B[k * 3 + i]; B[k * 3 + i] = B[k * 3 + j]; B[k * 3 + j] = -b;
+      float v = V[k * 3 + i]; V[k * 3 + i] = V[k * 3 + j]; V[k * 3 + j] = -v;
+    }
+  }
+}
+__device__ __forceinline__ void svd3(const Mat3& A, Mat3& U, float* sig, Mat3& Vm) {
+  float B[9], V[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) { B[i] = A.m[i]; V[i] = (i % 4 == 0) ? 1.f : 0.f; }
+#pragma unroll 1
+  for (int sweep = 0; sweep < FMPM_SVD_SWEEPS; sweep++) {
+    svd_rot(B, V, 0, 1); svd_rot(B, V, 0, 2); svd_rot(B, V, 1, 2);
+  }
+  float n[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) n[j] = sqrtf(B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j]);
+  svd_swap_cols(B, V, n, 0, 1); svd_swap_cols(B, V, n, 0, 2); svd_swap_cols(B, V, n, 1, 2);
+  // U columns = B columns / norm ; degenerate columns completed by cross products
+  float u[9];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float inv = n[j] > 1e-30f ? 1.f / n[j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) u[k * 3 + j] = B[k * 3 + j] * inv;
+  }
+  if (!(n[0] > 1e-30f)) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) u[i] = (i % 4 == 0) ? 1.f : 0.f;
+  } else {
+    if (!(n[1] > 1e-30f)) {
+      // unit vector orthogonal to u0: drop the smallest component direction
+      float ax = fabsf(u[0]), ay = fabsf(u[3]), az = fabsf(u[6]);
+      float e0 = (ax <= ay && ax <= az) ? 1.f : 0.f, e1 = (e0 == 0.f && ay <= az) ? 1.f : 0.f, e2 = (e0 == 0.f && e1 == 0.f) ? 1.f : 0.f;
+      float d = e0 * u[0] + e1 * u[3] + e2 * u[6];
+      float w0 = e0 - d * u[0], w1 = e1 - d * u[3], w2 = e2 - d * u[6];
+      float inv = rsqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+      u[1] = w0 * inv; u[4] = w1 * inv; u[7] = w2 * inv;
+    }
+    if (!(n[2] > 1e-30f)) {
+      u[2] = u[3] * u[7] - u[6] * u[4];
+      u[5] = u[6] * u[1] - u[0] * u[7];
+      u[8] = u[0] * u[4] - u[3] * u[1];
+    }
+  }
+  float detU = u[0] * (u[4] * u[8] - u[5] * u[7]) - u[1] * (u[3] * u[8] - u[5] * u[6]) + u[2] * (u[3] * u[7] - u[4] * u[6]);
+  if (detU < 0.f) { u[2] = -u[2]; u[5] = -u[5]; u[8] = -u[8]; n[2] = -n[2]; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) { U.m[i] = u[i]; Vm.m[i] = V[i]; }
+  sig[0] = n[0]; sig[1] = n[1]; sig[2] = n[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout accessors
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t pa_idx(const KParams& P, int f, int k, int s) { return ((size_t)f * 4 + k) * (size_t)P.N + s; }
+__device__ __forceinline__ size_t pf_idx(const KParams& P, int f, int k, int s) { return ((size_t)f * 2 + k) * (size_t)P.N + s; }
+__device__ __forceinline__ size_t pf8_idx(const KParams& P, int f, int s) { return (size_t)f * (size_t)P.N + s; }
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+struct PState {  // unpacked particle state of one frame
+  float x[3], v[3]; Mat3 C, F; int meta;
+};
+__device__ __forceinline__ void load_A(const float4* __restrict__ base, const KParams& P, int f, int s, PState& st) {
+  float4 a0 = base[pa_idx(P, f, 0, s)], a1 = base[pa_idx(P, f, 1, s)], a2 = base[pa_idx(P, f, 2, s)], a3 = base[pa_idx(P, f, 3, s)];
+  st.x[0] = a0.x; st.x[1] = a0.y; st.x[2] = a0.z; st.meta = __float_as_int(a0.w);
+  st.v[0] = a1.x; st.v[1] = a1.y; st.v[2] = a1.z;
+  st.C.m[0] = a1.w; st.C.m[1] = a2.x; st.C.m[2] = a2.y; st.C.m[3] = a2.z; st.C.m[4] = a2.w;
+  st.C.m[5] = a3.x; st.C.m[6] = a3.y; st.C.m[7] = a3.z; st.C.m[8] = a3.w;
+}
+__device__ __forceinline__ void load_F(const float4* __restrict__ pf, const float* __restrict__ pf8, const KParams& P, int f, int s, Mat3& F) {
+  float4 f0 = pf[pf_idx(P, f, 0, s)], f1 = pf[pf_idx(P, f, 1, s)];
+  F.m[0] = f0.x; F.m[1] = f0.y; F.m[2] = f0.z; F.m[3] = f0.w; F.m[4] = f1.x; F.m[5] = f1.y; F.m[6] = f1.z; F.m[7] = f1.w;
+  F.m[8] = pf8[pf8_idx(P, f, s)];
+}
+__device__ __forceinline__ void store_F(float4* __restrict__ pf, float* __restrict__ pf8, const KParams& P, int f, int s, const Mat3& F) {
+  pf[pf_idx(P, f, 0, s)] = make_float4(F.m[0], F.m[1], F.m[2], F.m[3]);
+  pf[pf_idx(P, f, 1, s)] = make_float4(F.m[4], F.m[5], F.m[6], F.m[7]);
+  pf8[pf8_idx(P, f, s)] = F.m[8];
+}
+__device__ __forceinline__ void store_A(float4* __restrict__ base, const KParams& P, int f, int s, const float* x, int meta, const float* v, const Mat3& C) {
+  base[pa_idx(P, f, 0, s)] = make_float4(x[0], x[1], x[2], __int_as_float(meta));
+  base[pa_idx(P, f, 1, s)] = make_float4(v[0], v[1], v[2], C.m[0]);
+  base[pa_idx(P, f, 2, s)] = make_float4(C.m[1], C.m[2], C.m[3], C.m[4]);
+  base[pa_idx(P, f, 3, s)] = make_float4(C.m[5], C.m[6], C.m[7], C.m[8]);
+}
+
+// MPM:335-337: base / fx / quadratic B-spline weights.  `ok` is false when the 3x3x3 stencil would leave
+// the grid (the reference has no bounds check there; such particles are frozen here instead of corrupting memory).
+__device__ __forceinline__ bool base_fx(const KParams& P, const float* x, int* b, float* fx) {
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    float g = x[d] * P.inv_dx;
+    float t = g - 0.5f;
+    ok = ok && (t > -1.0f) && (t < (float)(P.n - 2));
+    int bi = (int)t;  // cast(int): truncation toward zero
+    b[d] = bi; fx[d] = g - (float)bi;
+  }
+  ok = ok && b[0] >= 0 && b[1] >= 0 && b[2] >= 0 && b[0] <= P.n - 3 && b[1] <= P.n - 3 && b[2] <= P.n - 3;
+  return ok;
+}
+__device__ __forceinline__ void bspline(const float* fx, float w[3][3]) {
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    float a = 1.5f - fx[d], b = fx[d] - 1.0f, c = fx[d] - 0.5f;
+    w[0][d] = 0.5f * a * a; w[1][d] = 0.75f - b * b; w[2][d] = 0.5f * c * c;
+  }
+}
+__device__ __forceinline__ void bspline_d(const float* fx, float dw[3][3]) {
+#pragma unroll
+  for (int d = 0; d < 3; d++) { dw[0][d] = -(1.5f - fx[d]); dw[1][d] = -2.f * (fx[d] - 1.0f); dw[2][d] = fx[d] - 0.5f; }
+}
+
+// boundary.impose_x_v velocity part (boundaries.py:39-63 cylinder, :106-120 cube); fac = d v_out / d v_in (diagonal)
+__device__ __forceinline__ void boundary_v(const KParams& P, const float* pos, float* v, float* fac) {
+  fac[0] = fac[1] = fac[2] = 1.f;
+  if (P.boundary_type == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (pos[i] >= P.hi[i] && v[i] >= 0.f) fac[i] = -P.restitution;
+      else if (pos[i] <= P.lo[i] && v[i] <= 0.f) fac[i] = -P.restitution;
+    }
+  } else {
+    if (pos[1] > P.hi[1] && v[1] > 0.f) fac[1] = -P.restitution;
+    else if (pos[1] < P.lo[1] && v[1] < 0.f) fac[1] = -P.restitution;
+    float rx = pos[0] - P.cyl_cx, rz = pos[2] - P.cyl_cz;
+    float rn = sqrtf(rx * rx + rz * rz + FMPM_EPS);
+    if (rn > P.cyl_r) { fac[0] = 0.f; fac[2] = 0.f; }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (P.lock_mask & (1 << i)) fac[i] = 0.f;
+    v[i] = (fac[i] == 0.f) ? 0.f : v[i] * fac[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// constitutive update of one particle (MPM:254-264 F_tmp + svd, MPM:339-344 stress/affine,
+// MPM:356-378 F update).  Fills what the scatter needs.  `want_svd` outputs are only valid when
+// need_svd (mu != 0 or a plastic class).
+// ---------------------------------------------------------------------------------------------
+struct Constit {
+  Mat3 Ft, U, V, A, Fn; float sig[3]; float J; bool need_svd;
+};
+__device__ __forceinline__ void constitutive(const KParams& P, const PState& st, float mu, float lam, float mass, int cls, Constit& K) {
+  // F_tmp = (I + dt*C) @ F
+  Mat3 IdC;
+#pragma unroll
+  for (int i = 0; i < 9; i++) IdC.m[i] = P.dt * st.C.m[i] + ((i % 4 == 0) ? 1.f : 0.f);
+  K.Ft = m3_mul(IdC, st.F);
+  const bool plastic = (cls == FMPM_MAT_PLASTO_ELASTIC) || (cls == FMPM_MAT_PLASTO_ELASTIC_DEMO);
+  K.need_svd = (mu != 0.f) || plastic;
+  Mat3 stress;
+  if (K.need_svd) {
+    svd3(K.Ft, K.U, K.sig, K.V);
+    K.J = K.sig[0] * K.sig[1] * K.sig[2];
+    Mat3 R = m3_mul_nt(K.U, K.V);
+    stress = m3_scale(m3_mul_nt(m3_sub(K.Ft, R), K.Ft), 2.f * mu);
+  } else {
+    K.J = m3_det(K.Ft);  // == product of singular values with the ti.svd sign convention
+    stress = m3_zero();
+  }
+  float iso = lam * K.J * (K.J - 1.f);
+  stress.m[0] += iso; stress.m[4] += iso; stress.m[8] += iso;
+#pragma unroll
+  for (int i = 0; i < 9; i++) K.A.m[i] = P.k_stress * stress.m[i] + mass * st.C.m[i];
+  if (cls == FMPM_MAT_LIQUID) {
+    float s = (K.J > 0.f) ? cbrtf(K.J) : __int_as_float(0x7fc00000);  // pow(J, 1/3): NaN for J < 0 like the reference
+    if (K.J == 0.f) s = 0.f;
+    K.Fn = m3_zero(); K.Fn.m[0] = s; K.Fn.m[4] = s; K.Fn.m[8] = s;
+  } else if (plastic) {
+    Mat3 US = K.U;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      float sn = fminf(fmaxf(K.sig[d], 0.998f), 1.003f);
+      US.m[d] *= sn; US.m[3 + d] *= sn; US.m[6 + d] *= sn;
+    }
+    K.Fn = m3_mul_nt(US, K.V);
+  } else {
+    K.Fn = K.Ft;  // elastic / rigid
+  }
+}
+
+#define FMPM_CHECK_LAUNCH(h, name)                                                        \
+  do {                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                  \
+    if (e_ != cudaSuccess) {                                                              \
+      snprintf((h)->err, sizeof((h)->err), "%s: %s", name, cudaGetErrorString(e_));       \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)

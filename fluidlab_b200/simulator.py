@@ -1,0 +1,545 @@
+"""B200-native MLS-MPM simulator behind the reference's `MPMSimulator` interface.
+
+Host-side mirror of fluidlab/fluidengine/simulators/mpm_simulator.py (MPM): same constructor, `setup_boundary`,
+`build`, `step`, `step_grad`, `get_state`, `set_state`, `get_x`, `get_v`, `get_used`, `get_state_RL`, `set_x`,
+`set_used`, `reset_grad`, `enable_grad`/`disable_grad`, `cur_*` properties, checkpointed frame ring
+(`memory_to_cache` / `memory_from_cache`, MPM:777-912).  All physics runs in libfluidmpm.so (hand-written
+sm_100a CUDA, csrc/) through the C ABI of include/fluidmpm.h; torch tensors only own the device memory.
+
+What differs from the reference by design:
+  * particles are stored cell-sorted in float4 planes; the API translates to original particle order;
+  * F_tmp/U/S/V and the per-frame grids are never stored — the backward recomputes them;
+  * adjoints live in two ping-pong frames instead of a (T+1)-frame ring: `substep_grad(f)` reads the adjoint of
+    frame f+1 and overwrites the adjoint of frame f (losses seed the *current* frame through `add_x_grad_*`);
+  * checkpoints stay in HBM ('gpu', default), host RAM ('cpu') or disk ('disk') as torch tensors.
+"""
+import ctypes as C
+import os
+import uuid
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib
+from .boundaries import create_boundary
+from .macros import MU, LAMDA, MAT_CLASS, MAT_RIGID, DTYPE_NP
+
+
+class _Order:
+    """slot <-> particle-id maps of one cell-sort epoch (ids[slot] = pid, inv[pid] = slot); None = identity."""
+    __slots__ = ("ids", "inv")
+
+    def __init__(self, ids=None, inv=None):
+        self.ids, self.inv = ids, inv
+
+    def ids_ptr(self):
+        return None if self.ids is None else self.ids.data_ptr()
+
+    def inv_ptr(self):
+        return None if self.inv is None else self.inv.data_ptr()
+
+
+_IDENTITY = _Order()
+
+
+class _NPField:
+    """Tiny stand-in for the Taichi fields some reference callers read with .to_numpy() (optimizer/recorder.py:59)."""
+
+    def __init__(self, getter):
+        self._getter = getter
+
+    def to_numpy(self):
+        return self._getter()
+
+
+class MPMSimulator:
+    def __init__(self, dim, quality, gravity, horizon, max_substeps_local, max_substeps_global, ckpt_dest,
+                 device=None, sort_every=1):
+        assert dim == 3, 'only dim=3 is implemented (every shipped env uses 3, taichi_env.py:23)'
+        self.dim = dim
+        self.ckpt_dest = ckpt_dest
+        self.sim_id = str(uuid.uuid4())
+        self.gravity = tuple(float(g) for g in gravity)
+
+        # MPM:21-31
+        self.n_grid = int(64 * quality)
+        self.dx = 1 / self.n_grid
+        self.inv_dx = float(self.n_grid)
+        self.dt = 2e-4
+        self.p_vol = (self.dx * 0.5) ** 2
+        self.res = (self.n_grid,) * self.dim
+        self.max_substeps_local = max_substeps_local
+        self.max_substeps_global = max_substeps_global
+        self.horizon = horizon
+        self.n_substeps = int(2e-3 / self.dt)
+        self.max_steps_local = int(self.max_substeps_local / self.n_substeps)
+
+        assert self.n_substeps * self.horizon < self.max_substeps_global
+        assert self.max_substeps_local % self.n_substeps == 0
+
+        self.boundary = None
+        self.has_particles = False
+        self.sort_every = int(sort_every)  # cell-sort period in steps (0 = never)
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError('fluidlab_b200.MPMSimulator needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        self._lib = None
+        self._h = None
+
+    # ------------------------------------------------------------------------------------------ build
+    def setup_boundary(self, **kwargs):
+        self.boundary = create_boundary(**kwargs)
+
+    def build(self, agent, smoke_field, statics, particles):
+        if self.boundary is None:
+            self.boundary = create_boundary()
+        self.n_statics = len(statics) if statics is not None else 0
+        self.statics = statics
+        if self.n_statics > 0 and any(getattr(s, 'has_dynamics', False) for s in statics):
+            raise NotImplementedError('SDF statics with has_dynamics=True are not built yet (SURVEY.md §8 a9.2)')
+        if smoke_field is not None:
+            raise NotImplementedError('SmokeField is out of scope of this hot path (SURVEY.md §8f)')
+        self.smoke_field = None
+        self.agent = agent
+
+        if particles is not None:
+            self.has_particles = True
+            self.n_particles = len(particles['x'])
+            self._setup_device(particles)
+        else:
+            self.has_particles = False
+            self.n_particles = 0
+        self.actions_buffer = []
+        self.ckpt_ram = dict()
+        self.ckpt_dir = os.path.join('/tmp', 'fluidlab', self.sim_id)
+        self.cur_substep_global = 0
+        self.disable_grad()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc, what):
+        _lib.check(self._lib, self._h, rc, what)
+
+    def _setup_device(self, particles):
+        lib = self._lib = _lib.load()
+        dev, N, T, G = self.device, self.n_particles, self.max_substeps_local, self.n_grid ** 3
+        f32, i32 = torch.float32, torch.int32
+
+        # ---- particle info (MPM:136-175): one material-table row per distinct (material, rho)
+        mat = np.asarray(particles['mat']).astype(np.int32)
+        rho = np.asarray(particles['rho']).astype(DTYPE_NP)
+        if any(MAT_CLASS[int(m)] == MAT_RIGID for m in np.unique(mat)):
+            raise NotImplementedError('MAT_RIGID shape matching (MPM:449-505) is not built yet (SURVEY.md §8f rank 2)')
+        rows, mrow = {}, np.zeros(N, dtype=np.int32)
+        keys = np.stack([mat.astype(np.float64), rho.astype(np.float64)], 1)
+        uniq, inverse = np.unique(keys, axis=0, return_inverse=True)
+        assert len(uniq) <= 256, 'more than 256 distinct (material, rho) pairs'
+        table = np.zeros(len(uniq), dtype=[('mu', np.float32), ('lam', np.float32), ('mass', np.float32), ('cls', np.int32)])
+        for r, (m, rh) in enumerate(uniq):
+            m = int(m)
+            table[r] = (DTYPE_NP(MU[m]), DTYPE_NP(LAMDA[m]), DTYPE_NP(self.p_vol) * DTYPE_NP(rh), MAT_CLASS[m])  # mass: MPM:174 in f32
+            rows[r] = m
+        mrow[:] = inverse.reshape(-1)
+        self._row_material = rows
+        self._mat_np = mat
+        self._body_id_np = np.asarray(particles.get('body_id', np.zeros(N))).astype(np.int32)
+        self.n_bodies = int(particles['bodies']['n']) if 'bodies' in particles else 1
+        self._materials = torch.from_numpy(table.view(np.float32).reshape(-1, 4).copy()).to(dev)
+        self._mrow = torch.from_numpy(mrow).to(dev)
+
+        # ---- device buffers (torch owns the memory, the library only sees pointers)
+        self._pa = torch.zeros((T + 1, 4, N, 4), dtype=f32, device=dev)
+        self._pf = torch.zeros((T + 1, 2, N, 4), dtype=f32, device=dev)
+        self._pf8 = torch.zeros((T + 1, N), dtype=f32, device=dev)
+        self._grid_pm = torch.zeros((G, 4), dtype=f32, device=dev)
+        self._grid_v = torch.zeros((G, 4), dtype=f32, device=dev)
+        self._scratch_a = torch.empty((4, N, 4), dtype=f32, device=dev)
+        self._scratch_f = torch.empty((2, N, 4), dtype=f32, device=dev)
+        self._scratch_f8 = torch.empty((N,), dtype=f32, device=dev)
+        self._sort_bufs = [torch.empty((N,), dtype=i32, device=dev) for _ in range(4)]
+        self._ga = self._gf = self._gf8 = self._ggrid_v = self._ggrid_pm = None
+        # API-layout staging
+        self._sx = torch.empty((N, 3), dtype=f32, device=dev); self._sv = torch.empty((N, 3), dtype=f32, device=dev)
+        self._sC = torch.empty((N, 3, 3), dtype=f32, device=dev); self._sF = torch.empty((N, 3, 3), dtype=f32, device=dev)
+        self._sused = torch.empty((N,), dtype=i32, device=dev)
+
+        cfg = _lib.FmpmConfig()
+        cfg.n_grid, cfg.n_particles, cfg.max_substeps_local, cfg.n_substeps = self.n_grid, N, T, self.n_substeps
+        cfg.dt, cfg.dx, cfg.inv_dx, cfg.p_vol = self.dt, self.dx, self.inv_dx, self.p_vol
+        cfg.k_stress = -self.dt * self.p_vol * 4 * self.inv_dx * self.inv_dx  # MPM:343, double then rounded to f32
+        cfg.gravity = (C.c_float * 3)(*self.gravity)
+        b = self.boundary
+        cfg.boundary_type = b.type_id
+        cfg.b_lower = (C.c_float * 3)(*[float(v) for v in b.lower]); cfg.b_upper = (C.c_float * 3)(*[float(v) for v in b.upper])
+        cfg.cyl_center = (C.c_float * 2)(*[float(v) for v in b.xz_center]); cfg.cyl_radius = float(b.xz_radius)
+        cfg.restitution = b.restitution; cfg.lock_mask = b.lock_mask
+        cfg.n_materials = len(uniq)
+        cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        rc = lib.fmpm_create(C.byref(cfg), C.byref(h))
+        self._h = h
+        self._ck(rc, 'fmpm_create')
+        self._sort_tmp = torch.empty((int(lib.fmpm_sort_workspace_bytes(h)),), dtype=torch.uint8, device=dev)
+        self._bind()
+
+        # ---- initial frame (init_particles_kernel MPM:150-175): v = 0, F = I, C = 0
+        x0 = np.asarray(particles['x']).astype(DTYPE_NP)
+        used0 = np.asarray(particles['used']).astype(np.int32)
+        self._frame_ord = [_IDENTITY] * (T + 1)
+        self._gcur, self._grad_ord = 0, _IDENTITY
+        self.setframe(0, x0, np.zeros((N, 3), DTYPE_NP), np.zeros((N, 3, 3), DTYPE_NP),
+                      np.tile(np.eye(3, dtype=DTYPE_NP), (N, 1, 1)), used0)
+        self.particles_i = SimpleNamespace(mat=_NPField(lambda: self._mat_np.copy()))
+        self.particles_ng = SimpleNamespace(used=_NPField(lambda: np.stack([self.get_used(f) for f in range(1)])))
+
+    def _bind(self):
+        b = _lib.FmpmBuffers()
+        p = lambda t: None if t is None else t.data_ptr()
+        b.pa, b.pf, b.pf8 = p(self._pa), p(self._pf), p(self._pf8)
+        b.ga, b.gf, b.gf8 = p(self._ga), p(self._gf), p(self._gf8)
+        b.grid_pm, b.grid_v, b.ggrid_v, b.ggrid_pm = p(self._grid_pm), p(self._grid_v), p(self._ggrid_v), p(self._ggrid_pm)
+        b.materials = p(self._materials)
+        b.scratch_a, b.scratch_f, b.scratch_f8 = p(self._scratch_a), p(self._scratch_f), p(self._scratch_f8)
+        b.sort_keys_in, b.sort_keys_out, b.sort_vals_in, b.sort_vals_out = [p(t) for t in self._sort_bufs]
+        b.sort_tmp, b.sort_tmp_bytes = p(self._sort_tmp), self._sort_tmp.numel()
+        self._ck(self._lib.fmpm_bind(self._h, C.byref(b)), 'fmpm_bind')
+
+    def _ensure_grad_buffers(self):
+        if self._ga is None:
+            N, G, dev, f32 = self.n_particles, self.n_grid ** 3, self.device, torch.float32
+            self._ga = torch.zeros((2, 4, N, 4), dtype=f32, device=dev)
+            self._gf = torch.zeros((2, 2, N, 4), dtype=f32, device=dev)
+            self._gf8 = torch.zeros((2, N), dtype=f32, device=dev)
+            self._ggrid_v = torch.zeros((G, 4), dtype=f32, device=dev)
+            self._ggrid_pm = torch.zeros((G, 4), dtype=f32, device=dev)
+            self._bind()
+
+    def __del__(self):
+        try:
+            if self._h is not None and self._lib is not None:
+                self._lib.fmpm_destroy(self._h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------ grads
+    def reset_grad(self):  # MPM:203-205
+        if not self.has_particles:
+            return
+        self._ensure_grad_buffers()
+        self._ga.zero_(); self._gf.zero_(); self._gf8.zero_()
+        self._gcur = 0
+        self._grad_ord = self._frame_ord[self.cur_substep_local]
+
+    def enable_grad(self):  # MPM:207-212
+        self.grad_enabled = True
+        self.cur_substep_global = 0
+
+    def disable_grad(self):  # MPM:214-216
+        self.grad_enabled = False
+        self.cur_substep_global = 0
+
+    def _ensure_grad_order(self, order):
+        """Re-express the current adjoint buffer in the slot order `order` (no-op when it already is)."""
+        if self._grad_ord is order:
+            return
+        src, dst = self._gcur, 1 - self._gcur
+        self._ck(self._lib.fmpm_permute_grad(self._h, src, dst, self._grad_ord.ids_ptr(), order.inv_ptr(), self._stream()), 'fmpm_permute_grad')
+        self._gcur, self._grad_ord = dst, order
+
+    def add_x_grad_chamfer(self, tgt_dev, row_mask, weight, f=None):
+        """Seed of losses/shapematching_loss.py:80-84 (.grad): gx[f] += 2 w (x[f] - tgt) on the current adjoint frame."""
+        f = self.cur_substep_local if f is None else f
+        self._ensure_grad_order(self._frame_ord[f])
+        self._ck(self._lib.fmpm_loss_chamfer_grad(self._h, f, self._gcur, self._grad_ord.ids_ptr(), tgt_dev.data_ptr(), int(row_mask),
+                                                  float(weight), self._stream()), 'fmpm_loss_chamfer_grad')
+
+    def chamfer_loss(self, tgt_dev, row_mask, weight, out_dev, f=None):
+        """out_dev[0] += w * sum |x[f,p] - tgt[p]|^2 over used particles whose material row is in row_mask."""
+        f = self.cur_substep_local if f is None else f
+        self._ck(self._lib.fmpm_loss_chamfer(self._h, f, self._frame_ord[f].ids_ptr(), tgt_dev.data_ptr(), int(row_mask), float(weight),
+                                             out_dev.data_ptr(), self._stream()), 'fmpm_loss_chamfer')
+
+    def material_row_mask(self, material):
+        m = 0
+        for r, mat in self._row_material.items():
+            if mat == material:
+                assert r < 32
+                m |= 1 << r
+        return m
+
+    def get_grad(self, which=('x', 'v', 'C', 'F')):
+        """Adjoint of the current frame in original particle order (numpy), for tests / diagnostics."""
+        N, dev, f32 = self.n_particles, self.device, torch.float32
+        gx = torch.empty((N, 3), dtype=f32, device=dev); gv = torch.empty((N, 3), dtype=f32, device=dev)
+        gC = torch.empty((N, 3, 3), dtype=f32, device=dev); gF = torch.empty((N, 3, 3), dtype=f32, device=dev)
+        self._ck(self._lib.fmpm_read_grad(self._h, self._gcur, gx.data_ptr(), gv.data_ptr(), gC.data_ptr(), gF.data_ptr(),
+                                          self._grad_ord.ids_ptr(), self._stream()), 'fmpm_read_grad')
+        out = dict(x=gx, v=gv, C=gC, F=gF)
+        return {k: out[k].cpu().numpy() for k in which}
+
+    def set_grad(self, gx, gv, gC, gF):
+        """Overwrite the adjoint of the current frame (original particle order)."""
+        self._ensure_grad_buffers()
+        dev, f32 = self.device, torch.float32
+        t = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev) for a in (gx, gv, gC, gF)]
+        self._grad_ord = self._frame_ord[self.cur_substep_local]
+        self._ck(self._lib.fmpm_write_grad(self._h, self._gcur, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
+                                           self._grad_ord.ids_ptr(), self._stream()), 'fmpm_write_grad')
+
+    # ------------------------------------------------------------------------------------------ indices, MPM:225-252
+    def f_global_to_f_local(self, f_global):
+        return f_global % self.max_substeps_local
+
+    def f_local_to_s_local(self, f_local):
+        return f_local // self.n_substeps
+
+    def f_global_to_s_local(self, f_global):
+        return self.f_local_to_s_local(self.f_global_to_f_local(f_global))
+
+    def f_global_to_s_global(self, f_global):
+        return f_global // self.n_substeps
+
+    @property
+    def cur_substep_local(self):
+        return self.f_global_to_f_local(self.cur_substep_global)
+
+    @property
+    def cur_step_local(self):
+        return self.f_global_to_s_local(self.cur_substep_global)
+
+    @property
+    def cur_step_global(self):
+        return self.f_global_to_s_global(self.cur_substep_global)
+
+    # ------------------------------------------------------------------------------------------ substeps
+    def sort_frame(self, f):
+        """Cell-sort frame f in place (new slot order for the frames written from now on)."""
+        N, dev = self.n_particles, self.device
+        old = self._frame_ord[f]
+        new = _Order(torch.empty((N,), dtype=torch.int32, device=dev), torch.empty((N,), dtype=torch.int32, device=dev))
+        self._ck(self._lib.fmpm_sort(self._h, f, old.ids_ptr(), new.ids.data_ptr(), new.inv.data_ptr(), self._stream()), 'fmpm_sort')
+        self._frame_ord[f] = new
+
+    def substep(self, f, is_none_action):  # MPM:515-533
+        if self.has_particles:
+            self._ck(self._lib.fmpm_substep(self._h, f, self._stream()), 'fmpm_substep')
+            self._frame_ord[f + 1] = self._frame_ord[f]
+        if not is_none_action:
+            # agent.act writes frame f+1 of particles that are unused at f, so running it after g2p is equivalent
+            # to the reference order (MPM:521); agent.move was folded into agent.set_action (pose chain kernel).
+            self.agent.act(f, self.cur_substep_global)
+
+    def substep_grad(self, f, is_none_action):  # MPM:535-552
+        if self.has_particles:
+            self._ensure_grad_order(self._frame_ord[f])
+            gin, gout = self._gcur, 1 - self._gcur
+            self._ck(self._lib.fmpm_substep_grad(self._h, f, gin, gout, self._stream()), 'fmpm_substep_grad')
+            if not is_none_action:
+                self.agent.act_grad(f, self.cur_substep_global, gin)
+            self._gcur = gout
+
+    # ------------------------------------------------------------------------------------------ io, MPM:555-719
+    def _to_dev(self, arr, staging, dtype):
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        staging.copy_(torch.from_numpy(a).reshape(staging.shape), non_blocking=False)
+        return staging
+
+    def setframe(self, f, x, v, Cm, F, used):
+        """x,v,C,F,used: numpy arrays or torch tensors in original particle order (MPM:566-575)."""
+        def dev(a, st, dt):
+            if torch.is_tensor(a):
+                st.copy_(a.reshape(st.shape)); return st
+            return self._to_dev(a, st, dt)
+        sx, sv, sC, sF = dev(x, self._sx, np.float32), dev(v, self._sv, np.float32), dev(Cm, self._sC, np.float32), dev(F, self._sF, np.float32)
+        su = dev(used, self._sused, np.int32)
+        self._ck(self._lib.fmpm_write_frame(self._h, f, sx.data_ptr(), sv.data_ptr(), sC.data_ptr(), sF.data_ptr(), su.data_ptr(),
+                                            self._mrow.data_ptr(), None, self._stream()), 'fmpm_write_frame')
+        self._frame_ord[f] = _IDENTITY
+
+    def readframe_torch(self, f, want=('x', 'v', 'C', 'F', 'used')):
+        """Device tensors (staging buffers, valid until the next read) in original particle order."""
+        p = lambda k, t: t.data_ptr() if k in want else None
+        self._ck(self._lib.fmpm_read_frame(self._h, f, p('x', self._sx), p('v', self._sv), p('C', self._sC), p('F', self._sF), p('used', self._sused),
+                                           self._frame_ord[f].ids_ptr(), self._stream()), 'fmpm_read_frame')
+        out = dict(x=self._sx, v=self._sv, C=self._sC, F=self._sF, used=self._sused)
+        return {k: out[k] for k in want}
+
+    def readframe(self, f, want=('x', 'v', 'C', 'F', 'used')):
+        return {k: t.cpu().numpy() for k, t in self.readframe_torch(f, want).items()}
+
+    def get_state(self):  # MPM:611-631
+        f = self.cur_substep_local
+        state = {}
+        if self.has_particles:
+            state.update(self.readframe(f))
+        if self.agent is not None:
+            state['agent'] = self.agent.get_state(f)
+        return state
+
+    def set_state(self, f_global, state):  # MPM:633-644
+        f = self.f_global_to_f_local(f_global)
+        if self.has_particles:
+            self.setframe(f, state['x'], state['v'], state['C'], state['F'], state['used'])
+        if self.agent is not None:
+            self.agent.set_state(f, state['agent'])
+
+    def get_x(self, f=None):
+        f = self.cur_substep_local if f is None else f
+        if not self.has_particles:
+            return np.zeros((0, self.dim), dtype=DTYPE_NP)
+        return self.readframe(f, ('x',))['x']
+
+    def get_v(self, f):
+        if not self.has_particles:
+            return np.zeros((0, self.dim), dtype=DTYPE_NP)
+        return self.readframe(f, ('v',))['v']
+
+    def get_used(self, f=None):
+        f = self.cur_substep_local if f is None else f
+        if not self.has_particles:
+            return np.zeros((0,), dtype=np.int32)
+        return self.readframe(f, ('used',))['used']
+
+    def get_state_RL(self):  # MPM:683-696
+        f = self.cur_substep_local
+        state = {}
+        if self.has_particles:
+            state.update(self.readframe(f, ('x', 'v', 'used')))
+        if self.agent is not None:
+            state['agent'] = self.agent.get_state(f)
+        return state
+
+    def get_state_render(self, f):  # MPM:705-707
+        r = self.readframe(f, ('x', 'used'))
+        return SimpleNamespace(x=r['x'], used=r['used'])
+
+    def set_x(self, f, x):  # MPM:577-581
+        st = self.readframe(f)
+        self.setframe(f, x, st['v'], st['C'], st['F'], st['used'])
+
+    def set_used(self, f, used):  # MPM:583-586
+        st = self.readframe(f)
+        self.setframe(f, st['x'], st['v'], st['C'], st['F'], used)
+
+    def copy_frame(self, source, target):  # MPM:588-595
+        self._ck(self._lib.fmpm_copy_frame(self._h, source, target, self._stream()), 'fmpm_copy_frame')
+        self._frame_ord[target] = self._frame_ord[source]
+
+    # ------------------------------------------------------------------------------------------ step, MPM:721-775
+    def step(self, action=None):
+        if self.grad_enabled:
+            if self.cur_substep_local == 0:
+                self.actions_buffer = []
+        self.step_(action)
+        if self.grad_enabled:
+            self.actions_buffer.append(action)
+        if self.cur_substep_local == 0:
+            self.memory_to_cache()
+
+    def step_(self, action=None):
+        is_none_action = action is None
+        if not is_none_action:
+            self.agent.set_action(s=self.cur_step_local, s_global=self.cur_step_global, n_substeps=self.n_substeps, action=action)
+        if self.has_particles and self.sort_every > 0 and self.cur_step_global % self.sort_every == 0:
+            self.sort_frame(self.cur_substep_local)
+        for _ in range(self.n_substeps):
+            self.substep(self.cur_substep_local, is_none_action)
+            self.cur_substep_global += 1
+        assert self.cur_substep_global <= self.max_substeps_global
+
+    def step_grad(self, action=None):
+        if self.cur_substep_local == 0:
+            self.memory_from_cache()
+        is_none_action = action is None
+        for _ in range(self.n_substeps - 1, -1, -1):
+            self.cur_substep_global -= 1
+            self.substep_grad(self.cur_substep_local, is_none_action)
+        if not is_none_action:
+            self.agent.set_action_grad(s=self.cur_substep_local // self.n_substeps, s_global=self.cur_substep_global // self.n_substeps,
+                                       n_substeps=self.n_substeps, action=action)
+
+    # ------------------------------------------------------------------------------------------ checkpoint ring, MPM:777-912
+    def _ckpt_device(self):
+        return {'gpu': self.device, 'cpu': torch.device('cpu'), 'disk': torch.device('cpu')}[self.ckpt_dest]
+
+    def memory_to_cache(self):
+        T = self.max_substeps_local
+        if self.grad_enabled:
+            ckpt_start_step = self.cur_substep_global - T
+            ckpt_name = f'{ckpt_start_step:06d}'
+            d = self._ckpt_device()
+            ckpt = {'actions': list(self.actions_buffer)}
+            if self.has_particles:
+                o = self._frame_ord[0]
+                ckpt.update(pa=self._pa[0].to(d, copy=True), pf=self._pf[0].to(d, copy=True), pf8=self._pf8[0].to(d, copy=True),
+                            ids=None if o.ids is None else o.ids.to(d, copy=True), inv=None if o.inv is None else o.inv.to(d, copy=True))
+            if self.agent is not None:
+                ckpt['agent'] = self.agent.get_ckpt()
+            if self.ckpt_dest == 'disk':
+                os.makedirs(self.ckpt_dir, exist_ok=True)
+                torch.save(ckpt, os.path.join(self.ckpt_dir, f'{ckpt_name}.pt'))
+            else:
+                self.ckpt_ram[ckpt_name] = ckpt
+        # restart from frame 0 in memory
+        if self.has_particles:
+            self.copy_frame(T, 0)
+        if self.agent is not None:
+            self.agent.copy_frame(T, 0)
+
+    def memory_from_cache(self):
+        assert self.grad_enabled
+        T = self.max_substeps_local
+        # reference: copy_frame(0,T); copy_grad(0,T); reset_grad_till_frame(T).  The adjoint ping-pong frame already
+        # *is* "the adjoint of the current frame", so only the agent's per-frame adjoints need the shuffle.
+        if self.agent is not None:
+            self.agent.copy_frame(0, T)
+            self.agent.copy_grad(0, T)
+            self.agent.reset_grad_till_frame(T)
+        ckpt_start_step = self.cur_substep_global - T
+        ckpt_name = f'{ckpt_start_step:06d}'
+        if self.ckpt_dest == 'disk':
+            ckpt = torch.load(os.path.join(self.ckpt_dir, f'{ckpt_name}.pt'), weights_only=False)
+        else:
+            ckpt = self.ckpt_ram[ckpt_name]
+        if self.has_particles:
+            self._pa[0].copy_(ckpt['pa']); self._pf[0].copy_(ckpt['pf']); self._pf8[0].copy_(ckpt['pf8'])
+            self._frame_ord[0] = _IDENTITY if ckpt['ids'] is None else _Order(ckpt['ids'].to(self.device, copy=True), ckpt['inv'].to(self.device, copy=True))
+        if self.agent is not None:
+            self.agent.set_ckpt(ckpt['agent'])
+        # now that the first frame is loaded, a forward pass fills up the rest of the ring
+        self.cur_substep_global = ckpt_start_step
+        for action in ckpt['actions']:
+            self.step_(action)
+
+    # ------------------------------------------------------------------------------------------ phase-level access (tests, profiling)
+    def read_grid(self):
+        G, dev, f32 = self.n_grid ** 3, self.device, torch.float32
+        vin = torch.empty((G, 3), dtype=f32, device=dev); m = torch.empty((G,), dtype=f32, device=dev); vout = torch.empty((G, 3), dtype=f32, device=dev)
+        self._ck(self._lib.fmpm_read_grid(self._h, vin.data_ptr(), m.data_ptr(), vout.data_ptr(), self._stream()), 'fmpm_read_grid')
+        return vin.cpu().numpy(), m.cpu().numpy(), vout.cpu().numpy()
+
+    def read_grid_grad(self):
+        G, dev, f32 = self.n_grid ** 3, self.device, torch.float32
+        vin = torch.empty((G, 3), dtype=f32, device=dev); m = torch.empty((G,), dtype=f32, device=dev); vout = torch.empty((G, 3), dtype=f32, device=dev)
+        self._ck(self._lib.fmpm_read_grid_grad(self._h, vin.data_ptr(), m.data_ptr(), vout.data_ptr(), self._stream()), 'fmpm_read_grid_grad')
+        return vin.cpu().numpy(), m.cpu().numpy(), vout.cpu().numpy()
+
+    def phase(self, name, f, *args):
+        """Run one kernel phase by name ('clear_grid','p2g','grid_op','g2p','g2p_grad_scatter','grid_op_grad','particle_grad')."""
+        s = self._stream()
+        L, h = self._lib, self._h
+        if name == 'clear_grid': rc = L.fmpm_clear_grid(h, s)
+        elif name == 'p2g': rc = L.fmpm_p2g(h, f, int(args[0]) if args else 1, s)
+        elif name == 'grid_op': rc = L.fmpm_grid_op(h, f, int(args[0]) if args else 0, s)
+        elif name == 'g2p':
+            rc = L.fmpm_g2p(h, f, s); self._frame_ord[f + 1] = self._frame_ord[f]
+        elif name == 'g2p_grad_scatter': rc = L.fmpm_g2p_grad_scatter(h, f, self._gcur, s)
+        elif name == 'grid_op_grad': rc = L.fmpm_grid_op_grad(h, f, s)
+        elif name == 'particle_grad':
+            rc = L.fmpm_particle_grad(h, f, self._gcur, 1 - self._gcur, s); self._gcur = 1 - self._gcur
+        else: raise KeyError(name)
+        self._ck(rc, name)

@@ -1,0 +1,167 @@
+/* =====================================================================================
+ * include/fluidmpm.h — C ABI of libfluidmpm.so, the B200-native (sm_100a) MLS-MPM substep.
+ *
+ * Drop-in boundary for ONE hot path of zhouxian/FluidLab: the differentiable MLS-MPM substep of
+ * fluidlab/fluidengine/simulators/mpm_simulator.py (abbrev. MPM below).  The reference binds this
+ * path through Taichi kernels called from Python (`MPMSimulator.substep`, MPM:515-533, and
+ * `substep_grad`, MPM:535-552); a replacement binds the entry points below through ctypes
+ * (see INTEGRATION.md).  Plain pointers and sizes only — no torch types.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure (then fmpm_last_error() explains);
+ *    no exceptions cross the ABI; the reference's own error behaviour (Python asserts) lives in
+ *    the host layer (fluidlab_b200/).
+ *  - all pointers are DEVICE pointers owned by the caller (torch tensors) unless stated;
+ *    the library allocates nothing after fmpm_bind().
+ *  - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*), no implicit
+ *    synchronisation; one handle per GPU; not thread-safe per handle (the reference is
+ *    single-threaded, MPM:721-775).
+ *  - `f` is a LOCAL frame index in [0, max_substeps_local] (MPM:225-227).
+ *
+ * Device data layout.  N = particle slots, G = n_grid^3, T = max_substeps_local.
+ *  state ring  pa : float4[(T+1)][4][N]  plane0=(x0,x1,x2,meta) plane1=(v0,v1,v2,C00)
+ *                                         plane2=(C01,C02,C10,C11) plane3=(C12,C20,C21,C22)
+ *              pf : float4[(T+1)][2][N]  (F00,F01,F02,F10) (F11,F12,F20,F21)
+ *              pf8: float [(T+1)][N]     F22
+ *  meta (int bits in plane0.w): bit0 = used (MPM:86-88), bits 8..15 = row of the material table.
+ *  grads       ga/gf/gf8 : same planar layout, 2 frames (ping-pong: index 0/1).
+ *  grid        grid_pm : float4[G] (momentum xyz, mass)   — MPM:112-114 v_in, mass
+ *              grid_v  : float4[G] (v_out xyz, unused)     — MPM:115
+ *              ggrid_v : float4[G] adjoint of v_out;  ggrid_pm : float4[G] adjoint of (v_in, mass)
+ *  Particles are stored in SLOT order (cell-sorted); `ids[slot]` = original particle index and
+ *  `inv[pid]` = slot translate at the API boundary (fmpm_read_frame / fmpm_write_frame).
+ * ===================================================================================== */
+#ifndef FLUIDMPM_H_
+#define FLUIDMPM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct FmpmHandle FmpmHandle;
+
+/* material classes, fluidlab/configs/macros.py:37-41 */
+enum { FMPM_MAT_LIQUID = 200, FMPM_MAT_PLASTO_ELASTIC = 201, FMPM_MAT_ELASTIC = 202, FMPM_MAT_RIGID = 203,
+       FMPM_MAT_PLASTO_ELASTIC_DEMO = 204 };
+
+/* replaces MPMSimulator.__init__ constants (MPM:14-34) + setup_boundary (MPM:39-40,
+ * fluidlab/fluidengine/boundaries/boundaries.py:26-37,95-104) */
+typedef struct {
+  int n_grid;             /* MPM:21 */
+  int n_particles;        /* MPM:54 */
+  int max_substeps_local; /* MPM:27 (T) */
+  int n_substeps;         /* MPM:30 */
+  float dt, dx, inv_dx, p_vol; /* MPM:22-25 */
+  float k_stress;         /* -dt*p_vol*4*inv_dx^2 evaluated in double then rounded, MPM:343 */
+  float gravity[3];       /* MPM:19 */
+  int boundary_type;      /* 0 cube, 1 cylinder */
+  float b_lower[3], b_upper[3];
+  float cyl_center[2], cyl_radius;
+  float restitution;
+  int lock_mask;          /* bit d: lock_dims contains d */
+  int n_materials;        /* rows in the material table */
+  int device;             /* CUDA device ordinal */
+} FmpmConfig;
+
+/* one row per distinct (material, rho): replaces particles_i.{mu,lam,mass,mat_cls} (MPM:96-103,170-175) */
+typedef struct { float mu, lam, mass; int cls; } FmpmMaterial;
+
+typedef struct {
+  void* pa; void* pf; void* pf8;          /* state ring */
+  void* ga; void* gf; void* gf8;          /* grad ping-pong (may be NULL when grads are never used) */
+  void* grid_pm; void* grid_v; void* ggrid_v; void* ggrid_pm;
+  void* materials;                        /* FmpmMaterial[n_materials] */
+  void* scratch_a; void* scratch_f; void* scratch_f8;   /* one spare frame (sort / permute staging) */
+  void* sort_keys_in; void* sort_keys_out; void* sort_vals_in; void* sort_vals_out; /* int[N] each */
+  void* sort_tmp; unsigned long long sort_tmp_bytes;    /* >= fmpm_sort_workspace_bytes() */
+} FmpmBuffers;
+
+/* effector pose chain, fluidlab/fluidengine/effectors/effector.py:34-51 (fields), :157-161 (move_kernel),
+ * :218-260 (set_action / set_velocity / apply_action_p), boundary = boundaries.py:65-78,122-125 impose_x */
+typedef struct {
+  void* pos; void* quat; void* v; void* w;          /* float[(T+1)*3|4] */
+  void* gpos; void* gquat; void* gv; void* gw;      /* adjoints, same shapes */
+  void* act; void* gact;                            /* float[max_action_steps*action_dim] */
+  void* act_p; void* gact_p;                        /* float[action_dim] */
+  int action_dim;
+  float scale_v[6], scale_p[6];
+  int boundary_type; float b_lower[3], b_upper[3]; float cyl_center[2], cyl_radius;
+} FmpmEffector;
+
+/* injector, fluidlab/fluidengine/effectors/injector.py:54-68,80-105 (Injector) and :220-256 (BallInjector) */
+typedef struct {
+  int kind;                 /* 1 Injector, 2 BallInjector */
+  int flux;                 /* particles activated per substep */
+  float radius;
+  float inject_v[3], inject_p[3];
+  const void* random_vector; /* float[random_length*flux*3] */
+  const void* act_range;     /* int[n_act_range], original particle ids */
+  int n_act_range;
+} FmpmInjector;
+
+int  fmpm_create(const FmpmConfig* cfg, FmpmHandle** out);
+void fmpm_destroy(FmpmHandle* h);
+int  fmpm_bind(FmpmHandle* h, const FmpmBuffers* b);
+const char* fmpm_last_error(FmpmHandle* h);
+unsigned long long fmpm_sort_workspace_bytes(FmpmHandle* h);
+int  fmpm_abi_version(void);
+
+/* ---- forward substep, MPM:515-533 (reset_grid .. advect) -------------------------------------- */
+int fmpm_clear_grid(FmpmHandle* h, void* stream);                      /* MPM:219-223 */
+int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream);         /* MPM:254-264 + 331-378 fused */
+int fmpm_grid_op(FmpmHandle* h, int f, int clear_pm, void* stream);    /* MPM:380-398 */
+int fmpm_g2p(FmpmHandle* h, int f, void* stream);                      /* MPM:304-316 + 400-426 + 497-505 fused */
+int fmpm_substep(FmpmHandle* h, int f, void* stream);                  /* p2g, grid_op(clear), g2p; grid must be clear on entry */
+/* agent.act for injector agents, agents/agent_injector.py:23-32; run after fmpm_g2p of the same f */
+int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,
+                const void* inv, void* stream);
+
+/* ---- backward substep, MPM:535-552 ------------------------------------------------------------ */
+/* gin/gout in {0,1}: grad ping-pong index holding frame f+1 (in) and receiving frame f (out). */
+int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* stream);
+int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream);           /* g2p.grad: grid side */
+int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream);                        /* grid_op.grad */
+int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void* stream);    /* advect/g2p/p2g/svd/F_tmp .grad: particle side */
+int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjector* inj, const FmpmEffector* e, int act_id,
+                     const void* inv, void* stream);
+
+/* ---- frame ring / io, MPM:555-609 -------------------------------------------------------------- */
+/* API layout: x,v float[N,3]; C,F float[N,3,3]; used int[N]; mrow int[N] (material row); all indexed by
+ * ORIGINAL particle id.  ids == NULL means identity order. */
+int fmpm_write_frame(FmpmHandle* h, int f, const void* x, const void* v, const void* C, const void* F,
+                     const void* used, const void* mrow, const void* ids, void* stream);   /* setframe MPM:566-575 */
+int fmpm_read_frame(FmpmHandle* h, int f, void* x, void* v, void* C, void* F, void* used, const void* ids, void* stream); /* readframe MPM:555-564 */
+int fmpm_write_grad(FmpmHandle* h, int g, const void* x, const void* v, const void* C, const void* F, const void* ids, void* stream);
+int fmpm_read_grad(FmpmHandle* h, int g, void* x, void* v, void* C, void* F, const void* ids, void* stream);
+int fmpm_zero_grad(FmpmHandle* h, int g, void* stream);
+int fmpm_copy_frame(FmpmHandle* h, int src, int dst, void* stream);                        /* MPM:588-595 */
+/* re-express grad buffer gsrc (slot order ids_src) in the slot order whose inverse map is inv_dst -> buffer gdst */
+int fmpm_permute_grad(FmpmHandle* h, int gsrc, int gdst, const void* ids_src, const void* inv_dst, void* stream);
+/* cell-sort frame f in place: ids_in[slot] -> ids_out / inv_out describe the new order (ids_in may be NULL = identity) */
+int fmpm_sort(FmpmHandle* h, int f, const void* ids_in, void* ids_out, void* inv_out, void* stream);
+/* grid accessors for phase-level parity tests: float[G,3], float[G], float[G,3] (any may be NULL) */
+int fmpm_read_grid(FmpmHandle* h, void* v_in, void* mass, void* v_out, void* stream);
+int fmpm_read_grid_grad(FmpmHandle* h, void* gv_in, void* gmass, void* gv_out, void* stream);
+int fmpm_write_grid_grad(FmpmHandle* h, const void* gv_in, const void* gmass, const void* gv_out, void* stream);
+
+/* ---- effector chain --------------------------------------------------------------------------- */
+/* set_action (effector.py:262-268) for step s / s_global followed by the n_substeps move_kernel calls of that step
+ * (effector.py:157-161); `action` is a device float[action_dim]. */
+int fmpm_effector_step(FmpmHandle* h, const FmpmEffector* e, int s, int s_global, const void* action, void* stream);
+/* adjoint of the above: n_substeps move_kernel.grad (reverse) then set_velocity.grad (effector.py:270-274) */
+int fmpm_effector_step_grad(FmpmHandle* h, const FmpmEffector* e, int s, int s_global, void* stream);
+int fmpm_effector_apply_action_p(FmpmHandle* h, const FmpmEffector* e, void* stream);       /* effector.py:223-226 */
+int fmpm_effector_apply_action_p_grad(FmpmHandle* h, const FmpmEffector* e, void* stream);  /* effector.py:233-234 */
+
+/* ---- index-matched shape loss, fluidlab/fluidengine/losses/shapematching_loss.py:80-93 ---------- */
+/* loss_out[0] += weight * sum_{p used, mrow_mask bit set} |x[f,p]-tgt[p]|^2 ; tgt float[N,3] by original id */
+int fmpm_loss_chamfer(FmpmHandle* h, int f, const void* ids, const void* tgt, unsigned int mrow_mask_lo,
+                      float weight, void* loss_out, void* stream);
+/* x-grad of buffer g += 2*weight*(x-tgt) (compute_chamfer_loss_kernel.grad with total_loss.grad = 1) */
+int fmpm_loss_chamfer_grad(FmpmHandle* h, int f, int g, const void* ids, const void* tgt, unsigned int mrow_mask_lo,
+                           float weight, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDMPM_H_ */

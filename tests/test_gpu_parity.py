@@ -1,0 +1,269 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libfluidmpm.so, driven by fluidlab_b200) against the CPU
+oracle on the same seeded inputs.  Tolerances: BASELINE.json north_star — 1e-5 relative (fp32) on x/v/F after N
+substeps; 1e-4 on gradients.  `rel(a, b) = max|a-b| / max(|b|, floor)`."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_particles
+from fluidlab_b200 import macros as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+
+
+def rel(a, b, floor=1e-12):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), floor)
+
+
+def build_pair(P, n_grid, gravity=(0, -10, 0), boundary=None, T=10, precision=32, sort_every=1):
+    from oracle import oracle as orc
+    from fluidlab_b200 import MPMSimulator
+    o = orc.OracleSim(n_grid, P, gravity=gravity, boundary=boundary, max_substeps_local=T, precision=precision)
+    s = MPMSimulator(dim=3, quality=n_grid / 64, gravity=gravity, horizon=100, max_substeps_local=T, max_substeps_global=100000,
+                     ckpt_dest='gpu', sort_every=sort_every)
+    if boundary is not None:
+        s.setup_boundary(**boundary)
+    s.build(None, None, [], P)
+    return o, s
+
+
+def random_state(P, rng, amp_F=0.02, amp_C=5.0, amp_v=0.5):
+    N = len(P['x'])
+    f32 = lambda a: a.astype(np.float32)
+    return dict(x=f32(P['x']), v=f32(rng.randn(N, 3) * amp_v), C=f32(rng.randn(N, 3, 3) * amp_C),
+                F=f32(np.eye(3)[None] + rng.randn(N, 3, 3) * amp_F), used=P['used'].astype(np.int32))
+
+
+def set_both(o, s, st, f=0):
+    o.set_frame(f, st['x'], st['v'], st['C'], st['F'], st['used'])
+    s.setframe(f, st['x'], st['v'], st['C'], st['F'], st['used'])
+
+
+CUBE = dict(type='cube', lower=(0.2, 0.2, 0.2), upper=(0.8, 0.8, 0.8))
+CYL = dict(type='cylinder', xz_radius=0.25, xz_center=(0.5, 0.5), y_range=(0.25, 0.8))
+
+
+@pytest.mark.parametrize('mat', [M.WATER, M.ELASTIC, M.ICECREAM, M.MILK_VIS, M.PLASTIC_DEMO])
+@pytest.mark.parametrize('boundary', [CUBE, CYL], ids=['cube', 'cyl'])
+@pytest.mark.parametrize('sort', [False, True], ids=['unsorted', 'sorted'])
+def test_forward_phases_match_oracle(mat, boundary, sort):
+    _need_gpu()
+    rng = np.random.RandomState(11)
+    n_grid, N = 32, 6000
+    x = rng.uniform(0.22, 0.78, size=(N, 3))
+    used = (rng.rand(N) > 0.1).astype(np.int32)
+    P = make_particles(x, mat, n_grid, used=used)
+    o, s = build_pair(P, n_grid, boundary=boundary)
+    st = random_state(P, rng)
+    set_both(o, s, st)
+    if sort:
+        s.sort_frame(0)
+        back = s.readframe(0)
+        for k in ('x', 'v', 'C', 'F', 'used'):
+            assert np.array_equal(back[k], st[k]), f'sort/readframe does not round-trip {k}'
+    L = o.L
+    # p2g
+    L.orc_phase_reset_grid(o.h); L.orc_phase_p2g(o.h, 0, 1)
+    s.phase('clear_grid', 0); s.phase('p2g', 0, 1)
+    ovin, om, _ = o.get_grid(); gvin, gm, _ = s.read_grid()
+    assert rel(gm, om) < 1e-5 and rel(gvin, ovin) < 2e-5, (rel(gm, om), rel(gvin, ovin))
+    assert np.array_equal(gm > 0, om > 0)
+    # grid_op
+    L.orc_phase_grid_op(o.h, 0); s.phase('grid_op', 0, 0)
+    _, _, ovout = o.get_grid(); _, _, gvout = s.read_grid()
+    assert rel(gvout, ovout) < 2e-5, rel(gvout, ovout)
+    # g2p + advect (+ unused copy)
+    L.orc_phase_g2p(o.h, 0); s.phase('g2p', 0)
+    of, gf = o.get_frame(1), s.readframe(1)
+    assert np.array_equal(gf['used'], of['used'])
+    for k, tol in (('x', 1e-6), ('v', 2e-5), ('C', 5e-5), ('F', 1e-5)):
+        assert rel(gf[k], of[k]) < tol, (k, rel(gf[k], of[k]))
+
+
+@pytest.mark.parametrize('mat,n_sub', [(M.WATER, 100), (M.ELASTIC, 60), (M.ICECREAM, 60), (M.COFFEE_VIS, 60)])
+def test_forward_100_substeps_parity(mat, n_sub):
+    """x/v/F after N substeps within 1e-5 relative of the fp32 oracle (and of the fp64 oracle for x)."""
+    _need_gpu()
+    rng = np.random.RandomState(12)
+    n_grid = 32
+    b = __import__('fluidlab_b200').Bodies(particle_density=4e5)
+    b.add_body(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.6, 0.55, 0.6), material=mat)
+    Pb = b.get()
+    P = make_particles(Pb['x'], mat, n_grid)
+    o, s = build_pair(P, n_grid, gravity=(0, -10, 0), T=10)
+    for step in range(n_sub // 10):
+        s.step(None)
+        for _ in range(10):
+            o.substep(o.cur_substep_local); o.cur_substep_global += 1
+        if o.cur_substep_local == 0:
+            o.L.orc_copy_frame(o.h, o.T, 0)
+    assert s.cur_substep_global == n_sub
+    gf, of = s.get_state(), o.get_frame(o.cur_substep_local)
+    assert rel(gf['x'], of['x']) < 1e-5, rel(gf['x'], of['x'])
+    assert rel(gf['F'], of['F']) < 1e-5, rel(gf['F'], of['F'])
+    assert rel(gf['v'], of['v']) < (1e-5 if mat == M.WATER else 1e-4), rel(gf['v'], of['v'])
+    assert np.isfinite(gf['x']).all()
+
+
+def test_state_io_roundtrip_and_ring_wrap():
+    _need_gpu()
+    rng = np.random.RandomState(13)
+    n_grid, N = 32, 3000
+    P = make_particles(rng.uniform(0.3, 0.7, size=(N, 3)), M.WATER, n_grid)
+    o, s = build_pair(P, n_grid, T=20)
+    st = random_state(P, rng, amp_C=1.0)
+    s.set_state(0, st)
+    got = s.get_state()
+    for k in ('x', 'v', 'C', 'F', 'used'):
+        assert np.array_equal(got[k], st[k])
+    assert got['x'].dtype == np.float32 and got['used'].dtype == np.int32
+    # 3 steps = 30 substeps over a T=20 ring: wraps once (memory_to_cache copies frame T -> 0)
+    set_both(o, s, st)
+    for _ in range(3):
+        s.step(None); o.step(None)
+    assert s.cur_substep_local == 10 == o.cur_substep_local
+    assert rel(s.get_x(), o.get_frame(10)['x']) < 1e-5
+    assert rel(s.get_v(10), o.get_frame(10)['v']) < 1e-4
+    rl = s.get_state_RL()
+    assert set(rl) == {'x', 'v', 'used'}
+
+
+@pytest.mark.parametrize('mat', [M.WATER, M.ELASTIC, M.ICECREAM, M.MILK_VIS])
+@pytest.mark.parametrize('sort', [False, True], ids=['unsorted', 'sorted'])
+def test_substep_grad_matches_oracle(mat, sort):
+    """One backward substep: adjoint of frame f from a random adjoint of frame f+1, vs the fp64 oracle run on the
+    same fp32 inputs (1e-4 relative), including the intermediate grid adjoints."""
+    _need_gpu()
+    rng = np.random.RandomState(14)
+    n_grid, N = 32, 5000
+    used = (rng.rand(N) > 0.1).astype(np.int32)
+    P = make_particles(rng.uniform(0.25, 0.75, size=(N, 3)), mat, n_grid, used=used)
+    o, s = build_pair(P, n_grid, boundary=CUBE, precision=64)
+    st = random_state(P, rng, amp_F=0.05)
+    set_both(o, s, st)
+    if sort:
+        s.sort_frame(0)
+    s.substep(0, True); o.substep(0)
+    s.cur_substep_global = 1
+    g = {k: rng.randn(*st[k].shape).astype(np.float32) for k in ('x', 'v', 'C', 'F')}
+    o.reset_grad(); o.set_grad_frame(1, g['x'], g['v'], g['C'], g['F'])
+    s.reset_grad(); s.set_grad(g['x'], g['v'], g['C'], g['F'])
+    o.substep_grad(0)
+    s.cur_substep_global = 0
+    s.substep_grad(0, True)
+    ovin, om, ovout = o.get_grid_grad(); gvin, gm, gvout = s.read_grid_grad()
+    assert rel(gvout, ovout) < 1e-4, rel(gvout, ovout)
+    assert rel(gvin, ovin) < 1e-4 and rel(gm, om) < 1e-4, (rel(gvin, ovin), rel(gm, om))
+    og, gg = o.get_grad_frame(0), s.get_grad()
+    for k in ('x', 'v', 'C', 'F'):
+        assert rel(gg[k], og[k]) < 1e-4, (k, rel(gg[k], og[k]))
+    # unused particles pass the adjoint through unchanged (MPM:551)
+    idx = np.where(used == 0)[0]
+    assert np.array_equal(gg['v'][idx], g['v'][idx]) and np.array_equal(gg['F'][idx], g['F'][idx])
+
+
+def _latte_cfg(flux):
+    return dict(type='AgentInjector', effectors=[dict(
+        type='Injector',
+        params=dict(radius=0.0075, flux=flux, init_pos=(0.5, 0.5, 0.5), action_dim=3, inject_v=(0.0, -3.0, 0.0),
+                    action_scale_p=(1.0, 1.0, 1.0), action_scale_v=(1.0, 1.0, 1.0), locally_random=True),
+        boundary=dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.55, 0.55)))])
+
+
+def _latte_env(n_grid, n_coffee, n_milk, flux, T, horizon, sort_every=1):
+    """small LatteArt-like scene (envs/latteart_env.py): parked MILK + COFFEE pool + injector, via the TaichiEnv facade."""
+    from fluidlab_b200 import TaichiEnv, LatteArtLoss
+    from oracle import oracle as orc
+    rng = np.random.RandomState(21)
+    env = TaichiEnv(quality=n_grid / 64, max_substeps_local=T, gravity=(0.0, -20.0, 0.0), horizon=horizon, sort_every=sort_every)
+    np.random.seed(5)
+    env.setup_agent(_latte_cfg(flux))
+    x = np.concatenate([np.tile(M.NOWHERE, (n_milk, 1)), rng.uniform((0.35, 0.36, 0.35), (0.65, 0.45, 0.65), size=(n_coffee, 3))])
+    mat = np.concatenate([np.full(n_milk, M.MILK), np.full(n_coffee, M.COFFEE)])
+    used = np.concatenate([np.zeros(n_milk), np.ones(n_coffee)]).astype(np.int32)
+    P = make_particles(x, mat, n_grid, used=used)
+    env.particle_bodies.get = lambda: P  # inject the synthetic bodies
+    bnd = dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.34, 0.9))
+    env.setup_boundary(**bnd)
+    tgt = [rng.uniform(0.4, 0.6, size=x.shape).astype(np.float32) for _ in range(horizon)]
+    env.setup_loss(loss_cls=LatteArtLoss, type='diff', target=tgt, weights={'chamfer': 1.0})
+    env.build()
+    inj = env.agent.effectors[0]
+    o = orc.OracleSim(n_grid, P, gravity=(0, -20, 0), boundary=bnd, precision=64, max_substeps_local=T)
+    o.add_effector(type=1, action_dim=3, boundary=_latte_cfg(flux)['effectors'][0]['boundary'], radius=0.0075, flux=flux,
+                   inject_v=(0, -3, 0), inject_p=(0, 0, 0), locally_random=True, random_vector=inj.random_vector_np,
+                   act_range=np.where(used == 0)[0], max_action_steps=horizon + 1)
+    return env, o, P, tgt
+
+
+@pytest.mark.parametrize('sort_every', [0, 1])
+def test_dloss_daction_latteart_like(sort_every):
+    """Forward + backward through TaichiEnv (injector agent, index-matched MILK loss, T=20 ring -> chunk checkpoint and
+    re-simulation) vs the fp64 oracle: loss within 1e-5, dLoss/dAction (4 x 3) within 1e-4."""
+    _need_gpu()
+    n_steps, T = 3, 20
+    env, o, P, tgt = _latte_env(32, 4000, 400, 4, T, n_steps, sort_every)
+    rng = np.random.RandomState(22)
+    actions = rng.uniform(-0.004, 0.004, size=(n_steps, 3)).astype(np.float32)
+    action_p = np.array([0.47, 0.55, 0.52], dtype=np.float32)
+    # ---- CUDA path, exactly the call sequence of optimizer/solver.py:23-59
+    st0 = env.get_state()['state']
+    env.set_state(st0, grad_enabled=True)
+    env.apply_agent_action_p(action_p)
+    for i in range(n_steps):
+        env.step(actions[i])
+    info = env.get_final_loss()
+    env.reset_grad(); env.get_final_loss_grad()
+    for i in range(n_steps - 1, -1, -1):
+        env.step_grad(actions[i])
+    env.apply_agent_action_p_grad(action_p)
+    grad = env.agent.get_grad(n_steps)
+    # ---- oracle
+    N = len(P['x'])
+    o.enable_grad()
+    o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+    o.set_effector_state(0, 0, np.array([0.5, 0.5, 0.5, 1, 0, 0, 0, 0.0]))
+    o.apply_action_p(action_p)
+    total = 0.0
+    for i in range(n_steps):
+        o.step(actions[i]); total += o.loss_value(o.cur_substep_local, M.MILK, 1.0, tgt[i])
+    o.reset_grad()
+    for i in range(n_steps - 1, -1, -1):
+        o.loss_seed(o.cur_substep_local, M.MILK, 1.0, tgt[i]); o.step_grad(actions[i])
+    o.apply_action_p_grad()
+    og = o.get_action_grad(n_steps)
+    assert abs(info['loss'] - total) <= 1e-5 * abs(total), (info['loss'], total)
+    assert grad.shape == og.shape == (n_steps + 1, 3)
+    assert np.abs(og).max() > 1e-3
+    assert rel(grad, og) < 1e-4, (rel(grad, og), grad, og)
+    assert np.all(grad[:, 1] == 0)  # injector y is pinned by its own boundary (agent_latteart.yaml:23)
+    st = env.get_state()['state']
+    assert int(st['used'].sum()) == 4000  # set_state restored frame 0 semantics: get_state reads the current frame (0 after full backward)
+
+
+def test_out_of_grid_particles_are_frozen_not_corrupting():
+    _need_gpu()
+    n_grid = 32
+    x = np.array([[0.5, 0.5, 0.5], [0.999, 0.5, 0.5], [-0.2, 0.5, 0.5], [0.5, 1.7, 0.5]])
+    P = make_particles(x, M.WATER, n_grid)
+    _, s = build_pair(P, n_grid)
+    s.step(None)
+    st = s.get_state()
+    assert np.isfinite(st['x']).all()
+    assert np.array_equal(st['x'][1:], x[1:].astype(np.float32))  # frozen
+    assert st['x'][0, 1] < 0.5  # the in-grid particle fell
+
+
+def test_library_error_reporting():
+    _need_gpu()
+    P = make_particles(np.full((4, 3), 0.5), M.WATER, 32)
+    _, s = build_pair(P, 32)
+    from fluidlab_b200._lib import FmpmError
+    with pytest.raises(FmpmError, match='out of range'):
+        s.readframe(999)
