@@ -217,7 +217,9 @@ def main():
     t_p2g = time_phase(lambda: sim.phase('p2g', f, 0), pre=lambda: sim.phase('clear_grid', f))
     sim.phase('clear_grid', f); sim.phase('p2g', f, 0)
     g_t = int((sim._grid_pm[:, 3] > 0).sum().item())
-    t_gop = time_phase(lambda: sim.phase('grid_op', f, 0))
+    def _refill():
+        sim.phase('clear_grid', f); sim.phase('p2g', f, 0)
+    t_gop = time_phase(lambda: sim.phase('grid_op', f, 0), pre=_refill)  # includes the active-block compaction
     # g2p writes frame f+1: time it on a scratch frame pair (f -> f+1 is rewritten by the next step anyway)
     t_g2p = time_phase(lambda: sim._ck(sim._lib.fmpm_g2p(sim._h, f, sim._stream()), 'g2p'))
     sim.phase('clear_grid', f)

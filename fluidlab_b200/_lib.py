@@ -42,6 +42,7 @@ class FmpmBuffers(C.Structure):
         ("scratch_a", vp), ("scratch_f", vp), ("scratch_f8", vp),
         ("sort_keys_in", vp), ("sort_keys_out", vp), ("sort_vals_in", vp), ("sort_vals_out", vp),
         ("sort_tmp", vp), ("sort_tmp_bytes", C.c_ulonglong),
+        ("blk_flags", vp), ("blk_list", vp), ("blk_count", vp),
     ]
 
 

@@ -15,19 +15,10 @@
 #include <cstdio>
 #include "fmpm_common.cuh"
 
-#define FULL_MASK 0xffffffffu
+#include "fmpm_scatter.cuh"
+
 #define SC_WARPS 4
 #define SC_ROUNDS 4
-#define WSTR 33
-
-__device__ __forceinline__ void red_add_v4(float4* addr, const float4& v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-struct __align__(16) ScatterSmemB {
-  float4 uni[32 * 4];
-  float w[27 * WSTR + 5];
-};
 
 // grads in a ping-pong buffer g (0/1): same planar layout as the state ring with frame index g
 struct GState { float x[3], v[3]; Mat3 C, F; };
@@ -41,21 +32,13 @@ __device__ __forceinline__ void load_grad(const KParams& P, int g, int s, GState
 // g2p.grad, grid side:  gv_out[i] += w_i * (gv + 4 inv_dx * gC' (o - fx)),  gv = gv' + dt * gx'
 // =============================================================================================
 __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParams P, const int f, const int gin) {
-  __shared__ ScatterSmemB smem[SC_WARPS];
+  __shared__ ScatterSmem smem[SC_WARPS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  ScatterSmemB& S = smem[wib];
+  ScatterSmem& S = smem[wib];
   const long long gw = (long long)blockIdx.x * SC_WARPS + wib;
   const long long slot0 = gw * (32 * SC_ROUNDS);
   if (slot0 >= P.N) return;
-  // window state (lane = stencil node)
-  const int L = lane < 27 ? lane : 26;
-  const int na = L / 9, nb = (L / 3) % 3, nc = L % 3;
-  const float oa = (float)na, ob = (float)nb, oc = (float)nc;
-  const int lane_off = (na * P.n + nb) * P.n + nc;
-  const bool lane_valid = lane < 27;
-  float3 acc = make_float3(0.f, 0.f, 0.f);
-  int cur_key = -1;
-  float4* __restrict__ grid = P.ggrid_v;
+  Window W; window_init(W, lane, P.n, nullptr);
 #pragma unroll 1
   for (int r = 0; r < SC_ROUNDS; r++) {
     const long long rem = (long long)P.N - (slot0 + r * 32);
@@ -64,7 +47,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
     const long long sl = slot0 + r * 32 + lane;
     int key = -1;
     float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float w[3][3];
+    float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     if (sl < P.N) {
       const int s = (int)sl;
       const float4 a0 = P.pa[pa_idx(P, f, 0, s)];
@@ -78,76 +61,48 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
 #pragma unroll
         for (int i = 0; i < 3; i++) q[i] = (g.v[i] + P.dt * g.x[i]) - (B[i * 3] * fx[0] + B[i * 3 + 1] * fx[1] + B[i * 3 + 2] * fx[2]);
         bspline(fx, w);
-        key = (b[0] * P.n + b[1]) * P.n + b[2];
+        key = pack_key(b);
       }
     }
-    S.uni[lane * 4 + 0] = make_float4(q[0], q[1], q[2], 0.f);
-    S.uni[lane * 4 + 1] = make_float4(B[0], B[1], B[2], B[3]);
-    S.uni[lane * 4 + 2] = make_float4(B[4], B[5], B[6], B[7]);
-    S.uni[lane * 4 + 3] = make_float4(B[8], __int_as_float(key), 0.f, 0.f);
-    if (key >= 0) {
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b2 = 0; b2 < 3; b2++) {
-          const float wab = w[a][0] * w[b2][1];
-#pragma unroll
-          for (int c = 0; c < 3; c++) S.w[(a * 9 + b2 * 3 + c) * WSTR + lane] = wab * w[c][2];
-        }
-    }
+    const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, 0.f, w);
     __syncwarp();
-    for (int j = 0; j < cnt; j++) {
-      const float4 u3 = S.uni[j * 4 + 3];
-      const int k2 = __float_as_int(u3.y);
-      if (k2 < 0) continue;
-      if (k2 != cur_key) {
-        if (cur_key >= 0) {
-          if (k2 == cur_key + 1) {
-            if (lane_valid && nc == 0) red_add_v4(grid + cur_key + lane_off, make_float4(acc.x, acc.y, acc.z, 0.f));
-            float3 t;
-            t.x = __shfl_down_sync(FULL_MASK, acc.x, 1); t.y = __shfl_down_sync(FULL_MASK, acc.y, 1); t.z = __shfl_down_sync(FULL_MASK, acc.z, 1);
-            acc = (nc == 2 || !lane_valid) ? make_float3(0.f, 0.f, 0.f) : t;
-          } else {
-            if (lane_valid) red_add_v4(grid + cur_key + lane_off, make_float4(acc.x, acc.y, acc.z, 0.f));
-            acc = make_float3(0.f, 0.f, 0.f);
-          }
-        }
-        cur_key = k2;
-      }
-      const float4 u0 = S.uni[j * 4], u1 = S.uni[j * 4 + 1], u2 = S.uni[j * 4 + 2];
-      const float wt = S.w[L * WSTR + j];
-      const float t0 = fmaf(u1.z, oc, fmaf(u1.y, ob, fmaf(u1.x, oa, u0.x)));
-      const float t1 = fmaf(u2.y, oc, fmaf(u2.x, ob, fmaf(u1.w, oa, u0.y)));
-      const float t2 = fmaf(u3.x, oc, fmaf(u2.w, ob, fmaf(u2.z, oa, u0.z)));
-      acc.x = fmaf(wt, t0, acc.x); acc.y = fmaf(wt, t1, acc.y); acc.z = fmaf(wt, t2, acc.z);
-    }
+    window_consume(W, S, cnt, starts, P.ggrid_v);
     __syncwarp();
   }
-  if (cur_key >= 0 && lane_valid) red_add_v4(grid + cur_key + lane_off, make_float4(acc.x, acc.y, acc.z, 0.f));
+  window_flush_all(W, P.ggrid_v);
 }
 
 // =============================================================================================
 // grid_op.grad (MPM:539): v_out = B(v_in / m + dt g)
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= P.G) return;
-  const float4 pm = P.grid_pm[g];
-  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (pm.w > FMPM_EPS) {
-    const float inv_m = 1.f / pm.w;
-    float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
-    const int n = P.n;
-    const int i = g / (n * n), j = (g / n) % n, k = g % n;
-    const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
-    float fac[3];
-    boundary_v(P, pos, v, fac);
-    const float4 gv = P.ggrid_v[g];
-    const float vb0 = gv.x * fac[0], vb1 = gv.y * fac[1], vb2 = gv.z * fac[2];
-    out.x = vb0 * inv_m; out.y = vb1 * inv_m; out.z = vb2 * inv_m;
-    out.w = -(pm.x * vb0 + pm.y * vb1 + pm.z * vb2) * inv_m * inv_m;
+__global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int clear_pm) {
+  const int count = P.blk_count[0];
+  const int n = P.n, nb = P.nb;
+  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
+    const int blk = P.blk_list[bi];
+    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int t = threadIdx.x + r * 256;
+      const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+      const int g = (i * n + j) * n + k;
+      const float4 pm = P.grid_pm[g];
+      float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pm.w > FMPM_EPS) {
+        const float inv_m = 1.f / pm.w;
+        float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
+        const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
+        float fac[3];
+        boundary_v(P, pos, v, fac);
+        const float4 gv = P.ggrid_v[g];
+        const float vb0 = gv.x * fac[0], vb1 = gv.y * fac[1], vb2 = gv.z * fac[2];
+        out.x = vb0 * inv_m; out.y = vb1 * inv_m; out.z = vb2 * inv_m;
+        out.w = -(pm.x * vb0 + pm.y * vb1 + pm.z * vb2) * inv_m * inv_m;
+      }
+      P.ggrid_pm[g] = out;
+      if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
-  P.ggrid_pm[g] = out;
 }
 
 // =============================================================================================
@@ -328,11 +283,15 @@ static int check_bound_b(FmpmHandle* h, const char* name) {
   return 0;
 }
 
-extern "C" int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) {
+int fmpm_grid_op_impl(FmpmHandle* h, int clear_pm, int zero_ggv, void* stream);  // fmpm_forward.cu
+
+static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, void* stream) {
   if (check_bound_b(h, "fmpm_g2p_grad_scatter")) return 1;
   KParams P = make_kparams(h);
-  cudaError_t e = cudaMemsetAsync(P.ggrid_v, 0, (size_t)P.G * sizeof(float4), (cudaStream_t)stream);
-  if (e != cudaSuccess) { snprintf(h->err, sizeof(h->err), "fmpm_g2p_grad_scatter: %s", cudaGetErrorString(e)); return 1; }
+  if (dense_zero) {
+    cudaError_t e = cudaMemsetAsync(P.ggrid_v, 0, (size_t)P.G * sizeof(float4), (cudaStream_t)stream);
+    if (e != cudaSuccess) { snprintf(h->err, sizeof(h->err), "fmpm_g2p_grad_scatter: %s", cudaGetErrorString(e)); return 1; }
+  }
   if (P.N == 0) return 0;
   const long long warps = ((long long)P.N + 32 * SC_ROUNDS - 1) / (32 * SC_ROUNDS);
   const int blocks = (int)((warps + SC_WARPS - 1) / SC_WARPS);
@@ -340,14 +299,17 @@ extern "C" int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p_grad_scatter");
   return 0;
 }
-extern "C" int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream) {
-  (void)f;
+extern "C" int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) { return g2p_grad_scatter_impl(h, f, gin, 1, stream); }
+static int grid_op_grad_impl(FmpmHandle* h, int clear_pm, void* stream) {
   if (check_bound_b(h, "fmpm_grid_op_grad")) return 1;
   KParams P = make_kparams(h);
-  k_grid_op_grad<<<(P.G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P);
+  const int nblk = P.nb * P.nb * P.nb;
+  const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  k_grid_op_grad<<<grid, 256, 0, (cudaStream_t)stream>>>(P, clear_pm);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op_grad");
   return 0;
 }
+extern "C" int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream) { (void)f; return grid_op_grad_impl(h, 0, stream); }
 extern "C" int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void* stream) {
   if (check_bound_b(h, "fmpm_particle_grad")) return 1;
   KParams P = make_kparams(h);
@@ -359,11 +321,11 @@ extern "C" int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void*
 extern "C" int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* stream) {
   if (check_bound_b(h, "fmpm_substep_grad")) return 1;
   if (gin == gout || (gin | gout) & ~1) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad: gin/gout must be distinct in {0,1}"); return 1; }
-  // recompute the forward grid of frame f
-  if (fmpm_clear_grid(h, stream) || fmpm_p2g(h, f, 0, stream) || fmpm_grid_op(h, f, 0, stream)) return 1;
-  if (fmpm_g2p_grad_scatter(h, f, gin, stream) || fmpm_grid_op_grad(h, f, stream) || fmpm_particle_grad(h, f, gin, gout, stream)) return 1;
-  // leave the accumulators clear for the next forward substep
-  return fmpm_clear_grid(h, stream);
+  // recompute the forward grid of frame f (accumulators are clear on entry), zeroing the v_out adjoint of the active blocks
+  if (fmpm_p2g(h, f, 0, stream) || fmpm_grid_op_impl(h, 0, 1, stream)) return 1;
+  // adjoint: grid scatter, grid_op.grad (also leaves the accumulators clear for the next substep), per-particle part
+  if (g2p_grad_scatter_impl(h, f, gin, 0, stream) || grid_op_grad_impl(h, 1, stream)) return 1;
+  return fmpm_particle_grad(h, f, gin, gout, stream);
 }
 extern "C" int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjector* inj, const FmpmEffector* e, int act_id,
                                 const void* inv, void* stream) {

@@ -29,6 +29,7 @@ struct KParams {
   float4* ga; float4* gf; float* gf8;
   float4* grid_pm; float4* grid_v; float4* ggrid_v; float4* ggrid_pm;
   const float4* mats;  // (mu, lam, mass, cls-as-int-bits)
+  int* blk_flags; int* blk_list; int* blk_count; int nb;  // sparse grid: 8^3-node blocks
 };
 
 static inline KParams make_kparams(const FmpmHandle* h) {
@@ -46,6 +47,7 @@ static inline KParams make_kparams(const FmpmHandle* h) {
   P.grid_pm = (float4*)h->buf.grid_pm; P.grid_v = (float4*)h->buf.grid_v;
   P.ggrid_v = (float4*)h->buf.ggrid_v; P.ggrid_pm = (float4*)h->buf.ggrid_pm;
   P.mats = (const float4*)h->buf.materials;
+  P.blk_flags = (int*)h->buf.blk_flags; P.blk_list = (int*)h->buf.blk_list; P.blk_count = (int*)h->buf.blk_count; P.nb = c.n_grid / 8;
   return P;
 }
 

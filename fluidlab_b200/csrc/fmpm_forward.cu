@@ -18,87 +18,10 @@
 #include <cstdio>
 #include "fmpm_common.cuh"
 
-#define FULL_MASK 0xffffffffu
+#include "fmpm_scatter.cuh"
+
 #define P2G_WARPS 4
 #define P2G_ROUNDS 4
-#define WSTR 33
-
-__device__ __forceinline__ void red_add_v4(float4* addr, const float4& v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-struct __align__(16) ScatterSmem {
-  float4 uni[32 * 4];      // per particle: (q0,q1,q2,m) (B00,B01,B02,B10) (B11,B12,B20,B21) (B22,key,-,-)
-  float w[27 * WSTR + 5];  // w[node*33 + particle]  (stride 33: conflict-free for both access patterns)
-};
-
-// Sliding-window register scatter shared by p2g (momentum+mass) and the g2p adjoint (v_out adjoint).
-// Per lane (= stencil node (a,b,c), lane = a*9+b*3+c): acc += w * (q + B·(a,b,c)), acc.w += w*m.
-struct Window {
-  float4 acc; int cur_key;
-  float oa, ob, oc; int c; int lane_off; bool lane_valid; int wrow;
-};
-__device__ __forceinline__ void window_init(Window& W, int lane, int n) {
-  int L = lane < 27 ? lane : 26;
-  int a = L / 9, b = (L / 3) % 3, c = L % 3;
-  W.oa = (float)a; W.ob = (float)b; W.oc = (float)c; W.c = c;
-  W.lane_off = (a * n + b) * n + c;
-  W.lane_valid = lane < 27;
-  W.wrow = L * WSTR;
-  W.acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  W.cur_key = -1;
-}
-__device__ __forceinline__ void window_flush_all(Window& W, float4* __restrict__ grid) {
-  if (W.cur_key >= 0 && W.lane_valid) red_add_v4(grid + W.cur_key + W.lane_off, W.acc);
-  W.acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  W.cur_key = -1;
-}
-__device__ __forceinline__ void window_consume(Window& W, const ScatterSmem& S, int cnt, float4* __restrict__ grid) {
-  for (int j = 0; j < cnt; j++) {
-    const float4 u3 = S.uni[j * 4 + 3];
-    const int key = __float_as_int(u3.y);
-    if (key < 0) continue;  // warp-uniform
-    if (key != W.cur_key) {
-      if (W.cur_key >= 0) {
-        if (key == W.cur_key + 1) {  // next cell of the same z-column: plane c=0 is complete
-          if (W.lane_valid && W.c == 0) red_add_v4(grid + W.cur_key + W.lane_off, W.acc);
-          float4 t;
-          t.x = __shfl_down_sync(FULL_MASK, W.acc.x, 1); t.y = __shfl_down_sync(FULL_MASK, W.acc.y, 1);
-          t.z = __shfl_down_sync(FULL_MASK, W.acc.z, 1); t.w = __shfl_down_sync(FULL_MASK, W.acc.w, 1);
-          W.acc = (W.c == 2 || !W.lane_valid) ? make_float4(0.f, 0.f, 0.f, 0.f) : t;
-        } else {
-          if (W.lane_valid) red_add_v4(grid + W.cur_key + W.lane_off, W.acc);
-          W.acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      W.cur_key = key;
-    }
-    const float4 u0 = S.uni[j * 4], u1 = S.uni[j * 4 + 1], u2 = S.uni[j * 4 + 2];
-    const float w = S.w[W.wrow + j];
-    float t0 = fmaf(u1.z, W.oc, fmaf(u1.y, W.ob, fmaf(u1.x, W.oa, u0.x)));
-    float t1 = fmaf(u2.y, W.oc, fmaf(u2.x, W.ob, fmaf(u1.w, W.oa, u0.y)));
-    float t2 = fmaf(u3.x, W.oc, fmaf(u2.w, W.ob, fmaf(u2.z, W.oa, u0.z)));
-    W.acc.x = fmaf(w, t0, W.acc.x); W.acc.y = fmaf(w, t1, W.acc.y); W.acc.z = fmaf(w, t2, W.acc.z);
-    W.acc.w = fmaf(w, u0.w, W.acc.w);
-  }
-}
-// lane = particle: publish the scatter record (q, B, m, key, 27 weights) to the warp's shared staging area
-__device__ __forceinline__ void scatter_publish(ScatterSmem& S, int lane, int key, const float* q, const float* B, float m, const float w[3][3]) {
-  S.uni[lane * 4 + 0] = make_float4(q[0], q[1], q[2], m);
-  S.uni[lane * 4 + 1] = make_float4(B[0], B[1], B[2], B[3]);
-  S.uni[lane * 4 + 2] = make_float4(B[4], B[5], B[6], B[7]);
-  S.uni[lane * 4 + 3] = make_float4(B[8], __int_as_float(key), 0.f, 0.f);
-  if (key >= 0) {
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int b = 0; b < 3; b++) {
-        float wab = w[a][0] * w[b][1];
-#pragma unroll
-        for (int c = 0; c < 3; c++) S.w[(a * 9 + b * 3 + c) * WSTR + lane] = wab * w[c][2];
-      }
-  }
-}
 
 // =============================================================================================
 // p2g
@@ -111,7 +34,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(const KParams P, const i
   const long long gw = (long long)blockIdx.x * P2G_WARPS + wib;
   const long long slot0 = gw * (32 * P2G_ROUNDS);
   if (slot0 >= P.N) return;
-  Window W; window_init(W, lane, P.n);
+  Window W; window_init(W, lane, P.n, P.blk_flags);
 #pragma unroll 1
   for (int r = 0; r < P2G_ROUNDS; r++) {
     const long long sl = slot0 + r * 32 + lane;
@@ -120,7 +43,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(const KParams P, const i
     const int cnt = rem < 32 ? (int)rem : 32;
     int key = -1;
     float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, m = 0.f;
-    float w[3][3];
+    float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     if (sl < P.N) {
       const int s = (int)sl;
       PState st; load_A(P.pa, P, f, s, st); load_F(P.pf, P.pf8, P, f, s, st.F);
@@ -137,40 +60,70 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(const KParams P, const i
         for (int i = 0; i < 9; i++) B[i] = K.A.m[i] * P.dx;
 #pragma unroll
         for (int i = 0; i < 3; i++) q[i] = m * st.v[i] - (B[i * 3] * fx[0] + B[i * 3 + 1] * fx[1] + B[i * 3 + 2] * fx[2]);
-        key = (b[0] * P.n + b[1]) * P.n + b[2];
+        key = pack_key(b);
         if (kWriteF) store_F(P.pf, P.pf8, P, f + 1, s, K.Fn);
       } else if (kWriteF) {
         store_F(P.pf, P.pf8, P, f + 1, s, st.F);  // process_unused_particles (MPM:316) / frozen out-of-grid particle
       }
     }
-    scatter_publish(S, lane, key, q, B, m, w);
+    const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
     __syncwarp();
-    window_consume(W, S, cnt, P.grid_pm);
+    window_consume(W, S, cnt, starts, P.grid_pm);
     __syncwarp();
   }
   window_flush_all(W, P.grid_pm);
 }
 
 // =============================================================================================
-// grid_op
+// sparse grid: compaction of the active 8^3-node blocks flagged by the p2g flushes, then grid_op on them
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int clear_pm) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= P.G) return;
-  const float4 pm = P.grid_pm[g];
-  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (pm.w > FMPM_EPS) {
-    const float inv_m = 1.f / pm.w;
-    float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
-    const int n = P.n;
-    const int i = g / (n * n), j = (g / n) % n, k = g % n;
-    const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
-    float fac[3];
-    boundary_v(P, pos, v, fac);
-    out = make_float4(v[0], v[1], v[2], 0.f);
+__global__ void __launch_bounds__(1024) k_compact_blocks(const KParams P) {
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const int nblk = P.nb * P.nb * P.nb;
+  for (int base = 0; base < nblk; base += 1024) {
+    const int b = base + threadIdx.x;
+    const bool on = b < nblk && P.blk_flags[b] != 0;
+    if (on) P.blk_flags[b] = 0;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    int off = 0;
+    if ((threadIdx.x & 31) == 0 && m) off = atomicAdd(&s_count, __popc(m));
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (on) P.blk_list[off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = b;
   }
-  P.grid_v[g] = out;
-  if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (threadIdx.x == 0) P.blk_count[0] = s_count;
+}
+
+// MPM:380-398 on the active blocks; optionally clears the (momentum, mass) accumulators for the next substep
+// and zeroes the v_out adjoint of the same blocks (backward pass).
+__global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int clear_pm, const int zero_ggv) {
+  const int count = P.blk_count[0];
+  const int n = P.n, nb = P.nb;
+  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
+    const int blk = P.blk_list[bi];
+    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int t = threadIdx.x + r * 256;
+      const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+      const int g = (i * n + j) * n + k;
+      const float4 pm = P.grid_pm[g];
+      float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pm.w > FMPM_EPS) {
+        const float inv_m = 1.f / pm.w;
+        float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
+        const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
+        float fac[3];
+        boundary_v(P, pos, v, fac);
+        out = make_float4(v[0], v[1], v[2], 0.f);
+      }
+      P.grid_v[g] = out;
+      if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zero_ggv) P.ggrid_v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
 }
 
 // =============================================================================================
@@ -191,29 +144,43 @@ __global__ void __launch_bounds__(128) k_g2p(const KParams P, const int f) {
     P.pa[pa_idx(P, f + 1, 3, s)] = P.pa[pa_idx(P, f, 3, s)];
     return;
   }
+  // Separable evaluation of  v' = sum w g,  C' = 4 inv_dx sum w g (o - fx)^T  (MPM:409-416): reduce the three nodes of
+  // a z-column first (G0 = sum_k wz g, G1 = sum_k wz (k - fz) g), then fold the 9 columns in.  Packed FFMA2 throughout.
   float w[3][3]; bspline(fx, w);
-  float nv[3] = {0.f, 0.f, 0.f};
-  Mat3 nC = m3_zero();
+  const float2 wz0 = make_float2(w[0][2], w[0][2]), wz1 = make_float2(w[1][2], w[1][2]), wz2 = make_float2(w[2][2], w[2][2]);
+  const float wd0 = w[0][2] * (0.f - fx[2]), wd1 = w[1][2] * (1.f - fx[2]), wd2 = w[2][2] * (2.f - fx[2]);
+  const float2 wzd0 = make_float2(wd0, wd0), wzd1 = make_float2(wd1, wd1), wzd2 = make_float2(wd2, wd2);
+  const float2 wzz0 = make_float2(w[0][2], wd0), wzz1 = make_float2(w[1][2], wd1), wzz2 = make_float2(w[2][2], wd2);
+  float2 v01 = make_float2(0.f, 0.f);        // (v'_0, v'_1)
+  float2 v2c22 = make_float2(0.f, 0.f);      // (v'_2, S_22)
+  float2 c02_12 = make_float2(0.f, 0.f);     // (S_02, S_12)
+  float2 c00_10 = make_float2(0.f, 0.f), c01_11 = make_float2(0.f, 0.f), c20_21 = make_float2(0.f, 0.f);
   const float4* __restrict__ gv = P.grid_v + ((b[0] * P.n + b[1]) * P.n + b[2]);
-  const float c4 = 4.f * P.inv_dx;
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      const float wij = w[i][0] * w[j][1];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const float4 g = __ldg(gv + (i * P.n + j) * P.n + k);
-        const float wt = wij * w[k][2];
-        const float d0 = (float)i - fx[0], d1 = (float)j - fx[1], d2 = (float)k - fx[2];
-        const float wg0 = wt * g.x, wg1 = wt * g.y, wg2 = wt * g.z;
-        nv[0] += wg0; nv[1] += wg1; nv[2] += wg2;
-        const float s0 = c4 * wg0, s1 = c4 * wg1, s2 = c4 * wg2;
-        nC.m[0] = fmaf(s0, d0, nC.m[0]); nC.m[1] = fmaf(s0, d1, nC.m[1]); nC.m[2] = fmaf(s0, d2, nC.m[2]);
-        nC.m[3] = fmaf(s1, d0, nC.m[3]); nC.m[4] = fmaf(s1, d1, nC.m[4]); nC.m[5] = fmaf(s1, d2, nC.m[5]);
-        nC.m[6] = fmaf(s2, d0, nC.m[6]); nC.m[7] = fmaf(s2, d1, nC.m[7]); nC.m[8] = fmaf(s2, d2, nC.m[8]);
-      }
+      const float4* col = gv + (i * P.n + j) * P.n;
+      const float4 g0 = __ldg(col), g1 = __ldg(col + 1), g2 = __ldg(col + 2);
+      float2 G0xy = fmul2(make_float2(g0.x, g0.y), wz0); G0xy = ffma2(make_float2(g1.x, g1.y), wz1, G0xy); G0xy = ffma2(make_float2(g2.x, g2.y), wz2, G0xy);
+      float2 G1xy = fmul2(make_float2(g0.x, g0.y), wzd0); G1xy = ffma2(make_float2(g1.x, g1.y), wzd1, G1xy); G1xy = ffma2(make_float2(g2.x, g2.y), wzd2, G1xy);
+      float2 Gz = fmul2(make_float2(g0.z, g0.z), wzz0); Gz = ffma2(make_float2(g1.z, g1.z), wzz1, Gz); Gz = ffma2(make_float2(g2.z, g2.z), wzz2, Gz);  // (G0_z, G1_z)
+      const float wxy = w[i][0] * w[j][1];
+      const float bx = wxy * ((float)i - fx[0]), by = wxy * ((float)j - fx[1]);
+      const float2 a2 = make_float2(wxy, wxy);
+      v01 = ffma2(a2, G0xy, v01);
+      v2c22 = ffma2(a2, Gz, v2c22);
+      c02_12 = ffma2(a2, G1xy, c02_12);
+      c00_10 = ffma2(make_float2(bx, bx), G0xy, c00_10);
+      c01_11 = ffma2(make_float2(by, by), G0xy, c01_11);
+      c20_21 = ffma2(make_float2(bx, by), make_float2(Gz.x, Gz.x), c20_21);
     }
+  const float c4 = 4.f * P.inv_dx;
+  const float nv[3] = {v01.x, v01.y, v2c22.x};
+  Mat3 nC;
+  nC.m[0] = c4 * c00_10.x; nC.m[1] = c4 * c01_11.x; nC.m[2] = c4 * c02_12.x;
+  nC.m[3] = c4 * c00_10.y; nC.m[4] = c4 * c01_11.y; nC.m[5] = c4 * c02_12.y;
+  nC.m[6] = c4 * c20_21.x; nC.m[7] = c4 * c20_21.y; nC.m[8] = c4 * v2c22.y;
   const float nx[3] = {x[0] + P.dt * nv[0], x[1] + P.dt * nv[1], x[2] + P.dt * nv[2]};  // advect_kernel MPM:505
   store_A(P.pa, P, f + 1, s, nx, meta, nv, nC);
 }
@@ -285,13 +252,22 @@ extern "C" int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream) {
   return 0;
 }
 
-extern "C" int fmpm_grid_op(FmpmHandle* h, int f, int clear_pm, void* stream) {
-  (void)f;
+int fmpm_grid_op_impl(FmpmHandle* h, int clear_pm, int zero_ggv, void* stream) {
   if (check_bound(h, "fmpm_grid_op")) return 1;
   KParams P = make_kparams(h);
-  k_grid_op<<<(P.G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, clear_pm);
+  if (!P.blk_flags || !P.blk_list || !P.blk_count) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block buffers were not bound"); return 1; }
+  if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
+  k_compact_blocks<<<1, 1024, 0, (cudaStream_t)stream>>>(P);
+  FMPM_CHECK_LAUNCH(h, "fmpm_grid_op(compact)");
+  const int nblk = P.nb * P.nb * P.nb;
+  const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  k_grid_op<<<grid, 256, 0, (cudaStream_t)stream>>>(P, clear_pm, zero_ggv);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op");
   return 0;
+}
+extern "C" int fmpm_grid_op(FmpmHandle* h, int f, int clear_pm, void* stream) {
+  (void)f;
+  return fmpm_grid_op_impl(h, clear_pm, 0, stream);
 }
 
 extern "C" int fmpm_g2p(FmpmHandle* h, int f, void* stream) {

@@ -1,0 +1,146 @@
+// fmpm_scatter.cuh — register sliding-window scatter shared by p2g (momentum + mass) and the g2p adjoint
+// (v_out adjoint).  See fmpm_forward.cu for the rationale (no shared-memory float atomics on sm_100a).
+//
+// Two modes alternate inside a warp:
+//   particle mode  lane = particle slot: constitutive math, then `scatter_publish` stages per particle
+//                  (q, B, m) + its 27 stencil weights + its cell key into the warp's shared staging area and
+//                  derives, with ballots, the bit mask of positions where a new cell starts;
+//   node mode      lane = stencil node (a,b,c) (27 of 32 lanes): `window_consume` walks the staged particles
+//                  run by run (all particles of a run share one cell, so the inner loop has no branches:
+//                  4 LDS.128 + 1 LDS + 8 packed FFMA2 per particle) accumulating
+//                       acc(a,b,c) += w_abc * ( q + B·(a,b,c) ),   acc.m += w_abc * m
+//                  in registers; at a run boundary the window either shifts one cell along z (shuffle, flush of the
+//                  finished 3x3 plane) or is flushed entirely — flushes are REDG.E.ADD.F32x4 vector reductions.
+#pragma once
+#include <cuda_runtime.h>
+
+#define SC_FULL 0xffffffffu
+#define SC_WSTR 33
+
+__device__ __forceinline__ void red_add_v4(float4* addr, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {  // Blackwell packed fp32 FMA (FFMA2)
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
+        "l"(reinterpret_cast<const unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+  return d;
+}
+
+struct __align__(16) ScatterSmem {
+  float4 rec[32 * 4];          // per particle: (q0,q1,q2,m) (B00,B10,B20,0) (B01,B11,B21,0) (B02,B12,B22,0)
+  float w[27 * SC_WSTR + 5];   // w[node*33 + particle]: conflict-free for lane=particle stores and lane=node loads
+  int key[32];
+};
+
+// cell keys are the packed base coordinates (bx << 20 | by << 10 | bz), n_grid <= 1024
+__device__ __forceinline__ int pack_key(const int* b) { return (b[0] << 20) | (b[1] << 10) | b[2]; }
+
+struct Window {
+  float2 acc01, acc2m;   // (x,y) and (z,mass) accumulators of this lane's stencil node
+  int cur_key;           // packed cell whose 27 nodes the window currently covers (-1 = empty)
+  float oa, ob, oc; int a, b, c; bool lane_valid; int wrow;
+  int n, nb; int* flags; // grid size, blocks per dim, active-block flags (nullptr: do not flag)
+};
+__device__ __forceinline__ void window_init(Window& W, const int lane, const int n, int* flags) {
+  const int L = lane < 27 ? lane : 26;
+  const int a = L / 9, b = (L / 3) % 3, c = L % 3;
+  W.oa = (float)a; W.ob = (float)b; W.oc = (float)c; W.a = a; W.b = b; W.c = c;
+  W.lane_valid = lane < 27;
+  W.wrow = L * SC_WSTR;
+  W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
+  W.cur_key = -1;
+  W.n = n; W.nb = n >> 3; W.flags = flags;
+}
+// flush this lane's node sum of the current cell: one vector reduction, and flag the 8^3-node block it lands in
+__device__ __forceinline__ void window_red(const Window& W, float4* __restrict__ grid, const float4& v) {
+  const int i = (W.cur_key >> 20) + W.a, j = ((W.cur_key >> 10) & 1023) + W.b, k = (W.cur_key & 1023) + W.c;
+  red_add_v4(grid + ((i * W.n + j) * W.n + k), v);
+  if (W.flags) W.flags[((i >> 3) * W.nb + (j >> 3)) * W.nb + (k >> 3)] = 1;
+}
+__device__ __forceinline__ void window_flush_all(Window& W, float4* __restrict__ grid) {
+  if (W.cur_key >= 0 && W.lane_valid) window_red(W, grid, make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y));
+  W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
+  W.cur_key = -1;
+}
+// move the window to cell `key` (warp-uniform)
+__device__ __forceinline__ void window_move(Window& W, const int key, float4* __restrict__ grid) {
+  if (W.cur_key >= 0) {
+    const float4 v = make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y);
+    if (key == W.cur_key + 1) {  // next cell of the same z-column: plane c=0 is complete, shift the other two
+      if (W.lane_valid && W.c == 0) window_red(W, grid, v);
+      float4 t;
+      t.x = __shfl_down_sync(SC_FULL, v.x, 1); t.y = __shfl_down_sync(SC_FULL, v.y, 1);
+      t.z = __shfl_down_sync(SC_FULL, v.z, 1); t.w = __shfl_down_sync(SC_FULL, v.w, 1);
+      const bool z = (W.c == 2) || !W.lane_valid;
+      W.acc01 = z ? make_float2(0.f, 0.f) : make_float2(t.x, t.y);
+      W.acc2m = z ? make_float2(0.f, 0.f) : make_float2(t.z, t.w);
+    } else {
+      if (W.lane_valid) window_red(W, grid, v);
+      W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
+    }
+  }
+  W.cur_key = key;
+}
+
+// lane = particle.  key < 0: the particle contributes nothing (unused / out of grid / beyond N).
+// Returns the mask of staged positions at which a new cell run starts.  ALL 32 lanes must call.
+__device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int lane, const int key, const int carry_key, const float* q,
+                                                    const float* B, const float m, const float w[3][3]) {
+  S.rec[lane * 4 + 0] = make_float4(q[0], q[1], q[2], m);
+  S.rec[lane * 4 + 1] = make_float4(B[0], B[3], B[6], 0.f);
+  S.rec[lane * 4 + 2] = make_float4(B[1], B[4], B[7], 0.f);
+  S.rec[lane * 4 + 3] = make_float4(B[2], B[5], B[8], 0.f);
+  const bool valid = key >= 0;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const float wab = valid ? w[a][0] * w[b][1] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; c++) S.w[(a * 9 + b * 3 + c) * SC_WSTR + lane] = valid ? wab * w[c][2] : 0.f;
+    }
+  // effective key: a particle without a cell inherits the key of the nearest earlier one (it adds zeros to that run)
+  const unsigned V = __ballot_sync(SC_FULL, valid);
+  const unsigned below = V & (0xffffffffu >> (31 - lane));
+  const int src = below ? 31 - __clz(below) : 0;
+  const int ksrc = __shfl_sync(SC_FULL, key, src);
+  const int keff = below ? ksrc : carry_key;
+  int prev = __shfl_up_sync(SC_FULL, keff, 1);
+  if (lane == 0) prev = carry_key;
+  S.key[lane] = keff;
+  return __ballot_sync(SC_FULL, keff != prev);
+}
+
+// lane = stencil node.  Consumes `cnt` staged particles; `starts` from scatter_publish.
+__device__ __forceinline__ void window_consume(Window& W, const ScatterSmem& S, const int cnt, const unsigned starts, float4* __restrict__ grid) {
+  const float2 oa2 = make_float2(W.oa, W.oa), ob2 = make_float2(W.ob, W.ob), oc2 = make_float2(W.oc, W.oc);
+  int j = 0;
+  while (j < cnt) {
+    if ((starts >> j) & 1u) window_move(W, S.key[j], grid);
+    const unsigned rest = (j < 31) ? (starts >> (j + 1)) : 0u;
+    int end = rest ? (j + __ffs(rest)) : cnt;
+    end = end < cnt ? end : cnt;
+#pragma unroll 2
+    for (int p = j; p < end; p++) {
+      const float4 r0 = S.rec[p * 4], r1 = S.rec[p * 4 + 1], r2 = S.rec[p * 4 + 2], r3 = S.rec[p * 4 + 3];
+      const float w = S.w[W.wrow + p];
+      const float2 w2 = make_float2(w, w);
+      float2 t01 = ffma2(make_float2(r1.x, r1.y), oa2, make_float2(r0.x, r0.y));
+      float2 t2m = ffma2(make_float2(r1.z, r1.w), oa2, make_float2(r0.z, r0.w));
+      t01 = ffma2(make_float2(r2.x, r2.y), ob2, t01); t2m = ffma2(make_float2(r2.z, r2.w), ob2, t2m);
+      t01 = ffma2(make_float2(r3.x, r3.y), oc2, t01); t2m = ffma2(make_float2(r3.z, r3.w), oc2, t2m);
+      W.acc01 = ffma2(w2, t01, W.acc01); W.acc2m = ffma2(w2, t2m, W.acc2m);
+    }
+    j = end;
+  }
+}

@@ -161,6 +161,11 @@ class MPMSimulator:
         self._scratch_f = torch.empty((2, N, 4), dtype=f32, device=dev)
         self._scratch_f8 = torch.empty((N,), dtype=f32, device=dev)
         self._sort_bufs = [torch.empty((N,), dtype=i32, device=dev) for _ in range(4)]
+        assert self.n_grid % 8 == 0, 'n_grid must be a multiple of 8 (sparse grid blocks are 8x8x8 nodes)'
+        nblk = (self.n_grid // 8) ** 3
+        self._blk_flags = torch.zeros((nblk,), dtype=i32, device=dev)
+        self._blk_list = torch.zeros((nblk,), dtype=i32, device=dev)
+        self._blk_count = torch.zeros((1,), dtype=i32, device=dev)
         self._ga = self._gf = self._gf8 = self._ggrid_v = self._ggrid_pm = None
         # API-layout staging
         self._sx = torch.empty((N, 3), dtype=f32, device=dev); self._sv = torch.empty((N, 3), dtype=f32, device=dev)
@@ -206,6 +211,7 @@ class MPMSimulator:
         b.scratch_a, b.scratch_f, b.scratch_f8 = p(self._scratch_a), p(self._scratch_f), p(self._scratch_f8)
         b.sort_keys_in, b.sort_keys_out, b.sort_vals_in, b.sort_vals_out = [p(t) for t in self._sort_bufs]
         b.sort_tmp, b.sort_tmp_bytes = p(self._sort_tmp), self._sort_tmp.numel()
+        b.blk_flags, b.blk_list, b.blk_count = p(self._blk_flags), p(self._blk_list), p(self._blk_count)
         self._ck(self._lib.fmpm_bind(self._h, C.byref(b)), 'fmpm_bind')
 
     def _ensure_grad_buffers(self):

@@ -28,6 +28,8 @@
  *  grid        grid_pm : float4[G] (momentum xyz, mass)   — MPM:112-114 v_in, mass
  *              grid_v  : float4[G] (v_out xyz, unused)     — MPM:115
  *              ggrid_v : float4[G] adjoint of v_out;  ggrid_pm : float4[G] adjoint of (v_in, mass)
+ *              grid_v / ggrid_* are only defined on the ACTIVE 8^3-node blocks of the substep (blocks that received
+ *              mass in p2g); grid_pm is all-zero between substeps.  n_grid must be a multiple of 8.
  *  Particles are stored in SLOT order (cell-sorted); `ids[slot]` = original particle index and
  *  `inv[pid]` = slot translate at the API boundary (fmpm_read_frame / fmpm_write_frame).
  * ===================================================================================== */
@@ -74,6 +76,10 @@ typedef struct {
   void* scratch_a; void* scratch_f; void* scratch_f8;   /* one spare frame (sort / permute staging) */
   void* sort_keys_in; void* sort_keys_out; void* sort_vals_in; void* sort_vals_out; /* int[N] each */
   void* sort_tmp; unsigned long long sort_tmp_bytes;    /* >= fmpm_sort_workspace_bytes() */
+  /* sparse grid: 8x8x8-node blocks.  blk_flags int[(n_grid/8)^3] (zero-initialised by the caller), blk_list int[(n_grid/8)^3],
+   * blk_count int[1].  p2g flags the blocks it scatters into, fmpm_grid_op compacts them and every grid kernel of the
+   * substep (grid_op, clears, adjoint grid) visits only those blocks. */
+  void* blk_flags; void* blk_list; void* blk_count;
 } FmpmBuffers;
 
 /* effector pose chain, fluidlab/fluidengine/effectors/effector.py:34-51 (fields), :157-161 (move_kernel),
