@@ -46,28 +46,32 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe): ONE nvidia-smi process in
+    loop mode, started before and stopped after the timed region (forking a sampler per reading perturbs the launch loop)."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
-    def __init__(self, index=0):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([t.strip() for t in out.split(',')])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+    def __init__(self, index=0, period_ms=50):
+        self.index, self.period_ms, self.samples, self.proc = index, period_ms, [], None
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True); self._t.start(); return self
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index),
+                                          '-lms', str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)  # let it start sampling before the timed region
+        except Exception:
+            self.proc = None
+        return self
 
     def __exit__(self, *a):
-        self._stop.set(); self._t.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill(); out = ''
+            for line in out.strip().splitlines():
+                self.samples.append([t.strip() for t in line.split(',')])
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s and s[0].replace('.', '').isdigit()]
@@ -138,7 +142,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--particles', type=int, default=N_PARTICLES)
@@ -204,15 +208,20 @@ def main():
     used = int(sim.readframe_torch(f, ('used',))['used'].sum().item())
 
     def time_phase(fn, n=20, pre=None):
-        tot = 0.0
-        for i in range(n + 3):
-            if pre:
-                pre()
+        """average device time of fn(): n back-to-back launches between two events (no per-launch event overhead);
+        a `pre` callable (e.g. the grid clear) runs before every fn() and its own batched time is subtracted."""
+        def batch(body):
+            for _ in range(3):
+                body()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record(); torch.cuda.synchronize()
-            if i >= 3:
-                tot += a.elapsed_time(b)
-        return tot / n
+            torch.cuda.synchronize(); a.record()
+            for _ in range(n):
+                body()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        if pre is None:
+            return batch(fn)
+        return batch(lambda: (pre(), fn())) - batch(pre)
 
     t_p2g = time_phase(lambda: sim.phase('p2g', f, 0), pre=lambda: sim.phase('clear_grid', f))
     sim.phase('clear_grid', f); sim.phase('p2g', f, 0)

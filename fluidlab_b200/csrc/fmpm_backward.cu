@@ -180,12 +180,84 @@ __device__ __forceinline__ Mat3 constitutive_grad(const KParams& P, const Consti
   return gFt;
 }
 
-__global__ void __launch_bounds__(128) k_particle_grad(const KParams P, const int f, const int gin, const int gout) {
+#define PG_WARPS 4
+
+// Adjoint gather on the 27 stencil nodes, column-factored.  With g_i = v_out (forward), a_i = adjoint of v_in, am_i = adjoint
+// of mass, delta_i = o_i - fx, Mg = 4 inv_dx gC', Ma = A dx:
+//   vp    = sum w g                      (the forward v')
+//   gvp   = sum w a ,  S_ao = sum w a (x) o
+//   gfx   = -Mg^T vp - Ma^T gvp + sum_i s_i grad(w_i),   s_i = g_i.(gve + Mg delta_i) + a_i.(m v + Ma delta_i) + m am_i
+// (SURVEY.md Appendix A g2p.grad + p2g.grad particle side, regrouped so the z-direction is reduced first.)
+template <class ColG, class ColA>
+__device__ __forceinline__ void adjoint_gather(const float* fx, const float w[3][3], const float dw[3][3], ColG colg, ColA cola,
+                                               const float* gve, const Mat3& Mg, const float* mv, const Mat3& Ma, const float m,
+                                               float* vp, float* gvp, Mat3& S_ao, float* gfx) {
+  float a0[3], b0[3];  // coefficient bases: alpha0 = gve - Mg fx, beta0 = m v - Ma fx
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    a0[r] = gve[r] - (Mg.m[r * 3] * fx[0] + Mg.m[r * 3 + 1] * fx[1] + Mg.m[r * 3 + 2] * fx[2]);
+    b0[r] = mv[r] - (Ma.m[r * 3] * fx[0] + Ma.m[r * 3 + 1] * fx[1] + Ma.m[r * 3 + 2] * fx[2]);
+  }
+  vp[0] = vp[1] = vp[2] = 0.f; gvp[0] = gvp[1] = gvp[2] = 0.f; gfx[0] = gfx[1] = gfx[2] = 0.f;
+  S_ao = m3_zero();
+  float sgx = 0.f, sgy = 0.f, sgz = 0.f;  // sum_i s_i grad(w_i)
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float4* cg = colg(i * 3 + j);
+      const float4* ca = cola(i * 3 + j);
+      const float wxy = w[i][0] * w[j][1], dxw = dw[i][0] * w[j][1], dyw = w[i][0] * dw[j][1];
+      float cgb[3], cab[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        cgb[r] = a0[r] + Mg.m[r * 3] * (float)i + Mg.m[r * 3 + 1] * (float)j;
+        cab[r] = b0[r] + Ma.m[r * 3] * (float)i + Ma.m[r * 3 + 1] * (float)j;
+      }
+      float G0[3] = {0.f, 0.f, 0.f}, A0[3] = {0.f, 0.f, 0.f}, A1[3] = {0.f, 0.f, 0.f};
+      float s_w = 0.f, s_dz = 0.f;  // sum_k s wz[k], sum_k s dwz[k]
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float4 g = cg[k], a = ca[k];
+        const float kk = (float)k;
+        const float sv = g.x * (cgb[0] + Mg.m[2] * kk) + g.y * (cgb[1] + Mg.m[5] * kk) + g.z * (cgb[2] + Mg.m[8] * kk) +
+                         a.x * (cab[0] + Ma.m[2] * kk) + a.y * (cab[1] + Ma.m[5] * kk) + a.z * (cab[2] + Ma.m[8] * kk) + m * a.w;
+        const float wk = w[k][2];
+        s_w = fmaf(sv, wk, s_w); s_dz = fmaf(sv, dw[k][2], s_dz);
+        G0[0] = fmaf(wk, g.x, G0[0]); G0[1] = fmaf(wk, g.y, G0[1]); G0[2] = fmaf(wk, g.z, G0[2]);
+        A0[0] = fmaf(wk, a.x, A0[0]); A0[1] = fmaf(wk, a.y, A0[1]); A0[2] = fmaf(wk, a.z, A0[2]);
+        const float wkk = wk * kk;
+        A1[0] = fmaf(wkk, a.x, A1[0]); A1[1] = fmaf(wkk, a.y, A1[1]); A1[2] = fmaf(wkk, a.z, A1[2]);
+      }
+      sgx = fmaf(dxw, s_w, sgx); sgy = fmaf(dyw, s_w, sgy); sgz = fmaf(wxy, s_dz, sgz);
+      const float wi = wxy * (float)i, wj = wxy * (float)j;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        vp[r] = fmaf(wxy, G0[r], vp[r]);
+        gvp[r] = fmaf(wxy, A0[r], gvp[r]);
+        S_ao.m[r * 3 + 0] = fmaf(wi, A0[r], S_ao.m[r * 3 + 0]);
+        S_ao.m[r * 3 + 1] = fmaf(wj, A0[r], S_ao.m[r * 3 + 1]);
+        S_ao.m[r * 3 + 2] = fmaf(wxy, A1[r], S_ao.m[r * 3 + 2]);
+      }
+    }
+  // gfx = -Mg^T vp - Ma^T gvp + sum s grad w
+  gfx[0] = sgx - (Mg.m[0] * vp[0] + Mg.m[3] * vp[1] + Mg.m[6] * vp[2]) - (Ma.m[0] * gvp[0] + Ma.m[3] * gvp[1] + Ma.m[6] * gvp[2]);
+  gfx[1] = sgy - (Mg.m[1] * vp[0] + Mg.m[4] * vp[1] + Mg.m[7] * vp[2]) - (Ma.m[1] * gvp[0] + Ma.m[4] * gvp[1] + Ma.m[7] * gvp[2]);
+  gfx[2] = sgz - (Mg.m[2] * vp[0] + Mg.m[5] * vp[1] + Mg.m[8] * vp[2]) - (Ma.m[2] * gvp[0] + Ma.m[5] * gvp[1] + Ma.m[8] * gvp[2]);
+}
+
+__global__ void __launch_bounds__(PG_WARPS * 32) k_particle_grad(const KParams P, const int f, const int gin, const int gout) {
+  __shared__ float4 tiles[PG_WARPS][2][9 * G2P_ZMAX];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= P.N) return;
-  PState st; load_A(P.pa, P, f, s, st);
+  float4* tg = tiles[threadIdx.x >> 5][0];
+  float4* ta = tiles[threadIdx.x >> 5][1];
+  PState st; st.meta = 0; st.x[0] = st.x[1] = st.x[2] = 0.f;
+  if (s < P.N) load_A(P.pa, P, f, s, st);
   int b[3]; float fx[3];
-  const bool ok = (st.meta & 1) && base_fx(P, st.x, b, fx);
+  const bool ok = (s < P.N) && (st.meta & 1) && base_fx(P, st.x, b, fx);
+  const Footprint fp = footprint_of(ok, b);
+  if (fp.staged) { footprint_load(P.grid_v, P.n, fp, tg); footprint_load(P.ggrid_pm, P.n, fp, ta); }
+  if (s >= P.N) return;
   if (!ok) {  // process_unused_particles.grad (MPM:551): the adjoint passes straight through
 #pragma unroll
     for (int k = 0; k < 4; k++) P.ga[pa_idx(P, gout, k, s)] = P.ga[pa_idx(P, gin, k, s)];
@@ -195,62 +267,41 @@ __global__ void __launch_bounds__(128) k_particle_grad(const KParams P, const in
     return;
   }
   load_F(P.pf, P.pf8, P, f, s, st.F);
-  GState g; load_grad(P, gin, s, g);
   const float4 mt = __ldg(P.mats + ((st.meta >> 8) & 0xff));
   const float mu = mt.x, lam = mt.y, m = mt.z; const int cls = __float_as_int(mt.w);
   Constit K; constitutive(P, st, mu, lam, m, cls, K);
   float w[3][3], dw[3][3]; bspline(fx, w); bspline_d(fx, dw);
-  // advect_kernel.grad (MPM:443): gx += gx', gv' += dt * gx'
-  const float gve[3] = {g.v[0] + P.dt * g.x[0], g.v[1] + P.dt * g.x[1], g.v[2] + P.dt * g.x[2]};
-  const float c4 = 4.f * P.inv_dx;
-  float gfx[3] = {0.f, 0.f, 0.f}, gvp[3] = {0.f, 0.f, 0.f};
-  Mat3 gA = m3_zero();
-  const int cell = (b[0] * P.n + b[1]) * P.n + b[2];
-  const float4* __restrict__ gvo = P.grid_v + cell;
-  const float4* __restrict__ gpm = P.ggrid_pm + cell;
+  float gxin[3], gve[3], mv[3];
+  Mat3 Mg, Ma;
+  {
+    PState g; load_A(P.ga, P, gin, s, g);  // (gx', gv', gC')
+    const float c4 = 4.f * P.inv_dx;
 #pragma unroll
-  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) { gxin[k] = g.x[k]; gve[k] = g.v[k] + P.dt * g.x[k]; mv[k] = m * st.v[k]; }  // advect_kernel.grad (MPM:443)
 #pragma unroll
-    for (int j = 0; j < 3; j++)
+    for (int k = 0; k < 9; k++) { Mg.m[k] = c4 * g.C.m[k]; Ma.m[k] = K.A.m[k] * P.dx; }
+  }
+  float vp[3], gvp[3], gfx[3]; Mat3 S_ao;
+  if (fp.staged) {
+    const int zo = b[2] - fp.kmin;
+    adjoint_gather(fx, w, dw, [&](int c) { return tg + c * G2P_ZMAX + zo; }, [&](int c) { return ta + c * G2P_ZMAX + zo; }, gve, Mg, mv, Ma, m, vp, gvp, S_ao, gfx);
+  } else {
+    const int cell = (b[0] * P.n + b[1]) * P.n + b[2];
+    const float4* gvo = P.grid_v + cell; const float4* gpm = P.ggrid_pm + cell; const int n = P.n;
+    adjoint_gather(fx, w, dw, [&](int c) { return gvo + ((c / 3) * n + (c % 3)) * n; }, [&](int c) { return gpm + ((c / 3) * n + (c % 3)) * n; }, gve, Mg, mv, Ma, m, vp, gvp, S_ao, gfx);
+  }
+  // gA = sum w a (x) d,  d = (o - fx) dx
+  Mat3 gA;
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int off = (i * P.n + j) * P.n + k;
-        const float4 gg = __ldg(gvo + off);   // forward v_out
-        const float4 ga = __ldg(gpm + off);   // adjoint of (v_in, mass)
-        const float wt = w[i][0] * w[j][1] * w[k][2];
-        const float del[3] = {(float)i - fx[0], (float)j - fx[1], (float)k - fx[2]};
-        const float gwv[3] = {dw[i][0] * w[j][1] * w[k][2], w[i][0] * dw[j][1] * w[k][2], w[i][0] * w[j][1] * dw[k][2]};
-        // ---- g2p.grad, particle side
-        const float Cd0 = g.C.m[0] * del[0] + g.C.m[1] * del[1] + g.C.m[2] * del[2];
-        const float Cd1 = g.C.m[3] * del[0] + g.C.m[4] * del[1] + g.C.m[5] * del[2];
-        const float Cd2 = g.C.m[6] * del[0] + g.C.m[7] * del[1] + g.C.m[8] * del[2];
-        float wbar = gg.x * (gve[0] + c4 * Cd0) + gg.y * (gve[1] + c4 * Cd1) + gg.z * (gve[2] + c4 * Cd2);
-        const float Ctg0 = g.C.m[0] * gg.x + g.C.m[3] * gg.y + g.C.m[6] * gg.z;
-        const float Ctg1 = g.C.m[1] * gg.x + g.C.m[4] * gg.y + g.C.m[7] * gg.z;
-        const float Ctg2 = g.C.m[2] * gg.x + g.C.m[5] * gg.y + g.C.m[8] * gg.z;
-        float dbar0 = -c4 * wt * Ctg0, dbar1 = -c4 * wt * Ctg1, dbar2 = -c4 * wt * Ctg2;  // contribution to gfx through (o - fx)
-        // ---- p2g.grad, particle side (d_i = del * dx)
-        const float d0 = del[0] * P.dx, d1 = del[1] * P.dx, d2 = del[2] * P.dx;
-        const float Ad0 = K.A.m[0] * d0 + K.A.m[1] * d1 + K.A.m[2] * d2;
-        const float Ad1 = K.A.m[3] * d0 + K.A.m[4] * d1 + K.A.m[5] * d2;
-        const float Ad2 = K.A.m[6] * d0 + K.A.m[7] * d1 + K.A.m[8] * d2;
-        wbar += ga.x * (m * st.v[0] + Ad0) + ga.y * (m * st.v[1] + Ad1) + ga.z * (m * st.v[2] + Ad2) + m * ga.w;
-        const float Atg0 = K.A.m[0] * ga.x + K.A.m[3] * ga.y + K.A.m[6] * ga.z;
-        const float Atg1 = K.A.m[1] * ga.x + K.A.m[4] * ga.y + K.A.m[7] * ga.z;
-        const float Atg2 = K.A.m[2] * ga.x + K.A.m[5] * ga.y + K.A.m[8] * ga.z;
-        dbar0 -= P.dx * wt * Atg0; dbar1 -= P.dx * wt * Atg1; dbar2 -= P.dx * wt * Atg2;
-        gfx[0] += dbar0 + wbar * gwv[0]; gfx[1] += dbar1 + wbar * gwv[1]; gfx[2] += dbar2 + wbar * gwv[2];
-        const float wg0 = wt * ga.x, wg1 = wt * ga.y, wg2 = wt * ga.z;
-        gvp[0] += wg0; gvp[1] += wg1; gvp[2] += wg2;
-        gA.m[0] = fmaf(wg0, d0, gA.m[0]); gA.m[1] = fmaf(wg0, d1, gA.m[1]); gA.m[2] = fmaf(wg0, d2, gA.m[2]);
-        gA.m[3] = fmaf(wg1, d0, gA.m[3]); gA.m[4] = fmaf(wg1, d1, gA.m[4]); gA.m[5] = fmaf(wg1, d2, gA.m[5]);
-        gA.m[6] = fmaf(wg2, d0, gA.m[6]); gA.m[7] = fmaf(wg2, d1, gA.m[7]); gA.m[8] = fmaf(wg2, d2, gA.m[8]);
-      }
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) gA.m[r * 3 + c] = P.dx * (S_ao.m[r * 3 + c] - gvp[r] * fx[c]);
   float ox[3], ov[3];
 #pragma unroll
-  for (int k = 0; k < 3; k++) { ox[k] = g.x[k] + P.inv_dx * gfx[k]; ov[k] = m * gvp[k]; }
-  Mat3 gFt = constitutive_grad(P, K, mu, lam, cls, gA, g.F);
-  // compute_F_tmp.grad (MPM:546): gC += dt * gFt Fᵀ ; gF += (I + dt C)ᵀ gFt ; plus gC += m * gA
+  for (int k = 0; k < 3; k++) { ox[k] = gxin[k] + P.inv_dx * gfx[k]; ov[k] = m * gvp[k]; }
+  Mat3 gFn; load_F(P.gf, P.gf8, P, gin, s, gFn);
+  Mat3 gFt = constitutive_grad(P, K, mu, lam, cls, gA, gFn);
+  // compute_F_tmp.grad (MPM:546): gC += dt * gFt F^T ; gF += (I + dt C)^T gFt ; plus gC += m * gA
   Mat3 oC = m3_add(m3_scale(gA, m), m3_scale(m3_mul_nt(gFt, st.F), P.dt));
   Mat3 IdC;
 #pragma unroll
@@ -314,7 +365,7 @@ extern "C" int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void*
   if (check_bound_b(h, "fmpm_particle_grad")) return 1;
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_particle_grad<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f, gin, gout);
+  k_particle_grad<<<(P.N + PG_WARPS * 32 - 1) / (PG_WARPS * 32), PG_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f, gin, gout);
   FMPM_CHECK_LAUNCH(h, "fmpm_particle_grad");
   return 0;
 }

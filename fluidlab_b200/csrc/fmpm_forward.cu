@@ -20,14 +20,40 @@
 
 #include "fmpm_scatter.cuh"
 
+#ifndef P2G_WARPS
 #define P2G_WARPS 4
+#endif
+#ifndef P2G_ROUNDS
 #define P2G_ROUNDS 4
+#endif
+#ifndef P2G_MINB
+#define P2G_MINB 1
+#endif
 
 // =============================================================================================
 // p2g
 // =============================================================================================
+struct PRaw { float4 a0, a1, a2, a3, f0, f1; float f8; };
+__device__ __forceinline__ void p2g_load_raw(const KParams& P, const int f, const long long sl, PRaw& R) {
+  if (sl < P.N) {
+    const int s = (int)sl;
+    R.a0 = P.pa[pa_idx(P, f, 0, s)]; R.a1 = P.pa[pa_idx(P, f, 1, s)]; R.a2 = P.pa[pa_idx(P, f, 2, s)]; R.a3 = P.pa[pa_idx(P, f, 3, s)];
+    R.f0 = P.pf[pf_idx(P, f, 0, s)]; R.f1 = P.pf[pf_idx(P, f, 1, s)]; R.f8 = P.pf8[pf8_idx(P, f, s)];
+  } else {
+    R.a0 = make_float4(0.f, 0.f, 0.f, 0.f);  // meta = 0 -> unused
+  }
+}
+__device__ __forceinline__ void p2g_unpack(const PRaw& R, PState& st) {
+  st.x[0] = R.a0.x; st.x[1] = R.a0.y; st.x[2] = R.a0.z; st.meta = __float_as_int(R.a0.w);
+  st.v[0] = R.a1.x; st.v[1] = R.a1.y; st.v[2] = R.a1.z;
+  st.C.m[0] = R.a1.w; st.C.m[1] = R.a2.x; st.C.m[2] = R.a2.y; st.C.m[3] = R.a2.z; st.C.m[4] = R.a2.w;
+  st.C.m[5] = R.a3.x; st.C.m[6] = R.a3.y; st.C.m[7] = R.a3.z; st.C.m[8] = R.a3.w;
+  st.F.m[0] = R.f0.x; st.F.m[1] = R.f0.y; st.F.m[2] = R.f0.z; st.F.m[3] = R.f0.w;
+  st.F.m[4] = R.f1.x; st.F.m[5] = R.f1.y; st.F.m[6] = R.f1.z; st.F.m[7] = R.f1.w; st.F.m[8] = R.f8;
+}
+
 template <bool kWriteF>
-__global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(const KParams P, const int f) {
+__global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams P, const int f) {
   __shared__ ScatterSmem smem[P2G_WARPS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   ScatterSmem& S = smem[wib];
@@ -35,6 +61,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(const KParams P, const i
   const long long slot0 = gw * (32 * P2G_ROUNDS);
   if (slot0 >= P.N) return;
   Window W; window_init(W, lane, P.n, P.blk_flags);
+  PRaw R; p2g_load_raw(P, f, slot0 + lane, R);
 #pragma unroll 1
   for (int r = 0; r < P2G_ROUNDS; r++) {
     const long long sl = slot0 + r * 32 + lane;
@@ -46,7 +73,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(const KParams P, const i
     float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     if (sl < P.N) {
       const int s = (int)sl;
-      PState st; load_A(P.pa, P, f, s, st); load_F(P.pf, P.pf8, P, f, s, st.F);
+      PState st; p2g_unpack(R, st);
       int b[3]; float fx[3];
       const bool used = st.meta & 1;
       const bool ok = used && base_fx(P, st.x, b, fx);
@@ -67,6 +94,8 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(const KParams P, const i
       }
     }
     const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
+    // software pipelining: the next round's 100 B/particle are in flight while this round is scattered
+    if (r + 1 < P2G_ROUNDS) p2g_load_raw(P, f, sl + 32, R);
     __syncwarp();
     window_consume(W, S, cnt, starts, P.grid_pm);
     __syncwarp();
@@ -129,39 +158,25 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int clea
 // =============================================================================================
 // g2p (+ advect_used, process_unused_particles, advect_kernel)
 // =============================================================================================
-__global__ void __launch_bounds__(128) k_g2p(const KParams P, const int f) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= P.N) return;
-  const float4 a0 = P.pa[pa_idx(P, f, 0, s)];
-  const int meta = __float_as_int(a0.w);
-  const float x[3] = {a0.x, a0.y, a0.z};
-  int b[3]; float fx[3];
-  const bool ok = (meta & 1) && base_fx(P, x, b, fx);
-  if (!ok) {  // unused (MPM:309-316) or frozen: carry the state over unchanged
-    P.pa[pa_idx(P, f + 1, 0, s)] = a0;
-    P.pa[pa_idx(P, f + 1, 1, s)] = P.pa[pa_idx(P, f, 1, s)];
-    P.pa[pa_idx(P, f + 1, 2, s)] = P.pa[pa_idx(P, f, 2, s)];
-    P.pa[pa_idx(P, f + 1, 3, s)] = P.pa[pa_idx(P, f, 3, s)];
-    return;
-  }
-  // Separable evaluation of  v' = sum w g,  C' = 4 inv_dx sum w g (o - fx)^T  (MPM:409-416): reduce the three nodes of
-  // a z-column first (G0 = sum_k wz g, G1 = sum_k wz (k - fz) g), then fold the 9 columns in.  Packed FFMA2 throughout.
-  float w[3][3]; bspline(fx, w);
+#define G2P_WARPS 4
+
+// Separable evaluation of  v' = sum w g,  C' = 4 inv_dx sum w g (o - fx)^T  (MPM:409-416): reduce the three nodes of a
+// z-column first (G0 = sum_k wz g, G1 = sum_k wz (k - fz) g), then fold the 9 columns in.  Packed FFMA2 throughout.
+// `col(c)` returns a pointer to the three consecutive v_out nodes of stencil column c = i*3+j for this particle.
+template <class ColFn>
+__device__ __forceinline__ void g2p_gather(const float* fx, const float w[3][3], ColFn col, float* nv, Mat3& nC, const float c4) {
   const float2 wz0 = make_float2(w[0][2], w[0][2]), wz1 = make_float2(w[1][2], w[1][2]), wz2 = make_float2(w[2][2], w[2][2]);
   const float wd0 = w[0][2] * (0.f - fx[2]), wd1 = w[1][2] * (1.f - fx[2]), wd2 = w[2][2] * (2.f - fx[2]);
   const float2 wzd0 = make_float2(wd0, wd0), wzd1 = make_float2(wd1, wd1), wzd2 = make_float2(wd2, wd2);
   const float2 wzz0 = make_float2(w[0][2], wd0), wzz1 = make_float2(w[1][2], wd1), wzz2 = make_float2(w[2][2], wd2);
-  float2 v01 = make_float2(0.f, 0.f);        // (v'_0, v'_1)
-  float2 v2c22 = make_float2(0.f, 0.f);      // (v'_2, S_22)
-  float2 c02_12 = make_float2(0.f, 0.f);     // (S_02, S_12)
+  float2 v01 = make_float2(0.f, 0.f), v2c22 = make_float2(0.f, 0.f), c02_12 = make_float2(0.f, 0.f);
   float2 c00_10 = make_float2(0.f, 0.f), c01_11 = make_float2(0.f, 0.f), c20_21 = make_float2(0.f, 0.f);
-  const float4* __restrict__ gv = P.grid_v + ((b[0] * P.n + b[1]) * P.n + b[2]);
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      const float4* col = gv + (i * P.n + j) * P.n;
-      const float4 g0 = __ldg(col), g1 = __ldg(col + 1), g2 = __ldg(col + 2);
+      const float4* c = col(i * 3 + j);
+      const float4 g0 = c[0], g1 = c[1], g2 = c[2];
       float2 G0xy = fmul2(make_float2(g0.x, g0.y), wz0); G0xy = ffma2(make_float2(g1.x, g1.y), wz1, G0xy); G0xy = ffma2(make_float2(g2.x, g2.y), wz2, G0xy);
       float2 G1xy = fmul2(make_float2(g0.x, g0.y), wzd0); G1xy = ffma2(make_float2(g1.x, g1.y), wzd1, G1xy); G1xy = ffma2(make_float2(g2.x, g2.y), wzd2, G1xy);
       float2 Gz = fmul2(make_float2(g0.z, g0.z), wzz0); Gz = ffma2(make_float2(g1.z, g1.z), wzz1, Gz); Gz = ffma2(make_float2(g2.z, g2.z), wzz2, Gz);  // (G0_z, G1_z)
@@ -175,12 +190,44 @@ __global__ void __launch_bounds__(128) k_g2p(const KParams P, const int f) {
       c01_11 = ffma2(make_float2(by, by), G0xy, c01_11);
       c20_21 = ffma2(make_float2(bx, by), make_float2(Gz.x, Gz.x), c20_21);
     }
-  const float c4 = 4.f * P.inv_dx;
-  const float nv[3] = {v01.x, v01.y, v2c22.x};
-  Mat3 nC;
+  nv[0] = v01.x; nv[1] = v01.y; nv[2] = v2c22.x;
   nC.m[0] = c4 * c00_10.x; nC.m[1] = c4 * c01_11.x; nC.m[2] = c4 * c02_12.x;
   nC.m[3] = c4 * c00_10.y; nC.m[4] = c4 * c01_11.y; nC.m[5] = c4 * c02_12.y;
   nC.m[6] = c4 * c20_21.x; nC.m[7] = c4 * c20_21.y; nC.m[8] = c4 * v2c22.y;
+}
+
+__global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const int f) {
+  __shared__ float4 tiles[G2P_WARPS][9 * G2P_ZMAX];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  float4* tile = tiles[threadIdx.x >> 5];
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s < P.N) a0 = P.pa[pa_idx(P, f, 0, s)];
+  const int meta = __float_as_int(a0.w);
+  const float x[3] = {a0.x, a0.y, a0.z};
+  int b[3]; float fx[3];
+  const bool ok = (s < P.N) && (meta & 1) && base_fx(P, x, b, fx);
+  Footprint fp = footprint_of(ok, b);
+  if (fp.staged) footprint_load(P.grid_v, P.n, fp, tile);
+  const bool staged = fp.staged; const int kmin = fp.kmin;
+  if (s >= P.N) return;
+  if (!ok) {  // unused (MPM:309-316) or frozen: carry the state over unchanged
+    P.pa[pa_idx(P, f + 1, 0, s)] = a0;
+    P.pa[pa_idx(P, f + 1, 1, s)] = P.pa[pa_idx(P, f, 1, s)];
+    P.pa[pa_idx(P, f + 1, 2, s)] = P.pa[pa_idx(P, f, 2, s)];
+    P.pa[pa_idx(P, f + 1, 3, s)] = P.pa[pa_idx(P, f, 3, s)];
+    return;
+  }
+  float w[3][3]; bspline(fx, w);
+  float nv[3]; Mat3 nC;
+  const float c4 = 4.f * P.inv_dx;
+  if (staged) {
+    const float4* t0 = tile + (b[2] - kmin);
+    g2p_gather(fx, w, [&](int c) { return t0 + c * G2P_ZMAX; }, nv, nC, c4);
+  } else {
+    const float4* gv = P.grid_v + ((b[0] * P.n + b[1]) * P.n + b[2]);
+    const int n = P.n;
+    g2p_gather(fx, w, [&](int c) { return gv + ((c / 3) * n + (c % 3)) * n; }, nv, nC, c4);
+  }
   const float nx[3] = {x[0] + P.dt * nv[0], x[1] + P.dt * nv[1], x[2] + P.dt * nv[2]};  // advect_kernel MPM:505
   store_A(P.pa, P, f + 1, s, nx, meta, nv, nC);
 }
@@ -274,7 +321,7 @@ extern "C" int fmpm_g2p(FmpmHandle* h, int f, void* stream) {
   if (check_bound(h, "fmpm_g2p") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_g2p")) return 1;
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_g2p<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f);
+  k_g2p<<<(P.N + G2P_WARPS * 32 - 1) / (G2P_WARPS * 32), G2P_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f);
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p");
   return 0;
 }

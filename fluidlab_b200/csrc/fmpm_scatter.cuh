@@ -48,6 +48,7 @@ __device__ __forceinline__ int pack_key(const int* b) { return (b[0] << 20) | (b
 struct Window {
   float2 acc01, acc2m;   // (x,y) and (z,mass) accumulators of this lane's stencil node
   int cur_key;           // packed cell whose 27 nodes the window currently covers (-1 = empty)
+  int node;              // linear grid index of this lane's node for cur_key
   float oa, ob, oc; int a, b, c; bool lane_valid; int wrow;
   int n, nb; int* flags; // grid size, blocks per dim, active-block flags (nullptr: do not flag)
 };
@@ -58,38 +59,46 @@ __device__ __forceinline__ void window_init(Window& W, const int lane, const int
   W.lane_valid = lane < 27;
   W.wrow = L * SC_WSTR;
   W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
-  W.cur_key = -1;
+  W.cur_key = -1; W.node = 0;
   W.n = n; W.nb = n >> 3; W.flags = flags;
 }
-// flush this lane's node sum of the current cell: one vector reduction, and flag the 8^3-node block it lands in
-__device__ __forceinline__ void window_red(const Window& W, float4* __restrict__ grid, const float4& v) {
-  const int i = (W.cur_key >> 20) + W.a, j = ((W.cur_key >> 10) & 1023) + W.b, k = (W.cur_key & 1023) + W.c;
-  red_add_v4(grid + ((i * W.n + j) * W.n + k), v);
-  if (W.flags) W.flags[((i >> 3) * W.nb + (j >> 3)) * W.nb + (k >> 3)] = 1;
+// flag the 8^3-node block of this lane's node (test before write: the flag words are shared by every SM)
+__device__ __forceinline__ void window_flag(const Window& W, const int i, const int j, const int k) {
+  const int blk = ((i >> 3) * W.nb + (j >> 3)) * W.nb + (k >> 3);
+  if (W.flags[blk] == 0) W.flags[blk] = 1;
 }
 __device__ __forceinline__ void window_flush_all(Window& W, float4* __restrict__ grid) {
-  if (W.cur_key >= 0 && W.lane_valid) window_red(W, grid, make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y));
+  if (W.cur_key >= 0 && W.lane_valid) red_add_v4(grid + W.node, make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y));
   W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
   W.cur_key = -1;
 }
-// move the window to cell `key` (warp-uniform)
+// move the window to cell `key` (warp-uniform).  Blocks are flagged when the window is PLACED on a cell (every node of the
+// footprint receives a contribution from the cell's particles), so a z+1 shift only has to look at the new c=2 plane.
 __device__ __forceinline__ void window_move(Window& W, const int key, float4* __restrict__ grid) {
   if (W.cur_key >= 0) {
     const float4 v = make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y);
     if (key == W.cur_key + 1) {  // next cell of the same z-column: plane c=0 is complete, shift the other two
-      if (W.lane_valid && W.c == 0) window_red(W, grid, v);
+      if (W.lane_valid && W.c == 0) red_add_v4(grid + W.node, v);
       float4 t;
       t.x = __shfl_down_sync(SC_FULL, v.x, 1); t.y = __shfl_down_sync(SC_FULL, v.y, 1);
       t.z = __shfl_down_sync(SC_FULL, v.z, 1); t.w = __shfl_down_sync(SC_FULL, v.w, 1);
       const bool z = (W.c == 2) || !W.lane_valid;
       W.acc01 = z ? make_float2(0.f, 0.f) : make_float2(t.x, t.y);
       W.acc2m = z ? make_float2(0.f, 0.f) : make_float2(t.z, t.w);
-    } else {
-      if (W.lane_valid) window_red(W, grid, v);
-      W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
+      W.node += 1; W.cur_key = key;
+      if (W.flags && W.c == 2 && W.lane_valid) {
+        const int k = (key & 1023) + 2;
+        if ((k & 7) == 0) window_flag(W, (key >> 20) + W.a, ((key >> 10) & 1023) + W.b, k);
+      }
+      return;
     }
+    if (W.lane_valid) red_add_v4(grid + W.node, v);
+    W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
   }
+  const int i = (key >> 20) + W.a, j = ((key >> 10) & 1023) + W.b, k = (key & 1023) + W.c;
+  W.node = (i * W.n + j) * W.n + k;
   W.cur_key = key;
+  if (W.flags && W.lane_valid) window_flag(W, i, j, k);
 }
 
 // lane = particle.  key < 0: the particle contributes nothing (unused / out of grid / beyond N).
@@ -121,26 +130,66 @@ __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int la
   return __ballot_sync(SC_FULL, keff != prev);
 }
 
-// lane = stencil node.  Consumes `cnt` staged particles; `starts` from scatter_publish.
+// lane = stencil node.  Consumes the 32 staged particles (positions >= cnt carry zero weights, see scatter_publish)
+// in fixed groups of four: all 20 LDS of a group are issued first, then the 24 independent FFMA2 of q + B·o, and only
+// the two accumulator FFMA2 per particle form a dependent chain; run starts are a rare, warp-uniform branch.
 __device__ __forceinline__ void window_consume(Window& W, const ScatterSmem& S, const int cnt, const unsigned starts, float4* __restrict__ grid) {
   const float2 oa2 = make_float2(W.oa, W.oa), ob2 = make_float2(W.ob, W.ob), oc2 = make_float2(W.oc, W.oc);
-  int j = 0;
-  while (j < cnt) {
-    if ((starts >> j) & 1u) window_move(W, S.key[j], grid);
-    const unsigned rest = (j < 31) ? (starts >> (j + 1)) : 0u;
-    int end = rest ? (j + __ffs(rest)) : cnt;
-    end = end < cnt ? end : cnt;
-#pragma unroll 2
-    for (int p = j; p < end; p++) {
+  const int ngroups = (cnt + 3) >> 2;
+#pragma unroll 1
+  for (int g = 0; g < ngroups; g++) {
+    float2 t01[4], t2m[4], w2[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int p = g * 4 + u;
       const float4 r0 = S.rec[p * 4], r1 = S.rec[p * 4 + 1], r2 = S.rec[p * 4 + 2], r3 = S.rec[p * 4 + 3];
       const float w = S.w[W.wrow + p];
-      const float2 w2 = make_float2(w, w);
-      float2 t01 = ffma2(make_float2(r1.x, r1.y), oa2, make_float2(r0.x, r0.y));
-      float2 t2m = ffma2(make_float2(r1.z, r1.w), oa2, make_float2(r0.z, r0.w));
-      t01 = ffma2(make_float2(r2.x, r2.y), ob2, t01); t2m = ffma2(make_float2(r2.z, r2.w), ob2, t2m);
-      t01 = ffma2(make_float2(r3.x, r3.y), oc2, t01); t2m = ffma2(make_float2(r3.z, r3.w), oc2, t2m);
-      W.acc01 = ffma2(w2, t01, W.acc01); W.acc2m = ffma2(w2, t2m, W.acc2m);
+      w2[u] = make_float2(w, w);
+      float2 a = ffma2(make_float2(r1.x, r1.y), oa2, make_float2(r0.x, r0.y));
+      float2 b = ffma2(make_float2(r1.z, r1.w), oa2, make_float2(r0.z, r0.w));
+      a = ffma2(make_float2(r2.x, r2.y), ob2, a); b = ffma2(make_float2(r2.z, r2.w), ob2, b);
+      t01[u] = ffma2(make_float2(r3.x, r3.y), oc2, a); t2m[u] = ffma2(make_float2(r3.z, r3.w), oc2, b);
     }
-    j = end;
+    const unsigned sb = (starts >> (g * 4)) & 15u;
+    if (sb == 0u) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) { W.acc01 = ffma2(w2[u], t01[u], W.acc01); W.acc2m = ffma2(w2[u], t2m[u], W.acc2m); }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if ((sb >> u) & 1u) window_move(W, S.key[g * 4 + u], grid);
+        W.acc01 = ffma2(w2[u], t01[u], W.acc01); W.acc2m = ffma2(w2[u], t2m[u], W.acc2m);
+      }
+    }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-warp staging of a grid footprint for lane = particle gathers (g2p, per-particle adjoint): the 32 cell-sorted
+// particles of a warp normally sit in one z-column of cells, so their stencils cover 9 node columns x (kmax-kmin+3)
+// nodes.  The warp loads those with 9 coalesced 128-bit loads per lane into shared memory and every particle then
+// gathers its 27 nodes with LDS.128.  Warps whose particles straddle columns (or are unsorted) gather straight from L2.
+// ---------------------------------------------------------------------------------------------------------------
+#define G2P_ZMAX 32
+struct Footprint { bool staged; int bx0, by0, kmin, len; };
+__device__ __forceinline__ Footprint footprint_of(const bool ok, const int* b) {  // ALL 32 lanes must call
+  Footprint fp; fp.staged = false; fp.bx0 = fp.by0 = fp.kmin = 0; fp.len = 0;
+  const unsigned valid = __ballot_sync(SC_FULL, ok);
+  if (valid == 0u) return fp;
+  const int ref = __ffs(valid) - 1;
+  fp.bx0 = __shfl_sync(SC_FULL, b[0], ref); fp.by0 = __shfl_sync(SC_FULL, b[1], ref);
+  const bool same = __ballot_sync(SC_FULL, ok && (b[0] != fp.bx0 || b[1] != fp.by0)) == 0u;
+  fp.kmin = __reduce_min_sync(SC_FULL, ok ? b[2] : 0x7fffffff);
+  const int kmax = __reduce_max_sync(SC_FULL, ok ? b[2] : -1);
+  fp.len = kmax - fp.kmin + 3;
+  fp.staged = same && fp.len <= G2P_ZMAX;
+  return fp;
+}
+__device__ __forceinline__ void footprint_load(const float4* __restrict__ grid, const int n, const Footprint& fp, float4* tile) {
+  const int lane = threadIdx.x & 31;
+  if (lane < fp.len) {
+#pragma unroll
+    for (int c = 0; c < 9; c++) tile[c * G2P_ZMAX + lane] = grid[((fp.bx0 + c / 3) * n + (fp.by0 + c % 3)) * n + fp.kmin + lane];
+  }
+  __syncwarp();
 }
