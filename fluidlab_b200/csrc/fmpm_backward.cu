@@ -181,6 +181,9 @@ __device__ __forceinline__ Mat3 constitutive_grad(const KParams& P, const Consti
 }
 
 #define PG_WARPS 4
+#ifndef PG_MINB
+#define PG_MINB 4   // <=128 registers (16 warps/SM) with ~200 B of L1-resident spills: 164 us -> 121 us at 1M particles
+#endif
 
 // Adjoint gather on the 27 stencil nodes, column-factored.  With g_i = v_out (forward), a_i = adjoint of v_in, am_i = adjoint
 // of mass, delta_i = o_i - fx, Mg = 4 inv_dx gC', Ma = A dx:
@@ -246,7 +249,7 @@ __device__ __forceinline__ void adjoint_gather(const float* fx, const float w[3]
   gfx[2] = sgz - (Mg.m[2] * vp[0] + Mg.m[5] * vp[1] + Mg.m[8] * vp[2]) - (Ma.m[2] * gvp[0] + Ma.m[5] * gvp[1] + Ma.m[8] * gvp[2]);
 }
 
-__global__ void __launch_bounds__(PG_WARPS * 32) k_particle_grad(const KParams P, const int f, const int gin, const int gout) {
+__global__ void __launch_bounds__(PG_WARPS * 32, PG_MINB) k_particle_grad(const KParams P, const int f, const int gin, const int gout) {
   __shared__ float4 tiles[PG_WARPS][2][9 * G2P_ZMAX];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   float4* tg = tiles[threadIdx.x >> 5][0];

@@ -27,7 +27,7 @@
 #define P2G_ROUNDS 4
 #endif
 #ifndef P2G_MINB
-#define P2G_MINB 1
+#define P2G_MINB 5   // <=102 registers: 20 warps/SM; measured 15% faster than the unconstrained 128-register build
 #endif
 
 // =============================================================================================
