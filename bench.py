@@ -168,12 +168,30 @@ def main():
     K = args.steps
     T = 50
     N = args.particles
-    sim = MPMSimulator(dim=3, quality=QUALITY, gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T, max_substeps_global=10 ** 7,
-                       ckpt_dest='gpu', device=dev, sort_every=args.sort_every)
-    parts = workload_particles(N, seed=rank)
-    sim.build(None, None, [], parts)
+    slab = None
+    if world == 1:
+        sim = MPMSimulator(dim=3, quality=QUALITY, gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T, max_substeps_global=10 ** 7,
+                           ckpt_dest='gpu', device=dev, sort_every=args.sort_every)
+        parts = workload_particles(N, seed=rank)
+        sim.build(None, None, [], parts)
+        step_fn = lambda: sim.step(None)
+        workload = f'C2 water block free fall, {N} particles, 128^3 grid, fp32, forward (BASELINE.json configs[1])'
+        parallelism = 'single GPU'
+    else:
+        # weak scaling: the C2 block (same particle count and ~8 particles/cell per GPU) laid out as x-slabs of one global
+        # water body on a 256^3 grid; ghost planes of the (momentum, mass) grid are summed between neighbours every substep.
+        from fluidlab_b200.slab import SlabMPMSimulator, slab_bounds
+        q = 4; n = 64 * q; dx = 1.0 / n; slab_w = 24
+        bounds = slab_bounds(32, 32 + slab_w * world, world)
+        lo = ((bounds[rank] - 0.5) * dx, 0.30, 0.36); hi = ((bounds[rank + 1] - 0.5) * dx, 0.30 + 72 * dx, 0.36 + 72 * dx)
+        parts = workload_particles(N, seed=rank, lo=lo, hi=hi)
+        slab = SlabMPMSimulator(q, GRAVITY, parts, gid=np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1), max_substeps_local=T, device=dev)
+        sim = slab.sim
+        step_fn = slab.step
+        workload = (f'C2-weak: {N} water particles per GPU (~8/cell) as {world} x-slabs of one body, 256^3 grid, fp32, forward; value counts '
+                    f'1M-particle substeps (global substeps/s = value / n_gpus)')
+        parallelism = f'{world} x-slabs, per-substep ghost-plane sum exchange ({slab.ghost.bytes_per_exchange()} B/rank/substep) + per-step migration, NCCL'
     init = sim.get_state()
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -188,13 +206,13 @@ def main():
 
     # ------------------------------------------------------------------ device-resident throughput
     for _ in range(W):
-        sim.step(None)
+        step_fn()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as cs:
         e0.record()
         for _ in range(K):
-            sim.step(None)
+            step_fn()
         e1.record()
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -244,7 +262,7 @@ def main():
 
     # ------------------------------------------------------------------ forward+backward (BASELINE metric, second half)
     fb = None
-    if args.bwd:
+    if args.bwd and world == 1:
         import fluidlab_b200  # noqa
         nfb = max(2, min(K, 10))
         tgt = torch.zeros((N, 3), dtype=torch.float32, device=dev) + 0.5
@@ -279,14 +297,17 @@ def main():
     EP = 10  # steps per episode
     n_ep = max(1, K // EP)
     h2d = sum(t.numel() * t.element_size() for t in pin.values()) / EP
-    d2h = N * (12 + 12 + 4)
+    d2h = sim.n_particles * (12 + 12 + 4)
+    gid0 = slab.gid.clone() if slab is not None else None
 
     def episode():
         sim.cur_substep_global = 0
         sim.set_state(0, pin)                      # H2D of the episode's initial state (pinned host)
+        if slab is not None:
+            slab.gid.copy_(gid0)
         out = None
         for _ in range(EP):
-            sim.step(None)
+            step_fn()
             out = sim.get_state_RL()               # D2H of x, v, used every step (FluidEnv._get_obs)
         return out
     episode(); barrier()
@@ -304,11 +325,11 @@ def main():
         line = {
             'metric': 'mpm_substeps_per_s_fwd', 'value': value, 'unit': 'substeps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'C2 water block free fall, {N} particles/GPU, 128^3 grid, fp32, forward (BASELINE.json configs[1])',
+            'config': {'workload': workload,
                        'substeps_per_step': SUBSTEPS_PER_STEP, 'dt': 2e-4, 'gravity': GRAVITY, 'max_substeps_local': T,
                        'cell_sort_every_steps': args.sort_every,
                        'l2_policy': 'inputs larger than L2 (one substep touches >= 212 B x 1M particles = 212 MB > 126 MB L2)',
-                       'parallelism': 'single GPU' if world == 1 else f'{world} independent slabs-as-replicas (ghost exchange not built yet)'},
+                       'parallelism': parallelism},
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},

@@ -272,3 +272,15 @@ def test_library_error_reporting():
         s.phase('p2g', 999)
     with pytest.raises(FmpmError, match='gradient buffers were not bound'):
         s._ck(s._lib.fmpm_particle_grad(s._h, 0, 0, 1, s._stream()), 'particle_grad')
+
+
+def test_slab_sharded_forward_matches_single_gpu():
+    """2 ranks (nccl): x-slab sharding with ghost-plane exchange and migration == single-GPU result (tests/run_slab_gpu.py)."""
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29533', os.path.join(root, 'tests', 'run_slab_gpu.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'SLAB_PARITY_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
