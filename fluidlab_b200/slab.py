@@ -31,46 +31,35 @@ def slab_bounds(lo_plane, hi_plane, world, align=8):
 
 
 class GhostExchange:
-    """Sums the ghost planes of a (G,4) accumulator with the neighbouring slabs."""
+    """Sums the ghost planes of a (G,4) accumulator with the neighbouring slabs: one in-place all-reduce per slab boundary
+    over a 2-rank communicator, restricted to the `2*halo` planes around the boundary (contiguous: x is the slowest index)."""
 
     def __init__(self, n_grid, bounds, rank, world, halo=8, group=None):
-        self.n, self.bounds, self.rank, self.world, self.halo, self.group = n_grid, list(bounds), rank, world, halo, group
+        self.n, self.bounds, self.rank, self.world, self.halo = n_grid, list(bounds), rank, world, halo
         self.plane = n_grid * n_grid
-        self.neigh = []  # (peer, first_plane, last_plane_exclusive)
-        if rank > 0:
-            b = self.bounds[rank]
-            self.neigh.append((rank - 1, b - halo, b + halo))
-        if rank < world - 1:
-            b = self.bounds[rank + 1]
-            self.neigh.append((rank + 1, b - halo, b + halo))
-        self._recv = {}
+        self.regions = []  # (boundary index, first_plane, last_plane_exclusive, pair process group)
+        if world > 1:
+            # every rank creates every pair group, in the same order (torch.distributed requirement)
+            pgs = [dist.new_group([i, i + 1]) for i in range(world - 1)]
+            # even boundaries first, then odd ones: a globally consistent collective order, no deadlock
+            for i in list(range(0, world - 1, 2)) + list(range(1, world - 1, 2)):
+                if rank in (i, i + 1):
+                    b = self.bounds[i + 1]
+                    self.regions.append((i, b - halo, b + halo, pgs[i]))
 
     def bytes_per_exchange(self):
-        return sum((hi - lo) * self.plane * 16 for _, lo, hi in self.neigh)
+        return sum((hi - lo) * self.plane * 16 for _, lo, hi, _ in self.regions)
 
     def exchange_sum(self, grid):
         """grid: (G,4) float32 tensor (cuda for nccl, cpu for gloo).  In place: ghost regions become the 2-rank sums."""
-        if not self.neigh:
-            return
-        ops, views = [], []
-        for peer, lo, hi in self.neigh:
-            view = grid[lo * self.plane:hi * self.plane]
-            buf = self._recv.get(peer)
-            if buf is None or buf.shape != view.shape or buf.device != view.device:
-                buf = torch.empty_like(view); self._recv[peer] = buf
-            ops.append(dist.P2POp(dist.isend, view, peer, self.group))
-            ops.append(dist.P2POp(dist.irecv, buf, peer, self.group))
-            views.append((view, buf))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        for view, buf in views:
-            view.add_(buf)
+        for _, lo, hi, pg in self.regions:
+            dist.all_reduce(grid[lo * self.plane:hi * self.plane], group=pg)
 
     def flag_ghost_blocks(self, blk_flags):
         """mark the 8^3 blocks covering the ghost regions active so grid_op computes (and clears) them on both ranks."""
         nb = self.n // 8
         f = blk_flags.view(nb, nb, nb)
-        for _, lo, hi in self.neigh:
+        for _, lo, hi, _ in self.regions:
             f[lo // 8:(hi + 7) // 8] = 1
 
 
@@ -201,6 +190,10 @@ class SlabMPMSimulator:
         rec = torch.cat([self.gid.view(torch.float32).reshape(-1, 1), st['x'], st['v'], st['F'].reshape(-1, 9)], 1)
         rec = torch.where(used.reshape(-1, 1), rec, torch.full_like(rec, float('nan')))
         if self.world > 1:
+            cap = torch.tensor([rec.shape[0]], device=rec.device); dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+            pad = int(cap.item()) - rec.shape[0]
+            if pad:
+                rec = torch.cat([rec, torch.full((pad, rec.shape[1]), float('nan'), device=rec.device)], 0)
             out = [torch.empty_like(rec) for _ in range(self.world)]
             dist.all_gather(out, rec, group=self.group)
             rec = torch.cat(out, 0)

@@ -33,9 +33,14 @@ def multimat():
     for f in range(n_sub):
         o.substep(f)
     fr = o.get_frame(n_sub)
+    o64 = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=bnd, max_substeps_local=n_sub, precision=64)
+    for f in range(n_sub):
+        o64.substep(f)
+    f64 = o64.get_frame(n_sub)
     np.savez_compressed(os.path.join(HERE, 'multimat_n32_40sub.npz'), n_grid=n_grid, n_sub=n_sub, x0=x, mat=mat,
                         b_lower=bnd['lower'], b_upper=bnd['upper'], gravity=(0, -10, 0),
-                        x=fr['x'].astype(np.float32), v=fr['v'].astype(np.float32), C=fr['C'].astype(np.float32), F=fr['F'].astype(np.float32))
+                        x=fr['x'].astype(np.float32), v=fr['v'].astype(np.float32), C=fr['C'].astype(np.float32), F=fr['F'].astype(np.float32),
+                        x64=f64['x'], v64=f64['v'], F64=f64['F'])
 
 
 def latte_mini():
