@@ -187,7 +187,18 @@ def main():
         parts = workload_particles(N, seed=rank, lo=lo, hi=hi)
         slab = SlabMPMSimulator(q, GRAVITY, parts, gid=np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1), max_substeps_local=T, device=dev)
         sim = slab.sim
-        step_fn = slab.step
+        # the reference's fixed dt = 2e-4 is unstable for water at 256^3 beyond ~700 substeps (profiles/check_stability_256.py,
+        # SURVEY.md §8d C5): restore the initial state (device-side copy, ~0.1% of the time) every 30 steps
+        _cnt = [0]
+        _init_dev = {k: v.clone() for k, v in sim.readframe_torch(0).items()}
+        _gid0 = slab.gid.clone()
+
+        def step_fn():
+            if _cnt[0] and _cnt[0] % 30 == 0:
+                sim.cur_substep_global = 0
+                sim.set_state(0, _init_dev); slab.gid.copy_(_gid0)
+            _cnt[0] += 1
+            slab.step()
         workload = (f'C2-weak: {N} water particles per GPU (~8/cell) as {world} x-slabs of one body, 256^3 grid, fp32, forward; value counts '
                     f'1M-particle substeps (global substeps/s = value / n_gpus)')
         parallelism = f'{world} x-slabs, per-substep ghost-plane sum exchange ({slab.ghost.bytes_per_exchange()} B/rank/substep) + per-step migration, NCCL'

@@ -107,22 +107,16 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
 // sparse grid: compaction of the active 8^3-node blocks flagged by the p2g flushes, then grid_op on them
 // =============================================================================================
 __global__ void __launch_bounds__(1024) k_compact_blocks(const KParams P) {
-  __shared__ int s_count;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
+  // one CTA per 1024 flags; list order is arbitrary (blocks are processed independently); blk_count was zeroed by the host
   const int nblk = P.nb * P.nb * P.nb;
-  for (int base = 0; base < nblk; base += 1024) {
-    const int b = base + threadIdx.x;
-    const bool on = b < nblk && P.blk_flags[b] != 0;
-    if (on) P.blk_flags[b] = 0;
-    const unsigned m = __ballot_sync(0xffffffffu, on);
-    int off = 0;
-    if ((threadIdx.x & 31) == 0 && m) off = atomicAdd(&s_count, __popc(m));
-    off = __shfl_sync(0xffffffffu, off, 0);
-    if (on) P.blk_list[off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = b;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) P.blk_count[0] = s_count;
+  const int b = blockIdx.x * 1024 + threadIdx.x;
+  const bool on = b < nblk && P.blk_flags[b] != 0;
+  if (on) P.blk_flags[b] = 0;
+  const unsigned m = __ballot_sync(0xffffffffu, on);
+  int off = 0;
+  if ((threadIdx.x & 31) == 0 && m) off = atomicAdd(P.blk_count, __popc(m));
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (on) P.blk_list[off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = b;
 }
 
 // MPM:380-398 on the active blocks; optionally clears the (momentum, mass) accumulators for the next substep
@@ -304,9 +298,11 @@ int fmpm_grid_op_impl(FmpmHandle* h, int clear_pm, int zero_ggv, void* stream) {
   KParams P = make_kparams(h);
   if (!P.blk_flags || !P.blk_list || !P.blk_count) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block buffers were not bound"); return 1; }
   if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
-  k_compact_blocks<<<1, 1024, 0, (cudaStream_t)stream>>>(P);
-  FMPM_CHECK_LAUNCH(h, "fmpm_grid_op(compact)");
   const int nblk = P.nb * P.nb * P.nb;
+  cudaError_t e0 = cudaMemsetAsync(P.blk_count, 0, sizeof(int), (cudaStream_t)stream);
+  if (e0 != cudaSuccess) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: %s", cudaGetErrorString(e0)); return 1; }
+  k_compact_blocks<<<(nblk + 1023) / 1024, 1024, 0, (cudaStream_t)stream>>>(P);
+  FMPM_CHECK_LAUNCH(h, "fmpm_grid_op(compact)");
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
   k_grid_op<<<grid, 256, 0, (cudaStream_t)stream>>>(P, clear_pm, zero_ggv);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op");
