@@ -10,8 +10,9 @@ The reference is single-device (no collective anywhere); this is new design.  On
     grid index — with ONE in-place NCCL all-reduce per boundary over a 2-rank communicator (an all-reduce of only the
     ghost cells, over NVLink).  grid_op then runs redundantly on the ghosts, so g2p needs no second exchange;
   * at step boundaries particles whose centre plane left the slab migrate to the neighbour (100 B records + material row
-    + global id); a step without leavers anywhere costs one tiny all-gather of counts.  `halo` = 4 planes tolerates 3 cells
-    of drift between migrations (|v| < 3 dx / (10 dt) = 5.9 m/s at 256^3); raise it for faster flows.
+    + global id).  The leaver census is asynchronous (all-reduce -> pinned host, read one step later), so steps without
+    leavers never synchronise the host.  `halo` = 4 planes tolerates 3 cells of drift over the two steps between a
+    census and its migration (|v| < 3 dx / (20 dt) = 2.9 m/s at 256^3, 11.7 m/s at 64^3); raise `halo` for faster flows.
 
 `SlabMPMSimulator` covers the forward path (step / gather_state); the backward ghost exchange (v_out adjoint planes) is the
 mirror image and is not wired yet.
@@ -154,27 +155,46 @@ class SlabMPMSimulator:
         self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.ghost = GhostExchange(self.sim.n_grid, self.bounds, self.rank, self.world, halo=halo, group=group)
         self.n_migrated = 0
+        self._census_host = None
+        self._census_event = None
 
-    def _migrate(self):
+    def _census_async(self):
+        """enqueue (no host sync): per-rank leaver counts -> all-gather -> total -> pinned host; read one step later."""
         sim = self.sim
         f = sim.cur_substep_local
-        # cheap census straight from the planar frame (slot order): who left the slab?  one all-gather, one sync per step
         xs = sim._pa[f, 0, :, 0]
         alive = (sim._pa[f, 0, :, 3].view(torch.int32) & 1) != 0
         cp = (xs * sim.inv_dx - 0.5).to(torch.int32) + 1
-        n_left = (alive & (cp < self.lo)).sum() if self.rank > 0 else torch.zeros((), dtype=torch.int64, device=xs.device)
-        n_right = (alive & (cp >= self.hi)).sum() if self.rank < self.world - 1 else torch.zeros((), dtype=torch.int64, device=xs.device)
-        mine = torch.stack([n_left, n_right]).to(torch.int64)
-        allc = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(allc, mine, group=self.group)
-        if int(torch.stack(allc).sum().item()) == 0:
-            return
-        st = sim.readframe_torch(f)
-        state = dict(x=st['x'], v=st['v'], C=st['C'], F=st['F'], used=st['used'], mrow=sim._mrow, gid=self.gid)
-        n_out, n_in = migrate(state, self.lo, self.hi, self.rank, self.world, sim.inv_dx, self.group)
-        if n_out or n_in:
-            sim.setframe(f, state['x'], state['v'], state['C'], state['F'], state['used'])
-        self.n_migrated += n_out
+        out = torch.zeros((), dtype=torch.int64, device=xs.device)
+        if self.rank > 0:
+            out = out + (alive & (cp < self.lo)).sum()
+        if self.rank < self.world - 1:
+            out = out + (alive & (cp >= self.hi)).sum()
+        out = out.reshape(1)
+        dist.all_reduce(out, group=self.group)
+        if self._census_host is None:
+            self._census_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._census_host.copy_(out, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(xs.device))
+        self._census_event = ev
+
+    def _migrate(self):
+        """Particles that left the slab move to the neighbour.  The decision uses the census enqueued one step earlier
+        (identical on every rank), so a step without leavers anywhere costs no host synchronisation."""
+        sim = self.sim
+        need = False
+        if self._census_event is not None:
+            self._census_event.synchronize()
+            need = int(self._census_host[0]) != 0
+        if need:
+            f = sim.cur_substep_local
+            st = sim.readframe_torch(f)
+            state = dict(x=st['x'], v=st['v'], C=st['C'], F=st['F'], used=st['used'], mrow=sim._mrow, gid=self.gid)
+            n_out, n_in = migrate(state, self.lo, self.hi, self.rank, self.world, sim.inv_dx, self.group)
+            if n_out or n_in:
+                sim.setframe(f, state['x'], state['v'], state['C'], state['F'], state['used'])
+            self.n_migrated += n_out
+        self._census_async()
 
     def step(self):
         sim = self.sim
