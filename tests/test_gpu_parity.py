@@ -284,3 +284,56 @@ def test_slab_sharded_forward_matches_single_gpu():
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                         '--master-port', '29533', os.path.join(root, 'tests', 'run_slab_gpu.py')], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'SLAB_PARITY_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def latteart_demo_actions(horizon_action=250):
+    """scripted pour of envs/latteart_env.py:113-140 (demo_policy): returns (actions_v [T,3], action_p [3])."""
+    init_p = np.array([0.15, 0.65, 0.5]); x_range = 0.7
+    cur = init_p.copy(); amp = np.array([0.15, 0.25]); acts = np.zeros((horizon_action, 3))
+    for i in range(horizon_action):
+        t = i + 1
+        tx = init_p[0] + t / horizon_action * x_range
+        rad = t / horizon_action * (np.pi * 2) * 3
+        a = amp[1] - np.abs((t * 2 / horizon_action) - 1) * (amp[1] - amp[0])
+        tp = np.array([tx, init_p[1], np.sin(rad) * a + 0.5])
+        acts[i] = tp - cur; cur += acts[i]
+    return acts, init_p
+
+
+def test_c1_latteart_v0_full_size_100_substeps():
+    """BASELINE.json configs[0]: LatteArt-v0 default scene (envs/latteart_env.py:28-74, agent_latteart.yaml): 115,480 slots
+    (60,000 parked MILK + 55,480 COFFEE), 64^3, cylinder boundary, gravity -20, injector flux 2, 10 steps of the demo policy,
+    forward 100 substeps (two T=50 chunks) — CUDA vs the fp32 oracle."""
+    _need_gpu()
+    from fluidlab_b200 import TaichiEnv
+    from oracle import oracle as orc
+    env = TaichiEnv(dim=3, particle_density=1e6, max_substeps_local=50, gravity=(0.0, -20.0, 0.0), horizon=330)
+    np.random.seed(0)
+    env.setup_agent(dict(type='AgentInjector', effectors=[dict(type='Injector', params=dict(
+        radius=0.0075, flux=2, init_pos=(0.5, 0.5, 0.5), action_dim=3, inject_v=(0.0, -3.0, 0.0), action_scale_p=(1.0, 1.0, 1.0),
+        action_scale_v=(1.0, 1.0, 1.0), locally_random=True), boundary=dict(type='cylinder', xz_radius=0.42, xz_center=(0.5, 0.5), y_range=(0.65, 0.65)))]))
+    env.add_body(type='nowhere', n_particles=60000, material=M.MILK)
+    env.add_body(type='cylinder', center=(0.5, 0.55, 0.5), height=0.1, radius=0.42, material=M.COFFEE)
+    bnd = dict(type='cylinder', xz_radius=0.42, xz_center=(0.5, 0.5), y_range=(0.5, 0.95))
+    env.setup_boundary(**bnd)
+    env.build()
+    assert env.n_particles == 115480
+    Pb = env.particles
+    P = make_particles(Pb['x'], Pb['mat'], 64, used=Pb['used'].astype(np.int32))
+    inj = env.agent.effectors[0]
+    o = orc.OracleSim(64, P, gravity=(0, -20, 0), boundary=bnd, precision=32, max_substeps_local=50)
+    o.add_effector(type=1, action_dim=3, boundary=dict(type='cylinder', xz_radius=0.42, xz_center=(0.5, 0.5), y_range=(0.65, 0.65)), radius=0.0075, flux=2,
+                   inject_v=(0, -3, 0), inject_p=(0, 0, 0), locally_random=True, random_vector=inj.random_vector_np,
+                   act_range=np.where(P['used'] == 0)[0], max_action_steps=331)
+    acts, init_p = latteart_demo_actions()
+    env.apply_agent_action_p(init_p)
+    o.set_effector_state(0, 0, np.array([0.5, 0.5, 0.5, 1, 0, 0, 0, 0.0])); o.apply_action_p(init_p)
+    for i in range(10):
+        env.step(acts[i]); o.step(acts[i])
+    a, b = env.simulator.get_state(), o.get_frame(o.cur_substep_local)
+    assert np.array_equal(a['used'], b['used']) and int(a['used'].sum()) == 55480 + 2 * 100
+    act = a['used'] != 0
+    assert rel(a['x'][act], b['x'][act]) < 1e-5 and rel(a['F'][act], b['F'][act]) < 1e-5, (rel(a['x'][act], b['x'][act]), rel(a['F'][act], b['F'][act]))
+    assert rel(a['v'][act], b['v'][act]) < 1e-4, rel(a['v'][act], b['v'][act])
+    assert np.array_equal(a['x'][~act], b['x'][~act].astype(np.float32))  # parked milk untouched at NOWHERE
+    assert np.allclose(a['agent'][0][:7], o.effector_state(0, o.cur_substep_local)[:7], atol=1e-6)
