@@ -186,6 +186,156 @@ template <class R> struct Effector {
   }
 };
 
+
+// -------------------------------------------------------------------------------------
+// SDF mesh colliders: meshes/static.py:26-104 (Static) and meshes/dynamic.py:29-121 (Dynamic).
+// The baked volume is `voxels[res^3]` (utils/mesh.py:63-87) with T_mesh_to_voxels already
+// multiplied by inv(T_init) (meshes/mesh.py:121-127).
+// -------------------------------------------------------------------------------------
+template <class R> struct SdfMesh {
+  int res = 0;
+  std::vector<R> vox;
+  R T[16];       // T_mesh_to_voxels (row-major 4x4)
+  R Ainv[9];     // inverse of T[:3,:3]  (R_voxels_to_mesh)
+  R friction = 0, softness = 0;
+  int has_dynamics = 1;
+  // sdf_ : trilinear lookup, 1.0 outside the volume (static.py:35-48).  grad (optional) = d sdf / d pos_voxels.
+  R sdf_(const R* pv, R* grad) const {
+    int b[3]; for (int d = 0; d < 3; d++) b[d] = (int)std::floor(pv[d]);
+    if (grad) grad[0] = grad[1] = grad[2] = 0;
+    for (int d = 0; d < 3; d++) if (b[d] >= res - 1 || b[d] < 0) return R(1);
+    R sd = 0;
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+      int vp[3] = {b[0] + i, b[1] + j, b[2] + k};
+      R w[3], dwd[3];
+      for (int d = 0; d < 3; d++) { R t = pv[d] - (R)vp[d]; w[d] = R(1) - std::fabs(t); dwd[d] = t > 0 ? R(-1) : (t < 0 ? R(1) : R(0)); }
+      R val = vox[((size_t)vp[0] * res + vp[1]) * res + vp[2]];
+      sd += w[0] * w[1] * w[2] * val;
+      if (grad) { grad[0] += dwd[0] * w[1] * w[2] * val; grad[1] += w[0] * dwd[1] * w[2] * val; grad[2] += w[0] * w[1] * dwd[2] * val; }
+    }
+    return sd;
+  }
+  void to_voxels(const R* pm, R* pv) const { for (int r = 0; r < 3; r++) pv[r] = T[r * 4] * pm[0] + T[r * 4 + 1] * pm[1] + T[r * 4 + 2] * pm[2] + T[r * 4 + 3]; }
+  // normal_ in voxel space: central differences with delta = 1e-2 voxel, normalised with eps (static.py:66-79)
+  void normal_vox(const R* pv, R* nv, R* graw, R& gn) const {
+    const R delta = R(1e-2);
+    for (int i = 0; i < 3; i++) {
+      R inc[3] = {pv[0], pv[1], pv[2]}, dec[3] = {pv[0], pv[1], pv[2]};
+      inc[i] += delta; dec[i] -= delta;
+      graw[i] = (sdf_(inc, nullptr) - sdf_(dec, nullptr)) / (R(2) * delta);
+    }
+    gn = std::sqrt(graw[0] * graw[0] + graw[1] * graw[1] + graw[2] * graw[2] + R(1e-12));
+    for (int i = 0; i < 3; i++) nv[i] = graw[i] / gn;
+  }
+};
+
+template <class R> static inline void quat_rot_t(const R* q, const R* v, R* o) {  // utils/geom.py:92-97
+  R uv[3] = {q[2] * v[2] - q[3] * v[1], q[3] * v[0] - q[1] * v[2], q[1] * v[1] - q[2] * v[0]};
+  R uuv[3] = {q[2] * uv[2] - q[3] * uv[1], q[3] * uv[0] - q[1] * uv[2], q[1] * uv[1] - q[2] * uv[0]};
+  for (int k = 0; k < 3; k++) o[k] = v[k] + R(2) * (q[0] * uv[k] + uuv[k]);
+}
+template <class R> static inline void quat_inv_t(const R* q, R* qi) {  // utils/geom.py:30-32 (normalised conjugate)
+  R n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  qi[0] = q[0] / n; qi[1] = -q[1] / n; qi[2] = -q[2] / n; qi[3] = -q[3] / n;
+}
+
+// One collide evaluation (static: pos0 = pos1 = 0, quats identity, dynamic = false).  Forward value in `out`; when
+// gout != nullptr the adjoints of (v, p, pos0, pos1) are ACCUMULATED into gv, gp, gpos0, gpos1 (quaternion adjoints are not
+// restated: every shipped Rigid effector has action_dim = 3, so quat is constant).
+// Follows meshes/dynamic.py:93-121 (Dynamic.collide) / meshes/static.py:82-104 (Static.collide).
+template <class R> static void sdf_collide(const SdfMesh<R>& M, bool dynamic, const R* pos0, const R* q0, const R* pos1, const R* q1, R dt,
+                                           const R* p, const R* v, R* out, const R* gout, R* gv, R* gp, R* gpos0, R* gpos1) {
+  for (int k = 0; k < 3; k++) out[k] = v[k];
+  if (!M.has_dynamics) { if (gout) for (int k = 0; k < 3; k++) gv[k] += gout[k]; return; }
+  R qi[4], d0[3], pm[3], pv[3];
+  quat_inv_t(q0, qi);
+  for (int k = 0; k < 3; k++) d0[k] = p[k] - pos0[k];
+  quat_rot_t(qi, d0, pm);
+  M.to_voxels(pm, pv);
+  R gsd[3];
+  const R sd = M.sdf_(pv, gsd);
+  const R infl = dynamic ? std::min((R)std::exp(-sd * M.softness), R(1)) : R(1);
+  const bool hit = dynamic ? (sd <= 0 || (M.softness > 0 && infl > R(0.1))) : (sd <= 0);
+  if (!hit) { if (gout) for (int k = 0; k < 3; k++) gv[k] += gout[k]; return; }
+  R cv[3] = {0, 0, 0};
+  if (dynamic) {
+    R pw1[3]; quat_rot_t(q1, pm, pw1);
+    for (int k = 0; k < 3; k++) cv[k] = (pw1[k] + pos1[k] - p[k]) / dt;   // collider_v, dynamic.py:86-91
+  }
+  const bool sticky = dynamic && (M.friction > R(10));
+  R rel[3], nvx[3], graw[3], gnorm = 1, u[3], un = 1, n[3] = {0, 0, 0}, vn = 0, m = 0, rt[3], rtn = 0, g = 0, rt2[3];
+  bool flag = false;
+  if (sticky) { for (int k = 0; k < 3; k++) out[k] = cv[k]; }
+  else {
+    for (int k = 0; k < 3; k++) rel[k] = v[k] - cv[k];
+    M.normal_vox(pv, nvx, graw, gnorm);
+    R nm[3];
+    for (int r = 0; r < 3; r++) nm[r] = M.Ainv[r * 3] * nvx[0] + M.Ainv[r * 3 + 1] * nvx[1] + M.Ainv[r * 3 + 2] * nvx[2];
+    quat_rot_t(q0, nm, u);
+    un = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + R(1e-12));
+    for (int k = 0; k < 3; k++) n[k] = u[k] / un;
+    vn = rel[0] * n[0] + rel[1] * n[1] + rel[2] * n[2];
+    m = std::min(vn, R(0));
+    for (int k = 0; k < 3; k++) rt[k] = rel[k] - m * n[k];
+    rtn = std::sqrt(rt[0] * rt[0] + rt[1] * rt[1] + rt[2] * rt[2]);
+    g = std::max(R(0), rtn + vn * M.friction);
+    flag = (vn < 0) && (rtn > R(1e-12));
+    for (int k = 0; k < 3; k++) rt2[k] = flag ? rt[k] / rtn * g : rt[k];
+    for (int k = 0; k < 3; k++) out[k] = cv[k] + rt2[k] * infl + rel[k] * (R(1) - infl);
+  }
+  if (!gout) return;
+  // ------------------------------------------------------------------ adjoint
+  R gcv[3] = {gout[0], gout[1], gout[2]}, gpv[3] = {0, 0, 0}, gsdv = 0;
+  if (!sticky) {
+    R grt2[3], grel[3], ginfl = 0;
+    for (int k = 0; k < 3; k++) { grt2[k] = infl * gout[k]; ginfl += gout[k] * (rt2[k] - rel[k]); grel[k] = (R(1) - infl) * gout[k]; }
+    R grt[3] = {0, 0, 0}, gvn = 0, gn[3] = {0, 0, 0};
+    if (flag) {
+      const R sc = g / rtn;
+      R sbar = 0;
+      for (int k = 0; k < 3; k++) { grt[k] += sc * grt2[k]; sbar += rt[k] * grt2[k]; }
+      R grtn = -sbar * g / (rtn * rtn);
+      if (rtn + vn * M.friction > 0) { grtn += sbar / rtn; gvn += sbar / rtn * M.friction; }   // max(0, a): adjoint to a iff 0 < a
+      for (int k = 0; k < 3; k++) grt[k] += grtn * rt[k] / rtn;
+    } else {
+      for (int k = 0; k < 3; k++) grt[k] += grt2[k];
+    }
+    R gm = 0;
+    for (int k = 0; k < 3; k++) { grel[k] += grt[k]; gm -= grt[k] * n[k]; gn[k] -= m * grt[k]; }
+    if (vn < 0) gvn += gm;                                                                       // min(vn, 0): adjoint to vn iff vn < 0
+    for (int k = 0; k < 3; k++) { grel[k] += gvn * n[k]; gn[k] += gvn * rel[k]; }
+    for (int k = 0; k < 3; k++) { gv[k] += grel[k]; gcv[k] -= grel[k]; }
+    if (dynamic) {
+      // n = u / |u|_eps, u = R0 nm, nm = Ainv nvx, nvx = graw / |graw|_eps, graw = FD gradient of sdf_ at pv
+      R nd = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
+      R gu[3]; for (int k = 0; k < 3; k++) gu[k] = (gn[k] - n[k] * nd) / un;
+      R gnm[3]; quat_rot_t(qi, gu, gnm);
+      R gnvx[3]; for (int c = 0; c < 3; c++) gnvx[c] = M.Ainv[c] * gnm[0] + M.Ainv[3 + c] * gnm[1] + M.Ainv[6 + c] * gnm[2];
+      R nd2 = nvx[0] * gnvx[0] + nvx[1] * gnvx[1] + nvx[2] * gnvx[2];
+      R ggraw[3]; for (int k = 0; k < 3; k++) ggraw[k] = (gnvx[k] - nvx[k] * nd2) / gnorm;
+      const R delta = R(1e-2);
+      for (int i = 0; i < 3; i++) {
+        R inc[3] = {pv[0], pv[1], pv[2]}, dec[3] = {pv[0], pv[1], pv[2]}, gi[3], gd[3];
+        inc[i] += delta; dec[i] -= delta;
+        M.sdf_(inc, gi); M.sdf_(dec, gd);
+        for (int k = 0; k < 3; k++) gpv[k] += ggraw[i] * (gi[k] - gd[k]) / (R(2) * delta);
+      }
+      if (std::exp(-sd * M.softness) < R(1)) gsdv += ginfl * (-M.softness) * infl;               // min(e, 1): adjoint to e iff e < 1
+    }
+  }
+  if (dynamic) {
+    for (int k = 0; k < 3; k++) gpv[k] += gsdv * gsd[k];
+    // cv = (R1 pm + pos1 - p) / dt
+    R q1i[4]; quat_inv_t(q1, q1i);
+    R t1[3] = {gcv[0] / dt, gcv[1] / dt, gcv[2] / dt}, gpm[3];
+    quat_rot_t(q1i, t1, gpm);
+    for (int k = 0; k < 3; k++) { gpos1[k] += t1[k]; gp[k] -= t1[k]; }
+    for (int c = 0; c < 3; c++) gpm[c] += M.T[c] * gpv[0] + M.T[4 + c] * gpv[1] + M.T[8 + c] * gpv[2];   // pv = A pm + t
+    R gd0[3]; quat_rot_t(q0, gpm, gd0);                                                                // pm = R0^T (p - pos0)
+    for (int k = 0; k < 3; k++) { gp[k] += gd0[k]; gpos0[k] -= gd0[k]; }
+  }
+}
+
 template <class R> struct Sim {
   Config c;
   int N, G, T;
@@ -201,8 +351,26 @@ template <class R> struct Sim {
   std::vector<R> g_vin, g_m, g_vout;            // grid, MPM:112-117
   std::vector<R> gg_vin, gg_m, gg_vout;         // grid grads
   // agent
-  int agent_type = 0;     // 0 none, 2 AgentInjector (agents/agent_injector.py)
+  int agent_type = 0;     // 0 none, 1 AgentRigid (agents/agent_rigid.py), 2 AgentInjector (agents/agent_injector.py)
+  int collide_type = 0;   // 0 particle, 1 grid, 2 both (agents/agent.py:17)
   std::vector<Effector<R>> eff;
+  std::vector<SdfMesh<R>> statics;   // Statics (meshes/statics.py), collided in grid_op in order (MPM:388-390)
+  SdfMesh<R> rigid_mesh;             // mesh of the single Rigid effector (effectors/rigid.py:21-26)
+  bool has_rigid = false;
+
+  // agent.collide(f, pos, v, dt) for AgentRigid -> Rigid.collide -> Dynamic.collide; adjoint accumulates into effector gpos
+  inline void agent_collide(int f, const R* p, const R* vin, R* out, const R* gout, R* gvv, R* gpp) {
+    if (agent_type != 1 || !has_rigid) { for (int k = 0; k < 3; k++) out[k] = vin[k]; if (gout) for (int k = 0; k < 3; k++) gvv[k] += gout[k]; return; }
+    Effector<R>& e = eff[0];
+    R g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0};
+    sdf_collide(rigid_mesh, true, &e.pos[f * 3], &e.quat[f * 4], &e.pos[(f + 1) * 3], &e.quat[(f + 1) * 4], dt, p, vin, out, gout, gvv, gpp, g0, g1);
+    if (gout) for (int k = 0; k < 3; k++) {
+#pragma omp atomic
+      e.gpos[f * 3 + k] += g0[k];
+#pragma omp atomic
+      e.gpos[(f + 1) * 3 + k] += g1[k];
+    }
+  }
 
   explicit Sim(const Config& cfg) : c(cfg) {
     N = c.n_particles; T = c.T; G = c.n_grid * c.n_grid * c.n_grid;
@@ -378,6 +546,12 @@ template <class R> struct Sim {
         R vv[3];
         for (int a = 0; a < 3; a++) { vv[a] = inv_m * g_vin[g * 3 + a]; vv[a] += dt * (R)c.gravity[a]; }
         R pos[3] = {(R)i * dx, (R)j * dx, (R)k * dx};
+        const R zero3v[3] = {0, 0, 0}, idq[4] = {1, 0, 0, 0};
+        for (size_t si = 0; si < statics.size(); si++) {   // MPM:388-390
+          R o[3]; sdf_collide<R>(statics[si], false, zero3v, idq, zero3v, idq, dt, pos, vv, o, nullptr, nullptr, nullptr, nullptr, nullptr);
+          for (int a = 0; a < 3; a++) vv[a] = o[a];
+        }
+        if (collide_type >= 1) { R o[3]; agent_collide(f, pos, vv, o, nullptr, nullptr, nullptr); for (int a = 0; a < 3; a++) vv[a] = o[a]; }  // MPM:393-395
         R fac[3];
         boundary_v(pos, vv, fac);
         for (int a = 0; a < 3; a++) g_vout[g * 3 + a] = vv[a];
@@ -400,6 +574,11 @@ template <class R> struct Sim {
           nv[a] += weight * gv_[a];
           for (int b = 0; b < 3; b++) nC[a][b] += R(4) * inv_dx * weight * gv_[a] * dpos[b];
         }
+      }
+      if (collide_type == 0 || collide_type == 2) {   // MPM:419-422
+        R xt[3] = {xp[0] + dt * nv[0], xp[1] + dt * nv[1], xp[2] + dt * nv[2]}, o[3];
+        agent_collide(f, xt, nv, o, nullptr, nullptr, nullptr);
+        for (int a = 0; a < 3; a++) nv[a] = o[a];
       }
       size_t q = pi(f + 1, p);
       for (int a = 0; a < 3; a++) v[q * 3 + a] = nv[a];
@@ -537,7 +716,20 @@ template <class R> struct Sim {
       const R* xp = &x[a * 3];
       int base[3]; R fx[3]; base_fx(xp, base, fx);
       R w[3][3], dw[3][3]; weights(fx, w); dweights(fx, dw);
-      const R* gvn = &gv[b * 3];
+      R gvn_buf[3] = {gv[b * 3], gv[b * 3 + 1], gv[b * 3 + 2]};
+      if ((collide_type == 0 || collide_type == 2) && agent_type == 1 && has_rigid) {
+        // recompute the pre-collision v' and back-propagate through agent.collide(f, x + dt v', v', dt)  (MPM:419-422)
+        R nv0[3] = {0, 0, 0};
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) {
+          const R* gg = &g_vout[gidx(base[0] + i, base[1] + j, base[2] + k) * 3];
+          R weight = w[i][0] * w[j][1] * w[k][2];
+          for (int r = 0; r < 3; r++) nv0[r] += weight * gg[r];
+        }
+        R xt[3] = {xp[0] + dt * nv0[0], xp[1] + dt * nv0[1], xp[2] + dt * nv0[2]}, o[3], gvpre[3] = {0, 0, 0}, gxt[3] = {0, 0, 0};
+        agent_collide(f, xt, nv0, o, gvn_buf, gvpre, gxt);
+        for (int r = 0; r < 3; r++) { gx[a * 3 + r] += gxt[r]; gvn_buf[r] = gvpre[r] + dt * gxt[r]; }
+      }
+      const R* gvn = gvn_buf;
       M3<R> gCn = getM(gC, b);
       R gfx[3] = {0, 0, 0};
       for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) {
@@ -573,13 +765,37 @@ template <class R> struct Sim {
         R vv[3];
         for (int a = 0; a < 3; a++) { vv[a] = inv_m * g_vin[g * 3 + a]; vv[a] += dt * (R)c.gravity[a]; }
         R pos[3] = {(R)i * dx, (R)j * dx, (R)k * dx};
+        const R zero3v[3] = {0, 0, 0}, idq[4] = {1, 0, 0, 0};
+        // forward chain with the intermediate velocities kept
+        std::vector<V3<R>> chain;
+        chain.push_back(V3<R>{{vv[0], vv[1], vv[2]}});
+        for (size_t si = 0; si < statics.size(); si++) {
+          R o[3]; sdf_collide<R>(statics[si], false, zero3v, idq, zero3v, idq, dt, pos, chain.back().a, o, nullptr, nullptr, nullptr, nullptr, nullptr);
+          chain.push_back(V3<R>{{o[0], o[1], o[2]}});
+        }
+        if (collide_type >= 1) { R o[3]; agent_collide(f, pos, chain.back().a, o, nullptr, nullptr, nullptr); chain.push_back(V3<R>{{o[0], o[1], o[2]}}); }
+        R vlast[3] = {chain.back()[0], chain.back()[1], chain.back()[2]};
         R fac[3];
-        boundary_v(pos, vv, fac);
+        boundary_v(pos, vlast, fac);
+        R vb[3];
+        for (int a = 0; a < 3; a++) vb[a] = gg_vout[g * 3 + a] * fac[a];
+        int ci = (int)chain.size() - 1;
+        if (collide_type >= 1) {
+          R o[3], gvv[3] = {0, 0, 0}, gpp[3] = {0, 0, 0};
+          agent_collide(f, pos, chain[ci - 1].a, o, vb, gvv, gpp);   // node positions are constants: gpp is dropped
+          for (int a = 0; a < 3; a++) vb[a] = gvv[a];
+          ci--;
+        }
+        for (int si = (int)statics.size() - 1; si >= 0; si--) {
+          R o[3], gvv[3] = {0, 0, 0}, gpp[3] = {0, 0, 0}, g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0};
+          sdf_collide<R>(statics[si], false, zero3v, idq, zero3v, idq, dt, pos, chain[ci - 1].a, o, vb, gvv, gpp, g0, g1);
+          for (int a = 0; a < 3; a++) vb[a] = gvv[a];
+          ci--;
+        }
         R mbar = 0;
         for (int a = 0; a < 3; a++) {
-          R vb = gg_vout[g * 3 + a] * fac[a];
-          gg_vin[g * 3 + a] += vb * inv_m;
-          mbar += -(g_vin[g * 3 + a] * vb) * inv_m * inv_m;
+          gg_vin[g * 3 + a] += vb[a] * inv_m;
+          mbar += -(g_vin[g * 3 + a] * vb[a]) * inv_m * inv_m;
         }
         gg_m[g] += mbar;
       }

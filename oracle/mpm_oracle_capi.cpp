@@ -97,6 +97,25 @@ template <class R> static void apply_action_p_t(Sim<R>& S, int ei, const double*
   R aa[6]; for (int k = 0; k < S.eff[ei].cfg.action_dim; k++) aa[k] = (R)a[k];
   S.apply_action_p(ei, aa);
 }
+template <class R> static void fill_mesh(SdfMesh<R>& M, int res, const double* vox, const double* T, double friction, double softness) {
+  M.res = res; M.vox.resize((size_t)res * res * res);
+  for (size_t i = 0; i < M.vox.size(); i++) M.vox[i] = (R)vox[i];
+  for (int i = 0; i < 16; i++) M.T[i] = (R)T[i];
+  // inverse of the 3x3 block, evaluated in R like `T[:3,:3].inverse()` in the kernels (static.py:59)
+  M3<R> A; for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A[r][c] = M.T[r * 4 + c];
+  R d = det3(A);
+  R inv[9] = {(A[1][1] * A[2][2] - A[1][2] * A[2][1]) / d, (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / d, (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / d,
+              (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / d, (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / d, (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / d,
+              (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / d, (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / d, (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / d};
+  for (int i = 0; i < 9; i++) M.Ainv[i] = inv[i];
+  M.friction = (R)friction; M.softness = (R)softness; M.has_dynamics = 1;
+}
+template <class R> static void add_static_t(Sim<R>& S, int res, const double* vox, const double* T, double friction) {
+  SdfMesh<R> M; fill_mesh(M, res, vox, T, friction, 0.0); S.statics.push_back(M);
+}
+template <class R> static void set_rigid_t(Sim<R>& S, int res, const double* vox, const double* T, double friction, double softness, int collide_type) {
+  fill_mesh(S.rigid_mesh, res, vox, T, friction, softness); S.has_rigid = true; S.agent_type = 1; S.collide_type = collide_type;
+}
 template <class R> static void svd_t(const double* A, double* U, double* s, double* V) {
   M3<R> a, u, v; R sg[3];
   for (int i = 0; i < 9; i++) (&a.a[0][0])[i] = (R)A[i];
@@ -150,6 +169,18 @@ void orc_reset_grad(void* hp) { Handle* h = (Handle*)hp; DISPATCH(h, S.reset_gra
 double orc_loss_value(void* hp, int f, int mat, double w, const double* tgt) { Handle* h = (Handle*)hp; double r = 0; DISPATCH(h, r = S.loss_value(f, mat, w, tgt)); return r; }
 void orc_loss_seed(void* hp, int f, int mat, double w, const double* tgt) { Handle* h = (Handle*)hp; DISPATCH(h, S.loss_seed(f, mat, w, tgt)); }
 
+void orc_add_static(void* hp, int res, const double* vox, const double* T, double friction) { Handle* h = (Handle*)hp; DISPATCH(h, add_static_t(S, res, vox, T, friction)); }
+void orc_set_rigid_mesh(void* hp, int res, const double* vox, const double* T, double friction, double softness, int collide_type) {
+  Handle* h = (Handle*)hp; DISPATCH(h, set_rigid_t(S, res, vox, T, friction, softness, collide_type)); }
+// unit access to one collide evaluation (tests): io = [p(3) v(3) pos0(3) pos1(3)] -> out(3); with gout != null also the adjoints [gp gv gpos0 gpos1]
+void orc_sdf_collide_eval(int res, const double* vox, const double* T, double friction, double softness, int dynamic, double dt,
+                          const double* io, double* out, const double* gout, double* gio) {
+  SdfMesh<double> M; fill_mesh(M, res, vox, T, friction, softness);
+  const double q[4] = {1, 0, 0, 0};
+  double gp[3] = {0, 0, 0}, gv[3] = {0, 0, 0}, g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0};
+  sdf_collide<double>(M, dynamic != 0, io + 6, q, io + 9, q, dt, io, io + 3, out, gout, gv, gp, g0, g1);
+  if (gout) for (int k = 0; k < 3; k++) { gio[k] = gp[k]; gio[3 + k] = gv[k]; gio[6 + k] = g0[k]; gio[9 + k] = g1[k]; }
+}
 void orc_set_agent(void* hp, int agent_type) { Handle* h = (Handle*)hp; DISPATCH(h, S.agent_type = agent_type); }
 int orc_add_effector(void* hp, const EffectorCfg* cfg, const double* random_vector, const int* act_range, int n_act_range) {
   Handle* h = (Handle*)hp; int r = -1; DISPATCH(h, r = add_effector_t(S, cfg, random_vector, act_range, n_act_range)); return r; }

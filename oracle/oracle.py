@@ -214,6 +214,17 @@ class OracleSim:
             self.L.orc_set_agent(self.h, 2)
         return ei
 
+    # ---- SDF colliders (meshes/static.py, meshes/dynamic.py): voxels (res,res,res), T_mesh_to_voxels (4,4)
+    def add_static(self, voxels, T_mesh_to_voxels, friction):
+        vox = _d(voxels); T = _d(T_mesh_to_voxels)
+        self.L.orc_add_static(self.h, int(vox.shape[0]), _p(vox), _p(T), C.c_double(friction))
+
+    def set_rigid_mesh(self, voxels, T_mesh_to_voxels, friction, softness, collide_type='particle'):
+        """mesh of the (single) Rigid effector added with add_effector(type=0); agent becomes AgentRigid."""
+        vox = _d(voxels); T = _d(T_mesh_to_voxels)
+        ct = {'particle': 0, 'grid': 1, 'both': 2}[collide_type]
+        self.L.orc_set_rigid_mesh(self.h, int(vox.shape[0]), _p(vox), _p(T), C.c_double(friction), C.c_double(softness), ct)
+
     def effector_state(self, ei, f):
         st = np.zeros(8)
         self.L.orc_effector_get_state(self.h, ei, f, _p(st))

@@ -34,3 +34,25 @@ def make_particles(x, mat_ids, n_grid, used=None, rho=None):
 @pytest.fixture
 def particles_factory():
     return make_particles
+
+
+def sphere_sdf(radius, half_extent, res=32):
+    """synthetic baked SDF volume in the reference's pickle format (utils/mesh.py:63-87): voxels[res^3] of a sphere of
+    `radius` centred at the mesh origin; the volume spans [-half_extent, half_extent]^3 in mesh coordinates."""
+    ax = np.linspace(-half_extent, half_extent, res)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing='ij')
+    vox = (np.sqrt(X ** 2 + Y ** 2 + Z ** 2) - radius).astype(np.float32)
+    s = (res - 1) / (2 * half_extent)
+    T = np.eye(4); T[0, 0] = T[1, 1] = T[2, 2] = s; T[:3, 3] = s * half_extent
+    return vox, T
+
+
+def box_sdf(half, half_extent, res=32):
+    """SDF of an axis-aligned box with half sizes `half` (3,)"""
+    ax = np.linspace(-half_extent, half_extent, res)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing='ij')
+    q = np.stack([np.abs(X) - half[0], np.abs(Y) - half[1], np.abs(Z) - half[2]], -1)
+    vox = (np.linalg.norm(np.maximum(q, 0), axis=-1) + np.minimum(q.max(-1), 0)).astype(np.float32)
+    s = (res - 1) / (2 * half_extent)
+    T = np.eye(4); T[0, 0] = T[1, 1] = T[2, 2] = s; T[:3, 3] = s * half_extent
+    return vox, T
