@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libfluidmpm.so")
 _LIB = None
 
 vp = C.c_void_p
+C = C  # re-exported for struct builders (meshes.py)
 
 
 class FmpmConfig(C.Structure):
@@ -66,8 +67,18 @@ class FmpmInjector(C.Structure):
     ]
 
 
+class FmpmSdfMesh(C.Structure):
+    _fields_ = [("voxels", vp), ("res", C.c_int), ("T_mesh_to_voxels", C.c_float * 16), ("friction", C.c_float), ("softness", C.c_float)]
+
+
+class FmpmColliders(C.Structure):
+    _fields_ = [("n_statics", C.c_int), ("statics", FmpmSdfMesh * 4), ("has_rigid", C.c_int), ("collide_type", C.c_int),
+                ("rigid", FmpmSdfMesh), ("pos", vp), ("quat", vp), ("gpos", vp)]
+
+
 _I, _F, _U = C.c_int, C.c_float, C.c_uint
 _PROTOS = {
+    "fmpm_set_colliders": (_I, [vp, C.POINTER(FmpmColliders)]),
     "fmpm_create": (_I, [C.POINTER(FmpmConfig), C.POINTER(vp)]),
     "fmpm_destroy": (None, [vp]),
     "fmpm_bind": (_I, [vp, C.POINTER(FmpmBuffers)]),

@@ -130,5 +130,12 @@ class AgentInjector(Agent):
 
 
 class AgentRigid(Agent):
+    """Agent with one Rigid (agents/agent_rigid.py): its mesh collides with the material (collide_type particle/grid/both)."""
+
     def build(self, sim):
-        raise NotImplementedError('AgentRigid needs the SDF collide kernels, not built yet (SURVEY.md §8 a9.3)')
+        super().build(sim)
+        assert self.n_effectors == 1
+        assert isinstance(self.effectors[0], Rigid)
+        self.rigid = self.effectors[0]
+        assert self.rigid.mesh is not None, 'Rigid effector without a mesh'
+        sim.register_colliders()

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRCS = ["fmpm_forward.cu", "fmpm_backward.cu", "fmpm_io.cu"]
-HDRS = ["fmpm_common.cuh", "fmpm_scatter.cuh", os.path.join("..", "..", "include", "fluidmpm.h")]
+HDRS = ["fmpm_common.cuh", "fmpm_scatter.cuh", "fmpm_sdf.cuh", os.path.join("..", "..", "include", "fluidmpm.h")]
 OUT = os.path.join(HERE, "..", "libfluidmpm.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # no --use_fast_math: parity with the reference's IEEE fp32 arithmetic matters more than a few SFU cycles

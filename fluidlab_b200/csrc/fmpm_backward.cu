@@ -16,6 +16,7 @@
 #include "fmpm_common.cuh"
 
 #include "fmpm_scatter.cuh"
+#include "fmpm_sdf.cuh"
 
 #define SC_WARPS 4
 #define SC_ROUNDS 4
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
 // =============================================================================================
 // grid_op.grad (MPM:539): v_out = B(v_in / m + dt g)
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int clear_pm) {
+__global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int f, const int clear_pm) {
   const int count = P.blk_count[0];
   const int n = P.n, nb = P.nb;
   for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
@@ -88,21 +89,78 @@ __global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int
       const int g = (i * n + j) * n + k;
       const float4 pm = P.grid_pm[g];
       float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+      float pg0[3] = {0.f, 0.f, 0.f}, pg1[3] = {0.f, 0.f, 0.f};  // effector pose adjoint of this node (grid-level agent collide)
+      const bool agent_grid = P.col.has_rigid && P.col.collide_type >= 1;
       if (pm.w > FMPM_EPS) {
         const float inv_m = 1.f / pm.w;
         float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
         const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
+        // forward chain statics -> agent -> boundary with the intermediate velocities kept (MPM:388-398)
+        float vc[5][3];
+        vc[0][0] = v[0]; vc[0][1] = v[1]; vc[0][2] = v[2];
+#pragma unroll
+        for (int si = 0; si < 4; si++) {
+          if (si < P.col.n_statics) sdf_collide<false>(P.col.statics[si], false, nullptr, nullptr, nullptr, nullptr, P.dt, pos, vc[si], vc[si + 1], nullptr, nullptr, nullptr, nullptr, nullptr);
+          else { vc[si + 1][0] = vc[si][0]; vc[si + 1][1] = vc[si][1]; vc[si + 1][2] = vc[si][2]; }
+        }
+        float vl[3] = {vc[4][0], vc[4][1], vc[4][2]};
+        if (agent_grid) agent_collide<false>(P, f, pos, vc[4], vl, nullptr, nullptr, nullptr, nullptr, nullptr);
         float fac[3];
-        boundary_v(P, pos, v, fac);
+        boundary_v(P, pos, vl, fac);
         const float4 gv = P.ggrid_v[g];
-        const float vb0 = gv.x * fac[0], vb1 = gv.y * fac[1], vb2 = gv.z * fac[2];
-        out.x = vb0 * inv_m; out.y = vb1 * inv_m; out.z = vb2 * inv_m;
-        out.w = -(pm.x * vb0 + pm.y * vb1 + pm.z * vb2) * inv_m * inv_m;
+        float vb[3] = {gv.x * fac[0], gv.y * fac[1], gv.z * fac[2]};
+        if (agent_grid) {
+          float o[3], gvv[3] = {0.f, 0.f, 0.f}, gpp[3] = {0.f, 0.f, 0.f};  // node positions are constants: gpp is dropped
+          agent_collide<true>(P, f, pos, vc[4], o, vb, gvv, gpp, pg0, pg1);
+          vb[0] = gvv[0]; vb[1] = gvv[1]; vb[2] = gvv[2];
+        }
+#pragma unroll
+        for (int si = 3; si >= 0; si--) {
+          if (si < P.col.n_statics) {
+            float o[3], gvv[3] = {0.f, 0.f, 0.f}, gpp[3] = {0.f, 0.f, 0.f}, d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f};
+            sdf_collide<true>(P.col.statics[si], false, nullptr, nullptr, nullptr, nullptr, P.dt, pos, vc[si], o, vb, gvv, gpp, d0, d1);
+            vb[0] = gvv[0]; vb[1] = gvv[1]; vb[2] = gvv[2];
+          }
+        }
+        out.x = vb[0] * inv_m; out.y = vb[1] * inv_m; out.z = vb[2] * inv_m;
+        out.w = -(pm.x * vb[0] + pm.y * vb[1] + pm.z * vb[2]) * inv_m * inv_m;
       }
+      if (agent_grid && P.col.egpos) reduce_pose_grad(P.col.egpos, f, pg0, pg1);
       P.ggrid_pm[g] = out;
       if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+}
+
+// =============================================================================================
+// agent.collide(f, x + dt v', v', dt).grad at particle level (MPM:419-422 inside g2p.grad): pre-pass that rewrites the
+// frame-(f+1) adjoint in place so that the two kernels below see the adjoint of the PRE-collision v' and of x_tmp:
+//   gx' <- gx' + gxt ,  gv' <- gvpre - dt * gx'     (then gv'+dt*gx' = gvpre + dt*gxt, as the chain rule requires)
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_collide_particle_grad(const KParams P, const int f, const int gin) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
+  if (s < P.N) {
+    const float4 a0 = P.pa[pa_idx(P, f, 0, s)];
+    const float x[3] = {a0.x, a0.y, a0.z};
+    int b[3]; float fx[3];
+    if ((__float_as_int(a0.w) & 1) && base_fx(P, x, b, fx)) {
+      float w[3][3]; bspline(fx, w);
+      float nv[3]; Mat3 nC;
+      const float4* gvp = P.grid_v + ((b[0] * P.n + b[1]) * P.n + b[2]);
+      const int n = P.n;
+      g2p_gather(fx, w, [&](int c) { return gvp + ((c / 3) * n + (c % 3)) * n; }, nv, nC, 4.f * P.inv_dx);
+      float4 gx4 = P.ga[pa_idx(P, gin, 0, s)], gv4 = P.ga[pa_idx(P, gin, 1, s)];
+      const float gout[3] = {gv4.x + P.dt * gx4.x, gv4.y + P.dt * gx4.y, gv4.z + P.dt * gx4.z};
+      const float xt[3] = {x[0] + P.dt * nv[0], x[1] + P.dt * nv[1], x[2] + P.dt * nv[2]};
+      float o[3], gvpre[3] = {0.f, 0.f, 0.f}, gxt[3] = {0.f, 0.f, 0.f};
+      agent_collide<true>(P, f, xt, nv, o, gout, gvpre, gxt, g0, g1);
+      gv4.x = gvpre[0] - P.dt * gx4.x; gv4.y = gvpre[1] - P.dt * gx4.y; gv4.z = gvpre[2] - P.dt * gx4.z;
+      gx4.x += gxt[0]; gx4.y += gxt[1]; gx4.z += gxt[2];
+      P.ga[pa_idx(P, gin, 0, s)] = gx4; P.ga[pa_idx(P, gin, 1, s)] = gv4;
+    }
+  }
+  if (P.col.egpos) reduce_pose_grad(P.col.egpos, f, g0, g1);
 }
 
 // =============================================================================================
@@ -337,7 +395,7 @@ static int check_bound_b(FmpmHandle* h, const char* name) {
   return 0;
 }
 
-int fmpm_grid_op_impl(FmpmHandle* h, int clear_pm, int zero_ggv, void* stream);  // fmpm_forward.cu
+int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, void* stream);  // fmpm_forward.cu
 
 static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, void* stream) {
   if (check_bound_b(h, "fmpm_g2p_grad_scatter")) return 1;
@@ -354,16 +412,16 @@ static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, 
   return 0;
 }
 extern "C" int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) { return g2p_grad_scatter_impl(h, f, gin, 1, stream); }
-static int grid_op_grad_impl(FmpmHandle* h, int clear_pm, void* stream) {
+static int grid_op_grad_impl(FmpmHandle* h, int f, int clear_pm, void* stream) {
   if (check_bound_b(h, "fmpm_grid_op_grad")) return 1;
   KParams P = make_kparams(h);
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
-  k_grid_op_grad<<<grid, 256, 0, (cudaStream_t)stream>>>(P, clear_pm);
+  k_grid_op_grad<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op_grad");
   return 0;
 }
-extern "C" int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream) { (void)f; return grid_op_grad_impl(h, 0, stream); }
+extern "C" int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream) { return grid_op_grad_impl(h, f, 0, stream); }
 extern "C" int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void* stream) {
   if (check_bound_b(h, "fmpm_particle_grad")) return 1;
   KParams P = make_kparams(h);
@@ -376,9 +434,13 @@ extern "C" int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* 
   if (check_bound_b(h, "fmpm_substep_grad")) return 1;
   if (gin == gout || (gin | gout) & ~1) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad: gin/gout must be distinct in {0,1}"); return 1; }
   // recompute the forward grid of frame f (accumulators are clear on entry), zeroing the v_out adjoint of the active blocks
-  if (fmpm_p2g(h, f, 0, stream) || fmpm_grid_op_impl(h, 0, 1, stream)) return 1;
+  if (fmpm_p2g(h, f, 0, stream) || fmpm_grid_op_impl(h, f, 0, 1, stream)) return 1;
+  if (h->col.has_rigid && h->col.collide_type != 1) {  // particle-level agent collide: fold its adjoint into the frame-(f+1) adjoint
+    KParams P = make_kparams(h);
+    if (P.N > 0) { k_collide_particle_grad<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad(collide)"); }
+  }
   // adjoint: grid scatter, grid_op.grad (also leaves the accumulators clear for the next substep), per-particle part
-  if (g2p_grad_scatter_impl(h, f, gin, 0, stream) || grid_op_grad_impl(h, 1, stream)) return 1;
+  if (g2p_grad_scatter_impl(h, f, gin, 0, stream) || grid_op_grad_impl(h, f, 1, stream)) return 1;
   return fmpm_particle_grad(h, f, gin, gout, stream);
 }
 extern "C" int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjector* inj, const FmpmEffector* e, int act_id,

@@ -8,9 +8,17 @@
 
 #define FMPM_EPS 1e-12f  // configs/macros.py:213
 
+struct SdfDev { const float* vox; int res; float T[12]; float Ainv[9]; float friction, softness; };
+struct CollidersDev {
+  int n_statics; SdfDev statics[4];
+  int has_rigid; int collide_type; SdfDev rigid;
+  const float* epos; const float* equat; float* egpos;
+};
+
 struct FmpmHandle {
   FmpmConfig cfg;
   FmpmBuffers buf;
+  CollidersDev col;
   bool bound;
   char err[512];
   int sm_count;
@@ -30,6 +38,7 @@ struct KParams {
   float4* grid_pm; float4* grid_v; float4* ggrid_v; float4* ggrid_pm;
   const float4* mats;  // (mu, lam, mass, cls-as-int-bits)
   int* blk_flags; int* blk_list; int* blk_count; int nb;  // sparse grid: 8^3-node blocks
+  CollidersDev col;
 };
 
 static inline KParams make_kparams(const FmpmHandle* h) {
@@ -47,6 +56,7 @@ static inline KParams make_kparams(const FmpmHandle* h) {
   P.grid_pm = (float4*)h->buf.grid_pm; P.grid_v = (float4*)h->buf.grid_v;
   P.ggrid_v = (float4*)h->buf.ggrid_v; P.ggrid_pm = (float4*)h->buf.ggrid_pm;
   P.mats = (const float4*)h->buf.materials;
+  P.col = h->col;
   P.blk_flags = (int*)h->buf.blk_flags; P.blk_list = (int*)h->buf.blk_list; P.blk_count = (int*)h->buf.blk_count; P.nb = c.n_grid / 8;
   return P;
 }

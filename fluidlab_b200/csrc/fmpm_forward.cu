@@ -19,6 +19,7 @@
 #include "fmpm_common.cuh"
 
 #include "fmpm_scatter.cuh"
+#include "fmpm_sdf.cuh"
 
 #ifndef P2G_WARPS
 #define P2G_WARPS 4
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(1024) k_compact_blocks(const KParams P) {
 
 // MPM:380-398 on the active blocks; optionally clears the (momentum, mass) accumulators for the next substep
 // and zeroes the v_out adjoint of the same blocks (backward pass).
-__global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int clear_pm, const int zero_ggv) {
+__global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, const int clear_pm, const int zero_ggv) {
   const int count = P.blk_count[0];
   const int n = P.n, nb = P.nb;
   for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
@@ -138,6 +139,14 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int clea
         const float inv_m = 1.f / pm.w;
         float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
         const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
+        for (int si = 0; si < P.col.n_statics; si++) {  // statics[i].collide, MPM:388-390
+          float o[3]; sdf_collide<false>(P.col.statics[si], false, nullptr, nullptr, nullptr, nullptr, P.dt, pos, v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
+          v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
+        }
+        if (P.col.has_rigid && P.col.collide_type >= 1) {  // agent.collide at grid level, MPM:393-395
+          float o[3]; agent_collide<false>(P, f, pos, v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
+          v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
+        }
         float fac[3];
         boundary_v(P, pos, v, fac);
         out = make_float4(v[0], v[1], v[2], 0.f);
@@ -153,42 +162,6 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int clea
 // g2p (+ advect_used, process_unused_particles, advect_kernel)
 // =============================================================================================
 #define G2P_WARPS 4
-
-// Separable evaluation of  v' = sum w g,  C' = 4 inv_dx sum w g (o - fx)^T  (MPM:409-416): reduce the three nodes of a
-// z-column first (G0 = sum_k wz g, G1 = sum_k wz (k - fz) g), then fold the 9 columns in.  Packed FFMA2 throughout.
-// `col(c)` returns a pointer to the three consecutive v_out nodes of stencil column c = i*3+j for this particle.
-template <class ColFn>
-__device__ __forceinline__ void g2p_gather(const float* fx, const float w[3][3], ColFn col, float* nv, Mat3& nC, const float c4) {
-  const float2 wz0 = make_float2(w[0][2], w[0][2]), wz1 = make_float2(w[1][2], w[1][2]), wz2 = make_float2(w[2][2], w[2][2]);
-  const float wd0 = w[0][2] * (0.f - fx[2]), wd1 = w[1][2] * (1.f - fx[2]), wd2 = w[2][2] * (2.f - fx[2]);
-  const float2 wzd0 = make_float2(wd0, wd0), wzd1 = make_float2(wd1, wd1), wzd2 = make_float2(wd2, wd2);
-  const float2 wzz0 = make_float2(w[0][2], wd0), wzz1 = make_float2(w[1][2], wd1), wzz2 = make_float2(w[2][2], wd2);
-  float2 v01 = make_float2(0.f, 0.f), v2c22 = make_float2(0.f, 0.f), c02_12 = make_float2(0.f, 0.f);
-  float2 c00_10 = make_float2(0.f, 0.f), c01_11 = make_float2(0.f, 0.f), c20_21 = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const float4* c = col(i * 3 + j);
-      const float4 g0 = c[0], g1 = c[1], g2 = c[2];
-      float2 G0xy = fmul2(make_float2(g0.x, g0.y), wz0); G0xy = ffma2(make_float2(g1.x, g1.y), wz1, G0xy); G0xy = ffma2(make_float2(g2.x, g2.y), wz2, G0xy);
-      float2 G1xy = fmul2(make_float2(g0.x, g0.y), wzd0); G1xy = ffma2(make_float2(g1.x, g1.y), wzd1, G1xy); G1xy = ffma2(make_float2(g2.x, g2.y), wzd2, G1xy);
-      float2 Gz = fmul2(make_float2(g0.z, g0.z), wzz0); Gz = ffma2(make_float2(g1.z, g1.z), wzz1, Gz); Gz = ffma2(make_float2(g2.z, g2.z), wzz2, Gz);  // (G0_z, G1_z)
-      const float wxy = w[i][0] * w[j][1];
-      const float bx = wxy * ((float)i - fx[0]), by = wxy * ((float)j - fx[1]);
-      const float2 a2 = make_float2(wxy, wxy);
-      v01 = ffma2(a2, G0xy, v01);
-      v2c22 = ffma2(a2, Gz, v2c22);
-      c02_12 = ffma2(a2, G1xy, c02_12);
-      c00_10 = ffma2(make_float2(bx, bx), G0xy, c00_10);
-      c01_11 = ffma2(make_float2(by, by), G0xy, c01_11);
-      c20_21 = ffma2(make_float2(bx, by), make_float2(Gz.x, Gz.x), c20_21);
-    }
-  nv[0] = v01.x; nv[1] = v01.y; nv[2] = v2c22.x;
-  nC.m[0] = c4 * c00_10.x; nC.m[1] = c4 * c01_11.x; nC.m[2] = c4 * c02_12.x;
-  nC.m[3] = c4 * c00_10.y; nC.m[4] = c4 * c01_11.y; nC.m[5] = c4 * c02_12.y;
-  nC.m[6] = c4 * c20_21.x; nC.m[7] = c4 * c20_21.y; nC.m[8] = c4 * v2c22.y;
-}
 
 __global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const int f) {
   __shared__ float4 tiles[G2P_WARPS][9 * G2P_ZMAX];
@@ -221,6 +194,11 @@ __global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const i
     const float4* gv = P.grid_v + ((b[0] * P.n + b[1]) * P.n + b[2]);
     const int n = P.n;
     g2p_gather(fx, w, [&](int c) { return gv + ((c / 3) * n + (c % 3)) * n; }, nv, nC, c4);
+  }
+  if (P.col.has_rigid && P.col.collide_type != 1) {  // agent.collide at particle level (the default), MPM:419-422
+    const float xt[3] = {x[0] + P.dt * nv[0], x[1] + P.dt * nv[1], x[2] + P.dt * nv[2]};
+    float o[3]; agent_collide<false>(P, f, xt, nv, o, nullptr, nullptr, nullptr, nullptr, nullptr);
+    nv[0] = o[0]; nv[1] = o[1]; nv[2] = o[2];
   }
   const float nx[3] = {x[0] + P.dt * nv[0], x[1] + P.dt * nv[1], x[2] + P.dt * nv[2]};  // advect_kernel MPM:505
   store_A(P.pa, P, f + 1, s, nx, meta, nv, nC);
@@ -293,7 +271,7 @@ extern "C" int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream) {
   return 0;
 }
 
-int fmpm_grid_op_impl(FmpmHandle* h, int clear_pm, int zero_ggv, void* stream) {
+int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, void* stream) {
   if (check_bound(h, "fmpm_grid_op")) return 1;
   KParams P = make_kparams(h);
   if (!P.blk_flags || !P.blk_list || !P.blk_count) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block buffers were not bound"); return 1; }
@@ -304,13 +282,12 @@ int fmpm_grid_op_impl(FmpmHandle* h, int clear_pm, int zero_ggv, void* stream) {
   k_compact_blocks<<<(nblk + 1023) / 1024, 1024, 0, (cudaStream_t)stream>>>(P);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op(compact)");
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
-  k_grid_op<<<grid, 256, 0, (cudaStream_t)stream>>>(P, clear_pm, zero_ggv);
+  k_grid_op<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm, zero_ggv);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op");
   return 0;
 }
 extern "C" int fmpm_grid_op(FmpmHandle* h, int f, int clear_pm, void* stream) {
-  (void)f;
-  return fmpm_grid_op_impl(h, clear_pm, 0, stream);
+  return fmpm_grid_op_impl(h, f, clear_pm, 0, stream);
 }
 
 extern "C" int fmpm_g2p(FmpmHandle* h, int f, void* stream) {

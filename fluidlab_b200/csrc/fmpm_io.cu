@@ -16,6 +16,7 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
   if (!h) return 1;
   h->cfg = *cfg; h->bound = false; h->err[0] = 0; h->sm_count = 148;
   memset(&h->buf, 0, sizeof(h->buf));
+  memset(&h->col, 0, sizeof(h->col));
   *out = h;
   if (cfg->n_grid < 4 || cfg->n_particles < 0 || cfg->max_substeps_local < 1 || cfg->n_materials < 1 || cfg->n_materials > 256) {
     snprintf(h->err, sizeof(h->err), "fmpm_create: invalid config (n_grid %d, n_particles %d, T %d, n_materials %d)", cfg->n_grid,
@@ -33,6 +34,32 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
 }
 extern "C" void fmpm_destroy(FmpmHandle* h) { delete h; }
 extern "C" const char* fmpm_last_error(FmpmHandle* h) { return h ? h->err : "null handle"; }
+
+static void fill_sdf(SdfDev& d, const FmpmSdfMesh& m) {
+  d.vox = (const float*)m.voxels; d.res = m.res; d.friction = m.friction; d.softness = m.softness;
+  for (int i = 0; i < 12; i++) d.T[i] = m.T_mesh_to_voxels[i];
+  // R_voxels_to_mesh = T[:3,:3].inverse() evaluated in f32 like the reference kernels do (static.py:59)
+  const float* T = m.T_mesh_to_voxels;
+  const float a = T[0], b = T[1], c = T[2], d0 = T[4], e = T[5], f = T[6], g = T[8], hh = T[9], i = T[10];
+  const float det = a * (e * i - f * hh) - b * (d0 * i - f * g) + c * (d0 * hh - e * g);
+  d.Ainv[0] = (e * i - f * hh) / det; d.Ainv[1] = (c * hh - b * i) / det; d.Ainv[2] = (b * f - c * e) / det;
+  d.Ainv[3] = (f * g - d0 * i) / det; d.Ainv[4] = (a * i - c * g) / det; d.Ainv[5] = (c * d0 - a * f) / det;
+  d.Ainv[6] = (d0 * hh - e * g) / det; d.Ainv[7] = (b * g - a * hh) / det; d.Ainv[8] = (a * e - b * d0) / det;
+}
+extern "C" int fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c) {
+  if (!h || !c) return 1;
+  if (c->n_statics < 0 || c->n_statics > 4) { snprintf(h->err, sizeof(h->err), "fmpm_set_colliders: at most 4 statics (got %d)", c->n_statics); return 1; }
+  if (c->has_rigid && (!c->pos || !c->quat || !c->rigid.voxels)) { snprintf(h->err, sizeof(h->err), "fmpm_set_colliders: rigid collider needs voxels, pos and quat"); return 1; }
+  memset(&h->col, 0, sizeof(h->col));
+  h->col.n_statics = c->n_statics;
+  for (int s = 0; s < c->n_statics; s++) {
+    if (!c->statics[s].voxels || c->statics[s].res < 2) { snprintf(h->err, sizeof(h->err), "fmpm_set_colliders: static %d has no SDF volume", s); return 1; }
+    fill_sdf(h->col.statics[s], c->statics[s]);
+  }
+  h->col.has_rigid = c->has_rigid; h->col.collide_type = c->collide_type;
+  if (c->has_rigid) { fill_sdf(h->col.rigid, c->rigid); h->col.epos = (const float*)c->pos; h->col.equat = (const float*)c->quat; h->col.egpos = (float*)c->gpos; }
+  return 0;
+}
 
 static int sort_bits(const FmpmHandle* h) {
   long long G = (long long)h->cfg.n_grid * h->cfg.n_grid * h->cfg.n_grid;  // keys in [0, G]

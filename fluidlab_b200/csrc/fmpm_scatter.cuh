@@ -193,3 +193,40 @@ __device__ __forceinline__ void footprint_load(const float4* __restrict__ grid, 
   }
   __syncwarp();
 }
+
+// Separable evaluation of  v' = sum w g,  C' = 4 inv_dx sum w g (o - fx)^T  (MPM:409-416): reduce the three nodes of a
+// z-column first (G0 = sum_k wz g, G1 = sum_k wz (k - fz) g), then fold the 9 columns in.  Packed FFMA2 throughout.
+// `col(c)` returns a pointer to the three consecutive v_out nodes of stencil column c = i*3+j for this particle.
+template <class ColFn>
+__device__ __forceinline__ void g2p_gather(const float* fx, const float w[3][3], ColFn col, float* nv, Mat3& nC, const float c4) {
+  const float2 wz0 = make_float2(w[0][2], w[0][2]), wz1 = make_float2(w[1][2], w[1][2]), wz2 = make_float2(w[2][2], w[2][2]);
+  const float wd0 = w[0][2] * (0.f - fx[2]), wd1 = w[1][2] * (1.f - fx[2]), wd2 = w[2][2] * (2.f - fx[2]);
+  const float2 wzd0 = make_float2(wd0, wd0), wzd1 = make_float2(wd1, wd1), wzd2 = make_float2(wd2, wd2);
+  const float2 wzz0 = make_float2(w[0][2], wd0), wzz1 = make_float2(w[1][2], wd1), wzz2 = make_float2(w[2][2], wd2);
+  float2 v01 = make_float2(0.f, 0.f), v2c22 = make_float2(0.f, 0.f), c02_12 = make_float2(0.f, 0.f);
+  float2 c00_10 = make_float2(0.f, 0.f), c01_11 = make_float2(0.f, 0.f), c20_21 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float4* c = col(i * 3 + j);
+      const float4 g0 = c[0], g1 = c[1], g2 = c[2];
+      float2 G0xy = fmul2(make_float2(g0.x, g0.y), wz0); G0xy = ffma2(make_float2(g1.x, g1.y), wz1, G0xy); G0xy = ffma2(make_float2(g2.x, g2.y), wz2, G0xy);
+      float2 G1xy = fmul2(make_float2(g0.x, g0.y), wzd0); G1xy = ffma2(make_float2(g1.x, g1.y), wzd1, G1xy); G1xy = ffma2(make_float2(g2.x, g2.y), wzd2, G1xy);
+      float2 Gz = fmul2(make_float2(g0.z, g0.z), wzz0); Gz = ffma2(make_float2(g1.z, g1.z), wzz1, Gz); Gz = ffma2(make_float2(g2.z, g2.z), wzz2, Gz);  // (G0_z, G1_z)
+      const float wxy = w[i][0] * w[j][1];
+      const float bx = wxy * ((float)i - fx[0]), by = wxy * ((float)j - fx[1]);
+      const float2 a2 = make_float2(wxy, wxy);
+      v01 = ffma2(a2, G0xy, v01);
+      v2c22 = ffma2(a2, Gz, v2c22);
+      c02_12 = ffma2(a2, G1xy, c02_12);
+      c00_10 = ffma2(make_float2(bx, bx), G0xy, c00_10);
+      c01_11 = ffma2(make_float2(by, by), G0xy, c01_11);
+      c20_21 = ffma2(make_float2(bx, by), make_float2(Gz.x, Gz.x), c20_21);
+    }
+  nv[0] = v01.x; nv[1] = v01.y; nv[2] = v2c22.x;
+  nC.m[0] = c4 * c00_10.x; nC.m[1] = c4 * c01_11.x; nC.m[2] = c4 * c02_12.x;
+  nC.m[3] = c4 * c00_10.y; nC.m[4] = c4 * c01_11.y; nC.m[5] = c4 * c02_12.y;
+  nC.m[6] = c4 * c20_21.x; nC.m[7] = c4 * c20_21.y; nC.m[8] = c4 * v2c22.y;
+}
+

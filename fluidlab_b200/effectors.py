@@ -257,6 +257,9 @@ class BallInjector(Injector):
 
 
 class Rigid(Effector):
-    def __init__(self, **kwargs):
-        super().__init__(**kwargs)
-        raise NotImplementedError('Rigid (SDF mesh) effectors are not built yet (SURVEY.md §8 a9.3)')
+    """Rigid end-effector with an SDF mesh (effectors/rigid.py:11-38): `collide` = mesh.collide (meshes/dynamic.py:93-121),
+    evaluated inside the CUDA kernels (csrc/fmpm_sdf.cuh) at particle and/or grid level."""
+
+    def setup_mesh(self, **kwargs):
+        from .meshes import Dynamic
+        self.mesh = Dynamic(container=self, has_dynamics=True, **kwargs)

@@ -98,8 +98,6 @@ class MPMSimulator:
             self.boundary = create_boundary()
         self.n_statics = len(statics) if statics is not None else 0
         self.statics = statics
-        if self.n_statics > 0 and any(getattr(s, 'has_dynamics', False) for s in statics):
-            raise NotImplementedError('SDF statics with has_dynamics=True are not built yet (SURVEY.md §8 a9.2)')
         if smoke_field is not None:
             raise NotImplementedError('SmokeField is out of scope of this hot path (SURVEY.md §8f)')
         self.smoke_field = None
@@ -112,6 +110,8 @@ class MPMSimulator:
         else:
             self.has_particles = False
             self.n_particles = 0
+        if self.has_particles:
+            self.register_colliders()
         self.actions_buffer = []
         self.ckpt_ram = dict()
         self.ckpt_dir = os.path.join('/tmp', 'fluidlab', self.sim_id)
@@ -213,6 +213,24 @@ class MPMSimulator:
         b.sort_tmp, b.sort_tmp_bytes = p(self._sort_tmp), self._sort_tmp.numel()
         b.blk_flags, b.blk_list, b.blk_count = p(self._blk_flags), p(self._blk_list), p(self._blk_count)
         self._ck(self._lib.fmpm_bind(self._h, C.byref(b)), 'fmpm_bind')
+
+    def register_colliders(self):
+        """(re)send the SDF colliders to the library: statics with dynamics (MPM:388-390) and the agent's Rigid mesh
+        (agents/agent_rigid.py:21-23).  Called at build and again by AgentRigid.build once its effector owns device arrays."""
+        col = _lib.FmpmColliders()
+        dyn = [s for s in (self.statics or []) if getattr(s, 'has_dynamics', False)]
+        assert len(dyn) <= 4, 'at most 4 colliding statics'
+        col.n_statics = len(dyn)
+        for i, s in enumerate(dyn):
+            col.statics[i] = s.device_struct(_lib, self.device)
+        rigid = getattr(self.agent, 'rigid', None) if self.agent is not None else None
+        if rigid is not None and getattr(rigid, 'pos', None) is not None:
+            col.has_rigid = 1
+            col.collide_type = {'particle': 0, 'grid': 1, 'both': 2}[self.agent.collide_type]
+            col.rigid = rigid.mesh.device_struct(_lib, self.device)
+            col.pos, col.quat, col.gpos = rigid.pos.data_ptr(), rigid.quat.data_ptr(), rigid.gpos.data_ptr()
+        self._colliders = col  # keep the voxel tensors alive through the mesh objects
+        self._ck(self._lib.fmpm_set_colliders(self._h, C.byref(col)), 'fmpm_set_colliders')
 
     def _ensure_grad_buffers(self):
         if self._ga is None:

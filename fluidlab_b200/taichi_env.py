@@ -6,6 +6,7 @@ import numpy as np
 from .simulator import MPMSimulator
 from .bodies import Bodies
 from .macros import DTYPE_NP
+from .meshes import Statics
 from . import agents as _agents
 
 
@@ -28,7 +29,7 @@ class TaichiEnv:
                                       max_substeps_global=max_substeps_global, gravity=gravity, ckpt_dest=ckpt_dest,
                                       device=device, sort_every=sort_every)
         self.agent = None
-        self.statics = []
+        self.statics = Statics()
         self.particle_bodies = Bodies(dim=dim, particle_density=particle_density)
         self.renderer = None
         self.loss = None
@@ -50,10 +51,8 @@ class TaichiEnv:
     def setup_boundary(self, **kwargs):
         self.simulator.setup_boundary(**kwargs)
 
-    def add_static(self, **kwargs):
-        if kwargs.get('has_dynamics', False):
-            raise NotImplementedError('mesh statics with dynamics are not built yet (SURVEY.md §8 a9.2)')
-        self.statics.append(_Cfg(kwargs))  # visual-only statics do not touch the simulation
+    def add_static(self, **kwargs):  # taichi_env.py:89-90
+        self.statics.add_static(**kwargs)  # statics without dynamics are visual only and never reach the kernels
 
     def add_body(self, **kwargs):
         self.particle_bodies.add_body(**kwargs)
@@ -67,7 +66,7 @@ class TaichiEnv:
             self.n_particles = len(self.particles['x']); self.has_particles = True
         else:
             self.n_particles = 0; self.has_particles = False
-        self.simulator.build(self.agent, self.smoke_field, [], self.particles)
+        self.simulator.build(self.agent, self.smoke_field, self.statics, self.particles)
         if self.agent is not None:
             self.agent.build(self.simulator)
         if self.loss is not None:

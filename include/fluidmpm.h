@@ -105,6 +105,24 @@ typedef struct {
   int n_act_range;
 } FmpmInjector;
 
+/* SDF mesh colliders: fluidlab/fluidengine/meshes/static.py:26-104 (Static.collide, applied in grid_op MPM:388-390) and
+ * meshes/dynamic.py:29-121 (Dynamic.collide of the agent's Rigid effector, agents/agent_rigid.py:21-23, applied per particle in
+ * g2p MPM:419-422 and/or per node in grid_op MPM:393-395 according to Agent.collide_type, agents/agent.py:17). */
+typedef struct {
+  const void* voxels;            /* float[res^3], the baked SDF volume (utils/mesh.py:63-87) */
+  int res;
+  float T_mesh_to_voxels[16];    /* row-major 4x4, already multiplied by inv(T_init) (meshes/mesh.py:121-127) */
+  float friction, softness;      /* configs/macros.py:131-141 ; mesh cfg `softness` */
+} FmpmSdfMesh;
+typedef struct {
+  int n_statics; FmpmSdfMesh statics[4];
+  int has_rigid; int collide_type;          /* 0 particle, 1 grid, 2 both */
+  FmpmSdfMesh rigid;
+  const void* pos; const void* quat;        /* the Rigid effector's pose arrays float[(T+1)*3], float[(T+1)*4] */
+  void* gpos;                               /* adjoint of pos (may be NULL when grads are never used) */
+} FmpmColliders;
+int  fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c);
+
 int  fmpm_create(const FmpmConfig* cfg, FmpmHandle** out);
 void fmpm_destroy(FmpmHandle* h);
 int  fmpm_bind(FmpmHandle* h, const FmpmBuffers* b);

@@ -337,3 +337,76 @@ def test_c1_latteart_v0_full_size_100_substeps():
     assert rel(a['v'][act], b['v'][act]) < 1e-4, rel(a['v'][act], b['v'][act])
     assert np.array_equal(a['x'][~act], b['x'][~act].astype(np.float32))  # parked milk untouched at NOWHERE
     assert np.allclose(a['agent'][0][:7], o.effector_state(0, o.cur_substep_local)[:7], atol=1e-6)
+
+
+@pytest.mark.parametrize('collide_type,softness,with_static', [('particle', 100.0, False), ('both', 100.0, True), ('grid', 0.0, True)])
+def test_sdf_colliders_forward_and_dloss_daction(collide_type, softness, with_static):
+    """AgentRigid (Dynamic.collide, meshes/dynamic.py:93-121) + Static.collide (meshes/static.py:82-104) through TaichiEnv:
+    forward state vs the fp32 oracle and dLoss/dAction vs the fp64 oracle.  The contact map is only piecewise smooth
+    (hit / influence thresholds), so particles sitting on a threshold may flip between fp32 implementations: bars are
+    1e-4 (x), 1e-3 (gradient)."""
+    _need_gpu()
+    from conftest import sphere_sdf, box_sdf
+    from fluidlab_b200 import TaichiEnv, ShapeMatchingLoss
+    from oracle import oracle as orc
+    n_grid, N, n_steps, T = 32, 4000, 2, 20
+    rng = np.random.RandomState(51)
+    x = rng.uniform((0.40, 0.42, 0.40), (0.60, 0.58, 0.60), size=(N, 3))
+    P = make_particles(x, M.ELASTIC, n_grid)
+    vox, Tm = sphere_sdf(0.09, 0.2)
+    env = TaichiEnv(quality=n_grid / 64, max_substeps_local=T, gravity=(0.0, -10.0, 0.0), horizon=n_steps)
+    ebnd = dict(type='cube', lower=(0.05, 0.05, 0.05), upper=(0.95, 0.95, 0.95))
+    env.setup_agent(dict(type='AgentRigid', params=dict(collide_type=collide_type), effectors=[dict(
+        type='Rigid', params=dict(init_pos=(0.5, 0.64, 0.5), init_euler=(0.0, 0.0, 0.0), action_dim=3),
+        mesh=dict(file='sphere.obj', material=M.STIRRER, softness=softness, sdf=dict(voxels=vox, T_mesh_to_voxels=Tm)), boundary=ebnd)]))
+    bnd = dict(type='cube', lower=(0.25, 0.25, 0.25), upper=(0.75, 0.75, 0.75))
+    env.setup_boundary(**bnd)
+    if with_static:
+        bv, bT = box_sdf((0.3, 0.05, 0.3), 0.4)
+        env.add_static(file='box.obj', material=M.CUP, has_dynamics=True, pos=(0.5, 0.33, 0.5), sdf=dict(voxels=bv, T_mesh_to_voxels=bT))
+    env.particle_bodies.get = lambda: P
+    tgt = [rng.uniform(0.4, 0.6, size=x.shape).astype(np.float32) for _ in range(n_steps)]
+    env.setup_loss(loss_cls=ShapeMatchingLoss, matching_mat=M.ELASTIC, temporal_range_type='all', target=tgt, weights={'chamfer': 1.0})
+    env.build()
+    actions = np.array([[0.004, -0.03, 0.002], [-0.003, -0.03, 0.004]], dtype=np.float32)
+    action_p = np.array([0.5, 0.64, 0.5], dtype=np.float32)
+    st0 = env.get_state()['state']
+    env.set_state(st0, grad_enabled=True)
+    env.apply_agent_action_p(action_p)
+    for i in range(n_steps):
+        env.step(actions[i])
+    fr = env.simulator.get_state()
+    info = env.get_final_loss()
+    env.reset_grad(); env.get_final_loss_grad()
+    for i in range(n_steps - 1, -1, -1):
+        env.step_grad(actions[i])
+    env.apply_agent_action_p_grad(action_p)
+    grad = env.agent.get_grad(n_steps)
+
+    def oracle(prec):
+        o = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=bnd, precision=prec, max_substeps_local=T)
+        o.add_effector(type=0, action_dim=3, boundary=ebnd, max_action_steps=n_steps + 1, init_pos=(0.5, 0.64, 0.5))
+        mesh = env.agent.rigid.mesh
+        o.set_rigid_mesh(mesh.sdf_voxels_np, mesh.T_mesh_to_voxels_np, friction=mesh.friction, softness=mesh.softness, collide_type=collide_type)
+        for s in env.statics:
+            o.add_static(s.sdf_voxels_np, s.T_mesh_to_voxels_np, friction=s.friction)
+        o.enable_grad()
+        o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+        o.set_effector_state(0, 0, np.array([0.5, 0.64, 0.5, 1, 0, 0, 0, 0.0])); o.apply_action_p(action_p)
+        total = 0.0
+        for i in range(n_steps):
+            o.step(actions[i]); total += o.loss_value(o.cur_substep_local, M.ELASTIC, 1.0, tgt[i])
+        ofr = o.get_frame(o.cur_substep_local)
+        o.reset_grad()
+        for i in range(n_steps - 1, -1, -1):
+            o.loss_seed(o.cur_substep_local, M.ELASTIC, 1.0, tgt[i]); o.step_grad(actions[i])
+        o.apply_action_p_grad()
+        return ofr, total, o.get_action_grad(n_steps)
+    o32, _, _ = oracle(32)
+    _, loss64, g64 = oracle(64)
+    moved = np.abs(o32['v']).max()
+    assert moved > 0.5, 'the collider never pushed the material'
+    assert rel(fr['x'], o32['x']) < 1e-4, rel(fr['x'], o32['x'])
+    assert abs(info['loss'] - loss64) < 1e-4 * abs(loss64)
+    assert np.abs(g64).max() > 1e-3
+    assert rel(grad, g64) < 1e-3, (rel(grad, g64), grad, g64)
