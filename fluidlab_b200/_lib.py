@@ -73,7 +73,7 @@ class FmpmSdfMesh(C.Structure):
 
 class FmpmColliders(C.Structure):
     _fields_ = [("n_statics", C.c_int), ("statics", FmpmSdfMesh * 4), ("has_rigid", C.c_int), ("collide_type", C.c_int),
-                ("rigid", FmpmSdfMesh), ("pos", vp), ("quat", vp), ("gpos", vp)]
+                ("rigid", FmpmSdfMesh), ("pos", vp), ("quat", vp), ("gpos", vp), ("collide_y_min", C.c_float)]
 
 
 _I, _F, _U = C.c_int, C.c_float, C.c_uint

@@ -139,3 +139,61 @@ class AgentRigid(Agent):
         self.rigid = self.effectors[0]
         assert self.rigid.mesh is not None, 'Rigid effector without a mesh'
         sim.register_colliders()
+
+
+class AgentIceCreamDynamic(Agent):
+    """Static (Ball)Injector + controllable Rigid cone (agents/agent_icecreamdynamic.py): injects while
+    f_global < inject_till, the cone collides only above y = 0.25, actions are clipped to [-1, 1] / [0.05, 0.95]."""
+    collide_y_min = 0.25
+
+    def __init__(self, inject_till=0, **kwargs):
+        super().__init__(**kwargs)
+        self.inject_till = inject_till
+
+    def build(self, sim):
+        super().build(sim)
+        assert self.n_effectors == 2
+        assert isinstance(self.effectors[0], Injector)
+        self.injector = self.effectors[0]
+        assert isinstance(self.effectors[1], Rigid)
+        self.rigid = self.effectors[1]
+        self.injector.set_act_range(sim.get_used(0))
+        self.injector.finalize()
+        sim.register_colliders()
+
+    def act(self, f, f_global):
+        if f_global < self.inject_till:
+            self.injector.act(f, f_global)
+        else:
+            self.injector.act_id[f + 1] = self.injector.act_id[f]
+
+    def act_grad(self, f, f_global, gin=0):
+        if f_global < self.inject_till:
+            self.injector.act_grad(f, f_global, gin)
+
+    @property
+    def action_dim(self):
+        return self.rigid.action_dim
+
+    @property
+    def state_dim(self):
+        return self.rigid.state_dim
+
+    def set_action(self, s, s_global, n_substeps, action):
+        action = np.asarray(action).reshape(-1).clip(-1, 1)
+        assert len(action) == self.rigid.action_dim
+        # `move` runs for every effector (agent_icecreamdynamic.py:70-72); the injector's action buffer stays zero
+        self.injector.set_action(s, s_global, n_substeps, np.zeros(max(self.injector.action_dim, 1)))
+        self.rigid.set_action(s, s_global, n_substeps, action)
+
+    def set_action_grad(self, s, s_global, n_substeps, action):
+        self.rigid.set_action_grad(s, s_global, n_substeps, action)
+
+    def apply_action_p(self, action_p):
+        self.rigid.apply_action_p(np.asarray(action_p).reshape(-1).clip(0.05, 0.95))
+
+    def apply_action_p_grad(self, action_p):
+        self.rigid.apply_action_p_grad(np.asarray(action_p).reshape(-1).clip(0.05, 0.95))
+
+    def get_grad(self, n):
+        return self.rigid.get_action_grad(0, n)

@@ -13,6 +13,7 @@ struct CollidersDev {
   int n_statics; SdfDev statics[4];
   int has_rigid; int collide_type; SdfDev rigid;
   const float* epos; const float* equat; float* egpos;
+  float y_min;
 };
 
 struct FmpmHandle {

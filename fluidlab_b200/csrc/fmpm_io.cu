@@ -56,7 +56,7 @@ extern "C" int fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c) {
     if (!c->statics[s].voxels || c->statics[s].res < 2) { snprintf(h->err, sizeof(h->err), "fmpm_set_colliders: static %d has no SDF volume", s); return 1; }
     fill_sdf(h->col.statics[s], c->statics[s]);
   }
-  h->col.has_rigid = c->has_rigid; h->col.collide_type = c->collide_type;
+  h->col.has_rigid = c->has_rigid; h->col.collide_type = c->collide_type; h->col.y_min = c->collide_y_min;
   if (c->has_rigid) { fill_sdf(h->col.rigid, c->rigid); h->col.epos = (const float*)c->pos; h->col.equat = (const float*)c->quat; h->col.egpos = (float*)c->gpos; }
   return 0;
 }

@@ -178,6 +178,11 @@ __device__ __forceinline__ void sdf_collide(const SdfDev& M, const bool dynamic,
 template <bool kGrad>
 __device__ __forceinline__ void agent_collide(const KParams& P, const int f, const float* p, const float* v, float* out, const float* gout, float* gv,
                                               float* gp, float* g0, float* g1) {
+  if (!(p[1] > P.col.y_min)) {  // AgentIceCreamDynamic.collide: identity below y_min
+    out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+    if (kGrad) { gv[0] += gout[0]; gv[1] += gout[1]; gv[2] += gout[2]; }
+    return;
+  }
   const float* pos0 = P.col.epos + f * 3; const float* pos1 = P.col.epos + (f + 1) * 3;
   const float* q0 = P.col.equat + f * 4; const float* q1 = P.col.equat + (f + 1) * 4;
   const float a0[3] = {pos0[0], pos0[1], pos0[2]}, a1[3] = {pos1[0], pos1[1], pos1[2]};

@@ -221,6 +221,7 @@ class MPMSimulator:
         dyn = [s for s in (self.statics or []) if getattr(s, 'has_dynamics', False)]
         assert len(dyn) <= 4, 'at most 4 colliding statics'
         col.n_statics = len(dyn)
+        col.collide_y_min = float(getattr(self.agent, 'collide_y_min', -1e30)) if self.agent is not None else -1e30
         for i, s in enumerate(dyn):
             col.statics[i] = s.device_struct(_lib, self.device)
         rigid = getattr(self.agent, 'rigid', None) if self.agent is not None else None

@@ -120,6 +120,7 @@ typedef struct {
   FmpmSdfMesh rigid;
   const void* pos; const void* quat;        /* the Rigid effector's pose arrays float[(T+1)*3], float[(T+1)*4] */
   void* gpos;                               /* adjoint of pos (may be NULL when grads are never used) */
+  float collide_y_min;                      /* the rigid collider only acts where y > this (agents/agent_icecreamdynamic.py:38-43); -1e30 = everywhere */
 } FmpmColliders;
 int  fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c);
 

@@ -353,15 +353,19 @@ template <class R> struct Sim {
   // agent
   int agent_type = 0;     // 0 none, 1 AgentRigid (agents/agent_rigid.py), 2 AgentInjector (agents/agent_injector.py)
   int collide_type = 0;   // 0 particle, 1 grid, 2 both (agents/agent.py:17)
+  int rigid_idx = 0, inj_idx = 0;   // effector indices (AgentIceCreamDynamic: injector 0, rigid 1)
+  int inject_till = 1 << 30;        // agents/agent_icecreamdynamic.py:24-27
   std::vector<Effector<R>> eff;
   std::vector<SdfMesh<R>> statics;   // Statics (meshes/statics.py), collided in grid_op in order (MPM:388-390)
   SdfMesh<R> rigid_mesh;             // mesh of the single Rigid effector (effectors/rigid.py:21-26)
   bool has_rigid = false;
+  bool has_injector = false;
+  R collide_y_min = R(-1e30);        // AgentIceCreamDynamic.collide only acts above y = 0.25 (agents/agent_icecreamdynamic.py:38-43)
 
   // agent.collide(f, pos, v, dt) for AgentRigid -> Rigid.collide -> Dynamic.collide; adjoint accumulates into effector gpos
   inline void agent_collide(int f, const R* p, const R* vin, R* out, const R* gout, R* gvv, R* gpp) {
-    if (agent_type != 1 || !has_rigid) { for (int k = 0; k < 3; k++) out[k] = vin[k]; if (gout) for (int k = 0; k < 3; k++) gvv[k] += gout[k]; return; }
-    Effector<R>& e = eff[0];
+    if (agent_type != 1 || !has_rigid || !(p[1] > collide_y_min)) { for (int k = 0; k < 3; k++) out[k] = vin[k]; if (gout) for (int k = 0; k < 3; k++) gvv[k] += gout[k]; return; }
+    Effector<R>& e = eff[rigid_idx];
     R g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0};
     sdf_collide(rigid_mesh, true, &e.pos[f * 3], &e.quat[f * 4], &e.pos[(f + 1) * 3], &e.quat[(f + 1) * 4], dt, p, vin, out, gout, gvv, gpp, g0, g1);
     if (gout) for (int k = 0; k < 3; k++) {
@@ -600,9 +604,10 @@ template <class R> struct Sim {
     for (int k = 0; k < 3; k++) out[k] = vv[k] + R(2) * (q[0] * uv[k] + uuv[k]);
   }
   void agent_act(int f, int f_global) {  // agents/agent_injector.py:23-32 -> effectors/injector.py:80-105,240-256
-    if (agent_type != 2) return;
-    Effector<R>& e = eff[0];
+    if (!has_injector) return;
+    Effector<R>& e = eff[inj_idx];
     const EffectorCfg& ec = e.cfg;
+    if (f_global >= inject_till) { e.act_id[f + 1] = e.act_id[f]; return; }
     for (int i = 0; i < ec.flux; i++) {
       int pid = e.act_range[e.act_id[f] + i];
       int ridx = ec.locally_random ? f : f_global;
@@ -623,8 +628,8 @@ template <class R> struct Sim {
     e.act_id[f + 1] = e.act_id[f] + ec.flux;
   }
   void agent_act_grad(int f, int f_global) {  // adjoint of the above w.r.t. pos[f] (quat adjoint: not restated)
-    if (agent_type != 2) return;
-    Effector<R>& e = eff[0];
+    if (!has_injector || f_global >= inject_till) return;
+    Effector<R>& e = eff[inj_idx];
     for (int i = 0; i < e.cfg.flux; i++) {
       int pid = e.act_range[e.act_id[f] + i];
       size_t q = pi(f + 1, pid);

@@ -181,7 +181,10 @@ void orc_sdf_collide_eval(int res, const double* vox, const double* T, double fr
   sdf_collide<double>(M, dynamic != 0, io + 6, q, io + 9, q, dt, io, io + 3, out, gout, gv, gp, g0, g1);
   if (gout) for (int k = 0; k < 3; k++) { gio[k] = gp[k]; gio[3 + k] = gv[k]; gio[6 + k] = g0[k]; gio[9 + k] = g1[k]; }
 }
-void orc_set_agent(void* hp, int agent_type) { Handle* h = (Handle*)hp; DISPATCH(h, S.agent_type = agent_type); }
+void orc_set_collide_y_min(void* hp, double y) { Handle* h = (Handle*)hp; DISPATCH(h, S.collide_y_min = (decltype(S.dt))y); }
+void orc_set_agent(void* hp, int agent_type) { Handle* h = (Handle*)hp; DISPATCH(h, (S.agent_type = agent_type, S.has_injector = (agent_type == 2))); }
+void orc_set_agent_layout(void* hp, int inj_idx, int rigid_idx, int inject_till, int has_injector) {
+  Handle* h = (Handle*)hp; DISPATCH(h, (S.inj_idx = inj_idx, S.rigid_idx = rigid_idx, S.inject_till = inject_till, S.has_injector = has_injector != 0)); }
 int orc_add_effector(void* hp, const EffectorCfg* cfg, const double* random_vector, const int* act_range, int n_act_range) {
   Handle* h = (Handle*)hp; int r = -1; DISPATCH(h, r = add_effector_t(S, cfg, random_vector, act_range, n_act_range)); return r; }
 void orc_effector_set_state(void* hp, int ei, int f, const double* st) { Handle* h = (Handle*)hp; DISPATCH(h, eff_set_state_t(S, ei, f, st)); }

@@ -143,6 +143,7 @@ class OracleSim:
         self.grad_enabled = False
         self.has_agent = False
         self.n_eff = 0
+        self.act_eff = 0  # effector that receives the actions
         self.ckpt = {}
         self.actions_buffer = []
 
@@ -210,7 +211,7 @@ class OracleSim:
         self.has_agent = True
         self.n_eff = ei + 1
         self.action_dim = action_dim
-        if type != 0:
+        if type != 0 and ei == 0:
             self.L.orc_set_agent(self.h, 2)
         return ei
 
@@ -225,6 +226,15 @@ class OracleSim:
         ct = {'particle': 0, 'grid': 1, 'both': 2}[collide_type]
         self.L.orc_set_rigid_mesh(self.h, int(vox.shape[0]), _p(vox), _p(T), C.c_double(friction), C.c_double(softness), ct)
 
+    def set_collide_y_min(self, y):
+        self.L.orc_set_collide_y_min(self.h, C.c_double(y))
+
+    def set_icecream_agent(self, inject_till):
+        """AgentIceCreamDynamic layout: effector 0 = (Ball)Injector (never actuated), effector 1 = Rigid (actuated)."""
+        self.L.orc_set_agent_layout(self.h, 0, 1, int(inject_till), 1)
+        self.L.orc_set_collide_y_min(self.h, C.c_double(0.25))
+        self.act_eff = 1
+
     def effector_state(self, ei, f):
         st = np.zeros(8)
         self.L.orc_effector_get_state(self.h, ei, f, _p(st))
@@ -235,14 +245,14 @@ class OracleSim:
         self.L.orc_effector_set_state(self.h, ei, f, _p(s))
 
     def apply_action_p(self, action_p):
-        self.L.orc_effector_apply_action_p(self.h, 0, _p(_d(action_p)))
+        self.L.orc_effector_apply_action_p(self.h, self.act_eff, _p(_d(action_p)))
 
     def apply_action_p_grad(self):
-        self.L.orc_effector_apply_action_p_grad(self.h, 0)
+        self.L.orc_effector_apply_action_p_grad(self.h, self.act_eff)
 
     def get_action_grad(self, n):
         out = np.zeros((n + 1, self.action_dim))
-        self.L.orc_effector_get_action_grad(self.h, 0, n, _p(out))
+        self.L.orc_effector_get_action_grad(self.h, self.act_eff, n, _p(out))
         return out
 
     # ---- stepping contract, MPM:225-252, 721-775
@@ -278,7 +288,9 @@ class OracleSim:
     def step_(self, action=None):
         none_action = action is None
         if not none_action:
-            self.L.orc_effector_set_action(self.h, 0, self.cur_step_local, self.cur_step_global, _p(_d(action)))
+            for ei in range(self.n_eff):  # effectors that are not actuated still run their pose chain with a zero action
+                a = _d(action) if ei == self.act_eff else np.zeros(6)
+                self.L.orc_effector_set_action(self.h, ei, self.cur_step_local, self.cur_step_global, _p(a))
         for _ in range(self.n_substeps):
             self.substep(self.cur_substep_local, none_action)
             self.cur_substep_global += 1
@@ -323,7 +335,7 @@ class OracleSim:
             self.cur_substep_global -= 1
             self.substep_grad(self.cur_substep_local, none_action)
         if not none_action:
-            self.L.orc_effector_set_action_grad(self.h, 0, self.cur_substep_local // self.n_substeps,
+            self.L.orc_effector_set_action_grad(self.h, self.act_eff, self.cur_substep_local // self.n_substeps,
                                                 self.cur_substep_global // self.n_substeps)
 
     # ---- loss (losses/shapematching_loss.py:80-93)

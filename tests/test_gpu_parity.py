@@ -410,3 +410,77 @@ def test_sdf_colliders_forward_and_dloss_daction(collide_type, softness, with_st
     assert abs(info['loss'] - loss64) < 1e-4 * abs(loss64)
     assert np.abs(g64).max() > 1e-3
     assert rel(grad, g64) < 1e-3, (rel(grad, g64), grad, g64)
+
+
+def test_icecream_dynamic_like_scene():
+    """AgentIceCreamDynamic (agents/agent_icecreamdynamic.py, envs/configs/agent_icecreamdynamic.yaml): BallInjector of plasto-elastic
+    ICECREAM (stops at inject_till) + soft Rigid collider acting only above y = 0.25, forward + dLoss/dAction vs the oracle."""
+    _need_gpu()
+    from conftest import sphere_sdf
+    from fluidlab_b200 import TaichiEnv, ShapeMatchingLoss
+    from oracle import oracle as orc
+    n_grid, n_steps, T, flux, inject_till = 32, 3, 20, 4, 17
+    N = 600
+    x = np.tile(np.array(M.NOWHERE), (N, 1))
+    P = make_particles(x, M.ICECREAM, n_grid, used=np.zeros(N, np.int32))
+    vox, Tm = sphere_sdf(0.10, 0.2)
+    cube = dict(type='cube', lower=(0.05, 0.05, 0.05), upper=(0.95, 0.95, 0.95))
+    env = TaichiEnv(quality=n_grid / 64, max_substeps_local=T, gravity=(0.0, -10.0, 0.0), horizon=n_steps)
+    np.random.seed(9)
+    env.setup_agent(dict(type='AgentIceCreamDynamic', params=dict(inject_till=inject_till), effectors=[
+        dict(type='BallInjector', params=dict(locally_random=True, radius=0.035, flux=flux, init_pos=(0.5, 0.62, 0.5), inject_v=(0.0, -0.4, 0.0), action_dim=3), boundary=cube),
+        dict(type='Rigid', params=dict(init_pos=(0.5, 0.46, 0.5), action_dim=3),
+             mesh=dict(file='cone.obj', material=M.CONE, softness=100.0, sdf=dict(voxels=vox, T_mesh_to_voxels=Tm)), boundary=cube)]))
+    env.setup_boundary(**cube)
+    env.particle_bodies.get = lambda: P
+    rng = np.random.RandomState(61)
+    tgt = [rng.uniform(0.4, 0.6, size=x.shape).astype(np.float32) for _ in range(n_steps)]
+    env.setup_loss(loss_cls=ShapeMatchingLoss, matching_mat=M.ICECREAM, temporal_range_type='all', target=tgt, weights={'chamfer': 1.0})
+    env.build()
+    actions = np.array([[0.3, 0.2, -0.2], [-0.2, 0.4, 0.3], [0.1, -0.3, 0.2]], dtype=np.float32) * 0.02
+    action_p = np.array([0.5, 0.46, 0.5], dtype=np.float32)
+    st0 = env.get_state()['state']
+    env.set_state(st0, grad_enabled=True)
+    env.apply_agent_action_p(action_p)
+    for i in range(n_steps):
+        env.step(actions[i])
+    fr = env.simulator.get_state()
+    info = env.get_final_loss()
+    env.reset_grad(); env.get_final_loss_grad()
+    for i in range(n_steps - 1, -1, -1):
+        env.step_grad(actions[i])
+    env.apply_agent_action_p_grad(action_p)
+    grad = env.agent.get_grad(n_steps)
+    assert int(fr['used'].sum()) == flux * inject_till
+
+    def oracle(prec):
+        o = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=cube, precision=prec, max_substeps_local=T)
+        inj = env.agent.injector
+        o.add_effector(type=2, action_dim=3, boundary=cube, radius=0.035, flux=flux, inject_v=(0, -0.4, 0), locally_random=True,
+                       random_vector=inj.random_vector_np, act_range=np.arange(N), max_action_steps=n_steps + 1, init_pos=(0.5, 0.62, 0.5))
+        o.add_effector(type=0, action_dim=3, boundary=cube, max_action_steps=n_steps + 1, init_pos=(0.5, 0.46, 0.5))
+        mesh = env.agent.rigid.mesh
+        o.set_rigid_mesh(mesh.sdf_voxels_np, mesh.T_mesh_to_voxels_np, friction=mesh.friction, softness=mesh.softness, collide_type='particle')
+        o.set_icecream_agent(inject_till)
+        o.enable_grad()
+        o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+        o.set_effector_state(0, 0, np.array([0.5, 0.62, 0.5, 1, 0, 0, 0, 0.0]))
+        o.set_effector_state(1, 0, np.array([0.5, 0.46, 0.5, 1, 0, 0, 0, 0.0]))
+        o.apply_action_p(action_p)
+        total = 0.0
+        for i in range(n_steps):
+            o.step(actions[i]); total += o.loss_value(o.cur_substep_local, M.ICECREAM, 1.0, tgt[i])
+        ofr = o.get_frame(o.cur_substep_local)
+        o.reset_grad()
+        for i in range(n_steps - 1, -1, -1):
+            o.loss_seed(o.cur_substep_local, M.ICECREAM, 1.0, tgt[i]); o.step_grad(actions[i])
+        o.apply_action_p_grad()
+        return ofr, total, o.get_action_grad(n_steps)
+    o32, _, _ = oracle(32)
+    _, loss64, g64 = oracle(64)
+    assert np.array_equal(fr['used'], o32['used'])
+    act = fr['used'] != 0
+    assert rel(fr['x'][act], o32['x'][act]) < 1e-4, rel(fr['x'][act], o32['x'][act])
+    assert abs(info['loss'] - loss64) < 1e-4 * abs(loss64)
+    if np.abs(g64).max() > 1e-6:
+        assert rel(grad, g64) < 2e-3, (rel(grad, g64), grad, g64)
