@@ -81,6 +81,7 @@ class MPMSimulator:
         self.boundary = None
         self.has_particles = False
         self.sort_every = int(sort_every)  # cell-sort period in steps (0 = never)
+        self.use_graphs = True             # replay the 10 substeps of an agent-free step as one CUDA graph per local step index
         if device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError('fluidlab_b200.MPMSimulator needs a CUDA device (B200, sm_100a); there is no CPU fallback')
@@ -358,6 +359,30 @@ class MPMSimulator:
             # to the reference order (MPM:521); agent.move was folded into agent.set_action (pose chain kernel).
             self.agent.act(f, self.cur_substep_global)
 
+    def _graph_substeps(self):
+        """Forward substeps of one step (p2g / compaction / grid_op / g2p x n_substeps, no agent) as a captured CUDA graph, one per
+        local step index (frame pointers are baked into the kernel arguments).  Returns False if capture is unavailable."""
+        if not hasattr(self, '_graphs'):
+            self._graphs = {}
+        s_local = self.cur_step_local
+        f0 = self.cur_substep_local
+        g = self._graphs.get(s_local)
+        if g is None:
+            try:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(self.device)
+                with torch.cuda.graph(g):
+                    for i in range(self.n_substeps):
+                        self._ck(self._lib.fmpm_substep(self._h, f0 + i, self._stream()), 'fmpm_substep')
+                self._graphs[s_local] = g
+            except Exception:
+                self.use_graphs = False
+                return False
+        g.replay()
+        for i in range(self.n_substeps):
+            self._frame_ord[f0 + i + 1] = self._frame_ord[f0]
+        return True
+
     def substep_grad(self, f, is_none_action):  # MPM:535-552
         if self.has_particles:
             self._ensure_grad_order(self._frame_ord[f])
@@ -394,7 +419,17 @@ class MPMSimulator:
         return {k: out[k] for k in want}
 
     def readframe(self, f, want=('x', 'v', 'C', 'F', 'used')):
-        return {k: t.cpu().numpy() for k, t in self.readframe_torch(f, want).items()}
+        """numpy arrays (fresh allocations, like MPM:618-623) via persistent pinned host staging: one batch of async D2H copies,
+        one synchronisation, then a host memcpy out of the pinned buffers."""
+        dev = self.readframe_torch(f, want)
+        if not hasattr(self, '_pinned'):
+            self._pinned = {}
+        for k, t in dev.items():
+            if k not in self._pinned:
+                self._pinned[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._pinned[k].copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: self._pinned[k].numpy().copy() for k in dev}
 
     def get_state(self):  # MPM:611-631
         f = self.cur_substep_local
@@ -471,9 +506,12 @@ class MPMSimulator:
             self.agent.set_action(s=self.cur_step_local, s_global=self.cur_step_global, n_substeps=self.n_substeps, action=action)
         if self.has_particles and self.sort_every > 0 and self.cur_step_global % self.sort_every == 0:
             self.sort_frame(self.cur_substep_local)
-        for _ in range(self.n_substeps):
-            self.substep(self.cur_substep_local, is_none_action)
-            self.cur_substep_global += 1
+        if self.use_graphs and is_none_action and self.has_particles and self._graph_substeps():
+            self.cur_substep_global += self.n_substeps
+        else:
+            for _ in range(self.n_substeps):
+                self.substep(self.cur_substep_local, is_none_action)
+                self.cur_substep_global += 1
         assert self.cur_substep_global <= self.max_substeps_global
 
     def step_grad(self, action=None):
