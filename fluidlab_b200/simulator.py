@@ -419,17 +419,15 @@ class MPMSimulator:
         return {k: out[k] for k in want}
 
     def readframe(self, f, want=('x', 'v', 'C', 'F', 'used')):
-        """numpy arrays (fresh allocations, like MPM:618-623) via persistent pinned host staging: one batch of async D2H copies,
-        one synchronisation, then a host memcpy out of the pinned buffers."""
+        """numpy arrays (fresh allocations, like MPM:618-623).  Each array is the view of a freshly allocated PINNED host tensor
+        (torch's caching host allocator recycles the blocks), filled by one batch of async D2H copies + one synchronisation —
+        no staging copy on the host."""
         dev = self.readframe_torch(f, want)
-        if not hasattr(self, '_pinned'):
-            self._pinned = {}
+        host = {k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for k, t in dev.items()}
         for k, t in dev.items():
-            if k not in self._pinned:
-                self._pinned[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            self._pinned[k].copy_(t, non_blocking=True)
+            host[k].copy_(t, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return {k: self._pinned[k].numpy().copy() for k in dev}
+        return {k: h.numpy() for k, h in host.items()}
 
     def get_state(self):  # MPM:611-631
         f = self.cur_substep_local
