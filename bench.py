@@ -264,8 +264,12 @@ def main():
     peak, peak_src = peaks()
     p2g_bytes = 136 * used + 16 * g_t            # p2g particle bytes + accumulated grid write-back
     g2p_bytes = 76 * used + 12 * g_t             # g2p(+advect)
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tp) and world == 1 and N == N_PARTICLES:
+        traffic = json.load(open(tp)).get('k_p2g')  # from the committed ncu --set full capture of this same workload
     roof = {'bound': 'hbm', 'kernel': 'k_p2g', 'achieved': p2g_bytes / (t_p2g * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-            'frac': p2g_bytes / (t_p2g * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+            'frac': p2g_bytes / (t_p2g * 1e-3) / 1e9 / peak, 'traffic': traffic, 'peak_source': peak_src,
             'algorithmic_bytes_per_launch': p2g_bytes, 'launch_ms': t_p2g, 'n_used': used, 'touched_nodes': g_t}
     roof_pair = {'kernels': 'k_p2g+k_g2p', 'achieved': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9,
                  'frac': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9 / peak, 'p2g_ms': t_p2g, 'g2p_ms': t_g2p, 'grid_op_ms': t_gop,

@@ -36,8 +36,11 @@ __device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
   return d;
 }
 
+#define SC_REC 10
 struct __align__(16) ScatterSmem {
-  float4 rec[32 * 4];          // per particle: (q0,q1,q2,m) (B00,B10,B20,0) (B01,B11,B21,0) (B02,B12,B22,0)
+  // per particle: nine Q_ab = (q + a*B[:,0] + b*B[:,1], m) for the (a,b) node columns of the stencil, then (B02,B12,B22,0):
+  // a lane (a,b,c) needs only Q_ab + c*B[:,2], i.e. 2 LDS.128 + 1 LDS and 4 FFMA2 per particle
+  float4 rec[32 * SC_REC];
   float w[27 * SC_WSTR + 5];   // w[node*33 + particle]: conflict-free for lane=particle stores and lane=node loads
   int key[32];
 };
@@ -49,7 +52,7 @@ struct Window {
   float2 acc01, acc2m;   // (x,y) and (z,mass) accumulators of this lane's stencil node
   int cur_key;           // packed cell whose 27 nodes the window currently covers (-1 = empty)
   int node;              // linear grid index of this lane's node for cur_key
-  float oa, ob, oc; int a, b, c; bool lane_valid; int wrow;
+  float oa, ob, oc; int a, b, c; bool lane_valid; int wrow; int qidx;
   int n, nb; int* flags; // grid size, blocks per dim, active-block flags (nullptr: do not flag)
 };
 __device__ __forceinline__ void window_init(Window& W, const int lane, const int n, int* flags) {
@@ -57,7 +60,7 @@ __device__ __forceinline__ void window_init(Window& W, const int lane, const int
   const int a = L / 9, b = (L / 3) % 3, c = L % 3;
   W.oa = (float)a; W.ob = (float)b; W.oc = (float)c; W.a = a; W.b = b; W.c = c;
   W.lane_valid = lane < 27;
-  W.wrow = L * SC_WSTR;
+  W.wrow = L * SC_WSTR; W.qidx = a * 3 + b;
   W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
   W.cur_key = -1; W.node = 0;
   W.n = n; W.nb = n >> 3; W.flags = flags;
@@ -105,10 +108,17 @@ __device__ __forceinline__ void window_move(Window& W, const int key, float4* __
 // Returns the mask of staged positions at which a new cell run starts.  ALL 32 lanes must call.
 __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int lane, const int key, const int carry_key, const float* q,
                                                     const float* B, const float m, const float w[3][3]) {
-  S.rec[lane * 4 + 0] = make_float4(q[0], q[1], q[2], m);
-  S.rec[lane * 4 + 1] = make_float4(B[0], B[3], B[6], 0.f);
-  S.rec[lane * 4 + 2] = make_float4(B[1], B[4], B[7], 0.f);
-  S.rec[lane * 4 + 3] = make_float4(B[2], B[5], B[8], 0.f);
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float fa = (float)a;
+    const float qa0 = fmaf(fa, B[0], q[0]), qa1 = fmaf(fa, B[3], q[1]), qa2 = fmaf(fa, B[6], q[2]);
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const float fb = (float)b;
+      S.rec[lane * SC_REC + a * 3 + b] = make_float4(fmaf(fb, B[1], qa0), fmaf(fb, B[4], qa1), fmaf(fb, B[7], qa2), m);
+    }
+  }
+  S.rec[lane * SC_REC + 9] = make_float4(B[2], B[5], B[8], 0.f);
   const bool valid = key >= 0;
 #pragma unroll
   for (int a = 0; a < 3; a++)
@@ -130,11 +140,11 @@ __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int la
   return __ballot_sync(SC_FULL, keff != prev);
 }
 
-// lane = stencil node.  Consumes the 32 staged particles (positions >= cnt carry zero weights, see scatter_publish)
-// in fixed groups of four: all 20 LDS of a group are issued first, then the 24 independent FFMA2 of q + B·o, and only
-// the two accumulator FFMA2 per particle form a dependent chain; run starts are a rare, warp-uniform branch.
+// lane = stencil node.  Consumes the 32 staged particles (positions >= cnt carry zero weights, see scatter_publish) in fixed
+// groups of four: 12 LDS of a group are issued first, then 8 independent FFMA2 (Q_ab + c*B2), and only the two accumulator
+// FFMA2 per particle form a dependent chain; run starts are a rare, warp-uniform branch.
 __device__ __forceinline__ void window_consume(Window& W, const ScatterSmem& S, const int cnt, const unsigned starts, float4* __restrict__ grid) {
-  const float2 oa2 = make_float2(W.oa, W.oa), ob2 = make_float2(W.ob, W.ob), oc2 = make_float2(W.oc, W.oc);
+  const float2 oc2 = make_float2(W.oc, W.oc);
   const int ngroups = (cnt + 3) >> 2;
 #pragma unroll 1
   for (int g = 0; g < ngroups; g++) {
@@ -142,13 +152,11 @@ __device__ __forceinline__ void window_consume(Window& W, const ScatterSmem& S, 
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int p = g * 4 + u;
-      const float4 r0 = S.rec[p * 4], r1 = S.rec[p * 4 + 1], r2 = S.rec[p * 4 + 2], r3 = S.rec[p * 4 + 3];
+      const float4 Q = S.rec[p * SC_REC + W.qidx], B2 = S.rec[p * SC_REC + 9];
       const float w = S.w[W.wrow + p];
       w2[u] = make_float2(w, w);
-      float2 a = ffma2(make_float2(r1.x, r1.y), oa2, make_float2(r0.x, r0.y));
-      float2 b = ffma2(make_float2(r1.z, r1.w), oa2, make_float2(r0.z, r0.w));
-      a = ffma2(make_float2(r2.x, r2.y), ob2, a); b = ffma2(make_float2(r2.z, r2.w), ob2, b);
-      t01[u] = ffma2(make_float2(r3.x, r3.y), oc2, a); t2m[u] = ffma2(make_float2(r3.z, r3.w), oc2, b);
+      t01[u] = ffma2(make_float2(B2.x, B2.y), oc2, make_float2(Q.x, Q.y));
+      t2m[u] = ffma2(make_float2(B2.z, B2.w), oc2, make_float2(Q.z, Q.w));
     }
     const unsigned sb = (starts >> (g * 4)) & 15u;
     if (sb == 0u) {
