@@ -44,6 +44,7 @@ class FmpmBuffers(C.Structure):
         ("sort_keys_in", vp), ("sort_keys_out", vp), ("sort_vals_in", vp), ("sort_vals_out", vp),
         ("sort_tmp", vp), ("sort_tmp_bytes", C.c_ulonglong),
         ("blk_flags", vp), ("blk_list", vp), ("blk_count", vp),
+        ("grid_pm_ring", vp), ("grid_v_ring", vp), ("blk_list_ring", vp), ("blk_count_ring", vp),
     ]
 
 
@@ -90,6 +91,8 @@ _PROTOS = {
     "fmpm_grid_op": (_I, [vp, _I, _I, vp]),
     "fmpm_g2p": (_I, [vp, _I, vp]),
     "fmpm_substep": (_I, [vp, _I, vp]),
+    "fmpm_substep_store": (_I, [vp, _I, vp]),
+    "fmpm_substep_grad_stored": (_I, [vp, _I, _I, _I, vp]),
     "fmpm_inject": (_I, [vp, _I, C.POINTER(FmpmInjector), C.POINTER(FmpmEffector), _I, _I, vp, vp]),
     "fmpm_substep_grad": (_I, [vp, _I, _I, _I, vp]),
     "fmpm_g2p_grad_scatter": (_I, [vp, _I, _I, vp]),

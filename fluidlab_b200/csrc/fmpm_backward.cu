@@ -395,11 +395,12 @@ static int check_bound_b(FmpmHandle* h, const char* name) {
   return 0;
 }
 
-int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, void* stream);  // fmpm_forward.cu
+int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring_slot, void* stream);  // fmpm_forward.cu
+int fmpm_p2g_impl(FmpmHandle* h, int f, int write_F, int ring_slot, void* stream);                       // fmpm_forward.cu
 
-static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, void* stream) {
+static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, int ring_slot, void* stream) {
   if (check_bound_b(h, "fmpm_g2p_grad_scatter")) return 1;
-  KParams P = make_kparams(h);
+  KParams P = make_kparams(h, ring_slot);
   if (dense_zero) {
     cudaError_t e = cudaMemsetAsync(P.ggrid_v, 0, (size_t)P.G * sizeof(float4), (cudaStream_t)stream);
     if (e != cudaSuccess) { snprintf(h->err, sizeof(h->err), "fmpm_g2p_grad_scatter: %s", cudaGetErrorString(e)); return 1; }
@@ -411,36 +412,69 @@ static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, 
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p_grad_scatter");
   return 0;
 }
-extern "C" int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) { return g2p_grad_scatter_impl(h, f, gin, 1, stream); }
-static int grid_op_grad_impl(FmpmHandle* h, int f, int clear_pm, void* stream) {
+extern "C" int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) { return g2p_grad_scatter_impl(h, f, gin, 1, -1, stream); }
+static int grid_op_grad_impl(FmpmHandle* h, int f, int clear_pm, int ring_slot, void* stream) {
   if (check_bound_b(h, "fmpm_grid_op_grad")) return 1;
-  KParams P = make_kparams(h);
+  KParams P = make_kparams(h, ring_slot);
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
   k_grid_op_grad<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op_grad");
   return 0;
 }
-extern "C" int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream) { return grid_op_grad_impl(h, f, 0, stream); }
-extern "C" int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void* stream) {
+extern "C" int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream) { return grid_op_grad_impl(h, f, 0, -1, stream); }
+static int particle_grad_impl(FmpmHandle* h, int f, int gin, int gout, int ring_slot, void* stream) {
   if (check_bound_b(h, "fmpm_particle_grad")) return 1;
-  KParams P = make_kparams(h);
+  KParams P = make_kparams(h, ring_slot);
   if (P.N == 0) return 0;
   k_particle_grad<<<(P.N + PG_WARPS * 32 - 1) / (PG_WARPS * 32), PG_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f, gin, gout);
   FMPM_CHECK_LAUNCH(h, "fmpm_particle_grad");
   return 0;
 }
+extern "C" int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void* stream) { return particle_grad_impl(h, f, gin, gout, -1, stream); }
+
+// zero the v_out adjoint on the active blocks of the substep (stored-grid backward: no grid_op recompute to piggy-back on)
+__global__ void __launch_bounds__(256) k_zero_ggv_blocks(const KParams P) {
+  const int count = P.blk_count[0];
+  const int n = P.n, nb = P.nb;
+  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
+    const int blk = P.blk_list[bi];
+    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int t = threadIdx.x + r * 256;
+      const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+      P.ggrid_v[(i * n + j) * n + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+extern "C" int fmpm_substep_grad_stored(FmpmHandle* h, int f, int gin, int gout, void* stream) {
+  if (check_bound_b(h, "fmpm_substep_grad_stored")) return 1;
+  if (!h->buf.grid_pm_ring) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad_stored: the per-frame grid ring was not bound"); return 1; }
+  if (gin == gout || (gin | gout) & ~1) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad_stored: gin/gout must be distinct in {0,1}"); return 1; }
+  KParams P = make_kparams(h, f);
+  const int nblk = P.nb * P.nb * P.nb;
+  const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  k_zero_ggv_blocks<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_stored(zero)");
+  if (h->col.has_rigid && h->col.collide_type != 1 && P.N > 0) {
+    k_collide_particle_grad<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_stored(collide)");
+  }
+  if (g2p_grad_scatter_impl(h, f, gin, 0, f, stream) || grid_op_grad_impl(h, f, 0, f, stream)) return 1;
+  return particle_grad_impl(h, f, gin, gout, f, stream);
+}
+
 extern "C" int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* stream) {
   if (check_bound_b(h, "fmpm_substep_grad")) return 1;
   if (gin == gout || (gin | gout) & ~1) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad: gin/gout must be distinct in {0,1}"); return 1; }
   // recompute the forward grid of frame f (accumulators are clear on entry), zeroing the v_out adjoint of the active blocks
-  if (fmpm_p2g(h, f, 0, stream) || fmpm_grid_op_impl(h, f, 0, 1, stream)) return 1;
+  if (fmpm_p2g(h, f, 0, stream) || fmpm_grid_op_impl(h, f, 0, 1, -1, stream)) return 1;
   if (h->col.has_rigid && h->col.collide_type != 1) {  // particle-level agent collide: fold its adjoint into the frame-(f+1) adjoint
     KParams P = make_kparams(h);
     if (P.N > 0) { k_collide_particle_grad<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad(collide)"); }
   }
   // adjoint: grid scatter, grid_op.grad (also leaves the accumulators clear for the next substep), per-particle part
-  if (g2p_grad_scatter_impl(h, f, gin, 0, stream) || grid_op_grad_impl(h, f, 1, stream)) return 1;
+  if (g2p_grad_scatter_impl(h, f, gin, 0, -1, stream) || grid_op_grad_impl(h, f, 1, -1, stream)) return 1;
   return fmpm_particle_grad(h, f, gin, gout, stream);
 }
 extern "C" int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjector* inj, const FmpmEffector* e, int act_id,

@@ -42,7 +42,8 @@ struct KParams {
   CollidersDev col;
 };
 
-static inline KParams make_kparams(const FmpmHandle* h) {
+// ring_slot >= 0: the (momentum, mass) / v_out grids and the active-block list live in slot `ring_slot` of the per-frame ring
+static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1) {
   KParams P;
   const FmpmConfig& c = h->cfg;
   P.N = c.n_particles; P.n = c.n_grid; P.G = c.n_grid * c.n_grid * c.n_grid; P.T = c.max_substeps_local;
@@ -59,6 +60,13 @@ static inline KParams make_kparams(const FmpmHandle* h) {
   P.mats = (const float4*)h->buf.materials;
   P.col = h->col;
   P.blk_flags = (int*)h->buf.blk_flags; P.blk_list = (int*)h->buf.blk_list; P.blk_count = (int*)h->buf.blk_count; P.nb = c.n_grid / 8;
+  if (ring_slot >= 0 && h->buf.grid_pm_ring) {
+    const size_t nblk = (size_t)P.nb * P.nb * P.nb;
+    P.grid_pm = (float4*)h->buf.grid_pm_ring + (size_t)ring_slot * P.G;
+    P.grid_v = (float4*)h->buf.grid_v_ring + (size_t)ring_slot * P.G;
+    P.blk_list = (int*)h->buf.blk_list_ring + (size_t)ring_slot * nblk;
+    P.blk_count = (int*)h->buf.blk_count_ring + ring_slot;
+  }
   return P;
 }
 

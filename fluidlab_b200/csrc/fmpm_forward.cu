@@ -259,9 +259,9 @@ extern "C" int fmpm_clear_grid(FmpmHandle* h, void* stream) {
   return 0;
 }
 
-extern "C" int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream) {
+int fmpm_p2g_impl(FmpmHandle* h, int f, int write_F, int ring_slot, void* stream) {
   if (check_bound(h, "fmpm_p2g") || check_frame(h, f, h->cfg.max_substeps_local - (write_F ? 1 : 0), "fmpm_p2g")) return 1;
-  KParams P = make_kparams(h);
+  KParams P = make_kparams(h, ring_slot);
   if (P.N == 0) return 0;
   const long long warps = ((long long)P.N + 32 * P2G_ROUNDS - 1) / (32 * P2G_ROUNDS);
   const int blocks = (int)((warps + P2G_WARPS - 1) / P2G_WARPS);
@@ -270,10 +270,11 @@ extern "C" int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream) {
   FMPM_CHECK_LAUNCH(h, "fmpm_p2g");
   return 0;
 }
+extern "C" int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream) { return fmpm_p2g_impl(h, f, write_F, -1, stream); }
 
-int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, void* stream) {
+int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring_slot, void* stream) {
   if (check_bound(h, "fmpm_grid_op")) return 1;
-  KParams P = make_kparams(h);
+  KParams P = make_kparams(h, ring_slot);
   if (!P.blk_flags || !P.blk_list || !P.blk_count) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block buffers were not bound"); return 1; }
   if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
   const int nblk = P.nb * P.nb * P.nb;
@@ -287,16 +288,49 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, void* st
   return 0;
 }
 extern "C" int fmpm_grid_op(FmpmHandle* h, int f, int clear_pm, void* stream) {
-  return fmpm_grid_op_impl(h, f, clear_pm, 0, stream);
+  return fmpm_grid_op_impl(h, f, clear_pm, 0, -1, stream);
 }
 
-extern "C" int fmpm_g2p(FmpmHandle* h, int f, void* stream) {
+int fmpm_g2p_impl(FmpmHandle* h, int f, int ring_slot, void* stream) {
   if (check_bound(h, "fmpm_g2p") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_g2p")) return 1;
-  KParams P = make_kparams(h);
+  KParams P = make_kparams(h, ring_slot);
   if (P.N == 0) return 0;
   k_g2p<<<(P.N + G2P_WARPS * 32 - 1) / (G2P_WARPS * 32), G2P_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f);
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p");
   return 0;
+}
+
+extern "C" int fmpm_g2p(FmpmHandle* h, int f, void* stream) { return fmpm_g2p_impl(h, f, -1, stream); }
+
+// sparse clear of a ring slot: zero the (momentum, mass) nodes of the blocks its previous occupant touched
+__global__ void __launch_bounds__(256) k_clear_blocks(const KParams P) {
+  const int count = P.blk_count[0];
+  const int n = P.n, nb = P.nb;
+  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
+    const int blk = P.blk_list[bi];
+    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int t = threadIdx.x + r * 256;
+      const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+      P.grid_pm[(i * n + j) * n + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+extern "C" int fmpm_substep_store(FmpmHandle* h, int f, void* stream) {
+  if (check_bound(h, "fmpm_substep_store")) return 1;
+  if (!h->buf.grid_pm_ring || !h->buf.grid_v_ring || !h->buf.blk_list_ring || !h->buf.blk_count_ring) {
+    snprintf(h->err, sizeof(h->err), "fmpm_substep_store: the per-frame grid ring was not bound"); return 1;
+  }
+  if (check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_substep_store")) return 1;
+  KParams P = make_kparams(h, f);
+  const int nblk = P.nb * P.nb * P.nb;
+  const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  k_clear_blocks<<<grid, 256, 0, (cudaStream_t)stream>>>(P);  // previous occupant of slot f
+  FMPM_CHECK_LAUNCH(h, "fmpm_substep_store(clear)");
+  if (fmpm_p2g_impl(h, f, 1, f, stream)) return 1;
+  if (fmpm_grid_op_impl(h, f, 0, 0, f, stream)) return 1;
+  return fmpm_g2p_impl(h, f, f, stream);
 }
 
 extern "C" int fmpm_substep(FmpmHandle* h, int f, void* stream) {

@@ -82,6 +82,7 @@ class MPMSimulator:
         self.has_particles = False
         self.sort_every = int(sort_every)  # cell-sort period in steps (0 = never)
         self.use_graphs = True             # replay the 10 substeps of an agent-free step as one CUDA graph per local step index
+        self.store_grids = True            # grad mode: keep each ring frame's forward grid in HBM instead of recomputing it in the backward
         if device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError('fluidlab_b200.MPMSimulator needs a CUDA device (B200, sm_100a); there is no CPU fallback')
@@ -168,6 +169,8 @@ class MPMSimulator:
         self._blk_list = torch.zeros((nblk,), dtype=i32, device=dev)
         self._blk_count = torch.zeros((1,), dtype=i32, device=dev)
         self._ga = self._gf = self._gf8 = self._ggrid_v = self._ggrid_pm = None
+        self._pm_ring = self._v_ring = self._blk_list_ring = self._blk_count_ring = None
+        self._ring_valid = [False] * T
         # API-layout staging
         self._sx = torch.empty((N, 3), dtype=f32, device=dev); self._sv = torch.empty((N, 3), dtype=f32, device=dev)
         self._sC = torch.empty((N, 3, 3), dtype=f32, device=dev); self._sF = torch.empty((N, 3, 3), dtype=f32, device=dev)
@@ -213,6 +216,8 @@ class MPMSimulator:
         b.sort_keys_in, b.sort_keys_out, b.sort_vals_in, b.sort_vals_out = [p(t) for t in self._sort_bufs]
         b.sort_tmp, b.sort_tmp_bytes = p(self._sort_tmp), self._sort_tmp.numel()
         b.blk_flags, b.blk_list, b.blk_count = p(self._blk_flags), p(self._blk_list), p(self._blk_count)
+        b.grid_pm_ring, b.grid_v_ring = p(self._pm_ring), p(self._v_ring)
+        b.blk_list_ring, b.blk_count_ring = p(self._blk_list_ring), p(self._blk_count_ring)
         self._ck(self._lib.fmpm_bind(self._h, C.byref(b)), 'fmpm_bind')
 
     def register_colliders(self):
@@ -242,6 +247,17 @@ class MPMSimulator:
             self._gf8 = torch.zeros((2, N), dtype=f32, device=dev)
             self._ggrid_v = torch.zeros((G, 4), dtype=f32, device=dev)
             self._ggrid_pm = torch.zeros((G, 4), dtype=f32, device=dev)
+            # per-frame forward grids for the backward pass (like the reference's grid ring, MPM:117) when HBM allows:
+            # 32 B/node/frame; otherwise substep_grad recomputes the forward grid of each frame
+            T = self.max_substeps_local
+            need = T * G * 32
+            free, _ = torch.cuda.mem_get_info(dev)
+            if self.store_grids and need < 0.35 * free:
+                nblk = (self.n_grid // 8) ** 3
+                self._pm_ring = torch.zeros((T, G, 4), dtype=f32, device=dev)
+                self._v_ring = torch.zeros((T, G, 4), dtype=f32, device=dev)
+                self._blk_list_ring = torch.zeros((T, nblk), dtype=torch.int32, device=dev)
+                self._blk_count_ring = torch.zeros((T,), dtype=torch.int32, device=dev)
             self._bind()
 
     def __del__(self):
@@ -352,12 +368,23 @@ class MPMSimulator:
 
     def substep(self, f, is_none_action):  # MPM:515-533
         if self.has_particles:
-            self._ck(self._lib.fmpm_substep(self._h, f, self._stream()), 'fmpm_substep')
+            if self._storing():
+                self._ck(self._lib.fmpm_substep_store(self._h, f, self._stream()), 'fmpm_substep_store')
+                self._ring_valid[f] = True
+            else:
+                self._ck(self._lib.fmpm_substep(self._h, f, self._stream()), 'fmpm_substep')
+                self._ring_valid[f] = False
             self._frame_ord[f + 1] = self._frame_ord[f]
         if not is_none_action:
             # agent.act writes frame f+1 of particles that are unused at f, so running it after g2p is equivalent
             # to the reference order (MPM:521); agent.move was folded into agent.set_action (pose chain kernel).
             self.agent.act(f, self.cur_substep_global)
+
+    def _storing(self):
+        if not (self.grad_enabled and self.store_grids):
+            return False
+        self._ensure_grad_buffers()
+        return self._pm_ring is not None
 
     def _graph_substeps(self):
         """Forward substeps of one step (p2g / compaction / grid_op / g2p x n_substeps, no agent) as a captured CUDA graph, one per
@@ -366,28 +393,34 @@ class MPMSimulator:
             self._graphs = {}
         s_local = self.cur_step_local
         f0 = self.cur_substep_local
-        g = self._graphs.get(s_local)
+        store = self._storing()
+        g = self._graphs.get((s_local, store))
         if g is None:
             try:
+                fn = self._lib.fmpm_substep_store if store else self._lib.fmpm_substep
                 g = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize(self.device)
                 with torch.cuda.graph(g):
                     for i in range(self.n_substeps):
-                        self._ck(self._lib.fmpm_substep(self._h, f0 + i, self._stream()), 'fmpm_substep')
-                self._graphs[s_local] = g
+                        self._ck(fn(self._h, f0 + i, self._stream()), 'fmpm_substep')
+                self._graphs[(s_local, store)] = g
             except Exception:
                 self.use_graphs = False
                 return False
         g.replay()
         for i in range(self.n_substeps):
             self._frame_ord[f0 + i + 1] = self._frame_ord[f0]
+            self._ring_valid[f0 + i] = store
         return True
 
     def substep_grad(self, f, is_none_action):  # MPM:535-552
         if self.has_particles:
             self._ensure_grad_order(self._frame_ord[f])
             gin, gout = self._gcur, 1 - self._gcur
-            self._ck(self._lib.fmpm_substep_grad(self._h, f, gin, gout, self._stream()), 'fmpm_substep_grad')
+            if self._pm_ring is not None and self._ring_valid[f]:
+                self._ck(self._lib.fmpm_substep_grad_stored(self._h, f, gin, gout, self._stream()), 'fmpm_substep_grad_stored')
+            else:
+                self._ck(self._lib.fmpm_substep_grad(self._h, f, gin, gout, self._stream()), 'fmpm_substep_grad')
             if not is_none_action:
                 self.agent.act_grad(f, self.cur_substep_global, gin)
             self._gcur = gout

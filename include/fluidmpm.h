@@ -80,6 +80,11 @@ typedef struct {
    * blk_count int[1].  p2g flags the blocks it scatters into, fmpm_grid_op compacts them and every grid kernel of the
    * substep (grid_op, clears, adjoint grid) visits only those blocks. */
   void* blk_flags; void* blk_list; void* blk_count;
+  /* optional per-frame grid ring for the backward pass (all four NULL = recompute the forward grid per backward substep):
+   * grid_pm_ring / grid_v_ring float4[T][G] (zero-initialised), blk_list_ring int[T][(n_grid/8)^3], blk_count_ring int[T] (zero).
+   * fmpm_substep_store(f) leaves the (momentum, mass) and v_out grids of frame f in slot f; fmpm_substep_grad_stored(f) reads them.
+   * The reference keeps a grid per frame too (MPM:117), 56 B/node dense; here 32 B/node and only touched blocks are rewritten. */
+  void* grid_pm_ring; void* grid_v_ring; void* blk_list_ring; void* blk_count_ring;
 } FmpmBuffers;
 
 /* effector pose chain, fluidlab/fluidengine/effectors/effector.py:34-51 (fields), :157-161 (move_kernel),
@@ -137,6 +142,7 @@ int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream);         /* MPM:25
 int fmpm_grid_op(FmpmHandle* h, int f, int clear_pm, void* stream);    /* MPM:380-398 */
 int fmpm_g2p(FmpmHandle* h, int f, void* stream);                      /* MPM:304-316 + 400-426 + 497-505 fused */
 int fmpm_substep(FmpmHandle* h, int f, void* stream);                  /* p2g, grid_op(clear), g2p; grid must be clear on entry */
+int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, but the grids of frame f stay in ring slot f */
 /* agent.act for injector agents, agents/agent_injector.py:23-32; run after fmpm_g2p of the same f */
 int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,
                 const void* inv, void* stream);
@@ -144,6 +150,7 @@ int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffecto
 /* ---- backward substep, MPM:535-552 ------------------------------------------------------------ */
 /* gin/gout in {0,1}: grad ping-pong index holding frame f+1 (in) and receiving frame f (out). */
 int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* stream);
+int fmpm_substep_grad_stored(FmpmHandle* h, int f, int gin, int gout, void* stream);  /* uses the grids left by fmpm_substep_store(f) */
 int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream);           /* g2p.grad: grid side */
 int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream);                        /* grid_op.grad */
 int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void* stream);    /* advect/g2p/p2g/svd/F_tmp .grad: particle side */
