@@ -77,10 +77,9 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
 // grid_op.grad (MPM:539): v_out = B(v_in / m + dt g)
 // =============================================================================================
 __global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int f, const int clear_pm) {
-  const int count = P.blk_count[0];
-  const int n = P.n, nb = P.nb;
-  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
-    const int blk = P.blk_list[bi];
+  const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    if (P.blk_flags[blk] == 0) continue;  // CTA-uniform
     const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
@@ -129,6 +128,7 @@ __global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int
       P.ggrid_pm[g] = out;
       if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (clear_pm) { __syncthreads(); if (threadIdx.x == 0) P.blk_flags[blk] = 0; }  // recompute path: last consumer of the flags
   }
 }
 
@@ -435,10 +435,9 @@ extern "C" int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void*
 
 // zero the v_out adjoint on the active blocks of the substep (stored-grid backward: no grid_op recompute to piggy-back on)
 __global__ void __launch_bounds__(256) k_zero_ggv_blocks(const KParams P) {
-  const int count = P.blk_count[0];
-  const int n = P.n, nb = P.nb;
-  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
-    const int blk = P.blk_list[bi];
+  const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    if (P.blk_flags[blk] == 0) continue;
     const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
 #pragma unroll
     for (int r = 0; r < 2; r++) {

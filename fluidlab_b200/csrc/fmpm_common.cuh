@@ -64,8 +64,7 @@ static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1) {
     const size_t nblk = (size_t)P.nb * P.nb * P.nb;
     P.grid_pm = (float4*)h->buf.grid_pm_ring + (size_t)ring_slot * P.G;
     P.grid_v = (float4*)h->buf.grid_v_ring + (size_t)ring_slot * P.G;
-    P.blk_list = (int*)h->buf.blk_list_ring + (size_t)ring_slot * nblk;
-    P.blk_count = (int*)h->buf.blk_count_ring + ring_slot;
+    P.blk_flags = (int*)h->buf.blk_list_ring + (size_t)ring_slot * nblk;  // per-frame block flags
   }
   return P;
 }

@@ -105,28 +105,15 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
 }
 
 // =============================================================================================
-// sparse grid: compaction of the active 8^3-node blocks flagged by the p2g flushes, then grid_op on them
+// sparse grid: p2g flags the 8^3-node blocks it scatters into (blk_flags); every grid kernel of the substep scans the flag
+// array with a grid-stride loop and visits only flagged blocks (no separate compaction launch).
 // =============================================================================================
-__global__ void __launch_bounds__(1024) k_compact_blocks(const KParams P) {
-  // one CTA per 1024 flags; list order is arbitrary (blocks are processed independently); blk_count was zeroed by the host
-  const int nblk = P.nb * P.nb * P.nb;
-  const int b = blockIdx.x * 1024 + threadIdx.x;
-  const bool on = b < nblk && P.blk_flags[b] != 0;
-  if (on) P.blk_flags[b] = 0;
-  const unsigned m = __ballot_sync(0xffffffffu, on);
-  int off = 0;
-  if ((threadIdx.x & 31) == 0 && m) off = atomicAdd(P.blk_count, __popc(m));
-  off = __shfl_sync(0xffffffffu, off, 0);
-  if (on) P.blk_list[off + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = b;
-}
-
 // MPM:380-398 on the active blocks; optionally clears the (momentum, mass) accumulators for the next substep
 // and zeroes the v_out adjoint of the same blocks (backward pass).
-__global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, const int clear_pm, const int zero_ggv) {
-  const int count = P.blk_count[0];
-  const int n = P.n, nb = P.nb;
-  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
-    const int blk = P.blk_list[bi];
+__global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, const int clear_pm, const int zero_ggv, const int reset_flags) {
+  const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    if (P.blk_flags[blk] == 0) continue;  // CTA-uniform
     const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
@@ -155,6 +142,7 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, c
       if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (zero_ggv) P.ggrid_v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (reset_flags) { __syncthreads(); if (threadIdx.x == 0) P.blk_flags[blk] = 0; }
   }
 }
 
@@ -275,15 +263,13 @@ extern "C" int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream) { retur
 int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring_slot, void* stream) {
   if (check_bound(h, "fmpm_grid_op")) return 1;
   KParams P = make_kparams(h, ring_slot);
-  if (!P.blk_flags || !P.blk_list || !P.blk_count) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block buffers were not bound"); return 1; }
+  if (!P.blk_flags) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block flags were not bound"); return 1; }
   if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
   const int nblk = P.nb * P.nb * P.nb;
-  cudaError_t e0 = cudaMemsetAsync(P.blk_count, 0, sizeof(int), (cudaStream_t)stream);
-  if (e0 != cudaSuccess) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: %s", cudaGetErrorString(e0)); return 1; }
-  k_compact_blocks<<<(nblk + 1023) / 1024, 1024, 0, (cudaStream_t)stream>>>(P);
-  FMPM_CHECK_LAUNCH(h, "fmpm_grid_op(compact)");
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
-  k_grid_op<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm, zero_ggv);
+  // the flags are consumed (reset) here only when nothing later in the substep needs them: plain forward substeps
+  const int reset_flags = (clear_pm && ring_slot < 0) ? 1 : 0;
+  k_grid_op<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm, zero_ggv, reset_flags);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op");
   return 0;
 }
@@ -304,10 +290,9 @@ extern "C" int fmpm_g2p(FmpmHandle* h, int f, void* stream) { return fmpm_g2p_im
 
 // sparse clear of a ring slot: zero the (momentum, mass) nodes of the blocks its previous occupant touched
 __global__ void __launch_bounds__(256) k_clear_blocks(const KParams P) {
-  const int count = P.blk_count[0];
-  const int n = P.n, nb = P.nb;
-  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
-    const int blk = P.blk_list[bi];
+  const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    if (P.blk_flags[blk] == 0) continue;
     const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
@@ -315,11 +300,13 @@ __global__ void __launch_bounds__(256) k_clear_blocks(const KParams P) {
       const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
       P.grid_pm[(i * n + j) * n + k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) P.blk_flags[blk] = 0;
   }
 }
 extern "C" int fmpm_substep_store(FmpmHandle* h, int f, void* stream) {
   if (check_bound(h, "fmpm_substep_store")) return 1;
-  if (!h->buf.grid_pm_ring || !h->buf.grid_v_ring || !h->buf.blk_list_ring || !h->buf.blk_count_ring) {
+  if (!h->buf.grid_pm_ring || !h->buf.grid_v_ring || !h->buf.blk_list_ring) {
     snprintf(h->err, sizeof(h->err), "fmpm_substep_store: the per-frame grid ring was not bound"); return 1;
   }
   if (check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_substep_store")) return 1;

@@ -77,11 +77,12 @@ typedef struct {
   void* sort_keys_in; void* sort_keys_out; void* sort_vals_in; void* sort_vals_out; /* int[N] each */
   void* sort_tmp; unsigned long long sort_tmp_bytes;    /* >= fmpm_sort_workspace_bytes() */
   /* sparse grid: 8x8x8-node blocks.  blk_flags int[(n_grid/8)^3] (zero-initialised by the caller), blk_list int[(n_grid/8)^3],
-   * blk_count int[1].  p2g flags the blocks it scatters into, fmpm_grid_op compacts them and every grid kernel of the
-   * substep (grid_op, clears, adjoint grid) visits only those blocks. */
+   * blk_count int[1] (the last two are reserved).  p2g flags the blocks it scatters into and every grid kernel of the substep
+   * (grid_op, clears, adjoint grid) scans the flags and visits only those blocks; the last consumer resets them. */
   void* blk_flags; void* blk_list; void* blk_count;
   /* optional per-frame grid ring for the backward pass (all four NULL = recompute the forward grid per backward substep):
-   * grid_pm_ring / grid_v_ring float4[T][G] (zero-initialised), blk_list_ring int[T][(n_grid/8)^3], blk_count_ring int[T] (zero).
+   * grid_pm_ring / grid_v_ring float4[T][G] (zero-initialised), blk_list_ring int[T][(n_grid/8)^3] (zero; the per-frame block
+   * flags), blk_count_ring int[T] (reserved).
    * fmpm_substep_store(f) leaves the (momentum, mass) and v_out grids of frame f in slot f; fmpm_substep_grad_stored(f) reads them.
    * The reference keeps a grid per frame too (MPM:117), 56 B/node dense; here 32 B/node and only touched blocks are rewritten. */
   void* grid_pm_ring; void* grid_v_ring; void* blk_list_ring; void* blk_count_ring;
