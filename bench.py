@@ -148,7 +148,7 @@ def main():
     ap.add_argument('--particles', type=int, default=N_PARTICLES)
     ap.add_argument('--bwd', type=int, default=1, help='also time forward+backward (extra keys)')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--sort-every', type=int, default=1)
+    ap.add_argument('--sort-every', type=int, default=2, help='cell-sort period in steps (measured: 1 -> 6.59k, 2 -> 6.75k, 4 -> 6.70k substeps/s)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
