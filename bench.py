@@ -85,7 +85,7 @@ class ClockSampler:
                 'samples': len(self.samples)}
 
 
-def cpu_baseline_run(n_particles, max_seconds=20.0, max_substeps=6, threads=None):
+def cpu_baseline_run(n_particles, max_seconds=15.0, max_substeps=60, threads=None):
     """Time the CPU oracle (restatement of mpm_simulator.py:515-533, fp32, OpenMP) on the same workload."""
     from conftest import make_particles
     from oracle import oracle as orc

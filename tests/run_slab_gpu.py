@@ -27,7 +27,7 @@ def main():
     x = rng.uniform((0.2, 0.3, 0.3), (0.8, 0.5, 0.7), size=(Ntot, 3)).astype(np.float32)
     v0 = np.tile(np.array([3.0, 0.0, 0.5], dtype=np.float32), (Ntot, 1))  # 3 m/s along x: ~0.4 cells per step -> migration
     mat = np.where(x[:, 2] < 0.5, M.WATER, M.ELASTIC).astype(np.int32)
-    bounds = slab_bounds(8, 56, world)
+    bounds = slab_bounds(0, 64, world) if world > 2 else slab_bounds(8, 56, world)
     cp = centre_plane(torch.from_numpy(x), float(n)).numpy()
     lo = bounds[rank] if rank > 0 else -10 ** 6
     hi = bounds[rank + 1] if rank < world - 1 else 10 ** 6
