@@ -201,7 +201,8 @@ def main():
             slab.step()
         workload = (f'C2-weak: {N} water particles per GPU (~8/cell) as {world} x-slabs of one body, 256^3 grid, fp32, forward; value counts '
                     f'1M-particle substeps (global substeps/s = value / n_gpus)')
-        parallelism = f'{world} x-slabs, per-substep ghost-plane sum exchange ({slab.ghost.bytes_per_exchange()} B/rank/substep) + per-step migration, NCCL'
+        parallelism = (f'{world} x-slabs; ghost-plane reduction fused into p2g (vector REDs to the neighbour grid over NVLink peer memory, '
+                       f'{slab.ghost.bytes_per_exchange()} B of ghost planes per rank), one 4-byte all-reduce barrier per substep, per-step migration')
     init = sim.get_state()
     def barrier():
         if world > 1:
@@ -254,7 +255,7 @@ def main():
 
     t_p2g = time_phase(lambda: sim.phase('p2g', f, 0), pre=lambda: sim.phase('clear_grid', f))
     sim.phase('clear_grid', f); sim.phase('p2g', f, 0)
-    g_t = int((sim._grid_pm[:, 3] > 0).sum().item())
+    g_t = int((sim._grid_pm.reshape(-1, 4)[:, 3] > 0).sum().item())
     def _refill():
         sim.phase('clear_grid', f); sim.phase('p2g', f, 0)
     t_gop = time_phase(lambda: sim.phase('grid_op', f, 0), pre=_refill)  # includes the active-block compaction

@@ -77,9 +77,15 @@ class FmpmColliders(C.Structure):
                 ("rigid", FmpmSdfMesh), ("pos", vp), ("quat", vp), ("gpos", vp), ("collide_y_min", C.c_float)]
 
 
+class FmpmSlab(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("peer_pm_left", vp), ("peer_pm_right", vp), ("left_lo", C.c_int), ("left_hi", C.c_int),
+                ("right_lo", C.c_int), ("right_hi", C.c_int)]
+
+
 _I, _F, _U = C.c_int, C.c_float, C.c_uint
 _PROTOS = {
     "fmpm_set_colliders": (_I, [vp, C.POINTER(FmpmColliders)]),
+    "fmpm_set_slab": (_I, [vp, C.POINTER(FmpmSlab)]),
     "fmpm_create": (_I, [C.POINTER(FmpmConfig), C.POINTER(vp)]),
     "fmpm_destroy": (None, [vp]),
     "fmpm_bind": (_I, [vp, C.POINTER(FmpmBuffers)]),

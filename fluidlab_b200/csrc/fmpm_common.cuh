@@ -20,6 +20,7 @@ struct FmpmHandle {
   FmpmConfig cfg;
   FmpmBuffers buf;
   CollidersDev col;
+  FmpmSlab slab;
   bool bound;
   char err[512];
   int sm_count;
@@ -40,10 +41,12 @@ struct KParams {
   const float4* mats;  // (mu, lam, mass, cls-as-int-bits)
   int* blk_flags; int* blk_list; int* blk_count; int nb;  // sparse grid: 8^3-node blocks
   CollidersDev col;
+  // x-slab mode: neighbours' accumulators (peer memory over NVLink) and the node-plane ranges shared with them
+  float4* peer_l; float4* peer_r; int gl_lo, gl_hi, gr_lo, gr_hi;
 };
 
 // ring_slot >= 0: the (momentum, mass) / v_out grids and the active-block list live in slot `ring_slot` of the per-frame ring
-static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1) {
+static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1, int parity = 0) {
   KParams P;
   const FmpmConfig& c = h->cfg;
   P.N = c.n_particles; P.n = c.n_grid; P.G = c.n_grid * c.n_grid * c.n_grid; P.T = c.max_substeps_local;
@@ -60,6 +63,14 @@ static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1) {
   P.mats = (const float4*)h->buf.materials;
   P.col = h->col;
   P.blk_flags = (int*)h->buf.blk_flags; P.blk_list = (int*)h->buf.blk_list; P.blk_count = (int*)h->buf.blk_count; P.nb = c.n_grid / 8;
+  P.peer_l = P.peer_r = nullptr; P.gl_lo = P.gl_hi = P.gr_lo = P.gr_hi = 0;
+  if (h->slab.enabled) {  // accumulator double-buffered by substep parity; peers use the same parity
+    const size_t off = (size_t)(parity & 1) * P.G;
+    P.grid_pm += off;
+    if (h->slab.peer_pm_left) P.peer_l = (float4*)h->slab.peer_pm_left + off;
+    if (h->slab.peer_pm_right) P.peer_r = (float4*)h->slab.peer_pm_right + off;
+    P.gl_lo = h->slab.left_lo; P.gl_hi = h->slab.left_hi; P.gr_lo = h->slab.right_lo; P.gr_hi = h->slab.right_hi;
+  }
   if (ring_slot >= 0 && h->buf.grid_pm_ring) {
     const size_t nblk = (size_t)P.nb * P.nb * P.nb;
     P.grid_pm = (float4*)h->buf.grid_pm_ring + (size_t)ring_slot * P.G;

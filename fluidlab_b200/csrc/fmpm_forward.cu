@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
   const long long slot0 = gw * (32 * P2G_ROUNDS);
   if (slot0 >= P.N) return;
   Window W; window_init(W, lane, P.n, P.blk_flags);
+  window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi);
   PRaw R; p2g_load_raw(P, f, slot0 + lane, R);
 #pragma unroll 1
   for (int r = 0; r < P2G_ROUNDS; r++) {
@@ -241,7 +242,7 @@ static int check_frame(FmpmHandle* h, int f, int maxf, const char* name) {
 
 extern "C" int fmpm_clear_grid(FmpmHandle* h, void* stream) {
   if (check_bound(h, "fmpm_clear_grid")) return 1;
-  const size_t G = (size_t)h->cfg.n_grid * h->cfg.n_grid * h->cfg.n_grid;
+  const size_t G = (size_t)h->cfg.n_grid * h->cfg.n_grid * h->cfg.n_grid * (h->slab.enabled ? 2 : 1);
   cudaError_t e = cudaMemsetAsync(h->buf.grid_pm, 0, G * sizeof(float4), (cudaStream_t)stream);
   if (e != cudaSuccess) { snprintf(h->err, sizeof(h->err), "fmpm_clear_grid: %s", cudaGetErrorString(e)); return 1; }
   return 0;
@@ -249,7 +250,7 @@ extern "C" int fmpm_clear_grid(FmpmHandle* h, void* stream) {
 
 int fmpm_p2g_impl(FmpmHandle* h, int f, int write_F, int ring_slot, void* stream) {
   if (check_bound(h, "fmpm_p2g") || check_frame(h, f, h->cfg.max_substeps_local - (write_F ? 1 : 0), "fmpm_p2g")) return 1;
-  KParams P = make_kparams(h, ring_slot);
+  KParams P = make_kparams(h, ring_slot, f);
   if (P.N == 0) return 0;
   const long long warps = ((long long)P.N + 32 * P2G_ROUNDS - 1) / (32 * P2G_ROUNDS);
   const int blocks = (int)((warps + P2G_WARPS - 1) / P2G_WARPS);
@@ -262,7 +263,7 @@ extern "C" int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream) { retur
 
 int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring_slot, void* stream) {
   if (check_bound(h, "fmpm_grid_op")) return 1;
-  KParams P = make_kparams(h, ring_slot);
+  KParams P = make_kparams(h, ring_slot, f);
   if (!P.blk_flags) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block flags were not bound"); return 1; }
   if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
   const int nblk = P.nb * P.nb * P.nb;

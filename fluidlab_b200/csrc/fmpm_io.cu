@@ -17,6 +17,7 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
   h->cfg = *cfg; h->bound = false; h->err[0] = 0; h->sm_count = 148;
   memset(&h->buf, 0, sizeof(h->buf));
   memset(&h->col, 0, sizeof(h->col));
+  memset(&h->slab, 0, sizeof(h->slab));
   *out = h;
   if (cfg->n_grid < 4 || cfg->n_particles < 0 || cfg->max_substeps_local < 1 || cfg->n_materials < 1 || cfg->n_materials > 256) {
     snprintf(h->err, sizeof(h->err), "fmpm_create: invalid config (n_grid %d, n_particles %d, T %d, n_materials %d)", cfg->n_grid,
@@ -58,6 +59,15 @@ extern "C" int fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c) {
   }
   h->col.has_rigid = c->has_rigid; h->col.collide_type = c->collide_type; h->col.y_min = c->collide_y_min;
   if (c->has_rigid) { fill_sdf(h->col.rigid, c->rigid); h->col.epos = (const float*)c->pos; h->col.equat = (const float*)c->quat; h->col.egpos = (float*)c->gpos; }
+  return 0;
+}
+
+extern "C" int fmpm_set_slab(FmpmHandle* h, const FmpmSlab* s) {
+  if (!h || !s) return 1;
+  if (s->enabled && ((s->peer_pm_left && s->left_hi <= s->left_lo) || (s->peer_pm_right && s->right_hi <= s->right_lo))) {
+    snprintf(h->err, sizeof(h->err), "fmpm_set_slab: empty ghost plane range"); return 1;
+  }
+  h->slab = *s;
   return 0;
 }
 

@@ -54,6 +54,8 @@ struct Window {
   int node;              // linear grid index of this lane's node for cur_key
   float oa, ob, oc; int a, b, c; bool lane_valid; int wrow; int qidx;
   int n, nb; int* flags; // grid size, blocks per dim, active-block flags (nullptr: do not flag)
+  // x-slab mode: the neighbours' accumulators (NVLink peer memory) and the node planes shared with them
+  float4* peer_l; float4* peer_r; int gl_lo, gl_hi, gr_lo, gr_hi; int plane;
 };
 __device__ __forceinline__ void window_init(Window& W, const int lane, const int n, int* flags) {
   const int L = lane < 27 ? lane : 26;
@@ -64,6 +66,17 @@ __device__ __forceinline__ void window_init(Window& W, const int lane, const int
   W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
   W.cur_key = -1; W.node = 0;
   W.n = n; W.nb = n >> 3; W.flags = flags;
+  W.peer_l = W.peer_r = nullptr; W.gl_lo = W.gl_hi = W.gr_lo = W.gr_hi = 0; W.plane = 0;
+}
+__device__ __forceinline__ void window_set_slab(Window& W, float4* peer_l, float4* peer_r, int gl_lo, int gl_hi, int gr_lo, int gr_hi) {
+  W.peer_l = peer_l; W.peer_r = peer_r; W.gl_lo = gl_lo; W.gl_hi = gl_hi; W.gr_lo = gr_lo; W.gr_hi = gr_hi;
+}
+// one vector reduction into the local accumulator and, for nodes on a plane shared with a neighbouring slab, the same
+// reduction into that neighbour's accumulator over NVLink (the ghost all-reduce fused into the scatter)
+__device__ __forceinline__ void window_flush_node(const Window& W, float4* __restrict__ grid, const float4& v) {
+  red_add_v4(grid + W.node, v);
+  if (W.peer_r != nullptr && W.plane >= W.gr_lo && W.plane < W.gr_hi) red_add_v4(W.peer_r + W.node, v);
+  if (W.peer_l != nullptr && W.plane >= W.gl_lo && W.plane < W.gl_hi) red_add_v4(W.peer_l + W.node, v);
 }
 // flag the 8^3-node block of this lane's node (test before write: the flag words are shared by every SM)
 __device__ __forceinline__ void window_flag(const Window& W, const int i, const int j, const int k) {
@@ -71,7 +84,7 @@ __device__ __forceinline__ void window_flag(const Window& W, const int i, const 
   if (W.flags[blk] == 0) W.flags[blk] = 1;
 }
 __device__ __forceinline__ void window_flush_all(Window& W, float4* __restrict__ grid) {
-  if (W.cur_key >= 0 && W.lane_valid) red_add_v4(grid + W.node, make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y));
+  if (W.cur_key >= 0 && W.lane_valid) window_flush_node(W, grid, make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y));
   W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
   W.cur_key = -1;
 }
@@ -81,7 +94,7 @@ __device__ __forceinline__ void window_move(Window& W, const int key, float4* __
   if (W.cur_key >= 0) {
     const float4 v = make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y);
     if (key == W.cur_key + 1) {  // next cell of the same z-column: plane c=0 is complete, shift the other two
-      if (W.lane_valid && W.c == 0) red_add_v4(grid + W.node, v);
+      if (W.lane_valid && W.c == 0) window_flush_node(W, grid, v);
       float4 t;
       t.x = __shfl_down_sync(SC_FULL, v.x, 1); t.y = __shfl_down_sync(SC_FULL, v.y, 1);
       t.z = __shfl_down_sync(SC_FULL, v.z, 1); t.w = __shfl_down_sync(SC_FULL, v.w, 1);
@@ -95,11 +108,11 @@ __device__ __forceinline__ void window_move(Window& W, const int key, float4* __
       }
       return;
     }
-    if (W.lane_valid) red_add_v4(grid + W.node, v);
+    if (W.lane_valid) window_flush_node(W, grid, v);
     W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
   }
   const int i = (key >> 20) + W.a, j = ((key >> 10) & 1023) + W.b, k = (key & 1023) + W.c;
-  W.node = (i * W.n + j) * W.n + k;
+  W.node = (i * W.n + j) * W.n + k; W.plane = i;
   W.cur_key = key;
   if (W.flags && W.lane_valid) window_flag(W, i, j, k);
 }

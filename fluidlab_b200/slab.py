@@ -5,10 +5,13 @@ The reference is single-device (no collective anywhere); this is new design.  On
 
   * the grid's x node planes are cut into `world` contiguous slabs (boundaries multiples of 8 = sparse-block size);
     rank r owns the particles whose stencil-centre plane `int(x*inv_dx - 0.5) + 1` lies in [bounds[r], bounds[r+1]);
-  * every substep, after the local p2g, neighbouring ranks exchange ONLY the ghost region of the (momentum, mass)
-    accumulator — `halo` planes either side of their common boundary, one contiguous chunk because x is the slowest
-    grid index — with ONE in-place NCCL all-reduce per boundary over a 2-rank communicator (an all-reduce of only the
-    ghost cells, over NVLink).  grid_op then runs redundantly on the ghosts, so g2p needs no second exchange;
+  * the ghost region of the (momentum, mass) accumulator — `halo` node planes either side of a slab boundary — must hold the
+    sum of both neighbours' contributions.  Default (`exchange='peer'`): the reduction is FUSED INTO p2g: each rank maps its
+    neighbours' accumulators through CUDA IPC and p2g's vector reductions (REDG.F32x4) for nodes on shared planes go to the
+    local grid AND, over NVLink peer memory, to the neighbour's grid; the accumulator is double-buffered by substep parity so
+    a fast neighbour can never scatter into a buffer that is still being consumed, and one 4-byte all-reduce per substep is
+    the only synchronisation.  Fallback (`exchange='nccl'`): one in-place NCCL all-reduce of the ghost planes per boundary
+    over a 2-rank communicator.  grid_op then runs redundantly on the ghosts, so g2p needs no second exchange;
   * at step boundaries particles whose centre plane left the slab migrate to the neighbour (100 B records + material row
     + global id).  The leaver census is asynchronous (all-reduce -> pinned host, read one step later), so steps without
     leavers never synchronise the host.  `halo` = 4 planes tolerates 3 cells of drift over the two steps between a
@@ -130,7 +133,8 @@ def migrate(state, lo, hi, rank, world, inv_dx, group=None):
 class SlabMPMSimulator:
     """Forward MLS-MPM over x-slabs: one local `MPMSimulator` per rank + ghost exchange + migration."""
 
-    def __init__(self, quality, gravity, particles, gid, bounds, capacity, boundary=None, max_substeps_local=50, device=None, group=None, halo=4):
+    def __init__(self, quality, gravity, particles, gid, bounds, capacity, boundary=None, max_substeps_local=50, device=None, group=None, halo=4,
+                 exchange='peer'):
         from .simulator import MPMSimulator
         from .macros import NOWHERE
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -155,8 +159,40 @@ class SlabMPMSimulator:
         self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.ghost = GhostExchange(self.sim.n_grid, self.bounds, self.rank, self.world, halo=halo, group=group)
         self.n_migrated = 0
+        self.exchange = exchange if self.world > 1 else 'none'
+        if self.exchange == 'peer':
+            self._setup_peer(halo)
         self._census_host = None
         self._census_event = None
+
+    def _setup_peer(self, halo):
+        """double-buffer the accumulator, exchange CUDA IPC handles with the neighbours, register the peer pointers."""
+        import ctypes as C
+        from torch.multiprocessing.reductions import reduce_tensor
+        from . import _lib
+        sim = self.sim
+        G = sim.n_grid ** 3
+        sim._grid_pm = torch.zeros((2, G, 4), dtype=torch.float32, device=sim.device)
+        sim._bind()
+        fn, args = reduce_tensor(sim._grid_pm)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, args, group=self.group)
+        self._peers = {}
+        for peer in (self.rank - 1, self.rank + 1):
+            if 0 <= peer < self.world:
+                t = fn(*gathered[peer])           # the neighbour's accumulator mapped into this process (NVLink peer access)
+                assert t.shape == sim._grid_pm.shape
+                self._peers[peer] = t
+        slab = _lib.FmpmSlab()
+        slab.enabled = 1
+        lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        if self.rank - 1 in self._peers:
+            slab.peer_pm_left = self._peers[self.rank - 1].data_ptr(); slab.left_lo, slab.left_hi = lo - halo, lo + halo
+        if self.rank + 1 in self._peers:
+            slab.peer_pm_right = self._peers[self.rank + 1].data_ptr(); slab.right_lo, slab.right_hi = hi - halo, hi + halo
+        sim._ck(sim._lib.fmpm_set_slab(sim._h, C.byref(slab)), 'fmpm_set_slab')
+        self._bar = torch.zeros(1, dtype=torch.int32, device=sim.device)
+        dist.barrier(group=self.group)
 
     def _census_async(self):
         """enqueue (no host sync): per-rank leaver counts -> all-gather -> total -> pinned host; read one step later."""
@@ -204,7 +240,10 @@ class SlabMPMSimulator:
         for _ in range(sim.n_substeps):
             f = sim.cur_substep_local
             sim.phase('p2g', f, 1)
-            if self.world > 1:
+            if self.exchange == 'peer':
+                dist.all_reduce(self._bar, group=self.group)   # every rank's p2g (incl. its peer reductions) has completed
+                self.ghost.flag_ghost_blocks(sim._blk_flags)
+            elif self.exchange == 'nccl':
                 self.ghost.exchange_sum(sim._grid_pm)
                 self.ghost.flag_ghost_blocks(sim._blk_flags)
             sim.phase('grid_op', f, 1)

@@ -130,6 +130,19 @@ typedef struct {
 } FmpmColliders;
 int  fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c);
 
+/* Multi-GPU x-slab mode (no counterpart in the reference, which is single-device).  The (momentum, mass)
+ * accumulator becomes double-buffered by substep parity (grid_pm = float4[2][G]) and p2g adds every contribution that lands
+ * on a ghost plane BOTH to the local grid and, with a vector reduction over NVLink peer memory, to the neighbour's grid
+ * (peer_pm_* are the neighbours' grid_pm base pointers mapped into this process, e.g. through CUDA IPC).  After one barrier
+ * between the ranks both copies of the ghost region hold the full sums — the ghost all-reduce is fused into the scatter. */
+typedef struct {
+  int enabled;
+  void* peer_pm_left; void* peer_pm_right;   /* float4[2][G] of rank-1 / rank+1, NULL at the ends */
+  int left_lo, left_hi;                      /* node planes [lo,hi) shared with the left neighbour */
+  int right_lo, right_hi;                    /* node planes shared with the right neighbour */
+} FmpmSlab;
+int  fmpm_set_slab(FmpmHandle* h, const FmpmSlab* s);
+
 int  fmpm_create(const FmpmConfig* cfg, FmpmHandle** out);
 void fmpm_destroy(FmpmHandle* h);
 int  fmpm_bind(FmpmHandle* h, const FmpmBuffers* b);
