@@ -180,8 +180,13 @@ class SlabMPMSimulator:
         self._peers = {}
         for peer in (self.rank - 1, self.rank + 1):
             if 0 <= peer < self.world:
-                t = fn(*gathered[peer])           # the neighbour's accumulator mapped into this process (NVLink peer access)
+                t = fn(*gathered[peer])           # the neighbour's accumulator mapped into this process (CUDA IPC)
                 assert t.shape == sim._grid_pm.shape
+                assert torch.cuda.can_device_access_peer(sim.device.index, t.device.index), 'no NVLink/PCIe peer access between the slabs'
+                # torch enables peer access between two devices lazily, on the first cross-device copy: trigger it both ways so
+                # that kernels running on this GPU may dereference the mapped pointer
+                probe = t.view(-1)[:4].to(sim.device); probe.to(t.device)
+                torch.cuda.synchronize(sim.device)
                 self._peers[peer] = t
         slab = _lib.FmpmSlab()
         slab.enabled = 1
