@@ -9,8 +9,8 @@ The reference is single-device (no collective anywhere); this is new design.  On
     sum of both neighbours' contributions.  Default (`exchange='peer'`): the reduction is FUSED INTO p2g: each rank maps its
     neighbours' accumulators through CUDA IPC and p2g's vector reductions (REDG.F32x4) for nodes on shared planes go to the
     local grid AND, over NVLink peer memory, to the neighbour's grid; the accumulator is double-buffered by substep parity so
-    a fast neighbour can never scatter into a buffer that is still being consumed, and one 4-byte all-reduce per substep is
-    the only synchronisation.  Fallback (`exchange='nccl'`): one in-place NCCL all-reduce of the ghost planes per boundary
+    a fast neighbour can never scatter into a buffer that is still being consumed, and one device-side signal-pad barrier
+    per substep (symmetric memory) is the only synchronisation.  Fallback (`exchange='nccl'`): one in-place NCCL all-reduce of the ghost planes per boundary
     over a 2-rank communicator.  grid_op then runs redundantly on the ghosts, so g2p needs no second exchange;
   * at step boundaries particles whose centre plane left the slab migrate to the neighbour (100 B records + material row
     + global id).  The leaver census is asynchronous (all-reduce -> pinned host, read one step later), so steps without
@@ -166,37 +166,37 @@ class SlabMPMSimulator:
         self._census_event = None
 
     def _setup_peer(self, halo):
-        """double-buffer the accumulator, exchange CUDA IPC handles with the neighbours, register the peer pointers."""
+        """Double-buffer the accumulator in SYMMETRIC MEMORY (torch.distributed._symmetric_memory: every rank's buffer is mapped
+        into every other rank's address space over NVLink), and register the neighbours' pointers with the library.
+        Falls back to the NCCL ghost all-reduce if symmetric memory cannot be set up on this system."""
         import ctypes as C
-        from torch.multiprocessing.reductions import reduce_tensor
         from . import _lib
         sim = self.sim
         G = sim.n_grid ** 3
-        sim._grid_pm = torch.zeros((2, G, 4), dtype=torch.float32, device=sim.device)
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty((2, G, 4), dtype=torch.float32, device=sim.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group)
+            ptrs = list(hdl.buffer_ptrs)
+        except Exception as e:  # pragma: no cover - depends on the driver / fabric
+            if self.rank == 0:
+                print(f'[fluidlab_b200.slab] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL ghost all-reduce')
+            self.exchange = 'nccl'
+            return
+        sim._grid_pm = buf
         sim._bind()
-        fn, args = reduce_tensor(sim._grid_pm)
-        gathered = [None] * self.world
-        dist.all_gather_object(gathered, args, group=self.group)
-        self._peers = {}
-        for peer in (self.rank - 1, self.rank + 1):
-            if 0 <= peer < self.world:
-                t = fn(*gathered[peer])           # the neighbour's accumulator mapped into this process (CUDA IPC)
-                assert t.shape == sim._grid_pm.shape
-                assert torch.cuda.can_device_access_peer(sim.device.index, t.device.index), 'no NVLink/PCIe peer access between the slabs'
-                # torch enables peer access between two devices lazily, on the first cross-device copy: trigger it both ways so
-                # that kernels running on this GPU may dereference the mapped pointer
-                probe = t.view(-1)[:4].to(sim.device); probe.to(t.device)
-                torch.cuda.synchronize(sim.device)
-                self._peers[peer] = t
+        self._symm = hdl
         slab = _lib.FmpmSlab()
         slab.enabled = 1
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
-        if self.rank - 1 in self._peers:
-            slab.peer_pm_left = self._peers[self.rank - 1].data_ptr(); slab.left_lo, slab.left_hi = lo - halo, lo + halo
-        if self.rank + 1 in self._peers:
-            slab.peer_pm_right = self._peers[self.rank + 1].data_ptr(); slab.right_lo, slab.right_hi = hi - halo, hi + halo
+        if self.rank > 0:
+            slab.peer_pm_left = int(ptrs[self.rank - 1]); slab.left_lo, slab.left_hi = lo - halo, lo + halo
+        if self.rank < self.world - 1:
+            slab.peer_pm_right = int(ptrs[self.rank + 1]); slab.right_lo, slab.right_hi = hi - halo, hi + halo
         sim._ck(sim._lib.fmpm_set_slab(sim._h, C.byref(slab)), 'fmpm_set_slab')
-        self._bar = torch.zeros(1, dtype=torch.int32, device=sim.device)
+        torch.cuda.synchronize(sim.device)
         dist.barrier(group=self.group)
 
     def _census_async(self):
@@ -246,7 +246,7 @@ class SlabMPMSimulator:
             f = sim.cur_substep_local
             sim.phase('p2g', f, 1)
             if self.exchange == 'peer':
-                dist.all_reduce(self._bar, group=self.group)   # every rank's p2g (incl. its peer reductions) has completed
+                self._symm.barrier(channel=0)                  # device-side: every rank's p2g (incl. its peer reductions) has completed
                 self.ghost.flag_ghost_blocks(sim._blk_flags)
             elif self.exchange == 'nccl':
                 self.ghost.exchange_sum(sim._grid_pm)
