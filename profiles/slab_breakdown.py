@@ -10,7 +10,8 @@ q = 4; n = 64 * q; dx = 1.0 / n
 bounds = slab_bounds(32, 32 + 24 * world, world)
 lo = ((bounds[rank] - 0.5) * dx, 0.30, 0.36); hi = ((bounds[rank + 1] - 0.5) * dx, 0.30 + 72 * dx, 0.36 + 72 * dx)
 parts = bench.workload_particles(1_000_000, seed=rank, lo=lo, hi=hi)
-slab = SlabMPMSimulator(q, (0, -10, 0), parts, gid=np.arange(1_000_000) + rank * 1_000_000, bounds=bounds, capacity=1_100_000, device=dev)
+MODE = os.environ.get('SLAB_EXCHANGE', 'peer')
+slab = SlabMPMSimulator(q, (0, -10, 0), parts, gid=np.arange(1_000_000) + rank * 1_000_000, bounds=bounds, capacity=1_100_000, device=dev, exchange=MODE)
 sim = slab.sim
 for _ in range(3): slab.step()
 
@@ -21,7 +22,8 @@ def loop(n, exch, flags, mig=False):
         if mig and i % 10 == 0: slab._migrate(); sim.sort_frame(sim.cur_substep_local)
         f = sim.cur_substep_local
         sim.phase('p2g', f, 1)
-        if exch: slab.ghost.exchange_sum(sim._grid_pm)
+        if exch and slab.exchange == 'nccl': slab.ghost.exchange_sum(sim._grid_pm)
+        if exch and slab.exchange == 'peer': slab._symm.barrier(channel=0)
         if flags: slab.ghost.flag_ghost_blocks(sim._blk_flags)
         sim.phase('grid_op', f, 1); sim.phase('g2p', f)
         sim.cur_substep_global += 1
@@ -33,5 +35,5 @@ for name, kw in (('no exchange', dict(exch=False, flags=False)), ('flags only', 
                  ('exchange+flags', dict(exch=True, flags=True)), ('full (+migrate+sort per 10)', dict(exch=True, flags=True, mig=True))):
     loop(20, **kw)
     g, c = loop(100, **kw)
-    if rank == 0: print(f'{name:32s} gpu {g:7.1f} us/substep   cpu-issue {c:7.1f} us/substep', flush=True)
+    if rank == 0: print(f'[{slab.exchange}] {name:32s} gpu {g:7.1f} us/substep   cpu-issue {c:7.1f} us/substep', flush=True)
 dist.destroy_process_group()
