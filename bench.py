@@ -185,7 +185,8 @@ def main():
         bounds = slab_bounds(32, 32 + slab_w * world, world)
         lo = ((bounds[rank] - 0.5) * dx, 0.30, 0.36); hi = ((bounds[rank + 1] - 0.5) * dx, 0.30 + 72 * dx, 0.36 + 72 * dx)
         parts = workload_particles(N, seed=rank, lo=lo, hi=hi)
-        slab = SlabMPMSimulator(q, GRAVITY, parts, gid=np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1), max_substeps_local=T, device=dev)
+        slab = SlabMPMSimulator(q, GRAVITY, parts, gid=np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1), max_substeps_local=T, device=dev,
+                                exchange=os.environ.get('SLAB_EXCHANGE', 'peer'))
         sim = slab.sim
         # the reference's fixed dt = 2e-4 is unstable for water at 256^3 beyond ~700 substeps (profiles/check_stability_256.py,
         # SURVEY.md §8d C5): restore the initial state (device-side copy, ~0.1% of the time) every 30 steps
@@ -201,7 +202,7 @@ def main():
             slab.step()
         workload = (f'C2-weak: {N} water particles per GPU (~8/cell) as {world} x-slabs of one body, 256^3 grid, fp32, forward; value counts '
                     f'1M-particle substeps (global substeps/s = value / n_gpus)')
-        parallelism = (f'{world} x-slabs; ghost-plane reduction fused into p2g (vector REDs to the neighbour grid over NVLink peer memory, '
+        parallelism = (f'{world} x-slabs, exchange={slab.exchange}; ghost-plane reduction fused into p2g (vector REDs to the neighbour grid over NVLink peer memory, '
                        f'{slab.ghost.bytes_per_exchange()} B of ghost planes per rank), one 4-byte all-reduce barrier per substep, per-step migration')
     init = sim.get_state()
     def barrier():

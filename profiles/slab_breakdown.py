@@ -14,6 +14,7 @@ MODE = os.environ.get('SLAB_EXCHANGE', 'peer')
 slab = SlabMPMSimulator(q, (0, -10, 0), parts, gid=np.arange(1_000_000) + rank * 1_000_000, bounds=bounds, capacity=1_100_000, device=dev, exchange=MODE)
 sim = slab.sim
 for _ in range(3): slab.step()
+init = {k: v.clone() for k, v in sim.readframe_torch(sim.cur_substep_local).items()}
 
 def loop(n, exch, flags, mig=False):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
@@ -33,6 +34,7 @@ def loop(n, exch, flags, mig=False):
     return a.elapsed_time(b) / n * 1e3, cpu
 for name, kw in (('no exchange', dict(exch=False, flags=False)), ('flags only', dict(exch=False, flags=True)), ('exchange only', dict(exch=True, flags=False)),
                  ('exchange+flags', dict(exch=True, flags=True)), ('full (+migrate+sort per 10)', dict(exch=True, flags=True, mig=True))):
+    sim.cur_substep_global = 0; sim.set_state(0, init); sim.phase('clear_grid', 0); sim._blk_flags.zero_()
     loop(20, **kw)
     g, c = loop(100, **kw)
     if rank == 0: print(f'[{slab.exchange}] {name:32s} gpu {g:7.1f} us/substep   cpu-issue {c:7.1f} us/substep', flush=True)
