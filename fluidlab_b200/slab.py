@@ -20,6 +20,7 @@ The reference is single-device (no collective anywhere); this is new design.  On
 `SlabMPMSimulator` covers the forward path (step / gather_state); the backward ghost exchange (v_out adjoint planes) is the
 mirror image and is not wired yet.
 """
+import os
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -239,7 +240,7 @@ class SlabMPMSimulator:
 
     def step(self):
         sim = self.sim
-        if self.world > 1:
+        if self.world > 1 and not os.environ.get('SLAB_NO_MIGRATE'):
             self._migrate()
         sim.sort_frame(sim.cur_substep_local)
         for _ in range(sim.n_substeps):
