@@ -43,6 +43,7 @@ struct KParams {
   CollidersDev col;
   // x-slab mode: neighbours' accumulators (peer memory over NVLink) and the node-plane ranges shared with them
   float4* peer_l; float4* peer_r; int gl_lo, gl_hi, gr_lo, gr_hi;
+  int* peer_fl; int* peer_fr;
 };
 
 // ring_slot >= 0: the (momentum, mass) / v_out grids and the active-block list live in slot `ring_slot` of the per-frame ring
@@ -63,12 +64,16 @@ static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1, int 
   P.mats = (const float4*)h->buf.materials;
   P.col = h->col;
   P.blk_flags = (int*)h->buf.blk_flags; P.blk_list = (int*)h->buf.blk_list; P.blk_count = (int*)h->buf.blk_count; P.nb = c.n_grid / 8;
-  P.peer_l = P.peer_r = nullptr; P.gl_lo = P.gl_hi = P.gr_lo = P.gr_hi = 0;
+  P.peer_l = P.peer_r = nullptr; P.gl_lo = P.gl_hi = P.gr_lo = P.gr_hi = 0; P.peer_fl = P.peer_fr = nullptr;
   if (h->slab.enabled) {  // accumulator double-buffered by substep parity; peers use the same parity
     const size_t off = (size_t)(parity & 1) * P.G;
     P.grid_pm += off;
     if (h->slab.peer_pm_left) P.peer_l = (float4*)h->slab.peer_pm_left + off;
     if (h->slab.peer_pm_right) P.peer_r = (float4*)h->slab.peer_pm_right + off;
+    const size_t foff = (size_t)(parity & 1) * P.nb * P.nb * P.nb;
+    P.blk_flags += foff;
+    if (h->slab.peer_flags_left) P.peer_fl = (int*)h->slab.peer_flags_left + foff;
+    if (h->slab.peer_flags_right) P.peer_fr = (int*)h->slab.peer_flags_right + foff;
     P.gl_lo = h->slab.left_lo; P.gl_hi = h->slab.left_hi; P.gr_lo = h->slab.right_lo; P.gr_hi = h->slab.right_hi;
   }
   if (ring_slot >= 0 && h->buf.grid_pm_ring) {

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
   const long long slot0 = gw * (32 * P2G_ROUNDS);
   if (slot0 >= P.N) return;
   Window W; window_init(W, lane, P.n, P.blk_flags);
-  window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi);
+  window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);
   PRaw R; p2g_load_raw(P, f, slot0 + lane, R);
 #pragma unroll 1
   for (int r = 0; r < P2G_ROUNDS; r++) {
@@ -113,8 +113,20 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
 // and zeroes the v_out adjoint of the same blocks (backward pass).
 __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, const int clear_pm, const int zero_ggv, const int reset_flags) {
   const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    if (P.blk_flags[blk] == 0) continue;  // CTA-uniform
+  // this CTA owns blocks blockIdx.x + q*gridDim.x; their flags are fetched in parallel (thread q reads flag q) and the CTA
+  // then walks the flagged ones (nblk / gridDim.x <= 256 for every supported grid)
+  __shared__ int s_act[256];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  {
+    const int blk = blockIdx.x + threadIdx.x * gridDim.x;
+    if (blk < nblk && P.blk_flags[blk] != 0) s_act[atomicAdd(&s_n, 1)] = blk;
+  }
+  __syncthreads();
+  const int n_act = s_n;
+  for (int ai = 0; ai < n_act; ai++) {
+    const int blk = s_act[ai];
     const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, c
       if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (zero_ggv) P.ggrid_v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (reset_flags) { __syncthreads(); if (threadIdx.x == 0) P.blk_flags[blk] = 0; }
+    if (reset_flags && threadIdx.x == 0) P.blk_flags[blk] = 0;
   }
 }
 
@@ -267,7 +279,8 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring
   if (!P.blk_flags) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block flags were not bound"); return 1; }
   if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
   const int nblk = P.nb * P.nb * P.nb;
-  const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  if ((nblk + grid - 1) / grid > 256) grid = (nblk + 255) / 256;  // keep <= 256 blocks per CTA (parallel flag fetch)
   // the flags are consumed (reset) here only when nothing later in the substep needs them: plain forward substeps
   const int reset_flags = (clear_pm && ring_slot < 0) ? 1 : 0;
   k_grid_op<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm, zero_ggv, reset_flags);

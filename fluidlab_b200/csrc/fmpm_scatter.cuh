@@ -56,6 +56,7 @@ struct Window {
   int n, nb; int* flags; // grid size, blocks per dim, active-block flags (nullptr: do not flag)
   // x-slab mode: the neighbours' accumulators (NVLink peer memory) and the node planes shared with them
   float4* peer_l; float4* peer_r; int gl_lo, gl_hi, gr_lo, gr_hi; int plane;
+  int* peer_fl; int* peer_fr;
 };
 __device__ __forceinline__ void window_init(Window& W, const int lane, const int n, int* flags) {
   const int L = lane < 27 ? lane : 26;
@@ -66,10 +67,10 @@ __device__ __forceinline__ void window_init(Window& W, const int lane, const int
   W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
   W.cur_key = -1; W.node = 0;
   W.n = n; W.nb = n >> 3; W.flags = flags;
-  W.peer_l = W.peer_r = nullptr; W.gl_lo = W.gl_hi = W.gr_lo = W.gr_hi = 0; W.plane = 0;
+  W.peer_l = W.peer_r = nullptr; W.gl_lo = W.gl_hi = W.gr_lo = W.gr_hi = 0; W.plane = 0; W.peer_fl = W.peer_fr = nullptr;
 }
-__device__ __forceinline__ void window_set_slab(Window& W, float4* peer_l, float4* peer_r, int gl_lo, int gl_hi, int gr_lo, int gr_hi) {
-  W.peer_l = peer_l; W.peer_r = peer_r; W.gl_lo = gl_lo; W.gl_hi = gl_hi; W.gr_lo = gr_lo; W.gr_hi = gr_hi;
+__device__ __forceinline__ void window_set_slab(Window& W, float4* peer_l, float4* peer_r, int gl_lo, int gl_hi, int gr_lo, int gr_hi, int* peer_fl, int* peer_fr) {
+  W.peer_l = peer_l; W.peer_r = peer_r; W.gl_lo = gl_lo; W.gl_hi = gl_hi; W.gr_lo = gr_lo; W.gr_hi = gr_hi; W.peer_fl = peer_fl; W.peer_fr = peer_fr;
 }
 // one vector reduction into the local accumulator and, for nodes on a plane shared with a neighbouring slab, the same
 // reduction into that neighbour's accumulator over NVLink (the ghost all-reduce fused into the scatter)
@@ -82,6 +83,9 @@ __device__ __forceinline__ void window_flush_node(const Window& W, float4* __res
 __device__ __forceinline__ void window_flag(const Window& W, const int i, const int j, const int k) {
   const int blk = ((i >> 3) * W.nb + (j >> 3)) * W.nb + (k >> 3);
   if (W.flags[blk] == 0) W.flags[blk] = 1;
+  // x-slab mode: the neighbour must visit (and later clear) the blocks this rank reduces into over NVLink
+  if (W.peer_fr != nullptr && i >= W.gr_lo && i < W.gr_hi) W.peer_fr[blk] = 1;
+  if (W.peer_fl != nullptr && i >= W.gl_lo && i < W.gl_hi) W.peer_fl[blk] = 1;
 }
 __device__ __forceinline__ void window_flush_all(Window& W, float4* __restrict__ grid) {
   if (W.cur_key >= 0 && W.lane_valid) window_flush_node(W, grid, make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y));

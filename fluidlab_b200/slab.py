@@ -7,8 +7,8 @@ The reference is single-device (no collective anywhere); this is new design.  On
     rank r owns the particles whose stencil-centre plane `int(x*inv_dx - 0.5) + 1` lies in [bounds[r], bounds[r+1]);
   * the ghost region of the (momentum, mass) accumulator — `halo` node planes either side of a slab boundary — must hold the
     sum of both neighbours' contributions.  Default (`exchange='peer'`): the reduction is FUSED INTO p2g: each rank maps its
-    neighbours' accumulators through CUDA IPC and p2g's vector reductions (REDG.F32x4) for nodes on shared planes go to the
-    local grid AND, over NVLink peer memory, to the neighbour's grid; the accumulator is double-buffered by substep parity so
+    neighbours' accumulators (symmetric memory) and p2g's vector reductions (REDG.F32x4) for nodes on shared planes go to the
+    local grid AND, over NVLink peer memory, to the neighbour's grid (p2g also sets the neighbour's sparse-block flags); the accumulator is double-buffered by substep parity so
     a fast neighbour can never scatter into a buffer that is still being consumed, and one device-side signal-pad barrier
     per substep (symmetric memory) is the only synchronisation.  Fallback (`exchange='nccl'`): one in-place NCCL all-reduce of the ghost planes per boundary
     over a 2-rank communicator.  grid_op then runs redundantly on the ghosts, so g2p needs no second exchange;
@@ -181,21 +181,29 @@ class SlabMPMSimulator:
             buf.zero_()
             hdl = symm_mem.rendezvous(buf, group)
             ptrs = list(hdl.buffer_ptrs)
+            nblk = (sim.n_grid // 8) ** 3
+            fbuf = symm_mem.empty((2, nblk), dtype=torch.int32, device=sim.device)
+            fbuf.zero_()
+            fhdl = symm_mem.rendezvous(fbuf, group)
+            fptrs = list(fhdl.buffer_ptrs)
         except Exception as e:  # pragma: no cover - depends on the driver / fabric
             if self.rank == 0:
                 print(f'[fluidlab_b200.slab] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL ghost all-reduce')
             self.exchange = 'nccl'
             return
         sim._grid_pm = buf
+        sim._blk_flags = fbuf
         sim._bind()
-        self._symm = hdl
+        self._symm, self._symm_flags = hdl, fhdl
         slab = _lib.FmpmSlab()
         slab.enabled = 1
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         if self.rank > 0:
-            slab.peer_pm_left = int(ptrs[self.rank - 1]); slab.left_lo, slab.left_hi = lo - halo, lo + halo
+            slab.peer_pm_left = int(ptrs[self.rank - 1]); slab.peer_flags_left = int(fptrs[self.rank - 1])
+            slab.left_lo, slab.left_hi = lo - halo, lo + halo
         if self.rank < self.world - 1:
-            slab.peer_pm_right = int(ptrs[self.rank + 1]); slab.right_lo, slab.right_hi = hi - halo, hi + halo
+            slab.peer_pm_right = int(ptrs[self.rank + 1]); slab.peer_flags_right = int(fptrs[self.rank + 1])
+            slab.right_lo, slab.right_hi = hi - halo, hi + halo
         sim._ck(sim._lib.fmpm_set_slab(sim._h, C.byref(slab)), 'fmpm_set_slab')
         torch.cuda.synchronize(sim.device)
         dist.barrier(group=self.group)
@@ -247,8 +255,7 @@ class SlabMPMSimulator:
             f = sim.cur_substep_local
             sim.phase('p2g', f, 1)
             if self.exchange == 'peer':
-                self._symm.barrier(channel=0)                  # device-side: every rank's p2g (incl. its peer reductions) has completed
-                self.ghost.flag_ghost_blocks(sim._blk_flags)
+                self._symm.barrier(channel=0)   # device-side: every rank's p2g (incl. its peer reductions and peer block flags) has completed
             elif self.exchange == 'nccl':
                 self.ghost.exchange_sum(sim._grid_pm)
                 self.ghost.flag_ghost_blocks(sim._blk_flags)

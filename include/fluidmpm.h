@@ -138,6 +138,8 @@ int  fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c);
 typedef struct {
   int enabled;
   void* peer_pm_left; void* peer_pm_right;   /* float4[2][G] of rank-1 / rank+1, NULL at the ends */
+  void* peer_flags_left; void* peer_flags_right; /* the neighbours' blk_flags (int[2][(n_grid/8)^3]): p2g also flags the neighbour's blocks
+                                                 it reduces into; in slab mode blk_flags is double-buffered by parity like grid_pm */
   int left_lo, left_hi;                      /* node planes [lo,hi) shared with the left neighbour */
   int right_lo, right_hi;                    /* node planes shared with the right neighbour */
 } FmpmSlab;

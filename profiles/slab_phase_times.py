@@ -23,7 +23,8 @@ for step in range(10):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record(); sim.phase('p2g', f, 1)
         ev[1].record(); slab._symm.barrier(channel=0) if slab.exchange == 'peer' else slab.ghost.exchange_sum(sim._grid_pm)
-        ev[2].record(); slab.ghost.flag_ghost_blocks(sim._blk_flags)
+        ev[2].record()
+        if slab.exchange != 'peer': slab.ghost.flag_ghost_blocks(sim._blk_flags)
         ev[3].record(); sim.phase('grid_op', f, 1)
         ev[4].record(); sim.phase('g2p', f)
         ev[5].record(); torch.cuda.synchronize()
