@@ -202,8 +202,11 @@ def main():
             slab.step()
         workload = (f'C2-weak: {N} water particles per GPU (~8/cell) as {world} x-slabs of one body, 256^3 grid, fp32, forward; value counts '
                     f'1M-particle substeps (global substeps/s = value / n_gpus)')
-        parallelism = (f'{world} x-slabs, exchange={slab.exchange}; ghost-plane reduction fused into p2g (vector REDs to the neighbour grid over NVLink peer memory, '
-                       f'{slab.ghost.bytes_per_exchange()} B of ghost planes per rank), one 4-byte all-reduce barrier per substep, per-step migration')
+        if slab.exchange == 'peer':
+            parallelism = (f'{world} x-slabs; ghost-plane reduction fused into p2g (vector REDs into the neighbour grid over NVLink peer memory, '
+                           f'parity double-buffered), one device-side signal-pad barrier per substep, no data-path collective; per-step migration')
+        else:
+            parallelism = (f'{world} x-slabs; NCCL pair all-reduce of {slab.ghost.bytes_per_exchange()} B of ghost planes per rank per substep; per-step migration')
     init = sim.get_state()
     def barrier():
         if world > 1:

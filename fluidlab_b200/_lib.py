@@ -83,8 +83,17 @@ class FmpmSlab(C.Structure):
                 ("right_lo", C.c_int), ("right_hi", C.c_int)]
 
 
+class FmpmBodies(C.Structure):
+    _fields_ = [("n_bodies", C.c_int), ("info", vp), ("state", vp), ("grad", vp)]
+
+
+BODY_STATE_STRIDE, BODY_GRAD_STRIDE = 48, 32
+
 _I, _F, _U = C.c_int, C.c_float, C.c_uint
 _PROTOS = {
+    "fmpm_set_bodies": (_I, [vp, C.POINTER(FmpmBodies)]),
+    "fmpm_advect_rigid": (_I, [vp, _I, vp]),
+    "fmpm_advect_rigid_grad": (_I, [vp, _I, _I, vp, vp]),
     "fmpm_set_colliders": (_I, [vp, C.POINTER(FmpmColliders)]),
     "fmpm_set_slab": (_I, [vp, C.POINTER(FmpmSlab)]),
     "fmpm_create": (_I, [C.POINTER(FmpmConfig), C.POINTER(vp)]),

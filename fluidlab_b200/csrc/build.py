@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRCS = ["fmpm_forward.cu", "fmpm_backward.cu", "fmpm_io.cu"]
+SRCS = ["fmpm_forward.cu", "fmpm_backward.cu", "fmpm_io.cu", "fmpm_rigid.cu"]
 HDRS = ["fmpm_common.cuh", "fmpm_scatter.cuh", "fmpm_sdf.cuh", os.path.join("..", "..", "include", "fluidmpm.h")]
 OUT = os.path.join(HERE, "..", "libfluidmpm.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -21,10 +21,13 @@ struct FmpmHandle {
   FmpmBuffers buf;
   CollidersDev col;
   FmpmSlab slab;
+  FmpmBodies bodies;
   bool bound;
   char err[512];
   int sm_count;
 };
+
+int fmpm_advect_rigid_impl(FmpmHandle* h, int f, void* stream);  // fmpm_rigid.cu; no-op without MAT_RIGID bodies
 
 // kernel-side view (passed by value)
 struct KParams {

@@ -331,13 +331,15 @@ extern "C" int fmpm_substep_store(FmpmHandle* h, int f, void* stream) {
   FMPM_CHECK_LAUNCH(h, "fmpm_substep_store(clear)");
   if (fmpm_p2g_impl(h, f, 1, f, stream)) return 1;
   if (fmpm_grid_op_impl(h, f, 0, 0, f, stream)) return 1;
-  return fmpm_g2p_impl(h, f, f, stream);
+  if (fmpm_g2p_impl(h, f, f, stream)) return 1;
+  return fmpm_advect_rigid_impl(h, f, stream);
 }
 
 extern "C" int fmpm_substep(FmpmHandle* h, int f, void* stream) {
   if (fmpm_p2g(h, f, 1, stream)) return 1;
   if (fmpm_grid_op(h, f, 1, stream)) return 1;
-  return fmpm_g2p(h, f, stream);
+  if (fmpm_g2p(h, f, stream)) return 1;
+  return fmpm_advect_rigid_impl(h, f, stream);
 }
 
 extern "C" int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,

@@ -18,6 +18,7 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
   memset(&h->buf, 0, sizeof(h->buf));
   memset(&h->col, 0, sizeof(h->col));
   memset(&h->slab, 0, sizeof(h->slab));
+  memset(&h->bodies, 0, sizeof(h->bodies));
   *out = h;
   if (cfg->n_grid < 4 || cfg->n_particles < 0 || cfg->max_substeps_local < 1 || cfg->n_materials < 1 || cfg->n_materials > 256) {
     snprintf(h->err, sizeof(h->err), "fmpm_create: invalid config (n_grid %d, n_particles %d, T %d, n_materials %d)", cfg->n_grid,

@@ -134,8 +134,6 @@ class MPMSimulator:
         # ---- particle info (MPM:136-175): one material-table row per distinct (material, rho)
         mat = np.asarray(particles['mat']).astype(np.int32)
         rho = np.asarray(particles['rho']).astype(DTYPE_NP)
-        if any(MAT_CLASS[int(m)] == MAT_RIGID for m in np.unique(mat)):
-            raise NotImplementedError('MAT_RIGID shape matching (MPM:449-505) is not built yet (SURVEY.md §8f rank 2)')
         rows, mrow = {}, np.zeros(N, dtype=np.int32)
         keys = np.stack([mat.astype(np.float64), rho.astype(np.float64)], 1)
         uniq, inverse = np.unique(keys, axis=0, return_inverse=True)
@@ -151,6 +149,19 @@ class MPMSimulator:
         self._body_id_np = np.asarray(particles.get('body_id', np.zeros(N))).astype(np.int32)
         self.n_bodies = int(particles['bodies']['n']) if 'bodies' in particles else 1
         self._materials = torch.from_numpy(table.view(np.float32).reshape(-1, 4).copy()).to(dev)
+        # bodies (MPM:177-201): n_particles counts every slot of the body, mat_cls is that of its first particle.  The body id rides
+        # in bits 16..23 of the particle meta word (material row in bits 8..15), see include/fluidmpm.h.
+        nb = self.n_bodies
+        assert nb == int(self._body_id_np.max()) + 1, 'bodies["n"] must equal max(body_id) + 1 (MPM:179)'
+        binfo = np.zeros((nb, 2), dtype=np.int32)
+        for b in range(nb):
+            sel = np.where(self._body_id_np == b)[0]
+            binfo[b] = (len(sel), MAT_CLASS[int(mat[sel[0]])] if len(sel) else 0)
+        self._has_rigid_bodies = bool((binfo[:, 1] == MAT_RIGID).any())
+        if self._has_rigid_bodies:
+            assert nb <= 256, 'at most 256 bodies when MAT_RIGID bodies are present'
+            mrow = mrow | (self._body_id_np << 8)
+        self._body_info_np = binfo
         self._mrow = torch.from_numpy(mrow).to(dev)
 
         # ---- device buffers (torch owns the memory, the library only sees pointers)
@@ -194,6 +205,13 @@ class MPMSimulator:
         self._ck(rc, 'fmpm_create')
         self._sort_tmp = torch.empty((int(lib.fmpm_sort_workspace_bytes(h)),), dtype=torch.uint8, device=dev)
         self._bind()
+        if self._has_rigid_bodies:
+            self._body_info = torch.from_numpy(self._body_info_np).to(dev)
+            self._body_state = torch.zeros((T, self.n_bodies, _lib.BODY_STATE_STRIDE), dtype=f32, device=dev)
+            self._body_grad = torch.zeros((self.n_bodies, _lib.BODY_GRAD_STRIDE), dtype=f32, device=dev)
+            bd = _lib.FmpmBodies()
+            bd.n_bodies, bd.info, bd.state, bd.grad = self.n_bodies, self._body_info.data_ptr(), self._body_state.data_ptr(), self._body_grad.data_ptr()
+            self._ck(lib.fmpm_set_bodies(h, C.byref(bd)), 'fmpm_set_bodies')
 
         # ---- initial frame (init_particles_kernel MPM:150-175): v = 0, F = I, C = 0
         x0 = np.asarray(particles['x']).astype(DTYPE_NP)
@@ -380,6 +398,16 @@ class MPMSimulator:
             # to the reference order (MPM:521); agent.move was folded into agent.set_action (pose chain kernel).
             self.agent.act(f, self.cur_substep_global)
 
+    def _next_slot_map(self, f):
+        """int32[N]: slot in frame f+1 of the particle in slot s of frame f; None when both frames share one order."""
+        a, b = self._frame_ord[f], self._frame_ord[f + 1]
+        if a is b:
+            return None
+        ids = a.ids if a.ids is not None else torch.arange(self.n_particles, dtype=torch.int64, device=self.device)
+        if b.inv is None:
+            return ids.to(torch.int32)
+        return b.inv[ids.long()].to(torch.int32).contiguous()
+
     def _storing(self):
         if not (self.grad_enabled and self.store_grids):
             return False
@@ -417,6 +445,9 @@ class MPMSimulator:
         if self.has_particles:
             self._ensure_grad_order(self._frame_ord[f])
             gin, gout = self._gcur, 1 - self._gcur
+            if self._has_rigid_bodies:   # advect_grad, MPM:436-447 (needs v[f+1], which lives in the slot order of frame f+1)
+                nxt = self._next_slot_map(f)
+                self._ck(self._lib.fmpm_advect_rigid_grad(self._h, f, gin, None if nxt is None else nxt.data_ptr(), self._stream()), 'fmpm_advect_rigid_grad')
             if self._pm_ring is not None and self._ring_valid[f]:
                 self._ck(self._lib.fmpm_substep_grad_stored(self._h, f, gin, gout, self._stream()), 'fmpm_substep_grad_stored')
             else:

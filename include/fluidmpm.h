@@ -145,6 +145,20 @@ typedef struct {
 } FmpmSlab;
 int  fmpm_set_slab(FmpmHandle* h, const FmpmSlab* s);
 
+/* MAT_RIGID bodies: rigidity enforcement by shape matching (MPM:177-201 body structs, MPM:428-505 advect).
+ * The body id of a particle travels in bits 16..23 of its meta word: pass mrow[p] = material_row | (body_id << 8) to
+ * fmpm_write_frame.  All pointers are device memory owned by the caller. */
+#define FMPM_BODY_STATE_STRIDE 48   /* floats per body per frame: COM_t0[3] COM_t1[3] H[9] U[9] S[3] V[9] R[9] pad[3] */
+#define FMPM_BODY_GRAD_STRIDE 32    /* floats per body: gR[9] sum_gx[3] gH[9] gCOM_t0[3] gCOM_t1[3] pad[5] */
+typedef struct FmpmBodies {
+  int n_bodies;                               /* <= 256 */
+  const void* info;                           /* int[n_bodies][2]: n_particles (MPM:199-200), mat_cls (MPM:201) */
+  void* state;                                /* float[max_substeps_local][n_bodies][48]: body state of every substep of the ring,
+                                                 written by the forward pass and reused by the adjoint (the reference recomputes it, MPM:437-441) */
+  void* grad;                                 /* float[n_bodies][32]: adjoint scratch */
+} FmpmBodies;
+int  fmpm_set_bodies(FmpmHandle* h, const FmpmBodies* b);   /* n_bodies == 0 or NULL pointers: no rigid bodies */
+
 int  fmpm_create(const FmpmConfig* cfg, FmpmHandle** out);
 void fmpm_destroy(FmpmHandle* h);
 int  fmpm_bind(FmpmHandle* h, const FmpmBuffers* b);
@@ -157,7 +171,8 @@ int fmpm_clear_grid(FmpmHandle* h, void* stream);                      /* MPM:21
 int fmpm_p2g(FmpmHandle* h, int f, int write_F, void* stream);         /* MPM:254-264 + 331-378 fused */
 int fmpm_grid_op(FmpmHandle* h, int f, int clear_pm, void* stream);    /* MPM:380-398 */
 int fmpm_g2p(FmpmHandle* h, int f, void* stream);                      /* MPM:304-316 + 400-426 + 497-505 fused */
-int fmpm_substep(FmpmHandle* h, int f, void* stream);                  /* p2g, grid_op(clear), g2p; grid must be clear on entry */
+int fmpm_advect_rigid(FmpmHandle* h, int f, void* stream);             /* MPM:449-505 for MAT_RIGID bodies; after fmpm_g2p (no-op without such bodies) */
+int fmpm_substep(FmpmHandle* h, int f, void* stream);                  /* p2g, grid_op(clear), g2p, advect_rigid; grid must be clear on entry */
 int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, but the grids of frame f stay in ring slot f */
 /* agent.act for injector agents, agents/agent_injector.py:23-32; run after fmpm_g2p of the same f */
 int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,
@@ -167,6 +182,10 @@ int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffecto
 /* gin/gout in {0,1}: grad ping-pong index holding frame f+1 (in) and receiving frame f (out). */
 int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* stream);
 int fmpm_substep_grad_stored(FmpmHandle* h, int f, int gin, int gout, void* stream);  /* uses the grids left by fmpm_substep_store(f) */
+/* MPM:436-447 advect_grad for MAT_RIGID bodies: call BEFORE fmpm_substep_grad* / fmpm_g2p_grad_scatter of the same f (it rewrites
+ * the x and v adjoints of rigid particles in gin in place; no-op without such bodies).  next_slot: int[N], slot in frame f+1 of the
+ * particle in slot s of frame f, or NULL when both frames share one slot order (no cell sort between them). */
+int fmpm_advect_rigid_grad(FmpmHandle* h, int f, int gin, const void* next_slot, void* stream);
 int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream);           /* g2p.grad: grid side */
 int fmpm_grid_op_grad(FmpmHandle* h, int f, void* stream);                        /* grid_op.grad */
 int fmpm_particle_grad(FmpmHandle* h, int f, int gin, int gout, void* stream);    /* advect/g2p/p2g/svd/F_tmp .grad: particle side */

@@ -361,6 +361,18 @@ template <class R> struct Sim {
   bool has_rigid = false;
   bool has_injector = false;
   R collide_y_min = R(-1e30);        // AgentIceCreamDynamic.collide only acts above y = 0.25 (agents/agent_icecreamdynamic.py:38-43)
+  // bodies (MPM:177-201): rigidity enforcement by shape matching for MAT_RIGID bodies
+  int n_bodies = 0;
+  std::vector<int> body_id, body_n, body_cls;
+  struct BodyState { R c0[3], c1[3]; M3<R> H, U, V, Rm; R S[3]; };
+  std::vector<BodyState> bodies;
+  bool any_rigid_body() const { for (int b = 0; b < n_bodies; b++) if (body_cls[b] == MAT_RIGID) return true; return false; }
+  void set_bodies(const int* bid, int nb) {  // MPM:177-201 init_bodies: n_particles counts every slot of the body, mat_cls = its first particle's
+    n_bodies = nb; body_id.assign(bid, bid + N); body_n.assign(nb, 0); body_cls.assign(nb, 0); bodies.resize(nb);
+    std::vector<char> seen(nb, 0);
+    for (int p = 0; p < N; p++) { int b = bid[p]; body_n[b]++; if (!seen[b]) { seen[b] = 1; body_cls[b] = cls[p]; } }
+  }
+  inline bool rigid_p(int f, int p) const { return n_bodies > 0 && used[pi(f, p)] && cls[p] == MAT_RIGID; }
 
   // agent.collide(f, pos, v, dt) for AgentRigid -> Rigid.collide -> Dynamic.collide; adjoint accumulates into effector gpos
   inline void agent_collide(int f, const R* p, const R* vin, R* out, const R* gout, R* gvv, R* gpp) {
@@ -589,11 +601,86 @@ template <class R> struct Sim {
       setM(C, q, nC);
     }
   }
-  void advect(int f) {  // MPM:497-505, non-rigid branch
+  // MPM:449-495: reset_bodies_and_grad, compute_COM, compute_H, compute_H_svd, compute_R (serial sums: deterministic)
+  void body_forward(int f) {
+    for (int b = 0; b < n_bodies; b++) if (body_cls[b] == MAT_RIGID) {
+      BodyState& B = bodies[b];
+      for (int k = 0; k < 3; k++) B.c0[k] = B.c1[k] = R(0);
+      B.H = zero3<R>();
+    }
+    for (int p = 0; p < N; p++) if (rigid_p(f, p)) {   // MPM:456-462
+      BodyState& B = bodies[body_id[p]]; const R n = (R)body_n[body_id[p]];
+      size_t a = pi(f, p), b1 = pi(f + 1, p);
+      for (int k = 0; k < 3; k++) { B.c0[k] += x[a * 3 + k] / n; B.c1[k] += (x[a * 3 + k] + dt * v[b1 * 3 + k]) / n; }
+    }
+    for (int p = 0; p < N; p++) if (rigid_p(f, p)) {   // MPM:464-477
+      BodyState& B = bodies[body_id[p]];
+      size_t a = pi(f, p), b1 = pi(f + 1, p);
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+        B.H[i][j] += (x[a * 3 + i] - B.c0[i]) * (x[a * 3 + j] + dt * v[b1 * 3 + j] - B.c1[j]);
+    }
+    for (int b = 0; b < n_bodies; b++) if (body_cls[b] == MAT_RIGID) {   // MPM:479-495
+      BodyState& B = bodies[b];
+      svd3(B.H, B.U, B.S, B.V);
+      B.Rm = mul(B.V, tr(B.U));
+    }
+  }
+  void advect(int f) {  // MPM:428-434,497-505
+    const bool rb = any_rigid_body();
+    if (rb) body_forward(f);
 #pragma omp parallel for
     for (int p = 0; p < N; p++) if (used[pi(f, p)]) {
       size_t a = pi(f, p), b = pi(f + 1, p);
-      for (int k = 0; k < 3; k++) x[b * 3 + k] = x[a * 3 + k] + dt * v[b * 3 + k];
+      if (rb && cls[p] == MAT_RIGID) {
+        const BodyState& B = bodies[body_id[p]];
+        for (int k = 0; k < 3; k++) {
+          R acc = B.c1[k];
+          for (int j = 0; j < 3; j++) acc += B.Rm[k][j] * (x[a * 3 + j] - B.c0[j]);
+          x[b * 3 + k] = acc;
+        }
+      } else {
+        for (int k = 0; k < 3; k++) x[b * 3 + k] = x[a * 3 + k] + dt * v[b * 3 + k];
+      }
+    }
+  }
+  // MPM:436-447 advect_grad for the MAT_RIGID particles: advect_kernel.grad, compute_R.grad, compute_H_svd_grad (manual, MPM:485-489),
+  // compute_H.grad, compute_COM.grad.  Adds into gx[f] and gv[f+1]; gx[f+1] of rigid particles is consumed here.
+  void body_advect_grad(int f) {
+    body_forward(f);   // the reference recomputes the body state too (MPM:437-441)
+    struct BG { M3<R> gR, gH; R gc0[3], gc1[3]; };
+    std::vector<BG> g(n_bodies);
+    for (auto& q : g) { q.gR = zero3<R>(); q.gH = zero3<R>(); for (int k = 0; k < 3; k++) q.gc0[k] = q.gc1[k] = R(0); }
+    for (int p = 0; p < N; p++) if (rigid_p(f, p)) {   // advect_kernel.grad, rigid branch
+      const BodyState& B = bodies[body_id[p]]; BG& q = g[body_id[p]];
+      size_t a = pi(f, p), b1 = pi(f + 1, p);
+      const R* go = &gx[b1 * 3];
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) q.gR[i][j] += go[i] * (x[a * 3 + j] - B.c0[j]);
+      for (int j = 0; j < 3; j++) {
+        R t = 0; for (int i = 0; i < 3; i++) t += B.Rm[i][j] * go[i];
+        gx[a * 3 + j] += t; q.gc0[j] -= t; q.gc1[j] += go[j];
+      }
+    }
+    for (int b = 0; b < n_bodies; b++) if (body_cls[b] == MAT_RIGID) {   // compute_R.grad + compute_H_svd_grad
+      const BodyState& B = bodies[b];
+      M3<R> gV = mul(g[b].gR, B.U), gU = mul(tr(g[b].gR), B.V);
+      g[b].gH = backward_svd(gU, zero3<R>(), gV, B.U, B.S, B.V);
+    }
+    for (int p = 0; p < N; p++) if (rigid_p(f, p)) {   // compute_H.grad
+      const BodyState& B = bodies[body_id[p]]; BG& q = g[body_id[p]];
+      size_t a = pi(f, p), b1 = pi(f + 1, p);
+      R d0[3], d1[3];
+      for (int k = 0; k < 3; k++) { d0[k] = x[a * 3 + k] - B.c0[k]; d1[k] = x[a * 3 + k] + dt * v[b1 * 3 + k] - B.c1[k]; }
+      for (int i = 0; i < 3; i++) {
+        R t0 = 0, t1 = 0;
+        for (int j = 0; j < 3; j++) { t0 += q.gH[i][j] * d1[j]; t1 += q.gH[j][i] * d0[j]; }
+        gx[a * 3 + i] += t0 + t1; gv[b1 * 3 + i] += dt * t1;
+        q.gc0[i] -= t0; q.gc1[i] -= t1;
+      }
+    }
+    for (int p = 0; p < N; p++) if (rigid_p(f, p)) {   // compute_COM.grad
+      const BG& q = g[body_id[p]]; const R n = (R)body_n[body_id[p]];
+      size_t a = pi(f, p), b1 = pi(f + 1, p);
+      for (int k = 0; k < 3; k++) { gx[a * 3 + k] += q.gc0[k] / n + q.gc1[k] / n; gv[b1 * 3 + k] += dt * q.gc1[k] / n; }
     }
   }
 
@@ -713,11 +800,14 @@ template <class R> struct Sim {
   }
 
   // ---------------------------------------------------------------- adjoints
-  void g2p_advect_grad(int f) {  // advect_kernel.grad (MPM:443) then g2p.grad (MPM:538)
+  void g2p_advect_grad(int f) {  // advect_grad (MPM:436-447) then g2p.grad (MPM:538)
+    const bool rb = any_rigid_body();
+    if (rb) body_advect_grad(f);
 #pragma omp parallel for
     for (int p = 0; p < N; p++) if (used[pi(f, p)]) {
       size_t a = pi(f, p), b = pi(f + 1, p);
-      for (int k = 0; k < 3; k++) { gx[a * 3 + k] += gx[b * 3 + k]; gv[b * 3 + k] += dt * gx[b * 3 + k]; }
+      if (!(rb && cls[p] == MAT_RIGID))
+        for (int k = 0; k < 3; k++) { gx[a * 3 + k] += gx[b * 3 + k]; gv[b * 3 + k] += dt * gx[b * 3 + k]; }
       const R* xp = &x[a * 3];
       int base[3]; R fx[3]; base_fx(xp, base, fx);
       R w[3][3], dw[3][3]; weights(fx, w); dweights(fx, dw);

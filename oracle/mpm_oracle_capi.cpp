@@ -136,6 +136,7 @@ void orc_destroy(void* hp) { Handle* h = (Handle*)hp; delete h->f32; delete h->f
 void orc_set_threads(int n) { omp_set_num_threads(n); }
 int orc_get_max_threads() { return omp_get_max_threads(); }
 
+void orc_set_bodies(void* hp, const int* body_id, int n_bodies) { Handle* h = (Handle*)hp; DISPATCH(h, S.set_bodies(body_id, n_bodies)); }
 void orc_set_particle_info(void* hp, const int* mat, const int* cls, const double* mu, const double* lam, const double* mass) {
   Handle* h = (Handle*)hp; DISPATCH(h, set_info_t(S, mat, cls, mu, lam, mass)); }
 void orc_set_frame(void* hp, int f, const double* x, const double* v, const double* C, const double* F, const int* used) {

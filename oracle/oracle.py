@@ -215,6 +215,12 @@ class OracleSim:
             self.L.orc_set_agent(self.h, 2)
         return ei
 
+    def set_bodies(self, body_id, n_bodies=None):
+        """body ids per particle (MPM:177-201); enables shape matching for bodies whose first particle is MAT_RIGID."""
+        bid = np.ascontiguousarray(body_id, dtype=np.int32)
+        nb = int(bid.max()) + 1 if n_bodies is None else int(n_bodies)
+        self.L.orc_set_bodies(self.h, _p(bid), nb)
+
     # ---- SDF colliders (meshes/static.py, meshes/dynamic.py): voxels (res,res,res), T_mesh_to_voxels (4,4)
     def add_static(self, voxels, T_mesh_to_voxels, friction):
         vox = _d(voxels); T = _d(T_mesh_to_voxels)

@@ -484,3 +484,60 @@ def test_icecream_dynamic_like_scene():
     assert abs(info['loss'] - loss64) < 1e-4 * abs(loss64)
     if np.abs(g64).max() > 1e-6:
         assert rel(grad, g64) < 2e-3, (rel(grad, g64), grad, g64)
+
+
+def _rigid_bodies_scene(rng, n_grid=32):
+    """water pool + two MAT_RIGID cuboids (RIGID, RIGID_HEAVY) + an elastic blob (cf. envs/gatheringeasy_env.py:62-84)"""
+    xw = rng.uniform((0.30, 0.30, 0.30), (0.70, 0.42, 0.70), size=(6000, 3))
+    xa = rng.uniform((0.36, 0.44, 0.36), (0.48, 0.52, 0.46), size=(1500, 3))
+    xe = rng.uniform((0.40, 0.56, 0.52), (0.48, 0.62, 0.60), size=(600, 3))
+    xb = rng.uniform((0.54, 0.43, 0.50), (0.62, 0.57, 0.58), size=(1200, 3))
+    x = np.concatenate([xw, xa, xe, xb])
+    mat = np.concatenate([np.full(len(xw), M.WATER), np.full(len(xa), M.RIGID), np.full(len(xe), M.ELASTIC), np.full(len(xb), M.RIGID_HEAVY)])
+    bid = np.concatenate([np.zeros(len(xw)), np.ones(len(xa)), np.full(len(xe), 2), np.full(len(xb), 3)]).astype(np.int32)
+    P = make_particles(x, mat, n_grid)
+    P['body_id'] = bid; P['bodies'] = {'n': 4}
+    return P, bid
+
+
+def test_rigid_material_bodies_forward_and_adjoint():
+    """MAT_RIGID bodies (shape matching, MPM:449-505) and advect_grad (MPM:436-447, manual SVD adjoint :485-489): 20 substeps
+    forward over two cell-sort epochs (CUDA-graph path), then the adjoint back to frame 0, against the oracle."""
+    _need_gpu()
+    from oracle import oracle as orc
+    rng = np.random.RandomState(21)
+    n_grid, n_sub = 32, 20
+    P, bid = _rigid_bodies_scene(rng, n_grid)
+    o64, s = build_pair(P, n_grid, boundary=CUBE, T=40, precision=64)
+    o32 = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=CUBE, max_substeps_local=40, precision=32)
+    for o in (o64, o32):
+        o.set_bodies(bid, 4)
+    st = random_state(P, rng, amp_F=0.01, amp_C=2.0, amp_v=0.4)
+    s.enable_grad()
+    set_both(o64, s, st)
+    o32.set_frame(0, st['x'], st['v'], st['C'], st['F'], st['used'])
+    for f in range(n_sub):
+        o64.substep(f); o32.substep(f)
+    s.step(None); s.step(None)
+    assert s.cur_substep_local == n_sub
+    r64, r32, got = o64.get_frame(n_sub), o32.get_frame(n_sub), s.get_state()
+    for k, bar in (('x', 1e-5), ('v', 1e-4), ('F', 1e-5)):
+        tol = max(bar, 3 * rel(r32[k], r64[k]))
+        assert rel(got[k], r64[k]) < tol, (k, rel(got[k], r64[k]), tol)
+    for b in (1, 3):   # rigid bodies keep their shape
+        idx = np.where(bid == b)[0][:200]
+        d0 = np.linalg.norm(st['x'][idx][:, None] - st['x'][idx][None], axis=-1)
+        d1 = np.linalg.norm(got['x'][idx][:, None] - got['x'][idx][None], axis=-1)
+        assert np.abs(d1 - d0).max() < 2e-6
+    g = {k: rng.randn(*st[k].shape).astype(np.float32) for k in ('x', 'v', 'C', 'F')}
+    for o in (o64, o32):
+        o.reset_grad(); o.set_grad_frame(n_sub, g['x'], g['v'], g['C'], g['F'])
+        for f in reversed(range(n_sub)):
+            o.substep_grad(f)
+    s.reset_grad(); s.set_grad(g['x'], g['v'], g['C'], g['F'])
+    s.step_grad(None); s.step_grad(None)
+    assert s.cur_substep_local == 0
+    og, og32, gg = o64.get_grad_frame(0), o32.get_grad_frame(0), s.get_grad()
+    for k in ('x', 'v', 'C', 'F'):
+        tol = max(1e-4, 3 * rel(og32[k], og[k]))   # 20 substeps of fp32 round-off: bar = north-star 1e-4 or the fp32 oracle's own distance
+        assert rel(gg[k], og[k]) < tol, (k, rel(gg[k], og[k]), tol)

@@ -276,3 +276,69 @@ def test_sdf_collide_unit_adjoint_fd(friction, softness, dynamic):
         sel = slice(3, 6) if not dynamic else slice(0, 12)   # static colliders only need the velocity adjoint (node positions are constants)
         assert np.abs(fd[sel] - g[sel]).max() <= 1e-4 * max(1.0, np.abs(fd).max()), (fd, g)
     assert hits > 30
+
+
+# ------------------------------------------------------------------------------------------------
+# MAT_RIGID bodies: shape matching (MPM:449-505) and its adjoint (MPM:436-447, 485-489)
+# ------------------------------------------------------------------------------------------------
+def _rigid_mat_scene(precision, rng, n_grid=16):
+    """water pool + two rigid cuboids (different sizes so the singular values of H are separated) + one elastic blob"""
+    xa = rng.uniform((0.40, 0.50, 0.40), (0.50, 0.56, 0.47), size=(60, 3))
+    xb = rng.uniform((0.52, 0.48, 0.50), (0.60, 0.60, 0.56), size=(50, 3))
+    xw = rng.uniform((0.36, 0.36, 0.36), (0.64, 0.46, 0.64), size=(120, 3))
+    xe = rng.uniform((0.40, 0.58, 0.52), (0.48, 0.64, 0.60), size=(30, 3))
+    x = np.concatenate([xw, xa, xe, xb])
+    mat = np.concatenate([np.full(120, M.WATER), np.full(60, M.RIGID), np.full(30, M.ELASTIC), np.full(50, M.RIGID_HEAVY)])
+    bid = np.concatenate([np.zeros(120), np.ones(60), np.full(30, 2), np.full(50, 3)]).astype(np.int32)
+    P = make_particles(x, mat, n_grid)
+    P['body_id'] = bid; P['bodies'] = {'n': 4}
+    sim = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=dict(type='cube', lower=(0.32, 0.32, 0.32), upper=(0.68, 0.68, 0.68)),
+                        precision=precision, max_substeps_local=10)
+    sim.set_bodies(bid, 4)
+    return sim, P, bid
+
+
+def test_rigid_bodies_keep_their_shape():
+    rng = np.random.RandomState(11)
+    sim, P, bid = _rigid_mat_scene(64, rng)
+    st = _random_state(sim, rng, amp_F=0.0, amp_C=0.0, amp_v=0.8)
+    x0 = st['x']
+    for f in range(8):
+        sim.substep(f)
+    x1 = sim.get_frame(8)['x']
+    for b in (1, 3):
+        idx = np.where(bid == b)[0]
+        d0 = np.linalg.norm(x0[idx][:, None] - x0[idx][None], axis=-1)
+        d1 = np.linalg.norm(x1[idx][:, None] - x1[idx][None], axis=-1)
+        assert np.abs(d1 - d0).max() < 1e-12, 'pairwise distances of a MAT_RIGID body must be preserved (x <- R (x - c0) + c1)'
+        assert np.abs(x1[idx] - x0[idx]).max() > 1e-5   # ... while it actually moved
+    idx = np.where(bid == 2)[0]   # the elastic blob is free to deform
+    d0 = np.linalg.norm(x0[idx][:, None] - x0[idx][None], axis=-1); d1 = np.linalg.norm(x1[idx][:, None] - x1[idx][None], axis=-1)
+    assert np.abs(d1 - d0).max() > 1e-7
+
+
+def test_rigid_body_adjoint_matches_finite_differences():
+    rng = np.random.RandomState(12)
+    sim, P, bid = _rigid_mat_scene(64, rng)
+    st = _random_state(sim, rng)
+    n_sub = 3
+    wts = {k: rng.randn(*st[k].shape) for k in ('x', 'v', 'C', 'F')}
+    _run_loss(sim, st, n_sub, wts)
+    sim.reset_grad()
+    sim.set_grad_frame(n_sub, wts['x'], wts['v'], wts['C'], wts['F'])
+    for f in reversed(range(n_sub)):
+        sim.substep_grad(f)
+    g = sim.get_grad_frame(0)
+    eps = 1e-6
+    rigid = np.where((bid == 1) | (bid == 3))[0]
+    for key, width in (('x', 3), ('v', 3), ('C', 9), ('F', 9)):
+        flat = st[key].reshape(-1)
+        picks = [int(p) * width + int(rng.randint(width)) for p in rng.choice(rigid, 4, replace=False)] + list(rng.choice(flat.size, 3, replace=False))
+        for idx in picks:
+            old = flat[idx]
+            flat[idx] = old + eps; lp = _run_loss(sim, st, n_sub, wts)
+            flat[idx] = old - eps; lm = _run_loss(sim, st, n_sub, wts)
+            flat[idx] = old
+            fd = (lp - lm) / (2 * eps)
+            an = g[key].reshape(-1)[idx]
+            assert abs(fd - an) <= 2e-5 * max(1.0, abs(fd), abs(an)), (key, idx, fd, an)
