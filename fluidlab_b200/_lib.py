@@ -74,13 +74,18 @@ class FmpmSdfMesh(C.Structure):
 
 class FmpmColliders(C.Structure):
     _fields_ = [("n_statics", C.c_int), ("statics", FmpmSdfMesh * 4), ("has_rigid", C.c_int), ("collide_type", C.c_int),
-                ("rigid", FmpmSdfMesh), ("pos", vp), ("quat", vp), ("gpos", vp), ("collide_y_min", C.c_float)]
+                ("rigid", FmpmSdfMesh), ("pos", vp), ("quat", vp), ("gpos", vp), ("gquat", vp), ("collide_y_min", C.c_float)]
 
 
 class FmpmSlab(C.Structure):
     _fields_ = [("enabled", C.c_int), ("peer_pm_left", vp), ("peer_pm_right", vp), ("peer_flags_left", vp), ("peer_flags_right", vp),
                 ("left_lo", C.c_int), ("left_hi", C.c_int),
                 ("right_lo", C.c_int), ("right_hi", C.c_int)]
+
+
+class FmpmCollector(C.Structure):
+    _fields_ = [("boundary_type", C.c_int), ("lower", C.c_float * 3), ("upper", C.c_float * 3), ("cyl_center", C.c_float * 2),
+                ("cyl_radius", C.c_float), ("row_mask", C.c_uint)]
 
 
 class FmpmBodies(C.Structure):
@@ -92,6 +97,7 @@ BODY_STATE_STRIDE, BODY_GRAD_STRIDE = 48, 32
 _I, _F, _U = C.c_int, C.c_float, C.c_uint
 _PROTOS = {
     "fmpm_set_bodies": (_I, [vp, C.POINTER(FmpmBodies)]),
+    "fmpm_collect": (_I, [vp, _I, C.POINTER(FmpmCollector), vp]),
     "fmpm_advect_rigid": (_I, [vp, _I, vp]),
     "fmpm_advect_rigid_grad": (_I, [vp, _I, _I, vp, vp]),
     "fmpm_set_colliders": (_I, [vp, C.POINTER(FmpmColliders)]),

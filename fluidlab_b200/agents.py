@@ -1,7 +1,12 @@
-"""Agents: groups of effectors.  Mirrors fluidlab/fluidengine/agents/agent.py (`Agent` :9-152) and
-agents/agent_injector.py (`AgentInjector` :8-39).  `collide` of injector agents is the identity
-(agent_injector.py:34-36), so no collision kernel is involved for them."""
+"""Agents: groups of effectors.  Mirrors fluidlab/fluidengine/agents/agent.py (`Agent` :9-152),
+agents/agent_injector.py (`AgentInjector` :8-39), agents/agent_rigid.py, agents/agent_icecreamdynamic.py and the collector agents
+agents/agent_pouring.py / agents/agent_jetbot.py.  `collide` of injector agents is the identity (agent_injector.py:34-36), so no
+collision kernel is involved for them."""
+import ctypes as C
 import numpy as np
+from . import _lib
+from .boundaries import create_boundary
+from .macros import WATER
 from .effectors import Effector, Injector, BallInjector, Rigid  # noqa: F401 (names are eval'ed from yaml, agent.py:32)
 
 
@@ -40,6 +45,10 @@ class Agent:
         return
 
     def act_grad(self, f, f_global, gin=0):
+        return
+
+    def collect(self, f):
+        """collector agents only: runs BEFORE the substep kernels of frame f (the reference's agent.act precedes p2g, MPM:521)"""
         return
 
     @property
@@ -197,3 +206,52 @@ class AgentIceCreamDynamic(Agent):
 
     def get_grad(self, n):
         return self.rigid.get_action_grad(0, n)
+
+
+class _Collector:
+    """collector_act_kernel (agents/agent_pouring.py:31-41, agents/agent_jetbot.py:30-40): used particles outside
+    `collector_boundary` are parked at NOWHERE and leave the simulation.  `material`: None = every material."""
+
+    def _setup_collector(self, collector_boundary, material=None):
+        self.collector_boundary = create_boundary(**dict(collector_boundary))
+        self._collector_material = material
+        self._collector = None
+
+    def _build_collector(self, sim):
+        b = self.collector_boundary
+        c = _lib.FmpmCollector()
+        c.boundary_type = b.type_id
+        c.lower = (C.c_float * 3)(*[float(v) for v in b.lower]); c.upper = (C.c_float * 3)(*[float(v) for v in b.upper])
+        c.cyl_center = (C.c_float * 2)(*[float(v) for v in b.xz_center]); c.cyl_radius = float(b.xz_radius)
+        c.row_mask = 0xffffffff if self._collector_material is None else sim.material_row_mask(self._collector_material)
+        self._collector = c
+
+    def collect(self, f):
+        sim = self.sim
+        if sim.has_particles:
+            sim._ck(sim._lib.fmpm_collect(sim._h, f, C.byref(self._collector), sim._stream()), 'fmpm_collect')
+
+
+class AgentPouring(_Collector, AgentRigid):
+    """Agent with one Rigid and a collector (agents/agent_pouring.py): the mesh collides at grid AND particle level."""
+
+    def __init__(self, collector_boundary, **kwargs):
+        kwargs.pop('collide_type', None)
+        super().__init__(collide_type='both', **kwargs)
+        self._setup_collector(collector_boundary, material=None)
+
+    def build(self, sim):
+        super().build(sim)
+        self._build_collector(sim)
+
+
+class AgentJetBot(_Collector, AgentInjector):
+    """Agent with one Injector and a collector of WATER particles (agents/agent_jetbot.py)."""
+
+    def __init__(self, collector_boundary, **kwargs):
+        super().__init__(**kwargs)
+        self._setup_collector(collector_boundary, material=WATER)
+
+    def build(self, sim):
+        super().build(sim)
+        self._build_collector(sim)

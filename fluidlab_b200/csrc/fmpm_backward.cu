@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int
       const int g = (i * n + j) * n + k;
       const float4 pm = P.grid_pm[g];
       float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-      float pg0[3] = {0.f, 0.f, 0.f}, pg1[3] = {0.f, 0.f, 0.f};  // effector pose adjoint of this node (grid-level agent collide)
+      float pg0[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pg1[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // effector pose adjoint of this node (grid-level agent collide)
       const bool agent_grid = P.col.has_rigid && P.col.collide_type >= 1;
       if (pm.w > FMPM_EPS) {
         const float inv_m = 1.f / pm.w;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int
         out.x = vb[0] * inv_m; out.y = vb[1] * inv_m; out.z = vb[2] * inv_m;
         out.w = -(pm.x * vb[0] + pm.y * vb[1] + pm.z * vb[2]) * inv_m * inv_m;
       }
-      if (agent_grid && P.col.egpos) reduce_pose_grad(P.col.egpos, f, pg0, pg1);
+      if (agent_grid && P.col.egpos) reduce_pose_grad(P.col.egpos, P.col.egquat, f, pg0, pg1);
       P.ggrid_pm[g] = out;
       if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int
 // =============================================================================================
 __global__ void __launch_bounds__(128) k_collide_particle_grad(const KParams P, const int f, const int gin) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
+  float g0[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g1[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (s < P.N) {
     const float4 a0 = P.pa[pa_idx(P, f, 0, s)];
     const float x[3] = {a0.x, a0.y, a0.z};
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) k_collide_particle_grad(const KParams P, 
       P.ga[pa_idx(P, gin, 0, s)] = gx4; P.ga[pa_idx(P, gin, 1, s)] = gv4;
     }
   }
-  if (P.col.egpos) reduce_pose_grad(P.col.egpos, f, g0, g1);
+  if (P.col.egpos) reduce_pose_grad(P.col.egpos, P.col.egquat, f, g0, g1);
 }
 
 // =============================================================================================
@@ -372,15 +372,26 @@ __global__ void __launch_bounds__(PG_WARPS * 32, PG_MINB) k_particle_grad(const 
   store_F(P.gf, P.gf8, P, gout, s, oF);
 }
 
-// injector act adjoint (act_kernel.grad, agents/agent_injector.py:27-28): gpos[f] += gx[f+1, pid]
+// injector act adjoint (act_kernel.grad, agents/agent_injector.py:27-28): gpos[f] += gx[f+1, pid]; an Injector (not a BallInjector)
+// also rotates inject_p / inject_v by quat[f] (injector.py:93-96), whose adjoint goes to gquat[f] (6-DOF injectors, agent_transporting.yaml)
 __global__ void k_inject_grad(const KParams P, const int f, const int gin, const FmpmInjector inj, float* __restrict__ gpos,
-                              const int act_id, const int* __restrict__ inv) {
+                              const float* __restrict__ equat, float* __restrict__ gquat, const int act_id, const int* __restrict__ inv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= inj.flux) return;
   const int pid = ((const int*)inj.act_range)[act_id + i];
   const int s = inv ? inv[pid] : pid;
   const float4 g0 = P.ga[pa_idx(P, gin, 0, s)];
   atomicAdd(gpos + f * 3 + 0, g0.x); atomicAdd(gpos + f * 3 + 1, g0.y); atomicAdd(gpos + f * 3 + 2, g0.z);
+  if (inj.kind == 1 && gquat) {
+    const float4 g1 = P.ga[pa_idx(P, gin, 1, s)];
+    const float q[4] = {equat[f * 4], equat[f * 4 + 1], equat[f * 4 + 2], equat[f * 4 + 3]};
+    const float gx[3] = {g0.x, g0.y, g0.z}, gv[3] = {g1.x, g1.y, g1.z};
+    float gq[4] = {0.f, 0.f, 0.f, 0.f};
+    q_rot_adj_q(q, inj.inject_p, gx, gq);
+    q_rot_adj_q(q, inj.inject_v, gv, gq);
+#pragma unroll
+    for (int k = 0; k < 4; k++) atomicAdd(gquat + f * 4 + k, gq[k]);
+  }
 }
 
 // =============================================================================================
@@ -480,7 +491,7 @@ extern "C" int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjecto
                                 const void* inv, void* stream) {
   if (check_bound_b(h, "fmpm_inject_grad")) return 1;
   KParams P = make_kparams(h);
-  k_inject_grad<<<(inj->flux + 31) / 32, 32, 0, (cudaStream_t)stream>>>(P, f, gin, *inj, (float*)e->gpos, act_id, (const int*)inv);
+  k_inject_grad<<<(inj->flux + 31) / 32, 32, 0, (cudaStream_t)stream>>>(P, f, gin, *inj, (float*)e->gpos, (const float*)e->quat, (float*)e->gquat, act_id, (const int*)inv);
   FMPM_CHECK_LAUNCH(h, "fmpm_inject_grad");
   return 0;
 }

@@ -7,12 +7,13 @@
 #include "../../include/fluidmpm.h"
 
 #define FMPM_EPS 1e-12f  // configs/macros.py:213
+#define FMPM_NOWHERE (-100.0f)  // configs/macros.py:216
 
 struct SdfDev { const float* vox; int res; float T[12]; float Ainv[9]; float friction, softness; };
 struct CollidersDev {
   int n_statics; SdfDev statics[4];
   int has_rigid; int collide_type; SdfDev rigid;
-  const float* epos; const float* equat; float* egpos;
+  const float* epos; const float* equat; float* egpos; float* egquat;
   float y_min;
 };
 

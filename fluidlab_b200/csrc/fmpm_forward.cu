@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const i
   const bool staged = fp.staged; const int kmin = fp.kmin;
   if (s >= P.N) return;
   if (!ok) {  // unused (MPM:309-316) or frozen: carry the state over unchanged
+    if (meta & 2) {  // collected at this substep (fmpm_collect): parked, agents/agent_pouring.py:37-38
+      a0.x = a0.y = a0.z = FMPM_NOWHERE; a0.w = __int_as_float(meta & ~3);
+    }
     P.pa[pa_idx(P, f + 1, 0, s)] = a0;
     P.pa[pa_idx(P, f + 1, 1, s)] = P.pa[pa_idx(P, f, 1, s)];
     P.pa[pa_idx(P, f + 1, 2, s)] = P.pa[pa_idx(P, f, 2, s)];
@@ -340,6 +343,34 @@ extern "C" int fmpm_substep(FmpmHandle* h, int f, void* stream) {
   if (fmpm_grid_op(h, f, 1, stream)) return 1;
   if (fmpm_g2p(h, f, stream)) return 1;
   return fmpm_advect_rigid_impl(h, f, stream);
+}
+
+// collector_act_kernel (agents/agent_pouring.py:31-41, agents/agent_jetbot.py:30-40)
+__global__ void k_collect(const KParams P, const int f, const FmpmCollector c) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.N) return;
+  const float4 a0 = P.pa[pa_idx(P, f, 0, s)];
+  const int meta = __float_as_int(a0.w);
+  const int row = (meta >> 8) & 0xff;
+  if (!(meta & 1) || row >= 32 || !((c.row_mask >> row) & 1u)) return;
+  bool out = false;
+  if (c.boundary_type == 0) {   // boundaries.py:128-134
+    out = a0.x > c.upper[0] || a0.y > c.upper[1] || a0.z > c.upper[2] || a0.x < c.lower[0] || a0.y < c.lower[1] || a0.z < c.lower[2];
+  } else {                      // boundaries.py:81-93
+    out = a0.y > c.upper[1] || a0.y < c.lower[1];
+    const float rx = a0.x - c.cyl_center[0], rz = a0.z - c.cyl_center[1];
+    out = out || sqrtf(rx * rx + rz * rz + FMPM_EPS) > c.cyl_radius;
+  }
+  if (out) P.pa[pa_idx(P, f, 0, s)].w = __int_as_float((meta & ~1) | 2);
+}
+extern "C" int fmpm_collect(FmpmHandle* h, int f, const FmpmCollector* c, void* stream) {
+  if (check_bound(h, "fmpm_collect") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_collect")) return 1;
+  if (!c) { snprintf(h->err, sizeof(h->err), "fmpm_collect: null collector"); return 1; }
+  KParams P = make_kparams(h);
+  if (P.N == 0) return 0;
+  k_collect<<<(P.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, f, *c);
+  FMPM_CHECK_LAUNCH(h, "fmpm_collect");
+  return 0;
 }
 
 extern "C" int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,

@@ -59,7 +59,7 @@ extern "C" int fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c) {
     fill_sdf(h->col.statics[s], c->statics[s]);
   }
   h->col.has_rigid = c->has_rigid; h->col.collide_type = c->collide_type; h->col.y_min = c->collide_y_min;
-  if (c->has_rigid) { fill_sdf(h->col.rigid, c->rigid); h->col.epos = (const float*)c->pos; h->col.equat = (const float*)c->quat; h->col.egpos = (float*)c->gpos; }
+  if (c->has_rigid) { fill_sdf(h->col.rigid, c->rigid); h->col.epos = (const float*)c->pos; h->col.equat = (const float*)c->quat; h->col.egpos = (float*)c->gpos; h->col.egquat = (float*)c->gquat; }
   return 0;
 }
 
@@ -386,10 +386,10 @@ __global__ void k_effector_step(const FmpmEffector e, const int s, const int s_g
 }
 __global__ void k_effector_step_grad(const FmpmEffector e, const int s, const int s_global, const int ns) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const float* pos = (const float*)e.pos; const float* v = (const float*)e.v;
-  float* gpos = (float*)e.gpos; float* gv = (float*)e.gv; float* gw = (float*)e.gw; float* gact = (float*)e.gact;
+  const float* pos = (const float*)e.pos; const float* v = (const float*)e.v; const float* quat = (const float*)e.quat; const float* w = (const float*)e.w;
+  float* gpos = (float*)e.gpos; float* gv = (float*)e.gv; float* gw = (float*)e.gw; float* gquat = (float*)e.gquat; float* gact = (float*)e.gact;
   const int ad = e.action_dim;
-  for (int f = (s + 1) * ns - 1; f >= s * ns; f--) {                                     // move_kernel.grad (position part)
+  for (int f = (s + 1) * ns - 1; f >= s * ns; f--) {                                     // move_kernel.grad, effector.py:155
     float in[3], out[3], jac[9];
     for (int k = 0; k < 3; k++) in[k] = pos[f * 3 + k] + v[f * 3 + k];
     effector_impose_x(e, in, out, jac);
@@ -397,6 +397,28 @@ __global__ void k_effector_step_grad(const FmpmEffector e, const int s, const in
       float g = 0.f;
       for (int b = 0; b < 3; b++) g += jac[b * 3 + a] * gpos[(f + 1) * 3 + b];
       gpos[f * 3 + a] += g; gv[f * 3 + a] += g;
+    }
+    if (gquat) {
+      // quat[f+1] = normalize(qmul_raw(w2quat(w[f]), quat[f]))  (utils/geom.py:7-28): adjoints of quat[f] and w[f]
+      const float* wv = w + f * 3; const float* r = quat + f * 4; const float* g1 = gquat + (f + 1) * 4;
+      const float wn = sqrtf(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2] + FMPM_EPS);
+      const float sh = sinf(wn * 0.5f), ch = cosf(wn * 0.5f);
+      const float q[4] = {ch, wv[0] / wn * sh, wv[1] / wn * sh, wv[2] / wn * sh};
+      const float o[4] = {r[0] * q[0] - r[1] * q[1] - r[2] * q[2] - r[3] * q[3], r[0] * q[1] + r[1] * q[0] - r[2] * q[3] + r[3] * q[2],
+                          r[0] * q[2] + r[1] * q[3] + r[2] * q[0] - r[3] * q[1], r[0] * q[3] - r[1] * q[2] + r[2] * q[1] + r[3] * q[0]};
+      const float on = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+      float dd = 0.f;
+      for (int k = 0; k < 4; k++) dd += o[k] / on * g1[k];
+      float go[4];
+      for (int k = 0; k < 4; k++) go[k] = (g1[k] - o[k] / on * dd) / on;
+      const float gr[4] = {go[0] * q[0] + go[1] * q[1] + go[2] * q[2] + go[3] * q[3], -go[0] * q[1] + go[1] * q[0] + go[2] * q[3] - go[3] * q[2],
+                           -go[0] * q[2] - go[1] * q[3] + go[2] * q[0] + go[3] * q[1], -go[0] * q[3] + go[1] * q[2] - go[2] * q[1] + go[3] * q[0]};
+      const float gq[4] = {go[0] * r[0] + go[1] * r[1] + go[2] * r[2] + go[3] * r[3], -go[0] * r[1] + go[1] * r[0] - go[2] * r[3] + go[3] * r[2],
+                           -go[0] * r[2] + go[1] * r[3] + go[2] * r[0] - go[3] * r[1], -go[0] * r[3] - go[1] * r[2] + go[2] * r[1] + go[3] * r[0]};
+      for (int k = 0; k < 4; k++) gquat[f * 4 + k] += gr[k];
+      float gwn = -sh * 0.5f * gq[0];
+      for (int k = 0; k < 3; k++) gwn += gq[k + 1] * wv[k] * (ch * 0.5f * wn - sh) / (wn * wn);
+      for (int k = 0; k < 3; k++) gw[f * 3 + k] += gq[k + 1] * sh / wn + gwn * wv[k] / wn;
     }
   }
   if (ad > 0) {                                                                          // set_velocity.grad, effector.py:270-274

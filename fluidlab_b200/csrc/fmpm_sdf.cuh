@@ -15,6 +15,22 @@ __device__ __forceinline__ void q_inv(const float* q, float* qi) {  // utils/geo
   const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   qi[0] = q[0] / n; qi[1] = -q[1] / n; qi[2] = -q[2] / n; qi[3] = -q[3] / n;
 }
+// adjoint of o = q_rot(q, v) with respect to q (the polynomial of utils/geom.py:92-97 differentiated as written): gq += ...
+__device__ __forceinline__ void q_rot_adj_q(const float* q, const float* v, const float* go, float* gq) {
+  const float uv0 = q[2] * v[2] - q[3] * v[1], uv1 = q[3] * v[0] - q[1] * v[2], uv2 = q[1] * v[1] - q[2] * v[0];
+  const float gu0 = 2.f * (q[0] * go[0] + go[1] * q[3] - go[2] * q[2]), gu1 = 2.f * (q[0] * go[1] + go[2] * q[1] - go[0] * q[3]),
+              gu2 = 2.f * (q[0] * go[2] + go[0] * q[2] - go[1] * q[1]);   // adjoint of uv = 2 q0 go + 2 go x qv
+  gq[0] += 2.f * (go[0] * uv0 + go[1] * uv1 + go[2] * uv2);
+  gq[1] += 2.f * (uv1 * go[2] - uv2 * go[1]) + (v[1] * gu2 - v[2] * gu1);
+  gq[2] += 2.f * (uv2 * go[0] - uv0 * go[2]) + (v[2] * gu0 - v[0] * gu2);
+  gq[3] += 2.f * (uv0 * go[1] - uv1 * go[0]) + (v[0] * gu1 - v[1] * gu0);
+}
+// adjoint of qi = q_inv(q): gq += ...
+__device__ __forceinline__ void q_inv_adj(const float* q, const float* qi, const float* gqi, float* gq) {
+  const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const float d = qi[0] * gqi[0] + qi[1] * gqi[1] + qi[2] * gqi[2] + qi[3] * gqi[3];
+  gq[0] += (gqi[0] - qi[0] * d) / n; gq[1] -= (gqi[1] - qi[1] * d) / n; gq[2] -= (gqi[2] - qi[2] * d) / n; gq[3] -= (gqi[3] - qi[3] * d) / n;
+}
 
 // trilinear lookup, 1.0 outside (static.py:35-48); grad = d sdf / d pos_voxels when kGrad
 template <bool kGrad>
@@ -42,17 +58,19 @@ __device__ __forceinline__ float sdf_lookup(const SdfDev& M, const float* pv, fl
   return sd;
 }
 
-// One collide evaluation.  Static: dynamic = false (pos/quat ignored).  kGrad: adjoints of (v, p, pos0, pos1) are ACCUMULATED
-// (quaternion adjoints are not built: every shipped Rigid effector has action_dim 3, its quaternion is constant).
+// One collide evaluation.  Static: dynamic = false (pos/quat ignored).  kGrad: adjoints of (v, p) are ACCUMULATED into gv, gp and,
+// for dynamic colliders, those of the poses of frames f / f+1 into gpose0[7] / gpose1[7] = (pos[3], quat[4]) (6-DOF Rigid
+// effectors, agent_pouring.yaml; the quaternion part stays zero-gradient downstream when action_dim = 3).
 template <bool kGrad>
 __device__ __forceinline__ void sdf_collide(const SdfDev& M, const bool dynamic, const float* pos0, const float* q0, const float* pos1, const float* q1,
                                             const float dt, const float* p, const float* v, float* out, const float* gout, float* gv, float* gp,
-                                            float* gpos0, float* gpos1) {
+                                            float* gpose0, float* gpose1) {
   out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
-  float qi[4] = {1.f, 0.f, 0.f, 0.f}, pm[3] = {p[0], p[1], p[2]};
+  float qi[4] = {1.f, 0.f, 0.f, 0.f}, pm[3] = {p[0], p[1], p[2]}, d0[3] = {0.f, 0.f, 0.f};
   if (dynamic) {
     q_inv(q0, qi);
-    const float d0[3] = {p[0] - pos0[0], p[1] - pos0[1], p[2] - pos0[2]};
+#pragma unroll
+    for (int k = 0; k < 3; k++) d0[k] = p[k] - pos0[k];
     q_rot(qi, d0, pm);
   }
   float pv[3];
@@ -72,7 +90,7 @@ __device__ __forceinline__ void sdf_collide(const SdfDev& M, const bool dynamic,
   }
   const bool sticky = dynamic && (M.friction > 10.f);
   float rel[3] = {0.f, 0.f, 0.f}, nvx[3] = {0.f, 0.f, 0.f}, gnorm = 1.f, un = 1.f, n[3] = {0.f, 0.f, 0.f}, vn = 0.f, m = 0.f, rt[3] = {0.f, 0.f, 0.f},
-        rtn = 0.f, g = 0.f, rt2[3] = {0.f, 0.f, 0.f};
+        rtn = 0.f, g = 0.f, rt2[3] = {0.f, 0.f, 0.f}, nm[3] = {0.f, 0.f, 0.f};
   bool flag = false;
   if (sticky) { out[0] = cv[0]; out[1] = cv[1]; out[2] = cv[2]; }
   else {
@@ -90,7 +108,7 @@ __device__ __forceinline__ void sdf_collide(const SdfDev& M, const bool dynamic,
     gnorm = sqrtf(graw[0] * graw[0] + graw[1] * graw[1] + graw[2] * graw[2] + FMPM_EPS);
 #pragma unroll
     for (int i = 0; i < 3; i++) nvx[i] = graw[i] / gnorm;
-    float nm[3], u[3];
+    float u[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) nm[r] = M.Ainv[r * 3] * nvx[0] + M.Ainv[r * 3 + 1] * nvx[1] + M.Ainv[r * 3 + 2] * nvx[2];
     if (dynamic) q_rot(q0, nm, u); else { u[0] = nm[0]; u[1] = nm[1]; u[2] = nm[2]; }
@@ -141,6 +159,7 @@ __device__ __forceinline__ void sdf_collide(const SdfDev& M, const bool dynamic,
 #pragma unroll
       for (int k = 0; k < 3; k++) gu[k] = (gn[k] - n[k] * nd) / un;
       q_rot(qi, gu, gnm);
+      q_rot_adj_q(q0, nm, gu, gpose0 + 3);                                     // u = R(q0) nm
 #pragma unroll
       for (int c = 0; c < 3; c++) gnvx[c] = M.Ainv[c] * gnm[0] + M.Ainv[3 + c] * gnm[1] + M.Ainv[6 + c] * gnm[2];
       const float nd2 = nvx[0] * gnvx[0] + nvx[1] * gnvx[1] + nvx[2] * gnvx[2];
@@ -164,13 +183,17 @@ __device__ __forceinline__ void sdf_collide(const SdfDev& M, const bool dynamic,
     float q1i[4]; q_inv(q1, q1i);
     const float t1[3] = {gcv[0] / dt, gcv[1] / dt, gcv[2] / dt};
     float gpm[3]; q_rot(q1i, t1, gpm);
+    q_rot_adj_q(q1, pm, t1, gpose1 + 3);                                       // pw1 = R(q1) pm
 #pragma unroll
-    for (int k = 0; k < 3; k++) { gpos1[k] += t1[k]; gp[k] -= t1[k]; }
+    for (int k = 0; k < 3; k++) { gpose1[k] += t1[k]; gp[k] -= t1[k]; }
 #pragma unroll
     for (int c = 0; c < 3; c++) gpm[c] += M.T[c] * gpv[0] + M.T[4 + c] * gpv[1] + M.T[8 + c] * gpv[2];
     float gd0[3]; q_rot(q0, gpm, gd0);
 #pragma unroll
-    for (int k = 0; k < 3; k++) { gp[k] += gd0[k]; gpos0[k] -= gd0[k]; }
+    for (int k = 0; k < 3; k++) { gp[k] += gd0[k]; gpose0[k] -= gd0[k]; }
+    float gqi[4] = {0.f, 0.f, 0.f, 0.f};
+    q_rot_adj_q(qi, d0, gpm, gqi);                                             // pm = R(inv(q0)) (p - pos0)
+    q_inv_adj(q0, qi, gqi, gpose0 + 3);
   }
 }
 
@@ -190,14 +213,18 @@ __device__ __forceinline__ void agent_collide(const KParams& P, const int f, con
   sdf_collide<kGrad>(P.col.rigid, true, a0, b0, a1, b1, P.dt, p, v, out, gout, gv, gp, g0, g1);
 }
 
-// warp-reduced accumulation of an effector pose adjoint (6 floats) — one atomic per warp and component
-__device__ __forceinline__ void reduce_pose_grad(float* gpos, const int f, const float* g0, const float* g1) {
-  float vals[6] = {g0[0], g0[1], g0[2], g1[0], g1[1], g1[2]};
+// warp-reduced accumulation of the effector pose adjoints of frames f / f+1 (g0[7], g1[7] = pos[3] + quat[4]) — one atomic per
+// warp and component; gquat may be null (pose quaternion adjoint not requested)
+__device__ __forceinline__ void reduce_pose_grad(float* gpos, float* gquat, const int f, const float* g0, const float* g1) {
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
-    float x = vals[i];
+  for (int i = 0; i < 14; i++) {
+    float x = i < 7 ? g0[i] : g1[i - 7];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if ((threadIdx.x & 31) == 0 && x != 0.f) atomicAdd(gpos + (i < 3 ? f * 3 + i : (f + 1) * 3 + (i - 3)), x);
+    if ((threadIdx.x & 31) == 0 && x != 0.f) {
+      const int ff = i < 7 ? f : f + 1, c = i < 7 ? i : i - 7;
+      if (c < 3) atomicAdd(gpos + ff * 3 + c, x);
+      else if (gquat) atomicAdd(gquat + ff * 4 + (c - 3), x);
+    }
   }
 }

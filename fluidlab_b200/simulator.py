@@ -253,7 +253,7 @@ class MPMSimulator:
             col.has_rigid = 1
             col.collide_type = {'particle': 0, 'grid': 1, 'both': 2}[self.agent.collide_type]
             col.rigid = rigid.mesh.device_struct(_lib, self.device)
-            col.pos, col.quat, col.gpos = rigid.pos.data_ptr(), rigid.quat.data_ptr(), rigid.gpos.data_ptr()
+            col.pos, col.quat, col.gpos, col.gquat = rigid.pos.data_ptr(), rigid.quat.data_ptr(), rigid.gpos.data_ptr(), rigid.gquat.data_ptr()
         self._colliders = col  # keep the voxel tensors alive through the mesh objects
         self._ck(self._lib.fmpm_set_colliders(self._h, C.byref(col)), 'fmpm_set_colliders')
 
@@ -385,6 +385,8 @@ class MPMSimulator:
         self._frame_ord[f] = new
 
     def substep(self, f, is_none_action):  # MPM:515-533
+        if not is_none_action:
+            self.agent.collect(f)   # collector agents: particles leave at frame f, before p2g (agents/agent_pouring.py:31-41)
         if self.has_particles:
             if self._storing():
                 self._ck(self._lib.fmpm_substep_store(self._h, f, self._stream()), 'fmpm_substep_store')

@@ -126,6 +126,7 @@ typedef struct {
   FmpmSdfMesh rigid;
   const void* pos; const void* quat;        /* the Rigid effector's pose arrays float[(T+1)*3], float[(T+1)*4] */
   void* gpos;                               /* adjoint of pos (may be NULL when grads are never used) */
+  void* gquat;                              /* adjoint of quat, float[(T+1)*4] (NULL: not accumulated; needed for 6-DOF actions) */
   float collide_y_min;                      /* the rigid collider only acts where y > this (agents/agent_icecreamdynamic.py:38-43); -1e30 = everywhere */
 } FmpmColliders;
 int  fmpm_set_colliders(FmpmHandle* h, const FmpmColliders* c);
@@ -177,6 +178,18 @@ int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, 
 /* agent.act for injector agents, agents/agent_injector.py:23-32; run after fmpm_g2p of the same f */
 int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,
                 const void* inv, void* stream);
+
+/* collector_act_kernel of AgentPouring / AgentJetBot (agents/agent_pouring.py:31-41, agents/agent_jetbot.py:30-40): used particles of
+ * frame f that lie outside the collector boundary (boundaries.py:81-93,128-134 is_out) leave the simulation: used[f] = used[f+1] = 0,
+ * x[f+1] = NOWHERE (configs/macros.py:216).  Run BEFORE fmpm_substep(f) (the reference runs agent.act before p2g, MPM:521).  It only
+ * clears the `used` bit of frame f and tags the particle (meta bit 1); fmpm_g2p(f) then writes the parked position into frame f+1. */
+typedef struct FmpmCollector {
+  int boundary_type;                 /* 0 cube, 1 cylinder */
+  float lower[3], upper[3];          /* cylinder: [1] = y range */
+  float cyl_center[2], cyl_radius;
+  unsigned int row_mask;             /* material-table rows that are collected (AgentPouring: all rows; AgentJetBot: the WATER rows) */
+} FmpmCollector;
+int fmpm_collect(FmpmHandle* h, int f, const FmpmCollector* c, void* stream);
 
 /* ---- backward substep, MPM:535-552 ------------------------------------------------------------ */
 /* gin/gout in {0,1}: grad ping-pong index holding frame f+1 (in) and receiving frame f (out). */

@@ -239,12 +239,40 @@ template <class R> static inline void quat_inv_t(const R* q, R* qi) {  // utils/
   qi[0] = q[0] / n; qi[1] = -q[1] / n; qi[2] = -q[2] / n; qi[3] = -q[3] / n;
 }
 
+// adjoint of o = quat_rot_t(q, v) (the polynomial v + 2 (q0 (qv x v) + qv x (qv x v)), differentiated as written): accumulates into gq[4], gv[3]
+template <class R> static inline void quat_rot_adj(const R* q, const R* v, const R* go, R* gq, R* gv) {
+  const R uv[3] = {q[2] * v[2] - q[3] * v[1], q[3] * v[0] - q[1] * v[2], q[1] * v[1] - q[2] * v[0]};
+  // g_uv = 2 q0 go + 2 (go x qv)
+  const R guv[3] = {R(2) * (q[0] * go[0] + go[1] * q[3] - go[2] * q[2]), R(2) * (q[0] * go[1] + go[2] * q[1] - go[0] * q[3]),
+                    R(2) * (q[0] * go[2] + go[0] * q[2] - go[1] * q[1])};
+  if (gq) {
+    gq[0] += R(2) * (go[0] * uv[0] + go[1] * uv[1] + go[2] * uv[2]);
+    // g_qv = 2 (uv x go) + v x g_uv
+    gq[1] += R(2) * (uv[1] * go[2] - uv[2] * go[1]) + (v[1] * guv[2] - v[2] * guv[1]);
+    gq[2] += R(2) * (uv[2] * go[0] - uv[0] * go[2]) + (v[2] * guv[0] - v[0] * guv[2]);
+    gq[3] += R(2) * (uv[0] * go[1] - uv[1] * go[0]) + (v[0] * guv[1] - v[1] * guv[0]);
+  }
+  if (gv) {  // gv = go + g_uv x qv   (uv = qv x v)
+    gv[0] += go[0] + (guv[1] * q[3] - guv[2] * q[2]);
+    gv[1] += go[1] + (guv[2] * q[1] - guv[0] * q[3]);
+    gv[2] += go[2] + (guv[0] * q[2] - guv[1] * q[1]);
+  }
+}
+// adjoint of qi = quat_inv_t(q): accumulates into gq
+template <class R> static inline void quat_inv_adj(const R* q, const R* qi, const R* gqi, R* gq) {
+  const R n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const R d = qi[0] * gqi[0] + qi[1] * gqi[1] + qi[2] * gqi[2] + qi[3] * gqi[3];
+  const R sgn[4] = {R(1), R(-1), R(-1), R(-1)};
+  for (int k = 0; k < 4; k++) gq[k] += sgn[k] * (gqi[k] - qi[k] * d) / n;
+}
+
 // One collide evaluation (static: pos0 = pos1 = 0, quats identity, dynamic = false).  Forward value in `out`; when
-// gout != nullptr the adjoints of (v, p, pos0, pos1) are ACCUMULATED into gv, gp, gpos0, gpos1 (quaternion adjoints are not
-// restated: every shipped Rigid effector has action_dim = 3, so quat is constant).
+// gout != nullptr the adjoints of (v, p, pos0, pos1) are ACCUMULATED into gv, gp, gpos0, gpos1, and those of the pose quaternions
+// into gq0 / gq1 when these are given (6-DOF Rigid effectors: agent_pouring.yaml; quat is constant for action_dim = 3).
 // Follows meshes/dynamic.py:93-121 (Dynamic.collide) / meshes/static.py:82-104 (Static.collide).
 template <class R> static void sdf_collide(const SdfMesh<R>& M, bool dynamic, const R* pos0, const R* q0, const R* pos1, const R* q1, R dt,
-                                           const R* p, const R* v, R* out, const R* gout, R* gv, R* gp, R* gpos0, R* gpos1) {
+                                           const R* p, const R* v, R* out, const R* gout, R* gv, R* gp, R* gpos0, R* gpos1,
+                                           R* gq0 = nullptr, R* gq1 = nullptr) {
   for (int k = 0; k < 3; k++) out[k] = v[k];
   if (!M.has_dynamics) { if (gout) for (int k = 0; k < 3; k++) gv[k] += gout[k]; return; }
   R qi[4], d0[3], pm[3], pv[3];
@@ -263,13 +291,12 @@ template <class R> static void sdf_collide(const SdfMesh<R>& M, bool dynamic, co
     for (int k = 0; k < 3; k++) cv[k] = (pw1[k] + pos1[k] - p[k]) / dt;   // collider_v, dynamic.py:86-91
   }
   const bool sticky = dynamic && (M.friction > R(10));
-  R rel[3], nvx[3], graw[3], gnorm = 1, u[3], un = 1, n[3] = {0, 0, 0}, vn = 0, m = 0, rt[3], rtn = 0, g = 0, rt2[3];
+  R rel[3], nvx[3], graw[3], gnorm = 1, u[3], un = 1, n[3] = {0, 0, 0}, vn = 0, m = 0, rt[3], rtn = 0, g = 0, rt2[3], nm[3] = {0, 0, 0};
   bool flag = false;
   if (sticky) { for (int k = 0; k < 3; k++) out[k] = cv[k]; }
   else {
     for (int k = 0; k < 3; k++) rel[k] = v[k] - cv[k];
     M.normal_vox(pv, nvx, graw, gnorm);
-    R nm[3];
     for (int r = 0; r < 3; r++) nm[r] = M.Ainv[r * 3] * nvx[0] + M.Ainv[r * 3 + 1] * nvx[1] + M.Ainv[r * 3 + 2] * nvx[2];
     quat_rot_t(q0, nm, u);
     un = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + R(1e-12));
@@ -310,6 +337,7 @@ template <class R> static void sdf_collide(const SdfMesh<R>& M, bool dynamic, co
       R nd = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
       R gu[3]; for (int k = 0; k < 3; k++) gu[k] = (gn[k] - n[k] * nd) / un;
       R gnm[3]; quat_rot_t(qi, gu, gnm);
+      if (gq0) quat_rot_adj(q0, nm, gu, gq0, (R*)nullptr);
       R gnvx[3]; for (int c = 0; c < 3; c++) gnvx[c] = M.Ainv[c] * gnm[0] + M.Ainv[3 + c] * gnm[1] + M.Ainv[6 + c] * gnm[2];
       R nd2 = nvx[0] * gnvx[0] + nvx[1] * gnvx[1] + nvx[2] * gnvx[2];
       R ggraw[3]; for (int k = 0; k < 3; k++) ggraw[k] = (gnvx[k] - nvx[k] * nd2) / gnorm;
@@ -329,9 +357,11 @@ template <class R> static void sdf_collide(const SdfMesh<R>& M, bool dynamic, co
     R q1i[4]; quat_inv_t(q1, q1i);
     R t1[3] = {gcv[0] / dt, gcv[1] / dt, gcv[2] / dt}, gpm[3];
     quat_rot_t(q1i, t1, gpm);
+    if (gq1) quat_rot_adj(q1, pm, t1, gq1, (R*)nullptr);                                               // pw1 = R1 pm
     for (int k = 0; k < 3; k++) { gpos1[k] += t1[k]; gp[k] -= t1[k]; }
     for (int c = 0; c < 3; c++) gpm[c] += M.T[c] * gpv[0] + M.T[4 + c] * gpv[1] + M.T[8 + c] * gpv[2];   // pv = A pm + t
     R gd0[3]; quat_rot_t(q0, gpm, gd0);                                                                // pm = R0^T (p - pos0)
+    if (gq0) { R gqi[4] = {0, 0, 0, 0}; quat_rot_adj(qi, d0, gpm, gqi, (R*)nullptr); quat_inv_adj(q0, qi, gqi, gq0); }
     for (int k = 0; k < 3; k++) { gp[k] += gd0[k]; gpos0[k] -= gd0[k]; }
   }
 }
@@ -361,6 +391,31 @@ template <class R> struct Sim {
   bool has_rigid = false;
   bool has_injector = false;
   R collide_y_min = R(-1e30);        // AgentIceCreamDynamic.collide only acts above y = 0.25 (agents/agent_icecreamdynamic.py:38-43)
+  // collector of AgentPouring / AgentJetBot (agents/agent_pouring.py:31-41, agents/agent_jetbot.py:30-40); type -1 = none
+  int collector_type = -1;           // 0 cube, 1 cylinder (boundaries/boundaries.py:81-93,128-134 is_out)
+  R col_lo[3] = {0, 0, 0}, col_hi[3] = {1, 1, 1}, col_c[2] = {R(0.5), R(0.5)}, col_r = R(1);
+  int collector_mat = -1;            // -1: every material (AgentPouring); otherwise only that material (AgentJetBot: WATER)
+  R nowhere[3] = {R(-100), R(-100), R(-100)};   // configs/macros.py:216
+  inline bool collector_is_out(const R* xp) const {
+    bool out = false;
+    if (collector_type == 0) { for (int k = 0; k < 3; k++) if (xp[k] > col_hi[k] || xp[k] < col_lo[k]) out = true; }
+    else {
+      if (xp[1] > col_hi[1] || xp[1] < col_lo[1]) out = true;
+      R rx = xp[0] - col_c[0], rz = xp[2] - col_c[1];
+      if (std::sqrt(rx * rx + rz * rz + R(1e-12)) > col_r) out = true;
+    }
+    return out;
+  }
+  void collector_act(int f) {   // collect out-of-boundary particles: they leave the simulation at frame f already
+    if (collector_type < 0) return;
+    for (int p = 0; p < N; p++) if (used[pi(f, p)] && (collector_mat < 0 || mat[p] == collector_mat)) {
+      if (collector_is_out(&x[pi(f, p) * 3])) {
+        used[pi(f + 1, p)] = 0;
+        for (int k = 0; k < 3; k++) x[pi(f + 1, p) * 3 + k] = nowhere[k];
+        used[pi(f, p)] = 0;
+      }
+    }
+  }
   // bodies (MPM:177-201): rigidity enforcement by shape matching for MAT_RIGID bodies
   int n_bodies = 0;
   std::vector<int> body_id, body_n, body_cls;
@@ -378,13 +433,21 @@ template <class R> struct Sim {
   inline void agent_collide(int f, const R* p, const R* vin, R* out, const R* gout, R* gvv, R* gpp) {
     if (agent_type != 1 || !has_rigid || !(p[1] > collide_y_min)) { for (int k = 0; k < 3; k++) out[k] = vin[k]; if (gout) for (int k = 0; k < 3; k++) gvv[k] += gout[k]; return; }
     Effector<R>& e = eff[rigid_idx];
-    R g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0};
-    sdf_collide(rigid_mesh, true, &e.pos[f * 3], &e.quat[f * 4], &e.pos[(f + 1) * 3], &e.quat[(f + 1) * 4], dt, p, vin, out, gout, gvv, gpp, g0, g1);
-    if (gout) for (int k = 0; k < 3; k++) {
+    R g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, gq0[4] = {0, 0, 0, 0}, gq1[4] = {0, 0, 0, 0};
+    sdf_collide(rigid_mesh, true, &e.pos[f * 3], &e.quat[f * 4], &e.pos[(f + 1) * 3], &e.quat[(f + 1) * 4], dt, p, vin, out, gout, gvv, gpp, g0, g1, gq0, gq1);
+    if (gout) {
+      for (int k = 0; k < 3; k++) {
 #pragma omp atomic
-      e.gpos[f * 3 + k] += g0[k];
+        e.gpos[f * 3 + k] += g0[k];
 #pragma omp atomic
-      e.gpos[(f + 1) * 3 + k] += g1[k];
+        e.gpos[(f + 1) * 3 + k] += g1[k];
+      }
+      for (int k = 0; k < 4; k++) {
+#pragma omp atomic
+        e.gquat[f * 4 + k] += gq0[k];
+#pragma omp atomic
+        e.gquat[(f + 1) * 4 + k] += gq1[k];
+      }
     }
   }
 
@@ -714,13 +777,19 @@ template <class R> struct Sim {
     }
     e.act_id[f + 1] = e.act_id[f] + ec.flux;
   }
-  void agent_act_grad(int f, int f_global) {  // adjoint of the above w.r.t. pos[f] (quat adjoint: not restated)
+  void agent_act_grad(int f, int f_global) {  // adjoint of the above w.r.t. pos[f] and quat[f]
     if (!has_injector || f_global >= inject_till) return;
     Effector<R>& e = eff[inj_idx];
-    for (int i = 0; i < e.cfg.flux; i++) {
+    const EffectorCfg& ec = e.cfg;
+    for (int i = 0; i < ec.flux; i++) {
       int pid = e.act_range[e.act_id[f] + i];
       size_t q = pi(f + 1, pid);
       for (int k = 0; k < 3; k++) e.gpos[f * 3 + k] += gx[q * 3 + k];
+      if (ec.type == 1) {   // Injector rotates inject_p / inject_v by quat[f] (injector.py:93-96); BallInjector does not (:240-256)
+        R ip[3] = {(R)ec.inject_p[0], (R)ec.inject_p[1], (R)ec.inject_p[2]}, iv[3] = {(R)ec.inject_v[0], (R)ec.inject_v[1], (R)ec.inject_v[2]};
+        quat_rot_adj(&e.quat[f * 4], ip, &gx[q * 3], &e.gquat[f * 4], (R*)nullptr);
+        quat_rot_adj(&e.quat[f * 4], iv, &gv[q * 3], &e.gquat[f * 4], (R*)nullptr);
+      }
     }
   }
   void agent_move(int f) {  // effectors/effector.py:157-161 move_kernel
@@ -742,7 +811,7 @@ template <class R> struct Sim {
       for (int k = 0; k < 4; k++) e.quat[(f + 1) * 4 + k] = o[k] / on;
     }
   }
-  void agent_move_grad(int f) {  // move_kernel.grad, position part
+  void agent_move_grad(int f) {  // move_kernel.grad (effector.py:155): position and orientation
     for (auto& e : eff) {
       R in[3], out[3], jac[9];
       for (int k = 0; k < 3; k++) in[k] = e.pos[f * 3 + k] + e.v[f * 3 + k];
@@ -752,6 +821,25 @@ template <class R> struct Sim {
         for (int b = 0; b < 3; b++) g += jac[b * 3 + a] * e.gpos[(f + 1) * 3 + b];
         e.gpos[f * 3 + a] += g; e.gv[f * 3 + a] += g;
       }
+      // quat[f+1] = normalize(qmul_raw(w2quat(w[f]), quat[f]))   utils/geom.py:7-28
+      const R* wv = &e.w[f * 3]; const R* r = &e.quat[f * 4]; const R* gq1 = &e.gquat[(f + 1) * 4];
+      const R wn = std::sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2] + R(1e-12));
+      const R sh = std::sin(wn / 2), ch = std::cos(wn / 2);
+      const R q[4] = {ch, wv[0] / wn * sh, wv[1] / wn * sh, wv[2] / wn * sh};
+      const R o[4] = {r[0] * q[0] - r[1] * q[1] - r[2] * q[2] - r[3] * q[3], r[0] * q[1] + r[1] * q[0] - r[2] * q[3] + r[3] * q[2],
+                      r[0] * q[2] + r[1] * q[3] + r[2] * q[0] - r[3] * q[1], r[0] * q[3] - r[1] * q[2] + r[2] * q[1] + r[3] * q[0]};
+      const R on = std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+      R dd = 0; for (int k = 0; k < 4; k++) dd += o[k] / on * gq1[k];
+      R go[4]; for (int k = 0; k < 4; k++) go[k] = (gq1[k] - o[k] / on * dd) / on;
+      const R gr[4] = {go[0] * q[0] + go[1] * q[1] + go[2] * q[2] + go[3] * q[3], -go[0] * q[1] + go[1] * q[0] + go[2] * q[3] - go[3] * q[2],
+                       -go[0] * q[2] - go[1] * q[3] + go[2] * q[0] + go[3] * q[1], -go[0] * q[3] + go[1] * q[2] - go[2] * q[1] + go[3] * q[0]};
+      const R gq[4] = {go[0] * r[0] + go[1] * r[1] + go[2] * r[2] + go[3] * r[3], -go[0] * r[1] + go[1] * r[0] - go[2] * r[3] + go[3] * r[2],
+                       -go[0] * r[2] + go[1] * r[3] + go[2] * r[0] - go[3] * r[1], -go[0] * r[3] - go[1] * r[2] + go[2] * r[1] + go[3] * r[0]};
+      for (int k = 0; k < 4; k++) e.gquat[f * 4 + k] += gr[k];
+      // w2quat: q0 = cos(wn/2), q_k = w_k / wn * sin(wn/2), wn = |w|_eps
+      R gwn = -sh / 2 * gq[0];
+      for (int k = 0; k < 3; k++) gwn += gq[k + 1] * wv[k] * (ch / 2 * wn - sh) / (wn * wn);
+      for (int k = 0; k < 3; k++) e.gw[f * 3 + k] += gq[k + 1] * sh / wn + gwn * wv[k] / wn;
     }
   }
   void set_action(int ei, int s, int s_global, const R* action) {  // effector.py:218-221,252-260
@@ -793,7 +881,7 @@ template <class R> struct Sim {
   // ---------------------------------------------------------------- substep, MPM:515-533
   void substep(int f, int f_global, bool none_action) {
     reset_grid(); advect_used(f); process_unused(f);
-    if (!none_action) agent_act(f, f_global);
+    if (!none_action) { agent_act(f, f_global); collector_act(f); }
     compute_F_tmp_svd(f); p2g(f, true);
     if (!none_action) agent_move(f);
     grid_op(f); g2p(f); advect(f);

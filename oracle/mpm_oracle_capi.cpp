@@ -136,6 +136,11 @@ void orc_destroy(void* hp) { Handle* h = (Handle*)hp; delete h->f32; delete h->f
 void orc_set_threads(int n) { omp_set_num_threads(n); }
 int orc_get_max_threads() { return omp_get_max_threads(); }
 
+void orc_set_collector(void* hp, int type, const double* lo, const double* hi, const double* c, double r, int mat) {
+  Handle* h = (Handle*)hp;
+  DISPATCH(h, (S.collector_type = type, S.collector_mat = mat, S.col_r = (decltype(S.dt))r, S.col_c[0] = (decltype(S.dt))c[0], S.col_c[1] = (decltype(S.dt))c[1]));
+  for (int k = 0; k < 3; k++) DISPATCH(h, (S.col_lo[k] = (decltype(S.dt))lo[k], S.col_hi[k] = (decltype(S.dt))hi[k]));
+}
 void orc_set_bodies(void* hp, const int* body_id, int n_bodies) { Handle* h = (Handle*)hp; DISPATCH(h, S.set_bodies(body_id, n_bodies)); }
 void orc_set_particle_info(void* hp, const int* mat, const int* cls, const double* mu, const double* lam, const double* mass) {
   Handle* h = (Handle*)hp; DISPATCH(h, set_info_t(S, mat, cls, mu, lam, mass)); }
@@ -181,6 +186,17 @@ void orc_sdf_collide_eval(int res, const double* vox, const double* T, double fr
   double gp[3] = {0, 0, 0}, gv[3] = {0, 0, 0}, g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0};
   sdf_collide<double>(M, dynamic != 0, io + 6, q, io + 9, q, dt, io, io + 3, out, gout, gv, gp, g0, g1);
   if (gout) for (int k = 0; k < 3; k++) { gio[k] = gp[k]; gio[3 + k] = gv[k]; gio[6 + k] = g0[k]; gio[9 + k] = g1[k]; }
+}
+// same with free pose quaternions: io = [p(3) v(3) pos0(3) pos1(3) q0(4) q1(4)]; adjoints in the same layout
+void orc_sdf_collide_eval_q(int res, const double* vox, const double* T, double friction, double softness, double dt,
+                            const double* io, double* out, const double* gout, double* gio) {
+  SdfMesh<double> M; fill_mesh(M, res, vox, T, friction, softness);
+  double gp[3] = {0, 0, 0}, gv[3] = {0, 0, 0}, g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, gq0[4] = {0, 0, 0, 0}, gq1[4] = {0, 0, 0, 0};
+  sdf_collide<double>(M, true, io + 6, io + 12, io + 9, io + 16, dt, io, io + 3, out, gout, gv, gp, g0, g1, gq0, gq1);
+  if (gout) {
+    for (int k = 0; k < 3; k++) { gio[k] = gp[k]; gio[3 + k] = gv[k]; gio[6 + k] = g0[k]; gio[9 + k] = g1[k]; }
+    for (int k = 0; k < 4; k++) { gio[12 + k] = gq0[k]; gio[16 + k] = gq1[k]; }
+  }
 }
 void orc_set_collide_y_min(void* hp, double y) { Handle* h = (Handle*)hp; DISPATCH(h, S.collide_y_min = (decltype(S.dt))y); }
 void orc_set_agent(void* hp, int agent_type) { Handle* h = (Handle*)hp; DISPATCH(h, (S.agent_type = agent_type, S.has_injector = (agent_type == 2))); }

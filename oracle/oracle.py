@@ -215,6 +215,12 @@ class OracleSim:
             self.L.orc_set_agent(self.h, 2)
         return ei
 
+    def set_collector(self, boundary, mat=-1):
+        """collector of AgentPouring (mat=-1: every material) / AgentJetBot (mat=WATER); boundary: create_boundary kwargs."""
+        bf = boundary_fields(boundary)
+        self.L.orc_set_collector(self.h, int(bf["boundary_type"]), _p(_d(bf["b_lower"])), _p(_d(bf["b_upper"])), _p(_d(bf["cyl_center"])),
+                                 C.c_double(bf["cyl_radius"]), int(mat))
+
     def set_bodies(self, body_id, n_bodies=None):
         """body ids per particle (MPM:177-201); enables shape matching for bodies whose first particle is MAT_RIGID."""
         bid = np.ascontiguousarray(body_id, dtype=np.int32)

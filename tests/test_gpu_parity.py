@@ -541,3 +541,147 @@ def test_rigid_material_bodies_forward_and_adjoint():
     for k in ('x', 'v', 'C', 'F'):
         tol = max(1e-4, 3 * rel(og32[k], og[k]))   # 20 substeps of fp32 round-off: bar = north-star 1e-4 or the fp32 oracle's own distance
         assert rel(gg[k], og[k]) < tol, (k, rel(gg[k], og[k]), tol)
+
+
+def _run_env_fwd_bwd(env, actions, action_p):
+    n_steps = len(actions)
+    st0 = env.get_state()['state']
+    env.set_state(st0, grad_enabled=True)
+    env.apply_agent_action_p(action_p)
+    for i in range(n_steps):
+        env.step(actions[i])
+    fr = env.simulator.get_state()
+    info = env.get_final_loss()
+    env.reset_grad(); env.get_final_loss_grad()
+    for i in range(n_steps - 1, -1, -1):
+        env.step_grad(actions[i])
+    env.apply_agent_action_p_grad(action_p)
+    return fr, info, env.agent.get_grad(n_steps)
+
+
+def test_agent_pouring_6dof_collector():
+    """AgentPouring (agents/agent_pouring.py, envs/configs/agent_pouring.yaml): a 6-DOF Rigid (translation + rotation actions)
+    colliding at grid AND particle level, plus the collector that parks out-of-boundary particles at NOWHERE.  Forward state vs
+    the fp32 oracle, loss and dLoss/dAction (3 x 6, rotation columns included) vs the fp64 oracle."""
+    _need_gpu()
+    from conftest import box_sdf
+    from fluidlab_b200 import TaichiEnv, ShapeMatchingLoss
+    from oracle import oracle as orc
+    n_grid, N, n_steps, T = 32, 4000, 2, 20
+    rng = np.random.RandomState(71)
+    x = rng.uniform((0.40, 0.42, 0.40), (0.60, 0.58, 0.60), size=(N, 3))
+    P = make_particles(x, M.ELASTIC, n_grid)
+    vox, Tm = box_sdf(np.array([0.12, 0.05, 0.08]), 0.2)
+    env = TaichiEnv(quality=n_grid / 64, max_substeps_local=T, gravity=(0.0, -10.0, 0.0), horizon=n_steps)
+    ebnd = dict(type='cube', lower=(0.05, 0.05, 0.05), upper=(0.95, 0.95, 0.95))
+    cbnd = dict(type='cube', lower=(0.0, 0.0, 0.0), upper=(1.0, 1.0, 0.585))
+    env.setup_agent(dict(type='AgentPouring', params=dict(collector_boundary=cbnd), effectors=[dict(
+        type='Rigid', params=dict(init_pos=(0.5, 0.64, 0.5), init_euler=(0.0, 23.0, 0.0), action_dim=6,
+                                  action_scale_p=(1.0,) * 6, action_scale_v=(1.0,) * 6),
+        mesh=dict(file='glass.obj', material=M.STIRRER, softness=100.0, sdf=dict(voxels=vox, T_mesh_to_voxels=Tm)), boundary=ebnd)]))
+    bnd = dict(type='cube', lower=(0.25, 0.25, 0.25), upper=(0.75, 0.75, 0.75))
+    env.setup_boundary(**bnd)
+    env.particle_bodies.get = lambda: P
+    tgt = [rng.uniform(0.4, 0.6, size=x.shape).astype(np.float32) for _ in range(n_steps)]
+    env.setup_loss(loss_cls=ShapeMatchingLoss, matching_mat=M.ELASTIC, temporal_range_type='all', target=tgt, weights={'chamfer': 1.0})
+    env.build()
+    assert env.agent.collide_type == 'both'
+    actions = np.array([[0.004, -0.03, 0.002, 0.02, -0.03, 0.05], [-0.003, -0.03, 0.004, -0.04, 0.02, 0.03]], dtype=np.float32)
+    action_p = np.array([0.5, 0.64, 0.5, 0, 0, 0], dtype=np.float32)
+    init = np.concatenate([env.agent.rigid.init_pos, env.agent.rigid.init_rot, [0.0]]).astype(np.float64)
+    fr, info, grad = _run_env_fwd_bwd(env, actions, action_p)
+
+    def oracle(prec):
+        o = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=bnd, precision=prec, max_substeps_local=T)
+        o.add_effector(type=0, action_dim=6, scale_v=(1,) * 6, boundary=ebnd, max_action_steps=n_steps + 1, init_pos=(0.5, 0.64, 0.5))
+        mesh = env.agent.rigid.mesh
+        o.set_rigid_mesh(mesh.sdf_voxels_np, mesh.T_mesh_to_voxels_np, friction=mesh.friction, softness=mesh.softness, collide_type='both')
+        o.set_collector(cbnd, mat=-1)
+        o.enable_grad()
+        o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+        o.set_effector_state(0, 0, init); o.apply_action_p(action_p)
+        total = 0.0
+        for i in range(n_steps):
+            o.step(actions[i]); total += o.loss_value(o.cur_substep_local, M.ELASTIC, 1.0, tgt[i])
+        ofr = o.get_frame(o.cur_substep_local)
+        o.reset_grad()
+        for i in range(n_steps - 1, -1, -1):
+            o.loss_seed(o.cur_substep_local, M.ELASTIC, 1.0, tgt[i]); o.step_grad(actions[i])
+        o.apply_action_p_grad()
+        return ofr, total, o.get_action_grad(n_steps)
+    o32, _, _ = oracle(32)
+    _, loss64, g64 = oracle(64)
+    n_col = N - int(o32['used'].sum())
+    assert 0 < n_col < N // 2, n_col
+    flips = int((fr['used'] != o32['used']).sum())
+    assert flips <= 2, flips                                   # a particle within round-off of the collector plane may flip
+    both = (fr['used'] == 1) & (o32['used'] == 1)
+    assert np.all(fr['x'][fr['used'] == 0] == -100.0)          # parked at NOWHERE (agent_pouring.py:37-38)
+    assert rel(fr['x'][both], o32['x'][both]) < 1e-4
+    if flips == 0:
+        assert abs(info['loss'] - loss64) < 1e-4 * abs(loss64)
+        assert grad.shape == g64.shape == (n_steps + 1, 6)
+        assert np.abs(g64[:n_steps, 3:]).max() > 1e-4, 'rotation actions carry no gradient'
+        assert rel(grad, g64) < 1e-3, (rel(grad, g64), grad, g64)
+
+
+def test_agent_jetbot_6dof_injector_collector():
+    """AgentJetBot (agents/agent_jetbot.py, envs/configs/agent_transporting.yaml): a 6-DOF Injector (inject_p / inject_v rotate with
+    the pose, injector.py:93-96) and a collector of WATER particles; loss and dLoss/dAction (4 x 6) vs the fp64 oracle."""
+    _need_gpu()
+    from fluidlab_b200 import TaichiEnv, ShapeMatchingLoss
+    from oracle import oracle as orc
+    n_grid, n_pool, n_parked, flux, n_steps, T = 32, 3000, 400, 4, 3, 20
+    rng = np.random.RandomState(73)
+    x = np.concatenate([np.tile(M.NOWHERE, (n_parked, 1)), rng.uniform((0.36, 0.36, 0.36), (0.64, 0.44, 0.64), size=(n_pool, 3))])
+    used = np.concatenate([np.zeros(n_parked), np.ones(n_pool)]).astype(np.int32)
+    P = make_particles(x, M.WATER, n_grid, used=used)
+    N = len(x)
+    env = TaichiEnv(quality=n_grid / 64, max_substeps_local=T, gravity=(0.0, -10.0, 0.0), horizon=n_steps)
+    np.random.seed(11)
+    ebnd = dict(type='cube', lower=(0.1, 0.1, 0.1), upper=(0.9, 0.9, 0.9))
+    cbnd = dict(type='cube', lower=(0.0, 0.0, 0.0), upper=(1.0, 1.0, 0.60))
+    env.setup_agent(dict(type='AgentJetBot', params=dict(collector_boundary=cbnd), effectors=[dict(
+        type='Injector', params=dict(radius=0.015, flux=flux, init_pos=(0.58, 0.55, 0.5), init_euler=(20.0, 35.0, -10.0), inject_v=(-3.0, 0.0, 0.0),
+                                     inject_p=(-0.07, 0.0, 0.0), action_dim=6, action_scale_p=(1.0,) * 6, action_scale_v=(1.0, 1.0, 1.0, 5.0, 5.0, 5.0)),
+        boundary=ebnd)]))
+    bnd = dict(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.7, 0.7, 0.7))
+    env.setup_boundary(**bnd)
+    env.particle_bodies.get = lambda: P
+    tgt = [rng.uniform(0.4, 0.6, size=x.shape).astype(np.float32) for _ in range(n_steps)]
+    env.setup_loss(loss_cls=ShapeMatchingLoss, matching_mat=M.WATER, temporal_range_type='all', target=tgt, weights={'chamfer': 1.0})
+    env.build()
+    inj = env.agent.injector
+    actions = np.array([[0.003, -0.002, 0.001, 0.02, 0.03, -0.02], [-0.002, 0.001, 0.002, -0.01, 0.02, 0.03], [0.001, 0.0, -0.002, 0.03, -0.02, 0.01]],
+                       dtype=np.float32)
+    action_p = np.array([0.58, 0.55, 0.5, 0, 0, 0], dtype=np.float32)
+    init = np.concatenate([inj.init_pos, inj.init_rot, [0.0]]).astype(np.float64)
+    fr, info, grad = _run_env_fwd_bwd(env, actions, action_p)
+
+    o = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=bnd, precision=64, max_substeps_local=T)
+    o.add_effector(type=1, action_dim=6, scale_v=(1, 1, 1, 5, 5, 5), boundary=ebnd, radius=0.015, flux=flux, inject_v=(-3.0, 0, 0), inject_p=(-0.07, 0, 0),
+                   locally_random=inj.locally_random, random_vector=inj.random_vector_np, act_range=np.where(used == 0)[0], max_action_steps=n_steps + 1)
+    o.set_collector(cbnd, mat=M.WATER)
+    o.enable_grad()
+    o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+    o.set_effector_state(0, 0, init); o.apply_action_p(action_p)
+    total = 0.0
+    for i in range(n_steps):
+        o.step(actions[i]); total += o.loss_value(o.cur_substep_local, M.WATER, 1.0, tgt[i])
+    ofr = o.get_frame(o.cur_substep_local)
+    o.reset_grad()
+    for i in range(n_steps - 1, -1, -1):
+        o.loss_seed(o.cur_substep_local, M.WATER, 1.0, tgt[i]); o.step_grad(actions[i])
+    o.apply_action_p_grad()
+    g64 = o.get_action_grad(n_steps)
+    n_col = n_pool + flux * 10 * n_steps - int(ofr['used'].sum())
+    assert n_col > 0, 'nothing was collected'
+    flips = int((fr['used'] != ofr['used']).sum())
+    assert flips <= 2, flips
+    both = (fr['used'] == 1) & (ofr['used'] == 1)
+    assert rel(fr['x'][both], ofr['x'][both]) < 1e-5
+    if flips == 0:
+        assert abs(info['loss'] - total) <= 1e-5 * abs(total), (info['loss'], total)
+        assert grad.shape == g64.shape == (n_steps + 1, 6)
+        assert np.abs(g64[:n_steps, 3:]).max() > 1e-4
+        assert rel(grad, g64) < 1e-4, (rel(grad, g64), grad, g64)
