@@ -685,3 +685,108 @@ def test_agent_jetbot_6dof_injector_collector():
         assert grad.shape == g64.shape == (n_steps + 1, 6)
         assert np.abs(g64[:n_steps, 3:]).max() > 1e-4
         assert rel(grad, g64) < 1e-4, (rel(grad, g64), grad, g64)
+
+
+def _momentum(st, mass):
+    u = st['used'].astype(np.float64)
+    return (st['v'].astype(np.float64) * (mass * u)[:, None]).sum(0)
+
+
+@pytest.mark.parametrize('cfg', ['C2', 'C4'])
+def test_full_size_conservation_invariants(cfg):
+    """BASELINE.json configs[1] (C2: 1M WATER, 128^3) and configs[3] (C4: 1M ELASTIC + 1M ICECREAM, 192^3) at FULL size, where the
+    oracle is too slow: size-independent properties of MLS-MPM (SURVEY.md §8c pins 2).
+      * p2g of a stress-free state (F = I, C = 0): sum of grid mass = sum of particle mass, grid momentum = particle momentum;
+      * 30 free-flight substeps (no wall contact): internal forces cancel, so total momentum changes by exactly M g t;
+      * the cell-sorted, CUDA-graph step path reproduces the per-substep path bit for bit apart from summation order (1e-6)."""
+    _need_gpu()
+    from fluidlab_b200 import MPMSimulator
+    rs = np.random.RandomState(0)
+    if cfg == 'C2':
+        n_grid, g = 128, (0.0, -10.0, 0.0)
+        x = rs.uniform((0.25, 0.30, 0.25), (0.75, 0.54, 0.75), size=(1_000_000, 3)); mat = np.full(len(x), M.WATER)
+    else:
+        n_grid, g = 192, (0.0, -10.0, 0.0)
+        xa = rs.uniform((0.20, 0.30, 0.30), (0.45, 0.55, 0.70), size=(1_000_000, 3))
+        xb = rs.uniform((0.55, 0.30, 0.30), (0.80, 0.55, 0.70), size=(1_000_000, 3))
+        x = np.concatenate([xa, xb]); mat = np.concatenate([np.full(len(xa), M.ELASTIC), np.full(len(xb), M.ICECREAM)])
+    N = len(x)
+    P = make_particles(x, mat, n_grid)
+    mass = P['mass']
+
+    def build(sort_every, graphs):
+        s = MPMSimulator(dim=3, quality=n_grid / 64, gravity=g, horizon=100, max_substeps_local=50, max_substeps_global=100000, ckpt_dest='gpu',
+                         sort_every=sort_every)
+        s.use_graphs = graphs
+        s.build(None, None, [], P)
+        return s
+    s = build(1, True)
+    v0 = (rs.randn(N, 3) * 0.2).astype(np.float32)
+    st = s.get_state(); st['v'][:] = v0; s.set_state(0, st)
+    # ---- p2g conservation
+    s.sort_frame(0)
+    s.phase('clear_grid', 0); s.phase('p2g', 0, 0)
+    vin, m, _ = s.read_grid()
+    M_tot = mass.sum()
+    assert abs(m.astype(np.float64).sum() - M_tot) < 1e-6 * M_tot
+    p_grid, p_part = vin.astype(np.float64).sum(0), (v0.astype(np.float64) * mass[:, None]).sum(0)
+    scale = (np.abs(v0).astype(np.float64) * mass[:, None]).sum()
+    assert np.abs(p_grid - p_part).max() < 1e-6 * scale, (p_grid, p_part)
+    s.phase('grid_op', 0, 1)   # consume + clear the accumulator again (restores the between-substeps invariant)
+    # ---- momentum balance over 3 steps of free flight
+    p0 = _momentum(st, mass)
+    for _ in range(3):
+        s.step(None)
+    st1 = s.get_state()
+    assert np.isfinite(st1['x']).all() and int(st1['used'].sum()) == N
+    t = 30 * 2e-4
+    expect = p0 + M_tot * np.array(g) * t
+    got = _momentum(st1, mass)
+    assert np.abs(got - expect).max() < 2e-5 * max(np.abs(expect).max(), scale * 1e-2), (got, expect)
+    # ---- sorted + CUDA-graph path == unsorted per-substep path
+    s2 = build(0, False)
+    st2 = s2.get_state(); st2['v'][:] = v0; s2.set_state(0, st2)
+    for _ in range(3):
+        s2.step(None)
+    ref = s2.get_state()
+    for k, tol in (('x', 1e-6), ('v', 1e-4), ('F', 1e-5)):
+        assert rel(st1[k], ref[k]) < tol, (k, rel(st1[k], ref[k]))
+
+
+def test_full_size_directional_derivative_c2():
+    """C2 at full size, backward: <grad_v L, u> from step_grad vs the central difference of L(v0 +- eps u), L = sum w . x_T after one
+    step (10 substeps) — a size-independent check that the adjoint kernels, the per-frame grid ring and 64-bit indexing hold at
+    1M particles / 128^3 (fp32 forward differences: 2 % bar)."""
+    _need_gpu()
+    from fluidlab_b200 import MPMSimulator
+    rs = np.random.RandomState(0)
+    n_grid, N = 128, 1_000_000
+    x = rs.uniform((0.25, 0.30, 0.25), (0.75, 0.54, 0.75), size=(N, 3))
+    P = make_particles(x, M.WATER, n_grid)
+    s = MPMSimulator(dim=3, quality=2, gravity=(0.0, -10.0, 0.0), horizon=100, max_substeps_local=50, max_substeps_global=100000, ckpt_dest='gpu')
+    s.build(None, None, [], P)
+    v0 = (rs.randn(N, 3) * 0.2).astype(np.float32)
+    u = rs.randn(N, 3).astype(np.float32)
+    w = rs.randn(N, 3).astype(np.float32)
+    base = s.get_state()
+
+    def run(v):
+        st = dict(base); st['v'] = v
+        s.cur_substep_global = 0
+        s.set_state(0, st)
+        s.step(None)
+        return s.get_state()['x'].astype(np.float64)
+    s.enable_grad()
+    run(v0)
+    s.reset_grad()
+    z3, z9 = np.zeros((N, 3), np.float32), np.zeros((N, 3, 3), np.float32)
+    s.set_grad(w, z3, z9, z9)
+    s.step_grad(None)
+    gv = s.get_grad(('v',))['v'].astype(np.float64)
+    an = float((gv * u).sum())
+    s.disable_grad()
+    eps = 2e-2
+    lp = (run(v0 + eps * u) * w).sum(); lm = (run(v0 - eps * u) * w).sum()
+    fd = float(lp - lm) / (2 * eps)
+    assert abs(an) > 1e-3
+    assert abs(fd - an) < 2e-2 * abs(an), (fd, an)
