@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfluidmpm.so")
+LIB_PATH = os.environ.get("FMPM_LIB", os.path.join(_HERE, "libfluidmpm.so"))   # FMPM_LIB: A/B kernel variants (profiles/ab_variants.sh)
 _LIB = None
 
 vp = C.c_void_p

@@ -7,7 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRCS = ["fmpm_forward.cu", "fmpm_backward.cu", "fmpm_io.cu", "fmpm_rigid.cu"]
 HDRS = ["fmpm_common.cuh", "fmpm_scatter.cuh", "fmpm_sdf.cuh", os.path.join("..", "..", "include", "fluidmpm.h")]
-OUT = os.path.join(HERE, "..", "libfluidmpm.so")
+OUT = os.environ.get("FMPM_OUT", os.path.join(HERE, "..", "libfluidmpm.so"))   # FMPM_OUT: A/B variants (profiles/ab_variants.sh)
+OBJDIR = os.environ.get("FMPM_OBJDIR", HERE)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # no --use_fast_math: parity with the reference's IEEE fp32 arithmetic matters more than a few SFU cycles
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DFMPM_BUILD",
@@ -28,8 +29,9 @@ def build(force=False, verbose=False):
         return out
     objs = []
     procs = []
+    os.makedirs(OBJDIR, exist_ok=True)
     for s in SRCS:
-        o = os.path.join(HERE, s.replace(".cu", ".o"))
+        o = os.path.join(OBJDIR, s.replace(".cu", ".o"))
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(HERE, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)

@@ -25,7 +25,7 @@
 #define P2G_WARPS 4
 #endif
 #ifndef P2G_ROUNDS
-#define P2G_ROUNDS 4
+#define P2G_ROUNDS 2   // A/B on B200 (profiles/README.md): 2 -> 78.4 us, 4 -> 80.5, 8 -> 92.3, 16 -> 98.5 (tail / balance)
 #endif
 #ifndef P2G_MINB
 #define P2G_MINB 5   // <=102 registers: 20 warps/SM; measured 15% faster than the unconstrained 128-register build

@@ -1,0 +1,55 @@
+"""Per-phase device times of the forward substep on the C2 workload (1M water particles, 128^3), CUDA events around batches of
+launches.  Used for A/B runs of kernel variants: FMPM_LIB=<variant.so> python profiles/phase_times.py"""
+import os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from conftest import make_particles          # noqa: E402
+from fluidlab_b200 import MPMSimulator, macros as M   # noqa: E402
+
+N = int(os.environ.get('PT_N', 1_000_000))
+rs = np.random.RandomState(0)
+x = rs.uniform((0.25, 0.30, 0.25), (0.75, 0.54, 0.75), size=(N, 3))
+P = make_particles(x, M.WATER, 128)
+s = MPMSimulator(dim=3, quality=2, gravity=(0.0, -10.0, 0.0), horizon=1000, max_substeps_local=50, max_substeps_global=10 ** 7, ckpt_dest='gpu', sort_every=2)
+s.build(None, None, [], P)
+for _ in range(8):   # settle into a realistic, sorted state
+    s.step(None)
+f = s.cur_substep_local
+s.sort_frame(f)
+ev = lambda: torch.cuda.Event(enable_timing=True)
+out = {}
+REP = 20
+for name, args in (('p2g', (0,)), ('grid_op', (0,)), ('g2p', ())):
+    ts = []
+    for it in range(REP + 3):
+        # restore the between-phases state: accumulators hold p2g(f) before grid_op / g2p runs
+        s.phase('clear_grid', f); s.phase('p2g', f, 0)
+        if name != 'p2g':
+            s.phase('grid_op', f, 0)
+        if name == 'p2g':
+            s.phase('clear_grid', f)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        s.phase(name, f, *args)
+        e1.record(); torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        if name == 'p2g':
+            s.phase('grid_op', f, 1)
+        else:
+            s.phase('clear_grid', f)
+    out[name] = float(np.median(ts))
+# whole steps through the CUDA-graph path
+for _ in range(4):
+    s.step(None)
+torch.cuda.synchronize()
+e0, e1 = ev(), ev(); e0.record()
+K = 40
+for _ in range(K):
+    s.step(None)
+e1.record(); torch.cuda.synchronize()
+out['substep_avg'] = e0.elapsed_time(e1) * 1e3 / (K * 10)
+print(os.environ.get('FMPM_LIB', 'default'), ' '.join(f'{k} {v:.1f}us' for k, v in out.items()), f"-> {1e6 / out['substep_avg']:.0f} substeps/s")

@@ -733,20 +733,26 @@ def test_full_size_conservation_invariants(cfg):
     scale = (np.abs(v0).astype(np.float64) * mass[:, None]).sum()
     assert np.abs(p_grid - p_part).max() < 1e-6 * scale, (p_grid, p_part)
     s.phase('grid_op', 0, 1)   # consume + clear the accumulator again (restores the between-substeps invariant)
-    # ---- momentum balance over 3 steps of free flight
+    # ---- momentum balance in free flight.  C4 note: ELASTIC at 192^3 with the reference's fixed dt = 2e-4 has
+    # c dt / dx = sqrt((lam + 2 mu) / rho) * 2e-4 * 192 = 1.27 > 1 (explicit MPM is unstable there, any velocity noise explodes
+    # within ~30 substeps, in the reference too) -> C4 runs one step from rest; C2 runs three steps with random velocities.
+    n_steps = 3 if cfg == 'C2' else 1
+    if cfg == 'C4':
+        v0 = np.zeros_like(v0); scale = M_tot
+        st['v'][:] = 0.0; s.cur_substep_global = 0; s.set_state(0, st)
     p0 = _momentum(st, mass)
-    for _ in range(3):
+    for _ in range(n_steps):
         s.step(None)
     st1 = s.get_state()
     assert np.isfinite(st1['x']).all() and int(st1['used'].sum()) == N
-    t = 30 * 2e-4
+    t = n_steps * 10 * 2e-4
     expect = p0 + M_tot * np.array(g) * t
     got = _momentum(st1, mass)
     assert np.abs(got - expect).max() < 2e-5 * max(np.abs(expect).max(), scale * 1e-2), (got, expect)
     # ---- sorted + CUDA-graph path == unsorted per-substep path
     s2 = build(0, False)
     st2 = s2.get_state(); st2['v'][:] = v0; s2.set_state(0, st2)
-    for _ in range(3):
+    for _ in range(n_steps):
         s2.step(None)
     ref = s2.get_state()
     for k, tol in (('x', 1e-6), ('v', 1e-4), ('F', 1e-5)):
