@@ -761,8 +761,10 @@ def test_full_size_conservation_invariants(cfg):
 
 def test_full_size_directional_derivative_c2():
     """C2 at full size, backward: <grad_v L, u> from step_grad vs the central difference of L(v0 +- eps u), L = sum w . x_T after one
-    step (10 substeps) — a size-independent check that the adjoint kernels, the per-frame grid ring and 64-bit indexing hold at
-    1M particles / 128^3 (fp32 forward differences: 2 % bar)."""
+    step (10 substeps) — a size-independent check that the adjoint kernels, the per-frame grid ring and the indexing hold at
+    1M particles / 128^3.  u and w are SMOOTH fields of the particle position (wavelength >= 32 cells): a white-noise direction
+    is averaged away by the particle-grid transfers and leaves nothing but round-off to compare.
+    fp32 forward differences: 0.5 % bar."""
     _need_gpu()
     from fluidlab_b200 import MPMSimulator
     rs = np.random.RandomState(0)
@@ -771,9 +773,10 @@ def test_full_size_directional_derivative_c2():
     P = make_particles(x, M.WATER, n_grid)
     s = MPMSimulator(dim=3, quality=2, gravity=(0.0, -10.0, 0.0), horizon=100, max_substeps_local=50, max_substeps_global=100000, ckpt_dest='gpu')
     s.build(None, None, [], P)
-    v0 = (rs.randn(N, 3) * 0.2).astype(np.float32)
-    u = rs.randn(N, 3).astype(np.float32)
-    w = rs.randn(N, 3).astype(np.float32)
+    tp = 2 * np.pi
+    v0 = (0.2 * np.stack([np.sin(tp * x[:, 1] * 2), np.cos(tp * x[:, 2] * 3), np.sin(tp * x[:, 0] * 2 + 1.0)], 1)).astype(np.float32)
+    u = np.stack([np.sin(tp * (x[:, 0] * 3 + x[:, 2])), np.cos(tp * x[:, 1] * 4), np.sin(tp * (x[:, 2] * 2 - x[:, 1]))], 1).astype(np.float32)
+    w = np.stack([np.cos(tp * (x[:, 0] * 2 + 0.3)), np.sin(tp * (x[:, 1] * 3 + x[:, 0])), np.cos(tp * x[:, 2] * 3)], 1).astype(np.float32)
     base = s.get_state()
 
     def run(v):
@@ -794,5 +797,6 @@ def test_full_size_directional_derivative_c2():
     eps = 2e-2
     lp = (run(v0 + eps * u) * w).sum(); lm = (run(v0 - eps * u) * w).sum()
     fd = float(lp - lm) / (2 * eps)
-    assert abs(an) > 1e-3
-    assert abs(fd - an) < 2e-2 * abs(an), (fd, an)
+    ballistic = float((w.astype(np.float64) * u).sum()) * 10 * 2e-4
+    assert abs(an) > 0.1 * abs(ballistic) > 1.0, (an, ballistic)
+    assert abs(fd - an) < 5e-3 * abs(an), (fd, an, ballistic)
