@@ -19,7 +19,9 @@
 #include "fmpm_sdf.cuh"
 
 #define SC_WARPS 4
-#define SC_ROUNDS 4
+#ifndef SC_ROUNDS
+#define SC_ROUNDS 4   // 1 / 2 rounds: no gain for this kernel (A/B in profiles/README.md)
+#endif
 
 // grads in a ping-pong buffer g (0/1): same planar layout as the state ring with frame index g
 struct GState { float x[3], v[3]; Mat3 C, F; };

@@ -25,10 +25,14 @@
 #define P2G_WARPS 4
 #endif
 #ifndef P2G_ROUNDS
-#define P2G_ROUNDS 2   // A/B on B200 (profiles/README.md): 2 -> 78.4 us, 4 -> 80.5, 8 -> 92.3, 16 -> 98.5 (tail / balance)
+#define P2G_ROUNDS 1   // A/B on B200 (profiles/README.md): 1 -> 72.2 us (79 registers, no spill), 2 -> 77.8, 4 -> 80.5, 8 -> 92.3, 16 -> 98.5
 #endif
 #ifndef P2G_MINB
 #define P2G_MINB 5   // <=102 registers: 20 warps/SM; measured 15% faster than the unconstrained 128-register build
+#endif
+
+#ifndef P2G_PREFETCH
+#define P2G_PREFETCH 1   // (only matters for P2G_ROUNDS > 1) next round's particle data: 0 = not prefetched, 1 = into registers, 2 = prefetch.global.L2 only
 #endif
 
 // =============================================================================================
@@ -42,6 +46,18 @@ __device__ __forceinline__ void p2g_load_raw(const KParams& P, const int f, cons
     R.f0 = P.pf[pf_idx(P, f, 0, s)]; R.f1 = P.pf[pf_idx(P, f, 1, s)]; R.f8 = P.pf8[pf8_idx(P, f, s)];
   } else {
     R.a0 = make_float4(0.f, 0.f, 0.f, 0.f);  // meta = 0 -> unused
+  }
+}
+__device__ __forceinline__ void p2g_prefetch_l2(const KParams& P, const int f, const long long sl) {
+  if (sl < P.N) {
+    const int s = (int)sl;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pa + pa_idx(P, f, 0, s)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pa + pa_idx(P, f, 1, s)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pa + pa_idx(P, f, 2, s)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pa + pa_idx(P, f, 3, s)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pf + pf_idx(P, f, 0, s)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pf + pf_idx(P, f, 1, s)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pf8 + pf8_idx(P, f, s)));
   }
 }
 __device__ __forceinline__ void p2g_unpack(const PRaw& R, PState& st) {
@@ -69,6 +85,9 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
     const long long sl = slot0 + r * 32 + lane;
     const long long rem = (long long)P.N - (slot0 + r * 32);
     if (rem <= 0) break;  // warp-uniform
+#if P2G_PREFETCH != 1
+    if (r > 0) p2g_load_raw(P, f, sl, R);
+#endif
     const int cnt = rem < 32 ? (int)rem : 32;
     int key = -1;
     float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, m = 0.f;
@@ -97,7 +116,11 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
     }
     const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
     // software pipelining: the next round's 100 B/particle are in flight while this round is scattered
+#if P2G_PREFETCH == 1
     if (r + 1 < P2G_ROUNDS) p2g_load_raw(P, f, sl + 32, R);
+#elif P2G_PREFETCH == 2
+    if (r + 1 < P2G_ROUNDS) p2g_prefetch_l2(P, f, sl + 32);
+#endif
     __syncwarp();
     window_consume(W, S, cnt, starts, P.grid_pm);
     __syncwarp();
@@ -164,6 +187,7 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, c
 // =============================================================================================
 #define G2P_WARPS 4
 
+// no min-blocks bound: ptxas settles at 72 registers (7 CTAs/SM); (128,8) = 64 registers measured 35.1 us vs 33.3 us
 __global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const int f) {
   __shared__ float4 tiles[G2P_WARPS][9 * G2P_ZMAX];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;

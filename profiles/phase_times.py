@@ -42,6 +42,26 @@ for name, args in (('p2g', (0,)), ('grid_op', (0,)), ('g2p', ())):
         else:
             s.phase('clear_grid', f)
     out[name] = float(np.median(ts))
+if os.environ.get('PT_BWD'):
+    # backward phases of frame f (stored-grid mode is bypassed: the phase entry points use the scratch grids)
+    s.enable_grad(); s.cur_substep_global = f
+    s._ensure_grad_buffers()
+    s.reset_grad()
+    g = torch.randn((2, 4, N, 4), device=s.device) * 0.1
+    s._ga.copy_(g); s._gf.normal_(0, 0.1); s._gf8.normal_(0, 0.1)
+    s.phase('clear_grid', f); s.phase('p2g', f, 0); s.phase('grid_op', f, 0)   # forward grids + block flags of frame f stay in place
+    for name in ('g2p_grad_scatter', 'grid_op_grad', 'particle_grad'):
+        ts = []
+        for it in range(REP + 3):
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            s.phase(name, f, *((0,) if name == 'grid_op_grad' else ()))
+            e1.record(); torch.cuda.synchronize()
+            if it >= 3:
+                ts.append(e0.elapsed_time(e1) * 1e3)
+        out[name] = float(np.median(ts))
+    s.disable_grad()
 # whole steps through the CUDA-graph path
 for _ in range(4):
     s.step(None)
