@@ -257,15 +257,62 @@ def main():
             return batch(fn)
         return batch(lambda: (pre(), fn())) - batch(pre)
 
-    t_p2g = time_phase(lambda: sim.phase('p2g', f, 0), pre=lambda: sim.phase('clear_grid', f))
-    sim.phase('clear_grid', f); sim.phase('p2g', f, 0)
-    g_t = int((sim._grid_pm.reshape(-1, 4)[:, 3] > 0).sum().item())
-    def _refill():
+    sort_age = None
+    if slab is None:
+        # Average launch duration of every forward kernel OVER THE TIMED TRAJECTORY: the same W + K steps are replayed from the initial
+        # state on the per-substep path with CUDA events between the three launches of each substep (the stream stays saturated:
+        # ~40 us of host work per substep against ~130 us of device work), so stale-sort states weigh in exactly as they do in `value`.
+        L_, h_ = sim._lib, sim._h
+        evs, gts, rec = [], [], [False]
+        orig_substep, orig_graphs = L_.fmpm_substep, sim.use_graphs
+
+        def timed_substep(h, fr, stream):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record(); rc = L_.fmpm_p2g(h, fr, 1, stream)
+            e[1].record(); rc |= L_.fmpm_grid_op(h, fr, 1, stream)
+            e[2].record(); rc |= L_.fmpm_g2p(h, fr, stream)
+            e[3].record()
+            if rec[0]:
+                evs.append(e)
+            return rc
+        sim.cur_substep_global = 0
+        sim.set_state(0, init)
+        sim.use_graphs = False
+        L_.fmpm_substep = timed_substep
+        try:
+            for i in range(W + K):
+                rec[0] = i >= W
+                if rec[0] and (i - W) % max(1, K // 4) == 0:   # touched-node census at 4 points of the run (p2g of the current frame, accumulator only)
+                    fc = sim.cur_substep_local
+                    sim.phase('clear_grid', fc); sim.phase('p2g', fc, 0)
+                    gts.append(int((sim._grid_pm.reshape(-1, 4)[:, 3] > 0).sum().item()))
+                    sim.phase('grid_op', fc, 1)
+                sim.step(None)
+            torch.cuda.synchronize()
+        finally:
+            L_.fmpm_substep = orig_substep
+            sim.use_graphs = orig_graphs
+        t_p2g = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+        t_gop = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+        t_g2p = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+        g_t = int(np.mean(gts))
+        if args.sort_every > 1:   # how much the scatter slows down as the cell sort ages (steps since the last sort: 0, 1, ...)
+            per_age = [[] for _ in range(args.sort_every)]
+            for j, e in enumerate(evs):
+                per_age[((W + j // SUBSTEPS_PER_STEP) % args.sort_every)].append(e[0].elapsed_time(e[1]))
+            sort_age = [float(np.mean(a)) for a in per_age if a]
+        timing_note = f'mean over the {len(evs)} substeps of a replay of the timed trajectory (CUDA events between the launches)'
+    else:
+        t_p2g = time_phase(lambda: sim.phase('p2g', f, 0), pre=lambda: sim.phase('clear_grid', f))
         sim.phase('clear_grid', f); sim.phase('p2g', f, 0)
-    t_gop = time_phase(lambda: sim.phase('grid_op', f, 0), pre=_refill)  # includes the active-block compaction
-    # g2p writes frame f+1: time it on a scratch frame pair (f -> f+1 is rewritten by the next step anyway)
-    t_g2p = time_phase(lambda: sim._ck(sim._lib.fmpm_g2p(sim._h, f, sim._stream()), 'g2p'))
-    sim.phase('clear_grid', f)
+        g_t = int((sim._grid_pm.reshape(-1, 4)[:, 3] > 0).sum().item())
+        def _refill():
+            sim.phase('clear_grid', f); sim.phase('p2g', f, 0)
+        t_gop = time_phase(lambda: sim.phase('grid_op', f, 0), pre=_refill)
+        # g2p writes frame f+1: time it on a scratch frame pair (f -> f+1 is rewritten by the next step anyway)
+        t_g2p = time_phase(lambda: sim._ck(sim._lib.fmpm_g2p(sim._h, f, sim._stream()), 'g2p'))
+        sim.phase('clear_grid', f)
+        timing_note = 'batched launches on the final state'
     peak, peak_src = peaks()
     p2g_bytes = 136 * used + 16 * g_t            # p2g particle bytes + accumulated grid write-back
     g2p_bytes = 76 * used + 12 * g_t             # g2p(+advect)
@@ -275,10 +322,10 @@ def main():
         traffic = json.load(open(tp)).get('k_p2g')  # from the committed ncu --set full capture of this same workload
     roof = {'bound': 'hbm', 'kernel': 'k_p2g', 'achieved': p2g_bytes / (t_p2g * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
             'frac': p2g_bytes / (t_p2g * 1e-3) / 1e9 / peak, 'traffic': traffic, 'peak_source': peak_src,
-            'algorithmic_bytes_per_launch': p2g_bytes, 'launch_ms': t_p2g, 'n_used': used, 'touched_nodes': g_t}
+            'algorithmic_bytes_per_launch': p2g_bytes, 'launch_ms': t_p2g, 'n_used': used, 'touched_nodes': g_t, 'timing': timing_note}
     roof_pair = {'kernels': 'k_p2g+k_g2p', 'achieved': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9,
                  'frac': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9 / peak, 'p2g_ms': t_p2g, 'g2p_ms': t_g2p, 'grid_op_ms': t_gop,
-                 'bytes': p2g_bytes + g2p_bytes}
+                 'bytes': p2g_bytes + g2p_bytes, 'p2g_ms_by_steps_since_sort': sort_age}
 
     # ------------------------------------------------------------------ forward+backward (BASELINE metric, second half)
     fb = None

@@ -800,3 +800,57 @@ def test_full_size_directional_derivative_c2():
     ballistic = float((w.astype(np.float64) * u).sum()) * 10 * 2e-4
     assert abs(an) > 0.1 * abs(ballistic) > 1.0, (an, ballistic)
     assert abs(fd - an) < 5e-3 * abs(an), (fd, an, ballistic)
+
+
+@pytest.mark.parametrize('N', [1, 31, 33, 129])
+def test_ragged_particle_counts(N):
+    """particle counts that are not multiples of the warp / CTA sizes (1, 31, 33, 129): 20 substeps forward + the adjoint of one
+    substep against the oracle; every lane / tail guard of the kernels is exercised."""
+    _need_gpu()
+    rng = np.random.RandomState(100 + N)
+    n_grid = 16
+    P = make_particles(rng.uniform(0.35, 0.65, size=(N, 3)), M.ELASTIC if N % 2 else M.WATER, n_grid)
+    o, s = build_pair(P, n_grid, boundary=dict(type='cube', lower=(0.2, 0.2, 0.2), upper=(0.8, 0.8, 0.8)), T=20, precision=64)
+    st = random_state(P, rng, amp_F=0.02, amp_C=1.0, amp_v=0.3)
+    set_both(o, s, st)
+    s.step(None); s.step(None)
+    for f in range(20):
+        o.substep(f)
+    a, b = s.get_state(), o.get_frame(20)
+    for k, tol in (('x', 1e-5), ('v', 1e-4), ('F', 1e-5)):
+        assert rel(a[k], b[k]) < tol, (k, rel(a[k], b[k]))
+    g = {k: rng.randn(*st[k].shape).astype(np.float32) for k in ('x', 'v', 'C', 'F')}
+    set_both(o, s, st)
+    s.cur_substep_global = 0
+    s.substep(0, True); o.substep(0)
+    s.cur_substep_global = 1
+    o.reset_grad(); o.set_grad_frame(1, g['x'], g['v'], g['C'], g['F'])
+    s.reset_grad(); s.set_grad(g['x'], g['v'], g['C'], g['F'])
+    o.substep_grad(0)
+    s.cur_substep_global = 0
+    s.substep_grad(0, True)
+    og, gg = o.get_grad_frame(0), s.get_grad()
+    for k in ('x', 'v', 'C', 'F'):
+        assert rel(gg[k], og[k]) < 1e-4, (k, rel(gg[k], og[k]))
+
+
+def test_no_used_particles_and_no_particles():
+    """all slots parked (used = 0): the substep is the identity copy (process_unused_particles, MPM:309-316) and the adjoint passes
+    through; particles=None builds an agent-only simulator whose step only advances the counters (has_particles False, MPM:61-67)."""
+    _need_gpu()
+    from fluidlab_b200 import MPMSimulator
+    N, n_grid = 200, 16
+    P = make_particles(np.tile(np.array(M.NOWHERE), (N, 1)), M.MILK, n_grid, used=np.zeros(N, np.int32))
+    s = MPMSimulator(dim=3, quality=n_grid / 64, gravity=(0.0, -10.0, 0.0), horizon=100, max_substeps_local=20, max_substeps_global=100000, ckpt_dest='gpu')
+    s.build(None, None, [], P)
+    st0 = s.get_state()
+    s.step(None)
+    st1 = s.get_state()
+    for k in ('x', 'v', 'C', 'F', 'used'):
+        assert np.array_equal(st0[k], st1[k]), k
+    s2 = MPMSimulator(dim=3, quality=n_grid / 64, gravity=(0.0, -10.0, 0.0), horizon=100, max_substeps_local=20, max_substeps_global=100000, ckpt_dest='gpu')
+    s2.build(None, None, [], None)
+    assert not s2.has_particles and s2.n_particles == 0
+    s2.step(None)
+    assert s2.cur_substep_global == 10
+    assert s2.get_x().shape == (0, 3) and s2.get_state() == {}
