@@ -148,7 +148,7 @@ def main():
     ap.add_argument('--particles', type=int, default=N_PARTICLES)
     ap.add_argument('--bwd', type=int, default=1, help='also time forward+backward (extra keys)')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--sort-every', type=int, default=2, help='cell-sort period in steps (measured: 1 -> 6.59k, 2 -> 6.75k, 4 -> 6.70k substeps/s)')
+    ap.add_argument('--sort-every', type=int, default=4, help='cell-sort period in steps (measured with the warp-local key ranking: 1 -> 7.14k, 2 -> 7.43k, 4 -> 7.60k, 8 -> 7.44k substeps/s)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -297,10 +297,11 @@ def main():
         t_g2p = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
         g_t = int(np.mean(gts))
         if args.sort_every > 1:   # how much the scatter slows down as the cell sort ages (steps since the last sort: 0, 1, ...)
-            per_age = [[] for _ in range(args.sort_every)]
+            per_age = [[[], []] for _ in range(args.sort_every)]
             for j, e in enumerate(evs):
-                per_age[((W + j // SUBSTEPS_PER_STEP) % args.sort_every)].append(e[0].elapsed_time(e[1]))
-            sort_age = [float(np.mean(a)) for a in per_age if a]
+                age = (W + j // SUBSTEPS_PER_STEP) % args.sort_every
+                per_age[age][0].append(e[0].elapsed_time(e[1])); per_age[age][1].append(e[2].elapsed_time(e[3]))
+            sort_age = {'p2g': [float(np.mean(a[0])) for a in per_age if a[0]], 'g2p': [float(np.mean(a[1])) for a in per_age if a[1]]}
         timing_note = f'mean over the {len(evs)} substeps of a replay of the timed trajectory (CUDA events between the launches)'
     else:
         t_p2g = time_phase(lambda: sim.phase('p2g', f, 0), pre=lambda: sim.phase('clear_grid', f))
@@ -325,7 +326,7 @@ def main():
             'algorithmic_bytes_per_launch': p2g_bytes, 'launch_ms': t_p2g, 'n_used': used, 'touched_nodes': g_t, 'timing': timing_note}
     roof_pair = {'kernels': 'k_p2g+k_g2p', 'achieved': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9,
                  'frac': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9 / peak, 'p2g_ms': t_p2g, 'g2p_ms': t_g2p, 'grid_op_ms': t_gop,
-                 'bytes': p2g_bytes + g2p_bytes, 'p2g_ms_by_steps_since_sort': sort_age}
+                 'bytes': p2g_bytes + g2p_bytes, 'ms_by_steps_since_sort': sort_age}
 
     # ------------------------------------------------------------------ forward+backward (BASELINE metric, second half)
     fb = None

@@ -122,9 +122,30 @@ __device__ __forceinline__ void window_move(Window& W, const int key, float4* __
 }
 
 // lane = particle.  key < 0: the particle contributes nothing (unused / out of grid / beyond N).
-// Returns the mask of staged positions at which a new cell run starts.  ALL 32 lanes must call.
+// The 32 records are staged in ascending key order (stable counting rank inside the warp, one warp-uniform pass per distinct
+// key), so the node-mode pass sees every cell of the warp as ONE run even when the global cell sort is a few substeps old
+// (particles that changed cell since the last sort would otherwise split their neighbours' runs: each split costs a 27-node
+// flush).  With a fresh sort rank == lane.  Returns the mask of staged positions at which a new cell run starts.
+// ALL 32 lanes must call.
 __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int lane, const int key, const int carry_key, const float* q,
                                                     const float* B, const float m, const float w[3][3]) {
+  const bool valid = key >= 0;
+  const int skey = valid ? key : 0x7fffffff;   // particles without a cell go last and add zeros to the last run
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned remaining = SC_FULL, starts = 0u;
+  int base = 0, rank = 0, prevk = carry_key, mykey = carry_key;
+  while (remaining != 0u) {   // warp-uniform: ascending distinct keys
+    const bool pend = (remaining >> lane) & 1u;
+    const int kmin = __reduce_min_sync(SC_FULL, pend ? skey : 0x7fffffff);
+    const unsigned grp = __ballot_sync(SC_FULL, pend && skey == kmin);
+    if (kmin != 0x7fffffff) {
+      if (kmin != prevk) starts |= 1u << base;
+      prevk = kmin;
+    }
+    if (pend && skey == kmin) { rank = base + __popc(grp & lt); mykey = prevk; }
+    base += __popc(grp);
+    remaining &= ~grp;
+  }
 #pragma unroll
   for (int a = 0; a < 3; a++) {
     const float fa = (float)a;
@@ -132,29 +153,20 @@ __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int la
 #pragma unroll
     for (int b = 0; b < 3; b++) {
       const float fb = (float)b;
-      S.rec[lane * SC_REC + a * 3 + b] = make_float4(fmaf(fb, B[1], qa0), fmaf(fb, B[4], qa1), fmaf(fb, B[7], qa2), m);
+      S.rec[rank * SC_REC + a * 3 + b] = make_float4(fmaf(fb, B[1], qa0), fmaf(fb, B[4], qa1), fmaf(fb, B[7], qa2), m);
     }
   }
-  S.rec[lane * SC_REC + 9] = make_float4(B[2], B[5], B[8], 0.f);
-  const bool valid = key >= 0;
+  S.rec[rank * SC_REC + 9] = make_float4(B[2], B[5], B[8], 0.f);
 #pragma unroll
   for (int a = 0; a < 3; a++)
 #pragma unroll
     for (int b = 0; b < 3; b++) {
       const float wab = valid ? w[a][0] * w[b][1] : 0.f;
 #pragma unroll
-      for (int c = 0; c < 3; c++) S.w[(a * 9 + b * 3 + c) * SC_WSTR + lane] = valid ? wab * w[c][2] : 0.f;
+      for (int c = 0; c < 3; c++) S.w[(a * 9 + b * 3 + c) * SC_WSTR + rank] = valid ? wab * w[c][2] : 0.f;
     }
-  // effective key: a particle without a cell inherits the key of the nearest earlier one (it adds zeros to that run)
-  const unsigned V = __ballot_sync(SC_FULL, valid);
-  const unsigned below = V & (0xffffffffu >> (31 - lane));
-  const int src = below ? 31 - __clz(below) : 0;
-  const int ksrc = __shfl_sync(SC_FULL, key, src);
-  const int keff = below ? ksrc : carry_key;
-  int prev = __shfl_up_sync(SC_FULL, keff, 1);
-  if (lane == 0) prev = carry_key;
-  S.key[lane] = keff;
-  return __ballot_sync(SC_FULL, keff != prev);
+  S.key[rank] = mykey;
+  return starts;
 }
 
 // lane = stencil node.  Consumes the 32 staged particles (positions >= cnt carry zero weights, see scatter_publish) in fixed
