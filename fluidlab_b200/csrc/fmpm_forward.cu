@@ -39,11 +39,29 @@
 // p2g
 // =============================================================================================
 struct PRaw { float4 a0, a1, a2, a3, f0, f1; float f8; };
+#ifndef FMPM_STREAM_HINTS
+#define FMPM_STREAM_HINTS 2   // >= 1: particle planes of frame f are read with ld.global.cs (evict-first); >= 2: F[f+1] is written with st.global.cs.  A/B: 134.7 -> 134.1 -> 133.0 us per substep
+#endif
+#if FMPM_STREAM_HINTS
+#define P2G_LD(p) __ldcs(p)
+#else
+#define P2G_LD(p) (*(p))
+#endif
+// F[f+1] is next read one whole substep (>200 MB of traffic) later: with FMPM_STREAM_HINTS >= 2 it is written evict-first
+__device__ __forceinline__ void p2g_store_F(const KParams& P, const int f, const int s, const Mat3& F) {
+#if FMPM_STREAM_HINTS >= 2
+  __stcs(&P.pf[pf_idx(P, f, 0, s)], make_float4(F.m[0], F.m[1], F.m[2], F.m[3]));
+  __stcs(&P.pf[pf_idx(P, f, 1, s)], make_float4(F.m[4], F.m[5], F.m[6], F.m[7]));
+  __stcs(&P.pf8[pf8_idx(P, f, s)], F.m[8]);
+#else
+  store_F(P.pf, P.pf8, P, f, s, F);
+#endif
+}
 __device__ __forceinline__ void p2g_load_raw(const KParams& P, const int f, const long long sl, PRaw& R) {
   if (sl < P.N) {
     const int s = (int)sl;
-    R.a0 = P.pa[pa_idx(P, f, 0, s)]; R.a1 = P.pa[pa_idx(P, f, 1, s)]; R.a2 = P.pa[pa_idx(P, f, 2, s)]; R.a3 = P.pa[pa_idx(P, f, 3, s)];
-    R.f0 = P.pf[pf_idx(P, f, 0, s)]; R.f1 = P.pf[pf_idx(P, f, 1, s)]; R.f8 = P.pf8[pf8_idx(P, f, s)];
+    R.a0 = P2G_LD(&P.pa[pa_idx(P, f, 0, s)]); R.a1 = P2G_LD(&P.pa[pa_idx(P, f, 1, s)]); R.a2 = P2G_LD(&P.pa[pa_idx(P, f, 2, s)]); R.a3 = P2G_LD(&P.pa[pa_idx(P, f, 3, s)]);
+    R.f0 = P2G_LD(&P.pf[pf_idx(P, f, 0, s)]); R.f1 = P2G_LD(&P.pf[pf_idx(P, f, 1, s)]); R.f8 = P2G_LD(&P.pf8[pf8_idx(P, f, s)]);
   } else {
     R.a0 = make_float4(0.f, 0.f, 0.f, 0.f);  // meta = 0 -> unused
   }
@@ -109,9 +127,9 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
 #pragma unroll
         for (int i = 0; i < 3; i++) q[i] = m * st.v[i] - (B[i * 3] * fx[0] + B[i * 3 + 1] * fx[1] + B[i * 3 + 2] * fx[2]);
         key = pack_key(b);
-        if (kWriteF) store_F(P.pf, P.pf8, P, f + 1, s, K.Fn);
+        if (kWriteF) p2g_store_F(P, f + 1, s, K.Fn);
       } else if (kWriteF) {
-        store_F(P.pf, P.pf8, P, f + 1, s, st.F);  // process_unused_particles (MPM:316) / frozen out-of-grid particle
+        p2g_store_F(P, f + 1, s, st.F);  // process_unused_particles (MPM:316) / frozen out-of-grid particle
       }
     }
     const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
