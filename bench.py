@@ -401,7 +401,7 @@ def main():
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},
-            'gpu_launches': K * (SUBSTEPS_PER_STEP * 3 + (2 if args.sort_every else 0)),
+            'gpu_launches': K * SUBSTEPS_PER_STEP * 3 + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
             'roofline': roof, 'roofline_p2g_g2p': roof_pair,
             'fwd_bwd': fb,
             'cpu_baseline': cpu,
