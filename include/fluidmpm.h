@@ -23,7 +23,8 @@
  *                                         plane2=(C01,C02,C10,C11) plane3=(C12,C20,C21,C22)
  *              pf : float4[(T+1)][2][N]  (F00,F01,F02,F10) (F11,F12,F20,F21)
  *              pf8: float [(T+1)][N]     F22
- *  meta (int bits in plane0.w): bit0 = used (MPM:86-88), bits 8..15 = row of the material table.
+ *  meta (int bits in plane0.w): bit0 = used (MPM:86-88), bit1 = collected at this substep (fmpm_collect, transient),
+ *              bits 8..15 = row of the material table, bits 16..23 = body id (MPM:96-103; used by fmpm_advect_rigid).
  *  grads       ga/gf/gf8 : same planar layout, 2 frames (ping-pong: index 0/1).
  *  grid        grid_pm : float4[G] (momentum xyz, mass)   — MPM:112-114 v_in, mass
  *              grid_v  : float4[G] (v_out xyz, unused)     — MPM:115
