@@ -84,8 +84,78 @@ def latte_mini():
                         loss32=loss32, loss64=loss64, grad32=grad32, grad64=grad64)
 
 
+def rigid_pour_scene():
+    """everything a Pouring / Gathering scene exercises at once: WATER pool + one MAT_RIGID cuboid (shape matching, MPM:449-505) + an
+    elastic blob, a 6-DOF Rigid box collider at grid AND particle level (AgentPouring, 'both') and the collector."""
+    from conftest import box_sdf
+    rng = np.random.RandomState(103)
+    n_grid = 32
+    xw = rng.uniform((0.38, 0.30, 0.38), (0.62, 0.40, 0.62), size=(2500, 3))
+    xr = rng.uniform((0.42, 0.42, 0.44), (0.52, 0.48, 0.52), size=(700, 3))
+    xe = rng.uniform((0.53, 0.42, 0.50), (0.60, 0.50, 0.58), size=(500, 3))
+    x = np.concatenate([xw, xr, xe]).astype(np.float32)
+    mat = np.concatenate([np.full(len(xw), M.WATER), np.full(len(xr), M.RIGID), np.full(len(xe), M.ELASTIC)]).astype(np.int32)
+    bid = np.concatenate([np.zeros(len(xw)), np.ones(len(xr)), np.full(len(xe), 2)]).astype(np.int32)
+    vox, Tm = box_sdf(np.array([0.10, 0.04, 0.07]), 0.2)
+    cfg = dict(n_grid=n_grid, n_steps=2, T=20, x0=x, mat=mat, body_id=bid,
+               bnd=dict(type='cube', lower=(0.25, 0.25, 0.25), upper=(0.75, 0.75, 0.75)),
+               ebnd=dict(type='cube', lower=(0.05, 0.05, 0.05), upper=(0.95, 0.95, 0.95)),
+               cbnd=dict(type='cube', lower=(0.0, 0.0, 0.0), upper=(1.0, 1.0, 0.605)),
+               vox=vox.astype(np.float32), Tm=Tm.astype(np.float64), friction=float(M.FRICTION[M.STIRRER]), softness=100.0,
+               init=np.array([0.5, 0.56, 0.5, np.cos(0.15), 0.0, np.sin(0.15), 0.0, 0.0]),
+               actions=np.array([[0.004, -0.035, 0.002, 0.02, -0.03, 0.05], [-0.003, -0.035, 0.004, -0.04, 0.02, 0.03]], dtype=np.float32),
+               action_p=np.array([0.5, 0.56, 0.5, 0, 0, 0], dtype=np.float32),
+               tgt=rng.uniform(0.4, 0.6, size=(2,) + x.shape).astype(np.float32))
+    return cfg
+
+
+def run_rigid_pour(cfg, prec, threads=1):
+    P = make_particles(cfg['x0'], cfg['mat'], int(cfg['n_grid']))
+    N = len(cfg['x0'])
+    orc.lib().orc_set_threads(threads)
+    o = orc.OracleSim(int(cfg['n_grid']), P, gravity=(0, -10, 0), boundary=cfg['bnd'], max_substeps_local=int(cfg['T']), precision=prec)
+    o.set_bodies(cfg['body_id'], 3)
+    o.add_effector(type=0, action_dim=6, scale_v=(1,) * 6, boundary=cfg['ebnd'], max_action_steps=int(cfg['n_steps']) + 1)
+    o.set_rigid_mesh(cfg['vox'], cfg['Tm'], friction=cfg['friction'], softness=cfg['softness'], collide_type='both')
+    o.set_collector(cfg['cbnd'], mat=-1)
+    o.enable_grad()
+    o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+    o.set_effector_state(0, 0, cfg['init']); o.apply_action_p(cfg['action_p'])
+    loss = 0.0
+    n_steps = int(cfg['n_steps'])
+    for i in range(n_steps):
+        o.step(cfg['actions'][i]); loss += o.loss_value(o.cur_substep_local, M.WATER, 1.0, cfg['tgt'][i])
+    fr = o.get_frame(o.cur_substep_local)
+    o.reset_grad()
+    for i in range(n_steps - 1, -1, -1):
+        o.loss_seed(o.cur_substep_local, M.WATER, 1.0, cfg['tgt'][i]); o.step_grad(cfg['actions'][i])
+    o.apply_action_p_grad()
+    return fr, loss, o.get_action_grad(n_steps)
+
+
+def rigid_pour():
+    cfg = rigid_pour_scene()
+    fr, loss32, grad32 = run_rigid_pour(cfg, 32)
+    f64, loss64, grad64 = run_rigid_pour(cfg, 64)
+    flat = {k: v for k, v in cfg.items() if not isinstance(v, dict)}
+    for name in ('bnd', 'ebnd', 'cbnd'):
+        flat[name + '_lower'] = cfg[name]['lower']; flat[name + '_upper'] = cfg[name]['upper']
+    np.savez_compressed(os.path.join(HERE, 'rigid_pour_n32.npz'), **flat,
+                        x=fr['x'].astype(np.float32), v=fr['v'].astype(np.float32), F=fr['F'].astype(np.float32), used=fr['used'],
+                        x64=f64['x'], v64=f64['v'], F64=f64['F'], used64=f64['used'],
+                        loss32=loss32, loss64=loss64, grad32=grad32, grad64=grad64)
+
+
+def load_rigid_pour(path):
+    d = dict(np.load(path))
+    for name in ('bnd', 'ebnd', 'cbnd'):
+        d[name] = dict(type='cube', lower=tuple(d.pop(name + '_lower')), upper=tuple(d.pop(name + '_upper')))
+    d['friction'] = float(d['friction']); d['softness'] = float(d['softness'])
+    return d
+
+
 if __name__ == '__main__':
-    multimat(); latte_mini()
+    multimat(); latte_mini(); rigid_pour()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))
