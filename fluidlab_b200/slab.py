@@ -135,12 +135,13 @@ class SlabMPMSimulator:
     """Forward MLS-MPM over x-slabs: one local `MPMSimulator` per rank + ghost exchange + migration."""
 
     def __init__(self, quality, gravity, particles, gid, bounds, capacity, boundary=None, max_substeps_local=50, device=None, group=None, halo=4,
-                 exchange='peer'):
+                 exchange='peer', migrate=True):
         from .simulator import MPMSimulator
         from .macros import NOWHERE
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
+        self.migrate_enabled = bool(migrate)   # False: diagnostics only (particles must then stay inside their ghost range)
         n_loc = len(particles['x'])
         assert capacity >= n_loc
         pad = capacity - n_loc
@@ -248,7 +249,7 @@ class SlabMPMSimulator:
 
     def step(self):
         sim = self.sim
-        if self.world > 1 and not os.environ.get('SLAB_NO_MIGRATE'):
+        if self.world > 1 and self.migrate_enabled:
             self._migrate()
         sim.sort_frame(sim.cur_substep_local)
         for _ in range(sim.n_substeps):
