@@ -854,3 +854,62 @@ def test_no_used_particles_and_no_particles():
     s2.step(None)
     assert s2.cur_substep_global == 10
     assert s2.get_x().shape == (0, 3) and s2.get_state() == {}
+
+
+def test_c3_latteart_two_material_fwd_bwd_full_size():
+    """BASELINE.json configs[2] at FULL particle count and grid (262,144 slots = 62,144 parked MILK + 200,000 COFFEE, 128^3, cylinder
+    boundary r = 0.42, gravity -20, Injector with flux 8), with the horizon shortened to 3 steps over a T = 20 ring
+    (30 substeps, one checkpoint boundary) so that the fp64 oracle finishes in seconds: loss and dLoss/dAction (4 x 3) through
+    TaichiEnv's step / step_grad against the oracle."""
+    _need_gpu()
+    from fluidlab_b200 import TaichiEnv, LatteArtLoss
+    from oracle import oracle as orc
+    n_grid, n_coffee, n_milk, flux, n_steps, T = 128, 200_000, 62_144, 8, 3, 20
+    rs = np.random.RandomState(0)
+    acc = []
+    while sum(len(a) for a in acc) < n_coffee:   # rejection sampling in draw order (SURVEY.md §8d C3)
+        c = rs.uniform((0.08, 0.50, 0.08), (0.92, 0.60, 0.92), size=(100_000, 3))
+        acc.append(c[(c[:, 0] - 0.5) ** 2 + (c[:, 2] - 0.5) ** 2 <= 0.42 ** 2])
+    xc = np.concatenate(acc)[:n_coffee]
+    x = np.concatenate([np.tile(M.NOWHERE, (n_milk, 1)), xc])
+    mat = np.concatenate([np.full(n_milk, M.MILK), np.full(n_coffee, M.COFFEE)])
+    used = np.concatenate([np.zeros(n_milk), np.ones(n_coffee)]).astype(np.int32)
+    P = make_particles(x, mat, n_grid, used=used)
+    N = len(x)
+    ebnd = dict(type='cylinder', xz_radius=0.42, xz_center=(0.5, 0.5), y_range=(0.65, 0.65))
+    bnd = dict(type='cylinder', xz_radius=0.42, xz_center=(0.5, 0.5), y_range=(0.5, 0.95))
+    env = TaichiEnv(quality=2, max_substeps_local=T, gravity=(0.0, -20.0, 0.0), horizon=n_steps)
+    np.random.seed(0)
+    env.setup_agent(dict(type='AgentInjector', effectors=[dict(type='Injector', params=dict(
+        radius=0.0075, flux=flux, init_pos=(0.5, 0.5, 0.5), action_dim=3, inject_v=(0.0, -3.0, 0.0), locally_random=True), boundary=ebnd)]))
+    env.particle_bodies.get = lambda: P
+    env.setup_boundary(**bnd)
+    tgt = [rs.uniform(0.3, 0.7, size=x.shape).astype(np.float32) for _ in range(n_steps)]
+    env.setup_loss(loss_cls=LatteArtLoss, type='diff', target=tgt, weights={'chamfer': 1.0})
+    env.build()
+    inj = env.agent.effectors[0]
+    acts, init_p = latteart_demo_actions()
+    actions = acts[:n_steps].astype(np.float32)
+    action_p = init_p.astype(np.float32)
+    fr, info, grad = _run_env_fwd_bwd(env, actions, action_p)
+    o = orc.OracleSim(n_grid, P, gravity=(0, -20, 0), boundary=bnd, precision=64, max_substeps_local=T)
+    o.add_effector(type=1, action_dim=3, boundary=ebnd, radius=0.0075, flux=flux, inject_v=(0, -3, 0), inject_p=(0, 0, 0), locally_random=True,
+                   random_vector=inj.random_vector_np, act_range=np.where(used == 0)[0], max_action_steps=n_steps + 1)
+    o.enable_grad()
+    o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+    o.set_effector_state(0, 0, np.array([0.5, 0.5, 0.5, 1, 0, 0, 0, 0.0])); o.apply_action_p(action_p)
+    total = 0.0
+    for i in range(n_steps):
+        o.step(actions[i]); total += o.loss_value(o.cur_substep_local, M.MILK, 1.0, tgt[i])
+    ofr = o.get_frame(o.cur_substep_local)
+    o.reset_grad()
+    for i in range(n_steps - 1, -1, -1):
+        o.loss_seed(o.cur_substep_local, M.MILK, 1.0, tgt[i]); o.step_grad(actions[i])
+    o.apply_action_p_grad()
+    g64 = o.get_action_grad(n_steps)
+    assert np.array_equal(fr['used'], ofr['used']) and int(fr['used'].sum()) == n_coffee + flux * 10 * n_steps
+    act = fr['used'] != 0
+    assert rel(fr['x'][act], ofr['x'][act]) < 1e-5 and rel(fr['F'][act], ofr['F'][act]) < 1e-5
+    assert abs(info['loss'] - total) <= 1e-5 * abs(total), (info['loss'], total)
+    assert grad.shape == g64.shape == (n_steps + 1, 3) and np.abs(g64).max() > 1e-3
+    assert rel(grad, g64) < 1e-4, (rel(grad, g64), grad, g64)
