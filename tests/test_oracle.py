@@ -495,3 +495,67 @@ def test_6dof_injector_and_collector_dloss_daction_fd():
             return _pose_loss(sim, P, a, ap, wts, n_steps, init)[0]
         fd = (run(eps) - run(-eps)) / (2 * eps)
         assert abs(fd - g[i, j]) <= 1e-4 * max(1.0, abs(fd), np.abs(g).max()), (i, j, fd, g[i, j])
+
+
+# ------------------------------------------------------------------------------------------------
+# symmetry pins of the restatement (nothing pins it to the real reference: PARITY UNPINNED), fp64
+# ------------------------------------------------------------------------------------------------
+def _sym_run(x, v, C, F, mat, n_grid, gravity, boundary, n_sub=6):
+    P = make_particles(x, mat, n_grid)
+    sim = orc.OracleSim(n_grid, P, gravity=gravity, boundary=boundary, precision=64, max_substeps_local=10)
+    sim.set_frame(0, x, v, C, F, P['used'])
+    for f in range(n_sub):
+        sim.substep(f)
+    return sim.get_frame(n_sub)
+
+
+def _sym_state(rng, N, lo, hi):
+    x = rng.uniform(lo, hi, size=(N, 3))
+    return x, rng.randn(N, 3) * 0.4, rng.randn(N, 3, 3) * 2.0, np.eye(3)[None] + rng.randn(N, 3, 3) * 0.02
+
+
+@pytest.mark.parametrize("mat", [M.WATER, M.ELASTIC, M.ICECREAM])
+def test_particle_order_does_not_matter(mat):
+    rng = np.random.RandomState(61)
+    n_grid, N = 16, 200
+    bnd = dict(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.7, 0.7, 0.7))
+    x, v, C, F = _sym_state(rng, N, 0.36, 0.64)
+    a = _sym_run(x, v, C, F, mat, n_grid, (0, -10, 0), bnd)
+    perm = rng.permutation(N)
+    b = _sym_run(x[perm], v[perm], C[perm], F[perm], mat, n_grid, (0, -10, 0), bnd)
+    for k in ('x', 'v', 'C', 'F'):
+        assert np.abs(a[k][perm] - b[k]).max() < 1e-11 * max(1.0, np.abs(a[k]).max()), k
+
+
+@pytest.mark.parametrize("mat", [M.WATER, M.ELASTIC])
+def test_grid_aligned_translation_equivariance(mat):
+    """shifting particles AND walls by whole cells shifts the result by the same vector (base / fx / weights / boundary logic)"""
+    rng = np.random.RandomState(62)
+    n_grid, N = 32, 200
+    dx = 1.0 / n_grid
+    shift = np.array([3, -2, 5]) * dx
+    lo, hi = np.array([0.3, 0.3, 0.3]), np.array([0.6, 0.6, 0.6])
+    x, v, C, F = _sym_state(rng, N, 0.34, 0.56)
+    a = _sym_run(x, v, C, F, mat, n_grid, (0, -10, 0), dict(type='cube', lower=tuple(lo), upper=tuple(hi)))
+    b = _sym_run(x + shift, v, C, F, mat, n_grid, (0, -10, 0), dict(type='cube', lower=tuple(lo + shift), upper=tuple(hi + shift)))
+    assert np.abs(a['x'] + shift - b['x']).max() < 1e-9      # wall positions are rounded to f32 first (boundaries.py:99-104)
+    for k in ('v', 'C', 'F'):
+        assert np.abs(a[k] - b[k]).max() < 1e-6 * max(1.0, np.abs(a[k]).max()), k
+
+
+@pytest.mark.parametrize("mat", [M.WATER, M.ELASTIC, M.PLASTIC_DEMO])
+def test_axis_permutation_equivariance(mat):
+    """relabelling the axes (x,y,z) -> (z,x,y), with gravity and walls relabelled too, relabels the result: no axis is special in
+    p2g / grid_op / g2p / SVD / F-update (catches transposed C or F conventions and swapped stencil indices)"""
+    rng = np.random.RandomState(63)
+    n_grid, N = 16, 200
+    x, v, C, F = _sym_state(rng, N, 0.36, 0.64)
+    g = np.array([1.0, -10.0, 3.0])
+    lo, hi = np.array([0.30, 0.32, 0.28]), np.array([0.70, 0.66, 0.72])
+    a = _sym_run(x, v, C, F, mat, n_grid, tuple(g), dict(type='cube', lower=tuple(lo), upper=tuple(hi)))
+    p = [2, 0, 1]                      # new axis i = old axis p[i]
+    Pm = np.eye(3)[p]                  # y = Pm @ x
+    rot = lambda Mx: np.einsum('ij,njk,lk->nil', Pm, Mx, Pm)
+    b = _sym_run(x[:, p], v[:, p], rot(C), rot(F), mat, n_grid, tuple(g[p]), dict(type='cube', lower=tuple(lo[p]), upper=tuple(hi[p])))
+    assert np.abs(a['x'][:, p] - b['x']).max() < 1e-11 and np.abs(a['v'][:, p] - b['v']).max() < 1e-9
+    assert np.abs(rot(a['C']) - b['C']).max() < 1e-8 and np.abs(rot(a['F']) - b['F']).max() < 1e-10
