@@ -692,10 +692,10 @@ def _momentum(st, mass):
     return (st['v'].astype(np.float64) * (mass * u)[:, None]).sum(0)
 
 
-@pytest.mark.parametrize('cfg', ['C2', 'C4'])
+@pytest.mark.parametrize('cfg', ['C2', 'C4', 'C5'])
 def test_full_size_conservation_invariants(cfg):
-    """BASELINE.json configs[1] (C2: 1M WATER, 128^3) and configs[3] (C4: 1M ELASTIC + 1M ICECREAM, 192^3) at FULL size, where the
-    oracle is too slow: size-independent properties of MLS-MPM (SURVEY.md §8c pins 2).
+    """BASELINE.json configs[1] (C2: 1M WATER, 128^3), configs[3] (C4: 1M ELASTIC + 1M ICECREAM, 192^3) and configs[4] on ONE GPU
+    (C5: 8M WATER, 256^3) at FULL size, where the oracle is too slow: size-independent properties of MLS-MPM (SURVEY.md §8c pins 2).
       * p2g of a stress-free state (F = I, C = 0): sum of grid mass = sum of particle mass, grid momentum = particle momentum;
       * 30 free-flight substeps (no wall contact): internal forces cancel, so total momentum changes by exactly M g t;
       * the cell-sorted, CUDA-graph step path reproduces the per-substep path bit for bit apart from summation order (1e-6)."""
@@ -705,6 +705,9 @@ def test_full_size_conservation_invariants(cfg):
     if cfg == 'C2':
         n_grid, g = 128, (0.0, -10.0, 0.0)
         x = rs.uniform((0.25, 0.30, 0.25), (0.75, 0.54, 0.75), size=(1_000_000, 3)); mat = np.full(len(x), M.WATER)
+    elif cfg == 'C5':
+        n_grid, g = 256, (0.0, -10.0, 0.0)
+        x = rs.uniform((0.10, 0.20, 0.10), (0.90, 0.42, 0.90), size=(8_000_000, 3)); mat = np.full(len(x), M.WATER)
     else:
         n_grid, g = 192, (0.0, -10.0, 0.0)
         xa = rs.uniform((0.20, 0.30, 0.30), (0.45, 0.55, 0.70), size=(1_000_000, 3))
@@ -715,8 +718,8 @@ def test_full_size_conservation_invariants(cfg):
     mass = P['mass']
 
     def build(sort_every, graphs):
-        s = MPMSimulator(dim=3, quality=n_grid / 64, gravity=g, horizon=100, max_substeps_local=50, max_substeps_global=100000, ckpt_dest='gpu',
-                         sort_every=sort_every)
+        s = MPMSimulator(dim=3, quality=n_grid / 64, gravity=g, horizon=100, max_substeps_local=50 if cfg != 'C5' else 20, max_substeps_global=100000,
+                         ckpt_dest='gpu', sort_every=sort_every)
         s.use_graphs = graphs
         s.build(None, None, [], P)
         return s
@@ -736,7 +739,7 @@ def test_full_size_conservation_invariants(cfg):
     # ---- momentum balance in free flight.  C4 note: ELASTIC at 192^3 with the reference's fixed dt = 2e-4 has
     # c dt / dx = sqrt((lam + 2 mu) / rho) * 2e-4 * 192 = 1.27 > 1 (explicit MPM is unstable there, any velocity noise explodes
     # within ~30 substeps, in the reference too) -> C4 runs one step from rest; C2 runs three steps with random velocities.
-    n_steps = 3 if cfg == 'C2' else 1
+    n_steps = {'C2': 3, 'C4': 1, 'C5': 1}[cfg]
     if cfg == 'C4':
         v0 = np.zeros_like(v0); scale = M_tot
         st['v'][:] = 0.0; s.cur_substep_global = 0; s.set_state(0, st)
