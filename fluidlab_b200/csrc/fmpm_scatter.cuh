@@ -79,10 +79,12 @@ __device__ __forceinline__ void window_flush_node(const Window& W, float4* __res
   if (W.peer_r != nullptr && W.plane >= W.gr_lo && W.plane < W.gr_hi) red_add_v4(W.peer_r + W.node, v);
   if (W.peer_l != nullptr && W.plane >= W.gl_lo && W.plane < W.gl_hi) red_add_v4(W.peer_l + W.node, v);
 }
-// flag the 8^3-node block of this lane's node (test before write: the flag words are shared by every SM)
+// flag the 8^3-node block of this lane's node.  Plain store, no test-before-write: the ncu source page of the round-1 kernel
+// (profiles/README.md) charged 16 % of all stall samples to the ISETP waiting for that flag load, while the store is
+// fire-and-forget (same-address lanes coalesce; ~1e5 32-byte L2 writes per launch against 1.7e6 vector reductions).
 __device__ __forceinline__ void window_flag(const Window& W, const int i, const int j, const int k) {
   const int blk = ((i >> 3) * W.nb + (j >> 3)) * W.nb + (k >> 3);
-  if (W.flags[blk] == 0) W.flags[blk] = 1;
+  W.flags[blk] = 1;
   // x-slab mode: the neighbour must visit (and later clear) the blocks this rank reduces into over NVLink
   if (W.peer_fr != nullptr && i >= W.gr_lo && i < W.gr_hi) W.peer_fr[blk] = 1;
   if (W.peer_fl != nullptr && i >= W.gl_lo && i < W.gl_hi) W.peer_fl[blk] = 1;
