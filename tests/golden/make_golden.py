@@ -154,8 +154,57 @@ def load_rigid_pour(path):
     return d
 
 
+def c1_scene():
+    """BASELINE.json configs[0] / SURVEY.md §8d C1: LatteArt-v0 default scene (envs/latteart_env.py:28-74, agent_latteart.yaml) with the
+    host classes of fluidlab_b200 (no CUDA needed): 60,000 parked MILK + 55,480 COFFEE, cylinder boundary, Injector with flux 2, the
+    scripted pour.  The injector's random table is the first draw after np.random.seed(0), exactly as in the GPU test."""
+    from fluidlab_b200.bodies import Bodies
+    from test_gpu_parity import latteart_demo_actions
+    b = Bodies(dim=3, particle_density=1e6)
+    b.add_body(type='nowhere', n_particles=60000, material=M.MILK)
+    b.add_body(type='cylinder', center=(0.5, 0.55, 0.5), height=0.1, radius=0.42, material=M.COFFEE)
+    Pb = b.get()
+    rv = np.random.RandomState(0).uniform(size=(50, 2, 3)).astype(np.float32)
+    acts, init_p = latteart_demo_actions()
+    return Pb, rv, acts, init_p
+
+
+def run_c1(prec, n_steps=10):
+    Pb, rv, acts, init_p = c1_scene()
+    P = make_particles(Pb['x'], Pb['mat'], 64, used=Pb['used'].astype(np.int32))
+    bnd = dict(type='cylinder', xz_radius=0.42, xz_center=(0.5, 0.5), y_range=(0.5, 0.95))
+    orc.lib().orc_set_threads(orc.lib().orc_get_max_threads())
+    o = orc.OracleSim(64, P, gravity=(0, -20, 0), boundary=bnd, precision=prec, max_substeps_local=50)
+    o.add_effector(type=1, action_dim=3, boundary=dict(type='cylinder', xz_radius=0.42, xz_center=(0.5, 0.5), y_range=(0.65, 0.65)), radius=0.0075, flux=2,
+                   inject_v=(0, -3, 0), inject_p=(0, 0, 0), locally_random=True, random_vector=rv, act_range=np.where(P['used'] == 0)[0], max_action_steps=331)
+    o.set_effector_state(0, 0, np.array([0.5, 0.5, 0.5, 1, 0, 0, 0, 0.0])); o.apply_action_p(init_p)
+    for i in range(n_steps):
+        o.step(acts[i])
+    return o.get_frame(o.cur_substep_local), P
+
+
+def c1_sample_ids(used):
+    """first 48 used COFFEE slots + the 16 most recently injected MILK slots (slot order [milk..., coffee...])"""
+    coffee = np.where(used[60000:] != 0)[0][:48] + 60000
+    milk = np.where(used[:60000] != 0)[0][-16:]
+    return np.concatenate([milk, coffee])
+
+
+def c1_latteart():
+    """SURVEY.md §8c substitute pin 4: C1 after 100 substeps — 64 particles verbatim + checksums over all used particles."""
+    fr, P = run_c1(32)
+    f64, _ = run_c1(64)
+    ids = c1_sample_ids(fr['used'])
+    act = fr['used'] != 0
+    cs = lambda a: np.array([a[act].astype(np.float64).sum(), np.abs(a[act].astype(np.float64)).sum(), (a[act].astype(np.float64) ** 2).sum()])
+    np.savez_compressed(os.path.join(HERE, 'c1_latteart_100sub.npz'), ids=ids, n_used=int(act.sum()),
+                        x=fr['x'][ids].astype(np.float32), v=fr['v'][ids].astype(np.float32), F=fr['F'][ids].astype(np.float32),
+                        x64=f64['x'][ids], v64=f64['v'][ids], F64=f64['F'][ids],
+                        cs_x=cs(f64['x']), cs_v=cs(f64['v']), cs_F=cs(f64['F']), cs_x32=cs(fr['x']), cs_v32=cs(fr['v']), cs_F32=cs(fr['F']))
+
+
 if __name__ == '__main__':
-    multimat(); latte_mini(); rigid_pour()
+    multimat(); latte_mini(); rigid_pour(); c1_latteart()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

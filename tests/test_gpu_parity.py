@@ -337,6 +337,16 @@ def test_c1_latteart_v0_full_size_100_substeps():
     assert rel(a['v'][act], b['v'][act]) < 1e-4, rel(a['v'][act], b['v'][act])
     assert np.array_equal(a['x'][~act], b['x'][~act].astype(np.float32))  # parked milk untouched at NOWHERE
     assert np.allclose(a['agent'][0][:7], o.effector_state(0, o.cur_substep_local)[:7], atol=1e-6)
+    # committed golden of the same scene (tests/golden/c1_latteart_100sub.npz: 64 particles verbatim + checksums, fp32 and fp64 oracle)
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'c1_latteart_100sub.npz'))
+    ids = g['ids']
+    assert int(act.sum()) == int(g['n_used'])
+    for k, bar in (('x', 1e-5), ('v', 1e-4), ('F', 1e-5)):
+        assert rel(a[k][ids], g[k + '64']) < max(bar, 3 * rel(g[k], g[k + '64'])), (k, rel(a[k][ids], g[k + '64']))
+        aa = a[k][act].astype(np.float64)
+        cs = np.array([np.abs(aa).sum(), (aa ** 2).sum()])
+        assert np.allclose(cs, g['cs_' + k][1:], rtol=2e-3 if k == 'v' else 1e-4), (k, cs, g['cs_' + k])
 
 
 @pytest.mark.parametrize('collide_type,softness,with_static', [('particle', 100.0, False), ('both', 100.0, True), ('grid', 0.0, True)])
