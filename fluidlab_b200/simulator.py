@@ -417,7 +417,7 @@ class MPMSimulator:
         return self._pm_ring is not None
 
     def _graph_substeps(self):
-        """Forward substeps of one step (p2g / compaction / grid_op / g2p x n_substeps, no agent) as a captured CUDA graph, one per
+        """Forward substeps of one step (p2g / grid_op / g2p x n_substeps, no agent) as a captured CUDA graph, one per
         local step index (frame pointers are baked into the kernel arguments).  Returns False if capture is unavailable."""
         if not hasattr(self, '_graphs'):
             self._graphs = {}
