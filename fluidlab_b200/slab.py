@@ -72,12 +72,16 @@ def centre_plane(x, inv_dx):
     return (x[:, 0] * inv_dx - 0.5).to(torch.int32) + 1
 
 
-def migrate(state, lo, hi, rank, world, inv_dx, group=None):
+def migrate(state, lo, hi, rank, world, inv_dx, group=None, record=None):
     """Move particles whose centre plane left [lo, hi) to the neighbouring rank.
 
     state: dict of tensors in slot order — x (N,3), v (N,3), C (N,3,3), F (N,3,3) float32; used, mrow, gid (N,) int32.
     Modified in place (leavers become unused, arrivals fill unused slots).  Returns (n_sent, n_received).
-    One host synchronisation per call (counts); called once per step (10 substeps)."""
+    One host synchronisation per call (counts); called once per step (10 substeps).
+    record: optional dict that receives {'sent': {peer: slots}, 'recv': {peer: slots}} — what `migrate_grad` needs to send the
+    adjoint of every arrival back to the slot its particle left (the backward pass over x-slabs)."""
+    if record is not None:
+        record['sent'], record['recv'] = {}, {}
     if world == 1:
         return 0, 0
     x, used = state['x'], state['used']
@@ -97,6 +101,8 @@ def migrate(state, lo, hi, rank, world, inv_dx, group=None):
     for peer, m in masks.items():
         idx = torch.nonzero(m).reshape(-1)
         send[peer] = pack(idx).contiguous()
+        if record is not None:
+            record['sent'][peer] = idx.clone()
         used[idx] = 0
         state['x'][idx] = -100.0  # NOWHERE (configs/macros.py:216)
     # exchange counts, then payloads
@@ -124,11 +130,43 @@ def migrate(state, lo, hi, rank, world, inv_dx, group=None):
         free = torch.nonzero(used == 0).reshape(-1)
         assert free.numel() >= total_in, f'rank {rank}: slab capacity exhausted ({free.numel()} free slots, {total_in} arrivals)'
         dst = free[:total_in]
+        if record is not None:
+            o = 0
+            for p in sorted(recv):
+                record['recv'][p] = dst[o:o + n_in[p]].clone(); o += n_in[p]
         state['x'][dst] = rows[:, 0:3]; state['v'][dst] = rows[:, 3:6]
         state['C'][dst] = rows[:, 6:15].reshape(-1, 3, 3); state['F'][dst] = rows[:, 15:24].reshape(-1, 3, 3)
         state['mrow'][dst] = rows[:, 24].contiguous().view(torch.int32); state['gid'][dst] = rows[:, 25].contiguous().view(torch.int32)
         used[dst] = 1
     return sum(s.shape[0] for s in send.values()), total_in
+
+
+def migrate_grad(gstate, record, group=None):
+    """Adjoint of `migrate` on the particle adjoints: gstate = dict x (N,3), v (N,3), C (N,3,3), F (N,3,3) in the slot order AFTER the
+    migration that filled `record`; on return it is in the slot order BEFORE it.  The adjoint rows of every arrival travel back to the
+    rank and slot the particle left (its slot here held a parked particle before: zero adjoint), no counts need to be exchanged.
+    Unused slots are assumed to carry zero adjoint (the loss only reads used particles)."""
+    sent, recvd = record.get('sent', {}), record.get('recv', {})
+    if not sent and not recvd:
+        return
+
+    def pack(idx):
+        return torch.cat([gstate['x'][idx], gstate['v'][idx], gstate['C'][idx].reshape(-1, 9), gstate['F'][idx].reshape(-1, 9)], 1).contiguous()
+    dev = gstate['x'].device
+    out = {p: pack(idx) for p, idx in recvd.items() if idx.numel() > 0}
+    back = {p: torch.empty((idx.numel(), 24), dtype=torch.float32, device=dev) for p, idx in sent.items() if idx.numel() > 0}
+    ops = [dist.P2POp(dist.isend, out[p], p, group) for p in out] + [dist.P2POp(dist.irecv, back[p], p, group) for p in back]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for p, idx in recvd.items():
+        if idx.numel() > 0:
+            for k in ('x', 'v', 'C', 'F'):
+                gstate[k][idx] = 0
+    for p, rows in back.items():
+        idx = sent[p]
+        gstate['x'][idx] = rows[:, 0:3]; gstate['v'][idx] = rows[:, 3:6]
+        gstate['C'][idx] = rows[:, 6:15].reshape(-1, 3, 3); gstate['F'][idx] = rows[:, 15:24].reshape(-1, 3, 3)
 
 
 class SlabMPMSimulator:

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fluidlab_b200.slab import slab_bounds, GhostExchange, migrate, centre_plane
+from fluidlab_b200.slab import slab_bounds, GhostExchange, migrate, migrate_grad, centre_plane
 
 
 def _free_port():
@@ -105,3 +105,39 @@ def test_migration_moves_leavers_and_conserves_particles():
             assert np.array_equal(a['x'][i], x0) and np.array_equal(a['v'][i], v0) and np.array_equal(a['F'][i], F0) and int(a['mrow'][i]) == m0
     assert set(seen) == set(allb)
     assert out[0][2] == out[1][3] and out[1][2] == out[0][3] and out[0][2] + out[1][2] > 0
+
+
+def _migrate_adjoint_job(rank, world):
+    """<M u, w> on the used slots after the migration == <u, M^T w> on the used slots before it (summed over ranks)"""
+    n, inv_dx, bounds = 32, 32.0, [0, 16, 32]
+    rng = np.random.RandomState(17 + rank)
+    N = 64
+    x = rng.uniform(0.1, 0.9, size=(N, 3)).astype(np.float32)
+    used = np.ones(N, np.int32); used[48:] = 0; x[48:] = -100.0
+    f32 = lambda a: torch.from_numpy(a.astype(np.float32))
+    st = dict(x=torch.from_numpy(x.copy()), v=f32(rng.randn(N, 3)), C=f32(rng.randn(N, 3, 3)), F=f32(rng.randn(N, 3, 3)), used=torch.from_numpy(used.copy()),
+              mrow=torch.from_numpy(np.arange(N, dtype=np.int32) % 3), gid=torch.from_numpy(np.arange(N, dtype=np.int32) + 1000 * rank))
+    u = {k: st[k].clone().double() for k in ('x', 'v', 'C', 'F')}
+    used_before = st['used'].clone()
+    rec = {}
+    n_out, n_in = migrate(st, bounds[rank], bounds[rank + 1], rank, world, inv_dx, record=rec)
+    used_after = st['used'] != 0
+    w = {k: f32(rng.randn(*st[k].shape)) for k in ('x', 'v', 'C', 'F')}
+    for k in w:
+        w[k][~used_after] = 0
+    lhs = sum((st[k].double()[used_after] * w[k].double()[used_after]).sum() for k in w)
+    g = {k: w[k].clone() for k in w}
+    migrate_grad(g, rec)
+    ub = used_before != 0
+    assert all(float(g[k][~ub].abs().max()) == 0.0 for k in g), 'adjoint leaked into a slot that was parked before the migration'
+    rhs = sum((u[k][ub] * g[k].double()[ub]).sum() for k in g)
+    t = torch.tensor([float(lhs), float(rhs)], dtype=torch.float64)
+    dist.all_reduce(t)
+    return float(t[0]), float(t[1]), n_out, n_in
+
+
+def test_migrate_grad_is_the_adjoint_of_migrate():
+    out = _run(_migrate_adjoint_job)
+    lhs, rhs = out[0][0], out[0][1]
+    assert out[0][2] + out[1][2] > 0, 'nothing migrated'
+    assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs)), (lhs, rhs)
