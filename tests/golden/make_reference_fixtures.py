@@ -1,0 +1,170 @@
+"""Fixtures produced by the REAL reference code (run in the build container only; /root/reference does not exist on the GPU box).
+
+The host-side, NumPy-only parts of zhouxian/FluidLab that feed the hot path — the material tables of `fluidlab/configs/macros.py` and
+the particle samplers of `fluidlab/fluidengine/bodies/bodies.py` — import fine once `taichi` (used there only for a dtype alias) and the
+rendering / mesh dependencies are stubbed.  This script runs them UNMODIFIED and stores what `fluidlab_b200.macros` / `fluidlab_b200.bodies`
+must reproduce: the tables verbatim and, per sampled body, the particle count, three checksums and the first / last 16 rows.
+(The Taichi kernels themselves cannot run: the simulation path stays pinned by the oracle only)
+
+    python tests/golden/make_reference_fixtures.py        # writes tests/golden/reference_host_fixtures.npz
+"""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get('FLUIDLAB_REFERENCE', '/root/reference')
+
+# every sampler configuration the shipped envs use (envs/*.py add_body calls), plus the natural fillings
+BODY_CASES = [
+    ('latteart_coffee', dict(type='cylinder', center=(0.5, 0.55, 0.5), height=0.1, radius=0.42, material='COFFEE')),
+    ('nowhere', dict(type='nowhere', n_particles=1000, material='MILK')),
+    ('cube_random', dict(type='cube', lower=(0.2, 0.3, 0.2), upper=(0.45, 0.5, 0.6), material='WATER')),
+    ('cube_size_grid', dict(type='cube', lower=(0.3, 0.3, 0.3), size=(0.2, 0.1, 0.15), material='ELASTIC', filling='grid')),
+    ('cube_natural_euler', dict(type='cube', lower=(0.45, 0.45, 0.45), size=(0.1, 0.1, 0.1), euler=(45.0, 45.0, 45.0), material='RIGID_HEAVY', filling='natural')),
+    ('cylinder_natural', dict(type='cylinder', center=(0.5, 0.4, 0.5), height=0.12, radius=0.2, material='WATER', filling='natural')),
+    ('cylinder_grid', dict(type='cylinder', center=(0.5, 0.4, 0.5), height=0.12, radius=0.2, material='WATER', filling='grid')),
+    ('ball_random', dict(type='ball', center=(0.5, 0.5, 0.5), radius=0.1, material='ICECREAM')),
+    ('ball_natural', dict(type='ball', center=(0.4, 0.6, 0.5), radius=0.07, material='WATER', filling='natural')),
+    ('cube_euler_random', dict(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.5, 0.4, 0.5), euler=(0.0, -75.0, 10.0), material='ELASTIC')),
+]
+TABLES = ('MU', 'LAMDA', 'RHO', 'MAT_CLASS', 'FRICTION')
+
+
+MESH_CASES = [   # (name, baked sdf pickle, pos, euler, scale): the shipped collider configs (envs/configs/agent_*.yaml, envs/*_env.py add_static)
+    ('stirrer', 'stirrer-128.sdf', (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (0.6, 0.4, 0.6)),
+    ('cone_tip', 'cone_tip-128.sdf', (0.0, 0.0, 0.0), (-90.0, 0.0, 30.0), (0.726, 0.726, 0.726)),
+    ('glass', 'glass-128.sdf', (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (0.75, 0.65, 0.75)),
+    ('laddle', 'laddle-128.sdf', (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (0.35, 0.45, 0.35)),
+    ('static_tank', 'bowl-128.sdf', (0.5, 0.4, 0.5), (0.0, 45.0, 10.0), (1.2, 0.8, 1.2)),
+]
+EFFECTOR_CASES = [   # constructor kwargs of effectors/effector.py:18-52 and effectors/injector.py:12-60,220-240 (no Taichi arithmetic involved)
+    ('injector_local', 'Injector', dict(radius=0.0075, flux=2, init_pos=(0.5, 0.5, 0.5), init_euler=(10.0, 20.0, 30.0), action_dim=3, inject_v=(0.0, -3.0, 0.0),
+                                        locally_random=True)),
+    ('injector_global', 'Injector', dict(radius=0.015, flux=4, init_pos=(0.5, 0.8, 0.5), init_euler=(0.0, 0.0, 0.0), action_dim=6, inject_v=(-3.0, 0.0, 0.0),
+                                         inject_p=(-0.07, 0.0, 0.0), locally_random=False)),
+    ('ball_injector', 'BallInjector', dict(radius=0.035, flux=4, init_pos=(0.5, 0.6, 0.5), action_dim=3, inject_v=(0.0, -0.4, 0.0), locally_random=True)),
+]
+EFFECTOR_COMMON = dict(max_substeps_local=50, max_substeps_global=400, max_action_steps_global=40, ckpt_dest='cpu')
+
+
+def load_reference():
+    class _Obj:   # stands in for every Taichi object (fields, vectors, decorators); fields remember what from_numpy() received
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            if len(a) == 1 and not k and callable(a[0]) and not isinstance(a[0], _Obj):
+                return a[0]          # decorator use: @ti.kernel, @ti.func, @ti.data_oriented
+            return _Obj()
+
+        def __getattr__(self, k):
+            if k.startswith('__'):
+                raise AttributeError(k)
+            o = _Obj(); object.__setattr__(self, k, o); return o
+
+        def from_numpy(self, a):
+            object.__setattr__(self, 'np_value', np.array(a))
+
+        def __getitem__(self, k):
+            return _Obj()
+
+        def __setitem__(self, k, v):
+            pass
+
+        def __iter__(self):
+            return iter(())
+
+    class _Stub(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith('__'):
+                raise AttributeError(k)
+            o = _Obj(); setattr(self, k, o); return o
+    ti = _Stub('taichi'); ti.f32, ti.f64, ti.i32 = 'f32', 'f64', 'i32'
+    sys.modules['taichi'] = ti
+    for name in ('trimesh', 'yacs', 'yacs.config', 'gym', 'gym.spaces', 'mesh_to_sdf', 'skimage', 'skimage.measure', 'matplotlib', 'matplotlib.pyplot',
+                 'imageio', 'pyrender', 'open3d', 'cv2'):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = _Stub(name)
+    sys.path.insert(0, REF)
+    macros = importlib.import_module('fluidlab.configs.macros')
+    spec = importlib.util.spec_from_file_location('ref_bodies', os.path.join(REF, 'fluidlab/fluidengine/bodies/bodies.py'))
+    bodies = importlib.util.module_from_spec(spec); spec.loader.exec_module(bodies)
+    return macros, bodies
+
+
+def summarize(x):
+    x = np.asarray(x, dtype=np.float64)
+    return dict(n=len(x), cs=np.array([x.sum(), np.abs(x).sum(), (x * np.arange(1, x.size + 1).reshape(x.shape)).sum()]), head=x[:16].copy(), tail=x[-16:].copy())
+
+
+def main():
+    RM, RB = load_reference()
+    out = {}
+    names = [k for k in dir(RM) if k.isupper() and isinstance(getattr(RM, k), int) and k not in ('DTYPE_NP',)]
+    out['int_names'] = np.array(names); out['int_values'] = np.array([getattr(RM, k) for k in names], dtype=np.int64)
+    for t in TABLES:
+        tab = getattr(RM, t)
+        keys = sorted(tab)
+        out[f'tab_{t}_keys'] = np.array(keys, dtype=np.int64); out[f'tab_{t}_vals'] = np.array([tab[k] for k in keys], dtype=np.float64)
+    out['NOWHERE'] = np.array(RM.NOWHERE, dtype=np.float64); out['EPS'] = np.float64(RM.EPS)
+    np.random.seed(12345)   # the samplers re-seed to 0 internally and must restore this state
+    for name, kw in BODY_CASES:
+        kw = dict(kw); kw['material'] = getattr(RM, kw['material'])
+        b = RB.Bodies(dim=3, particle_density=1e6)
+        b.add_body(**kw)
+        g = b.get()
+        s = summarize(g['x'])
+        out[f'body_{name}_n'] = s['n']; out[f'body_{name}_cs'] = s['cs']; out[f'body_{name}_head'] = s['head']; out[f'body_{name}_tail'] = s['tail']
+        out[f'body_{name}_used'] = int(np.asarray(g['used']).sum()); out[f'body_{name}_rho'] = float(np.asarray(g['rho'])[0])
+    out['rng_after'] = np.random.uniform(size=4)   # the global RNG stream must be untouched by add_body
+    # two bodies in one container: ids and concatenation order
+    b = RB.Bodies(dim=3, particle_density=1e6)
+    b.add_body(type='nowhere', n_particles=60000, material=RM.MILK)
+    b.add_body(type='cylinder', center=(0.5, 0.55, 0.5), height=0.1, radius=0.42, material=RM.COFFEE)
+    g = b.get()
+    out['latteart_n'] = len(g['x']); out['latteart_used'] = int(np.asarray(g['used']).sum())
+    out['latteart_body_id_counts'] = np.bincount(np.asarray(g['body_id']).astype(np.int64))
+    # meshes: the reference's own Mesh.init_transform (meshes/mesh.py:97-127) composes T_mesh_to_voxels <- T_file @ inv(T_init); run it on an
+    # instance that carries only what those lines read (vertices / colours are rendering data and replaced by one dummy vertex)
+    import pickle as pkl
+    mesh_mod = importlib.import_module('fluidlab.fluidengine.meshes.mesh')
+    for name, fn, pos, euler, scale in MESH_CASES:
+        path = os.path.join(REF, 'fluidlab/assets/meshes/processed', fn)
+        if not os.path.exists(path):
+            continue
+        sdf = pkl.load(open(path, 'rb'))
+        m = mesh_mod.Mesh.__new__(mesh_mod.Mesh)
+        m.scale, m.pos, m.euler = scale, pos, np.array(euler)   # what Mesh.__init__ stores (meshes/mesh.py:16-39, eval_str'ed tuples)
+        m.raw_vertices = np.zeros((1, 3), np.float32); m.raw_vertex_normals_np = np.zeros((1, 3), np.float32)
+        m.faces_np = np.zeros(3, np.int32); m.colors_np = np.zeros((1, 4), np.float32); m.n_vertices, m.n_faces = 1, 3
+        m.has_dynamics = True
+        m.sdf_voxels_np = sdf['voxels'].astype(np.float32); m.T_mesh_to_voxels_np = sdf['T_mesh_to_voxels'].astype(np.float32)
+        m.init_transform()
+        out[f'mesh_{name}_T_file'] = np.asarray(sdf['T_mesh_to_voxels'], dtype=np.float64)
+        out[f'mesh_{name}_T'] = np.asarray(m.T_mesh_to_voxels_np, dtype=np.float64)
+        out[f'mesh_{name}_res'] = int(sdf['voxels'].shape[0]); out[f'mesh_{name}_vox_cs'] = np.float64(np.asarray(sdf['voxels'], dtype=np.float64).sum())
+    # effectors: initial pose quaternion (scipy 'zyx' euler convention, effector.py:40-44) and the injectors' pre-drawn random tables
+    inj = importlib.import_module('fluidlab.fluidengine.effectors.injector')
+    for name, cls, kw in EFFECTOR_CASES:
+        np.random.seed(777)
+        e = getattr(inj, cls)(**EFFECTOR_COMMON, **kw)
+        out[f'eff_{name}_init_state'] = np.asarray(e.init_state, dtype=np.float64)
+        rv = getattr(e, 'random_vector_np', None)
+        if rv is None or isinstance(rv, list):
+            rv = e.random_vector.np_value
+        out[f'eff_{name}_rv_shape'] = np.array(rv.shape); out[f'eff_{name}_rv_head'] = np.asarray(rv, dtype=np.float64).reshape(-1, 3)[:24]
+        out[f'eff_{name}_rv_sum'] = np.float64(np.asarray(rv, dtype=np.float64).sum())
+        out[f'eff_{name}_rng_after'] = np.random.uniform(size=2)
+    np.savez_compressed(os.path.join(HERE, 'reference_host_fixtures.npz'), **out)
+    print('wrote', os.path.getsize(os.path.join(HERE, 'reference_host_fixtures.npz')), 'bytes;', {k: int(out[f'body_{k}_n']) for k, _ in BODY_CASES})
+
+
+if __name__ == '__main__':
+    main()

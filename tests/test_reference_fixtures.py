@@ -1,0 +1,87 @@
+"""Host-side pieces pinned against the REAL reference: `tests/golden/reference_host_fixtures.npz` was produced by running the
+unmodified `fluidlab/configs/macros.py` and `fluidlab/fluidengine/bodies/bodies.py` of zhouxian/FluidLab
+(tests/golden/make_reference_fixtures.py, build container only).  fluidlab_b200.macros / fluidlab_b200.bodies must reproduce them."""
+import os
+import sys
+import numpy as np
+
+from fluidlab_b200 import macros as M
+from fluidlab_b200.bodies import Bodies
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+sys.path.insert(0, G)
+D = np.load(os.path.join(G, 'reference_host_fixtures.npz'))
+
+
+def test_material_tables_equal_the_reference_macros():
+    for name, val in zip(D['int_names'], D['int_values']):
+        name = str(name)
+        if hasattr(M, name) and isinstance(getattr(M, name), int):
+            assert getattr(M, name) == int(val), name
+    for must in ('WATER', 'ELASTIC', 'MILK', 'COFFEE', 'ICECREAM', 'RIGID', 'RIGID_HEAVY', 'MAT_LIQUID', 'MAT_ELASTIC', 'MAT_RIGID', 'MAT_PLASTO_ELASTIC'):
+        assert hasattr(M, must), must
+    for t in ('MU', 'LAMDA', 'RHO', 'MAT_CLASS', 'FRICTION'):
+        tab = getattr(M, t)
+        for k, v in zip(D[f'tab_{t}_keys'], D[f'tab_{t}_vals']):
+            assert float(tab[int(k)]) == float(v), (t, int(k), tab[int(k)], v)
+        assert len(tab) == len(D[f'tab_{t}_keys']), t
+    assert list(M.NOWHERE) == list(D['NOWHERE'])
+
+
+def test_samplers_reproduce_the_reference_particle_sets():
+    import make_reference_fixtures as mk
+    np.random.seed(12345)
+    for name, kw in mk.BODY_CASES:
+        kw = dict(kw); kw['material'] = getattr(M, kw['material'])
+        b = Bodies(dim=3, particle_density=1e6)
+        b.add_body(**kw)
+        g = b.get()
+        s = mk.summarize(g['x'])
+        assert s['n'] == int(D[f'body_{name}_n']), (name, s['n'])
+        assert int(np.asarray(g['used']).sum()) == int(D[f'body_{name}_used']) and float(np.asarray(g['rho'])[0]) == float(D[f'body_{name}_rho']), name
+        for k in ('head', 'tail'):
+            assert np.abs(s[k] - D[f'body_{name}_{k}']).max() <= 1e-15 * max(1.0, np.abs(s[k]).max()), (name, k)
+        assert np.allclose(s['cs'], D[f'body_{name}_cs'], rtol=1e-13, atol=1e-9), (name, s['cs'], D[f'body_{name}_cs'])
+    assert np.array_equal(np.random.uniform(size=4), D['rng_after']), 'add_body must leave the global NumPy RNG stream untouched'
+    b = Bodies(dim=3, particle_density=1e6)
+    b.add_body(type='nowhere', n_particles=60000, material=M.MILK)
+    b.add_body(type='cylinder', center=(0.5, 0.55, 0.5), height=0.1, radius=0.42, material=M.COFFEE)
+    g = b.get()
+    assert len(g['x']) == int(D['latteart_n']) == 115480 and int(np.asarray(g['used']).sum()) == int(D['latteart_used']) == 55480
+    assert np.array_equal(np.bincount(np.asarray(g['body_id']).astype(np.int64)), D['latteart_body_id_counts'])
+
+
+def test_effector_initial_pose_and_injector_random_tables_equal_the_reference():
+    """initial pose (scipy 'zyx' euler -> wxyz quaternion, effectors/effector.py:40-52) and the random tables the injectors draw from the
+    global NumPy RNG at construction (effectors/injector.py:54-60, 220-240) — values AND RNG-stream consumption."""
+    import make_reference_fixtures as mk
+    from fluidlab_b200 import effectors as E
+    for name, cls, kw in mk.EFFECTOR_CASES:
+        np.random.seed(777)
+        e = getattr(E, cls)(**mk.EFFECTOR_COMMON, **kw)
+        assert np.allclose(np.asarray(e.init_state, dtype=np.float64)[:7], D[f'eff_{name}_init_state'][:7], rtol=0, atol=1e-7), name
+        rv = np.asarray(e.random_vector_np)
+        assert list(rv.shape) == list(D[f'eff_{name}_rv_shape']), name
+        assert np.array_equal(rv.astype(np.float32).reshape(-1, 3)[:24], D[f'eff_{name}_rv_head'].astype(np.float32)), name
+        assert abs(float(rv.astype(np.float64).sum()) - float(D[f'eff_{name}_rv_sum'])) < 1e-6 * rv.size, name
+        assert np.array_equal(np.random.uniform(size=2), D[f'eff_{name}_rng_after']), (name, 'RNG stream consumption differs')
+
+
+def test_mesh_transform_equals_the_reference_init_transform():
+    """T_mesh_to_voxels <- T_file @ inv(trans_quat_to_T(pos, quat) @ scale_to_T(scale)) as the reference's own Mesh.init_transform
+    (meshes/mesh.py:97-127) evaluates it in float32 for the shipped collider configs; fluidlab_b200.meshes.Mesh must give the same 4x4."""
+    import make_reference_fixtures as mk
+    from fluidlab_b200.meshes import Static
+    n = 0
+    for name, fn, pos, euler, scale in mk.MESH_CASES:
+        if f'mesh_{name}_T' not in D.files:
+            continue
+        res = int(D[f'mesh_{name}_res'])
+        m = Static(file=fn.replace('-128.sdf', '.obj'), material=M.CUP, pos=pos, euler=euler, scale=scale, has_dynamics=True,
+                   sdf=dict(voxels=np.zeros((2, 2, 2), np.float32), T_mesh_to_voxels=D[f'mesh_{name}_T_file']))
+        ref = D[f'mesh_{name}_T']
+        err = np.abs(np.asarray(m.T_mesh_to_voxels_np, dtype=np.float64) - ref).max() / np.abs(ref).max()
+        assert err < 2e-6, (name, err)        # both sides are float32 matrix products / inverses (different LAPACK call order)
+        assert res == 128
+        n += 1
+    assert n >= 4
