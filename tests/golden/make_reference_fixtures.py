@@ -99,6 +99,70 @@ def load_reference():
     return macros, bodies
 
 
+TRACE_T, TRACE_ACTIONS = 20, [[0.1, 0.0, 0.0], [0.0, 0.2, 0.0], [0.0, 0.0, 0.3], None, None]   # 5 steps over a 2-step ring: two wrap-arounds
+
+
+class TraceAgent:
+    """records the calls the simulator's step / step_grad / checkpoint logic makes on its agent (agents/agent.py API)"""
+
+    def __init__(self, trace, sim_ref):
+        self.trace, self.sim_ref = trace, sim_ref
+
+    def _ev(self, name, *args):
+        self.trace.append([name, int(self.sim_ref().cur_substep_global)] + [None if a is None else int(a) for a in args])
+
+    def set_action(self, s, s_global, n_substeps, action):
+        self._ev('agent.set_action', s, s_global, n_substeps)
+
+    def set_action_grad(self, s, s_global, n_substeps, action):
+        self._ev('agent.set_action_grad', s, s_global, n_substeps)
+
+    def copy_frame(self, a, b):
+        self._ev('agent.copy_frame', a, b)
+
+    def copy_grad(self, a, b):
+        self._ev('agent.copy_grad', a, b)
+
+    def reset_grad_till_frame(self, f):
+        self._ev('agent.reset_grad_till_frame', f)
+
+    def get_ckpt(self, ckpt_name=None):
+        self._ev('agent.get_ckpt')
+        return {}
+
+    def set_ckpt(self, ckpt=None, ckpt_name=None):
+        self._ev('agent.set_ckpt')
+
+
+def drive(sim):
+    """the call sequence of optimizer/solver.py:23-59 at simulator level: forward all steps, then backward in reverse order"""
+    sim.enable_grad()
+    for a in TRACE_ACTIONS:
+        sim.step(None if a is None else np.array(a, dtype=np.float32))
+    for a in reversed(TRACE_ACTIONS):
+        sim.step_grad(None if a is None else np.array(a, dtype=np.float32))
+
+
+def reference_step_trace():
+    """run the REAL MPMSimulator.step / step_ / step_grad / memory_to_cache / memory_from_cache (MPM:721-912) with every Taichi kernel
+    replaced by a recorder: the orchestration (ring indices, checkpoint names, re-simulation, agent calls) is pure Python."""
+    sim_mod = importlib.import_module('fluidlab.fluidengine.simulators.mpm_simulator')
+    S = sim_mod.MPMSimulator
+    trace = []
+    sim = S(dim=3, quality=0.25, gravity=(0.0, -10.0, 0.0), horizon=10, max_substeps_local=TRACE_T, max_substeps_global=1000, ckpt_dest='cpu')
+    rec = lambda name: (lambda *a, **k: trace.append([name, int(sim.cur_substep_global)] + [int(v) if isinstance(v, (int, np.integer)) else None for v in a[:2]]))
+    sim.substep = lambda f, none: trace.append(['substep', int(sim.cur_substep_global), int(f), int(bool(none))])
+    sim.substep_grad = lambda f, none: trace.append(['substep_grad', int(sim.cur_substep_global), int(f), int(bool(none))])
+    for name in ('copy_frame', 'copy_grad', 'reset_grad_till_frame', 'readframe', 'setframe'):
+        setattr(sim, name, rec(name))
+    import weakref
+    agent = TraceAgent(trace, weakref.ref(sim))
+    n = 4
+    sim.build(agent, None, [], dict(x=np.full((n, 3), 0.5), used=np.ones(n), mat=np.zeros(n), rho=np.ones(n), body_id=np.zeros(n), bodies={'n': 1}))
+    drive(sim)
+    return trace
+
+
 def summarize(x):
     x = np.asarray(x, dtype=np.float64)
     return dict(n=len(x), cs=np.array([x.sum(), np.abs(x).sum(), (x * np.arange(1, x.size + 1).reshape(x.shape)).sum()]), head=x[:16].copy(), tail=x[-16:].copy())
@@ -162,6 +226,8 @@ def main():
         out[f'eff_{name}_rv_shape'] = np.array(rv.shape); out[f'eff_{name}_rv_head'] = np.asarray(rv, dtype=np.float64).reshape(-1, 3)[:24]
         out[f'eff_{name}_rv_sum'] = np.float64(np.asarray(rv, dtype=np.float64).sum())
         out[f'eff_{name}_rng_after'] = np.random.uniform(size=2)
+    import json
+    out['step_trace_json'] = np.array(json.dumps(reference_step_trace()))
     np.savez_compressed(os.path.join(HERE, 'reference_host_fixtures.npz'), **out)
     print('wrote', os.path.getsize(os.path.join(HERE, 'reference_host_fixtures.npz')), 'bytes;', {k: int(out[f'body_{k}_n']) for k, _ in BODY_CASES})
 

@@ -85,3 +85,38 @@ def test_mesh_transform_equals_the_reference_init_transform():
         assert res == 128
         n += 1
     assert n >= 4
+
+
+def test_step_and_checkpoint_orchestration_equals_the_reference():
+    """The ring / checkpoint / re-simulation orchestration of MPMSimulator.step, step_, step_grad, memory_to_cache and memory_from_cache
+    (MPM:721-912) is pure Python: the fixture holds the event trace of the REAL reference code run with recorder kernels (5 steps over a
+    2-step ring, forward then backward).  fluidlab_b200.MPMSimulator — built without CUDA, kernels replaced by the same recorders — must
+    emit the same sequence of substeps, adjoint substeps, agent calls and frame-0 restarts, with the same global substep counters.
+    (Its particle adjoints live in a ping-pong pair, so the reference's particle copy_frame(0,T) / copy_grad / reset_grad_till_frame in
+    memory_from_cache have no counterpart and are filtered out.)"""
+    import json
+    import weakref
+    import torch
+    import make_reference_fixtures as mk
+    from fluidlab_b200.simulator import MPMSimulator, _IDENTITY
+    T = mk.TRACE_T
+    ref = json.loads(str(D['step_trace_json']))
+    keep = lambda e: (e[0] in ('substep', 'substep_grad') or e[0].startswith('agent.') or (e[0] == 'copy_frame' and e[2:4] == [T, 0]))
+    ref = [e for e in ref if keep(e)]
+    trace = []
+    sim = MPMSimulator.__new__(MPMSimulator)
+    sim.dim, sim.n_substeps, sim.max_substeps_local, sim.max_substeps_global, sim.horizon = 3, 10, T, 1000, 10
+    sim.ckpt_dest, sim.device = 'cpu', torch.device('cpu')
+    sim.has_particles, sim.smoke_field, sim.sort_every, sim.use_graphs, sim.store_grids = True, None, 0, False, False
+    sim.actions_buffer, sim.ckpt_ram, sim.cur_substep_global, sim.grad_enabled = [], {}, 0, False
+    sim._pa, sim._pf, sim._pf8 = torch.zeros((T + 1, 4, 4, 4)), torch.zeros((T + 1, 2, 4, 4)), torch.zeros((T + 1, 4))
+    sim._frame_ord = [_IDENTITY] * (T + 1)
+    sim._h = sim._lib = None
+    sim.substep = lambda f, none: trace.append(['substep', int(sim.cur_substep_global), int(f), int(bool(none))])
+    sim.substep_grad = lambda f, none: trace.append(['substep_grad', int(sim.cur_substep_global), int(f), int(bool(none))])
+    sim.copy_frame = lambda a, b: trace.append(['copy_frame', int(sim.cur_substep_global), int(a), int(b)])
+    sim.agent = mk.TraceAgent(trace, weakref.ref(sim))
+    mk.drive(sim)
+    assert len(trace) == len(ref), (len(trace), len(ref))
+    for i, (a, b) in enumerate(zip(trace, ref)):
+        assert a == b, (i, a, b)
