@@ -65,6 +65,8 @@ def load_reference():
         def __getattr__(self, k):
             if k.startswith('__'):
                 raise AttributeError(k)
+            if k == 'grad_for':          # @ti.ad.grad_for(fn) is a decorator FACTORY
+                return lambda *_: (lambda g: g)
             o = _Obj(); object.__setattr__(self, k, o); return o
 
         def from_numpy(self, a):
@@ -87,12 +89,13 @@ def load_reference():
     ti = _Stub('taichi'); ti.f32, ti.f64, ti.i32 = 'f32', 'f64', 'i32'
     sys.modules['taichi'] = ti
     for name in ('trimesh', 'yacs', 'yacs.config', 'gym', 'gym.spaces', 'mesh_to_sdf', 'skimage', 'skimage.measure', 'matplotlib', 'matplotlib.pyplot',
-                 'imageio', 'pyrender', 'open3d', 'cv2'):
+                 'imageio', 'pyrender', 'open3d', 'cv2', 'OpenGL', 'OpenGL.GL', 'pyglet'):
         try:
             importlib.import_module(name)
         except Exception:
             sys.modules[name] = _Stub(name)
     sys.path.insert(0, REF)
+    sys.modules['fluidlab.fluidengine.renderers.gl_renderer_src'] = _Stub('fluidlab.fluidengine.renderers.gl_renderer_src')   # compiled FleX binding
     macros = importlib.import_module('fluidlab.configs.macros')
     spec = importlib.util.spec_from_file_location('ref_bodies', os.path.join(REF, 'fluidlab/fluidengine/bodies/bodies.py'))
     bodies = importlib.util.module_from_spec(spec); spec.loader.exec_module(bodies)
@@ -141,6 +144,80 @@ def drive(sim):
         sim.step(None if a is None else np.array(a, dtype=np.float32))
     for a in reversed(TRACE_ACTIONS):
         sim.step_grad(None if a is None else np.array(a, dtype=np.float32))
+
+
+class Recorder:
+    """stand-in for simulator / agent / loss objects: every method call is appended to the shared trace"""
+
+    def __init__(self, name, trace):
+        object.__setattr__(self, '_name', name); object.__setattr__(self, '_trace', trace)
+
+    def __getattr__(self, k):
+        if k.startswith('__'):
+            raise AttributeError(k)
+
+        def call(*a, **kw):
+            args = [('arr%d' % np.asarray(v).size if v is not None and not isinstance(v, (int, float, bool, dict)) else (v if not isinstance(v, dict) else 'dict'))
+                    for v in list(a) + [kw[q] for q in sorted(kw)]]
+            self._trace.append([f'{self._name}.{k}'] + args)
+        return call
+
+    def __setattr__(self, k, v):
+        self._trace.append([f'{self._name}.{k}=', v if isinstance(v, (int, float, bool)) else 'obj'])
+
+    def __bool__(self):
+        return True
+
+
+def drive_env(env):
+    """optimizer/solver.py:23-59 at TaichiEnv level"""
+    a = np.array([0.1, 0.2, 0.3]); ap = np.array([0.5, 0.6, 0.5])
+    env.set_state({'x': 0}, grad_enabled=True)
+    env.apply_agent_action_p(ap)
+    for act in (a, a, None):
+        env.step(act)
+    env.get_final_loss()
+    env.reset_grad(); env.get_final_loss_grad()
+    for act in (None, a, a):
+        env.step_grad(act)
+    env.apply_agent_action_p_grad(ap)
+    env.set_state({'x': 0}, grad_enabled=False)
+    env.step(a)
+    env.get_state_RL()
+
+
+def make_env_with_recorders(cls, trace):
+    env = cls.__new__(cls)
+    env.simulator, env.agent, env.loss = Recorder('simulator', trace), Recorder('agent', trace), Recorder('loss', trace)
+    env.smoke_field, env.renderer, env.t = None, None, 0
+    return env
+
+
+def reference_env_trace():
+    te = importlib.import_module('fluidlab.fluidengine.taichi_env')
+    trace = []
+    drive_env(make_env_with_recorders(te.TaichiEnv, trace))
+    return trace
+
+
+def reference_temporal_range_schedule(losses):
+    """ShapeMatchingLoss.expand_temporal_range (losses/shapematching_loss.py:110-130), the reference's own code, fed a loss sequence"""
+    sm = importlib.import_module('fluidlab.fluidengine.losses.shapematching_loss')
+    L = sm.ShapeMatchingLoss.__new__(sm.ShapeMatchingLoss)
+    L.temporal_range_type, L.temporal_range, L.best_loss, L.plateau_count, L.inf = 'expand', [0, 50], 1e8, 0, 1e8
+    L.plateau_thresh, L.plateau_count_limit, L.temporal_expand_speed, L.max_loss_steps = [0.01, 0.5], 5, 50, 220
+    out = []
+    import io, contextlib
+    for v in losses:
+        L.total_loss = {None: float(v)}
+        with contextlib.redirect_stdout(io.StringIO()):
+            L.expand_temporal_range()
+        out.append([L.temporal_range[1], L.plateau_count, float(L.best_loss)])
+    return out
+
+
+LOSS_SEQUENCE = [100.0, 90.0, 89.5, 89.4, 89.39, 89.38, 89.37, 89.36, 120.0, 80.0, 79.9, 79.95, 79.9, 79.9, 79.9, 79.9, 300.0, 299.0, 299.0, 299.0,
+                 299.0, 299.0, 298.0, 100.0, 99.9, 99.9, 99.9, 99.9, 99.9, 99.9]
 
 
 def reference_step_trace():
@@ -228,6 +305,8 @@ def main():
         out[f'eff_{name}_rng_after'] = np.random.uniform(size=2)
     import json
     out['step_trace_json'] = np.array(json.dumps(reference_step_trace()))
+    out['env_trace_json'] = np.array(json.dumps(reference_env_trace()))
+    out['temporal_range_schedule'] = np.array(reference_temporal_range_schedule(LOSS_SEQUENCE), dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, 'reference_host_fixtures.npz'), **out)
     print('wrote', os.path.getsize(os.path.join(HERE, 'reference_host_fixtures.npz')), 'bytes;', {k: int(out[f'body_{k}_n']) for k, _ in BODY_CASES})
 

@@ -120,3 +120,34 @@ def test_step_and_checkpoint_orchestration_equals_the_reference():
     assert len(trace) == len(ref), (len(trace), len(ref))
     for i, (a, b) in enumerate(zip(trace, ref)):
         assert a == b, (i, a, b)
+
+
+def test_taichi_env_call_sequence_equals_the_reference():
+    """TaichiEnv.set_state / step / step_grad / reset_grad / get_final_loss(_grad) / apply_agent_action_p(_grad) (fluidengine/taichi_env.py:136-222)
+    only sequence calls on the simulator, the agent and the loss: the fixture is the trace of the REAL class driven with recorder objects."""
+    import json
+    import make_reference_fixtures as mk
+    from fluidlab_b200.taichi_env import TaichiEnv
+    ref = json.loads(str(D['env_trace_json']))
+    trace = []
+    mk.drive_env(mk.make_env_with_recorders(TaichiEnv, trace))
+    assert trace == ref, [(i, a, b) for i, (a, b) in enumerate(zip(trace, ref)) if a != b][:3]
+
+
+def test_temporal_range_schedule_equals_the_reference():
+    """ShapeMatchingLoss.expand_temporal_range (losses/shapematching_loss.py:110-130): plateau counting and horizon expansion driven by a
+    loss sequence — the fixture was produced by the reference's own method."""
+    import io
+    import contextlib
+    import make_reference_fixtures as mk
+    from fluidlab_b200.losses import ShapeMatchingLoss
+    L = ShapeMatchingLoss.__new__(ShapeMatchingLoss)
+    L.temporal_range_type, L.temporal_range, L.best_loss, L.plateau_count, L.inf = 'expand', [0, 50], 1e8, 0, 1e8
+    L.plateau_thresh, L.plateau_count_limit, L.temporal_expand_speed, L.max_loss_steps = [0.01, 0.5], 5, 50, 220
+    got = []
+    for v in mk.LOSS_SEQUENCE:
+        L.total_loss = float(v)
+        with contextlib.redirect_stdout(io.StringIO()):
+            L.expand_temporal_range()
+        got.append([L.temporal_range[1], L.plateau_count, float(L.best_loss)])
+    assert np.array_equal(np.array(got, dtype=np.float64), D['temporal_range_schedule'])
