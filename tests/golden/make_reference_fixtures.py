@@ -87,6 +87,7 @@ def load_reference():
                 raise AttributeError(k)
             o = _Obj(); setattr(self, k, o); return o
     ti = _Stub('taichi'); ti.f32, ti.f64, ti.i32 = 'f32', 'f64', 'i32'
+    ti.static = lambda x: x          # loops over ti.static(range(n)) keep iterating
     sys.modules['taichi'] = ti
     for name in ('trimesh', 'yacs', 'yacs.config', 'gym', 'gym.spaces', 'mesh_to_sdf', 'skimage', 'skimage.measure', 'matplotlib', 'matplotlib.pyplot',
                  'imageio', 'pyrender', 'open3d', 'cv2', 'OpenGL', 'OpenGL.GL', 'pyglet'):
@@ -157,8 +158,14 @@ class Recorder:
             raise AttributeError(k)
 
         def call(*a, **kw):
-            args = [('arr%d' % np.asarray(v).size if v is not None and not isinstance(v, (int, float, bool, dict)) else (v if not isinstance(v, dict) else 'dict'))
-                    for v in list(a) + [kw[q] for q in sorted(kw)]]
+            def brief(v):
+                if v is None or isinstance(v, (int, float, bool, str)):
+                    return v
+                if isinstance(v, dict):
+                    return 'dict'
+                arr = np.asarray(v, dtype=np.float64).reshape(-1)
+                return [round(float(q), 6) for q in arr] if arr.size <= 12 else 'arr%d' % arr.size
+            args = [brief(v) for v in list(a) + [kw[q] for q in sorted(kw)]]
             self._trace.append([f'{self._name}.{k}'] + args)
         return call
 
@@ -167,6 +174,46 @@ class Recorder:
 
     def __bool__(self):
         return True
+
+
+class MockEffector(Recorder):
+    def __init__(self, name, trace, action_dim, tag):
+        Recorder.__init__(self, name, trace)
+        object.__setattr__(self, 'action_dim', action_dim); object.__setattr__(self, 'tag', tag); object.__setattr__(self, 'state_dim', 7)
+
+    def get_action_grad(self, s, n):
+        self._trace.append([f'{self._name}.get_action_grad', s, n])
+        return None if self.action_dim == 0 else np.full((n + 1, self.action_dim), float(self.tag))
+
+    def get_state(self, f):
+        self._trace.append([f'{self._name}.get_state', f])
+        return np.full(7, float(self.tag))
+
+
+def drive_agent(agent, trace):
+    """Agent (agents/agent.py:68-131): how actions are split over the effectors and in which order the effectors are visited"""
+    agent.effectors = [MockEffector('eff0', trace, 3, 1), MockEffector('eff1', trace, 0, 2), MockEffector('eff2', trace, 6, 3)]
+    agent.action_dims = [0, 3, 3, 9]
+    agent.n_effectors = 3
+    act = np.arange(9) * 0.5
+    agent.set_action(1, 4, 10, act); agent.set_action_grad(1, 4, 10, act)
+    agent.apply_action_p(act + 1); agent.apply_action_p_grad(act + 1)
+    g = agent.get_grad(2)
+    trace.append(['get_grad.result', list(np.asarray(g).shape), [float(v) for v in np.asarray(g)[0]]])
+    agent.move(7); agent.move_grad(7)
+    st = agent.get_state(3)
+    trace.append(['get_state.result', [float(np.asarray(s)[0]) for s in st]])
+    agent.set_state(3, [np.arange(7.0), np.arange(7.0) + 1, np.arange(7.0) + 2])
+    agent.copy_frame(20, 0); agent.copy_grad(0, 20); agent.reset_grad_till_frame(20); agent.reset_grad()
+    trace.append(['dims', int(agent.action_dim), int(agent.state_dim)])
+
+
+def reference_agent_trace():
+    ag = importlib.import_module('fluidlab.fluidengine.agents.agent')
+    trace = []
+    a = ag.Agent(max_substeps_local=20, max_substeps_global=1000, max_action_steps_global=50, ckpt_dest='cpu')
+    drive_agent(a, trace)
+    return trace
 
 
 def drive_env(env):
@@ -306,6 +353,7 @@ def main():
     import json
     out['step_trace_json'] = np.array(json.dumps(reference_step_trace()))
     out['env_trace_json'] = np.array(json.dumps(reference_env_trace()))
+    out['agent_trace_json'] = np.array(json.dumps(reference_agent_trace()))
     out['temporal_range_schedule'] = np.array(reference_temporal_range_schedule(LOSS_SEQUENCE), dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, 'reference_host_fixtures.npz'), **out)
     print('wrote', os.path.getsize(os.path.join(HERE, 'reference_host_fixtures.npz')), 'bytes;', {k: int(out[f'body_{k}_n']) for k, _ in BODY_CASES})

@@ -151,3 +151,16 @@ def test_temporal_range_schedule_equals_the_reference():
             L.expand_temporal_range()
         got.append([L.temporal_range[1], L.plateau_count, float(L.best_loss)])
     assert np.array_equal(np.array(got, dtype=np.float64), D['temporal_range_schedule'])
+
+
+def test_agent_effector_dispatch_equals_the_reference():
+    """Agent (agents/agent.py:68-131): splitting of the action vector over the effectors, visiting order forward / reverse, get_grad
+    concatenation, state get / set, frame and adjoint shuffles — trace of the REAL class with recorder effectors."""
+    import json
+    import make_reference_fixtures as mk
+    from fluidlab_b200.agents import Agent
+    ref = json.loads(str(D['agent_trace_json']))
+    trace = []
+    a = Agent(max_substeps_local=20, max_substeps_global=1000, max_action_steps_global=50, ckpt_dest='cpu')
+    mk.drive_agent(a, trace)
+    assert trace == ref, [(i, x, y) for i, (x, y) in enumerate(zip(trace, ref)) if x != y][:3]
