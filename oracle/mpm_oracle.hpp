@@ -5,13 +5,15 @@
 // zhouxian/FluidLab, file fluidlab/fluidengine/simulators/mpm_simulator.py (abbrev. MPM).
 // Every function cites the reference lines it follows.
 //
-// PARITY UNPINNED: the reference ships no tests / golden vectors and its arithmetic for
-// `ti.svd` and `kernel.grad` lives in taichi==1.1.0 (environment.yml:250), which is not
-// installable here.  The SVD convention (U,V proper rotations, singular values sorted
-// descending, sign carried by the smallest) and the autodiff tie rules (branch conditions
-// and int casts carry no gradient, min/max send the adjoint to the selected operand) are
-// restated from the published behaviour of Taichi 1.1.0; the adjoints are validated against
-// central finite differences in double precision (tests/test_oracle_adjoint.py).
+// PARITY STATUS.  Taichi (taichi==1.1.0, environment.yml:250) is not installable here and the reference ships no tests or golden
+// vectors.  FORWARD: pinned to the reference itself — its unmodified kernel source runs on a NumPy emulation of the Taichi API in the
+// build container (tests/golden/taichi_emu.py, make_reference_run.py) and tests/test_reference_run.py requires this oracle to reproduce
+// those runs (all material classes, both boundaries, MAT_RIGID bodies, injectors, collectors, 6-DOF pose chain, Static / Dynamic SDF
+// colliders at grid and particle level).  STILL UNPINNED against Taichi: the internals of `ti.svd` (convention assumed: U, V proper
+// rotations, singular values sorted descending, sign carried by the smallest; the emulation assumes the same) and `kernel.grad`
+// (Taichi's autodiff: branch conditions and int casts carry no gradient, min/max send the adjoint to the selected operand).  The
+// hand-written adjoints are validated against central finite differences in double precision (tests/test_oracle.py) and against
+// torch.autograd applied to an independent PyTorch restatement (tests/test_torch_autodiff_crosscheck.py).
 //
 // Templated on the scalar so the same code gives the fp32 arithmetic of the reference
 // (DTYPE_TI = f32, configs/macros.py:207-211) and an fp64 ground truth.

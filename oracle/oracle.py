@@ -8,8 +8,8 @@ this module; the product package (fluidlab_b200/) never does.
 (fluidlab/fluidengine/simulators/mpm_simulator.py:721-912): `step`, `step_grad`, frame ring of
 `max_substeps_local+1` frames, chunk checkpoint + re-simulation in the backward pass.
 
-PARITY UNPINNED (see the header of mpm_oracle.hpp): Taichi is not installable here, the
-reference ships no golden vectors.
+PARITY STATUS (see the header of mpm_oracle.hpp): forward pinned to runs of the reference's own kernels on an emulated Taichi API
+(tests/test_reference_run.py); `ti.svd` internals and Taichi's autodiff stay unpinned (adjoints: finite differences + torch.autograd).
 """
 import ctypes as C
 import os

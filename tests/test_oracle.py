@@ -498,7 +498,7 @@ def test_6dof_injector_and_collector_dloss_daction_fd():
 
 
 # ------------------------------------------------------------------------------------------------
-# symmetry pins of the restatement (nothing pins it to the real reference: PARITY UNPINNED), fp64
+# symmetry pins of the restatement, fp64
 # ------------------------------------------------------------------------------------------------
 def _sym_run(x, v, C, F, mat, n_grid, gravity, boundary, n_sub=6):
     P = make_particles(x, mat, n_grid)
