@@ -148,13 +148,23 @@ def scene_jetbot(R):
     actions = np.array([[0.003, -0.002, 0.001, 0.02, 0.03, -0.02], [-0.002, 0.001, 0.002, -0.01, 0.02, 0.03], [0.001, 0.0, -0.002, 0.03, -0.02, 0.01]], dtype=np.float32)
     action_p = np.array([0.58, 0.55, 0.5, 0, 0, 0], dtype=np.float32)
     agent.apply_action_p(action_p)
+    # the reference's own index-matched loss (losses/shapematching_loss.py:80-93) accumulated the way TaichiEnv.step does (taichi_env.py:171-172)
+    sm = importlib.import_module('fluidlab.fluidengine.losses.shapematching_loss')
+    import taichi as ti
+    tgt = rng.uniform(0.4, 0.6, size=(n_steps, N, 3)).astype(np.float32)
+    loss = sm.ShapeMatchingLoss(matching_mat=M.WATER, temporal_range_type='all', max_loss_steps=n_steps, weights={'chamfer': 1.0}, target_file=None)
+    loss.build(S)
+    loss.target = {'x': [tgt[i] for i in range(n_steps)]}
+    loss.tgt_particles_x = ti.Vector.field(3, dtype=R['macros'].DTYPE_TI, shape=N)
     for i in range(n_steps):
         S.step(actions[i])
+        loss.step()
+    ref_loss = float(loss.get_final_loss()['loss'])
     out = read_frame(S, S.cur_substep_local)
     pose = np.asarray(inj.get_state(S.cur_substep_local), dtype=np.float64)
     return dict(n_grid=n_grid, n_steps=n_steps, T=T, flux=flux, x0=x, used0=used, mat=mat, b_lower=bnd['lower'], b_upper=bnd['upper'], e_lower=ebnd['lower'],
                 e_upper=ebnd['upper'], c_lower=cbnd['lower'], c_upper=cbnd['upper'], actions=actions, action_p=action_p, init_state=np.asarray(inj.init_state, dtype=np.float64),
-                random_vector=inj.random_vector.to_numpy(), ref_pose=pose, **{'ref_' + k: a for k, a in out.items()})
+                random_vector=inj.random_vector.to_numpy(), ref_pose=pose, tgt=tgt, ref_loss=ref_loss, **{'ref_' + k: a for k, a in out.items()})
 
 
 # ---------------------------------------------------------------------------------------------------------------- scene 4

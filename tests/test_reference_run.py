@@ -75,8 +75,11 @@ def test_agent_jetbot_6dof_injector_and_collector(prec):
     o.set_collector(cube(d['c_lower'], d['c_upper']), mat=M.WATER)
     o.set_frame(0, d['x0'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), d['used0'])
     o.set_effector_state(0, 0, np.concatenate([d['init_state'][:7], [0.0]])); o.apply_action_p(d['action_p'])
+    total = 0.0
     for i in range(int(d['n_steps'])):
         o.step(d['actions'][i])
+        total += o.loss_value(o.cur_substep_local, M.WATER, 1.0, d['tgt'][i])   # vs the reference's own ShapeMatchingLoss kernels
+    assert abs(total - float(d['ref_loss'])) < 1e-5 * float(d['ref_loss']), (total, float(d['ref_loss']))
     fr = o.get_frame(o.cur_substep_local)
     n_used = int(d['ref_used'].sum())
     assert n_used < int(d['used0'].sum()) + int(d['flux']) * 10 * int(d['n_steps']), 'the reference run collected nothing'
