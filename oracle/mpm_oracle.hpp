@@ -12,8 +12,9 @@
 // colliders at grid and particle level).  STILL UNPINNED against Taichi: the internals of `ti.svd` (convention assumed: U, V proper
 // rotations, singular values sorted descending, sign carried by the smallest; the emulation assumes the same) and `kernel.grad`
 // (Taichi's autodiff: branch conditions and int casts carry no gradient, min/max send the adjoint to the selected operand).  The
-// hand-written adjoints are validated against central finite differences in double precision (tests/test_oracle.py) and against
-// torch.autograd applied to an independent PyTorch restatement (tests/test_torch_autodiff_crosscheck.py).
+// hand-written adjoints are validated against central finite differences THROUGH THE REFERENCE'S OWN FORWARD KERNELS run in float64
+// (tests/golden/make_reference_fd.py, tests/test_reference_run.py), against central differences of this oracle (tests/test_oracle.py)
+// and against torch.autograd applied to an independent PyTorch restatement (tests/test_torch_autodiff_crosscheck.py).
 //
 // Templated on the scalar so the same code gives the fp32 arithmetic of the reference
 // (DTYPE_TI = f32, configs/macros.py:207-211) and an fp64 ground truth.

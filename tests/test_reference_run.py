@@ -128,3 +128,61 @@ def test_agent_icecream_dynamic_ball_injector_static_and_rigid_colliders(prec):
     assert int(d['ref_used'].sum()) == int(d['flux']) * int(d['inject_till'])     # injection stopped at inject_till
     check(fr, d)
     assert np.abs(o.effector_state(1, o.cur_substep_local)[:7] - d['ref_pose'][:7]).max() < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# adjoints vs central differences THROUGH THE REFERENCE'S OWN FORWARD CODE in fp64 (tests/golden/make_reference_fd.py)
+# ------------------------------------------------------------------------------------------------------------------------------------
+FD = np.load(os.path.join(G, 'reference_fd.npz'))
+
+
+def test_substep_adjoint_equals_finite_differences_of_the_reference_forward():
+    """3 substeps of a WATER / ELASTIC / ICECREAM / MILK_VIS cloud: the oracle's fp64 adjoint of L = sum w . state_3 w.r.t. 20 entries of
+    (x, v, C, F)_0 against central differences of the REFERENCE's forward kernels run in float64 (its own `dprecision = 64` switch)."""
+    n_grid, n_sub = int(FD['cloud_n_grid']), int(FD['cloud_n_sub'])
+    P = make_particles(FD['cloud_x'], FD['cloud_mat'], n_grid)
+    # the fp64 reference run holds the material constants and the particle mass in double (make_particles rounds them to f32 like the f32 build)
+    P['mu'] = np.array([M.MU[int(m)] for m in FD['cloud_mat']], dtype=np.float64); P['lam'] = np.array([M.LAMDA[int(m)] for m in FD['cloud_mat']], dtype=np.float64)
+    P['mass'] = (0.5 / n_grid) ** 2 * np.array([M.RHO[int(m)] for m in FD['cloud_mat']], dtype=np.float64)
+    o = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=cube(FD['cloud_lower'], FD['cloud_upper']), precision=64, max_substeps_local=10)
+    o.set_frame(0, FD['cloud_x'], FD['cloud_v'], FD['cloud_C'], FD['cloud_F'], P['used'])
+    for f in range(n_sub):
+        o.substep(f)
+    fr = o.get_frame(n_sub)
+    w = {k: FD['cloud_w_' + k] for k in ('x', 'v', 'C', 'F')}
+    loss = sum((w[k] * fr[k]).sum() for k in w)
+    assert abs(loss - float(FD['cloud_loss'])) < 1e-9 * max(1.0, abs(loss)), (loss, float(FD['cloud_loss']))   # forward, fp64 vs fp64
+    o.reset_grad(); o.set_grad_frame(n_sub, w['x'], w['v'], w['C'], w['F'])
+    for f in reversed(range(n_sub)):
+        o.substep_grad(f)
+    g = o.get_grad_frame(0)
+    for key, idx, fd in zip(FD['cloud_pick_key'], FD['cloud_pick_idx'], FD['cloud_fd']):
+        an = g[str(key)].reshape(-1)[int(idx)]
+        assert abs(an - fd) <= 2e-6 * max(1.0, abs(fd)), (str(key), int(idx), an, fd)
+
+
+def test_dloss_daction_equals_finite_differences_of_the_reference_forward():
+    """6-DOF Injector (AgentInjector, pose / quaternion chain, rotated inject_p / inject_v) + the reference's own ShapeMatchingLoss: the
+    oracle's dLoss/dAction (velocity, rotation and initial-position actions) against central differences of the reference forward in fp64."""
+    d = FD
+    N = len(d['inj_x'])
+    n_steps = int(d['inj_n_steps'])
+    P = make_particles(d['inj_x'], d['inj_mat'], int(d['inj_n_grid']), used=d['inj_used'])
+    o = orc.OracleSim(int(d['inj_n_grid']), P, gravity=(0, -10, 0), boundary=cube(d['inj_lower'], d['inj_upper']), precision=64, max_substeps_local=int(d['inj_T']))
+    o.add_effector(type=1, action_dim=6, scale_v=(1, 1, 1, 5, 5, 5), boundary=cube(d['inj_e_lower'], d['inj_e_upper']), radius=0.015, flux=int(d['inj_flux']),
+                   inject_v=(-3.0, 0.5, 0.0), inject_p=(-0.07, 0.01, 0.0), locally_random=True, random_vector=d['inj_random_vector'],
+                   act_range=np.where(d['inj_used'] == 0)[0], max_action_steps=20)
+    o.enable_grad()
+    o.set_frame(0, d['inj_x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), d['inj_used'])
+    o.set_effector_state(0, 0, np.concatenate([d['inj_init_state'][:7], [0.0]])); o.apply_action_p(d['inj_action_p'])
+    total = 0.0
+    for i in range(n_steps):
+        o.step(d['inj_actions'][i]); total += o.loss_value(o.cur_substep_local, M.MILK, 1.0, d['inj_tgt'][i])
+    assert abs(total - float(d['inj_loss'])) < 1e-9 * abs(total), (total, float(d['inj_loss']))
+    o.reset_grad()
+    for i in range(n_steps - 1, -1, -1):
+        o.loss_seed(o.cur_substep_local, M.MILK, 1.0, d['inj_tgt'][i]); o.step_grad(d['inj_actions'][i])
+    o.apply_action_p_grad()
+    g = o.get_action_grad(n_steps)
+    for (i, j), fd in zip(d['inj_picks'], d['inj_fd']):
+        assert abs(g[int(i), int(j)] - fd) <= 2e-6 * max(1.0, abs(fd)), (int(i), int(j), g[int(i), int(j)], fd)
