@@ -186,3 +186,62 @@ def test_dloss_daction_equals_finite_differences_of_the_reference_forward():
     g = o.get_action_grad(n_steps)
     for (i, j), fd in zip(d['inj_picks'], d['inj_fd']):
         assert abs(g[int(i), int(j)] - fd) <= 2e-6 * max(1.0, abs(fd)), (int(i), int(j), g[int(i), int(j)], fd)
+
+
+def test_mat_rigid_adjoint_equals_finite_differences_of_the_reference_forward():
+    """advect_grad of MAT_RIGID bodies (shape matching + manual SVD adjoint, MPM:436-447, 485-489): oracle fp64 adjoint at 16 entries of rigid
+    particles' (x, v, C, F)_0 against central differences of the reference's forward kernels (compute_COM / compute_H / ti.svd-emulated /
+    compute_R / advect_kernel) in float64."""
+    d = FD
+    n_grid, n_sub = int(d['rb_n_grid']), int(d['rb_n_sub'])
+    P = make_particles(d['rb_x'], d['rb_mat'], n_grid)
+    P['mu'] = np.array([M.MU[int(m)] for m in d['rb_mat']], dtype=np.float64); P['lam'] = np.array([M.LAMDA[int(m)] for m in d['rb_mat']], dtype=np.float64)
+    P['mass'] = (0.5 / n_grid) ** 2 * np.array([M.RHO[int(m)] for m in d['rb_mat']], dtype=np.float64)
+    o = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=cube(d['rb_lower'], d['rb_upper']), precision=64, max_substeps_local=10)
+    o.set_bodies(d['rb_bid'], 3)
+    o.set_frame(0, d['rb_x'], d['rb_v'], d['rb_C'], d['rb_F'], P['used'])
+    for f in range(n_sub):
+        o.substep(f)
+    fr = o.get_frame(n_sub)
+    w = {k: d['rb_w_' + k] for k in ('x', 'v', 'C', 'F')}
+    loss = sum((w[k] * fr[k]).sum() for k in w)
+    assert abs(loss - float(d['rb_loss'])) < 1e-9 * max(1.0, abs(loss)), (loss, float(d['rb_loss']))
+    o.reset_grad(); o.set_grad_frame(n_sub, w['x'], w['v'], w['C'], w['F'])
+    for f in reversed(range(n_sub)):
+        o.substep_grad(f)
+    g = o.get_grad_frame(0)
+    for key, idx, fd in zip(d['rb_pick_key'], d['rb_pick_idx'], d['rb_fd']):
+        an = g[str(key)].reshape(-1)[int(idx)]
+        assert abs(an - fd) <= 5e-6 * max(1.0, abs(fd)), (str(key), int(idx), an, fd)
+
+
+def test_dloss_daction_6dof_collider_equals_finite_differences_of_the_reference_forward():
+    """6-DOF Rigid (rotated, scaled box mesh) colliding at grid AND particle level through the reference's own Dynamic.collide: the oracle's
+    dLoss/dAction against central differences of the reference forward in float64.  The contact map is piecewise smooth (hit / influence
+    thresholds), so three step sizes were recorded and the closest one must agree."""
+    d = FD
+    N, n_steps = len(d['po_x']), int(d['po_n_steps'])
+    P = make_particles(d['po_x'], d['po_mat'], int(d['po_n_grid']))
+    P['mu'] = np.array([M.MU[int(m)] for m in d['po_mat']], dtype=np.float64); P['lam'] = np.array([M.LAMDA[int(m)] for m in d['po_mat']], dtype=np.float64)
+    P['mass'] = (0.5 / int(d['po_n_grid'])) ** 2 * np.ones(N)
+    o = orc.OracleSim(int(d['po_n_grid']), P, gravity=(0, -10, 0), boundary=cube(d['po_lower'], d['po_upper']), precision=64, max_substeps_local=int(d['po_T']))
+    o.add_effector(type=0, action_dim=6, scale_v=(1,) * 6, boundary=cube(d['po_e_lower'], d['po_e_upper']), max_action_steps=20)
+    o.set_rigid_mesh(d['po_vox'], d['po_T_final'], friction=float(d['po_friction']), softness=100.0, collide_type='both')
+    o.enable_grad()
+    o.set_frame(0, d['po_x'], d['po_v0'], d['po_C0'], d['po_F0'], np.ones(N, np.int32))
+    o.set_effector_state(0, 0, np.concatenate([d['po_init_state'][:7], [0.0]])); o.apply_action_p(d['po_action_p'])
+    for i in range(n_steps):
+        o.step(d['po_actions'][i])
+    fr = o.get_frame(o.cur_substep_local)
+    loss = float((d['po_w'] * fr['x']).sum())
+    assert abs(loss - float(d['po_loss'])) < 1e-7 * max(1.0, abs(loss)), (loss, float(d['po_loss']))
+    o.reset_grad()
+    o.set_grad_frame(o.cur_substep_local, d['po_w'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.zeros((N, 3, 3)))
+    for i in range(n_steps - 1, -1, -1):
+        o.step_grad(d['po_actions'][i])
+    o.apply_action_p_grad()
+    g = o.get_action_grad(n_steps)
+    scale = max(1.0, np.abs(d['po_fd']).max())
+    for q, (i, j) in enumerate(d['po_picks']):
+        err = min(abs(g[int(i), int(j)] - fd) for fd in d['po_fd'][:, q])
+        assert err <= 1e-5 * scale, (int(i), int(j), g[int(i), int(j)], d['po_fd'][:, q])
