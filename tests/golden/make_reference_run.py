@@ -167,6 +167,42 @@ def scene_jetbot(R):
                 random_vector=inj.random_vector.to_numpy(), ref_pose=pose, tgt=tgt, ref_loss=ref_loss, **{'ref_' + k: a for k, a in out.items()})
 
 
+# ---------------------------------------------------------------------------------------------------------------- scene 3b
+def scene_latteart(R):
+    """the LatteArt configuration (envs/latteart_env.py, agent_latteart.yaml) in miniature: AgentInjector with a locally-random Injector whose
+    own boundary is a cylinder with y pinned (the radial clamp of CylinderBoundary.impose_x is hit by the actions), parked MILK injected into a
+    COFFEE pool inside a cylinder boundary, gravity -20; 3 steps"""
+    from fluidlab_b200 import macros as M
+    rng = np.random.RandomState(205)
+    n_grid, n_coffee, n_milk, flux, n_steps, T = 16, 110, 70, 2, 3, 20
+    x = np.concatenate([np.tile(M.NOWHERE, (n_milk, 1)), rng.uniform((0.37, 0.36, 0.37), (0.63, 0.45, 0.63), size=(n_coffee, 3))]).astype(np.float32)
+    used = np.concatenate([np.zeros(n_milk), np.ones(n_coffee)]).astype(np.int32)
+    mat = np.concatenate([np.full(n_milk, M.MILK), np.full(n_coffee, M.COFFEE)]).astype(np.int32)
+    N = len(x)
+    bnd = dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.34, 0.9))
+    ebnd = dict(type='cylinder', xz_radius=0.12, xz_center=(0.5, 0.5), y_range=(0.55, 0.55))
+    common = dict(max_substeps_local=T, max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
+    np.random.seed(32)
+    agent = R['agents'].AgentInjector(**common)
+    agent.add_effector(type='Injector', params=dict(radius=0.0075, flux=flux, init_pos=(0.5, 0.5, 0.5), action_dim=3, inject_v=(0.0, -3.0, 0.0), action_scale_p=(1.0, 1.0, 1.0),
+                                                     action_scale_v=(1.0, 1.0, 1.0), locally_random=True), mesh_cfg=None, boundary_cfg=ebnd)
+    S = R['sim'].MPMSimulator(dim=3, quality=n_grid / 64, gravity=(0.0, -20.0, 0.0), horizon=10, max_substeps_local=T, max_substeps_global=1000, ckpt_dest='cpu')
+    S.setup_boundary(**bnd)
+    rho = np.array([R['macros'].RHO[int(m)] for m in mat], dtype=np.float32)
+    S.build(agent, None, [], dict(x=x, used=used, mat=mat, rho=rho, body_id=np.zeros(N), bodies={'n': 1}))
+    agent.build(S)
+    inj = agent.effectors[0]
+    actions = np.array([[0.05, 0.02, 0.03], [0.06, -0.01, 0.05], [-0.02, 0.0, 0.04]], dtype=np.float32)   # leaves the r = 0.12 cylinder: radial clamp + pinned y
+    action_p = np.array([0.47, 0.7, 0.52], dtype=np.float32)
+    agent.apply_action_p(action_p)
+    for i in range(n_steps):
+        S.step(actions[i])
+    out = read_frame(S, S.cur_substep_local)
+    return dict(n_grid=n_grid, n_steps=n_steps, T=T, flux=flux, x0=x, used0=used, mat=mat, actions=actions, action_p=action_p,
+                init_state=np.asarray(inj.init_state, dtype=np.float64), random_vector=inj.random_vector.to_numpy(),
+                ref_pose=np.asarray(inj.get_state(S.cur_substep_local), dtype=np.float64), **{'ref_' + k: a for k, a in out.items()})
+
+
 # ---------------------------------------------------------------------------------------------------------------- scene 4
 def scene_pouring(R):
     """the real AgentPouring (agents/agent_pouring.py): 6-DOF Rigid whose Dynamic mesh (meshes/dynamic.py) collides at grid AND particle
@@ -254,7 +290,7 @@ def scene_icecream(R):
 def main():
     R = load_reference()
     patch_mesh_io(R)
-    for name, fn in (('multimat', scene_multimat), ('rigid_bodies', scene_rigid_bodies), ('jetbot', scene_jetbot), ('pouring', scene_pouring),
+    for name, fn in (('multimat', scene_multimat), ('rigid_bodies', scene_rigid_bodies), ('jetbot', scene_jetbot), ('latteart', scene_latteart), ('pouring', scene_pouring),
                      ('icecream', scene_icecream)):
         d = fn(R)
         np.savez_compressed(os.path.join(HERE, f'reference_run_{name}.npz'), **d)

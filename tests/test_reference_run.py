@@ -88,6 +88,26 @@ def test_agent_jetbot_6dof_injector_and_collector(prec):
 
 
 @pytest.mark.parametrize('prec', [32, 64])
+def test_latteart_like_injector_with_cylinder_boundaries(prec):
+    d = np.load(os.path.join(G, 'reference_run_latteart.npz'))
+    N = len(d['x0'])
+    P = make_particles(d['x0'], d['mat'], int(d['n_grid']), used=d['used0'])
+    bnd = dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.34, 0.9))
+    ebnd = dict(type='cylinder', xz_radius=0.12, xz_center=(0.5, 0.5), y_range=(0.55, 0.55))
+    o = orc.OracleSim(int(d['n_grid']), P, gravity=(0, -20, 0), boundary=bnd, precision=prec, max_substeps_local=int(d['T']))
+    o.add_effector(type=1, action_dim=3, boundary=ebnd, radius=0.0075, flux=int(d['flux']), inject_v=(0, -3, 0), inject_p=(0, 0, 0), locally_random=True,
+                   random_vector=d['random_vector'], act_range=np.where(d['used0'] == 0)[0], max_action_steps=20)
+    o.set_frame(0, d['x0'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), d['used0'])
+    o.set_effector_state(0, 0, np.concatenate([d['init_state'][:7], [0.0]])); o.apply_action_p(d['action_p'])
+    for i in range(int(d['n_steps'])):
+        o.step(d['actions'][i])
+    pose = o.effector_state(0, o.cur_substep_local)
+    assert abs(pose[1] - 0.55) < 1e-6 and abs(np.hypot(pose[0] - 0.5, pose[2] - 0.5) - 0.12) < 1e-5, 'the scene must exercise the pinned y and the radial clamp'
+    assert np.abs(pose[:7] - d['ref_pose'][:7]).max() < 2e-6
+    check(o.get_frame(o.cur_substep_local), d)
+
+
+@pytest.mark.parametrize('prec', [32, 64])
 def test_agent_pouring_6dof_rigid_collider_both_levels(prec):
     d = np.load(os.path.join(G, 'reference_run_pouring.npz'))
     N = len(d['x0'])
