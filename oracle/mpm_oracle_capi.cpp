@@ -213,6 +213,13 @@ void orc_effector_apply_action_p_grad(void* hp, int ei) { Handle* h = (Handle*)h
 void orc_effector_get_action_grad(void* hp, int ei, int n, double* out) { Handle* h = (Handle*)hp; DISPATCH(h, eff_get_grad_t(S, ei, n, out)); }
 void orc_effector_get_pose_grad(void* hp, int ei, int f, double* out) { Handle* h = (Handle*)hp; DISPATCH(h, eff_get_pose_grad_t(S, ei, f, out)); }
 
+// unit access to the manual SVD adjoint (MPM:272-292): gU, gS (diagonal matrix), gV, U, sig[3], V -> gA (row-major 3x3), double precision
+void orc_backward_svd(const double* gU, const double* gS, const double* gV, const double* U, const double* sig, const double* V, double* out) {
+  M3<double> a, b, c, u, v;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { a[i][j] = gU[i * 3 + j]; b[i][j] = gS[i * 3 + j]; c[i][j] = gV[i * 3 + j]; u[i][j] = U[i * 3 + j]; v[i][j] = V[i * 3 + j]; }
+  M3<double> r = backward_svd<double>(a, b, c, u, sig, v);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[i * 3 + j] = r[i][j];
+}
 void orc_svd3(const double* A, double* U, double* s, double* V, int precision) {
   if (precision == 32) svd_t<float>(A, U, s, V); else svd_t<double>(A, U, s, V);
 }

@@ -272,6 +272,18 @@ def main():
                inj_flux=c['flux'], inj_n_steps=c['n_steps'], inj_T=c['T'], inj_lower=c['lower'], inj_upper=c['upper'], inj_e_lower=c['e_lower'], inj_e_upper=c['e_upper'],
                inj_picks=np.array(c['picks']), inj_fd=np.array(fd), inj_loss=val, inj_random_vector=aux['random_vector'], inj_init_state=aux['init_state'])
     print('injector loss', val, 'fd', np.array(fd))
+    # E: the reference's manual SVD adjoint MPM:272-292 (backward_svd + clamp), called directly on random inputs incl. near-degenerate sigmas
+    S0 = R['sim'].MPMSimulator(dim=3, quality=0.25, gravity=(0.0, -10.0, 0.0), horizon=10, max_substeps_local=10, max_substeps_global=1000, ckpt_dest='cpu')
+    import taichi as ti
+    rng = np.random.RandomState(305)
+    cases = []
+    for it in range(24):
+        A = np.eye(3) + rng.randn(3, 3) * (0.3 if it % 3 else 1e-5)       # every third case: nearly equal singular values (the 1e-8 clamp acts)
+        U, Sg, Vh = np.linalg.svd(A); V = Vh.T
+        gU, gV, gS = rng.randn(3, 3), rng.randn(3, 3), np.diag(rng.randn(3))
+        r = S0.backward_svd(ti.Matrix(gU.tolist()), ti.Matrix(gS.tolist()), ti.Matrix(gV.tolist()), ti.Matrix(U.tolist()), ti.Matrix(np.diag(Sg).tolist()), ti.Matrix(V.tolist()))
+        cases.append(np.concatenate([gU.ravel(), gS.ravel(), gV.ravel(), U.ravel(), Sg, V.ravel(), np.asarray(r, dtype=np.float64).ravel()]))
+    out['svd_grad_cases'] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, 'reference_fd.npz'), **out)
     print('wrote', os.path.getsize(os.path.join(HERE, 'reference_fd.npz')), 'bytes')
 
