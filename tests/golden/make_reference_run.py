@@ -167,6 +167,34 @@ def scene_jetbot(R):
                 random_vector=inj.random_vector.to_numpy(), ref_pose=pose, tgt=tgt, ref_loss=ref_loss, **{'ref_' + k: a for k, a in out.items()})
 
 
+# ---------------------------------------------------------------------------------------------------------------- scene 2b
+def scene_locked(R):
+    """the boundary options of envs/transporting_env.py:80-87: a cube boundary with lock_dims=[2] (z velocity zeroed on every grid node) and a
+    non-zero restitution (walls reflect), water + a MAT_RIGID body thrown against the walls; 10 substeps"""
+    from fluidlab_b200 import macros as M
+    rng = np.random.RandomState(206)
+    n_grid, n_sub = 16, 10
+    xw = rng.uniform((0.34, 0.33, 0.40), (0.50, 0.45, 0.60), size=(60, 3))
+    xr = rng.uniform((0.55, 0.34, 0.42), (0.65, 0.44, 0.52), size=(30, 3))
+    x = np.concatenate([xw, xr]).astype(np.float32)
+    mat = np.concatenate([np.full(60, M.WATER), np.full(30, M.RIGID_HEAVY)]).astype(np.int32)
+    bid = np.concatenate([np.zeros(60), np.ones(30)]).astype(np.int32)
+    N = len(x)
+    v = (rng.randn(N, 3) * 0.3 + np.array([1.5, -2.0, 0.8])).astype(np.float32)     # towards the +x wall and the floor
+    C = (rng.randn(N, 3, 3) * 2.0).astype(np.float32); F = (np.eye(3)[None] + rng.randn(N, 3, 3) * 0.02).astype(np.float32)
+    bnd = dict(type='cube', lower=(0.32, 0.32, 0.32), upper=(0.68, 0.68, 0.68), restitution=0.25, lock_dims=[2])
+    S = R['sim'].MPMSimulator(dim=3, quality=n_grid / 64, gravity=(0.0, -10.0, 0.0), horizon=10, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu')
+    S.setup_boundary(**bnd)
+    rho = np.array([R['macros'].RHO[int(m)] for m in mat], dtype=np.float32)
+    S.build(None, None, [], dict(x=x, used=np.ones(N), mat=mat, rho=rho, body_id=bid, bodies={'n': 2}))
+    S.setframe(0, x, v, C, F, np.ones(N, np.int32))
+    for f in range(n_sub):
+        S.substep(f, True)
+    out = read_frame(S, n_sub)
+    return dict(n_grid=n_grid, n_sub=n_sub, x0=x, v0=v, C0=C, F0=F, mat=mat, body_id=bid, b_lower=bnd['lower'], b_upper=bnd['upper'], restitution=0.25,
+                lock_dims=np.array([2]), **{'ref_' + k: a for k, a in out.items()})
+
+
 # ---------------------------------------------------------------------------------------------------------------- scene 3b
 def scene_latteart(R):
     """the LatteArt configuration (envs/latteart_env.py, agent_latteart.yaml) in miniature: AgentInjector with a locally-random Injector whose
@@ -290,7 +318,7 @@ def scene_icecream(R):
 def main():
     R = load_reference()
     patch_mesh_io(R)
-    for name, fn in (('multimat', scene_multimat), ('rigid_bodies', scene_rigid_bodies), ('jetbot', scene_jetbot), ('latteart', scene_latteart), ('pouring', scene_pouring),
+    for name, fn in (('multimat', scene_multimat), ('rigid_bodies', scene_rigid_bodies), ('locked', scene_locked), ('jetbot', scene_jetbot), ('latteart', scene_latteart), ('pouring', scene_pouring),
                      ('icecream', scene_icecream)):
         d = fn(R)
         np.savez_compressed(os.path.join(HERE, f'reference_run_{name}.npz'), **d)

@@ -930,27 +930,33 @@ def test_c3_latteart_two_material_fwd_bwd_full_size():
     assert rel(grad, g64) < 1e-4, (rel(grad, g64), grad, g64)
 
 
-@pytest.mark.parametrize('scene', ['multimat', 'rigid_bodies'])
+@pytest.mark.parametrize('scene', ['multimat', 'rigid_bodies', 'locked'])
 def test_cuda_matches_runs_of_the_real_reference_kernels(scene):
     """tests/golden/reference_run_<scene>.npz hold particle states produced by the UNMODIFIED reference kernels executed on a NumPy emulation
     of the Taichi API (tests/golden/make_reference_run.py).  The CUDA path is compared with them directly (not through the oracle):
-    every material class + cube walls + unused slots (12 substeps); two MAT_RIGID bodies + water + elastic in a cylinder (10 substeps)."""
+    every material class + cube walls + unused slots (12 substeps); two MAT_RIGID bodies + water + elastic in a cylinder (10 substeps);
+    transporting_env's boundary options (restitution + lock_dims=[2]) with water and a MAT_RIGID body hitting the walls (10 substeps)."""
     _need_gpu()
     import os
     from fluidlab_b200 import MPMSimulator
     d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', f'reference_run_{scene}.npz'))
     n_grid, n_sub = int(d['n_grid']), int(d['n_sub'])
-    P = make_particles(d['x0'], d['mat'], n_grid, used=d['used0'])
-    if scene == 'rigid_bodies':
+    used0 = d['used0'] if 'used0' in d else np.ones(len(d['x0']), np.int32)
+    gravity = tuple(float(g) for g in d['gravity']) if 'gravity' in d else (0.0, -10.0, 0.0)
+    P = make_particles(d['x0'], d['mat'], n_grid, used=used0)
+    if scene == 'locked':
+        P['body_id'] = d['body_id']; P['bodies'] = {'n': 2}
+        bnd = dict(type='cube', lower=tuple(d['b_lower']), upper=tuple(d['b_upper']), restitution=float(d['restitution']), lock_dims=[int(v) for v in d['lock_dims']])
+    elif scene == 'rigid_bodies':
         P['body_id'] = d['body_id']; P['bodies'] = {'n': 4}
         bnd = dict(type='cylinder', xz_radius=float(d['xz_radius']), xz_center=tuple(d['xz_center']), y_range=tuple(d['y_range']))
     else:
         bnd = dict(type='cube', lower=tuple(d['b_lower']), upper=tuple(d['b_upper']))
-    s = MPMSimulator(dim=3, quality=n_grid / 64, gravity=tuple(float(g) for g in d['gravity']), horizon=100, max_substeps_local=20, max_substeps_global=100000,
+    s = MPMSimulator(dim=3, quality=n_grid / 64, gravity=gravity, horizon=100, max_substeps_local=20, max_substeps_global=100000,
                      ckpt_dest='gpu')
     s.setup_boundary(**bnd)
     s.build(None, None, [], P)
-    s.setframe(0, d['x0'], d['v0'], d['C0'], d['F0'], d['used0'])
+    s.setframe(0, d['x0'], d['v0'], d['C0'], d['F0'], used0)
     s.sort_frame(0)
     for f in range(n_sub):
         s.substep(f, True)

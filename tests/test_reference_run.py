@@ -65,6 +65,23 @@ def test_mat_rigid_bodies_and_cylinder_boundary(prec):
 
 
 @pytest.mark.parametrize('prec', [32, 64])
+def test_boundary_restitution_and_lock_dims(prec):
+    d = np.load(os.path.join(G, 'reference_run_locked.npz'))
+    N = len(d['x0'])
+    P = make_particles(d['x0'], d['mat'], int(d['n_grid']))
+    bnd = dict(type='cube', lower=tuple(d['b_lower']), upper=tuple(d['b_upper']), restitution=float(d['restitution']), lock_dims=[int(v) for v in d['lock_dims']])
+    o = orc.OracleSim(int(d['n_grid']), P, gravity=(0, -10, 0), boundary=bnd, precision=prec, max_substeps_local=20)
+    o.set_bodies(d['body_id'], 2)
+    o.set_frame(0, d['x0'], d['v0'], d['C0'], d['F0'], np.ones(N, np.int32))
+    for f in range(int(d['n_sub'])):
+        o.substep(f)
+    fr = o.get_frame(int(d['n_sub']))
+    assert np.all(d['ref_v'][:, 2] == 0.0), 'lock_dims=[2] must zero the z velocity of every particle'
+    assert d['ref_x'][:, 0].max() > 0.62 and d['ref_x'][:, 1].min() < 0.37, 'the scene must reach the walls'
+    check(fr, d)
+
+
+@pytest.mark.parametrize('prec', [32, 64])
 def test_agent_jetbot_6dof_injector_and_collector(prec):
     d = np.load(os.path.join(G, 'reference_run_jetbot.npz'))
     N = len(d['x0'])
