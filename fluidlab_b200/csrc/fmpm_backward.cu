@@ -428,7 +428,7 @@ static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, 
 extern "C" int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) { return g2p_grad_scatter_impl(h, f, gin, 1, -1, stream); }
 static int grid_op_grad_impl(FmpmHandle* h, int f, int clear_pm, int ring_slot, void* stream) {
   if (check_bound_b(h, "fmpm_grid_op_grad")) return 1;
-  KParams P = make_kparams(h, ring_slot);
+  KParams P = make_kparams(h, ring_slot, f);   // x-slab mode: the accumulator / block flags of substep parity f
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
   k_grid_op_grad<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm);
@@ -487,6 +487,25 @@ extern "C" int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* 
   }
   // adjoint: grid scatter, grid_op.grad (also leaves the accumulators clear for the next substep), per-particle part
   if (g2p_grad_scatter_impl(h, f, gin, 0, -1, stream) || grid_op_grad_impl(h, f, 1, -1, stream)) return 1;
+  return fmpm_particle_grad(h, f, gin, gout, stream);
+}
+// x-slab backward: fmpm_substep_grad cut at its two ghost exchanges.  Sequence per rank and substep:
+//   fmpm_p2g(f, 0)  ->  [ghost sum of the (momentum, mass) planes]  ->  fmpm_substep_grad_scatter
+//                   ->  [ghost sum of the v_out-adjoint planes]     ->  fmpm_substep_grad_finish
+extern "C" int fmpm_substep_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) {
+  if (check_bound_b(h, "fmpm_substep_grad_scatter")) return 1;
+  if (gin & ~1) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad_scatter: gin must be 0 or 1"); return 1; }
+  if (fmpm_grid_op_impl(h, f, 0, 1, -1, stream)) return 1;
+  if (h->col.has_rigid && h->col.collide_type != 1) {
+    KParams P = make_kparams(h);
+    if (P.N > 0) { k_collide_particle_grad<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_scatter(collide)"); }
+  }
+  return g2p_grad_scatter_impl(h, f, gin, 0, -1, stream);
+}
+extern "C" int fmpm_substep_grad_finish(FmpmHandle* h, int f, int gin, int gout, void* stream) {
+  if (check_bound_b(h, "fmpm_substep_grad_finish")) return 1;
+  if (gin == gout || (gin | gout) & ~1) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad_finish: gin/gout must be distinct in {0,1}"); return 1; }
+  if (grid_op_grad_impl(h, f, 1, -1, stream)) return 1;
   return fmpm_particle_grad(h, f, gin, gout, stream);
 }
 extern "C" int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjector* inj, const FmpmEffector* e, int act_id,

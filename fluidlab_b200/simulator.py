@@ -642,6 +642,64 @@ class MPMSimulator:
         for action in ckpt['actions']:
             self.step_(action)
 
+    # ------------------------------------------------------------------------------------------ x-slab hooks (fluidlab_b200/slab.py)
+    # The slab orchestration only talks to its local simulator through these (and step-level methods), so the same orchestration
+    # can be driven on CPU by an oracle-backed stand-in in tests/test_slab_cpu.py.
+    def slab_positions(self, f):
+        """(x coordinate, alive mask) of every slot of frame f, in the slot order of the frame (device views, no copy)."""
+        return self._pa[f, 0, :, 0], (self._pa[f, 0, :, 3].view(torch.int32) & 1) != 0
+
+    def slab_grid_acc(self, f):
+        """live (G,4) (momentum, mass) accumulator of substep f (double-buffered by substep parity in peer mode)."""
+        g = self._grid_pm
+        return g[f & 1] if g.dim() == 3 else g
+
+    def slab_grid_acc_commit(self, f, acc):
+        pass   # `acc` is the live buffer
+
+    def slab_grid_adj(self, f):
+        """live (G,4) adjoint of grid.v_out."""
+        return self._ggrid_v
+
+    def slab_grid_adj_commit(self, f, adj):
+        pass
+
+    def slab_flag_blocks(self, f, flagger):
+        b = self._blk_flags
+        flagger(b[f & 1] if b.dim() == 2 else b)
+
+    def slab_substep_grad_p2g(self, f):
+        """backward substep f, part 1: recompute the (momentum, mass) scatter of frame f (ghost sum follows)."""
+        self._ensure_grad_order(self._frame_ord[f])
+        self._ck(self._lib.fmpm_p2g(self._h, f, 0, self._stream()), 'fmpm_p2g')
+
+    def slab_substep_grad_scatter(self, f):
+        """part 2: grid_op of frame f + g2p.grad scatter of the v_out adjoint (ghost sum of that adjoint follows)."""
+        self._ck(self._lib.fmpm_substep_grad_scatter(self._h, f, self._gcur, self._stream()), 'fmpm_substep_grad_scatter')
+
+    def slab_substep_grad_finish(self, f):
+        """part 3: grid_op.grad (leaves the accumulators clear) + the particle side; the adjoint of frame f becomes current."""
+        gin, gout = self._gcur, 1 - self._gcur
+        self._ck(self._lib.fmpm_substep_grad_finish(self._h, f, gin, gout, self._stream()), 'fmpm_substep_grad_finish')
+        self._gcur = gout
+
+    def read_grad_torch(self):
+        """current adjoint frame in original particle order: dict of fresh device tensors x,v (N,3), C,F (N,3,3)."""
+        N, dev, f32 = self.n_particles, self.device, torch.float32
+        g = dict(x=torch.empty((N, 3), dtype=f32, device=dev), v=torch.empty((N, 3), dtype=f32, device=dev),
+                 C=torch.empty((N, 3, 3), dtype=f32, device=dev), F=torch.empty((N, 3, 3), dtype=f32, device=dev))
+        self._ck(self._lib.fmpm_read_grad(self._h, self._gcur, g['x'].data_ptr(), g['v'].data_ptr(), g['C'].data_ptr(), g['F'].data_ptr(),
+                                          self._grad_ord.ids_ptr(), self._stream()), 'fmpm_read_grad')
+        return g
+
+    def write_grad_torch(self, g):
+        """overwrite the current adjoint frame from device tensors in original particle order (it is then IN original order)."""
+        self._ensure_grad_buffers()
+        t = [g[k].to(self.device, torch.float32).contiguous() for k in ('x', 'v', 'C', 'F')]
+        self._grad_ord = _IDENTITY
+        self._ck(self._lib.fmpm_write_grad(self._h, self._gcur, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
+                                           self._grad_ord.ids_ptr(), self._stream()), 'fmpm_write_grad')
+
     # ------------------------------------------------------------------------------------------ phase-level access (tests, profiling)
     def read_grid(self):
         G, dev, f32 = self.n_grid ** 3, self.device, torch.float32

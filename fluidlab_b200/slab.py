@@ -17,8 +17,15 @@ The reference is single-device (no collective anywhere); this is new design.  On
     leavers never synchronise the host.  `halo` = 4 planes tolerates 3 cells of drift over the two steps between a
     census and its migration (|v| < 3 dx / (20 dt) = 2.9 m/s at 256^3, 11.7 m/s at 64^3); raise `halo` for faster flows.
 
-`SlabMPMSimulator` covers the forward path (step / gather_state); the backward ghost exchange (v_out adjoint planes) is the
-mirror image and is not wired yet.
+Backward (`SlabMPMSimulator.step_grad`, SURVEY.md §8e "Backward"): per substep the forward scatter of frame f is recomputed with the same
+ghost sum as in the forward pass, g2p's adjoint scatters the v_out adjoint onto owned + ghost planes, ONE more ghost sum (all-reduce of
+the 2*halo planes per slab boundary) completes it, and grid_op.grad runs redundantly on the ghosts so the particle side (p2g.grad) needs
+no further exchange.  At step boundaries `migrate_grad` sends the adjoint of every migrated particle back to the rank and slot it left.
+A backward pass must fit one checkpoint chunk (n_steps * 10 <= max_substeps_local); the sharded ring wrap-around is not implemented.
+
+The orchestration talks to the local simulator only through `MPMSimulator`'s step-level methods and its `slab_*` hooks, so
+tests/test_slab_cpu.py drives this same code on CPU (gloo, world_size 2) with an oracle-backed stand-in and checks forward AND backward
+against the single-domain oracle.
 """
 import os
 import numpy as np
@@ -66,6 +73,11 @@ class GhostExchange:
         f = blk_flags.view(nb, nb, nb)
         for _, lo, hi, _ in self.regions:
             f[lo // 8:(hi + 7) // 8] = 1
+
+
+class _Done:
+    def synchronize(self):
+        pass
 
 
 def centre_plane(x, inv_dx):
@@ -173,8 +185,7 @@ class SlabMPMSimulator:
     """Forward MLS-MPM over x-slabs: one local `MPMSimulator` per rank + ghost exchange + migration."""
 
     def __init__(self, quality, gravity, particles, gid, bounds, capacity, boundary=None, max_substeps_local=50, device=None, group=None, halo=4,
-                 exchange='peer', migrate=True):
-        from .simulator import MPMSimulator
+                 exchange='peer', migrate=True, sim_factory=None):
         from .macros import NOWHERE
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -188,11 +199,16 @@ class SlabMPMSimulator:
         for k in ('mat', 'rho', 'body_id'):
             P[k] = np.concatenate([np.asarray(particles[k]), np.full(pad, np.asarray(particles[k])[0] if n_loc else 0)])
         P['used'] = np.concatenate([np.asarray(particles['used']).astype(np.int32), np.zeros(pad, np.int32)])
-        self.sim = MPMSimulator(dim=3, quality=quality, gravity=gravity, horizon=10 ** 5, max_substeps_local=max_substeps_local,
-                                max_substeps_global=10 ** 7, ckpt_dest='gpu', device=device, sort_every=1)
-        if boundary is not None:
-            self.sim.setup_boundary(**boundary)
-        self.sim.build(None, None, [], P)
+        if sim_factory is None:
+            from .simulator import MPMSimulator
+            self.sim = MPMSimulator(dim=3, quality=quality, gravity=gravity, horizon=10 ** 5, max_substeps_local=max_substeps_local,
+                                    max_substeps_global=10 ** 7, ckpt_dest='gpu', device=device, sort_every=1)
+            if boundary is not None:
+                self.sim.setup_boundary(**boundary)
+            self.sim.build(None, None, [], P)
+        else:   # tests: a stand-in with MPMSimulator's step-level methods and slab_* hooks (tests/test_slab_cpu.py)
+            self.sim = sim_factory(quality=quality, gravity=gravity, particles=P, boundary=boundary, max_substeps_local=max_substeps_local)
+            exchange = 'nccl' if exchange == 'peer' else exchange   # "nccl" = the all-reduce exchange, whatever the backend
         dev = self.sim.device
         self.gid = torch.from_numpy(np.concatenate([np.asarray(gid, dtype=np.int32), np.full(pad, -1, np.int32)])).to(dev)
         self.bounds = list(bounds)
@@ -204,6 +220,8 @@ class SlabMPMSimulator:
             self._setup_peer(halo)
         self._census_host = None
         self._census_event = None
+        self._records = {}      # global step index -> what migrate() did before that step (for step_grad)
+        self._gid_before = {}   # global step index -> slot -> global id map before that migration
 
     def _setup_peer(self, halo):
         """Double-buffer the accumulator in SYMMETRIC MEMORY (torch.distributed._symmetric_memory: every rank's buffer is mapped
@@ -251,8 +269,7 @@ class SlabMPMSimulator:
         """enqueue (no host sync): per-rank leaver counts -> all-gather -> total -> pinned host; read one step later."""
         sim = self.sim
         f = sim.cur_substep_local
-        xs = sim._pa[f, 0, :, 0]
-        alive = (sim._pa[f, 0, :, 3].view(torch.int32) & 1) != 0
+        xs, alive = sim.slab_positions(f)
         cp = (xs * sim.inv_dx - 0.5).to(torch.int32) + 1
         out = torch.zeros((), dtype=torch.int64, device=xs.device)
         if self.rank > 0:
@@ -261,6 +278,9 @@ class SlabMPMSimulator:
             out = out + (alive & (cp >= self.hi)).sum()
         out = out.reshape(1)
         dist.all_reduce(out, group=self.group)
+        if xs.device.type != 'cuda':   # host stand-in (tests): nothing is asynchronous
+            self._census_host, self._census_event = out.clone(), _Done()
+            return
         if self._census_host is None:
             self._census_host = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._census_host.copy_(out, non_blocking=True)
@@ -279,9 +299,14 @@ class SlabMPMSimulator:
             f = sim.cur_substep_local
             st = sim.readframe_torch(f)
             state = dict(x=st['x'], v=st['v'], C=st['C'], F=st['F'], used=st['used'], mrow=sim._mrow, gid=self.gid)
-            n_out, n_in = migrate(state, self.lo, self.hi, self.rank, self.world, sim.inv_dx, self.group)
+            rec = {} if sim.grad_enabled else None
+            gid_before = self.gid.clone() if sim.grad_enabled else None
+            n_out, n_in = migrate(state, self.lo, self.hi, self.rank, self.world, sim.inv_dx, self.group, record=rec)
             if n_out or n_in:
                 sim.setframe(f, state['x'], state['v'], state['C'], state['F'], state['used'])
+                if rec is not None:
+                    self._records[sim.cur_step_global] = rec
+                    self._gid_before[sim.cur_step_global] = gid_before
             self.n_migrated += n_out
         self._census_async()
 
@@ -296,13 +321,77 @@ class SlabMPMSimulator:
             if self.exchange == 'peer':
                 self._symm.barrier(channel=0)   # device-side: every rank's p2g (incl. its peer reductions and peer block flags) has completed
             elif self.exchange == 'nccl':
-                self.ghost.exchange_sum(sim._grid_pm)
-                self.ghost.flag_ghost_blocks(sim._blk_flags)
+                self._ghost_sum_acc(f)
             sim.phase('grid_op', f, 1)
             sim.phase('g2p', f)
             sim.cur_substep_global += 1
         if sim.cur_substep_local == 0:
+            assert not sim.grad_enabled, 'a differentiated slab trajectory must fit one chunk (n_steps * 10 <= max_substeps_local)'
             sim.memory_to_cache()
+
+    def _ghost_sum_acc(self, f):
+        sim = self.sim
+        acc = sim.slab_grid_acc(f)
+        self.ghost.exchange_sum(acc)
+        sim.slab_grid_acc_commit(f, acc)
+        sim.slab_flag_blocks(f, self.ghost.flag_ghost_blocks)
+
+    # ------------------------------------------------------------------------------------------ backward
+    def enable_grad(self):
+        self.sim.enable_grad()
+        self._records, self._gid_before = {}, {}
+
+    def local_state(self):
+        """current frame of this rank in slot order: dict(gid, used, x, v, C, F) of device tensors (staging views: copy to keep)."""
+        st = self.sim.readframe_torch(self.sim.cur_substep_local)
+        return dict(gid=self.gid, **st)
+
+    def set_final_grad(self, gx, gv=None, gC=None, gF=None):
+        """seed the adjoint of the current frame (slot order of `local_state`); missing parts are zero."""
+        sim = self.sim
+        sim.reset_grad()
+        N = gx.shape[0]
+        z3 = torch.zeros((N, 3), dtype=torch.float32, device=gx.device); z9 = torch.zeros((N, 3, 3), dtype=torch.float32, device=gx.device)
+        sim.write_grad_torch(dict(x=gx, v=z3 if gv is None else gv, C=z9 if gC is None else gC, F=z9 if gF is None else gF))
+
+    def _substep_grad(self, f):
+        sim = self.sim
+        sim.slab_substep_grad_p2g(f)
+        if self.exchange == 'peer':
+            self._symm.barrier(channel=0)
+        elif self.exchange == 'nccl':
+            self._ghost_sum_acc(f)
+        sim.slab_substep_grad_scatter(f)
+        if self.world > 1:   # complete the v_out adjoint on the planes shared with the neighbours
+            adj = sim.slab_grid_adj(f)
+            self.ghost.exchange_sum(adj)
+            sim.slab_grid_adj_commit(f, adj)
+        sim.slab_substep_grad_finish(f)
+
+    def step_grad(self):
+        """adjoint of the most recent `step()` not yet undone; call in exact reverse order after `set_final_grad`."""
+        sim = self.sim
+        assert sim.grad_enabled and sim.cur_substep_global >= sim.n_substeps
+        assert sim.cur_substep_global <= sim.max_substeps_local, 'a differentiated slab trajectory must fit one chunk'
+        for _ in range(sim.n_substeps):
+            sim.cur_substep_global -= 1
+            self._substep_grad(sim.cur_substep_local)
+        s = sim.cur_step_global
+        rec = self._records.get(s)
+        if rec is not None:   # this step began with a migration: send the adjoints of the arrivals back where they came from
+            g = sim.read_grad_torch()
+            migrate_grad(g, rec, self.group)
+            sim.write_grad_torch(g)
+            self.gid = self._gid_before[s]
+
+    def gather_grad(self):
+        """adjoint of the current frame for all used particles of all ranks, sorted by global id: dict(gid, x, v, C, F) numpy."""
+        sim = self.sim
+        used = sim.readframe_torch(sim.cur_substep_local, ('used',))['used'] != 0
+        g = sim.read_grad_torch()
+        rec = torch.cat([self.gid.view(torch.float32).reshape(-1, 1), g['x'], g['v'], g['C'].reshape(-1, 9), g['F'].reshape(-1, 9)], 1)
+        r, gid = self._gather_by_gid(rec, used)
+        return dict(gid=gid, x=r[:, 1:4], v=r[:, 4:7], C=r[:, 7:16].reshape(-1, 3, 3), F=r[:, 16:25].reshape(-1, 3, 3))
 
     def gather_state(self):
         """all used particles of all ranks, sorted by global id: dict(gid, x, v, F) numpy (every rank gets the same)."""
@@ -310,6 +399,11 @@ class SlabMPMSimulator:
         st = sim.readframe_torch(sim.cur_substep_local)
         used = st['used'] != 0
         rec = torch.cat([self.gid.view(torch.float32).reshape(-1, 1), st['x'], st['v'], st['F'].reshape(-1, 9)], 1)
+        r, gid = self._gather_by_gid(rec, used)
+        return dict(gid=gid, x=r[:, 1:4], v=r[:, 4:7], F=r[:, 7:16].reshape(-1, 3, 3))
+
+    def _gather_by_gid(self, rec, used):
+        """rows of the used slots of every rank (column 0 = global id bits), sorted by global id; same result on every rank."""
         rec = torch.where(used.reshape(-1, 1), rec, torch.full_like(rec, float('nan')))
         if self.world > 1:
             cap = torch.tensor([rec.shape[0]], device=rec.device); dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
@@ -324,5 +418,4 @@ class SlabMPMSimulator:
         rec = rec[keep]
         gid = rec[:, 0].contiguous().view(torch.int32).numpy()
         order = np.argsort(gid, kind='stable')
-        r = rec.numpy()[order]
-        return dict(gid=gid[order], x=r[:, 1:4], v=r[:, 4:7], F=r[:, 7:16].reshape(-1, 3, 3))
+        return rec.numpy()[order], gid[order]

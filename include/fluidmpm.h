@@ -196,6 +196,11 @@ int fmpm_collect(FmpmHandle* h, int f, const FmpmCollector* c, void* stream);
 /* gin/gout in {0,1}: grad ping-pong index holding frame f+1 (in) and receiving frame f (out). */
 int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* stream);
 int fmpm_substep_grad_stored(FmpmHandle* h, int f, int gin, int gout, void* stream);  /* uses the grids left by fmpm_substep_store(f) */
+/* x-slab backward (no reference counterpart): fmpm_substep_grad cut at its two ghost exchanges.  Per rank and substep:
+ *   fmpm_p2g(f, 0) -> [ghost sum of the (momentum, mass) planes] -> fmpm_substep_grad_scatter (grid_op + g2p.grad grid scatter)
+ *                  -> [ghost sum of the v_out-adjoint planes]    -> fmpm_substep_grad_finish  (grid_op.grad, accumulators cleared, particle side) */
+int fmpm_substep_grad_scatter(FmpmHandle* h, int f, int gin, void* stream);
+int fmpm_substep_grad_finish(FmpmHandle* h, int f, int gin, int gout, void* stream);
 /* MPM:436-447 advect_grad for MAT_RIGID bodies: call BEFORE fmpm_substep_grad* / fmpm_g2p_grad_scatter of the same f (it rewrites
  * the x and v adjoints of rigid particles in gin in place; no-op without such bodies).  next_slot: int[N], slot in frame f+1 of the
  * particle in slot s of frame f, or NULL when both frames share one slot order (no cell sort between them). */

@@ -44,6 +44,10 @@ template <class R> static void get_grid_t(Sim<R>& S, double* vin, double* m, dou
   for (size_t i = 0; i < (size_t)S.G * 3; i++) { vin[i] = S.g_vin[i]; vout[i] = S.g_vout[i]; }
   for (size_t i = 0; i < (size_t)S.G; i++) m[i] = S.g_m[i];
 }
+template <class R> static void set_grid_t(Sim<R>& S, const double* vin, const double* m) {
+  for (size_t i = 0; i < (size_t)S.G * 3; i++) S.g_vin[i] = (R)vin[i];
+  for (size_t i = 0; i < (size_t)S.G; i++) S.g_m[i] = (R)m[i];
+}
 template <class R> static void get_grid_grad_t(Sim<R>& S, double* vin, double* m, double* vout) {
   for (size_t i = 0; i < (size_t)S.G * 3; i++) { vin[i] = S.gg_vin[i]; vout[i] = S.gg_vout[i]; }
   for (size_t i = 0; i < (size_t)S.G; i++) m[i] = S.gg_m[i];
@@ -153,6 +157,7 @@ void orc_set_grad_frame(void* hp, int f, const double* x, const double* v, const
 void orc_get_grad_frame(void* hp, int f, double* x, double* v, double* C, double* F) {
   Handle* h = (Handle*)hp; DISPATCH(h, get_grad_t(S, f, x, v, C, F)); }
 void orc_get_grid(void* hp, double* vin, double* m, double* vout) { Handle* h = (Handle*)hp; DISPATCH(h, get_grid_t(S, vin, m, vout)); }
+void orc_set_grid(void* hp, const double* vin, const double* m) { Handle* h = (Handle*)hp; DISPATCH(h, set_grid_t(S, vin, m)); }
 void orc_get_grid_grad(void* hp, double* vin, double* m, double* vout) { Handle* h = (Handle*)hp; DISPATCH(h, get_grid_grad_t(S, vin, m, vout)); }
 void orc_set_grid_grad(void* hp, const double* vin, const double* m, const double* vout) { Handle* h = (Handle*)hp; DISPATCH(h, set_grid_grad_t(S, vin, m, vout)); }
 
@@ -165,6 +170,7 @@ void orc_phase_grid_op(void* hp, int f) { Handle* h = (Handle*)hp; DISPATCH(h, S
 void orc_phase_g2p(void* hp, int f) { Handle* h = (Handle*)hp; DISPATCH(h, (S.advect_used(f), S.process_unused(f), S.g2p(f), S.advect(f))); }
 void orc_phase_g2p_grad(void* hp, int f) { Handle* h = (Handle*)hp; DISPATCH(h, S.g2p_advect_grad(f)); }
 void orc_phase_grid_op_grad(void* hp, int f) { Handle* h = (Handle*)hp; DISPATCH(h, S.grid_op_grad(f)); }
+void orc_phase_unused_grad(void* hp, int f) { Handle* h = (Handle*)hp; DISPATCH(h, S.process_unused_grad(f)); }
 void orc_phase_p2g_grad(void* hp, int f) { Handle* h = (Handle*)hp; DISPATCH(h, S.p2g_grad(f)); }
 
 void orc_copy_frame(void* hp, int s, int t) { Handle* h = (Handle*)hp; DISPATCH(h, S.copy_frame(s, t)); }

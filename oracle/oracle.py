@@ -177,6 +177,10 @@ class OracleSim:
         self.L.orc_get_grid(self.h, _p(vin), _p(m), _p(vout))
         return vin, m, vout
 
+    def set_grid(self, vin, m):
+        """overwrite grid.v_in / grid.mass (the x-slab tests write the ghost-summed accumulator back, tests/test_slab_cpu.py)"""
+        self.L.orc_set_grid(self.h, _p(_d(vin)), _p(_d(m)))
+
     def get_grid_grad(self):
         G = self.n_grid ** 3
         vin = np.zeros((G, 3)); m = np.zeros((G,)); vout = np.zeros((G, 3))

@@ -141,3 +141,188 @@ def test_migrate_grad_is_the_adjoint_of_migrate():
     lhs, rhs = out[0][0], out[0][1]
     assert out[0][2] + out[1][2] > 0, 'nothing migrated'
     assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
+# ----------------------------------------------------------------------------------------------------------------------------------------
+# The slab ORCHESTRATION of the product (fluidlab_b200/slab.py: SlabMPMSimulator.step / step_grad, ghost sums, migration and its adjoint)
+# driven on CPU: the local simulator is replaced by a stand-in with MPMSimulator's step-level methods and slab_* hooks whose kernels are
+# the oracle's phases.  The sharded result (2 ranks, gloo) must equal the single-domain oracle, forward and backward.
+# ----------------------------------------------------------------------------------------------------------------------------------------
+class OracleLocalSim:
+    """stand-in for fluidlab_b200.simulator.MPMSimulator inside SlabMPMSimulator (test infrastructure: wraps oracle.OracleSim)"""
+
+    def __init__(self, quality, gravity, particles, boundary, max_substeps_local):
+        from oracle import oracle as orc
+        from conftest import make_particles
+        self.n_grid = int(round(64 * quality)); self.inv_dx = float(self.n_grid)
+        self.n_substeps = 10; self.max_substeps_local = max_substeps_local
+        self.device = torch.device('cpu')
+        self.N = len(particles['x'])
+        self._make = lambda mat: make_particles(np.zeros((len(mat), 3)), mat, self.n_grid)
+        P = make_particles(particles['x'], particles['mat'], self.n_grid, used=particles['used'])
+        self.o = orc.OracleSim(self.n_grid, P, gravity=gravity, boundary=boundary, precision=32, max_substeps_local=max_substeps_local)
+        self._mrow = torch.from_numpy(np.asarray(particles['mat'], dtype=np.int32).copy())   # "material row" = the material id itself
+        self._layouts = [(0, self._mrow.clone())]   # (first frame, material per slot): migrations change what a slot holds
+        self.cur_substep_global = 0
+        self.grad_enabled = False
+        self._acc = None; self._adj = None; self._gframe = 0
+
+    # indices
+    @property
+    def cur_substep_local(self): return self.cur_substep_global % self.max_substeps_local
+    @property
+    def cur_step_global(self): return self.cur_substep_global // self.n_substeps
+    def enable_grad(self): self.grad_enabled = True; self.cur_substep_global = 0
+    def memory_to_cache(self): self.o.L.orc_copy_frame(self.o.h, self.max_substeps_local, 0)
+
+    def _use_layout(self, f):
+        mrow = [m for f0, m in self._layouts if f0 <= f][-1]
+        P = self._make(mrow.numpy())
+        from oracle.oracle import _p, _d
+        self.o.L.orc_set_particle_info(self.o.h, _p(P['mat']), _p(P['cls']), _p(_d(P['mu'])), _p(_d(P['lam'])), _p(_d(P['mass'])))
+
+    # frames
+    def sort_frame(self, f): pass
+    def readframe_torch(self, f, want=('x', 'v', 'C', 'F', 'used')):
+        fr = self.o.get_frame(f)
+        out = {k: torch.from_numpy(fr[k].astype(np.float32)) for k in ('x', 'v', 'C', 'F')}
+        out['used'] = torch.from_numpy(fr['used'].astype(np.int32))
+        return {k: out[k] for k in want}
+    def setframe(self, f, x, v, Cm, F, used):
+        self.o.set_frame(f, x.numpy(), v.numpy(), Cm.numpy(), F.numpy(), used.numpy())
+        self._layouts = [(f0, m) for f0, m in self._layouts if f0 < f] + [(f, self._mrow.clone())]
+        self._use_layout(f)
+    def slab_positions(self, f):
+        fr = self.o.get_frame(f)
+        return torch.from_numpy(fr['x'][:, 0].astype(np.float32)), torch.from_numpy(fr['used'] != 0)
+
+    # forward phases
+    def phase(self, name, f, *a):
+        L, h = self.o.L, self.o.h
+        if name == 'p2g':
+            L.orc_phase_reset_grid(h); L.orc_phase_p2g(h, f, int(a[0]) if a else 1)
+            vin, m, _ = self.o.get_grid()
+            self._acc = torch.from_numpy(np.concatenate([vin, m[:, None]], 1).astype(np.float32))
+        elif name == 'grid_op': L.orc_phase_grid_op(h, f)
+        elif name == 'g2p': L.orc_phase_g2p(h, f)
+        else: raise KeyError(name)
+    def slab_grid_acc(self, f): return self._acc
+    def slab_grid_acc_commit(self, f, acc): self.o.set_grid(acc[:, :3].numpy(), acc[:, 3].numpy())
+    def slab_flag_blocks(self, f, flagger): flagger(torch.zeros((self.n_grid // 8) ** 3, dtype=torch.int32))
+
+    # backward
+    def reset_grad(self):
+        self.o.L.orc_reset_grad(self.o.h); self._gframe = self.cur_substep_local
+    def write_grad_torch(self, g):
+        self.o.set_grad_frame(self._gframe, g['x'].numpy(), g['v'].numpy(), g['C'].numpy(), g['F'].numpy())
+    def read_grad_torch(self):
+        g = self.o.get_grad_frame(self._gframe)
+        return {k: torch.from_numpy(g[k].astype(np.float32)) for k in ('x', 'v', 'C', 'F')}
+    def slab_substep_grad_p2g(self, f):
+        assert self._gframe == f + 1
+        self._use_layout(f)
+        z3, z9 = np.zeros((self.N, 3)), np.zeros((self.N, 3, 3))
+        self.o.set_grad_frame(f, z3, z3, z9, z9)
+        self.phase('p2g', f, 0)
+    def slab_substep_grad_scatter(self, f):
+        L, h = self.o.L, self.o.h
+        L.orc_phase_grid_op(h, f); L.orc_phase_g2p_grad(h, f)
+        _, _, gvout = self.o.get_grid_grad()
+        self._adj = torch.from_numpy(gvout.astype(np.float32))
+    def slab_grid_adj(self, f): return self._adj
+    def slab_grid_adj_commit(self, f, adj):
+        G = self.n_grid ** 3
+        self.o.set_grid_grad(np.zeros((G, 3)), np.zeros(G), adj.numpy())
+    def slab_substep_grad_finish(self, f):
+        L, h = self.o.L, self.o.h
+        L.orc_phase_grid_op_grad(h, f); L.orc_phase_p2g_grad(h, f); L.orc_phase_unused_grad(h, f)
+        self._gframe = f
+
+
+_SLAB_STEPS = 5
+
+
+def _slab_scene():
+    from fluidlab_b200 import macros as M
+    rng = np.random.RandomState(11)
+    n, Ntot = 32, 1500
+    x = rng.uniform((0.30, 0.35, 0.35), (0.70, 0.55, 0.65), size=(Ntot, 3)).astype(np.float32)
+    # a fast stream along +x in the lower half and along -x in the upper half: particles cross the slab boundary in both directions
+    v0 = np.where(x[:, 1:2] < 0.45, np.array([[6.0, 0.0, 0.5]]), np.array([[-6.0, 0.3, 0.0]])).astype(np.float32)
+    v0 += (rng.randn(Ntot, 3) * 0.2).astype(np.float32)
+    mat = np.where(x[:, 2] < 0.5, M.WATER, M.ELASTIC).astype(np.int32)
+    tgt = (x + rng.randn(Ntot, 3) * 0.05).astype(np.float32)
+    return n, x, v0, mat, tgt
+
+
+def _slab_fwd_bwd_job(rank, world):
+    from fluidlab_b200 import macros as M
+    from fluidlab_b200.slab import SlabMPMSimulator
+    torch.set_num_threads(1)
+    n, x, v0, mat, tgt = _slab_scene()
+    bounds = slab_bounds(0, 32, world)
+    cp = centre_plane(torch.from_numpy(x), float(n)).numpy()
+    mine = np.where((cp >= bounds[rank]) & (cp < bounds[rank + 1]))[0]
+    parts = dict(x=x[mine], mat=mat[mine], used=np.ones(len(mine), np.int32), rho=np.array([M.RHO[m] for m in mat[mine]]), body_id=np.zeros(len(mine), np.int32),
+                 bodies={'n': 1})
+    slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts, gid=mine, bounds=bounds, capacity=len(mine) + 400, max_substeps_local=60, halo=4,
+                            exchange='nccl', sim_factory=OracleLocalSim)
+    st = slab.sim.readframe_torch(0)
+    st['v'][:len(mine)] = torch.from_numpy(v0[mine])
+    slab.sim.setframe(0, st['x'], st['v'], st['C'], st['F'], st['used'])
+    slab.enable_grad()
+    n_steps = _SLAB_STEPS
+    for _ in range(n_steps):
+        slab.step()
+    fwd = slab.gather_state()
+    ls = slab.local_state()
+    used = (ls['used'] != 0)
+    gid = ls['gid'].long().clamp(min=0)
+    gx = 2.0 * (ls['x'] - torch.from_numpy(tgt)[gid]) * used[:, None]
+    slab.set_final_grad(gx.float())
+    for _ in range(n_steps):
+        slab.step_grad()
+    grad = slab.gather_grad()
+    return fwd, grad, slab.n_migrated, sorted(slab._records)
+
+
+def test_slab_orchestration_forward_and_backward_match_the_single_domain_oracle():
+    """2 ranks over gloo: SlabMPMSimulator.step x5 (ghost sums, migration in both directions at two step boundaries) then step_grad x5
+    (ghost sums of the accumulator AND of the v_out adjoint, migrate_grad) == the single-domain oracle's states and
+    dLoss/d(x0, v0, C0, F0).  The sharded run computes in fp32; it must be as close to the fp64 single-domain result as the fp32
+    single-domain run is (x3 slack), i.e. sharding adds nothing beyond summation-order noise."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import oracle as orc
+    from conftest import make_particles
+    out = _run(_slab_fwd_bwd_job)
+    n, x, v0, mat, tgt = _slab_scene()
+    N, S = len(x), _SLAB_STEPS
+    ref = {}
+    for prec in (32, 64):
+        o = orc.OracleSim(n, make_particles(x, mat, n), gravity=(0.0, -10.0, 0.0), precision=prec, max_substeps_local=60)
+        o.set_frame(0, x, v0, np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), np.ones(N, np.int32))
+        o.enable_grad()
+        for _ in range(S):
+            o.step(None)
+        fr = o.get_frame(10 * S)
+        o.reset_grad()
+        z9 = np.zeros((N, 3, 3))
+        o.set_grad_frame(10 * S, 2.0 * (fr['x'] - tgt), np.zeros((N, 3)), z9, z9)
+        for _ in range(S):
+            o.step_grad(None)
+        ref[prec] = (fr, o.get_grad_frame(0))
+    rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
+    fr64, g64 = ref[64]
+    fr32, g32 = ref[32]
+    for r in (0, 1):
+        fwd, grad, n_mig, rec_steps = out[r]
+        assert np.array_equal(fwd['gid'], np.arange(N)) and np.array_equal(grad['gid'], np.arange(N)), 'particles lost or duplicated'
+        for k in ('x', 'v', 'F'):
+            assert rel(fwd[k], fr64[k]) < max(3 * rel(fr32[k], fr64[k]), 1e-6), (k, rel(fwd[k], fr64[k]), rel(fr32[k], fr64[k]))
+        for k in ('x', 'v', 'C', 'F'):
+            assert np.abs(g64[k]).max() > 0
+            assert rel(grad[k], g64[k]) < max(3 * rel(g32[k], g64[k]), 1e-6), (k, rel(grad[k], g64[k]), rel(g32[k], g64[k]))
+        assert rel(grad['x'], g64['x']) < 1e-4 and rel(grad['v'], g64['v']) < 1e-4
+    assert out[0][2] > 0 and out[1][2] > 0, 'the scene must migrate particles in both directions'
+    assert len(out[0][3]) >= 2, 'migrations must happen at more than one step boundary'
