@@ -94,6 +94,21 @@ class FmpmBodies(C.Structure):
 
 BODY_STATE_STRIDE, BODY_GRAD_STRIDE = 48, 32
 
+
+# ---- include/fluidsmoke.h
+class FsmkConfig(C.Structure):
+    _fields_ = [("res", C.c_int), ("max_steps_local", C.c_int), ("q_dim", C.c_int), ("solver_iters", C.c_int), ("dt", C.c_float),
+                ("lower_y", C.c_int), ("higher_y", C.c_int), ("low_T", C.c_float), ("inject_v", C.c_float * 3), ("device", C.c_int)]
+
+
+class FsmkBuffers(C.Structure):
+    _fields_ = [(k, vp) for k in ("v", "v_tmp", "div", "p", "q", "is_free", "gv", "gv_tmp", "gdiv", "gp", "gq", "tmp_a", "tmp_b", "acc")]
+
+
+class FsmkAircon(C.Structure):
+    _fields_ = [(k, vp) for k in ("pos", "quat", "s", "r", "gpos", "gquat", "gs", "gr")]
+
+
 _I, _F, _U = C.c_int, C.c_float, C.c_uint
 _PROTOS = {
     "fmpm_set_bodies": (_I, [vp, C.POINTER(FmpmBodies)]),
@@ -142,6 +157,34 @@ _PROTOS = {
     "fmpm_loss_chamfer_grad": (_I, [vp, _I, _I, vp, vp, _U, _F, vp]),
 }
 EXPORTS = tuple(_PROTOS.keys())
+_SMOKE_PROTOS = {
+    "fsmk_create": (_I, [C.POINTER(FsmkConfig), C.POINTER(vp)]),
+    "fsmk_destroy": (None, [vp]),
+    "fsmk_bind": (_I, [vp, C.POINTER(FsmkBuffers)]),
+    "fsmk_set_statics": (_I, [vp, _I, C.POINTER(FmpmSdfMesh)]),
+    "fsmk_set_aircon": (_I, [vp, C.POINTER(FsmkAircon)]),
+    "fsmk_last_error": (C.c_char_p, [vp]),
+    "fsmk_step": (_I, [vp, _I, _I, vp]),
+    "fsmk_step_grad": (_I, [vp, _I, _I, vp]),
+    "fsmk_free_space": (_I, [vp, _I, vp]),
+    "fsmk_advect": (_I, [vp, _I, _I, vp]),
+    "fsmk_divergence": (_I, [vp, _I, vp]),
+    "fsmk_pressure": (_I, [vp, _I, vp]),
+    "fsmk_project": (_I, [vp, _I, vp]),
+    "fsmk_project_grad": (_I, [vp, _I, vp]),
+    "fsmk_pressure_grad": (_I, [vp, _I, vp]),
+    "fsmk_divergence_grad": (_I, [vp, _I, vp]),
+    "fsmk_advect_grad": (_I, [vp, _I, _I, vp]),
+}
+SMOKE_EXPORTS = tuple(_SMOKE_PROTOS.keys())
+
+
+def attach_smoke_protos(L):
+    for name, (res, args) in _SMOKE_PROTOS.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    return L
 
 
 def load():
@@ -157,6 +200,7 @@ def load():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        attach_smoke_protos(L)
         _LIB = L
     return _LIB
 

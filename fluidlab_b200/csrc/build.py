@@ -1,12 +1,13 @@
 """Build libfluidmpm.so in-tree with nvcc for sm_100a (B200).  No torch headers are involved: the library
-is a plain C-ABI shared object (include/fluidmpm.h) driven through ctypes."""
+is a plain C-ABI shared object (include/fluidmpm.h, include/fluidsmoke.h) driven through ctypes."""
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRCS = ["fmpm_forward.cu", "fmpm_backward.cu", "fmpm_io.cu", "fmpm_rigid.cu"]
-HDRS = ["fmpm_common.cuh", "fmpm_scatter.cuh", "fmpm_sdf.cuh", os.path.join("..", "..", "include", "fluidmpm.h")]
+SRCS = ["fmpm_forward.cu", "fmpm_backward.cu", "fmpm_io.cu", "fmpm_rigid.cu", "fsmk_smoke.cu"]
+HDRS = ["fmpm_common.cuh", "fmpm_scatter.cuh", "fmpm_sdf.cuh", os.path.join("..", "..", "include", "fluidmpm.h"),
+        os.path.join("..", "..", "include", "fluidsmoke.h")]
 OUT = os.environ.get("FMPM_OUT", os.path.join(HERE, "..", "libfluidmpm.so"))   # FMPM_OUT: A/B variants (profiles/ab_variants.sh)
 OBJDIR = os.environ.get("FMPM_OBJDIR", HERE)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -56,6 +56,12 @@ class TiArr(np.ndarray):
         r = np.ndarray.__getitem__(self, k)
         return r
 
+    # component access, smoke_field.py:247-258
+    x = property(lambda self: self[0], lambda self, v: self.__setitem__(0, v))
+    y = property(lambda self: self[1], lambda self, v: self.__setitem__(1, v))
+    z = property(lambda self: self[2], lambda self, v: self.__setitem__(2, v))
+    w = property(lambda self: self[3], lambda self, v: self.__setitem__(3, v))
+
     # --- ti.Vector / ti.Matrix methods used by the reference
     def norm(self, eps=0.0):
         a = np.asarray(self)
@@ -204,6 +210,10 @@ class Field:
     def copy_from(self, other):
         self.arr[...] = other.arr
 
+    @property
+    def n(self):          # ti.Vector.field(n, ...).n (smoke_field.py:334)
+        return self.arr.shape[-1]
+
     def __iter__(self):   # struct-for over a field iterates its INDICES
         if len(self.shape) == 1:
             return iter(range(self.shape[0]))
@@ -244,6 +254,10 @@ class StructField:
             raise AttributeError(k)
         f = Field.__new__(Field)
         f.arr, f.dtype, f.grad, f.tail = self.data[k], self.data[k].dtype, None, ()
+        if self.__dict__.get('grad') is not None:
+            g = Field.__new__(Field)
+            g.arr, g.dtype, g.grad, g.tail = self.grad.data[k], self.grad.data[k].dtype, None, ()
+            f.grad = g
         return f
 
     def fill(self, v):
@@ -383,8 +397,9 @@ def _value_copy(v):
 
 def install_value_semantics(ref_root):
     """Taichi vectors / matrices have VALUE semantics: `inc = pos_voxels; inc[i] += delta` (meshes/dynamic.py:72-76) must not touch
-    `pos_voxels`.  Python names alias, so the reference's source is compiled with every plain `name = other_name` assignment rewritten to
-    `name = copy(other_name)`.  Nothing else of the source is changed."""
+    `pos_voxels`.  Python names alias, so the reference's source is compiled with every plain `name = other_name` / `name = field[...]` /
+    `name = obj.attr` assignment rewritten to `name = copy(...)` (a no-op for anything that is not an array).  Nothing else of the source
+    is changed."""
     import ast
     import builtins
     from importlib.machinery import SourceFileLoader
@@ -393,7 +408,9 @@ def install_value_semantics(ref_root):
     class T(ast.NodeTransformer):
         def visit_Assign(self, node):
             self.generic_visit(node)
-            if isinstance(node.value, ast.Name) and all(isinstance(t, ast.Name) for t in node.targets):
+            # `name = other_name`, and loads such as `vl = self.grid.v_tmp[s, I]` / `x = self.particles[f, p].x` (a field load yields a VALUE in
+            # Taichi; smoke_field.py:238-248 then overwrites components of the local)
+            if isinstance(node.value, (ast.Name, ast.Subscript, ast.Attribute)) and all(isinstance(t, ast.Name) for t in node.targets):
                 node.value = ast.Call(func=ast.Name(id='__ti_value_copy__', ctx=ast.Load()), args=[node.value], keywords=[])
             return node
     orig = SourceFileLoader.source_to_code
