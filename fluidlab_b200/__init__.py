@@ -7,7 +7,8 @@ from .simulator import MPMSimulator  # noqa: F401
 from .taichi_env import TaichiEnv  # noqa: F401
 from .bodies import Bodies  # noqa: F401
 from .boundaries import create_boundary  # noqa: F401
-from .agents import Agent, AgentInjector, AgentRigid, AgentIceCreamDynamic, AgentPouring, AgentJetBot  # noqa: F401
-from .effectors import Effector, Injector, BallInjector, Rigid  # noqa: F401
+from .agents import Agent, AgentInjector, AgentRigid, AgentIceCreamDynamic, AgentPouring, AgentJetBot, AgentCirculation  # noqa: F401
+from .effectors import Effector, Injector, BallInjector, Rigid, AirCon  # noqa: F401
+from .smoke import SmokeField  # noqa: F401
 from .meshes import Static, Dynamic, Statics  # noqa: F401
-from .losses import Loss, ShapeMatchingLoss, LatteArtLoss  # noqa: F401
+from .losses import Loss, ShapeMatchingLoss, LatteArtLoss, CirculationLoss  # noqa: F401

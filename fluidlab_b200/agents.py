@@ -7,7 +7,7 @@ import numpy as np
 from . import _lib
 from .boundaries import create_boundary
 from .macros import WATER
-from .effectors import Effector, Injector, BallInjector, Rigid  # noqa: F401 (names are eval'ed from yaml, agent.py:32)
+from .effectors import Effector, Injector, BallInjector, Rigid, AirCon  # noqa: F401 (names are eval'ed from yaml, agent.py:32)
 
 
 class Agent:
@@ -255,3 +255,14 @@ class AgentJetBot(_Collector, AgentInjector):
     def build(self, sim):
         super().build(sim)
         self._build_collector(sim)
+
+
+class AgentCirculation(Agent):
+    """agent of the air-circulation env (agents/agent_circulation.py:8-23): one AirCon effector, no collision with the MPM particles."""
+
+    def build(self, sim):
+        super().build(sim)
+        assert self.n_effectors == 1 and isinstance(self.effectors[0], AirCon)
+        self.aircon = self.effectors[0]
+        if getattr(sim, 'smoke_field', None) is not None:
+            sim.smoke_field.bind_aircon(self.aircon)   # the effector's device arrays exist now

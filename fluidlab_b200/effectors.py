@@ -4,7 +4,7 @@ Mirrors fluidlab/fluidengine/effectors/effector.py (`Effector`: fields :34-51, m
 :262-268, set_velocity :252-260, apply_action_p :223-231, get_action_grad :276-283, ckpt :83-139) and
 effectors/injector.py (`Injector` :12-105, `BallInjector` :215-256).  The pose chain of one step (set_action +
 n_substeps move_kernel calls) is one tiny kernel launch (fmpm_effector_step); its adjoint likewise.
-Rigid (SDF-mesh) effectors are not built yet.
+`AirCon` (effectors/aircon.py) adds the strength / radius channels the smoke solver reads.
 """
 import ctypes as C
 import numpy as np
@@ -31,11 +31,11 @@ class Effector:
         self.max_action_steps_global = max_action_steps_global
         self.ckpt_dest = ckpt_dest
         self.action_dim = action_dim
-        assert action_dim in (0, 3, 6)
+        assert action_dim in (0, 3, 6, 8), 'action layouts of the reference: none, xyz, xyz + rotation, AirCon (+ strength, radius)'
         self.init_pos = np.array(_tup(init_pos))
         self.init_rot = _xyzw_to_wxyz(Rotation.from_euler('zyx', _tup(init_euler)[::-1], degrees=True).as_quat())
-        self.action_scale_v = np.array(list(_tup(action_scale_v)) + [1.0] * 6, dtype=DTYPE_NP)[:6]
-        self.action_scale_p = np.array(list(_tup(action_scale_p)) + [1.0] * 6, dtype=DTYPE_NP)[:6]
+        self.action_scale_v = np.array(list(_tup(action_scale_v)) + [1.0] * 8, dtype=DTYPE_NP)[:8]
+        self.action_scale_p = np.array(list(_tup(action_scale_p)) + [1.0] * 8, dtype=DTYPE_NP)[:8]
         self.boundary = None
         self.mesh = None
         self.sim = None
@@ -72,7 +72,7 @@ class Effector:
                         ('act_p', self.action_buffer_p), ('gact_p', self.action_buffer_p_grad)):
             setattr(e, name, t.data_ptr())
         e.action_dim = self.action_dim
-        e.scale_v = (C.c_float * 6)(*[float(x) for x in self.action_scale_v]); e.scale_p = (C.c_float * 6)(*[float(x) for x in self.action_scale_p])
+        e.scale_v = (C.c_float * 6)(*[float(x) for x in self.action_scale_v[:6]]); e.scale_p = (C.c_float * 6)(*[float(x) for x in self.action_scale_p[:6]])
         b = self.boundary
         e.boundary_type = b.type_id
         e.b_lower = (C.c_float * 3)(*[float(x) for x in b.lower]); e.b_upper = (C.c_float * 3)(*[float(x) for x in b.upper])
@@ -263,3 +263,69 @@ class Rigid(Effector):
     def setup_mesh(self, **kwargs):
         from .meshes import Dynamic
         self.mesh = Dynamic(container=self, has_dynamics=True, **kwargs)
+
+
+class AirCon(Effector):
+    """The air conditioner of the circulation task (effectors/aircon.py:12-26): a 6-DOF pose chain plus a blowing strength `s` and a
+    radius `r` per substep, set from action components 6 and 7 (aircon.py:225-241).  The smoke solver reads pos/quat/s/r[f] and
+    accumulates their adjoints (csrc/fsmk_smoke.cu); the pose part of the chain is the ordinary effector kernel."""
+    state_dim = 9
+
+    def __init__(self, inject_v=(-0.3, 0.0, 1.0), **kwargs):
+        super().__init__(**kwargs)
+        self.inject_v = np.array(_tup(inject_v), dtype=DTYPE_NP)
+        self.has_dynamics = False
+
+    def build(self, sim):
+        T, dev = self.max_substeps_local, sim.device
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        self.s, self.r, self.gs, self.gr = z(T + 1), z(T + 1), z(T + 1), z(T + 1)
+        super().build(sim)
+
+    def reset_grad(self):  # aircon.py:52-60
+        super().reset_grad()
+        self.gs.zero_(); self.gr.zero_()
+
+    def set_action(self, s, s_global, n_substeps, action):  # aircon.py:225-241
+        super().set_action(s, s_global, n_substeps, action)
+        if self.action_dim > 6:
+            j0, j1 = s * n_substeps, (s + 1) * n_substeps
+            self.s[j0:j1] = self.action_buffer[s_global, 6] * float(self.action_scale_v[6])
+            self.r[j0:j1] = self.action_buffer[s_global, 7] * float(self.action_scale_v[7])
+
+    def set_action_grad(self, s, s_global, n_substeps, action):
+        if self.action_dim > 6:
+            j0, j1 = s * n_substeps, (s + 1) * n_substeps
+            self.action_buffer_grad[s_global, 6] += self.gs[j0:j1].sum() * float(self.action_scale_v[6])
+            self.action_buffer_grad[s_global, 7] += self.gr[j0:j1].sum() * float(self.action_scale_v[7])
+        super().set_action_grad(s, s_global, n_substeps, action)
+
+    def get_state(self, f):  # aircon.py:188-211
+        out = np.zeros(9, dtype=DTYPE_NP)
+        out[:7] = super().get_state(f)
+        out[7], out[8] = float(self.s[f]), float(self.r[f])
+        return out
+
+    def set_state(self, f, state):
+        ss = self.get_state(f)
+        ss[:len(state)] = state
+        t = torch.from_numpy(np.asarray(ss, dtype=np.float32)).to(self.pos.device)
+        self.pos[f] = t[:3]; self.quat[f] = t[3:7]; self.s[f] = t[7]; self.r[f] = t[8]
+
+    def copy_frame(self, source, target):  # aircon.py:154-161
+        super().copy_frame(source, target)
+        self.s[target] = self.s[source]; self.r[target] = self.r[source]
+
+    def copy_grad(self, source, target):
+        super().copy_grad(source, target)
+        self.gs[target] = self.gs[source]; self.gr[target] = self.gr[source]
+
+    def reset_grad_till_frame(self, f):
+        super().reset_grad_till_frame(f)
+        self.gs[:f].zero_(); self.gr[:f].zero_()
+
+    def get_ckpt(self):
+        c = super().get_ckpt(); c['s'] = self.s[0].clone(); c['r'] = self.r[0].clone(); return c
+
+    def set_ckpt(self, ckpt):
+        super().set_ckpt(ckpt); self.s[0] = ckpt['s']; self.r[0] = ckpt['r']

@@ -133,3 +133,49 @@ class LatteArtLoss(ShapeMatchingLoss):
         info = super().get_final_loss()
         info['reward'] = float(np.sum((121.3 - self.step_loss.cpu().numpy()) * 0.025))
         return info
+
+
+class CirculationLoss(Loss):
+    """temperature loss of the air-circulation task (losses/circulation_loss.py:14-147): 15 detector cells of the smoke field at height 64;
+    the first five should stay hot (|q - 1|), the others reach `target_temp` (|q - 0|).  The per-step value is 15 numbers gathered on the
+    device; its seed adds sign(q - target) * weight to the smoke field's q adjoint."""
+    DETECTORS = [[25, 85], [35, 85], [15, 85], [25, 75], [25, 95], [25, 42], [35, 42], [15, 42], [25, 32], [25, 52], [107, 65], [115, 65], [99, 65], [107, 45], [107, 85]]
+
+    def __init__(self, type='diff', **kwargs):
+        super().__init__(**kwargs)
+        self.temporal_range_type = 'all'
+        self.target_temp, self.detector_h = 0.0, 64
+
+    def build(self, sim):
+        self.temp_weight = self.weights['temp']
+        self.temporal_range = [0, self.max_loss_steps]
+        self.smoke_field = sim.smoke_field
+        assert self.smoke_field is not None, 'CirculationLoss needs a smoke field (losses/loss.py:41-42)'
+        n = self.smoke_field.n_grid
+        cells = [(x * n + self.detector_h) * n + z for x, z in self.DETECTORS]
+        self._cells = torch.tensor(cells, dtype=torch.long, device=sim.device)
+        self._target = torch.tensor([1.0] * 5 + [self.target_temp] * 10, dtype=torch.float32, device=sim.device)
+        super().build(sim)
+
+    def compute_step_loss(self, s, f):  # circulation_loss.py:85-105: step_loss[s] += w * sum |q[s_local, cell][0] - target|
+        q = self.smoke_field._q[self.sim.cur_step_local, 0]
+        self.step_loss[s] += self.temp_weight * (q[self._cells] - self._target).abs().sum()
+
+    def compute_step_loss_grad(self, s, f):
+        if self._step_grad_on[s]:
+            sf = self.smoke_field
+            sf._ensure_grad_buffers()
+            q = sf._q[self.sim.cur_step_local, 0]
+            sf._gq[self.sim.cur_step_local, 0].index_add_(0, self._cells, self.temp_weight * torch.sign(q[self._cells] - self._target))
+
+    def get_final_loss(self):  # circulation_loss.py:118-128
+        self.total_loss = float(self.step_loss[self.temporal_range[0]:self.temporal_range[1]].sum().item())
+        return {'loss': self.total_loss, 'last_step_loss': float(self.step_loss[self.max_loss_steps - 1].item()), 'temporal_range': self.temporal_range[1]}
+
+    def get_final_loss_grad(self):
+        self._step_grad_on[:] = False
+        self._step_grad_on[self.temporal_range[0]:self.temporal_range[1]] = True
+
+    def get_step_loss(self):  # circulation_loss.py:136-144
+        cur = float(self.step_loss[self.sim.cur_step_global - 1].item())
+        return {'reward': 1.0 * (11 - cur), 'loss': 1.0 * cur}

@@ -100,9 +100,7 @@ class MPMSimulator:
             self.boundary = create_boundary()
         self.n_statics = len(statics) if statics is not None else 0
         self.statics = statics
-        if smoke_field is not None:
-            raise NotImplementedError('SmokeField is out of scope of this hot path (SURVEY.md §8f)')
-        self.smoke_field = None
+        self.smoke_field = smoke_field   # built by TaichiEnv.build after the simulator (taichi_env.py:125-126)
         self.agent = agent
 
         if particles is not None:
@@ -502,6 +500,8 @@ class MPMSimulator:
             state.update(self.readframe(f))
         if self.agent is not None:
             state['agent'] = self.agent.get_state(f)
+        if self.smoke_field is not None:
+            state['smoke_field'] = self.smoke_field.get_state(self.cur_step_local)
         return state
 
     def set_state(self, f_global, state):  # MPM:633-644
@@ -510,6 +510,8 @@ class MPMSimulator:
             self.setframe(f, state['x'], state['v'], state['C'], state['F'], state['used'])
         if self.agent is not None:
             self.agent.set_state(f, state['agent'])
+        if self.smoke_field is not None:
+            self.smoke_field.set_state(self.f_local_to_s_local(f), state['smoke_field'])
 
     def get_x(self, f=None):
         f = self.cur_substep_local if f is None else f
@@ -535,6 +537,8 @@ class MPMSimulator:
             state.update(self.readframe(f, ('x', 'v', 'used')))
         if self.agent is not None:
             state['agent'] = self.agent.get_state(f)
+        if self.smoke_field is not None:
+            state['smoke_field'] = self.smoke_field.get_state(self.cur_step_local)
         return state
 
     def get_state_render(self, f):  # MPM:705-707
@@ -568,6 +572,8 @@ class MPMSimulator:
         is_none_action = action is None
         if not is_none_action:
             self.agent.set_action(s=self.cur_step_local, s_global=self.cur_step_global, n_substeps=self.n_substeps, action=action)
+        if self.smoke_field is not None:   # smoke simulates at step level, not substep (MPM:744-747)
+            self.smoke_field.step(s=self.cur_step_local, f=self.cur_substep_local)
         if self.has_particles and self.sort_every > 0 and self.cur_step_global % self.sort_every == 0:
             self.sort_frame(self.cur_substep_local)
         if self.use_graphs and is_none_action and self.has_particles and self._graph_substeps():
@@ -585,6 +591,8 @@ class MPMSimulator:
         for _ in range(self.n_substeps - 1, -1, -1):
             self.cur_substep_global -= 1
             self.substep_grad(self.cur_substep_local, is_none_action)
+        if self.smoke_field is not None:   # MPM:765-767
+            self.smoke_field.step_grad(s=self.cur_step_local, f=self.cur_substep_local)
         if not is_none_action:
             self.agent.set_action_grad(s=self.cur_substep_local // self.n_substeps, s_global=self.cur_substep_global // self.n_substeps,
                                        n_substeps=self.n_substeps, action=action)
@@ -606,6 +614,8 @@ class MPMSimulator:
                             ids=None if o.ids is None else o.ids.to(d, copy=True), inv=None if o.inv is None else o.inv.to(d, copy=True))
             if self.agent is not None:
                 ckpt['agent'] = self.agent.get_ckpt()
+            if self.smoke_field is not None:
+                ckpt['smoke_field'] = self.smoke_field.get_ckpt()
             if self.ckpt_dest == 'disk':
                 os.makedirs(self.ckpt_dir, exist_ok=True)
                 torch.save(ckpt, os.path.join(self.ckpt_dir, f'{ckpt_name}.pt'))
@@ -614,6 +624,8 @@ class MPMSimulator:
         # restart from frame 0 in memory
         if self.has_particles:
             self.copy_frame(T, 0)
+        if self.smoke_field is not None:
+            self.smoke_field.copy_frame(self.max_steps_local, 0)
         if self.agent is not None:
             self.agent.copy_frame(T, 0)
 
@@ -622,6 +634,10 @@ class MPMSimulator:
         T = self.max_substeps_local
         # reference: copy_frame(0,T); copy_grad(0,T); reset_grad_till_frame(T).  The adjoint ping-pong frame already
         # *is* "the adjoint of the current frame", so only the agent's per-frame adjoints need the shuffle.
+        if self.smoke_field is not None:
+            self.smoke_field.copy_frame(0, self.max_steps_local)
+            self.smoke_field.copy_grad(0, self.max_steps_local)
+            self.smoke_field.reset_grad_till_frame(self.max_steps_local)
         if self.agent is not None:
             self.agent.copy_frame(0, T)
             self.agent.copy_grad(0, T)
@@ -637,6 +653,8 @@ class MPMSimulator:
             self._frame_ord[0] = _IDENTITY if ckpt['ids'] is None else _Order(ckpt['ids'].to(self.device, copy=True), ckpt['inv'].to(self.device, copy=True))
         if self.agent is not None:
             self.agent.set_ckpt(ckpt['agent'])
+        if self.smoke_field is not None:
+            self.smoke_field.set_ckpt(ckpt=ckpt['smoke_field'])
         # now that the first frame is loaded, a forward pass fills up the rest of the ring
         self.cur_substep_global = ckpt_start_step
         for action in ckpt['actions']:

@@ -1,7 +1,7 @@
 """Engine facade with the reference's `TaichiEnv` interface (fluidlab/fluidengine/taichi_env.py:17-222) so the
 reference's envs/ and optimizer/ drive the B200 simulator unchanged: setup_agent / setup_boundary / add_body /
 setup_loss / build / step / step_grad / get_state / set_state / reset_grad / loss and action accessors.
-Renderers, SmokeField and mesh statics with dynamics are outside this hot path."""
+Renderers are outside this path; `setup_smoke_field` attaches the B200 smoke solver (smoke.py)."""
 import numpy as np
 from .simulator import MPMSimulator
 from .bodies import Bodies
@@ -51,6 +51,10 @@ class TaichiEnv:
     def setup_boundary(self, **kwargs):
         self.simulator.setup_boundary(**kwargs)
 
+    def setup_smoke_field(self, **kwargs):  # taichi_env.py:95-100
+        from .smoke import SmokeField
+        self.smoke_field = SmokeField(dim=self.dim, ckpt_dest=self.ckpt_dest, **kwargs)
+
     def add_static(self, **kwargs):  # taichi_env.py:89-90
         self.statics.add_static(**kwargs)  # statics without dynamics are visual only and never reach the kernels
 
@@ -69,6 +73,8 @@ class TaichiEnv:
         self.simulator.build(self.agent, self.smoke_field, self.statics, self.particles)
         if self.agent is not None:
             self.agent.build(self.simulator)
+        if self.smoke_field is not None:   # taichi_env.py:125-126
+            self.smoke_field.build(self.simulator, self.agent)
         if self.loss is not None:
             self.loss.build(self.simulator)
         self.t = 0
@@ -77,6 +83,8 @@ class TaichiEnv:
         self.simulator.reset_grad()
         if self.agent is not None:
             self.agent.reset_grad()
+        if self.smoke_field is not None:   # taichi_env.py:142-143
+            self.smoke_field.reset_grad()
         if self.loss is not None:
             self.loss.reset_grad()
 
