@@ -421,7 +421,7 @@ static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, 
   if (P.N == 0) return 0;
   const long long warps = ((long long)P.N + 32 * SC_ROUNDS - 1) / (32 * SC_ROUNDS);
   const int blocks = (int)((warps + SC_WARPS - 1) / SC_WARPS);
-  k_g2p_grad_scatter<<<blocks, SC_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f, gin);
+  FMPM_LAUNCH(k_g2p_grad_scatter, blocks, SC_WARPS * 32, 0, stream, P, f, gin);
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p_grad_scatter");
   return 0;
 }
@@ -431,7 +431,7 @@ static int grid_op_grad_impl(FmpmHandle* h, int f, int clear_pm, int ring_slot, 
   KParams P = make_kparams(h, ring_slot, f);   // x-slab mode: the accumulator / block flags of substep parity f
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
-  k_grid_op_grad<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm);
+  FMPM_LAUNCH(k_grid_op_grad, grid, 256, 0, stream, P, f, clear_pm);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op_grad");
   return 0;
 }
@@ -440,7 +440,7 @@ static int particle_grad_impl(FmpmHandle* h, int f, int gin, int gout, int ring_
   if (check_bound_b(h, "fmpm_particle_grad")) return 1;
   KParams P = make_kparams(h, ring_slot);
   if (P.N == 0) return 0;
-  k_particle_grad<<<(P.N + PG_WARPS * 32 - 1) / (PG_WARPS * 32), PG_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f, gin, gout);
+  FMPM_LAUNCH(k_particle_grad, (P.N + PG_WARPS * 32 - 1) / (PG_WARPS * 32), PG_WARPS * 32, 0, stream, P, f, gin, gout);
   FMPM_CHECK_LAUNCH(h, "fmpm_particle_grad");
   return 0;
 }
@@ -467,10 +467,10 @@ extern "C" int fmpm_substep_grad_stored(FmpmHandle* h, int f, int gin, int gout,
   KParams P = make_kparams(h, f);
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
-  k_zero_ggv_blocks<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  FMPM_LAUNCH(k_zero_ggv_blocks, grid, 256, 0, stream, P);
   FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_stored(zero)");
   if (h->col.has_rigid && h->col.collide_type != 1 && P.N > 0) {
-    k_collide_particle_grad<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_stored(collide)");
+    FMPM_LAUNCH(k_collide_particle_grad, (P.N + 127) / 128, 128, 0, stream, P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_stored(collide)");
   }
   if (g2p_grad_scatter_impl(h, f, gin, 0, f, stream) || grid_op_grad_impl(h, f, 0, f, stream)) return 1;
   return particle_grad_impl(h, f, gin, gout, f, stream);
@@ -483,7 +483,7 @@ extern "C" int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* 
   if (fmpm_p2g(h, f, 0, stream) || fmpm_grid_op_impl(h, f, 0, 1, -1, stream)) return 1;
   if (h->col.has_rigid && h->col.collide_type != 1) {  // particle-level agent collide: fold its adjoint into the frame-(f+1) adjoint
     KParams P = make_kparams(h);
-    if (P.N > 0) { k_collide_particle_grad<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad(collide)"); }
+    if (P.N > 0) { FMPM_LAUNCH(k_collide_particle_grad, (P.N + 127) / 128, 128, 0, stream, P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad(collide)"); }
   }
   // adjoint: grid scatter, grid_op.grad (also leaves the accumulators clear for the next substep), per-particle part
   if (g2p_grad_scatter_impl(h, f, gin, 0, -1, stream) || grid_op_grad_impl(h, f, 1, -1, stream)) return 1;
@@ -498,7 +498,7 @@ extern "C" int fmpm_substep_grad_scatter(FmpmHandle* h, int f, int gin, void* st
   if (fmpm_grid_op_impl(h, f, 0, 1, -1, stream)) return 1;
   if (h->col.has_rigid && h->col.collide_type != 1) {
     KParams P = make_kparams(h);
-    if (P.N > 0) { k_collide_particle_grad<<<(P.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_scatter(collide)"); }
+    if (P.N > 0) { FMPM_LAUNCH(k_collide_particle_grad, (P.N + 127) / 128, 128, 0, stream, P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_scatter(collide)"); }
   }
   return g2p_grad_scatter_impl(h, f, gin, 0, -1, stream);
 }
@@ -512,7 +512,7 @@ extern "C" int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjecto
                                 const void* inv, void* stream) {
   if (check_bound_b(h, "fmpm_inject_grad")) return 1;
   KParams P = make_kparams(h);
-  k_inject_grad<<<(inj->flux + 31) / 32, 32, 0, (cudaStream_t)stream>>>(P, f, gin, *inj, (float*)e->gpos, (const float*)e->quat, (float*)e->gquat, act_id, (const int*)inv);
+  FMPM_LAUNCH(k_inject_grad, (inj->flux + 31) / 32, 32, 0, stream, P, f, gin, *inj, (float*)e->gpos, (const float*)e->quat, (float*)e->gquat, act_id, (const int*)inv);
   FMPM_CHECK_LAUNCH(h, "fmpm_inject_grad");
   return 0;
 }

@@ -359,6 +359,17 @@ __device__ __forceinline__ void constitutive(const KParams& P, const PState& st,
   }
 }
 
+// Kernel launch and the few constructs the host compiler cannot take.  FMPM_HOST_EMU is only ever defined by tests/cuda_emu/cuda_runtime.h:
+// with that directory first on the include path g++ builds these translation units UNCHANGED, one host thread per CUDA thread, so the
+// kernel bodies and the host launch logic run under `pytest -m "not gpu"` (tests/test_cuda_emu_*.py).  nvcc never sees that header.
+#ifdef FMPM_HOST_EMU
+#define FMPM_LAUNCH(kern, grid, block, smem, stream, ...) cuemu::launch(dim3(grid), dim3(block), smem, [&]() { kern(__VA_ARGS__); })
+#define FMPM_DYN_SMEM(type, name) type* name = (type*)cuemu::dyn_smem()
+#else
+#define FMPM_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define FMPM_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 #define FMPM_CHECK_LAUNCH(h, name)                                                        \
   do {                                                                                    \
     cudaError_t e_ = cudaGetLastError();                                                  \

@@ -67,6 +67,7 @@ __device__ __forceinline__ void p2g_load_raw(const KParams& P, const int f, cons
   }
 }
 __device__ __forceinline__ void p2g_prefetch_l2(const KParams& P, const int f, const long long sl) {
+#ifndef FMPM_HOST_EMU
   if (sl < P.N) {
     const int s = (int)sl;
     asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pa + pa_idx(P, f, 0, s)));
@@ -77,6 +78,7 @@ __device__ __forceinline__ void p2g_prefetch_l2(const KParams& P, const int f, c
     asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pf + pf_idx(P, f, 1, s)));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pf8 + pf8_idx(P, f, s)));
   }
+#endif
 }
 __device__ __forceinline__ void p2g_unpack(const PRaw& R, PState& st) {
   st.x[0] = R.a0.x; st.x[1] = R.a0.y; st.x[2] = R.a0.z; st.meta = __float_as_int(R.a0.w);
@@ -311,8 +313,8 @@ int fmpm_p2g_impl(FmpmHandle* h, int f, int write_F, int ring_slot, void* stream
   if (P.N == 0) return 0;
   const long long warps = ((long long)P.N + 32 * P2G_ROUNDS - 1) / (32 * P2G_ROUNDS);
   const int blocks = (int)((warps + P2G_WARPS - 1) / P2G_WARPS);
-  if (write_F) k_p2g<true><<<blocks, P2G_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f);
-  else k_p2g<false><<<blocks, P2G_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f);
+  if (write_F) FMPM_LAUNCH(k_p2g<true>, blocks, P2G_WARPS * 32, 0, stream, P, f);
+  else FMPM_LAUNCH(k_p2g<false>, blocks, P2G_WARPS * 32, 0, stream, P, f);
   FMPM_CHECK_LAUNCH(h, "fmpm_p2g");
   return 0;
 }
@@ -328,7 +330,7 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring
   if ((nblk + grid - 1) / grid > 256) grid = (nblk + 255) / 256;  // keep <= 256 blocks per CTA (parallel flag fetch)
   // the flags are consumed (reset) here only when nothing later in the substep needs them: plain forward substeps
   const int reset_flags = (clear_pm && ring_slot < 0) ? 1 : 0;
-  k_grid_op<<<grid, 256, 0, (cudaStream_t)stream>>>(P, f, clear_pm, zero_ggv, reset_flags);
+  FMPM_LAUNCH(k_grid_op, grid, 256, 0, stream, P, f, clear_pm, zero_ggv, reset_flags);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op");
   return 0;
 }
@@ -340,7 +342,7 @@ int fmpm_g2p_impl(FmpmHandle* h, int f, int ring_slot, void* stream) {
   if (check_bound(h, "fmpm_g2p") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_g2p")) return 1;
   KParams P = make_kparams(h, ring_slot);
   if (P.N == 0) return 0;
-  k_g2p<<<(P.N + G2P_WARPS * 32 - 1) / (G2P_WARPS * 32), G2P_WARPS * 32, 0, (cudaStream_t)stream>>>(P, f);
+  FMPM_LAUNCH(k_g2p, (P.N + G2P_WARPS * 32 - 1) / (G2P_WARPS * 32), G2P_WARPS * 32, 0, stream, P, f);
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p");
   return 0;
 }
@@ -372,7 +374,7 @@ extern "C" int fmpm_substep_store(FmpmHandle* h, int f, void* stream) {
   KParams P = make_kparams(h, f);
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
-  k_clear_blocks<<<grid, 256, 0, (cudaStream_t)stream>>>(P);  // previous occupant of slot f
+  FMPM_LAUNCH(k_clear_blocks, grid, 256, 0, stream, P);  // previous occupant of slot f
   FMPM_CHECK_LAUNCH(h, "fmpm_substep_store(clear)");
   if (fmpm_p2g_impl(h, f, 1, f, stream)) return 1;
   if (fmpm_grid_op_impl(h, f, 0, 0, f, stream)) return 1;
@@ -410,7 +412,7 @@ extern "C" int fmpm_collect(FmpmHandle* h, int f, const FmpmCollector* c, void* 
   if (!c) { snprintf(h->err, sizeof(h->err), "fmpm_collect: null collector"); return 1; }
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_collect<<<(P.N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, f, *c);
+  FMPM_LAUNCH(k_collect, (P.N + 255) / 256, 256, 0, stream, P, f, *c);
   FMPM_CHECK_LAUNCH(h, "fmpm_collect");
   return 0;
 }
@@ -423,7 +425,7 @@ extern "C" int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const 
     return 2;
   }
   KParams P = make_kparams(h);
-  k_inject<<<(inj->flux + 31) / 32, 32, 0, (cudaStream_t)stream>>>(P, f, *inj, (const float*)e->pos, (const float*)e->quat, act_id, rand_row, (const int*)inv);
+  FMPM_LAUNCH(k_inject, (inj->flux + 31) / 32, 32, 0, stream, P, f, *inj, (const float*)e->pos, (const float*)e->quat, act_id, rand_row, (const int*)inv);
   FMPM_CHECK_LAUNCH(h, "fmpm_inject");
   return 0;
 }

@@ -160,7 +160,7 @@ extern "C" int fmpm_write_frame(FmpmHandle* h, int f, const void* x, const void*
   if (!x || !v || !C || !F || !used) { snprintf(h->err, sizeof(h->err), "fmpm_write_frame: null input"); return 1; }
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_write_planar<<<nblk(P.N, 256), 256, 0, (cudaStream_t)stream>>>(P, P.pa, P.pf, P.pf8, f, (const float*)x, (const float*)v, (const float*)C,
+  FMPM_LAUNCH(k_write_planar, nblk(P.N, 256), 256, 0, stream, P, P.pa, P.pf, P.pf8, f, (const float*)x, (const float*)v, (const float*)C,
                                                                      (const float*)F, (const int*)used, (const int*)mrow, (const int*)ids);
   FMPM_CHECK_LAUNCH(h, "fmpm_write_frame");
   return 0;
@@ -170,7 +170,7 @@ extern "C" int fmpm_read_frame(FmpmHandle* h, int f, void* x, void* v, void* C, 
   if (f < 0 || f > h->cfg.max_substeps_local) { snprintf(h->err, sizeof(h->err), "fmpm_read_frame: frame %d out of range", f); return 1; }
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_read_planar<<<nblk(P.N, 256), 256, 0, (cudaStream_t)stream>>>(P, P.pa, P.pf, P.pf8, f, (float*)x, (float*)v, (float*)C, (float*)F, (int*)used,
+  FMPM_LAUNCH(k_read_planar, nblk(P.N, 256), 256, 0, stream, P, P.pa, P.pf, P.pf8, f, (float*)x, (float*)v, (float*)C, (float*)F, (int*)used,
                                                                     (const int*)ids);
   FMPM_CHECK_LAUNCH(h, "fmpm_read_frame");
   return 0;
@@ -180,7 +180,7 @@ extern "C" int fmpm_write_grad(FmpmHandle* h, int g, const void* x, const void* 
   if (!h->buf.ga || (g & ~1)) { snprintf(h->err, sizeof(h->err), "fmpm_write_grad: no grad buffers / bad index"); return 1; }
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_write_planar<<<nblk(P.N, 256), 256, 0, (cudaStream_t)stream>>>(P, P.ga, P.gf, P.gf8, g, (const float*)x, (const float*)v, (const float*)C,
+  FMPM_LAUNCH(k_write_planar, nblk(P.N, 256), 256, 0, stream, P, P.ga, P.gf, P.gf8, g, (const float*)x, (const float*)v, (const float*)C,
                                                                      (const float*)F, nullptr, nullptr, (const int*)ids);
   FMPM_CHECK_LAUNCH(h, "fmpm_write_grad");
   return 0;
@@ -190,7 +190,7 @@ extern "C" int fmpm_read_grad(FmpmHandle* h, int g, void* x, void* v, void* C, v
   if (!h->buf.ga || (g & ~1)) { snprintf(h->err, sizeof(h->err), "fmpm_read_grad: no grad buffers / bad index"); return 1; }
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_read_planar<<<nblk(P.N, 256), 256, 0, (cudaStream_t)stream>>>(P, P.ga, P.gf, P.gf8, g, (float*)x, (float*)v, (float*)C, (float*)F, nullptr,
+  FMPM_LAUNCH(k_read_planar, nblk(P.N, 256), 256, 0, stream, P, P.ga, P.gf, P.gf8, g, (float*)x, (float*)v, (float*)C, (float*)F, nullptr,
                                                                     (const int*)ids);
   FMPM_CHECK_LAUNCH(h, "fmpm_read_grad");
   return 0;
@@ -237,7 +237,7 @@ extern "C" int fmpm_permute_grad(FmpmHandle* h, int gsrc, int gdst, const void* 
   if (!h->buf.ga || gsrc == gdst || ((gsrc | gdst) & ~1)) { snprintf(h->err, sizeof(h->err), "fmpm_permute_grad: bad buffers"); return 1; }
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_permute_grad<<<nblk(P.N, 256), 256, 0, (cudaStream_t)stream>>>(P, gsrc, gdst, (const int*)ids_src, (const int*)inv_dst);
+  FMPM_LAUNCH(k_permute_grad, nblk(P.N, 256), 256, 0, stream, P, gsrc, gdst, (const int*)ids_src, (const int*)inv_dst);
   FMPM_CHECK_LAUNCH(h, "fmpm_permute_grad");
   return 0;
 }
@@ -278,12 +278,12 @@ extern "C" int fmpm_sort(FmpmHandle* h, int f, const void* ids_in, void* ids_out
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  k_sort_keys<<<nblk(P.N, 256), 256, 0, st>>>(P, f, (int*)b.sort_keys_in, (int*)b.sort_vals_in);
+  FMPM_LAUNCH(k_sort_keys, nblk(P.N, 256), 256, 0, st, P, f, (int*)b.sort_keys_in, (int*)b.sort_vals_in);
   FMPM_CHECK_LAUNCH(h, "fmpm_sort(keys)");
   size_t bytes = (size_t)b.sort_tmp_bytes;
   CHECK_CUDA(h, "fmpm_sort(radix)", cub::DeviceRadixSort::SortPairs(b.sort_tmp, bytes, (const int*)b.sort_keys_in, (int*)b.sort_keys_out,
                                                                     (const int*)b.sort_vals_in, (int*)b.sort_vals_out, P.N, 0, sort_bits(h), st));
-  k_reorder<<<nblk(P.N, 256), 256, 0, st>>>(P, f, (const int*)b.sort_vals_out, (const int*)ids_in, (int*)ids_out, (int*)inv_out, (float4*)b.scratch_a,
+  FMPM_LAUNCH(k_reorder, nblk(P.N, 256), 256, 0, st, P, f, (const int*)b.sort_vals_out, (const int*)ids_in, (int*)ids_out, (int*)inv_out, (float4*)b.scratch_a,
                                             (float4*)b.scratch_f, (float*)b.scratch_f8);
   FMPM_CHECK_LAUNCH(h, "fmpm_sort(reorder)");
   const size_t N = P.N;
@@ -313,21 +313,21 @@ __global__ void k_write_grid(const int G, float4* __restrict__ a, float4* __rest
 extern "C" int fmpm_read_grid(FmpmHandle* h, void* v_in, void* mass, void* v_out, void* stream) {
   CHECK_BOUND(h, "fmpm_read_grid");
   KParams P = make_kparams(h);
-  k_read_grid<<<nblk(P.G, 256), 256, 0, (cudaStream_t)stream>>>(P.G, P.grid_pm, P.grid_v, (float*)v_in, (float*)mass, (float*)v_out);
+  FMPM_LAUNCH(k_read_grid, nblk(P.G, 256), 256, 0, stream, P.G, P.grid_pm, P.grid_v, (float*)v_in, (float*)mass, (float*)v_out);
   FMPM_CHECK_LAUNCH(h, "fmpm_read_grid");
   return 0;
 }
 extern "C" int fmpm_read_grid_grad(FmpmHandle* h, void* gv_in, void* gmass, void* gv_out, void* stream) {
   CHECK_BOUND(h, "fmpm_read_grid_grad");
   KParams P = make_kparams(h);
-  k_read_grid<<<nblk(P.G, 256), 256, 0, (cudaStream_t)stream>>>(P.G, P.ggrid_pm, P.ggrid_v, (float*)gv_in, (float*)gmass, (float*)gv_out);
+  FMPM_LAUNCH(k_read_grid, nblk(P.G, 256), 256, 0, stream, P.G, P.ggrid_pm, P.ggrid_v, (float*)gv_in, (float*)gmass, (float*)gv_out);
   FMPM_CHECK_LAUNCH(h, "fmpm_read_grid_grad");
   return 0;
 }
 extern "C" int fmpm_write_grid_grad(FmpmHandle* h, const void* gv_in, const void* gmass, const void* gv_out, void* stream) {
   CHECK_BOUND(h, "fmpm_write_grid_grad");
   KParams P = make_kparams(h);
-  k_write_grid<<<nblk(P.G, 256), 256, 0, (cudaStream_t)stream>>>(P.G, P.ggrid_pm, P.ggrid_v, (const float*)gv_in, (const float*)gmass, (const float*)gv_out);
+  FMPM_LAUNCH(k_write_grid, nblk(P.G, 256), 256, 0, stream, P.G, P.ggrid_pm, P.ggrid_v, (const float*)gv_in, (const float*)gmass, (const float*)gv_out);
   FMPM_CHECK_LAUNCH(h, "fmpm_write_grid_grad");
   return 0;
 }
@@ -443,25 +443,25 @@ __global__ void k_effector_apply_p(const FmpmEffector e, const int grad) {
 extern "C" int fmpm_effector_step(FmpmHandle* h, const FmpmEffector* e, int s, int s_global, const void* action, void* stream) {
   if (!h || !e) return 1;
   if ((s + 1) * h->cfg.n_substeps > h->cfg.max_substeps_local) { snprintf(h->err, sizeof(h->err), "fmpm_effector_step: step %d exceeds the local ring", s); return 1; }
-  k_effector_step<<<1, 32, 0, (cudaStream_t)stream>>>(*e, s, s_global, h->cfg.n_substeps, (const float*)action);
+  FMPM_LAUNCH(k_effector_step, 1, 32, 0, stream, *e, s, s_global, h->cfg.n_substeps, (const float*)action);
   FMPM_CHECK_LAUNCH(h, "fmpm_effector_step");
   return 0;
 }
 extern "C" int fmpm_effector_step_grad(FmpmHandle* h, const FmpmEffector* e, int s, int s_global, void* stream) {
   if (!h || !e) return 1;
-  k_effector_step_grad<<<1, 32, 0, (cudaStream_t)stream>>>(*e, s, s_global, h->cfg.n_substeps);
+  FMPM_LAUNCH(k_effector_step_grad, 1, 32, 0, stream, *e, s, s_global, h->cfg.n_substeps);
   FMPM_CHECK_LAUNCH(h, "fmpm_effector_step_grad");
   return 0;
 }
 extern "C" int fmpm_effector_apply_action_p(FmpmHandle* h, const FmpmEffector* e, void* stream) {
   if (!h || !e) return 1;
-  k_effector_apply_p<<<1, 32, 0, (cudaStream_t)stream>>>(*e, 0);
+  FMPM_LAUNCH(k_effector_apply_p, 1, 32, 0, stream, *e, 0);
   FMPM_CHECK_LAUNCH(h, "fmpm_effector_apply_action_p");
   return 0;
 }
 extern "C" int fmpm_effector_apply_action_p_grad(FmpmHandle* h, const FmpmEffector* e, void* stream) {
   if (!h || !e) return 1;
-  k_effector_apply_p<<<1, 32, 0, (cudaStream_t)stream>>>(*e, 1);
+  FMPM_LAUNCH(k_effector_apply_p, 1, 32, 0, stream, *e, 1);
   FMPM_CHECK_LAUNCH(h, "fmpm_effector_apply_action_p_grad");
   return 0;
 }
@@ -514,7 +514,7 @@ extern "C" int fmpm_loss_chamfer(FmpmHandle* h, int f, const void* ids, const vo
   CHECK_BOUND(h, "fmpm_loss_chamfer");
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_loss_chamfer<<<nblk(P.N, 256), 256, 0, (cudaStream_t)stream>>>(P, f, (const int*)ids, (const float*)tgt, mask, weight, (float*)loss_out);
+  FMPM_LAUNCH(k_loss_chamfer, nblk(P.N, 256), 256, 0, stream, P, f, (const int*)ids, (const float*)tgt, mask, weight, (float*)loss_out);
   FMPM_CHECK_LAUNCH(h, "fmpm_loss_chamfer");
   return 0;
 }
@@ -523,7 +523,7 @@ extern "C" int fmpm_loss_chamfer_grad(FmpmHandle* h, int f, int g, const void* i
   if (!h->buf.ga || (g & ~1)) { snprintf(h->err, sizeof(h->err), "fmpm_loss_chamfer_grad: no grad buffers / bad index"); return 1; }
   KParams P = make_kparams(h);
   if (P.N == 0) return 0;
-  k_loss_chamfer_grad<<<nblk(P.N, 256), 256, 0, (cudaStream_t)stream>>>(P, f, g, (const int*)ids, (const float*)tgt, mask, weight);
+  FMPM_LAUNCH(k_loss_chamfer_grad, nblk(P.N, 256), 256, 0, stream, P, f, g, (const int*)ids, (const float*)tgt, mask, weight);
   FMPM_CHECK_LAUNCH(h, "fmpm_loss_chamfer_grad");
   return 0;
 }

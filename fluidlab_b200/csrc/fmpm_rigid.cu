@@ -253,10 +253,10 @@ int fmpm_advect_rigid_impl(FmpmHandle* h, int f, void* stream) {
   const int* info = (const int*)b.info;
   if (cudaMemsetAsync(state, 0, sizeof(float) * (size_t)b.n_bodies * BS, st) != cudaSuccess) { snprintf(h->err, sizeof(h->err), "fmpm_advect_rigid: memset failed"); return 1; }
   const int blocks = (P.N + 255) / 256;
-  k_body_com<<<blocks, 256, 0, st>>>(P, f, info, state, b.n_bodies);
-  k_body_H<<<blocks, 256, 0, st>>>(P, f, info, state, b.n_bodies);
-  k_body_solve<<<(b.n_bodies + 31) / 32, 32, 0, st>>>(info, state, b.n_bodies);
-  k_body_advect<<<blocks, 256, 0, st>>>(P, f, info, state, b.n_bodies);
+  FMPM_LAUNCH(k_body_com, blocks, 256, 0, st, P, f, info, state, b.n_bodies);
+  FMPM_LAUNCH(k_body_H, blocks, 256, 0, st, P, f, info, state, b.n_bodies);
+  FMPM_LAUNCH(k_body_solve, (b.n_bodies + 31) / 32, 32, 0, st, info, state, b.n_bodies);
+  FMPM_LAUNCH(k_body_advect, blocks, 256, 0, st, P, f, info, state, b.n_bodies);
   FMPM_CHECK_LAUNCH(h, "fmpm_advect_rigid");
   return 0;
 }
@@ -278,9 +278,9 @@ extern "C" int fmpm_advect_rigid_grad(FmpmHandle* h, int f, int gin, const void*
   const int* info = (const int*)b.info;
   if (cudaMemsetAsync(bg, 0, sizeof(float) * (size_t)b.n_bodies * BG, st) != cudaSuccess) { snprintf(h->err, sizeof(h->err), "fmpm_advect_rigid_grad: memset failed"); return 1; }
   const int blocks = (P.N + 255) / 256;
-  k_body_grad_reduce<<<blocks, 256, 0, st>>>(P, f, gin, info, state, bg, b.n_bodies);
-  k_body_grad_solve<<<(b.n_bodies + 31) / 32, 32, 0, st>>>(info, state, bg, b.n_bodies);
-  k_body_grad_apply<<<blocks, 256, 0, st>>>(P, f, gin, (const int*)next_slot, info, state, bg, b.n_bodies);
+  FMPM_LAUNCH(k_body_grad_reduce, blocks, 256, 0, st, P, f, gin, info, state, bg, b.n_bodies);
+  FMPM_LAUNCH(k_body_grad_solve, (b.n_bodies + 31) / 32, 32, 0, st, info, state, bg, b.n_bodies);
+  FMPM_LAUNCH(k_body_grad_apply, blocks, 256, 0, st, P, f, gin, (const int*)next_slot, info, state, bg, b.n_bodies);
   FMPM_CHECK_LAUNCH(h, "fmpm_advect_rigid_grad");
   return 0;
 }

@@ -17,6 +17,11 @@
 #define SC_FULL 0xffffffffu
 #define SC_WSTR 33
 
+#ifdef FMPM_HOST_EMU   // host build of the CUDA execution-model tests (tests/cuda_emu/): no PTX there
+__device__ __forceinline__ void red_add_v4(float4* addr, const float4& v) { atomicAdd(&addr->x, v.x); atomicAdd(&addr->y, v.y); atomicAdd(&addr->z, v.z); atomicAdd(&addr->w, v.w); }
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#else
 __device__ __forceinline__ void red_add_v4(float4* addr, const float4& v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -35,6 +40,7 @@ __device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
       : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
   return d;
 }
+#endif
 
 #define SC_REC 10
 struct __align__(16) ScatterSmem {

@@ -56,16 +56,6 @@ static SParams make_sparams(const FsmkHandle* h) {
   return P;
 }
 
-// kernel launch.  FSMK_HOST_EMU is only ever defined by tests/cuda_emu/cuda_runtime.h, which lets the HOST compiler build this file with one
-// host thread per CUDA thread (tests/test_smoke_cuda_emu.py); nvcc always takes the second branch.
-#ifdef FSMK_HOST_EMU
-#define FSMK_LAUNCH(kern, grid, block, smem, stream, ...) cuemu::launch(dim3(grid), dim3(block), smem, [&]() { kern(__VA_ARGS__); })
-#define FSMK_DYN_SMEM(type, name) type* name = (type*)cuemu::dyn_smem()
-#else
-#define FSMK_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__)
-#define FSMK_DYN_SMEM(type, name) extern __shared__ type name[]
-#endif
-
 #define FSMK_CHECK_LAUNCH(h, name)                                                   \
   do {                                                                               \
     cudaError_t e_ = cudaGetLastError();                                             \
@@ -229,7 +219,7 @@ __global__ void __launch_bounds__(256) k_divergence(const SParams P, const int s
 template <bool kGrad>
 __global__ void __launch_bounds__(256) k_jacobi_tile(const SParams P, const int s, const float* __restrict__ pin, float* __restrict__ pout, float* __restrict__ acc_out,
                                                       const int ns, const int first) {
-  FSMK_DYN_SMEM(float, sm);
+  FMPM_DYN_SMEM(float, sm);
   const int H = P.H, cells = H * JT_L * JT_L;
   float* a0 = sm; float* a1 = a0 + cells; float* aux = a1 + cells;            // aux: div (forward) or acc (adjoint)
   unsigned char* mk = (unsigned char*)(aux + cells);
@@ -529,14 +519,14 @@ extern "C" int fsmk_free_space(FsmkHandle* h, int s, void* stream) {
   if (check(h, "fsmk_free_space", s, false)) return 1;
   SParams P = make_sparams(h);
   if (P.H == 0) return 0;
-  FSMK_LAUNCH(k_free_space, band_blocks(P, 256), 256, 0,stream, P, s);
+  FMPM_LAUNCH(k_free_space, band_blocks(P, 256), 256, 0,stream, P, s);
   FSMK_CHECK_LAUNCH(h, "fsmk_free_space");
   return 0;
 }
 extern "C" int fsmk_advect(FsmkHandle* h, int s, int f, void* stream) {
   if (check(h, "fsmk_advect", s, false) || check_air(h, "fsmk_advect")) return 1;
   SParams P = make_sparams(h);
-  FSMK_LAUNCH(k_advect, (P.G + 255) / 256, 256, 0, stream, P, s, f);
+  FMPM_LAUNCH(k_advect, (P.G + 255) / 256, 256, 0, stream, P, s, f);
   FSMK_CHECK_LAUNCH(h, "fsmk_advect");
   return 0;
 }
@@ -544,7 +534,7 @@ extern "C" int fsmk_divergence(FsmkHandle* h, int s, void* stream) {
   if (check(h, "fsmk_divergence", s, false)) return 1;
   SParams P = make_sparams(h);
   if (P.H == 0) return 0;
-  FSMK_LAUNCH(k_divergence, band_blocks(P, 256), 256, 0,stream, P, s);
+  FMPM_LAUNCH(k_divergence, band_blocks(P, 256), 256, 0,stream, P, s);
   FSMK_CHECK_LAUNCH(h, "fsmk_divergence");
   return 0;
 }
@@ -564,9 +554,9 @@ static int jacobi_chain(FsmkHandle* h, const SParams& P, int s, const float* src
     if (tiled) {
       const dim3 grid((P.n + JT_OUT - 1) / JT_OUT, (P.n + JT_OUT - 1) / JT_OUT);
       const size_t smem = (size_t)P.H * JT_L * JT_L * (3 * sizeof(float) + 1);
-      FSMK_LAUNCH(k_jacobi_tile<kGrad>, grid, 256, smem, stream, P, s, in, out, acc, ns, l == 0);
+      FMPM_LAUNCH(k_jacobi_tile<kGrad>, grid, 256, smem, stream, P, s, in, out, acc, ns, l == 0);
     } else {
-      FSMK_LAUNCH(k_jacobi_simple<kGrad>, band_blocks(P, 256), 256, 0,stream, P, s, in, out, acc, ns, l == 0);
+      FMPM_LAUNCH(k_jacobi_simple<kGrad>, band_blocks(P, 256), 256, 0,stream, P, s, in, out, acc, ns, l == 0);
     }
     FSMK_CHECK_LAUNCH(h, name);
     in = out; done += ns;
@@ -583,7 +573,7 @@ extern "C" int fsmk_project(FsmkHandle* h, int s, void* stream) {
   if (check(h, "fsmk_project", s, false)) return 1;
   SParams P = make_sparams(h);
   if (P.H == 0) return 0;
-  FSMK_LAUNCH(k_project, band_blocks(P, 256), 256, 0,stream, P, s);
+  FMPM_LAUNCH(k_project, band_blocks(P, 256), 256, 0,stream, P, s);
   FSMK_CHECK_LAUNCH(h, "fsmk_project");
   return 0;
 }
@@ -596,7 +586,7 @@ extern "C" int fsmk_project_grad(FsmkHandle* h, int s, void* stream) {
   if (check(h, "fsmk_project_grad", s, true)) return 1;
   SParams P = make_sparams(h);
   if (P.H == 0) return 0;
-  FSMK_LAUNCH(k_project_grad, band_blocks(P, 256), 256, 0,stream, P, s);
+  FMPM_LAUNCH(k_project_grad, band_blocks(P, 256), 256, 0,stream, P, s);
   FSMK_CHECK_LAUNCH(h, "fsmk_project_grad");
   return 0;
 }
@@ -609,7 +599,7 @@ extern "C" int fsmk_pressure_grad(FsmkHandle* h, int s, void* stream) {
   const int launches = h->cfg.solver_iters == 0 ? 1 : (h->cfg.solver_iters + per - 1) / per;
   float* res = (float*)(((launches - 1) & 1) ? h->buf.tmp_b : h->buf.tmp_a);
   if (jacobi_chain<true>(h, P, s, P.gp + (size_t)(s + 1) * P.G, res, stream, "fsmk_pressure_grad")) return 1;
-  FSMK_LAUNCH(k_pressure_grad_finish, band_blocks(P, 256), 256, 0,stream, P, s, res, (const float*)h->buf.acc);
+  FMPM_LAUNCH(k_pressure_grad_finish, band_blocks(P, 256), 256, 0,stream, P, s, res, (const float*)h->buf.acc);
   FSMK_CHECK_LAUNCH(h, "fsmk_pressure_grad(finish)");
   return 0;
 }
@@ -617,7 +607,7 @@ extern "C" int fsmk_divergence_grad(FsmkHandle* h, int s, void* stream) {
   if (check(h, "fsmk_divergence_grad", s, true)) return 1;
   SParams P = make_sparams(h);
   if (P.H == 0) return 0;
-  FSMK_LAUNCH(k_divergence_grad, band_blocks(P, 256), 256, 0,stream, P, s);
+  FMPM_LAUNCH(k_divergence_grad, band_blocks(P, 256), 256, 0,stream, P, s);
   FSMK_CHECK_LAUNCH(h, "fsmk_divergence_grad");
   return 0;
 }
@@ -625,10 +615,10 @@ extern "C" int fsmk_advect_grad(FsmkHandle* h, int s, int f, void* stream) {
   if (check(h, "fsmk_advect_grad", s, true) || check_air(h, "fsmk_advect_grad")) return 1;
   SParams P = make_sparams(h);
   if (P.H > 0) {
-    FSMK_LAUNCH(k_advect_grad, band_blocks(P, 128), 128, 0,stream, P, s, f);
+    FMPM_LAUNCH(k_advect_grad, band_blocks(P, 128), 128, 0,stream, P, s, f);
     FSMK_CHECK_LAUNCH(h, "fsmk_advect_grad");
   }
-  FSMK_LAUNCH(k_advect_grad_nonfree, (P.G + 255) / 256, 256, 0, stream, P, s);
+  FMPM_LAUNCH(k_advect_grad_nonfree, (P.G + 255) / 256, 256, 0, stream, P, s);
   FSMK_CHECK_LAUNCH(h, "fsmk_advect_grad(nonfree)");
   return 0;
 }

@@ -1,7 +1,7 @@
 // tests/cuda_emu/cuda_runtime.h — TEST INFRASTRUCTURE ONLY: a tiny model of the CUDA execution model for the HOST compiler.
 //
 // There is no GPU in the build container.  With this directory first on the include path, `g++ -x c++ file.cu` compiles a .cu translation
-// unit of the product unchanged: kernels become ordinary functions and FSMK_LAUNCH (the product's launch macro) runs them with one real
+// unit of the product unchanged: kernels become ordinary functions and FMPM_LAUNCH (the product's launch macro) runs them with one real
 // host thread per CUDA thread, one block at a time — so __syncthreads, __shared__ memory, warp shuffles and atomics behave as on the
 // device.  tests/test_smoke_cuda_emu.py uses it to check the kernel bodies AND the host launch logic of fluidlab_b200/csrc/fsmk_smoke.cu
 // against the oracle before any GPU time is spent.  Nothing here is reachable from the product: libfluidmpm.so is built by nvcc only.
@@ -24,7 +24,8 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
-#define FSMK_HOST_EMU 1
+#define __align__(n) alignas(n)
+#define FMPM_HOST_EMU 1
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
@@ -45,9 +46,14 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "cuda_emu"; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s_, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s_, n); return cudaSuccess; }
+struct cudaDeviceProp { int multiProcessorCount; };
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 2; return cudaSuccess; }   // few SMs: small grids, fewer host threads
 
 namespace cuemu {
-struct Warp { float slot[32]; std::unique_ptr<std::barrier<>> bar; };
+struct Warp { unsigned long long slot[32]; std::unique_ptr<std::barrier<>> bar; };
 struct Block { std::unique_ptr<std::barrier<>> bar; std::vector<Warp> warps; std::vector<unsigned char> smem; };
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline thread_local dim3 t_blockDim, t_gridDim;
@@ -70,8 +76,9 @@ template <class F> inline void launch(dim3 grid, dim3 block, size_t smem, F&& bo
         t_threadIdx = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
         t_blockIdx = uint3{bx, by, bz}; t_blockDim = block; t_gridDim = grid; t_block = &B; t_lin = t;
         body();
-        // a thread that leaves early must not strand the others at a later barrier: the product's kernels only use barriers / shuffles on
-        // paths every thread of the block takes, which is what the device requires as well
+        // like the hardware, a thread that has exited no longer takes part in the barriers / warp collectives of the others
+        B.warps[t / 32].bar->arrive_and_drop();
+        B.bar->arrive_and_drop();
       });
     }
     for (auto& x : th) x.join();
@@ -86,17 +93,39 @@ inline void* dyn_smem() { return t_block->smem.data(); }
 #define gridDim (cuemu::t_gridDim)
 
 static inline void __syncthreads() { cuemu::t_block->bar->arrive_and_wait(); }
-static inline float cuemu_shfl(float x, int src_lane) {
+static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::t_block->warps[cuemu::t_lin / 32].bar->arrive_and_wait(); }
+// every lane of the warp publishes a value, then reads what it needs (lanes that have exited keep their last published value)
+template <class T, class F> static inline auto cuemu_collective(T x, F&& read) {
+  static_assert(sizeof(T) <= 8, "warp slots are 8 bytes");
   cuemu::Warp& w = cuemu::t_block->warps[cuemu::t_lin / 32];
   const int lane = cuemu::t_lin % 32;
-  w.slot[lane] = x;
+  unsigned long long raw = 0; memcpy(&raw, &x, sizeof(T));
+  w.slot[lane] = raw;
   w.bar->arrive_and_wait();
-  const float r = (src_lane >= 0 && src_lane < 32) ? w.slot[src_lane] : x;
+  auto get = [&](int l) { T v; memcpy(&v, &w.slot[l], sizeof(T)); return v; };
+  auto r = read(get, lane);
   w.bar->arrive_and_wait();
   return r;
 }
-static inline float __shfl_down_sync(unsigned, float x, int off) { return cuemu_shfl(x, cuemu::t_lin % 32 + off); }
-static inline float __shfl_xor_sync(unsigned, float x, int m) { return cuemu_shfl(x, (cuemu::t_lin % 32) ^ m); }
+template <class T> static inline T __shfl_sync(unsigned, T x, int src) { return cuemu_collective(x, [&](auto get, int) { return get(src & 31); }); }
+template <class T> static inline T __shfl_down_sync(unsigned, T x, int off) { return cuemu_collective(x, [&](auto get, int lane) { return lane + off < 32 ? get(lane + off) : x; }); }
+template <class T> static inline T __shfl_up_sync(unsigned, T x, int off) { return cuemu_collective(x, [&](auto get, int lane) { return lane - off >= 0 ? get(lane - off) : x; }); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T x, int m) { return cuemu_collective(x, [&](auto get, int lane) { return get(lane ^ m); }); }
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+  return cuemu_collective((int)(pred != 0), [&](auto get, int) { unsigned b = 0; for (int l = 0; l < 32; l++) if (((mask >> l) & 1u) && get(l)) b |= 1u << l; return b; });
+}
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+template <class T> static inline T __reduce_min_sync(unsigned mask, T x) {
+  return cuemu_collective(x, [&](auto get, int) { T m = x; for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) m = std::min(m, get(l)); return m; });
+}
+template <class T> static inline T __reduce_max_sync(unsigned mask, T x) {
+  return cuemu_collective(x, [&](auto get, int) { T m = x; for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) m = std::max(m, get(l)); return m; });
+}
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+template <class T> static inline T __ldcs(const T* p) { return *p; }
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 static inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_relaxed); }
 template <class T> static inline T __ldg(const T* p) { return *p; }

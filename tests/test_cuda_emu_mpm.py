@@ -1,0 +1,87 @@
+"""The WHOLE product on CPU: fluidlab_b200's Python host driving its real .cu translation units, compiled by g++ against a model of the
+CUDA execution model (tests/cuda_emu/: one host thread per CUDA thread; __syncthreads, shared memory, warp collectives, atomics, the
+time-blocked tiles ... behave as on the device), with CPU tensors in place of HBM.
+
+Why: the build container has no GPU and GPU minutes are rationed, so this is where kernel logic and host sequencing get checked on every
+`pytest -m "not gpu"` run — against the same oracle the GPU parity tests use.  It says nothing about performance or about hardware
+behaviour beyond the programming model; tests/test_gpu_parity.py and tests/test_zz_smoke_gpu.py remain the parity gate on a B200."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'cuda_emu'))
+import harness  # noqa: E402
+
+from conftest import make_particles  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+@pytest.fixture
+def emu():
+    L = harness.enable()
+    yield L
+    harness.disable()
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def test_product_fails_loudly_without_cuda_when_the_emulation_is_off():
+    from fluidlab_b200 import MPMSimulator
+    assert not harness._state
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        MPMSimulator(dim=3, quality=0.25, gravity=(0, -10, 0), horizon=10, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu')
+
+
+def test_mpm_kernels_forward_and_backward_match_the_fp64_oracle(emu):
+    """k_p2g (register sliding-window scatter, warp-local key ranking), k_grid_op (sparse blocks, cube walls), k_g2p, the cell sort, the
+    stored-grid backward (k_g2p_grad_scatter, k_grid_op_grad, k_particle_grad with the SVD adjoint) on water + elastic + plasto-elastic
+    particles: one step (10 substeps) forward and backward through MPMSimulator.step / step_grad."""
+    from fluidlab_b200 import MPMSimulator, macros as M
+    rng = np.random.RandomState(3)
+    n, N = 16, 300
+    x = rng.uniform(0.35, 0.65, size=(N, 3)).astype(np.float32)
+    mat = np.array([[M.WATER, M.ELASTIC, M.ICECREAM][i % 3] for i in range(N)], dtype=np.int32)
+    v0 = (rng.randn(N, 3) * 0.5).astype(np.float32)
+    # F0 away from the identity: with equal singular values the SVD adjoint sits on its 1e-8 clamp and fp32 results split into branches
+    F0 = (np.eye(3)[None] + rng.randn(N, 3, 3) * 0.05).astype(np.float32); C0 = (rng.randn(N, 3, 3) * 2.0).astype(np.float32)
+    P = make_particles(x, mat, n)
+    bnd = dict(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.7, 0.7, 0.7))
+    for store in (True, False):
+        s = MPMSimulator(dim=3, quality=n / 64, gravity=(0, -10, 0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+        s.use_graphs, s.store_grids = False, store
+        s.setup_boundary(**bnd)
+        s.build(None, None, [], P)
+        st = s.get_state(); st['v'][:] = v0; st['F'][:] = F0; st['C'][:] = C0; s.set_state(0, st)
+        s.enable_grad()
+        s.step(None)
+        fr = s.get_state()
+        w = rng.randn(N, 3).astype(np.float32)
+        z9 = np.zeros((N, 3, 3), np.float32)
+        s.reset_grad(); s.set_grad(w, np.zeros((N, 3), np.float32), z9, z9)
+        s.step_grad(None)
+        g = s.get_grad()
+        o = orc.OracleSim(n, P, gravity=(0, -10, 0), boundary=bnd, precision=64, max_substeps_local=20)
+        o.set_frame(0, x, v0, C0, F0, np.ones(N, np.int32))
+        o.enable_grad(); o.step(None)
+        ofr = o.get_frame(10)
+        o.reset_grad(); o.set_grad_frame(10, w, np.zeros((N, 3)), z9, z9); o.step_grad(None)
+        og = o.get_grad_frame(0)
+        assert rel(fr['x'], ofr['x']) < 1e-6 and rel(fr['F'], ofr['F']) < 1e-5 and rel(fr['v'], ofr['v']) < 1e-4, {k: rel(fr[k], ofr[k]) for k in 'xvCF'}
+        for k in 'xvCF':
+            assert rel(g[k], og[k]) < 1e-4, (store, k, rel(g[k], og[k]))
+
+
+def test_circulation_stack_on_the_emulated_device(emu):
+    """AgentCirculation + AirCon + SmokeField + CirculationLoss + parked MPM particles through TaichiEnv (reduced: 24^3 smoke grid, 10 sweeps)"""
+    from circulation_case import run_circulation_stack
+    dets = [[5, 16], [7, 16], [3, 16], [5, 14], [5, 18], [5, 8], [7, 8], [3, 8], [5, 6], [5, 10], [20, 12], [21, 12], [18, 12], [20, 9], [20, 16]]
+    run_circulation_stack(device='cpu', res=24, iters=10, band=(8, 14), detectors=dets, detector_h=11, n_steps=3, max_substeps_local=40)
