@@ -1,20 +1,23 @@
 // tests/cuda_emu/cuda_runtime.h — TEST INFRASTRUCTURE ONLY: a tiny model of the CUDA execution model for the HOST compiler.
 //
 // There is no GPU in the build container.  With this directory first on the include path, `g++ -x c++ file.cu` compiles a .cu translation
-// unit of the product unchanged: kernels become ordinary functions and FMPM_LAUNCH (the product's launch macro) runs them with one real
-// host thread per CUDA thread, one block at a time — so __syncthreads, __shared__ memory, warp shuffles and atomics behave as on the
-// device.  tests/test_smoke_cuda_emu.py uses it to check the kernel bodies AND the host launch logic of fluidlab_b200/csrc/fsmk_smoke.cu
+// unit of the product unchanged: kernels become ordinary functions and FMPM_LAUNCH (the product's launch macro) runs them with one
+// user-space fiber per CUDA thread, a block per OS worker thread — so __syncthreads, __shared__ memory, warp shuffles and atomics
+// behave as on the device.  tests/test_smoke_cuda_emu.py uses it to check the kernel bodies AND the host launch logic of fluidlab_b200/csrc/fsmk_smoke.cu
 // against the oracle before any GPU time is spent.  Nothing here is reachable from the product: libfluidmpm.so is built by nvcc only.
 #pragma once
 #include <algorithm>
 #include <atomic>
-#include <barrier>
+#include <cstdio>
+#include <ucontext.h>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -23,7 +26,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local   /* one block at a time per OS worker thread */
 #define __align__(n) alignas(n)
 #define FMPM_HOST_EMU 1
 
@@ -53,59 +56,121 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSucces
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 2; return cudaSuccess; }   // few SMs: small grids, fewer host threads
 
 namespace cuemu {
-struct Warp { unsigned long long slot[32]; std::unique_ptr<std::barrier<>> bar; };
-struct Block { std::unique_ptr<std::barrier<>> bar; std::vector<Warp> warps; std::vector<unsigned char> smem; };
-inline thread_local uint3 t_threadIdx, t_blockIdx;
-inline thread_local dim3 t_blockDim, t_gridDim;
-inline thread_local Block* t_block = nullptr;
-inline thread_local int t_lin = 0;
-
-template <class F> inline void launch(dim3 grid, dim3 block, size_t smem, F&& body) {
-  const int nt = (int)(block.x * block.y * block.z);
-  if (nt % 32 != 0) abort();   // the shuffle model needs whole warps
-  for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
-    Block B;
-    B.bar = std::make_unique<std::barrier<>>(nt);
-    B.warps.resize(nt / 32);
-    for (auto& w : B.warps) w.bar = std::make_unique<std::barrier<>>(32);
-    B.smem.assign(smem + 16, 0);
-    std::vector<std::thread> th;
-    th.reserve(nt);
-    for (int t = 0; t < nt; t++) {
-      th.emplace_back([&, t]() {
-        t_threadIdx = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
-        t_blockIdx = uint3{bx, by, bz}; t_blockDim = block; t_gridDim = grid; t_block = &B; t_lin = t;
-        body();
-        // like the hardware, a thread that has exited no longer takes part in the barriers / warp collectives of the others
-        B.warps[t / 32].bar->arrive_and_drop();
-        B.bar->arrive_and_drop();
-      });
-    }
-    for (auto& x : th) x.join();
-  }
+// One CUDA thread = one user-space fiber (ucontext); one CUDA block = the fibers of one OS worker thread, scheduled round-robin and
+// switched only at barriers / warp collectives; blocks of a grid run concurrently on a few OS workers.  A barrier that can never complete
+// (a genuine synchronisation bug in a kernel) is detected and aborts with a message instead of hanging.
+enum { RUN = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3 };
+struct Fiber { ucontext_t ctx; int state; uint3 tid; int lin; };
+struct BlockRun {
+  std::vector<Fiber> fib;
+  ucontext_t sched;
+  int cur = 0, nt = 0, alive = 0, arrived = 0;
+  std::vector<int> warp_alive, warp_arrived;
+  std::vector<unsigned long long> slots;   // 32 per warp
+  std::vector<unsigned char> smem;
+  uint3 bid; dim3 bdim, gdim;
+  const std::function<void()>* body = nullptr;
+};
+inline thread_local BlockRun* t_run = nullptr;
+inline Fiber& cur() { return t_run->fib[t_run->cur]; }
+inline void yield_to_sched() { BlockRun* r = t_run; swapcontext(&r->fib[r->cur].ctx, &r->sched); }
+inline void release(BlockRun* r, int what, int warp) {
+  for (auto& f : r->fib) if (f.state == what && (what == WAIT_BLOCK || f.lin / 32 == warp)) f.state = RUN;
 }
-inline void* dyn_smem() { return t_block->smem.data(); }
+inline void sync_block() {
+  BlockRun* r = t_run;
+  if (++r->arrived == r->alive) { r->arrived = 0; release(r, WAIT_BLOCK, 0); return; }
+  cur().state = WAIT_BLOCK; yield_to_sched();
+}
+inline void sync_warp() {
+  BlockRun* r = t_run; const int w = cur().lin / 32;
+  if (++r->warp_arrived[w] == r->warp_alive[w]) { r->warp_arrived[w] = 0; release(r, WAIT_WARP, w); return; }
+  cur().state = WAIT_WARP; yield_to_sched();
+}
+inline void fiber_main() {
+  BlockRun* r = t_run;
+  (*r->body)();
+  // like the hardware, a thread that has exited no longer takes part in the barriers / warp collectives of the others
+  Fiber& f = cur(); const int w = f.lin / 32;
+  f.state = DONE;
+  r->alive--; r->warp_alive[w]--;
+  if (r->alive > 0 && r->arrived == r->alive) { r->arrived = 0; release(r, WAIT_BLOCK, 0); }
+  if (r->warp_alive[w] > 0 && r->warp_arrived[w] == r->warp_alive[w]) { r->warp_arrived[w] = 0; release(r, WAIT_WARP, w); }
+  yield_to_sched();
+}
+struct Worker {   // per OS thread: fiber stacks are allocated once and reused
+  std::vector<char*> stacks;
+  static constexpr size_t STACK = 512 * 1024;
+  char* stack(int i) { while ((int)stacks.size() <= i) stacks.push_back((char*)aligned_alloc(64, STACK)); return stacks[i]; }
+};
+inline void run_block(Worker& wk, uint3 bid, dim3 block, dim3 grid, size_t smem, const std::function<void()>& body) {
+  const int nt = (int)(block.x * block.y * block.z);
+  BlockRun R;
+  R.fib.resize(nt); R.nt = R.alive = nt; R.warp_alive.assign(nt / 32, 32); R.warp_arrived.assign(nt / 32, 0); R.slots.assign(nt, 0);
+  R.smem.assign(smem + 16, 0); R.bid = bid; R.bdim = block; R.gdim = grid; R.body = &body;
+  t_run = &R;
+  for (int t = 0; t < nt; t++) {
+    Fiber& f = R.fib[t];
+    f.state = RUN; f.lin = t;
+    f.tid = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = wk.stack(t); f.ctx.uc_stack.ss_size = Worker::STACK; f.ctx.uc_link = &R.sched;
+    makecontext(&f.ctx, (void (*)())fiber_main, 0);
+  }
+  for (;;) {
+    bool progressed = false, all_done = true;
+    for (int t = 0; t < nt; t++) {
+      if (R.fib[t].state == RUN) { R.cur = t; swapcontext(&R.sched, &R.fib[t].ctx); progressed = true; }
+      if (R.fib[t].state != DONE) all_done = false;
+    }
+    if (all_done) break;
+    if (!progressed) { fprintf(stderr, "cuda_emu: deadlock in block (%u,%u,%u): a barrier / warp collective is not reached by every live thread\n", bid.x, bid.y, bid.z); abort(); }
+  }
+  t_run = nullptr;
+}
+template <class F> inline void launch(dim3 grid, dim3 block, size_t smem, F&& body_) {
+  const int nt = (int)(block.x * block.y * block.z);
+  if (nt % 32 != 0) abort();   // the warp model needs whole warps
+  const std::function<void()> body = body_;
+  const long long nb = (long long)grid.x * grid.y * grid.z;
+  const int nw = (int)std::min<long long>(nb, std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
+  std::atomic<long long> next{0};
+  auto work = [&]() {
+    static thread_local Worker wk;
+    for (;;) {
+      const long long b = next.fetch_add(1);
+      if (b >= nb) break;
+      run_block(wk, uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y))}, block, grid, smem, body);
+    }
+  };
+  if (nw == 1) { work(); return; }
+  std::vector<std::thread> th;
+  for (int i = 0; i < nw; i++) th.emplace_back(work);
+  for (auto& t : th) t.join();
+}
+inline void* dyn_smem() { return t_run->smem.data(); }
 }  // namespace cuemu
 
-#define threadIdx (cuemu::t_threadIdx)
-#define blockIdx (cuemu::t_blockIdx)
-#define blockDim (cuemu::t_blockDim)
-#define gridDim (cuemu::t_gridDim)
+#define threadIdx (cuemu::cur().tid)
+#define blockIdx (cuemu::t_run->bid)
+#define blockDim (cuemu::t_run->bdim)
+#define gridDim (cuemu::t_run->gdim)
 
-static inline void __syncthreads() { cuemu::t_block->bar->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::t_block->warps[cuemu::t_lin / 32].bar->arrive_and_wait(); }
+static inline void __syncthreads() { cuemu::sync_block(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::sync_warp(); }
 // every lane of the warp publishes a value, then reads what it needs (lanes that have exited keep their last published value)
 template <class T, class F> static inline auto cuemu_collective(T x, F&& read) {
   static_assert(sizeof(T) <= 8, "warp slots are 8 bytes");
-  cuemu::Warp& w = cuemu::t_block->warps[cuemu::t_lin / 32];
-  const int lane = cuemu::t_lin % 32;
+  cuemu::BlockRun* r = cuemu::t_run;
+  const int lin = cuemu::cur().lin, lane = lin % 32;
+  unsigned long long* slot = r->slots.data() + (lin / 32) * 32;
   unsigned long long raw = 0; memcpy(&raw, &x, sizeof(T));
-  w.slot[lane] = raw;
-  w.bar->arrive_and_wait();
-  auto get = [&](int l) { T v; memcpy(&v, &w.slot[l], sizeof(T)); return v; };
-  auto r = read(get, lane);
-  w.bar->arrive_and_wait();
-  return r;
+  slot[lane] = raw;
+  cuemu::sync_warp();
+  auto get = [&](int l) { T v; memcpy(&v, &slot[l], sizeof(T)); return v; };
+  auto res = read(get, lane);
+  cuemu::sync_warp();
+  return res;
 }
 template <class T> static inline T __shfl_sync(unsigned, T x, int src) { return cuemu_collective(x, [&](auto get, int) { return get(src & 31); }); }
 template <class T> static inline T __shfl_down_sync(unsigned, T x, int off) { return cuemu_collective(x, [&](auto get, int lane) { return lane + off < 32 ? get(lane + off) : x; }); }

@@ -85,3 +85,88 @@ def test_circulation_stack_on_the_emulated_device(emu):
     from circulation_case import run_circulation_stack
     dets = [[5, 16], [7, 16], [3, 16], [5, 14], [5, 18], [5, 8], [7, 8], [3, 8], [5, 6], [5, 10], [20, 12], [21, 12], [18, 12], [20, 9], [20, 16]]
     run_circulation_stack(device='cpu', res=24, iters=10, band=(8, 14), detectors=dets, detector_h=11, n_steps=3, max_substeps_local=40)
+
+
+# ---------------------------------------------------------------------------------------------------------------- x-slabs, 2 ranks (gloo)
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _slab_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        harness.enable()
+        from fluidlab_b200 import MPMSimulator, macros as M
+        from fluidlab_b200.slab import SlabMPMSimulator, slab_bounds, centre_plane
+        rng = np.random.RandomState(21)
+        n, Ntot, n_steps = 32, 700, 5
+        x = rng.uniform((0.32, 0.36, 0.36), (0.68, 0.54, 0.64), size=(Ntot, 3)).astype(np.float32)
+        v0 = np.where(x[:, 1:2] < 0.45, np.array([[6.0, 0.0, 0.5]]), np.array([[-6.0, 0.3, 0.0]])).astype(np.float32) + (rng.randn(Ntot, 3) * 0.2).astype(np.float32)
+        mat = np.where(x[:, 2] < 0.5, M.WATER, M.ELASTIC).astype(np.int32)
+        F0 = (np.eye(3)[None] + rng.randn(Ntot, 3, 3) * 0.04).astype(np.float32)
+        tgt = torch.from_numpy((x + rng.randn(Ntot, 3) * 0.05).astype(np.float32))
+        bounds = slab_bounds(0, 32, world)
+        cp = centre_plane(torch.from_numpy(x), float(n)).numpy()
+        mine = np.where((cp >= bounds[rank]) & (cp < bounds[rank + 1]))[0]
+
+        def parts(idx):
+            return dict(x=x[idx], mat=mat[idx], used=np.ones(len(idx), np.int32), rho=np.array([M.RHO[m] for m in mat[idx]]), body_id=np.zeros(len(idx), np.int32), bodies={'n': 1})
+        slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=len(mine) + 300, max_substeps_local=60, device='cpu', halo=4,
+                                exchange='nccl')
+        slab.sim.use_graphs = False
+        st = slab.sim.get_state()
+        st['v'][:len(mine)] = v0[mine]; st['F'][:len(mine)] = F0[mine]
+        slab.sim.set_state(0, st)
+        slab.enable_grad()
+        for _ in range(n_steps):
+            slab.step()
+        fwd = slab.gather_state()
+        ls = slab.local_state()
+        used = ls['used'] != 0
+        gx = 2.0 * (ls['x'] - tgt[ls['gid'].long().clamp(min=0)]) * used[:, None]
+        slab.set_final_grad(gx.clone())
+        for _ in range(n_steps):
+            slab.step_grad()
+        grad = slab.gather_grad()
+        out = dict(fwd=fwd, grad=grad, migrated=slab.n_migrated, rec=sorted(slab._records))
+        if rank == 0:   # the single-domain reference: the same product on the same emulated device
+            ref = MPMSimulator(dim=3, quality=0.5, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=60, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+            ref.use_graphs = False
+            ref.build(None, None, [], parts(np.arange(Ntot)))
+            s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
+            ref.enable_grad()
+            for _ in range(n_steps):
+                ref.step(None)
+            r = ref.get_state()
+            ref.reset_grad()
+            z9 = np.zeros((Ntot, 3, 3), np.float32)
+            ref.set_grad(2.0 * (r['x'] - tgt.numpy()), np.zeros((Ntot, 3), np.float32), z9, z9)
+            for _ in range(n_steps):
+                ref.step_grad(None)
+            out.update(ref_state={k: r[k] for k in ('x', 'v', 'F')}, ref_grad=ref.get_grad())
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_sharded_forward_and_backward_match_the_single_domain_run_on_the_emulated_device():
+    """the CUDA leg of the x-slab path that tests/run_slab_gpu.py exercises on 2 GPUs, here on 2 gloo ranks with the emulated device:
+    SlabMPMSimulator.step (ghost all-reduce of the accumulator, migration) and step_grad (fmpm_p2g(write_F=0) -> ghost sum ->
+    fmpm_substep_grad_scatter -> ghost sum of the v_out adjoint -> fmpm_substep_grad_finish, migrate_grad) against MPMSimulator on one
+    domain: states and dL/d(x0, v0, C0, F0)."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_slab_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    out = dict(ret)
+    N = 700
+    ref_s, ref_g = out[0]['ref_state'], out[0]['ref_grad']
+    for r in (0, 1):
+        fwd, grad = out[r]['fwd'], out[r]['grad']
+        assert np.array_equal(fwd['gid'], np.arange(N)) and np.array_equal(grad['gid'], np.arange(N)), 'particles lost or duplicated'
+        assert rel(fwd['x'], ref_s['x']) < 1e-5 and rel(fwd['F'], ref_s['F']) < 1e-5 and rel(fwd['v'], ref_s['v']) < 1e-4
+        errs = {k: rel(grad[k], ref_g[k].astype(np.float64)) for k in 'xvCF'}
+        assert errs['x'] < 1e-4 and errs['v'] < 1e-4 and errs['C'] < 2e-3 and errs['F'] < 2e-3, errs
+    assert out[0]['migrated'] > 0 and out[1]['migrated'] > 0 and len(out[0]['rec']) >= 2, (out[0]['migrated'], out[1]['migrated'], out[0]['rec'])
