@@ -10,6 +10,22 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    if os.environ.get("FLUIDLAB_CUDA_EMU") == "1":
+        # Development aid (never set by the driver): run `-m gpu` tests of SMALL scenes on the CUDA execution-model shim of tests/cuda_emu/, e.g.
+        #   FLUIDLAB_CUDA_EMU=1 python -m pytest tests/test_gpu_parity.py -m gpu -k "reference_kernels or rigid"
+        # Simulators built without an explicit device land on CPU tensors and the emulated library; anything that touches CUDA directly fails.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "cuda_emu"))
+        import harness
+        import torch
+        harness.enable()
+        torch.cuda.is_available = lambda: True
+        from fluidlab_b200 import simulator
+        init = simulator.MPMSimulator.__init__
+
+        def emu_init(self, *a, device=None, **k):
+            init(self, *a, device="cpu" if device is None else device, **k)
+            self.use_graphs = False
+        simulator.MPMSimulator.__init__ = emu_init
 
 
 def make_particles(x, mat_ids, n_grid, used=None, rho=None):
