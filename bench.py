@@ -148,6 +148,8 @@ def main():
     ap.add_argument('--particles', type=int, default=N_PARTICLES)
     ap.add_argument('--bwd', type=int, default=1, help='also time forward+backward (extra keys)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--fuse-g2p2g', type=int, default=0, help='1: forward steps use fmpm_substeps_fused (inner g2p / p2g pairs in one kernel; verified on the CPU '
+                    'execution-model shim, not yet measured on a B200 — A/B it against the default before switching)')
     ap.add_argument('--sort-every', type=int, default=4, help='cell-sort period in steps (measured with the warp-local key ranking: 1 -> 7.14k, 2 -> 7.43k, 4 -> 7.60k, 8 -> 7.44k substeps/s)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -174,6 +176,7 @@ def main():
                            ckpt_dest='gpu', device=dev, sort_every=args.sort_every)
         parts = workload_particles(N, seed=rank)
         sim.build(None, None, [], parts)
+        sim.fuse_g2p2g = bool(args.fuse_g2p2g)
         step_fn = lambda: sim.step(None)
         workload = f'C2 water block free fall, {N} particles, 128^3 grid, fp32, forward (BASELINE.json configs[1])'
         parallelism = 'single GPU'
@@ -264,7 +267,8 @@ def main():
         # ~40 us of host work per substep against ~130 us of device work), so stale-sort states weigh in exactly as they do in `value`.
         L_, h_ = sim._lib, sim._h
         evs, gts, rec = [], [], [False]
-        orig_substep, orig_graphs = L_.fmpm_substep, sim.use_graphs
+        orig_substep, orig_graphs, orig_fuse = L_.fmpm_substep, sim.use_graphs, sim.fuse_g2p2g
+        sim.fuse_g2p2g = False   # the per-kernel replay times the plain p2g / grid_op / g2p kernels (they are what SURVEY 8d's byte counts describe)
 
         def timed_substep(h, fr, stream):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -292,6 +296,7 @@ def main():
         finally:
             L_.fmpm_substep = orig_substep
             sim.use_graphs = orig_graphs
+            sim.fuse_g2p2g = orig_fuse
         t_p2g = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
         t_gop = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
         t_g2p = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
@@ -396,12 +401,13 @@ def main():
             'config': {'workload': workload,
                        'substeps_per_step': SUBSTEPS_PER_STEP, 'dt': 2e-4, 'gravity': GRAVITY, 'max_substeps_local': T,
                        'cell_sort_every_steps': args.sort_every,
+                       'g2p2g_fused': bool(args.fuse_g2p2g) and world == 1,
                        'l2_policy': 'inputs larger than L2 (one substep touches >= 212 B x 1M particles = 212 MB > 126 MB L2)',
                        'parallelism': parallelism},
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},
-            'gpu_launches': K * SUBSTEPS_PER_STEP * 3 + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
+            'gpu_launches': K * ((2 * SUBSTEPS_PER_STEP + 1) if (args.fuse_g2p2g and world == 1) else SUBSTEPS_PER_STEP * 3) + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
             'roofline': roof, 'roofline_p2g_g2p': roof_pair,
             'fwd_bwd': fb,
             'cpu_baseline': cpu,

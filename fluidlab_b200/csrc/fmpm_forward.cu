@@ -253,6 +253,98 @@ __global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const i
 }
 
 // =============================================================================================
+// g2p2g: g2p of frame f FUSED with p2g of frame f+1 (forward-only steps without agents; Wang et al. 2020 call the pattern G2P2G).
+// A particle's new velocity / affine matrix / position never leave registers between the gather and the next scatter, so an
+// intermediate substep moves x + meta (16 B) and F (36 B) in and out: 104 B per particle instead of the 212 B of p2g + g2p, and a
+// substep is two launches (grid_op, g2p2g) instead of three.  v and C of the intermediate frames are NOT materialised (kWriteVC =
+// false); the step's first p2g and last g2p are the plain kernels, so every step boundary holds a complete frame.
+// The scatter's warp-local key ranking (fmpm_scatter.cuh) absorbs the mismatch between the slot order (cells of the last sort)
+// and the cells of x[f+1].
+// =============================================================================================
+template <bool kWriteVC>
+__global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_g2p2g(const KParams P, const int f) {
+  __shared__ ScatterSmem smem[P2G_WARPS];
+  static_assert(sizeof(((ScatterSmem*)0)->rec) >= 9 * G2P_ZMAX * sizeof(float4), "the gather tile is staged in the scatter records' storage");
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  ScatterSmem& S = smem[wib];
+  float4* tile = S.rec;   // gather tile first, scatter records afterwards (a __syncwarp separates the two uses)
+  const long long slot0 = ((long long)blockIdx.x * P2G_WARPS + wib) * 32;
+  if (slot0 >= P.N) return;   // warp-uniform
+  const long long sl = slot0 + lane;
+  const long long rem = (long long)P.N - slot0;
+  const int cnt = rem < 32 ? (int)rem : 32;
+  Window W; window_init(W, lane, P.n, P.blk_flags);
+  // ---- g2p of frame f (MPM:304-316, 400-426, 497-505)
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sl < P.N) a0 = P2G_LD(&P.pa[pa_idx(P, f, 0, (int)sl)]);
+  const int meta = __float_as_int(a0.w);
+  const float x[3] = {a0.x, a0.y, a0.z};
+  int b[3]; float fx[3];
+  const bool ok = (sl < P.N) && (meta & 1) && base_fx(P, x, b, fx);
+  Footprint fp = footprint_of(ok, b);
+  if (fp.staged) footprint_load(P.grid_v, P.n, fp, tile);
+  int key = -1;
+  float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, m = 0.f;
+  float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  if (sl < P.N) {
+    const int s = (int)sl;
+    PState st;
+    {  // F[f+1] was written by the p2g / g2p2g of frame f
+      const float4 f0 = P2G_LD(&P.pf[pf_idx(P, f + 1, 0, s)]), f1 = P2G_LD(&P.pf[pf_idx(P, f + 1, 1, s)]);
+      st.F.m[0] = f0.x; st.F.m[1] = f0.y; st.F.m[2] = f0.z; st.F.m[3] = f0.w; st.F.m[4] = f1.x; st.F.m[5] = f1.y; st.F.m[6] = f1.z; st.F.m[7] = f1.w;
+      st.F.m[8] = P2G_LD(&P.pf8[pf8_idx(P, f + 1, s)]);
+    }
+    if (!ok) {  // unused (MPM:309-316) or frozen: the whole state is carried over unchanged
+      if (meta & 2) { a0.x = a0.y = a0.z = FMPM_NOWHERE; a0.w = __int_as_float(meta & ~3); }
+      P.pa[pa_idx(P, f + 1, 0, s)] = a0;
+      P.pa[pa_idx(P, f + 1, 1, s)] = P.pa[pa_idx(P, f, 1, s)];
+      P.pa[pa_idx(P, f + 1, 2, s)] = P.pa[pa_idx(P, f, 2, s)];
+      P.pa[pa_idx(P, f + 1, 3, s)] = P.pa[pa_idx(P, f, 3, s)];
+      p2g_store_F(P, f + 2, s, st.F);
+    } else {
+      bspline(fx, w);
+      const float c4 = 4.f * P.inv_dx;
+      if (fp.staged) {
+        const float4* t0 = tile + (b[2] - fp.kmin);
+        g2p_gather(fx, w, [&](int c) { return t0 + c * G2P_ZMAX; }, st.v, st.C, c4);
+      } else {
+        const float4* gv = P.grid_v + ((b[0] * P.n + b[1]) * P.n + b[2]);
+        const int n = P.n;
+        g2p_gather(fx, w, [&](int c) { return gv + ((c / 3) * n + (c % 3)) * n; }, st.v, st.C, c4);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; d++) st.x[d] = x[d] + P.dt * st.v[d];   // advect_kernel MPM:505
+      st.meta = meta;
+      // ---- p2g of frame f+1 (MPM:254-264, 331-378)
+      int b1[3]; float fx1[3];
+      const bool ok1 = base_fx(P, st.x, b1, fx1);
+      if (kWriteVC || !ok1) store_A(P.pa, P, f + 1, s, st.x, meta, st.v, st.C);
+      else P.pa[pa_idx(P, f + 1, 0, s)] = make_float4(st.x[0], st.x[1], st.x[2], __int_as_float(meta));
+      if (ok1) {
+        const float4 mt = __ldg(P.mats + ((meta >> 8) & 0xff));
+        Constit K; constitutive(P, st, mt.x, mt.y, mt.z, __float_as_int(mt.w), K);
+        m = mt.z;
+        bspline(fx1, w);
+#pragma unroll
+        for (int i = 0; i < 9; i++) B[i] = K.A.m[i] * P.dx;
+#pragma unroll
+        for (int i = 0; i < 3; i++) q[i] = m * st.v[i] - (B[i * 3] * fx1[0] + B[i * 3 + 1] * fx1[1] + B[i * 3 + 2] * fx1[2]);
+        key = pack_key(b1);
+        p2g_store_F(P, f + 2, s, K.Fn);
+      } else {
+        p2g_store_F(P, f + 2, s, st.F);
+      }
+    }
+  }
+  __syncwarp();   // every lane is done with the gather tile before the scatter staging is written
+  const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
+  __syncwarp();
+  window_consume(W, S, cnt, starts, P.grid_pm);
+  __syncwarp();
+  window_flush_all(W, P.grid_pm);
+}
+
+// =============================================================================================
 // injector act (agents/agent_injector.py:30-32 -> effectors/injector.py:80-105, 240-256)
 // =============================================================================================
 __device__ __forceinline__ void quat_rot(const float* q, const float* v, float* o) {  // utils/geom.py:92-97
@@ -380,6 +472,31 @@ extern "C" int fmpm_substep_store(FmpmHandle* h, int f, void* stream) {
   if (fmpm_grid_op_impl(h, f, 0, 0, f, stream)) return 1;
   if (fmpm_g2p_impl(h, f, f, stream)) return 1;
   return fmpm_advect_rigid_impl(h, f, stream);
+}
+
+// g2p(f) fused with p2g(f+1): forward-only steps without agents, MAT_RIGID bodies or slabs (see k_g2p2g)
+extern "C" int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream) {
+  if (check_bound(h, "fmpm_g2p2g") || check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_g2p2g")) return 1;
+  if (h->col.has_rigid || h->bodies.n_bodies > 0 || h->slab.enabled) {
+    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: not available with a rigid effector, MAT_RIGID bodies or x-slabs"); return 1;
+  }
+  KParams P = make_kparams(h);
+  if (P.N == 0) return 0;
+  const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
+  if (write_vc) FMPM_LAUNCH(k_g2p2g<true>, blocks, P2G_WARPS * 32, 0, stream, P, f);
+  else FMPM_LAUNCH(k_g2p2g<false>, blocks, P2G_WARPS * 32, 0, stream, P, f);
+  FMPM_CHECK_LAUNCH(h, "fmpm_g2p2g");
+  return 0;
+}
+// n forward substeps f0 .. f0+n-1 with the inner g2p / p2g pairs fused: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1).
+// Frames f0 and f0+n are complete; the frames in between hold x, used and F only.  The grid must be clear on entry (as for fmpm_substep).
+extern "C" int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream) {
+  if (n < 1) { if (h) snprintf(h->err, sizeof(h->err), "fmpm_substeps_fused: n must be >= 1"); return 1; }
+  if (fmpm_p2g(h, f0, 1, stream)) return 1;
+  for (int i = 0; i + 1 < n; i++)
+    if (fmpm_grid_op(h, f0 + i, 1, stream) || fmpm_g2p2g(h, f0 + i, 0, stream)) return 1;
+  if (fmpm_grid_op(h, f0 + n - 1, 1, stream)) return 1;
+  return fmpm_g2p(h, f0 + n - 1, stream);
 }
 
 extern "C" int fmpm_substep(FmpmHandle* h, int f, void* stream) {

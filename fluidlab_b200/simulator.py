@@ -83,6 +83,8 @@ class MPMSimulator:
         self.sort_every = int(sort_every)  # cell-sort period in steps (0 = never)
         self.use_graphs = True             # replay the 10 substeps of an agent-free step as one CUDA graph per local step index
         self.store_grids = True            # grad mode: keep each ring frame's forward grid in HBM instead of recomputing it in the backward
+        self.fuse_g2p2g = False            # forward-only agent-free steps: inner g2p / p2g pairs fused (fmpm_substeps_fused).  Verified on the
+                                           # CPU execution-model shim, NOT yet measured on a B200: opt-in until it is
         if device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError('fluidlab_b200.MPMSimulator needs a CUDA device (B200, sm_100a); there is no CPU fallback')
@@ -408,6 +410,10 @@ class MPMSimulator:
             return ids.to(torch.int32)
         return b.inv[ids.long()].to(torch.int32).contiguous()
 
+    def _can_fuse(self):
+        """g2p2g fusion applies to forward-only steps without an agent, MAT_RIGID bodies or stored grids (csrc/fmpm_forward.cu: k_g2p2g)"""
+        return bool(getattr(self, 'fuse_g2p2g', False)) and not self.grad_enabled and not getattr(self, '_has_rigid_bodies', False) and self.agent is None
+
     def _storing(self):
         if not (self.grad_enabled and self.store_grids):
             return False
@@ -429,8 +435,11 @@ class MPMSimulator:
                 g = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize(self.device)
                 with torch.cuda.graph(g):
-                    for i in range(self.n_substeps):
-                        self._ck(fn(self._h, f0 + i, self._stream()), 'fmpm_substep')
+                    if self._can_fuse():
+                        self._ck(self._lib.fmpm_substeps_fused(self._h, f0, self.n_substeps, self._stream()), 'fmpm_substeps_fused')
+                    else:
+                        for i in range(self.n_substeps):
+                            self._ck(fn(self._h, f0 + i, self._stream()), 'fmpm_substep')
                 self._graphs[(s_local, store)] = g
             except Exception:
                 self.use_graphs = False
@@ -577,6 +586,13 @@ class MPMSimulator:
         if self.has_particles and self.sort_every > 0 and self.cur_step_global % self.sort_every == 0:
             self.sort_frame(self.cur_substep_local)
         if self.use_graphs and is_none_action and self.has_particles and self._graph_substeps():
+            self.cur_substep_global += self.n_substeps
+        elif is_none_action and self.has_particles and self._can_fuse():
+            f0 = self.cur_substep_local
+            self._ck(self._lib.fmpm_substeps_fused(self._h, f0, self.n_substeps, self._stream()), 'fmpm_substeps_fused')
+            for i in range(self.n_substeps):
+                self._frame_ord[f0 + i + 1] = self._frame_ord[f0]
+                self._ring_valid[f0 + i] = False
             self.cur_substep_global += self.n_substeps
         else:
             for _ in range(self.n_substeps):

@@ -176,6 +176,12 @@ int fmpm_g2p(FmpmHandle* h, int f, void* stream);                      /* MPM:30
 int fmpm_advect_rigid(FmpmHandle* h, int f, void* stream);             /* MPM:449-505 for MAT_RIGID bodies; after fmpm_g2p (no-op without such bodies) */
 int fmpm_substep(FmpmHandle* h, int f, void* stream);                  /* p2g, grid_op(clear), g2p, advect_rigid; grid must be clear on entry */
 int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, but the grids of frame f stay in ring slot f */
+/* forward-only fusion (no reference counterpart): g2p of frame f + p2g of frame f+1 in one kernel — v, C and x stay in registers
+ * between the gather and the next scatter (104 B instead of 212 B per particle and substep).  write_vc = 0: v and C of frame f+1 are not
+ * materialised.  Not available with a rigid effector, MAT_RIGID bodies or x-slabs. */
+int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream);
+/* n substeps f0..f0+n-1: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1); frames f0 and f0+n are complete */
+int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream);
 /* agent.act for injector agents, agents/agent_injector.py:23-32; run after fmpm_g2p of the same f */
 int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,
                 const void* inv, void* stream);

@@ -170,3 +170,39 @@ def test_slab_sharded_forward_and_backward_match_the_single_domain_run_on_the_em
         errs = {k: rel(grad[k], ref_g[k].astype(np.float64)) for k in 'xvCF'}
         assert errs['x'] < 1e-4 and errs['v'] < 1e-4 and errs['C'] < 2e-3 and errs['F'] < 2e-3, errs
     assert out[0]['migrated'] > 0 and out[1]['migrated'] > 0 and len(out[0]['rec']) >= 2, (out[0]['migrated'], out[1]['migrated'], out[0]['rec'])
+
+
+def test_g2p2g_fused_substeps_equal_the_unfused_path(emu):
+    """fmpm_substeps_fused (p2g, [grid_op, g2p2g] x 9, grid_op, g2p: the inner gather / scatter pairs in ONE kernel, v and C never leaving
+    registers) against the plain p2g / grid_op / g2p substeps and against the fp64 oracle: water + elastic + plasto-elastic particles, 12 %
+    unused slots, cube walls, two steps (so the second starts from the complete frame the first one's final g2p wrote)."""
+    from fluidlab_b200 import MPMSimulator, macros as M
+    rng = np.random.RandomState(7)
+    n, N = 16, 330
+    x = rng.uniform(0.34, 0.66, size=(N, 3)).astype(np.float32)
+    mat = np.array([[M.WATER, M.ELASTIC, M.ICECREAM][i % 3] for i in range(N)], dtype=np.int32)
+    used = (rng.rand(N) > 0.12).astype(np.int32)
+    v0 = (rng.randn(N, 3) * 0.8).astype(np.float32)
+    F0 = (np.eye(3)[None] + rng.randn(N, 3, 3) * 0.05).astype(np.float32); C0 = (rng.randn(N, 3, 3) * 2.0).astype(np.float32)
+    P = make_particles(x, mat, n, used=used)
+    bnd = dict(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.7, 0.7, 0.7))
+    out = {}
+    for fuse in (False, True):
+        s = MPMSimulator(dim=3, quality=n / 64, gravity=(0.3, -10, 0), horizon=50, max_substeps_local=40, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+        s.use_graphs, s.fuse_g2p2g = False, fuse
+        s.setup_boundary(**bnd)
+        s.build(None, None, [], P)
+        st = s.get_state(); st['v'][:] = v0; st['F'][:] = F0; st['C'][:] = C0; s.set_state(0, st)
+        assert s._can_fuse() == fuse
+        s.step(None); s.step(None)
+        out[fuse] = s.get_state()
+    o = orc.OracleSim(n, P, gravity=(0.3, -10, 0), boundary=bnd, precision=64, max_substeps_local=40)
+    o.set_frame(0, x, v0, C0, F0, used)
+    o.step(None); o.step(None)
+    ofr = o.get_frame(20)
+    u = used != 0
+    assert np.array_equal(out[True]['used'], used) and np.array_equal(out[False]['used'], used)
+    for k, bar in (('x', 1e-6), ('F', 1e-5), ('v', 1e-4), ('C', 1e-3)):
+        assert rel(out[True][k][u], out[False][k][u].astype(np.float64)) < bar, (k, rel(out[True][k][u], out[False][k][u].astype(np.float64)))
+        assert rel(out[True][k][u], ofr[k][u]) < bar, (k, rel(out[True][k][u], ofr[k][u]))
+        assert np.array_equal(out[True][k][~u], out[False][k][~u]), 'parked particles must be carried over untouched'
