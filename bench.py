@@ -393,6 +393,32 @@ def main():
     e2e_ms = max_over_ranks(max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3))
     e2e_val = world * n_ep * EP * SUBSTEPS_PER_STEP / (e2e_ms * 1e-3)
 
+    # the same episodes with the observation assembled on the device (MPMSimulator.get_obs_RL): FluidEnv._get_obs keeps
+    # ~200 particles per body, so the per-step D2H shrinks from 28 B x N to a few KB.  Reported as an EXTRA key; `e2e` stays the full-state API.
+    e2e_obs = None
+    if slab is None:
+        try:
+            def episode_obs():
+                sim.cur_substep_global = 0
+                sim.set_state(0, pin)
+                out = None
+                for _ in range(EP):
+                    step_fn()
+                    out = sim.get_obs_RL(200)
+                return out
+            o = episode_obs(); barrier()
+            t0 = time.perf_counter()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n_ep):
+                episode_obs()
+            b.record(); barrier()
+            ms_o = max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3)
+            e2e_obs = {'value': n_ep * EP * SUBSTEPS_PER_STEP / (ms_o * 1e-3), 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(o.nbytes),
+                       'api': 'MPMSimulator.set_state(pinned host)/step/get_obs_RL(200): FluidEnv._get_obs assembled on the device'}
+        except Exception as ex:   # never let the extra measurement take the bench line down
+            e2e_obs = {'error': f'{type(ex).__name__}: {ex}'}
+
     if rank == 0:
         cpu = None if args.no_cpu else cpu_baseline_run(N)
         line = {
@@ -408,6 +434,7 @@ def main():
             'e2e': {'value': e2e_val, 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},
             'gpu_launches': K * ((2 * SUBSTEPS_PER_STEP + 1) if (args.fuse_g2p2g and world == 1) else SUBSTEPS_PER_STEP * 3) + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
+            'e2e_obs_bridge': e2e_obs,
             'roofline': roof, 'roofline_p2g_g2p': roof_pair,
             'fwd_bwd': fb,
             'cpu_baseline': cpu,

@@ -148,6 +148,7 @@ class MPMSimulator:
         self._mat_np = mat
         self._body_id_np = np.asarray(particles.get('body_id', np.zeros(N))).astype(np.int32)
         self.n_bodies = int(particles['bodies']['n']) if 'bodies' in particles else 1
+        self._bodies_info = particles.get('bodies')
         self._materials = torch.from_numpy(table.view(np.float32).reshape(-1, 4).copy()).to(dev)
         # bodies (MPM:177-201): n_particles counts every slot of the body, mat_cls is that of its first particle.  The body id rides
         # in bits 16..23 of the particle meta word (material row in bits 8..15), see include/fluidmpm.h.
@@ -549,6 +550,49 @@ class MPMSimulator:
         if self.smoke_field is not None:
             state['smoke_field'] = self.smoke_field.get_state(self.cur_step_local)
         return state
+
+    # ---- observation bridge: what envs/fluid_env.py:99-125 builds from get_state_RL, subsampled ON THE DEVICE
+    def build_obs_index(self, n_obs_ptcls_per_body=200, bodies=None):
+        """particle ids FluidEnv._get_obs keeps: per body `particle_ids[::max(1, n // n_obs_ptcls_per_body)]` (fluid_env.py:104-112)."""
+        if bodies is None:
+            bodies = getattr(self, '_bodies_info', None)
+        if not self.has_particles or bodies is None or 'particle_ids' not in bodies:
+            bodies = {'n': 1, 'n_particles': [self.n_particles], 'particle_ids': [np.arange(self.n_particles)]}
+        ids = []
+        for b in range(int(bodies['n'])):
+            pid = np.asarray(bodies['particle_ids'][b])
+            ids.append(pid[::max(1, int(bodies['n_particles'][b]) // int(n_obs_ptcls_per_body))])
+        self._obs_ids = [torch.from_numpy(np.ascontiguousarray(i, dtype=np.int64)).to(self.device) for i in ids]
+        return ids
+
+    def get_obs_RL(self, n_obs_ptcls_per_body=200):
+        """The observation vector of FluidEnv._get_obs (fluid_env.py:99-125) — per body x, v, used of the kept particles, then the agent
+        state, then the smoke field's v / q[::10, 60:68, ::10] — assembled on the device and copied to the host as ONE small array
+        (the reference moves the whole x, v, used state across PCIe every step, README.md:62).  Returns float32 numpy."""
+        f = self.cur_substep_local
+        parts = []
+        if self.has_particles:
+            if getattr(self, '_obs_ids', None) is None or getattr(self, '_obs_n', None) != n_obs_ptcls_per_body:
+                self.build_obs_index(n_obs_ptcls_per_body); self._obs_n = n_obs_ptcls_per_body
+            st = self.readframe_torch(f, ('x', 'v', 'used'))
+            for ids in self._obs_ids:
+                parts += [st['x'][ids].reshape(-1), st['v'][ids].reshape(-1), st['used'][ids].to(torch.float32).reshape(-1)]
+        if self.agent is not None:
+            for e in self.agent.effectors:
+                parts.append(torch.cat([e.pos[f], e.quat[f]]) if not hasattr(e, 's') else torch.cat([e.pos[f], e.quat[f], e.s[f:f + 1], e.r[f:f + 1]]))
+                if hasattr(e, 'act_id'):
+                    parts.append(torch.tensor([float(e.act_id[f])], dtype=torch.float32, device=self.device))
+        if self.smoke_field is not None:
+            sf, n = self.smoke_field, self.smoke_field.n_grid
+            s_loc = self.cur_step_local
+            v = sf._v[s_loc, :, :3].reshape(n, n, n, 3)[::10, 60:68, ::10]
+            q = sf._q[s_loc].reshape(sf.q_dim, n, n, n).permute(1, 2, 3, 0)[::10, 60:68, ::10]
+            parts += [v.reshape(-1), q.reshape(-1)]
+        dev = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.float32, device=self.device)
+        host = torch.empty(dev.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
 
     def get_state_render(self, f):  # MPM:705-707
         r = self.readframe(f, ('x', 'used'))

@@ -101,6 +101,10 @@ class TaichiEnv:
     def get_state_RL(self):
         return self.simulator.get_state_RL()
 
+    def get_obs_RL(self, n_obs_ptcls_per_body=200):
+        """FluidEnv._get_obs's vector (envs/fluid_env.py:99-125) assembled on the device: one small D2H instead of the full state"""
+        return self.simulator.get_obs_RL(n_obs_ptcls_per_body)
+
     def step(self, action=None):  # taichi_env.py:165-174
         if action is not None:
             assert self.agent is not None, 'Environment has no agent to execute action.'

@@ -206,3 +206,34 @@ def test_g2p2g_fused_substeps_equal_the_unfused_path(emu):
         assert rel(out[True][k][u], out[False][k][u].astype(np.float64)) < bar, (k, rel(out[True][k][u], out[False][k][u].astype(np.float64)))
         assert rel(out[True][k][u], ofr[k][u]) < bar, (k, rel(out[True][k][u], ofr[k][u]))
         assert np.array_equal(out[True][k][~u], out[False][k][~u]), 'parked particles must be carried over untouched'
+
+
+def test_device_side_observation_equals_fluid_env_get_obs(emu):
+    """MPMSimulator.get_obs_RL against envs/fluid_env.py:99-125 evaluated on the full get_state_RL() state: two
+    bodies with different strides, an injector agent (8-vector state) — the same numbers, one small host copy."""
+    from fluidlab_b200 import TaichiEnv, macros as M
+    env = TaichiEnv(dim=3, quality=0.25, particle_density=3e4, max_substeps_local=40, gravity=(0.0, -10.0, 0.0), horizon=20, ckpt_dest='cpu', device='cpu')
+    env.simulator.use_graphs = False
+    env.setup_agent(dict(type='AgentInjector', effectors=[dict(type='Injector', params=dict(radius=0.02, flux=2, init_pos=(0.5, 0.6, 0.5), inject_v=(0.0, -2.0, 0.0), action_dim=3),
+                                                               boundary=dict(type='cube', lower=(0.1, 0.1, 0.1), upper=(0.9, 0.9, 0.9)))]))
+    env.setup_boundary(type='cube', lower=(0.2, 0.2, 0.2), upper=(0.8, 0.8, 0.8))
+    env.add_body(type='nowhere', n_particles=60, material=M.MILK)
+    env.add_body(type='cube', lower=(0.35, 0.3, 0.35), upper=(0.65, 0.42, 0.65), material=M.WATER)
+    env.build()
+    for _ in range(2):
+        env.step(np.array([0.01, 0.0, -0.005]))
+    n_obs = 25
+    got = env.get_obs_RL(n_obs)
+    state = env.get_state_RL()
+    obs = []
+    bodies = env.particles['bodies']
+    assert bodies['n'] == 2
+    for b in range(bodies['n']):     # fluid_env.py:104-115, verbatim logic
+        ids = bodies['particle_ids'][b]
+        step = max(1, bodies['n_particles'][b] // n_obs)
+        obs += [state['x'][ids][::step].flatten(), state['v'][ids][::step].flatten(), state['used'][ids][::step].flatten()]
+    obs += state['agent']
+    want = np.concatenate(obs).astype(np.float32)
+    assert got.dtype == np.float32 and got.shape == want.shape and got.size < 0.2 * state['x'].size * 3
+    assert np.array_equal(got, want)
+    assert state['used'][bodies['particle_ids'][0]].sum() == 40, 'the injector must have activated 2 particles in each of the 20 substeps'
