@@ -1,0 +1,49 @@
+"""TEST INFRASTRUCTURE: run bench.py's `ours` arm on the CUDA execution-model shim with a tiny workload, to check the SCRIPT (argument
+handling, replay, e2e episodes, JSON line) in a container without a GPU.  The numbers it prints are meaningless.
+
+    python tests/cuda_emu/run_bench_emu.py --particles 3000 --steps 2 --warmup 1 --no-cpu [--fuse-g2p2g 1]
+"""
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+import torch  # noqa: E402
+import harness  # noqa: E402
+
+
+class _TimedEvent:
+    def __init__(self, *a, **k):
+        self.t = None
+
+    def record(self, *a, **k):
+        self.t = time.perf_counter()
+
+    def synchronize(self):
+        pass
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+def main():
+    harness.enable()
+    torch.cuda.Event = _TimedEvent
+    torch.cuda.set_device = lambda *a, **k: None
+    real_device = torch.device
+    torch.device = lambda *a, **k: real_device('cpu') if a and a[0] == 'cuda' else real_device(*a, **k)
+    from fluidlab_b200 import simulator
+    init = simulator.MPMSimulator.__init__
+
+    def emu_init(self, *a, **k):
+        init(self, *a, **k)
+        self.use_graphs = False
+    simulator.MPMSimulator.__init__ = emu_init
+    import bench
+    bench.main()
+
+
+if __name__ == '__main__':
+    main()

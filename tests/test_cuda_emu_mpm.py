@@ -237,3 +237,23 @@ def test_device_side_observation_equals_fluid_env_get_obs(emu):
     assert got.dtype == np.float32 and got.shape == want.shape and got.size < 0.2 * state['x'].size * 3
     assert np.array_equal(got, want)
     assert state['used'][bodies['particle_ids'][0]].sum() == 40, 'the injector must have activated 2 particles in each of the 20 substeps'
+
+
+def test_bench_script_runs_end_to_end_on_the_emulated_device():
+    """bench.py's `ours` arm (warm-up, timed steps, per-kernel replay, e2e episodes with host buffers, the guarded observation-bridge
+    episodes, JSON line) with a tiny workload on the shim: checks the SCRIPT, the driver's contract keys and the fused path's flag — the
+    numbers are meaningless here."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'cuda_emu', 'run_bench_emu.py'), '--particles', '1500', '--steps', '2', '--warmup', '1', '--no-cpu', '--bwd', '0',
+                        '--fuse-g2p2g', '1'], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e',
+              'gpu_launches', 'roofline', 'cpu_baseline'):
+        assert k in line, k
+    assert line['metric'] == 'mpm_substeps_per_s_fwd' and line['warmup'] >= 3 and line['value'] > 0 and line['e2e']['value'] > 0
+    assert line['config']['g2p2g_fused'] is True and line['gpu_launches'] == 2 * 21 + 2
+    assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
+    ob = line['e2e_obs_bridge']
+    assert 'error' not in ob and ob['d2h_bytes_per_step'] < line['e2e']['d2h_bytes_per_step']
