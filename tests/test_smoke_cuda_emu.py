@@ -248,3 +248,22 @@ def test_product_host_class_on_the_emulated_library(emu, monkeypatch):
     assert np.abs(ga - gb).max() < 1e-4 * np.abs(gb).max()
     sf.copy_grad(0, 4); sf.reset_grad_till_frame(2)
     assert np.array_equal(sf.get_grad(4)['v'], a['v']) and not np.any(sf.get_grad(0)['v']) and not np.any(sf.get_grad(1)['q'])
+
+
+def test_smoke_timing_script_runs_on_the_emulated_library(emu, monkeypatch):
+    """profiles/smoke_times.py (the per-phase timing script queued for the next GPU round) at a reduced size on the shim: script sanity only"""
+    import sys
+    import time
+    import torch
+    from fluidlab_b200 import smoke as smoke_mod
+    monkeypatch.setattr(smoke_mod._lib, 'load', lambda: emu)
+    sys.path.insert(0, os.path.join(ROOT, 'profiles'))
+    import smoke_times
+
+    class Ev:
+        def __init__(self, **k): self.t = 0.0
+        def record(self): self.t = time.perf_counter()
+        def elapsed_time(self, o): return (o.t - self.t) * 1e3
+    out = smoke_times.run(res=24, dev=torch.device('cpu'), reps=1, band=(8, 14), iters_list=(5,), event_cls=Ev, sync=lambda: None)
+    ms = out['runs'][0]['ms']
+    assert set(ms) >= {'step', 'step_grad', 'pressure', 'advect_grad'} and all(v > 0 for v in ms.values())
