@@ -746,6 +746,19 @@ class MPMSimulator:
         b = self._blk_flags
         flagger(b[f & 1] if b.dim() == 2 else b)
 
+    def slab_snapshot_frame(self, f):
+        """everything needed to put ring frame f back later (state planes + its slot order): the chunk checkpoint of a sharded run"""
+        o = self._frame_ord[f]
+        return dict(pa=self._pa[f].clone(), pf=self._pf[f].clone(), pf8=self._pf8[f].clone(), order=o, mrow=self._mrow.clone())
+
+    def slab_restore_frame(self, f, snap):
+        self._pa[f].copy_(snap['pa']); self._pf[f].copy_(snap['pf']); self._pf8[f].copy_(snap['pf8'])
+        self._frame_ord[f] = snap['order']
+        self._mrow.copy_(snap['mrow'])
+
+    def slab_adjoint_moves_to_frame(self, f):
+        pass   # the adjoint ping-pong buffer always holds "the adjoint of the current frame": nothing is indexed by frame here
+
     def slab_substep_grad_p2g(self, f):
         """backward substep f, part 1: recompute the (momentum, mass) scatter of frame f (ghost sum follows)."""
         self._ensure_grad_order(self._frame_ord[f])

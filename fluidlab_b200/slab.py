@@ -21,7 +21,9 @@ Backward (`SlabMPMSimulator.step_grad`, SURVEY.md §8e "Backward"): per substep 
 ghost sum as in the forward pass, g2p's adjoint scatters the v_out adjoint onto owned + ghost planes, ONE more ghost sum (all-reduce of
 the 2*halo planes per slab boundary) completes it, and grid_op.grad runs redundantly on the ghosts so the particle side (p2g.grad) needs
 no further exchange.  At step boundaries `migrate_grad` sends the adjoint of every migrated particle back to the rank and slot it left.
-A backward pass must fit one checkpoint chunk (n_steps * 10 <= max_substeps_local); the sharded ring wrap-around is not implemented.
+Trajectories longer than the ring are handled like the single-GPU path (MPM:777-912): every chunk's first frame (+ global ids, material
+rows, pending leaver census) is checkpointed in HBM when the chunk starts, and the backward pass re-runs a chunk forward — ghost sums and
+migrations included, in lockstep on all ranks — before walking it backwards.
 
 The orchestration talks to the local simulator only through `MPMSimulator`'s step-level methods and its `slab_*` hooks, so
 tests/test_slab_cpu.py drives this same code on CPU (gloo, world_size 2) with an oracle-backed stand-in and checks forward AND backward
@@ -222,6 +224,8 @@ class SlabMPMSimulator:
         self._census_event = None
         self._records = {}      # global step index -> what migrate() did before that step (for step_grad)
         self._gid_before = {}   # global step index -> slot -> global id map before that migration
+        self._chunks = {}       # first global substep of a chunk -> checkpoint taken when the chunk started (grad mode)
+        self._replaying = False
 
     def _setup_peer(self, halo):
         """Double-buffer the accumulator in SYMMETRIC MEMORY (torch.distributed._symmetric_memory: every rank's buffer is mapped
@@ -310,8 +314,46 @@ class SlabMPMSimulator:
             self.n_migrated += n_out
         self._census_async()
 
+    def _checkpoint_chunk_start(self):
+        """grad mode, first step of a chunk: keep what a later re-run of this chunk must start from (the reference checkpoints frame 0 of
+        every chunk too, MPM:777-852; here additionally what migration changes — slot -> global id, material rows — and the census that
+        decides whether THIS step migrates)"""
+        sim = self.sim
+        pending = None
+        if self._census_event is not None:
+            self._census_event.synchronize()
+            pending = int(self._census_host[0])
+        self._chunks[sim.cur_substep_global] = dict(frame=sim.slab_snapshot_frame(0), gid=self.gid.clone(), census=pending)
+
+    def _replay_chunk(self, start):
+        """backward pass at a chunk boundary (MPM:856-912): restore the chunk's first frame and run it forward again, exchanges included"""
+        sim = self.sim
+        ck = self._chunks[start]
+        sim.slab_restore_frame(0, ck['frame'])
+        sim.slab_adjoint_moves_to_frame(sim.max_substeps_local)   # copy_grad(0, T) + reset_grad_till_frame(T) of MPM:858-860
+        self.gid = ck['gid'].clone()
+        if self._census_event is not None:
+            self._census_event.synchronize()   # no copy into the host word is in flight any more
+        if ck['census'] is None:
+            self._census_event = None
+        else:
+            if self._census_host is None:
+                self._census_host = torch.zeros(1, dtype=torch.int64)
+            self._census_host[0] = ck['census']
+            self._census_event = _Done()
+        n_steps = sim.max_substeps_local // sim.n_substeps
+        sim.cur_substep_global = start
+        self._replaying = True
+        try:
+            for _ in range(n_steps):
+                self.step()
+        finally:
+            self._replaying = False
+
     def step(self):
         sim = self.sim
+        if sim.grad_enabled and sim.cur_substep_local == 0 and not self._replaying:
+            self._checkpoint_chunk_start()
         if self.world > 1 and self.migrate_enabled:
             self._migrate()
         sim.sort_frame(sim.cur_substep_local)
@@ -325,9 +367,11 @@ class SlabMPMSimulator:
             sim.phase('grid_op', f, 1)
             sim.phase('g2p', f)
             sim.cur_substep_global += 1
-        if sim.cur_substep_local == 0:
-            assert not sim.grad_enabled, 'a differentiated slab trajectory must fit one chunk (n_steps * 10 <= max_substeps_local)'
-            sim.memory_to_cache()
+        if sim.cur_substep_local == 0 and not self._replaying:   # ring wrap: frame T becomes frame 0 of the next chunk
+            if sim.grad_enabled:
+                sim.copy_frame(sim.max_substeps_local, 0)
+            else:
+                sim.memory_to_cache()
 
     def _ghost_sum_acc(self, f):
         sim = self.sim
@@ -339,7 +383,7 @@ class SlabMPMSimulator:
     # ------------------------------------------------------------------------------------------ backward
     def enable_grad(self):
         self.sim.enable_grad()
-        self._records, self._gid_before = {}, {}
+        self._records, self._gid_before, self._chunks = {}, {}, {}
 
     def local_state(self):
         """current frame of this rank in slot order: dict(gid, used, x, v, C, F) of device tensors (staging views: copy to keep)."""
@@ -372,7 +416,8 @@ class SlabMPMSimulator:
         """adjoint of the most recent `step()` not yet undone; call in exact reverse order after `set_final_grad`."""
         sim = self.sim
         assert sim.grad_enabled and sim.cur_substep_global >= sim.n_substeps
-        assert sim.cur_substep_global <= sim.max_substeps_local, 'a differentiated slab trajectory must fit one chunk'
+        if sim.cur_substep_local == 0:   # the step to undo is the last one of the previous chunk: bring that chunk back into the ring
+            self._replay_chunk(sim.cur_substep_global - sim.max_substeps_local)
         for _ in range(sim.n_substeps):
             sim.cur_substep_global -= 1
             self._substep_grad(sim.cur_substep_local)

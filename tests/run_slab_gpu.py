@@ -39,7 +39,7 @@ def main():
     def parts(idx):
         return dict(x=x[idx], mat=mat[idx], used=np.ones(len(idx), np.int32), rho=np.array([M.RHO[m] for m in mat[idx]]), body_id=np.zeros(len(idx), np.int32), bodies={'n': 1})
     exchange = os.environ.get('SLAB_EXCHANGE', 'peer')
-    slab = SlabMPMSimulator(q, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=int(len(mine) * 1.5) + 1000, max_substeps_local=60 if os.environ.get('SLAB_MODE') == 'backward' else 20, device=dev,
+    slab = SlabMPMSimulator(q, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=int(len(mine) * 1.5) + 1000, max_substeps_local=20, device=dev,
                             exchange=exchange)
     st = slab.sim.get_state()
     st['v'][:len(mine)] = v0[mine]
@@ -75,7 +75,7 @@ def main():
 
 def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
     from fluidlab_b200 import MPMSimulator
-    n_steps = 5   # 50 substeps: fits the 60-frame ring (a differentiated slab trajectory must fit one chunk); migrations at steps 2 and 4
+    n_steps = 5   # 50 substeps on a 20-frame ring: two wraps (chunk checkpoints + re-runs in the backward pass); migrations at steps 2 and 4
     tgt = torch.from_numpy((x + np.random.RandomState(9).randn(Ntot, 3).astype(np.float32) * 0.05).astype(np.float32)).to(dev)
     slab.enable_grad()
     for _ in range(n_steps):
@@ -90,7 +90,7 @@ def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
     migrated = torch.tensor([slab.n_migrated, len(slab._records)], device=dev); dist.all_reduce(migrated)
     ok = True
     if rank == 0:
-        ref = MPMSimulator(dim=3, quality=q, gravity=(0.0, -10.0, 0.0), horizon=1000, max_substeps_local=60, max_substeps_global=10 ** 6, ckpt_dest='gpu', device=dev)
+        ref = MPMSimulator(dim=3, quality=q, gravity=(0.0, -10.0, 0.0), horizon=1000, max_substeps_local=20, max_substeps_global=10 ** 6, ckpt_dest='gpu', device=dev)
         ref.build(None, None, [], parts(np.arange(Ntot)))
         s0 = ref.get_state(); s0['v'][:] = v0; ref.set_state(0, s0)
         ref.enable_grad()

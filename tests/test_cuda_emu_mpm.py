@@ -114,7 +114,7 @@ def _slab_worker(rank, world, port, ret):
 
         def parts(idx):
             return dict(x=x[idx], mat=mat[idx], used=np.ones(len(idx), np.int32), rho=np.array([M.RHO[m] for m in mat[idx]]), body_id=np.zeros(len(idx), np.int32), bodies={'n': 1})
-        slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=len(mine) + 300, max_substeps_local=60, device='cpu', halo=4,
+        slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=len(mine) + 300, max_substeps_local=20, device='cpu', halo=4,
                                 exchange='nccl')
         slab.sim.use_graphs = False
         st = slab.sim.get_state()
@@ -133,7 +133,7 @@ def _slab_worker(rank, world, port, ret):
         grad = slab.gather_grad()
         out = dict(fwd=fwd, grad=grad, migrated=slab.n_migrated, rec=sorted(slab._records))
         if rank == 0:   # the single-domain reference: the same product on the same emulated device
-            ref = MPMSimulator(dim=3, quality=0.5, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=60, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+            ref = MPMSimulator(dim=3, quality=0.5, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
             ref.use_graphs = False
             ref.build(None, None, [], parts(np.arange(Ntot)))
             s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
@@ -156,7 +156,8 @@ def test_slab_sharded_forward_and_backward_match_the_single_domain_run_on_the_em
     """the CUDA leg of the x-slab path that tests/run_slab_gpu.py exercises on 2 GPUs, here on 2 gloo ranks with the emulated device:
     SlabMPMSimulator.step (ghost all-reduce of the accumulator, migration) and step_grad (fmpm_p2g(write_F=0) -> ghost sum ->
     fmpm_substep_grad_scatter -> ghost sum of the v_out adjoint -> fmpm_substep_grad_finish, migrate_grad) against MPMSimulator on one
-    domain: states and dL/d(x0, v0, C0, F0)."""
+    domain: states and dL/d(x0, v0, C0, F0).  The ring holds 2 steps and the trajectory has 5: both sides wrap twice, the sharded side
+    checkpoints every chunk start and re-runs each chunk (exchanges and migrations included) during the backward pass."""
     import torch.multiprocessing as mp
     mgr = mp.Manager(); ret = mgr.dict()
     mp.spawn(_slab_worker, args=(2, _free_port(), ret), nprocs=2, join=True)

@@ -2,6 +2,7 @@
 import os
 import socket
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -174,6 +175,14 @@ class OracleLocalSim:
     def cur_step_global(self): return self.cur_substep_global // self.n_substeps
     def enable_grad(self): self.grad_enabled = True; self.cur_substep_global = 0
     def memory_to_cache(self): self.o.L.orc_copy_frame(self.o.h, self.max_substeps_local, 0)
+    def copy_frame(self, a, b): self.o.L.orc_copy_frame(self.o.h, a, b)
+    def slab_snapshot_frame(self, f):
+        return dict(frame=self.o.get_frame(f), mrow=self._mrow.clone(), layouts=[(f0, m.clone()) for f0, m in self._layouts])
+    def slab_restore_frame(self, f, snap):
+        fr = snap['frame']
+        self.o.set_frame(f, fr['x'], fr['v'], fr['C'], fr['F'], fr['used'])
+        self._mrow.copy_(snap['mrow']); self._layouts = [(0, snap['mrow'].clone())]
+        self._use_layout(f)
 
     def _use_layout(self, f):
         mrow = [m for f0, m in self._layouts if f0 <= f][-1]
@@ -218,6 +227,8 @@ class OracleLocalSim:
     def read_grad_torch(self):
         g = self.o.get_grad_frame(self._gframe)
         return {k: torch.from_numpy(g[k].astype(np.float32)) for k in ('x', 'v', 'C', 'F')}
+    def slab_adjoint_moves_to_frame(self, f):   # the oracle keeps one adjoint per ring frame (like the reference): MPM:858-860
+        self.o.L.orc_copy_grad(self.o.h, 0, f); self.o.L.orc_reset_grad_till(self.o.h, f); self._gframe = f
     def slab_substep_grad_p2g(self, f):
         assert self._gframe == f + 1
         self._use_layout(f)
@@ -255,7 +266,7 @@ def _slab_scene():
     return n, x, v0, mat, tgt
 
 
-def _slab_fwd_bwd_job(rank, world):
+def _slab_fwd_bwd_job(rank, world, T=60):
     from fluidlab_b200 import macros as M
     from fluidlab_b200.slab import SlabMPMSimulator
     torch.set_num_threads(1)
@@ -265,7 +276,7 @@ def _slab_fwd_bwd_job(rank, world):
     mine = np.where((cp >= bounds[rank]) & (cp < bounds[rank + 1]))[0]
     parts = dict(x=x[mine], mat=mat[mine], used=np.ones(len(mine), np.int32), rho=np.array([M.RHO[m] for m in mat[mine]]), body_id=np.zeros(len(mine), np.int32),
                  bodies={'n': 1})
-    slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts, gid=mine, bounds=bounds, capacity=len(mine) + 400, max_substeps_local=60, halo=4,
+    slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts, gid=mine, bounds=bounds, capacity=len(mine) + 400, max_substeps_local=T, halo=4,
                             exchange='nccl', sim_factory=OracleLocalSim)
     st = slab.sim.readframe_torch(0)
     st['v'][:len(mine)] = torch.from_numpy(v0[mine])
@@ -286,16 +297,22 @@ def _slab_fwd_bwd_job(rank, world):
     return fwd, grad, slab.n_migrated, sorted(slab._records)
 
 
-def test_slab_orchestration_forward_and_backward_match_the_single_domain_oracle():
+def _slab_fwd_bwd_job_short_ring(rank, world):
+    return _slab_fwd_bwd_job(rank, world, T=20)
+
+
+@pytest.mark.parametrize('job', [_slab_fwd_bwd_job, _slab_fwd_bwd_job_short_ring], ids=['one_chunk', 'ring_of_2_steps'])
+def test_slab_orchestration_forward_and_backward_match_the_single_domain_oracle(job):
     """2 ranks over gloo: SlabMPMSimulator.step x5 (ghost sums, migration in both directions at two step boundaries) then step_grad x5
     (ghost sums of the accumulator AND of the v_out adjoint, migrate_grad) == the single-domain oracle's states and
-    dLoss/d(x0, v0, C0, F0).  The sharded run computes in fp32; it must be as close to the fp64 single-domain result as the fp32
+    dLoss/d(x0, v0, C0, F0).  `ring_of_2_steps`: the ring holds 2 steps, so the 5-step trajectory wraps twice — every chunk start is
+    checkpointed and the backward pass re-runs each chunk (ghost sums and migrations included) before walking it.  The sharded run computes in fp32; it must be as close to the fp64 single-domain result as the fp32
     single-domain run is (x3 slack), i.e. sharding adds nothing beyond summation-order noise."""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from oracle import oracle as orc
     from conftest import make_particles
-    out = _run(_slab_fwd_bwd_job)
+    out = _run(job)
     n, x, v0, mat, tgt = _slab_scene()
     N, S = len(x), _SLAB_STEPS
     ref = {}
