@@ -82,3 +82,37 @@ def run_circulation_stack(device=None, res=128, iters=50, band=None, detectors=N
     assert seen > 0, 'the loss must depend on the air conditioner'
     assert np.abs(grad[:n_steps, :6]).max() > 0, 'the pose components of dLoss/dAction must be populated (pose adjoints flow through the effector chain)'
     return env, o
+
+
+def run_reference_stack_case(device=None):
+    """tests/golden/reference_circulation.npz: the reference's OWN MPMSimulator + AgentCirculation + AirCon + SmokeField (10 parked
+    particles, a Static 'room'), 3 x MPMSimulator.step(action) on the Taichi emulation (tests/golden/make_reference_smoke.py stack).  The
+    product's TaichiEnv stack on the emulated device must reproduce the air conditioner's trajectory (pose chain with rotation, strength
+    and radius channels of the 8-component action, apply_action_p) and the smoke state after every step."""
+    from fluidlab_b200 import TaichiEnv, macros as M
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_circulation.npz'))
+    env = TaichiEnv(dim=3, quality=0.25, particle_density=1e6, max_substeps_local=int(d['T']), gravity=(0.0, -20.0, 0.0), horizon=10, ckpt_dest='gpu' if device is None else 'cpu', device=device)
+    env.simulator.use_graphs = device is None
+    env.setup_agent(dict(type='AgentCirculation', effectors=[dict(type='AirCon', params=dict(init_pos=tuple(d['init_pos']), action_dim=8, action_scale_p=(1.0,) * 8,
+                                                                                            action_scale_v=tuple(d['scale_v']), inject_v=tuple(d['inject_v'])),
+                                                                 boundary=dict(type='cube', lower=tuple(d['e_lower']), upper=tuple(d['e_upper'])))]))
+    env.add_static(file='room.obj', material=M.PILLAR, has_dynamics=True, sdf=dict(voxels=d['room_vox'], T_mesh_to_voxels=d['room_T']))
+    env.add_body(type='nowhere', n_particles=10, material=M.WATER)
+    env.setup_smoke_field(res=int(d['res']), dt=float(d['dt']), solver_iters=int(d['iters']), decay=0.99, q_dim=int(d['q_dim']))
+    env.smoke_field.lower_y, env.smoke_field.higher_y = int(d['lower_y']), int(d['higher_y'])
+    env.build()
+    env.apply_agent_action_p(d['action_p'])
+    for a in d['actions']:
+        env.step(a)
+    air, sf = env.agent.aircon, env.smoke_field
+    nf = 10 * len(d['actions'])
+    assert rel(air.pos[:nf + 1].cpu().numpy(), d['ref_pos']) < 1e-6 and rel(air.quat[:nf + 1].cpu().numpy(), d['ref_quat']) < 1e-6
+    assert rel(air.s[:nf].cpu().numpy(), d['ref_s']) < 1e-6 and rel(air.r[:nf].cpu().numpy(), d['ref_r']) < 1e-6
+    assert np.abs(d['ref_quat'][nf][1:]).max() > 0.05 and np.ptp(d['ref_s']) > 0, 'the reference trajectory must rotate and vary its strength'
+    assert rel(env.agent.get_state(nf)[0], d['ref_state']) < 1e-6
+    for s in (1, 2, 3):
+        st = sf.get_state(s)
+        for k in ('v', 'p', 'q'):
+            assert rel(st[k], d[f'ref{s}_{k}']) < 2e-5, (s, k, rel(st[k], d[f'ref{s}_{k}']))
+    assert np.abs(d['ref3_v']).max() > 1.0

@@ -13,7 +13,9 @@ Two products, both in tests/golden/reference_smoke.npz:
 The only patches: `lower_y` / `higher_y` (instance attributes, SF:26-27) are lowered so a 20^3 grid has a free band, and the module's bare
 `max` / `min` (Taichi built-ins inside @ti.func, SF:304) are bound to the emulated ones.
 
-    python tests/golden/make_reference_smoke.py
+    python tests/golden/make_reference_smoke.py          # float32 run
+    python tests/golden/make_reference_smoke.py fd       # float64 finite differences
+    python tests/golden/make_reference_smoke.py stack    # the real MPMSimulator + AgentCirculation + AirCon + SmokeField stack
 """
 import importlib
 import os
@@ -105,7 +107,56 @@ def run(R, st0, air, vox, T, n_steps):
     return S, T_used, q_init
 
 
+def circulation_stack(R):
+    """THE REAL STACK of envs/circulation_env.py, reduced: the reference's MPMSimulator (10 parked particles) + AgentCirculation + AirCon
+    (8-component action through set_action_kernel / set_velocity / move_kernel) + SmokeField, stepped with MPMSimulator.step(action)
+    (mpm_simulator.py:734-753: set_action, smoke step at step level, 10 substeps with agent.move) -> reference_circulation.npz"""
+    M, ti = R['macros'], R['ti']
+    agents = importlib.import_module('fluidlab.fluidengine.agents')
+    sim_mod = importlib.import_module('fluidlab.fluidengine.simulators.mpm_simulator')
+    T = 40
+    agent = agents.AgentCirculation(max_substeps_local=T, max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
+    params = dict(init_pos=(0.8, 0.8, 0.5), action_dim=8, action_scale_p=(1.0,) * 8, action_scale_v=(1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1000.0, 50.0), inject_v=INJECT_V)
+    ebnd = dict(type='cube', lower=(0.05, 0.05, 0.05), upper=(0.95, 0.95, 0.95))
+    agent.add_effector(type='AirCon', params=params, mesh_cfg=None, boundary_cfg=ebnd)
+    S = sim_mod.MPMSimulator(dim=3, quality=0.25, gravity=(0.0, -20.0, 0.0), horizon=10, max_substeps_local=T, max_substeps_global=1000, ckpt_dest='cpu')
+    smoke = R['smoke'].SmokeField(dim=3, ckpt_dest='cpu', res=RES, dt=DT, solver_iters=ITERS, q_dim=QD)
+    smoke.lower_y, smoke.higher_y = LOWER_Y, HIGHER_Y
+    N = 10
+    x = np.tile(np.array([-100.0, -100.0, -100.0], dtype=np.float32), (N, 1))
+    statics = R['meshes'].Statics()
+    _, _, vox, Tm, _, _ = inputs()     # the "room" volume (second entry): no free cell touches the x / z domain edge
+    R['mrr'].SDF_REGISTRY['room.obj'] = dict(voxels=vox[1], T_mesh_to_voxels=Tm[1])
+    statics.add_static(file='room.obj', material=M.PILLAR, has_dynamics=True, pos=(0.0, 0.0, 0.0))
+    S.build(agent, smoke, statics, dict(x=x, used=np.zeros(N), mat=np.full(N, M.WATER), rho=np.ones(N, np.float32), body_id=np.zeros(N), bodies={'n': 1}))
+    agent.build(S)
+    smoke.build(S, agent)
+    action_p = np.array([0.55, 0.5, 0.45, 0.0, 0.0, 0.0, 0.0, 0.0], dtype=np.float32)
+    actions = np.array([[0.010, 0.002, 0.005, 0.00, 0.10, 0.00, 0.020, 0.040], [0.005, -0.004, 0.010, 0.05, 0.05, -0.02, 0.030, 0.050],
+                        [-0.008, 0.003, 0.002, -0.03, 0.08, 0.04, 0.015, 0.030]], dtype=np.float32)
+    agent.apply_action_p(action_p)
+    for a in actions:
+        S.step(a)
+    air = agent.aircon
+    nf = 10 * len(actions)
+    out = dict(res=RES, lower_y=LOWER_Y, higher_y=HIGHER_Y, iters=ITERS, dt=DT, q_dim=QD, inject_v=np.array(INJECT_V), T=T, action_p=action_p, actions=actions,
+               scale_v=np.array(params['action_scale_v']), e_lower=np.array(ebnd['lower']), e_upper=np.array(ebnd['upper']), init_pos=np.array(params['init_pos']),
+               ref_pos=np.stack([np.asarray(air.pos[f]) for f in range(nf + 1)]), ref_quat=np.stack([np.asarray(air.quat[f]) for f in range(nf + 1)]),
+               ref_s=np.array([float(air.s[f]) for f in range(nf)]), ref_r=np.array([float(air.r[f]) for f in range(nf)]),
+               ref_state=np.asarray(agent.get_state(nf)[0], dtype=np.float64), room_vox=vox[1].astype(np.float32),
+               room_T=np.asarray(statics[0].T_mesh_to_voxels_np, dtype=np.float64))
+    for s_ in (1, 2, 3):
+        st = smoke.get_state(s_)
+        for k in ('v', 'p', 'q'):
+            out[f'ref{s_}_{k}'] = st[k].astype(np.float32)
+    path = os.path.join(HERE, 'reference_circulation.npz')
+    np.savez_compressed(path, **out)
+    print('reference_circulation.npz', os.path.getsize(path), 'bytes; |v| max', float(np.abs(out['ref3_v']).max()))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'stack':
+        return circulation_stack(load(False))
     fp64 = len(sys.argv) > 1 and sys.argv[1] == 'fd'
     R = load(fp64)
     st0, air, vox, T, w, dirs = inputs()

@@ -258,3 +258,10 @@ def test_bench_script_runs_end_to_end_on_the_emulated_device():
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
     ob = line['e2e_obs_bridge']
     assert 'error' not in ob and ob['d2h_bytes_per_step'] < line['e2e']['d2h_bytes_per_step']
+
+
+def test_circulation_stack_equals_a_run_of_the_real_reference_stack(emu):
+    """the product's TaichiEnv circulation stack on the emulated device against tests/golden/reference_circulation.npz (a run of the
+    reference's OWN MPMSimulator + AgentCirculation + AirCon + SmokeField); see tests/circulation_case.py"""
+    from circulation_case import run_reference_stack_case
+    run_reference_stack_case(device='cpu')

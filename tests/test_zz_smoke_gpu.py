@@ -106,3 +106,11 @@ def test_circulation_stack_through_taichi_env():
     _need_gpu()
     from circulation_case import run_circulation_stack
     run_circulation_stack(device=None)
+
+
+def test_circulation_stack_equals_a_run_of_the_real_reference_stack():
+    """tests/golden/reference_circulation.npz: the reference's OWN MPMSimulator + AgentCirculation + AirCon + SmokeField stepped on the Taichi
+    emulation; the product's TaichiEnv stack on the B200 must reproduce the air conditioner's trajectory and the smoke states."""
+    _need_gpu()
+    from circulation_case import run_reference_stack_case
+    run_reference_stack_case(device=None)
