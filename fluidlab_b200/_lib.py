@@ -80,7 +80,7 @@ class FmpmColliders(C.Structure):
 class FmpmSlab(C.Structure):
     _fields_ = [("enabled", C.c_int), ("peer_pm_left", vp), ("peer_pm_right", vp), ("peer_flags_left", vp), ("peer_flags_right", vp),
                 ("left_lo", C.c_int), ("left_hi", C.c_int),
-                ("right_lo", C.c_int), ("right_hi", C.c_int)]
+                ("right_lo", C.c_int), ("right_hi", C.c_int), ("peer_ggv_left", vp), ("peer_ggv_right", vp)]
 
 
 class FmpmCollector(C.Structure):

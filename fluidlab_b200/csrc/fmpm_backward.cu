@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
   const long long slot0 = gw * (32 * SC_ROUNDS);
   if (slot0 >= P.N) return;
   Window W; window_init(W, lane, P.n, nullptr);
+  window_set_slab(W, P.peer_gl, P.peer_gr, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, nullptr, nullptr);   // x-slab backward: ghost planes also go to the neighbour
 #pragma unroll 1
   for (int r = 0; r < SC_ROUNDS; r++) {
     const long long rem = (long long)P.N - (slot0 + r * 32);
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
 // =============================================================================================
 // grid_op.grad (MPM:539): v_out = B(v_in / m + dt g)
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int f, const int clear_pm) {
+__global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int f, const int clear_pm, const int zero_ggv_after) {
   const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     if (P.blk_flags[blk] == 0) continue;  // CTA-uniform
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) k_grid_op_grad(const KParams P, const int
       }
       if (agent_grid && P.col.egpos) reduce_pose_grad(P.col.egpos, P.col.egquat, f, pg0, pg1);
       P.ggrid_pm[g] = out;
+      if (zero_ggv_after) P.ggrid_v[g] = make_float4(0.f, 0.f, 0.f, 0.f);   // consumed: all-zero again before any neighbour's next scatter
       if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (clear_pm) { __syncthreads(); if (threadIdx.x == 0) P.blk_flags[blk] = 0; }  // recompute path: last consumer of the flags
@@ -426,12 +428,12 @@ static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, 
   return 0;
 }
 extern "C" int fmpm_g2p_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) { return g2p_grad_scatter_impl(h, f, gin, 1, -1, stream); }
-static int grid_op_grad_impl(FmpmHandle* h, int f, int clear_pm, int ring_slot, void* stream) {
+static int grid_op_grad_impl(FmpmHandle* h, int f, int clear_pm, int ring_slot, void* stream, int zero_ggv_after = 0) {
   if (check_bound_b(h, "fmpm_grid_op_grad")) return 1;
   KParams P = make_kparams(h, ring_slot, f);   // x-slab mode: the accumulator / block flags of substep parity f
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
-  FMPM_LAUNCH(k_grid_op_grad, grid, 256, 0, stream, P, f, clear_pm);
+  FMPM_LAUNCH(k_grid_op_grad, grid, 256, 0, stream, P, f, clear_pm, zero_ggv_after);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op_grad");
   return 0;
 }
@@ -495,7 +497,10 @@ extern "C" int fmpm_substep_grad(FmpmHandle* h, int f, int gin, int gout, void* 
 extern "C" int fmpm_substep_grad_scatter(FmpmHandle* h, int f, int gin, void* stream) {
   if (check_bound_b(h, "fmpm_substep_grad_scatter")) return 1;
   if (gin & ~1) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad_scatter: gin must be 0 or 1"); return 1; }
-  if (fmpm_grid_op_impl(h, f, 0, 1, -1, stream)) return 1;
+  // fused ghost reduction of the v_out adjoint (peer_ggv_*): the buffer is all-zero here (grid_op.grad zeroes what it consumes), and a
+  // neighbour may already be scattering into it, so it must NOT be zeroed now
+  const int fused = h->slab.enabled && (h->slab.peer_ggv_left || h->slab.peer_ggv_right);
+  if (fmpm_grid_op_impl(h, f, 0, fused ? 0 : 1, -1, stream)) return 1;
   if (h->col.has_rigid && h->col.collide_type != 1) {
     KParams P = make_kparams(h);
     if (P.N > 0) { FMPM_LAUNCH(k_collide_particle_grad, (P.N + 127) / 128, 128, 0, stream, P, f, gin); FMPM_CHECK_LAUNCH(h, "fmpm_substep_grad_scatter(collide)"); }
@@ -505,7 +510,8 @@ extern "C" int fmpm_substep_grad_scatter(FmpmHandle* h, int f, int gin, void* st
 extern "C" int fmpm_substep_grad_finish(FmpmHandle* h, int f, int gin, int gout, void* stream) {
   if (check_bound_b(h, "fmpm_substep_grad_finish")) return 1;
   if (gin == gout || (gin | gout) & ~1) { snprintf(h->err, sizeof(h->err), "fmpm_substep_grad_finish: gin/gout must be distinct in {0,1}"); return 1; }
-  if (grid_op_grad_impl(h, f, 1, -1, stream)) return 1;
+  const int fused = h->slab.enabled && (h->slab.peer_ggv_left || h->slab.peer_ggv_right);
+  if (grid_op_grad_impl(h, f, 1, -1, stream, fused)) return 1;
   return fmpm_particle_grad(h, f, gin, gout, stream);
 }
 extern "C" int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjector* inj, const FmpmEffector* e, int act_id,

@@ -48,6 +48,7 @@ struct KParams {
   // x-slab mode: neighbours' accumulators (peer memory over NVLink) and the node-plane ranges shared with them
   float4* peer_l; float4* peer_r; int gl_lo, gl_hi, gr_lo, gr_hi;
   int* peer_fl; int* peer_fr;
+  float4* peer_gl; float4* peer_gr;   // the neighbours' v_out adjoint (backward ghost reduction fused into g2p.grad's scatter)
 };
 
 // ring_slot >= 0: the (momentum, mass) / v_out grids and the active-block list live in slot `ring_slot` of the per-frame ring
@@ -68,7 +69,7 @@ static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1, int 
   P.mats = (const float4*)h->buf.materials;
   P.col = h->col;
   P.blk_flags = (int*)h->buf.blk_flags; P.blk_list = (int*)h->buf.blk_list; P.blk_count = (int*)h->buf.blk_count; P.nb = c.n_grid / 8;
-  P.peer_l = P.peer_r = nullptr; P.gl_lo = P.gl_hi = P.gr_lo = P.gr_hi = 0; P.peer_fl = P.peer_fr = nullptr;
+  P.peer_l = P.peer_r = nullptr; P.gl_lo = P.gl_hi = P.gr_lo = P.gr_hi = 0; P.peer_fl = P.peer_fr = nullptr; P.peer_gl = P.peer_gr = nullptr;
   if (h->slab.enabled) {  // accumulator double-buffered by substep parity; peers use the same parity
     const size_t off = (size_t)(parity & 1) * P.G;
     P.grid_pm += off;
@@ -79,6 +80,7 @@ static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1, int 
     if (h->slab.peer_flags_left) P.peer_fl = (int*)h->slab.peer_flags_left + foff;
     if (h->slab.peer_flags_right) P.peer_fr = (int*)h->slab.peer_flags_right + foff;
     P.gl_lo = h->slab.left_lo; P.gl_hi = h->slab.left_hi; P.gr_lo = h->slab.right_lo; P.gr_hi = h->slab.right_hi;
+    P.peer_gl = (float4*)h->slab.peer_ggv_left; P.peer_gr = (float4*)h->slab.peer_ggv_right;
   }
   if (ring_slot >= 0 && h->buf.grid_pm_ring) {
     const size_t nblk = (size_t)P.nb * P.nb * P.nb;

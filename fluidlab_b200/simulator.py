@@ -264,7 +264,8 @@ class MPMSimulator:
             self._ga = torch.zeros((2, 4, N, 4), dtype=f32, device=dev)
             self._gf = torch.zeros((2, 2, N, 4), dtype=f32, device=dev)
             self._gf8 = torch.zeros((2, N), dtype=f32, device=dev)
-            self._ggrid_v = torch.zeros((G, 4), dtype=f32, device=dev)
+            if getattr(self, '_ggrid_v', None) is None:   # x-slab peer mode pre-binds a buffer in symmetric memory (slab.py)
+                self._ggrid_v = torch.zeros((G, 4), dtype=f32, device=dev)
             self._ggrid_pm = torch.zeros((G, 4), dtype=f32, device=dev)
             # per-frame forward grids for the backward pass (like the reference's grid ring, MPM:117) when HBM allows:
             # 32 B/node/frame; otherwise substep_grad recomputes the forward grid of each frame

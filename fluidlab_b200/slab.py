@@ -11,7 +11,8 @@ The reference is single-device (no collective anywhere); this is new design.  On
     local grid AND, over NVLink peer memory, to the neighbour's grid (p2g also sets the neighbour's sparse-block flags); the accumulator is double-buffered by substep parity so
     a fast neighbour can never scatter into a buffer that is still being consumed, and one device-side signal-pad barrier
     per substep (symmetric memory) is the only synchronisation.  Fallback (`exchange='nccl'`): one in-place NCCL all-reduce of the ghost planes per boundary
-    over a 2-rank communicator.  grid_op then runs redundantly on the ghosts, so g2p needs no second exchange;
+    over a 2-rank communicator.  grid_op then runs redundantly on the ghosts, so g2p needs no second exchange.  The backward pass mirrors it:
+    g2p.grad's scatter of the v_out adjoint reduces into the neighbour's adjoint grid over peer memory as well (second barrier per substep);
   * at step boundaries particles whose centre plane left the slab migrate to the neighbour (100 B records + material row
     + global id).  The leaver census is asynchronous (all-reduce -> pinned host, read one step later), so steps without
     leavers never synchronise the host.  `halo` = 4 planes tolerates 3 cells of drift over the two steps between a
@@ -80,6 +81,27 @@ class GhostExchange:
 class _Done:
     def synchronize(self):
         pass
+
+
+class SymmetricMemoryPeers:
+    """Buffers every rank can address directly: torch.distributed._symmetric_memory (CUDA: each rank's allocation is mapped into every
+    other rank's address space over NVLink) + its device-side signal-pad barrier.  `alloc` returns (local tensor, [base pointer of rank r's
+    copy in THIS process]).  tests/test_cuda_emu_mpm.py substitutes a POSIX-shared-memory implementation to drive the same kernels on CPU."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm_mem, self.group, self.device = symm_mem, group if group is not None else dist.group.WORLD, device
+        self._handles = []
+
+    def alloc(self, shape, dtype):
+        buf = self._symm_mem.empty(tuple(shape), dtype=dtype, device=self.device)
+        buf.zero_()
+        hdl = self._symm_mem.rendezvous(buf, self.group)
+        self._handles.append(hdl)
+        return buf, list(hdl.buffer_ptrs)
+
+    def barrier(self):
+        self._handles[0].barrier(channel=0)   # device-side: everything the ranks enqueued before it (incl. their peer reductions) has completed
 
 
 def centre_plane(x, inv_dx):
@@ -187,7 +209,7 @@ class SlabMPMSimulator:
     """Forward MLS-MPM over x-slabs: one local `MPMSimulator` per rank + ghost exchange + migration."""
 
     def __init__(self, quality, gravity, particles, gid, bounds, capacity, boundary=None, max_substeps_local=50, device=None, group=None, halo=4,
-                 exchange='peer', migrate=True, sim_factory=None):
+                 exchange='peer', migrate=True, sim_factory=None, peer_factory=None):
         from .macros import NOWHERE
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -218,6 +240,7 @@ class SlabMPMSimulator:
         self.ghost = GhostExchange(self.sim.n_grid, self.bounds, self.rank, self.world, halo=halo, group=group)
         self.n_migrated = 0
         self.exchange = exchange if self.world > 1 else 'none'
+        self._peer_factory = peer_factory if peer_factory is not None else SymmetricMemoryPeers
         if self.exchange == 'peer':
             self._setup_peer(halo)
         self._census_host = None
@@ -228,25 +251,20 @@ class SlabMPMSimulator:
         self._replaying = False
 
     def _setup_peer(self, halo):
-        """Double-buffer the accumulator in SYMMETRIC MEMORY (torch.distributed._symmetric_memory: every rank's buffer is mapped
-        into every other rank's address space over NVLink), and register the neighbours' pointers with the library.
+        """Double-buffer the accumulator in PEER-ADDRESSABLE memory (symmetric memory: every rank's buffer is mapped into every other
+        rank's address space over NVLink), and register the neighbours' pointers with the library.  The v_out adjoint gets a (single)
+        peer-addressable buffer as well, so the backward ghost reduction is fused into g2p.grad's scatter the same way.
         Falls back to the NCCL ghost all-reduce if symmetric memory cannot be set up on this system."""
         import ctypes as C
         from . import _lib
         sim = self.sim
         G = sim.n_grid ** 3
+        nblk = (sim.n_grid // 8) ** 3
         try:
-            import torch.distributed._symmetric_memory as symm_mem
-            group = self.group if self.group is not None else dist.group.WORLD
-            buf = symm_mem.empty((2, G, 4), dtype=torch.float32, device=sim.device)
-            buf.zero_()
-            hdl = symm_mem.rendezvous(buf, group)
-            ptrs = list(hdl.buffer_ptrs)
-            nblk = (sim.n_grid // 8) ** 3
-            fbuf = symm_mem.empty((2, nblk), dtype=torch.int32, device=sim.device)
-            fbuf.zero_()
-            fhdl = symm_mem.rendezvous(fbuf, group)
-            fptrs = list(fhdl.buffer_ptrs)
+            peers = self._peer_factory(self.group, sim.device)
+            buf, ptrs = peers.alloc((2, G, 4), torch.float32)
+            fbuf, fptrs = peers.alloc((2, nblk), torch.int32)
+            gbuf, gptrs = peers.alloc((G, 4), torch.float32)
         except Exception as e:  # pragma: no cover - depends on the driver / fabric
             if self.rank == 0:
                 print(f'[fluidlab_b200.slab] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL ghost all-reduce')
@@ -254,19 +272,21 @@ class SlabMPMSimulator:
             return
         sim._grid_pm = buf
         sim._blk_flags = fbuf
+        sim._ggrid_v = gbuf          # kept by MPMSimulator._ensure_grad_buffers
         sim._bind()
-        self._symm, self._symm_flags = hdl, fhdl
+        self._peers = peers
         slab = _lib.FmpmSlab()
         slab.enabled = 1
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         if self.rank > 0:
-            slab.peer_pm_left = int(ptrs[self.rank - 1]); slab.peer_flags_left = int(fptrs[self.rank - 1])
+            slab.peer_pm_left = int(ptrs[self.rank - 1]); slab.peer_flags_left = int(fptrs[self.rank - 1]); slab.peer_ggv_left = int(gptrs[self.rank - 1])
             slab.left_lo, slab.left_hi = lo - halo, lo + halo
         if self.rank < self.world - 1:
-            slab.peer_pm_right = int(ptrs[self.rank + 1]); slab.peer_flags_right = int(fptrs[self.rank + 1])
+            slab.peer_pm_right = int(ptrs[self.rank + 1]); slab.peer_flags_right = int(fptrs[self.rank + 1]); slab.peer_ggv_right = int(gptrs[self.rank + 1])
             slab.right_lo, slab.right_hi = hi - halo, hi + halo
         sim._ck(sim._lib.fmpm_set_slab(sim._h, C.byref(slab)), 'fmpm_set_slab')
-        torch.cuda.synchronize(sim.device)
+        if sim.device.type == 'cuda':
+            torch.cuda.synchronize(sim.device)
         dist.barrier(group=self.group)
 
     def _census_async(self):
@@ -361,7 +381,7 @@ class SlabMPMSimulator:
             f = sim.cur_substep_local
             sim.phase('p2g', f, 1)
             if self.exchange == 'peer':
-                self._symm.barrier(channel=0)   # device-side: every rank's p2g (incl. its peer reductions and peer block flags) has completed
+                self._peers.barrier()   # device-side: every rank's p2g (incl. its peer reductions and peer block flags) has completed
             elif self.exchange == 'nccl':
                 self._ghost_sum_acc(f)
             sim.phase('grid_op', f, 1)
@@ -402,11 +422,13 @@ class SlabMPMSimulator:
         sim = self.sim
         sim.slab_substep_grad_p2g(f)
         if self.exchange == 'peer':
-            self._symm.barrier(channel=0)
+            self._peers.barrier()
         elif self.exchange == 'nccl':
             self._ghost_sum_acc(f)
         sim.slab_substep_grad_scatter(f)
-        if self.world > 1:   # complete the v_out adjoint on the planes shared with the neighbours
+        if self.exchange == 'peer':
+            self._peers.barrier()   # every rank's g2p.grad scatter, incl. its reductions into the neighbours' v_out adjoint, has completed
+        elif self.world > 1:        # complete the v_out adjoint on the planes shared with the neighbours
             adj = sim.slab_grid_adj(f)
             self.ghost.exchange_sum(adj)
             sim.slab_grid_adj_commit(f, adj)

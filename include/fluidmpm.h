@@ -144,6 +144,10 @@ typedef struct {
                                                  it reduces into; in slab mode blk_flags is double-buffered by parity like grid_pm */
   int left_lo, left_hi;                      /* node planes [lo,hi) shared with the left neighbour */
   int right_lo, right_hi;                    /* node planes shared with the right neighbour */
+  /* backward pass (optional, NULL = the caller sums the ghost planes of the v_out adjoint itself, e.g. with an all-reduce): the
+   * neighbours' ggrid_v (float4[G], single-buffered).  g2p.grad's scatter then adds every contribution on a shared plane to the
+   * neighbour's v_out adjoint as well, and grid_op.grad zeroes what it consumed, so the buffer is all-zero between substeps. */
+  void* peer_ggv_left; void* peer_ggv_right;
 } FmpmSlab;
 int  fmpm_set_slab(FmpmHandle* h, const FmpmSlab* s);
 

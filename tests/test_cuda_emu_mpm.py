@@ -92,7 +92,37 @@ def _free_port():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _slab_worker(rank, world, port, ret):
+class ShmPeers:
+    """stand-in for fluidlab_b200.slab.SymmetricMemoryPeers on the emulated device: every rank's buffer is a POSIX shared-memory file that
+    the other rank processes map too, so the kernels' peer pointers (vector reductions into the neighbour's grids, block flags) address
+    real shared memory across processes; the barrier is a gloo barrier (the emulated kernels are synchronous)."""
+    _count = 0
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.tag = os.environ['MASTER_PORT']
+        self._keep = []
+
+    def alloc(self, shape, dtype):
+        idx = ShmPeers._count; ShmPeers._count += 1
+        numel = int(np.prod(shape))
+        path = lambda r: f'/dev/shm/fmpm_emu_{self.tag}_{idx}_{r}'
+        mine = torch.from_file(path(self.rank), shared=True, size=numel, dtype=dtype)
+        mine.zero_()
+        self.dist.barrier(group=self.group)
+        maps = [mine if r == self.rank else torch.from_file(path(r), shared=True, size=numel, dtype=dtype) for r in range(self.world)]
+        self._keep += maps
+        self.dist.barrier(group=self.group)
+        os.unlink(path(self.rank))   # the mappings stay valid; nothing is left behind in /dev/shm
+        return mine.view(*shape), [m.data_ptr() for m in maps]
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+def _slab_worker(rank, world, port, ret, exchange='nccl'):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     torch.set_num_threads(1)
@@ -115,7 +145,8 @@ def _slab_worker(rank, world, port, ret):
         def parts(idx):
             return dict(x=x[idx], mat=mat[idx], used=np.ones(len(idx), np.int32), rho=np.array([M.RHO[m] for m in mat[idx]]), body_id=np.zeros(len(idx), np.int32), bodies={'n': 1})
         slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=len(mine) + 300, max_substeps_local=20, device='cpu', halo=4,
-                                exchange='nccl')
+                                exchange=exchange, peer_factory=ShmPeers)
+        assert slab.exchange == exchange
         slab.sim.use_graphs = False
         st = slab.sim.get_state()
         st['v'][:len(mine)] = v0[mine]; st['F'][:len(mine)] = F0[mine]
@@ -152,15 +183,18 @@ def _slab_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_slab_sharded_forward_and_backward_match_the_single_domain_run_on_the_emulated_device():
+@pytest.mark.parametrize('exchange', ['nccl', 'peer'])
+def test_slab_sharded_forward_and_backward_match_the_single_domain_run_on_the_emulated_device(exchange):
     """the CUDA leg of the x-slab path that tests/run_slab_gpu.py exercises on 2 GPUs, here on 2 gloo ranks with the emulated device:
     SlabMPMSimulator.step (ghost all-reduce of the accumulator, migration) and step_grad (fmpm_p2g(write_F=0) -> ghost sum ->
     fmpm_substep_grad_scatter -> ghost sum of the v_out adjoint -> fmpm_substep_grad_finish, migrate_grad) against MPMSimulator on one
     domain: states and dL/d(x0, v0, C0, F0).  The ring holds 2 steps and the trajectory has 5: both sides wrap twice, the sharded side
-    checkpoints every chunk start and re-runs each chunk (exchanges and migrations included) during the backward pass."""
+    checkpoints every chunk start and re-runs each chunk (exchanges and migrations included) during the backward pass.
+    `peer`: the fused path of the product — p2g's and g2p.grad's vector reductions for nodes on shared planes go straight into the
+    neighbour's grids (here: POSIX shared memory across the two rank processes instead of NVLink peer memory), no all-reduce anywhere."""
     import torch.multiprocessing as mp
     mgr = mp.Manager(); ret = mgr.dict()
-    mp.spawn(_slab_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    mp.spawn(_slab_worker, args=(2, _free_port(), ret, exchange), nprocs=2, join=True)
     out = dict(ret)
     N = 700
     ref_s, ref_g = out[0]['ref_state'], out[0]['ref_grad']
