@@ -60,10 +60,28 @@ namespace cuemu {
 // switched only at barriers / warp collectives; blocks of a grid run concurrently on a few OS workers.  A barrier that can never complete
 // (a genuine synchronisation bug in a kernel) is detected and aborts with a message instead of hanging.
 enum { RUN = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3 };
+#if defined(__x86_64__) && !defined(CUEMU_USE_UCONTEXT)
+// user-space context switch without the two rt_sigprocmask system calls swapcontext makes: callee-saved registers + stack pointer
+#define CUEMU_FAST_SWITCH 1
+__attribute__((naked, noinline)) static void cuemu_switch(void** /*save_sp: rdi*/, void* /*load_sp: rsi*/) {
+  asm volatile(
+      "pushq %rbp\n\tpushq %rbx\n\tpushq %r12\n\tpushq %r13\n\tpushq %r14\n\tpushq %r15\n\t"
+      "movq %rsp, (%rdi)\n\t"
+      "movq %rsi, %rsp\n\t"
+      "popq %r15\n\tpopq %r14\n\tpopq %r13\n\tpopq %r12\n\tpopq %rbx\n\tpopq %rbp\n\t"
+      "ret\n\t");
+}
+struct Fiber { void* sp; int state; uint3 tid; int lin; };
+#else
 struct Fiber { ucontext_t ctx; int state; uint3 tid; int lin; };
+#endif
 struct BlockRun {
   std::vector<Fiber> fib;
+#ifdef CUEMU_FAST_SWITCH
+  void* sched = nullptr;
+#else
   ucontext_t sched;
+#endif
   int cur = 0, nt = 0, alive = 0, arrived = 0;
   std::vector<int> warp_alive, warp_arrived;
   std::vector<unsigned long long> slots;   // 32 per warp
@@ -73,7 +91,11 @@ struct BlockRun {
 };
 inline thread_local BlockRun* t_run = nullptr;
 inline Fiber& cur() { return t_run->fib[t_run->cur]; }
+#ifdef CUEMU_FAST_SWITCH
+inline void yield_to_sched() { BlockRun* r = t_run; cuemu_switch(&r->fib[r->cur].sp, r->sched); }
+#else
 inline void yield_to_sched() { BlockRun* r = t_run; swapcontext(&r->fib[r->cur].ctx, &r->sched); }
+#endif
 inline void release(BlockRun* r, int what, int warp) {
   for (auto& f : r->fib) if (f.state == what && (what == WAIT_BLOCK || f.lin / 32 == warp)) f.state = RUN;
 }
@@ -98,10 +120,21 @@ inline void fiber_main() {
   if (r->warp_alive[w] > 0 && r->warp_arrived[w] == r->warp_alive[w]) { r->warp_arrived[w] = 0; release(r, WAIT_WARP, w); }
   yield_to_sched();
 }
-struct Worker {   // per OS thread: fiber stacks are allocated once and reused
-  std::vector<char*> stacks;
+struct Worker {   // per OS worker thread of one launch; fiber stacks come from a process-wide cache and go back to it
   static constexpr size_t STACK = 512 * 1024;
-  char* stack(int i) { while ((int)stacks.size() <= i) stacks.push_back((char*)aligned_alloc(64, STACK)); return stacks[i]; }
+  std::vector<char*> stacks;
+  static std::mutex& mu() { static std::mutex m; return m; }
+  static std::vector<char*>& cache() { static std::vector<char*>* c = new std::vector<char*>(); return *c; }
+  char* stack(int i) {
+    while ((int)stacks.size() <= i) {
+      char* p = nullptr;
+      { std::lock_guard<std::mutex> lk(mu()); if (!cache().empty()) { p = cache().back(); cache().pop_back(); } }
+      if (!p) p = (char*)aligned_alloc(64, STACK);
+      stacks.push_back(p);
+    }
+    return stacks[i];
+  }
+  ~Worker() { std::lock_guard<std::mutex> lk(mu()); for (char* p : stacks) cache().push_back(p); }
 };
 inline void run_block(Worker& wk, uint3 bid, dim3 block, dim3 grid, size_t smem, const std::function<void()>& body) {
   const int nt = (int)(block.x * block.y * block.z);
@@ -113,14 +146,28 @@ inline void run_block(Worker& wk, uint3 bid, dim3 block, dim3 grid, size_t smem,
     Fiber& f = R.fib[t];
     f.state = RUN; f.lin = t;
     f.tid = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+#ifdef CUEMU_FAST_SWITCH
+    {  // initial frame: six callee-saved slots, then the entry point `ret` jumps to, then a null return address (fiber_main never returns)
+      void** top = (void**)(((uintptr_t)wk.stack(t) + Worker::STACK) & ~(uintptr_t)15);
+      *--top = nullptr;
+      *--top = (void*)fiber_main;
+      for (int i = 0; i < 6; i++) *--top = nullptr;
+      f.sp = top;
+    }
+#else
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = wk.stack(t); f.ctx.uc_stack.ss_size = Worker::STACK; f.ctx.uc_link = &R.sched;
     makecontext(&f.ctx, (void (*)())fiber_main, 0);
+#endif
   }
   for (;;) {
     bool progressed = false, all_done = true;
     for (int t = 0; t < nt; t++) {
+#ifdef CUEMU_FAST_SWITCH
+      if (R.fib[t].state == RUN) { R.cur = t; cuemu_switch(&R.sched, R.fib[t].sp); progressed = true; }
+#else
       if (R.fib[t].state == RUN) { R.cur = t; swapcontext(&R.sched, &R.fib[t].ctx); progressed = true; }
+#endif
       if (R.fib[t].state != DONE) all_done = false;
     }
     if (all_done) break;
@@ -136,7 +183,7 @@ template <class F> inline void launch(dim3 grid, dim3 block, size_t smem, F&& bo
   const int nw = (int)std::min<long long>(nb, std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
   std::atomic<long long> next{0};
   auto work = [&]() {
-    static thread_local Worker wk;
+    Worker wk;
     for (;;) {
       const long long b = next.fetch_add(1);
       if (b >= nb) break;
