@@ -317,7 +317,12 @@ def main():
         t_gop = time_phase(lambda: sim.phase('grid_op', f, 0), pre=_refill)
         # g2p writes frame f+1: time it on a scratch frame pair (f -> f+1 is rewritten by the next step anyway)
         t_g2p = time_phase(lambda: sim._ck(sim._lib.fmpm_g2p(sim._h, f, sim._stream()), 'g2p'))
+        # In peer mode every p2g above also reduced into the NEIGHBOURS' accumulators, unsynchronised: all ranks must have finished their
+        # isolated launches before anyone clears, or a late reduction lands in an accumulator that the next step assumes clear (found by
+        # running this arm on the CPU execution-model shim with skewed ranks, tests/cuda_emu/run_bench_emu.py).
+        barrier()
         sim.phase('clear_grid', f)
+        barrier()
         timing_note = 'batched launches on the final state'
     peak, peak_src = peaks()
     p2g_bytes = 136 * used + 16 * g_t            # p2g particle bytes + accumulated grid write-back

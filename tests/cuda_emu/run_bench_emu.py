@@ -41,6 +41,14 @@ def main():
         init(self, *a, **k)
         self.use_graphs = False
     simulator.MPMSimulator.__init__ = emu_init
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:   # multi-rank arm: gloo instead of nccl, POSIX shared memory instead of NVLink peer memory
+        import torch.distributed as dist
+        real_init = dist.init_process_group
+        dist.init_process_group = lambda backend=None, **k: real_init('gloo', **{kk: vv for kk, vv in k.items() if kk != 'device_id'})
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        import test_cuda_emu_mpm
+        from fluidlab_b200 import slab
+        slab.SymmetricMemoryPeers = test_cuda_emu_mpm.ShmPeers
     import bench
     bench.main()
 
