@@ -222,13 +222,14 @@ def test_g2p2g_fused_substeps_equal_the_unfused_path(emu):
     P = make_particles(x, mat, n, used=used)
     bnd = dict(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.7, 0.7, 0.7))
     out = {}
-    for fuse in (False, True):
-        s = MPMSimulator(dim=3, quality=n / 64, gravity=(0.3, -10, 0), horizon=50, max_substeps_local=40, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
-        s.use_graphs, s.fuse_g2p2g = False, fuse
+    for fuse in (False, True, 'unsorted'):   # 'unsorted': no cell sort at all — the scatter's warp-local key ranking carries the whole burden
+        s = MPMSimulator(dim=3, quality=n / 64, gravity=(0.3, -10, 0), horizon=50, max_substeps_local=40, max_substeps_global=1000, ckpt_dest='cpu', device='cpu',
+                         sort_every=0 if fuse == 'unsorted' else 1)
+        s.use_graphs, s.fuse_g2p2g = False, bool(fuse)
         s.setup_boundary(**bnd)
         s.build(None, None, [], P)
         st = s.get_state(); st['v'][:] = v0; st['F'][:] = F0; st['C'][:] = C0; s.set_state(0, st)
-        assert s._can_fuse() == fuse
+        assert s._can_fuse() == bool(fuse)
         s.step(None); s.step(None)
         out[fuse] = s.get_state()
     o = orc.OracleSim(n, P, gravity=(0.3, -10, 0), boundary=bnd, precision=64, max_substeps_local=40)
@@ -241,6 +242,7 @@ def test_g2p2g_fused_substeps_equal_the_unfused_path(emu):
         assert rel(out[True][k][u], out[False][k][u].astype(np.float64)) < bar, (k, rel(out[True][k][u], out[False][k][u].astype(np.float64)))
         assert rel(out[True][k][u], ofr[k][u]) < bar, (k, rel(out[True][k][u], ofr[k][u]))
         assert np.array_equal(out[True][k][~u], out[False][k][~u]), 'parked particles must be carried over untouched'
+        assert rel(out['unsorted'][k][u], ofr[k][u]) < bar, ('unsorted', k, rel(out['unsorted'][k][u], ofr[k][u]))
 
 
 def test_device_side_observation_equals_fluid_env_get_obs(emu):
