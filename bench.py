@@ -369,6 +369,36 @@ def main():
         fb = {'value': world * nfb * SUBSTEPS_PER_STEP / (fb_ms * 1e-3), 'unit': 'substeps/s (each = 1 forward + 1 backward substep, incl. chunk re-simulation and set_state)',
               'steps': nfb, 'runs_ms': fb_runs, 'particle_grad_ms': t_pg, 'g2p_grad_scatter_ms_incl_dense_clear': t_sc}
         sim.disable_grad()
+        # The same pass with a ring that holds the WHOLE trajectory (max_substeps_local = (steps + 1) * 10 instead of the reference's 50):
+        # (steps * 10 + 1) frames x 100 B x N + the per-frame grids are ~18 GB at 1M particles / 100 substeps — nothing on a 180 GB B200 — and
+        # the backward pass no longer re-simulates every chunk (MPM:856-912).  Extra key; the headline fwd_bwd keeps the reference's scheme.
+        try:
+            T2 = (nfb + 1) * SUBSTEPS_PER_STEP
+            sim2 = MPMSimulator(dim=3, quality=QUALITY, gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T2, max_substeps_global=10 ** 7,
+                                ckpt_dest='gpu', device=dev, sort_every=args.sort_every)
+            sim2.build(None, None, [], parts)
+            tgt2, mask2 = tgt, sim2.material_row_mask(fluidlab_b200.macros.WATER)
+
+            def fwd_bwd2():
+                sim2.set_state(0, init); sim2.enable_grad()
+                for _ in range(nfb):
+                    sim2.step(None)
+                sim2.reset_grad()
+                sim2.add_x_grad_chamfer(tgt2, mask2, 1.0)
+                for _ in range(nfb):
+                    sim2.step_grad(None)
+            fwd_bwd2(); barrier()
+            runs2 = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fwd_bwd2(); b.record(); barrier()
+                runs2.append(a.elapsed_time(b))
+            fb['whole_trajectory_ring'] = {'value': nfb * SUBSTEPS_PER_STEP / (float(np.median(runs2)) * 1e-3), 'unit': 'substeps/s (1 forward + 1 backward substep each, no re-simulation)',
+                                           'max_substeps_local': T2, 'runs_ms': runs2, 'stored_grids': sim2._pm_ring is not None}
+            del sim2
+            torch.cuda.empty_cache()
+        except Exception as ex:   # an extra: never let it take the bench line down
+            fb['whole_trajectory_ring'] = {'error': f'{type(ex).__name__}: {ex}'}
 
     # ------------------------------------------------------------------ end to end through the public API with host buffers
     pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in init.items() if k in ('x', 'v', 'C', 'F', 'used')}

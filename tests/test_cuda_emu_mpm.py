@@ -282,8 +282,7 @@ def test_bench_script_runs_end_to_end_on_the_emulated_device():
     numbers are meaningless here."""
     import json
     import subprocess
-    r = subprocess.run([sys.executable, os.path.join(HERE, 'cuda_emu', 'run_bench_emu.py'), '--particles', '1500', '--steps', '2', '--warmup', '1', '--no-cpu', '--bwd', '0',
-                        '--fuse-g2p2g', '1'], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'cuda_emu', 'run_bench_emu.py'), '--particles', '1200', '--steps', '2', '--warmup', '1', '--no-cpu', '--fuse-g2p2g', '1'], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e',
@@ -292,6 +291,8 @@ def test_bench_script_runs_end_to_end_on_the_emulated_device():
     assert line['metric'] == 'mpm_substeps_per_s_fwd' and line['warmup'] >= 3 and line['value'] > 0 and line['e2e']['value'] > 0
     assert line['config']['g2p2g_fused'] is True and line['gpu_launches'] == 2 * 21 + 2
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
+    fb = line['fwd_bwd']
+    assert fb['value'] > 0 and 'error' not in fb['whole_trajectory_ring'] and fb['whole_trajectory_ring']['max_substeps_local'] == 30
     ob = line['e2e_obs_bridge']
     assert 'error' not in ob and ob['d2h_bytes_per_step'] < line['e2e']['d2h_bytes_per_step']
 
