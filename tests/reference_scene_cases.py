@@ -1,0 +1,74 @@
+"""The PRODUCT (fluidlab_b200: MPMSimulator + agents, real kernels) against runs of the reference's own agent scenes
+(tests/golden/reference_run_{latteart,jetbot}.npz — the unmodified reference classes stepped on the Taichi emulation,
+tests/golden/make_reference_run.py).  tests/test_reference_run.py pins the ORACLE to these fixtures; here the device path is compared with
+them directly.  Shared by tests/test_cuda_emu_mpm.py (emulated device) and tests/test_gpu_parity.py (B200)."""
+import os
+import numpy as np
+
+from conftest import make_particles
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+BARS = dict(x=1e-5, F=2e-5, v=2e-4, C=2e-3)
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(b).max(), 1e-12))
+
+
+def _check(fr, d):
+    assert np.array_equal(fr['used'], d['ref_used']), 'used flags differ from the reference run'
+    u = fr['used'] != 0
+    for k, bar in BARS.items():
+        assert rel(fr[k][u], d['ref_' + k][u]) < bar, (k, rel(fr[k][u], d['ref_' + k][u]))
+    assert np.array_equal(fr['x'][~u], d['ref_x'][~u]), 'parked particles differ'
+
+
+def _sim(d, device, gravity, bnd):
+    from fluidlab_b200 import MPMSimulator
+    s = MPMSimulator(dim=3, quality=int(d['n_grid']) / 64, gravity=gravity, horizon=10, max_substeps_local=int(d['T']), max_substeps_global=1000,
+                     ckpt_dest='gpu' if device is None else 'cpu', device=device)
+    s.setup_boundary(**bnd)
+    return s
+
+
+def _drive(s, agent, inj, d):
+    inj.random_vector_np = np.asarray(d['random_vector'], dtype=np.float32)     # the reference drew it from the global NumPy RNG
+    P = make_particles(d['x0'], d['mat'], int(d['n_grid']), used=d['used0'])
+    s.build(agent, None, [], P)
+    agent.build(s)
+    assert np.abs(inj.get_state(0)[:7] - d['init_state'][:7]).max() < 1e-6, 'init_pos / init_euler -> pose (effector.py:63-73)'
+    agent.apply_action_p(d['action_p'])
+    for a in d['actions']:
+        s.step(a)
+    f = s.cur_substep_local
+    assert np.abs(inj.get_state(f)[:7] - d['ref_pose'][:7]).max() < 2e-6, (inj.get_state(f), d['ref_pose'])
+    _check(s.readframe(f), d)
+
+
+def run_latteart_case(device=None):
+    """AgentInjector + locally-random Injector whose own boundary is a y-pinned cylinder (radial clamp hit), MILK injected into COFFEE,
+    cylinder domain, gravity -20, 3 steps"""
+    from fluidlab_b200 import AgentInjector
+    d = np.load(os.path.join(G, 'reference_run_latteart.npz'))
+    s = _sim(d, device, (0.0, -20.0, 0.0), dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.34, 0.9)))
+    common = dict(max_substeps_local=int(d['T']), max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
+    agent = AgentInjector(**common)
+    agent.add_effector(type='Injector', params=dict(radius=0.0075, flux=int(d['flux']), init_pos=(0.5, 0.5, 0.5), action_dim=3, inject_v=(0.0, -3.0, 0.0),
+                                                    action_scale_p=(1.0, 1.0, 1.0), action_scale_v=(1.0, 1.0, 1.0), locally_random=True),
+                       mesh_cfg=None, boundary_cfg=dict(type='cylinder', xz_radius=0.12, xz_center=(0.5, 0.5), y_range=(0.55, 0.55)))
+    _drive(s, agent, agent.effectors[0], d)
+
+
+def run_jetbot_case(device=None):
+    """AgentJetBot: a 6-DOF Injector (rotated pose, pose chain with quaternions) injecting WATER into a pool + the collector, 3 steps"""
+    from fluidlab_b200 import AgentJetBot
+    d = np.load(os.path.join(G, 'reference_run_jetbot.npz'))
+    cube = lambda lo, hi: dict(type='cube', lower=tuple(lo), upper=tuple(hi))
+    s = _sim(d, device, (0.0, -10.0, 0.0), cube(d['b_lower'], d['b_upper']))
+    common = dict(max_substeps_local=int(d['T']), max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
+    agent = AgentJetBot(collector_boundary=cube(d['c_lower'], d['c_upper']), **common)
+    agent.add_effector(type='Injector', params=dict(radius=0.015, flux=int(d['flux']), init_pos=(0.58, 0.55, 0.5), init_euler=(20.0, 35.0, -10.0), inject_v=(-3.0, 0.0, 0.0),
+                                                    inject_p=(-0.07, 0.0, 0.0), action_dim=6, action_scale_p=(1.0,) * 6, action_scale_v=(1.0, 1.0, 1.0, 5.0, 5.0, 5.0)),
+                       mesh_cfg=None, boundary_cfg=cube(d['e_lower'], d['e_upper']))
+    _drive(s, agent, agent.effectors[0], d)
+    assert int(d['ref_used'].sum()) < int(d['used0'].sum()) + int(d['flux']) * 10 * int(d['n_steps']), 'the reference run collected nothing'

@@ -302,3 +302,10 @@ def test_circulation_stack_equals_a_run_of_the_real_reference_stack(emu):
     reference's OWN MPMSimulator + AgentCirculation + AirCon + SmokeField); see tests/circulation_case.py"""
     from circulation_case import run_reference_stack_case
     run_reference_stack_case(device='cpu')
+
+
+@pytest.mark.parametrize('scene', ['latteart', 'jetbot'])
+def test_agent_scenes_equal_runs_of_the_real_reference_agents(emu, scene):
+    """product (real kernels on the emulated device) vs runs of the reference's own AgentInjector / AgentJetBot scenes; tests/reference_scene_cases.py"""
+    import reference_scene_cases as cases
+    getattr(cases, f'run_{scene}_case')(device='cpu')

@@ -982,3 +982,13 @@ def test_slab_sharded_backward_matches_single_gpu(exchange):
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                         '--master-port', '29547', os.path.join(root, 'tests', 'run_slab_gpu.py')], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and 'SLAB_GRAD_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize('scene', ['latteart', 'jetbot'])
+def test_cuda_matches_runs_of_the_real_reference_agents(scene):
+    """the CUDA path against runs of the reference's own AgentInjector (LatteArt configuration in miniature) and AgentJetBot (6-DOF injector +
+    collector) scenes, stepped with the unmodified reference classes on the Taichi emulation (tests/reference_scene_cases.py; verified on the
+    CPU execution-model shim, first hardware run pending)"""
+    _need_gpu()
+    import reference_scene_cases as cases
+    getattr(cases, f'run_{scene}_case')(device=None)
