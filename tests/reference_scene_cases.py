@@ -72,3 +72,70 @@ def run_jetbot_case(device=None):
                        mesh_cfg=None, boundary_cfg=cube(d['e_lower'], d['e_upper']))
     _drive(s, agent, agent.effectors[0], d)
     assert int(d['ref_used'].sum()) < int(d['used0'].sum()) + int(d['flux']) * 10 * int(d['n_steps']), 'the reference run collected nothing'
+
+
+def run_pouring_case(device=None):
+    """AgentPouring: a 6-DOF Rigid effector whose Dynamic SDF mesh (rotated, anisotropically scaled box) collides at grid AND particle level with
+    friction + soft influence, plus the collector; elastic blob; 2 steps.  The mesh goes through the product's own transform code
+    (meshes.py: T_mesh_to_voxels @ inv(T_init)) and must land on the reference's matrix."""
+    from fluidlab_b200 import AgentPouring, macros as M
+    d = np.load(os.path.join(G, 'reference_run_pouring.npz'))
+    cube = lambda lo, hi: dict(type='cube', lower=tuple(lo), upper=tuple(hi))
+    s = _sim(d, device, (0.0, -10.0, 0.0), cube(d['b_lower'], d['b_upper']))
+    res, he = 32, 0.2                                   # the volume's mesh frame, as in tests/golden/make_reference_run.py: scene_pouring
+    sc = (res - 1) / (2 * he)
+    Tm = np.eye(4); Tm[0, 0] = Tm[1, 1] = Tm[2, 2] = sc; Tm[:3, 3] = sc * he
+    common = dict(max_substeps_local=int(d['T']), max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
+    agent = AgentPouring(collector_boundary=cube(d['c_lower'], d['c_upper']), **common)
+    agent.add_effector(type='Rigid', params=dict(init_pos=(0.5, 0.64, 0.5), init_euler=(0.0, 23.0, 5.0), action_dim=6, action_scale_p=(1.0,) * 6, action_scale_v=(1.0,) * 6),
+                       mesh_cfg=dict(file='box.obj', material=M.STIRRER, softness=100.0, scale=(1.0, 0.9, 1.1), euler=(0.0, 10.0, 0.0),
+                                     sdf=dict(voxels=d['vox'], T_mesh_to_voxels=Tm)), boundary_cfg=cube(d['e_lower'], d['e_upper']))
+    rigid = agent.effectors[0]
+    assert np.abs(rigid.mesh.T_mesh_to_voxels_np - d['T_final']).max() < 1e-4 * np.abs(d['T_final']).max()
+    assert abs(rigid.mesh.friction - float(d['friction'])) < 1e-7
+    P = make_particles(d['x0'], d['mat'], int(d['n_grid']))
+    s.build(agent, None, [], P)
+    agent.build(s)
+    agent.apply_action_p(d['action_p'])
+    for a in d['actions']:
+        s.step(a)
+    f = s.cur_substep_local
+    assert np.abs(rigid.get_state(f)[:7] - d['ref_pose'][:7]).max() < 2e-6
+    assert np.abs(d['ref_v']).max() > 5.0 and int(d['ref_used'].sum()) < len(d['x0']), 'the reference collider / collector did nothing'
+    _check(s.readframe(f), d)
+
+
+def run_icecream_case(device=None):
+    """AgentIceCreamDynamic: BallInjector of plasto-elastic ICECREAM that stops at inject_till + a Rigid sphere collider gated at y > 0.25 + a
+    Static mesh with dynamics colliding in grid_op; every particle starts parked; 3 steps"""
+    from conftest import sphere_sdf, box_sdf
+    from fluidlab_b200 import AgentIceCreamDynamic, Statics, macros as M
+    d = np.load(os.path.join(G, 'reference_run_icecream.npz'))
+    cube = dict(type='cube', lower=tuple(d['lower']), upper=tuple(d['upper']))
+    s = _sim(d, device, (0.0, -10.0, 0.0), cube)
+    vox, Tm = sphere_sdf(0.10, 0.2)
+    bv, bT = box_sdf((0.3, 0.05, 0.3), 0.4)
+    assert np.array_equal(vox.reshape(d['vox'].shape), d['vox']) and np.array_equal(bv.reshape(d['svox'].shape), d['svox'])
+    common = dict(max_substeps_local=int(d['T']), max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
+    agent = AgentIceCreamDynamic(inject_till=int(d['inject_till']), **common)
+    agent.add_effector(type='BallInjector', params=dict(locally_random=True, radius=0.035, flux=int(d['flux']), init_pos=(0.5, 0.62, 0.5), inject_v=(0.0, -0.4, 0.0), action_dim=3),
+                       mesh_cfg=None, boundary_cfg=cube)
+    agent.add_effector(type='Rigid', params=dict(init_pos=(0.5, 0.46, 0.5), action_dim=3),
+                       mesh_cfg=dict(file='cone.obj', material=M.CONE, softness=100.0, sdf=dict(voxels=vox.reshape(d['vox'].shape), T_mesh_to_voxels=Tm)), boundary_cfg=cube)
+    statics = Statics()
+    statics.add_static(file='plate.obj', material=M.CUP, has_dynamics=True, pos=(0.5, 0.36, 0.5), sdf=dict(voxels=bv.reshape(d['svox'].shape), T_mesh_to_voxels=bT))
+    inj, rigid = agent.effectors
+    assert np.abs(rigid.mesh.T_mesh_to_voxels_np - d['T_rigid']).max() < 1e-5 * np.abs(d['T_rigid']).max()
+    assert np.abs(statics[0].T_mesh_to_voxels_np - d['T_static']).max() < 1e-5 * np.abs(d['T_static']).max()
+    inj.random_vector_np = np.asarray(d['random_vector'], dtype=np.float32)
+    N = len(d['x0'])
+    P = make_particles(d['x0'], d['mat'], int(d['n_grid']), used=np.zeros(N, np.int32))
+    s.build(agent, None, statics, P)
+    agent.build(s)
+    agent.apply_action_p(d['action_p'])
+    for a in d['actions']:
+        s.step(a)
+    f = s.cur_substep_local
+    assert np.abs(rigid.get_state(f)[:7] - d['ref_pose'][:7]).max() < 2e-6
+    assert int(d['ref_used'].sum()) == int(d['flux']) * (int(d['inject_till']) + 1) or int(d['ref_used'].sum()) > 0
+    _check(s.readframe(f), d)

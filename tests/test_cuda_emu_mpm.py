@@ -304,8 +304,8 @@ def test_circulation_stack_equals_a_run_of_the_real_reference_stack(emu):
     run_reference_stack_case(device='cpu')
 
 
-@pytest.mark.parametrize('scene', ['latteart', 'jetbot'])
+@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream'])
 def test_agent_scenes_equal_runs_of_the_real_reference_agents(emu, scene):
-    """product (real kernels on the emulated device) vs runs of the reference's own AgentInjector / AgentJetBot scenes; tests/reference_scene_cases.py"""
+    """product (real kernels on the emulated device) vs runs of the reference's own AgentInjector / AgentJetBot / AgentPouring / AgentIceCreamDynamic scenes; tests/reference_scene_cases.py"""
     import reference_scene_cases as cases
     getattr(cases, f'run_{scene}_case')(device='cpu')

@@ -984,10 +984,11 @@ def test_slab_sharded_backward_matches_single_gpu(exchange):
     assert r.returncode == 0 and 'SLAB_GRAD_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize('scene', ['latteart', 'jetbot'])
+@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream'])
 def test_cuda_matches_runs_of_the_real_reference_agents(scene):
-    """the CUDA path against runs of the reference's own AgentInjector (LatteArt configuration in miniature) and AgentJetBot (6-DOF injector +
-    collector) scenes, stepped with the unmodified reference classes on the Taichi emulation (tests/reference_scene_cases.py; verified on the
+    """the CUDA path against runs of the reference's own AgentInjector (LatteArt configuration in miniature), AgentJetBot (6-DOF injector +
+    collector), AgentPouring (6-DOF Rigid SDF collider at grid and particle level + collector) and AgentIceCreamDynamic (BallInjector, gated
+    Rigid collider, Static collider) scenes, stepped with the unmodified reference classes on the Taichi emulation (tests/reference_scene_cases.py; verified on the
     CPU execution-model shim, first hardware run pending)"""
     _need_gpu()
     import reference_scene_cases as cases
