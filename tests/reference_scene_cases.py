@@ -139,3 +139,33 @@ def run_icecream_case(device=None):
     assert np.abs(rigid.get_state(f)[:7] - d['ref_pose'][:7]).max() < 2e-6
     assert int(d['ref_used'].sum()) == int(d['flux']) * (int(d['inject_till']) + 1) or int(d['ref_used'].sum()) > 0
     _check(s.readframe(f), d)
+
+
+def run_cloud_adjoint_case(device=None):
+    """the device ADJOINT (fp32) against central finite differences taken through the reference's own forward kernels in float64
+    (tests/golden/reference_fd.npz, make_reference_fd.py): L = sum w . state_3 of a WATER / ELASTIC / ICECREAM / MILK_VIS cloud, 20 picked
+    entries of dL/d(x, v, C, F)_0.  fp32 against an fp64 finite difference: 2e-3 of the largest picked derivative."""
+    from fluidlab_b200 import MPMSimulator
+    FD = np.load(os.path.join(G, 'reference_fd.npz'), allow_pickle=True)
+    n_grid, n_sub = int(FD['cloud_n_grid']), int(FD['cloud_n_sub'])
+    P = make_particles(FD['cloud_x'], FD['cloud_mat'], n_grid)
+    s = MPMSimulator(dim=3, quality=n_grid / 64, gravity=(0.0, -10.0, 0.0), horizon=10, max_substeps_local=10, max_substeps_global=1000,
+                     ckpt_dest='gpu' if device is None else 'cpu', device=device)
+    s.setup_boundary(type='cube', lower=tuple(FD['cloud_lower']), upper=tuple(FD['cloud_upper']))
+    s.build(None, None, [], P)
+    s.setframe(0, FD['cloud_x'], FD['cloud_v'], FD['cloud_C'], FD['cloud_F'], np.ones(len(FD['cloud_x']), np.int32))
+    s.enable_grad()
+    for f in range(n_sub):
+        s.substep(f, True); s.cur_substep_global += 1
+    fr = s.readframe(n_sub)
+    w = {k: FD['cloud_w_' + k] for k in ('x', 'v', 'C', 'F')}
+    loss = sum((w[k] * fr[k].astype(np.float64)).sum() for k in w)
+    assert abs(loss - float(FD['cloud_loss'])) < 2e-5 * max(1.0, abs(loss)), (loss, float(FD['cloud_loss']))
+    s.reset_grad(); s.set_grad(w['x'], w['v'], w['C'], w['F'])
+    for f in reversed(range(n_sub)):
+        s.cur_substep_global -= 1; s.substep_grad(f, True)
+    g = s.get_grad()
+    scale = float(np.abs(FD['cloud_fd']).max())
+    for key, idx, fd in zip(FD['cloud_pick_key'], FD['cloud_pick_idx'], FD['cloud_fd']):
+        an = float(g[str(key)].reshape(-1)[int(idx)])
+        assert abs(an - fd) <= 2e-3 * scale, (str(key), int(idx), an, float(fd), scale)

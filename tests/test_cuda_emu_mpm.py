@@ -309,3 +309,8 @@ def test_agent_scenes_equal_runs_of_the_real_reference_agents(emu, scene):
     """product (real kernels on the emulated device) vs runs of the reference's own AgentInjector / AgentJetBot / AgentPouring / AgentIceCreamDynamic scenes; tests/reference_scene_cases.py"""
     import reference_scene_cases as cases
     getattr(cases, f'run_{scene}_case')(device='cpu')
+
+
+def test_device_adjoint_equals_finite_differences_through_the_reference_forward(emu):
+    import reference_scene_cases as cases
+    cases.run_cloud_adjoint_case(device='cpu')

@@ -993,3 +993,10 @@ def test_cuda_matches_runs_of_the_real_reference_agents(scene):
     _need_gpu()
     import reference_scene_cases as cases
     getattr(cases, f'run_{scene}_case')(device=None)
+
+
+def test_cuda_adjoint_equals_finite_differences_through_the_reference_forward():
+    """the CUDA adjoint kernels against central differences of the REFERENCE's own forward kernels run in float64 (tests/reference_scene_cases.py)"""
+    _need_gpu()
+    import reference_scene_cases as cases
+    cases.run_cloud_adjoint_case(device=None)
