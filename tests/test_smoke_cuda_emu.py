@@ -267,3 +267,27 @@ def test_smoke_timing_script_runs_on_the_emulated_library(emu, monkeypatch):
     out = smoke_times.run(res=24, dev=torch.device('cpu'), reps=1, band=(8, 14), iters_list=(5,), event_cls=Ev, sync=lambda: None)
     ms = out['runs'][0]['ms']
     assert set(ms) >= {'step', 'step_grad', 'pressure', 'advect_grad'} and all(v > 0 for v in ms.values())
+
+
+@pytest.mark.parametrize('band', [(3, 12), (2, 15)], ids=['H8_tiled', 'H12_sweep_per_launch'])
+def test_other_band_heights_forward_and_adjoint(emu, band):
+    """band of 8 layers: the largest the time-blocked tile kernel takes; 12 layers: the one-sweep-per-launch fallback (k_jacobi_simple).
+    Same inputs as the reference-run fixture, other free band; against the oracle, forward and adjoint."""
+    d = dict(np.load(os.path.join(GOLDEN, 'reference_smoke.npz')))
+    fd = np.load(os.path.join(GOLDEN, 'reference_smoke_fd.npz'))
+    d['lower_y'], d['higher_y'] = np.int64(band[0]), np.int64(band[1])
+    e, o = _pair(emu, d, 11)
+    for s in range(2):
+        e.step(s, 10 * s); o.step(s, 10 * s)
+    assert np.array_equal(e.a['is_free'][0].reshape((e.n,) * 3), o.is_free(0)) and o.is_free(0).sum() > 0
+    a, b = e.get_state(2), o.get_state(2)
+    for k in ('v', 'p', 'q'):
+        assert rel(a[k], b[k]) < 1e-5, (band, k, rel(a[k], b[k]))
+    o.reset_grad()
+    z = o._alloc(); z['v'], z['q'], z['p'] = fd['w_v'], fd['w_q'], fd['w_p']
+    o.set_grad(2, z); e.set_grad(2, z)
+    for s in (1, 0):
+        e.step_grad(s, 10 * s); o.step_grad(s, 10 * s)
+    a, b = e.get_state(0, grad=True), o.get_grad(0)
+    for k in ('v', 'q', 'p'):
+        assert rel(a[k], b[k]) < 1e-4, (band, k, rel(a[k], b[k]))
