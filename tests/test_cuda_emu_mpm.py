@@ -85,6 +85,8 @@ def test_circulation_stack_on_the_emulated_device(emu):
     from circulation_case import run_circulation_stack
     dets = [[5, 16], [7, 16], [3, 16], [5, 14], [5, 18], [5, 8], [7, 8], [3, 8], [5, 6], [5, 10], [20, 12], [21, 12], [18, 12], [20, 9], [20, 16]]
     run_circulation_stack(device='cpu', res=24, iters=10, band=(8, 14), detectors=dets, detector_h=11, n_steps=3, max_substeps_local=40)
+    # a ring of 2 steps for a 3-step trajectory: MPM ring and smoke ring wrap, the backward pass re-runs the first chunk (smoke steps included)
+    run_circulation_stack(device='cpu', res=24, iters=10, band=(8, 14), detectors=dets, detector_h=11, n_steps=3, max_substeps_local=20, ring_wraps=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------- x-slabs, 2 ranks (gloo)

@@ -106,6 +106,9 @@ def test_circulation_stack_through_taichi_env():
     _need_gpu()
     from circulation_case import run_circulation_stack
     run_circulation_stack(device=None)
+    # reduced size with a ring of 2 steps for 3 steps: MPM and smoke rings wrap, the backward pass re-runs the first chunk
+    dets = [[5, 16], [7, 16], [3, 16], [5, 14], [5, 18], [5, 8], [7, 8], [3, 8], [5, 6], [5, 10], [20, 12], [21, 12], [18, 12], [20, 9], [20, 16]]
+    run_circulation_stack(device=None, res=24, iters=10, band=(8, 14), detectors=dets, detector_h=11, n_steps=3, max_substeps_local=20, ring_wraps=True)
 
 
 def test_circulation_stack_equals_a_run_of_the_real_reference_stack():
