@@ -595,6 +595,13 @@ class MPMSimulator:
         torch.cuda.current_stream(self.device).synchronize()
         return host.numpy()
 
+    def get_state_render_device(self, f):
+        """x (N,3) float32 and used (N,) int32 of frame f in original particle order as DEVICE tensors (staging buffers, valid until the next
+        read) — `torch.utils.dlpack.to_dlpack(t)` / `__dlpack__` hands them to a renderer without the GPU -> CPU -> GPU round trip the
+        reference's renderers make (renderers/gl_renderer.py:172-177, README.md:62)."""
+        r = self.readframe_torch(f, ('x', 'used'))
+        return SimpleNamespace(x=r['x'], used=r['used'])
+
     def get_state_render(self, f):  # MPM:705-707
         r = self.readframe(f, ('x', 'used'))
         return SimpleNamespace(x=r['x'], used=r['used'])

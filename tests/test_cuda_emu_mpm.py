@@ -276,6 +276,11 @@ def test_device_side_observation_equals_fluid_env_get_obs(emu):
     assert got.dtype == np.float32 and got.shape == want.shape and got.size < 0.2 * state['x'].size * 3
     assert np.array_equal(got, want)
     assert state['used'][bodies['particle_ids'][0]].sum() == 40, 'the injector must have activated 2 particles in each of the 20 substeps'
+    # render bridge: the same positions as device tensors, exportable through DLPack
+    import torch
+    r = env.simulator.get_state_render_device(env.simulator.cur_substep_local)
+    x_dl = torch.utils.dlpack.from_dlpack(torch.utils.dlpack.to_dlpack(r.x))
+    assert np.array_equal(x_dl.cpu().numpy(), state['x']) and np.array_equal(r.used.cpu().numpy(), state['used'])
 
 
 def test_bench_script_runs_end_to_end_on_the_emulated_device():
