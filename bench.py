@@ -377,6 +377,7 @@ def main():
             sim2 = MPMSimulator(dim=3, quality=QUALITY, gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T2, max_substeps_global=10 ** 7,
                                 ckpt_dest='gpu', device=dev, sort_every=args.sort_every)
             sim2.build(None, None, [], parts)
+            sim2.fuse_g2p2g = bool(args.fuse_g2p2g)
             tgt2, mask2 = tgt, sim2.material_row_mask(fluidlab_b200.macros.WATER)
 
             def fwd_bwd2():

@@ -131,6 +131,7 @@ _PROTOS = {
     "fmpm_substep_store": (_I, [vp, _I, vp]),
     "fmpm_g2p2g": (_I, [vp, _I, _I, vp]),
     "fmpm_substeps_fused": (_I, [vp, _I, _I, vp]),
+    "fmpm_substeps_fused_store": (_I, [vp, _I, _I, vp]),
     "fmpm_substep_grad_stored": (_I, [vp, _I, _I, _I, vp]),
     "fmpm_substep_grad_scatter": (_I, [vp, _I, _I, vp]),
     "fmpm_substep_grad_finish": (_I, [vp, _I, _I, _I, vp]),

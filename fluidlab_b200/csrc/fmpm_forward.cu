@@ -488,6 +488,40 @@ extern "C" int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream) {
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p2g");
   return 0;
 }
+// the same fusion in grad mode with per-frame grids (fmpm_substep_store): g2p gathers from ring slot f, p2g scatters into ring slot f+1, and
+// every frame is written completely (the backward pass reads x, v, C, F of every frame): 148 B instead of 212 B per particle and substep
+static int g2p2g_store_impl(FmpmHandle* h, int f, void* stream) {
+  if (check_bound(h, "fmpm_g2p2g(store)") || check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_g2p2g(store)")) return 1;
+  if (h->col.has_rigid || h->bodies.n_bodies > 0 || h->slab.enabled) {
+    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: not available with a rigid effector, MAT_RIGID bodies or x-slabs"); return 1;
+  }
+  KParams P = make_kparams(h, f + 1);            // scatter target: accumulator + block flags of slot f+1
+  P.grid_v = make_kparams(h, f).grid_v;          // gather source: v_out of slot f
+  if (P.N == 0) return 0;
+  const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
+  FMPM_LAUNCH(k_g2p2g<true>, blocks, P2G_WARPS * 32, 0, stream, P, f);
+  FMPM_CHECK_LAUNCH(h, "fmpm_g2p2g(store)");
+  return 0;
+}
+extern "C" int fmpm_substeps_fused_store(FmpmHandle* h, int f0, int n, void* stream) {
+  if (check_bound(h, "fmpm_substeps_fused_store")) return 1;
+  if (!h->buf.grid_pm_ring || !h->buf.grid_v_ring || !h->buf.blk_list_ring) {
+    snprintf(h->err, sizeof(h->err), "fmpm_substeps_fused_store: the per-frame grid ring was not bound"); return 1;
+  }
+  if (n < 1 || check_frame(h, f0 + n - 1, h->cfg.max_substeps_local - 1, "fmpm_substeps_fused_store")) return 1;
+  const int nblk = (h->cfg.n_grid / 8) * (h->cfg.n_grid / 8) * (h->cfg.n_grid / 8);
+  const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  for (int i = 0; i < n; i++) {
+    const int f = f0 + i;
+    KParams P = make_kparams(h, f);
+    FMPM_LAUNCH(k_clear_blocks, grid, 256, 0, stream, P);   // previous occupant of slot f
+    FMPM_CHECK_LAUNCH(h, "fmpm_substeps_fused_store(clear)");
+    if (i == 0) { if (fmpm_p2g_impl(h, f, 1, f, stream)) return 1; }
+    else if (g2p2g_store_impl(h, f - 1, stream)) return 1;
+    if (fmpm_grid_op_impl(h, f, 0, 0, f, stream)) return 1;
+  }
+  return fmpm_g2p_impl(h, f0 + n - 1, f0 + n - 1, stream);
+}
 // n forward substeps f0 .. f0+n-1 with the inner g2p / p2g pairs fused: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1).
 // Frames f0 and f0+n are complete; the frames in between hold x, used and F only.  The grid must be clear on entry (as for fmpm_substep).
 extern "C" int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream) {

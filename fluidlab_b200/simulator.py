@@ -413,8 +413,17 @@ class MPMSimulator:
         return b.inv[ids.long()].to(torch.int32).contiguous()
 
     def _can_fuse(self):
-        """g2p2g fusion applies to forward-only steps without an agent, MAT_RIGID bodies or stored grids (csrc/fmpm_forward.cu: k_g2p2g)"""
-        return bool(getattr(self, 'fuse_g2p2g', False)) and not self.grad_enabled and not getattr(self, '_has_rigid_bodies', False) and self.agent is None
+        """g2p2g fusion applies to steps without an agent or MAT_RIGID bodies: forward-only (fmpm_substeps_fused) and, in grad mode, the
+        stored-grid path (fmpm_substeps_fused_store); not the recompute path (csrc/fmpm_forward.cu: k_g2p2g)"""
+        if not bool(getattr(self, 'fuse_g2p2g', False)) or getattr(self, '_has_rigid_bodies', False) or self.agent is not None:
+            return False
+        return (not self.grad_enabled) or self._storing()
+
+    def _fused_substeps(self, f0):
+        if self._storing():
+            self._ck(self._lib.fmpm_substeps_fused_store(self._h, f0, self.n_substeps, self._stream()), 'fmpm_substeps_fused_store')
+        else:
+            self._ck(self._lib.fmpm_substeps_fused(self._h, f0, self.n_substeps, self._stream()), 'fmpm_substeps_fused')
 
     def _storing(self):
         if not (self.grad_enabled and self.store_grids):
@@ -430,7 +439,8 @@ class MPMSimulator:
         s_local = self.cur_step_local
         f0 = self.cur_substep_local
         store = self._storing()
-        g = self._graphs.get((s_local, store))
+        key = (s_local, store, self._can_fuse())
+        g = self._graphs.get(key)
         if g is None:
             try:
                 fn = self._lib.fmpm_substep_store if store else self._lib.fmpm_substep
@@ -438,11 +448,11 @@ class MPMSimulator:
                 torch.cuda.synchronize(self.device)
                 with torch.cuda.graph(g):
                     if self._can_fuse():
-                        self._ck(self._lib.fmpm_substeps_fused(self._h, f0, self.n_substeps, self._stream()), 'fmpm_substeps_fused')
+                        self._fused_substeps(f0)
                     else:
                         for i in range(self.n_substeps):
                             self._ck(fn(self._h, f0 + i, self._stream()), 'fmpm_substep')
-                self._graphs[(s_local, store)] = g
+                self._graphs[key] = g
             except Exception:
                 self.use_graphs = False
                 return False
@@ -641,10 +651,11 @@ class MPMSimulator:
             self.cur_substep_global += self.n_substeps
         elif is_none_action and self.has_particles and self._can_fuse():
             f0 = self.cur_substep_local
-            self._ck(self._lib.fmpm_substeps_fused(self._h, f0, self.n_substeps, self._stream()), 'fmpm_substeps_fused')
+            store = self._storing()
+            self._fused_substeps(f0)
             for i in range(self.n_substeps):
                 self._frame_ord[f0 + i + 1] = self._frame_ord[f0]
-                self._ring_valid[f0 + i] = False
+                self._ring_valid[f0 + i] = store
             self.cur_substep_global += self.n_substeps
         else:
             for _ in range(self.n_substeps):

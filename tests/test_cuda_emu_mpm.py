@@ -55,16 +55,17 @@ def test_mpm_kernels_forward_and_backward_match_the_fp64_oracle(emu):
     F0 = (np.eye(3)[None] + rng.randn(N, 3, 3) * 0.05).astype(np.float32); C0 = (rng.randn(N, 3, 3) * 2.0).astype(np.float32)
     P = make_particles(x, mat, n)
     bnd = dict(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.7, 0.7, 0.7))
-    for store in (True, False):
+    w = rng.randn(N, 3).astype(np.float32)     # one seed direction for every configuration (the fp32 error depends on it, not on the path)
+    for store, fuse in ((True, False), (False, False), (True, True)):   # last: grad-mode g2p2g fusion (fmpm_substeps_fused_store)
         s = MPMSimulator(dim=3, quality=n / 64, gravity=(0, -10, 0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
-        s.use_graphs, s.store_grids = False, store
+        s.use_graphs, s.store_grids, s.fuse_g2p2g = False, store, fuse
         s.setup_boundary(**bnd)
         s.build(None, None, [], P)
         st = s.get_state(); st['v'][:] = v0; st['F'][:] = F0; st['C'][:] = C0; s.set_state(0, st)
         s.enable_grad()
+        assert s._can_fuse() == fuse
         s.step(None)
         fr = s.get_state()
-        w = rng.randn(N, 3).astype(np.float32)
         z9 = np.zeros((N, 3, 3), np.float32)
         s.reset_grad(); s.set_grad(w, np.zeros((N, 3), np.float32), z9, z9)
         s.step_grad(None)
@@ -77,7 +78,7 @@ def test_mpm_kernels_forward_and_backward_match_the_fp64_oracle(emu):
         og = o.get_grad_frame(0)
         assert rel(fr['x'], ofr['x']) < 1e-6 and rel(fr['F'], ofr['F']) < 1e-5 and rel(fr['v'], ofr['v']) < 1e-4, {k: rel(fr[k], ofr[k]) for k in 'xvCF'}
         for k in 'xvCF':
-            assert rel(g[k], og[k]) < 1e-4, (store, k, rel(g[k], og[k]))
+            assert rel(g[k], og[k]) < 1e-4, (store, fuse, k, rel(g[k], og[k]))
 
 
 def test_circulation_stack_on_the_emulated_device(emu):
