@@ -191,6 +191,7 @@ def main():
         slab = SlabMPMSimulator(q, GRAVITY, parts, gid=np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1), max_substeps_local=T, device=dev,
                                 exchange=os.environ.get('SLAB_EXCHANGE', 'peer'))
         sim = slab.sim
+        sim.fuse_g2p2g = bool(args.fuse_g2p2g)   # x-slab mode: the fused kernel's scatter half reduces frame f+1's ghost planes into the neighbour
         # the reference's fixed dt = 2e-4 is unstable for water at 256^3 beyond ~700 substeps (profiles/check_stability_256.py,
         # SURVEY.md §8d C5): restore the initial state (device-side copy, ~0.1% of the time) every 30 steps
         _cnt = [0]
@@ -463,13 +464,13 @@ def main():
             'config': {'workload': workload,
                        'substeps_per_step': SUBSTEPS_PER_STEP, 'dt': 2e-4, 'gravity': GRAVITY, 'max_substeps_local': T,
                        'cell_sort_every_steps': args.sort_every,
-                       'g2p2g_fused': bool(args.fuse_g2p2g) and world == 1,
+                       'g2p2g_fused': bool(args.fuse_g2p2g),
                        'l2_policy': 'inputs larger than L2 (one substep touches >= 212 B x 1M particles = 212 MB > 126 MB L2)',
                        'parallelism': parallelism},
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},
-            'gpu_launches': K * ((2 * SUBSTEPS_PER_STEP + 1) if (args.fuse_g2p2g and world == 1) else SUBSTEPS_PER_STEP * 3) + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
+            'gpu_launches': K * ((2 * SUBSTEPS_PER_STEP + 1) if args.fuse_g2p2g else SUBSTEPS_PER_STEP * 3) + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
             'e2e_obs_bridge': e2e_obs,
             'roofline': roof, 'roofline_p2g_g2p': roof_pair,
             'fwd_bwd': fb,

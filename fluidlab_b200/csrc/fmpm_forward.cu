@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_g2p2g(const KParam
   const long long rem = (long long)P.N - slot0;
   const int cnt = rem < 32 ? (int)rem : 32;
   Window W; window_init(W, lane, P.n, P.blk_flags);
+  window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);   // x-slab mode: like k_p2g
   // ---- g2p of frame f (MPM:304-316, 400-426, 497-505)
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (sl < P.N) a0 = P2G_LD(&P.pa[pa_idx(P, f, 0, (int)sl)]);
@@ -477,10 +478,10 @@ extern "C" int fmpm_substep_store(FmpmHandle* h, int f, void* stream) {
 // g2p(f) fused with p2g(f+1): forward-only steps without agents, MAT_RIGID bodies or slabs (see k_g2p2g)
 extern "C" int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream) {
   if (check_bound(h, "fmpm_g2p2g") || check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_g2p2g")) return 1;
-  if (h->col.has_rigid || h->bodies.n_bodies > 0 || h->slab.enabled) {
-    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: not available with a rigid effector, MAT_RIGID bodies or x-slabs"); return 1;
+  if (h->col.has_rigid || h->bodies.n_bodies > 0) {
+    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: not available with a rigid effector or MAT_RIGID bodies"); return 1;
   }
-  KParams P = make_kparams(h);
+  KParams P = make_kparams(h, -1, f + 1);   // x-slab mode: the scatter goes to the accumulator / block flags / peers of substep parity f+1
   if (P.N == 0) return 0;
   const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
   if (write_vc) FMPM_LAUNCH(k_g2p2g<true>, blocks, P2G_WARPS * 32, 0, stream, P, f);

@@ -832,6 +832,8 @@ class MPMSimulator:
         elif name == 'grid_op': rc = L.fmpm_grid_op(h, f, int(args[0]) if args else 0, s)
         elif name == 'g2p':
             rc = L.fmpm_g2p(h, f, s); self._frame_ord[f + 1] = self._frame_ord[f]
+        elif name == 'g2p2g':
+            rc = L.fmpm_g2p2g(h, f, 0, s); self._frame_ord[f + 1] = self._frame_ord[f]
         elif name == 'g2p_grad_scatter': rc = L.fmpm_g2p_grad_scatter(h, f, self._gcur, s)
         elif name == 'grid_op_grad': rc = L.fmpm_grid_op_grad(h, f, s)
         elif name == 'particle_grad':

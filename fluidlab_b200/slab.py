@@ -377,15 +377,20 @@ class SlabMPMSimulator:
         if self.world > 1 and self.migrate_enabled:
             self._migrate()
         sim.sort_frame(sim.cur_substep_local)
-        for _ in range(sim.n_substeps):
+        fuse = bool(getattr(sim, 'fuse_g2p2g', False)) and not sim.grad_enabled   # forward-only: g2p(f) + p2g(f+1) in one kernel (k_g2p2g)
+        for i in range(sim.n_substeps):
             f = sim.cur_substep_local
-            sim.phase('p2g', f, 1)
+            if not (fuse and i > 0):
+                sim.phase('p2g', f, 1)        # fused mode: the previous iteration's g2p2g already scattered frame f
             if self.exchange == 'peer':
                 self._peers.barrier()   # device-side: every rank's p2g (incl. its peer reductions and peer block flags) has completed
             elif self.exchange == 'nccl':
                 self._ghost_sum_acc(f)
             sim.phase('grid_op', f, 1)
-            sim.phase('g2p', f)
+            if fuse and i + 1 < sim.n_substeps:
+                sim.phase('g2p2g', f)
+            else:
+                sim.phase('g2p', f)
             sim.cur_substep_global += 1
         if sim.cur_substep_local == 0 and not self._replaying:   # ring wrap: frame T becomes frame 0 of the next chunk
             if sim.grad_enabled:

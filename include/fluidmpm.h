@@ -182,7 +182,8 @@ int fmpm_substep(FmpmHandle* h, int f, void* stream);                  /* p2g, g
 int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, but the grids of frame f stay in ring slot f */
 /* forward-only fusion (no reference counterpart): g2p of frame f + p2g of frame f+1 in one kernel — v, C and x stay in registers
  * between the gather and the next scatter (104 B instead of 212 B per particle and substep).  write_vc = 0: v and C of frame f+1 are not
- * materialised.  Not available with a rigid effector, MAT_RIGID bodies or x-slabs. */
+ * materialised.  Not available with a rigid effector or MAT_RIGID bodies.  x-slab mode: the scatter half behaves like fmpm_p2g(f+1)
+ * (peer reductions into the neighbours' accumulators of parity f+1): synchronise the ranks before fmpm_grid_op(f+1). */
 int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream);
 /* n substeps f0..f0+n-1: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1); frames f0 and f0+n are complete */
 int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream);

@@ -125,7 +125,7 @@ class ShmPeers:
         self.dist.barrier(group=self.group)
 
 
-def _slab_worker(rank, world, port, ret, exchange='nccl'):
+def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     torch.set_num_threads(1)
@@ -154,6 +154,22 @@ def _slab_worker(rank, world, port, ret, exchange='nccl'):
         st = slab.sim.get_state()
         st['v'][:len(mine)] = v0[mine]; st['F'][:len(mine)] = F0[mine]
         slab.sim.set_state(0, st)
+        if fused:   # forward-only: g2p(f) + p2g(f+1) fused, the scatter half reducing into the neighbour's accumulator of parity f+1
+            slab.sim.fuse_g2p2g = True
+            for _ in range(n_steps):
+                slab.step()
+            out = dict(fwd=slab.gather_state(), migrated=slab.n_migrated)
+            if rank == 0:
+                ref = MPMSimulator(dim=3, quality=0.5, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+                ref.use_graphs = False
+                ref.build(None, None, [], parts(np.arange(Ntot)))
+                s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
+                for _ in range(n_steps):
+                    ref.step(None)
+                r = ref.get_state()
+                out.update(ref_state={k: r[k] for k in ('x', 'v', 'F')})
+            ret[rank] = out
+            return
         slab.enable_grad()
         for _ in range(n_steps):
             slab.step()
@@ -310,6 +326,22 @@ def test_circulation_stack_equals_a_run_of_the_real_reference_stack(emu):
     reference's OWN MPMSimulator + AgentCirculation + AirCon + SmokeField); see tests/circulation_case.py"""
     from circulation_case import run_reference_stack_case
     run_reference_stack_case(device='cpu')
+
+
+@pytest.mark.parametrize('exchange', ['peer', 'nccl'])
+def test_slab_forward_with_g2p2g_fusion_on_the_emulated_device(exchange):
+    """x-slabs + g2p2g: the fused kernel's scatter half reduces the ghost planes of frame f+1 into the neighbour's accumulator (peer) or the
+    all-reduce follows it (nccl); 5 steps with migrations and two ring wraps against the single-domain (unfused) product"""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_slab_worker, args=(2, _free_port(), ret, exchange, True), nprocs=2, join=True)
+    out = dict(ret)
+    ref_s = out[0]['ref_state']
+    for r in (0, 1):
+        fwd = out[r]['fwd']
+        assert np.array_equal(fwd['gid'], np.arange(700)), 'particles lost or duplicated'
+        assert rel(fwd['x'], ref_s['x']) < 1e-5 and rel(fwd['F'], ref_s['F']) < 1e-5 and rel(fwd['v'], ref_s['v']) < 1e-4
+    assert out[0]['migrated'] > 0 and out[1]['migrated'] > 0
 
 
 @pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream'])
