@@ -189,7 +189,7 @@ def main():
         lo = ((bounds[rank] - 0.5) * dx, 0.30, 0.36); hi = ((bounds[rank + 1] - 0.5) * dx, 0.30 + 72 * dx, 0.36 + 72 * dx)
         parts = workload_particles(N, seed=rank, lo=lo, hi=hi)
         slab = SlabMPMSimulator(q, GRAVITY, parts, gid=np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1), max_substeps_local=T, device=dev,
-                                exchange=os.environ.get('SLAB_EXCHANGE', 'peer'))
+                                exchange=os.environ.get('SLAB_EXCHANGE', 'peer'), sync=os.environ.get('SLAB_SYNC', 'barrier'))
         sim = slab.sim
         sim.fuse_g2p2g = bool(args.fuse_g2p2g)   # x-slab mode: the fused kernel's scatter half reduces frame f+1's ghost planes into the neighbour
         # the reference's fixed dt = 2e-4 is unstable for water at 256^3 beyond ~700 substeps (profiles/check_stability_256.py,
@@ -207,8 +207,10 @@ def main():
         workload = (f'C2-weak: {N} water particles per GPU (~8/cell) as {world} x-slabs of one body, 256^3 grid, fp32, forward; value counts '
                     f'1M-particle substeps (global substeps/s = value / n_gpus)')
         if slab.exchange == 'peer':
+            sync_txt = ('one neighbour handshake per substep inside the library, the whole step in one call' if slab.sync == 'signal'
+                        else 'one device-side signal-pad barrier per substep')
             parallelism = (f'{world} x-slabs; ghost-plane reduction fused into p2g (vector REDs into the neighbour grid over NVLink peer memory, '
-                           f'parity double-buffered), one device-side signal-pad barrier per substep, no data-path collective; per-step migration')
+                           f'parity double-buffered), {sync_txt}, no data-path collective; per-step migration')
         else:
             parallelism = (f'{world} x-slabs; NCCL pair all-reduce of {slab.ghost.bytes_per_exchange()} B of ghost planes per rank per substep; per-step migration')
     init = sim.get_state()

@@ -80,7 +80,8 @@ class FmpmColliders(C.Structure):
 class FmpmSlab(C.Structure):
     _fields_ = [("enabled", C.c_int), ("peer_pm_left", vp), ("peer_pm_right", vp), ("peer_flags_left", vp), ("peer_flags_right", vp),
                 ("left_lo", C.c_int), ("left_hi", C.c_int),
-                ("right_lo", C.c_int), ("right_hi", C.c_int), ("peer_ggv_left", vp), ("peer_ggv_right", vp)]
+                ("right_lo", C.c_int), ("right_hi", C.c_int), ("peer_ggv_left", vp), ("peer_ggv_right", vp),
+                ("signal", vp), ("peer_signal_left", vp), ("peer_signal_right", vp)]
 
 
 class FmpmCollector(C.Structure):
@@ -117,6 +118,8 @@ _PROTOS = {
     "fmpm_advect_rigid_grad": (_I, [vp, _I, _I, vp, vp]),
     "fmpm_set_colliders": (_I, [vp, C.POINTER(FmpmColliders)]),
     "fmpm_set_slab": (_I, [vp, C.POINTER(FmpmSlab)]),
+    "fmpm_slab_sync": (_I, [vp, vp]),
+    "fmpm_substeps_slab": (_I, [vp, _I, _I, _I, vp]),
     "fmpm_create": (_I, [C.POINTER(FmpmConfig), C.POINTER(vp)]),
     "fmpm_destroy": (None, [vp]),
     "fmpm_bind": (_I, [vp, C.POINTER(FmpmBuffers)]),

@@ -72,6 +72,50 @@ extern "C" int fmpm_set_slab(FmpmHandle* h, const FmpmSlab* s) {
   return 0;
 }
 
+// neighbour handshake of the x-slab mode: epochs in peer-addressable memory.  A rank posts e = ++epoch into its neighbours' slots (after a
+// system-scope fence: its peer reductions of the kernels before are visible first) and waits until both neighbours posted >= e.  The spin
+// is bounded: a rank that never arrives (a crashed peer) raises the error flag instead of hanging the GPU.
+#ifdef FMPM_HOST_EMU
+#define FMPM_SYSTEM_FENCE() std::atomic_thread_fence(std::memory_order_seq_cst)
+#else
+#define FMPM_SYSTEM_FENCE() __threadfence_system()
+#endif
+#ifndef FMPM_SYNC_SPIN_LIMIT
+#define FMPM_SYNC_SPIN_LIMIT (1LL << 31)
+#endif
+__global__ void k_slab_sync(int* sig, int* peer_l, int* peer_r) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int e = sig[2] + 1;
+  sig[2] = e;
+  FMPM_SYSTEM_FENCE();
+  if (peer_l) ((volatile int*)peer_l)[1] = e;   // I am my left neighbour's RIGHT neighbour
+  if (peer_r) ((volatile int*)peer_r)[0] = e;   // and my right neighbour's LEFT neighbour
+  FMPM_SYSTEM_FENCE();
+  long long spins = 0;
+  if (peer_l) while (((volatile int*)sig)[0] < e) { if (++spins > FMPM_SYNC_SPIN_LIMIT) { sig[3] = 1; break; } }
+  if (peer_r) while (((volatile int*)sig)[1] < e) { if (++spins > FMPM_SYNC_SPIN_LIMIT) { sig[3] = 1; break; } }
+  FMPM_SYSTEM_FENCE();
+}
+extern "C" int fmpm_slab_sync(FmpmHandle* h, void* stream) {
+  if (!h) return 1;
+  if (!h->slab.enabled || !h->slab.signal) { snprintf(h->err, sizeof(h->err), "fmpm_slab_sync: the handshake arrays were not set (FmpmSlab.signal)"); return 1; }
+  FMPM_LAUNCH(k_slab_sync, 1, 32, 0, stream, (int*)h->slab.signal, (int*)h->slab.peer_signal_left, (int*)h->slab.peer_signal_right);
+  FMPM_CHECK_LAUNCH(h, "fmpm_slab_sync");
+  return 0;
+}
+extern "C" int fmpm_substeps_slab(FmpmHandle* h, int f0, int n, int fuse, void* stream) {
+  if (!h) return 1;
+  if (n < 1) { snprintf(h->err, sizeof(h->err), "fmpm_substeps_slab: n must be >= 1"); return 1; }
+  for (int i = 0; i < n; i++) {
+    const int f = f0 + i;
+    if (!(fuse && i > 0) && fmpm_p2g(h, f, 1, stream)) return 1;    // fused: the previous substep's g2p2g scattered frame f already
+    if (fmpm_slab_sync(h, stream) || fmpm_grid_op(h, f, 1, stream)) return 1;
+    if (fuse && i + 1 < n) { if (fmpm_g2p2g(h, f, 0, stream)) return 1; }
+    else if (fmpm_g2p(h, f, stream)) return 1;
+  }
+  return 0;
+}
+
 static int sort_bits(const FmpmHandle* h) {
   long long G = (long long)h->cfg.n_grid * h->cfg.n_grid * h->cfg.n_grid;  // keys in [0, G]
   int bits = 1;

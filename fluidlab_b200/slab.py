@@ -209,7 +209,7 @@ class SlabMPMSimulator:
     """Forward MLS-MPM over x-slabs: one local `MPMSimulator` per rank + ghost exchange + migration."""
 
     def __init__(self, quality, gravity, particles, gid, bounds, capacity, boundary=None, max_substeps_local=50, device=None, group=None, halo=4,
-                 exchange='peer', migrate=True, sim_factory=None, peer_factory=None):
+                 exchange='peer', migrate=True, sim_factory=None, peer_factory=None, sync='barrier'):
         from .macros import NOWHERE
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -241,6 +241,11 @@ class SlabMPMSimulator:
         self.n_migrated = 0
         self.exchange = exchange if self.world > 1 else 'none'
         self._peer_factory = peer_factory if peer_factory is not None else SymmetricMemoryPeers
+        # 'barrier': one device-side barrier over ALL ranks per substep (symmetric-memory signal pads; measured in round 1).
+        # 'signal' : a handshake with the two NEIGHBOURS only, inside the library (fmpm_slab_sync), and the whole step in one C call
+        #            (fmpm_substeps_slab) — verified on the CPU execution-model shim, not yet measured on hardware: opt-in.
+        assert sync in ('barrier', 'signal')
+        self.sync = sync if exchange == 'peer' else 'barrier'
         if self.exchange == 'peer':
             self._setup_peer(halo)
         self._census_host = None
@@ -265,6 +270,7 @@ class SlabMPMSimulator:
             buf, ptrs = peers.alloc((2, G, 4), torch.float32)
             fbuf, fptrs = peers.alloc((2, nblk), torch.int32)
             gbuf, gptrs = peers.alloc((G, 4), torch.float32)
+            sbuf, sptrs = peers.alloc((8,), torch.int32)
         except Exception as e:  # pragma: no cover - depends on the driver / fabric
             if self.rank == 0:
                 print(f'[fluidlab_b200.slab] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL ghost all-reduce')
@@ -275,14 +281,18 @@ class SlabMPMSimulator:
         sim._ggrid_v = gbuf          # kept by MPMSimulator._ensure_grad_buffers
         sim._bind()
         self._peers = peers
+        self._signal = sbuf
         slab = _lib.FmpmSlab()
         slab.enabled = 1
+        slab.signal = sbuf.data_ptr()
         lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         if self.rank > 0:
             slab.peer_pm_left = int(ptrs[self.rank - 1]); slab.peer_flags_left = int(fptrs[self.rank - 1]); slab.peer_ggv_left = int(gptrs[self.rank - 1])
+            slab.peer_signal_left = int(sptrs[self.rank - 1])
             slab.left_lo, slab.left_hi = lo - halo, lo + halo
         if self.rank < self.world - 1:
             slab.peer_pm_right = int(ptrs[self.rank + 1]); slab.peer_flags_right = int(fptrs[self.rank + 1]); slab.peer_ggv_right = int(gptrs[self.rank + 1])
+            slab.peer_signal_right = int(sptrs[self.rank + 1])
             slab.right_lo, slab.right_hi = hi - halo, hi + halo
         sim._ck(sim._lib.fmpm_set_slab(sim._h, C.byref(slab)), 'fmpm_set_slab')
         if sim.device.type == 'cuda':
@@ -378,12 +388,20 @@ class SlabMPMSimulator:
             self._migrate()
         sim.sort_frame(sim.cur_substep_local)
         fuse = bool(getattr(sim, 'fuse_g2p2g', False)) and not sim.grad_enabled   # forward-only: g2p(f) + p2g(f+1) in one kernel (k_g2p2g)
+        if self.exchange == 'peer' and self.sync == 'signal':   # the whole step in one library call, neighbour handshakes between the phases
+            f0 = sim.cur_substep_local
+            sim._ck(sim._lib.fmpm_substeps_slab(sim._h, f0, sim.n_substeps, int(fuse), sim._stream()), 'fmpm_substeps_slab')
+            for i in range(sim.n_substeps):
+                sim._frame_ord[f0 + i + 1] = sim._frame_ord[f0]
+            sim.cur_substep_global += sim.n_substeps
+            self._wrap_if_needed()
+            return
         for i in range(sim.n_substeps):
             f = sim.cur_substep_local
             if not (fuse and i > 0):
                 sim.phase('p2g', f, 1)        # fused mode: the previous iteration's g2p2g already scattered frame f
             if self.exchange == 'peer':
-                self._peers.barrier()   # device-side: every rank's p2g (incl. its peer reductions and peer block flags) has completed
+                self._sync_ranks()   # device-side: every rank's p2g (incl. its peer reductions and peer block flags) has completed
             elif self.exchange == 'nccl':
                 self._ghost_sum_acc(f)
             sim.phase('grid_op', f, 1)
@@ -392,11 +410,25 @@ class SlabMPMSimulator:
             else:
                 sim.phase('g2p', f)
             sim.cur_substep_global += 1
+        self._wrap_if_needed()
+
+    def _wrap_if_needed(self):
+        sim = self.sim
         if sim.cur_substep_local == 0 and not self._replaying:   # ring wrap: frame T becomes frame 0 of the next chunk
             if sim.grad_enabled:
                 sim.copy_frame(sim.max_substeps_local, 0)
             else:
                 sim.memory_to_cache()
+
+    def sync_error(self):
+        """True if a neighbour handshake ever gave up waiting (a peer rank stopped): host-synchronising, for tests / diagnostics"""
+        return self.exchange == 'peer' and int(self._signal[3]) != 0
+
+    def _sync_ranks(self):
+        if self.sync == 'signal':
+            self.sim._ck(self.sim._lib.fmpm_slab_sync(self.sim._h, self.sim._stream()), 'fmpm_slab_sync')
+        else:
+            self._peers.barrier()
 
     def _ghost_sum_acc(self, f):
         sim = self.sim
@@ -427,12 +459,12 @@ class SlabMPMSimulator:
         sim = self.sim
         sim.slab_substep_grad_p2g(f)
         if self.exchange == 'peer':
-            self._peers.barrier()
+            self._sync_ranks()
         elif self.exchange == 'nccl':
             self._ghost_sum_acc(f)
         sim.slab_substep_grad_scatter(f)
         if self.exchange == 'peer':
-            self._peers.barrier()   # every rank's g2p.grad scatter, incl. its reductions into the neighbours' v_out adjoint, has completed
+            self._sync_ranks()   # every rank's g2p.grad scatter, incl. its reductions into the neighbours' v_out adjoint, has completed
         elif self.world > 1:        # complete the v_out adjoint on the planes shared with the neighbours
             adj = sim.slab_grid_adj(f)
             self.ghost.exchange_sum(adj)

@@ -148,8 +148,17 @@ typedef struct {
    * neighbours' ggrid_v (float4[G], single-buffered).  g2p.grad's scatter then adds every contribution on a shared plane to the
    * neighbour's v_out adjoint as well, and grid_op.grad zeroes what it consumed, so the buffer is all-zero between substeps. */
   void* peer_ggv_left; void* peer_ggv_right;
+  /* neighbour handshake (optional; NULL = the caller synchronises the ranks itself, e.g. with a symmetric-memory barrier): `signal` is this
+   * rank's int[8] in peer-addressable memory — [0] last epoch posted by the left neighbour, [1] by the right one, [2] this rank's epoch
+   * counter (device side), [3] error flag (a wait gave up) — peer_signal_* the neighbours' arrays.  fmpm_slab_sync posts this rank's next
+   * epoch to both neighbours and waits for theirs: a slab only exchanges with its two neighbours, so no global barrier is needed. */
+  void* signal; void* peer_signal_left; void* peer_signal_right;
 } FmpmSlab;
 int  fmpm_set_slab(FmpmHandle* h, const FmpmSlab* s);
+int  fmpm_slab_sync(FmpmHandle* h, void* stream);     /* one tiny kernel: post epoch to the neighbours, spin (bounded) until theirs arrived */
+/* the forward substeps f0..f0+n-1 of one x-slab rank in ONE call (no host round trip per phase; CUDA-graph capturable): per substep
+ * p2g (or, with fuse != 0, the previous substep's g2p2g) -> fmpm_slab_sync -> grid_op -> g2p / g2p2g.  Needs the handshake arrays. */
+int  fmpm_substeps_slab(FmpmHandle* h, int f0, int n, int fuse, void* stream);
 
 /* MAT_RIGID bodies: rigidity enforcement by shape matching (MPM:177-201 body structs, MPM:428-505 advect).
  * The body id of a particle travels in bits 16..23 of its meta word: pass mrow[p] = material_row | (body_id << 8) to

@@ -40,7 +40,7 @@ def main():
         return dict(x=x[idx], mat=mat[idx], used=np.ones(len(idx), np.int32), rho=np.array([M.RHO[m] for m in mat[idx]]), body_id=np.zeros(len(idx), np.int32), bodies={'n': 1})
     exchange = os.environ.get('SLAB_EXCHANGE', 'peer')
     slab = SlabMPMSimulator(q, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=int(len(mine) * 1.5) + 1000, max_substeps_local=20, device=dev,
-                            exchange=exchange)
+                            exchange=exchange, sync=os.environ.get('SLAB_SYNC', 'barrier'))
     st = slab.sim.get_state()
     st['v'][:len(mine)] = v0[mine]
     slab.sim.set_state(0, st)

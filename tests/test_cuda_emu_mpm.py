@@ -125,7 +125,7 @@ class ShmPeers:
         self.dist.barrier(group=self.group)
 
 
-def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False):
+def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='barrier'):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     torch.set_num_threads(1)
@@ -148,8 +148,8 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False):
         def parts(idx):
             return dict(x=x[idx], mat=mat[idx], used=np.ones(len(idx), np.int32), rho=np.array([M.RHO[m] for m in mat[idx]]), body_id=np.zeros(len(idx), np.int32), bodies={'n': 1})
         slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=len(mine) + 300, max_substeps_local=20, device='cpu', halo=4,
-                                exchange=exchange, peer_factory=ShmPeers)
-        assert slab.exchange == exchange
+                                exchange=exchange, peer_factory=ShmPeers, sync=sync)
+        assert slab.exchange == exchange and (slab.sync == sync or exchange != 'peer')
         slab.sim.use_graphs = False
         st = slab.sim.get_state()
         st['v'][:len(mine)] = v0[mine]; st['F'][:len(mine)] = F0[mine]
@@ -159,6 +159,7 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False):
             for _ in range(n_steps):
                 slab.step()
             out = dict(fwd=slab.gather_state(), migrated=slab.n_migrated)
+            assert not slab.sync_error()
             if rank == 0:
                 ref = MPMSimulator(dim=3, quality=0.5, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
                 ref.use_graphs = False
@@ -181,6 +182,7 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False):
         for _ in range(n_steps):
             slab.step_grad()
         grad = slab.gather_grad()
+        assert not slab.sync_error()
         out = dict(fwd=fwd, grad=grad, migrated=slab.n_migrated, rec=sorted(slab._records))
         if rank == 0:   # the single-domain reference: the same product on the same emulated device
             ref = MPMSimulator(dim=3, quality=0.5, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
@@ -202,7 +204,7 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('exchange', ['nccl', 'peer'])
+@pytest.mark.parametrize('exchange', ['nccl', 'peer', 'peer-signal'])
 def test_slab_sharded_forward_and_backward_match_the_single_domain_run_on_the_emulated_device(exchange):
     """the CUDA leg of the x-slab path that tests/run_slab_gpu.py exercises on 2 GPUs, here on 2 gloo ranks with the emulated device:
     SlabMPMSimulator.step (ghost all-reduce of the accumulator, migration) and step_grad (fmpm_p2g(write_F=0) -> ghost sum ->
@@ -213,7 +215,8 @@ def test_slab_sharded_forward_and_backward_match_the_single_domain_run_on_the_em
     neighbour's grids (here: POSIX shared memory across the two rank processes instead of NVLink peer memory), no all-reduce anywhere."""
     import torch.multiprocessing as mp
     mgr = mp.Manager(); ret = mgr.dict()
-    mp.spawn(_slab_worker, args=(2, _free_port(), ret, exchange), nprocs=2, join=True)
+    sync = 'signal' if exchange.endswith('-signal') else 'barrier'   # 'signal': neighbour handshakes inside the library instead of a barrier over all ranks
+    mp.spawn(_slab_worker, args=(2, _free_port(), ret, exchange.split('-')[0], False, sync), nprocs=2, join=True)
     out = dict(ret)
     N = 700
     ref_s, ref_g = out[0]['ref_state'], out[0]['ref_grad']
@@ -328,13 +331,14 @@ def test_circulation_stack_equals_a_run_of_the_real_reference_stack(emu):
     run_reference_stack_case(device='cpu')
 
 
-@pytest.mark.parametrize('exchange', ['peer', 'nccl'])
+@pytest.mark.parametrize('exchange', ['peer', 'nccl', 'peer-signal'])
 def test_slab_forward_with_g2p2g_fusion_on_the_emulated_device(exchange):
     """x-slabs + g2p2g: the fused kernel's scatter half reduces the ghost planes of frame f+1 into the neighbour's accumulator (peer) or the
     all-reduce follows it (nccl); 5 steps with migrations and two ring wraps against the single-domain (unfused) product"""
     import torch.multiprocessing as mp
     mgr = mp.Manager(); ret = mgr.dict()
-    mp.spawn(_slab_worker, args=(2, _free_port(), ret, exchange, True), nprocs=2, join=True)
+    sync = 'signal' if exchange.endswith('-signal') else 'barrier'   # 'signal': the whole step is ONE library call (fmpm_substeps_slab)
+    mp.spawn(_slab_worker, args=(2, _free_port(), ret, exchange.split('-')[0], True, sync), nprocs=2, join=True)
     out = dict(ret)
     ref_s = out[0]['ref_state']
     for r in (0, 1):
