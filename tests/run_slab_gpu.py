@@ -41,6 +41,7 @@ def main():
     exchange = os.environ.get('SLAB_EXCHANGE', 'peer')
     slab = SlabMPMSimulator(q, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=int(len(mine) * 1.5) + 1000, max_substeps_local=20, device=dev,
                             exchange=exchange, sync=os.environ.get('SLAB_SYNC', 'barrier'))
+    slab.sim.fuse_g2p2g = bool(int(os.environ.get('SLAB_FUSE', '0')))   # forward mode only: g2p(f) + p2g(f+1) fused
     st = slab.sim.get_state()
     st['v'][:len(mine)] = v0[mine]
     slab.sim.set_state(0, st)
@@ -65,7 +66,7 @@ def main():
         rel = lambda a, b: float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
         assert len(got['gid']) == Ntot and np.array_equal(got['gid'], np.arange(Ntot)), 'particles lost or duplicated'
         ex, ev, eF = rel(got['x'], r['x']), rel(got['v'], r['v']), rel(got['F'], r['F'])
-        print(f'slab world={world} exchange={exchange}: migrated={int(migrated.item())} rel err x={ex:.2e} v={ev:.2e} F={eF:.2e}')
+        print(f'slab world={world} exchange={exchange} sync={slab.sync} fused={slab.sim.fuse_g2p2g}: migrated={int(migrated.item())} rel err x={ex:.2e} v={ev:.2e} F={eF:.2e}')
         ok = ex < 1e-5 and eF < 1e-5 and ev < 1e-4 and int(migrated.item()) > 0
         print('SLAB_PARITY_OK' if ok else 'SLAB_PARITY_FAIL')
     dist.barrier()

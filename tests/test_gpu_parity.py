@@ -1000,3 +1000,19 @@ def test_cuda_adjoint_equals_finite_differences_through_the_reference_forward():
     _need_gpu()
     import reference_scene_cases as cases
     cases.run_cloud_adjoint_case(device=None)
+
+
+@pytest.mark.parametrize('fuse', ['0', '1'])
+def test_slab_sharded_forward_with_neighbour_handshake(fuse):
+    """2 ranks: x-slab forward with sync='signal' (neighbour handshake inside the library, the whole step in one call) and optionally the
+    g2p2g fusion == the single-GPU result (tests/run_slab_gpu.py with SLAB_SYNC=signal, SLAB_FUSE); verified on the CPU execution-model shim,
+    first hardware run pending; needs 2 GPUs"""
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SLAB_SYNC='signal', SLAB_FUSE=fuse)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29551', os.path.join(root, 'tests', 'run_slab_gpu.py')], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and 'SLAB_PARITY_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
