@@ -358,3 +358,21 @@ def test_agent_scenes_equal_runs_of_the_real_reference_agents(emu, scene):
 def test_device_adjoint_equals_finite_differences_through_the_reference_forward(emu):
     import reference_scene_cases as cases
     cases.run_cloud_adjoint_case(device='cpu')
+
+
+def test_multi_rank_bench_arm_runs_on_the_emulated_device():
+    """bench.py --gpus 2 (x-slabs, peer ghost reduction over shared memory standing in for NVLink, neighbour-handshake sync, g2p2g fusion, per-kernel
+    timing section with its cross-rank clear, e2e episodes with migration) as two gloo ranks on the shim: the SCRIPT must finish and print the line"""
+    import json
+    import subprocess
+    port = _free_port()
+    procs = []
+    for r in (0, 1):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), SLAB_SYNC='signal')
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, 'cuda_emu', 'run_bench_emu.py'), '--gpus', '2', '--particles', '3000', '--steps', '2', '--warmup', '1',
+                                       '--no-cpu', '--bwd', '0', '--fuse-g2p2g', '1'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
+    outs = [p.communicate(timeout=900) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs[0][1][-2000:] + outs[1][1][-2000:]
+    line = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert line['n_gpus'] == 2 and line['value'] > 0 and line['e2e']['value'] > 0 and line['config']['g2p2g_fused'] is True
+    assert 'neighbour handshake' in line['config']['parallelism'] and outs[1][0].strip() == ''
