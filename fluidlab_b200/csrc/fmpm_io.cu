@@ -74,15 +74,25 @@ extern "C" int fmpm_set_slab(FmpmHandle* h, const FmpmSlab* s) {
 
 // neighbour handshake of the x-slab mode: epochs in peer-addressable memory.  A rank posts e = ++epoch into its neighbours' slots (after a
 // system-scope fence: its peer reductions of the kernels before are visible first) and waits until both neighbours posted >= e.  The spin
-// is bounded: a rank that never arrives (a crashed peer) raises the error flag instead of hanging the GPU.
+// is bounded IN TIME (globaltimer): a rank that never arrives (a crashed peer) raises the error flag instead of hanging the GPU.
 #ifdef FMPM_HOST_EMU
+#include <chrono>
 #define FMPM_SYSTEM_FENCE() std::atomic_thread_fence(std::memory_order_seq_cst)
+static inline unsigned long long fmpm_now_ns() { return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #else
 #define FMPM_SYSTEM_FENCE() __threadfence_system()
+__device__ __forceinline__ unsigned long long fmpm_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
-#ifndef FMPM_SYNC_SPIN_LIMIT
-#define FMPM_SYNC_SPIN_LIMIT (1LL << 31)
+#ifndef FMPM_SYNC_TIMEOUT_NS
+#define FMPM_SYNC_TIMEOUT_NS 10000000000ULL   // 10 s: ranks enter a step together (the migration census is a collective), real skews are microseconds
 #endif
+__device__ __forceinline__ void slab_wait(volatile int* slot, const int e, int* err) {
+  if (*slot >= e) return;
+  const unsigned long long t0 = fmpm_now_ns();
+  while (*slot < e) {
+    if (fmpm_now_ns() - t0 > FMPM_SYNC_TIMEOUT_NS) { *err = 1; return; }   // never hang the GPU on a peer that stopped
+  }
+}
 __global__ void k_slab_sync(int* sig, int* peer_l, int* peer_r) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int e = sig[2] + 1;
@@ -91,9 +101,8 @@ __global__ void k_slab_sync(int* sig, int* peer_l, int* peer_r) {
   if (peer_l) ((volatile int*)peer_l)[1] = e;   // I am my left neighbour's RIGHT neighbour
   if (peer_r) ((volatile int*)peer_r)[0] = e;   // and my right neighbour's LEFT neighbour
   FMPM_SYSTEM_FENCE();
-  long long spins = 0;
-  if (peer_l) while (((volatile int*)sig)[0] < e) { if (++spins > FMPM_SYNC_SPIN_LIMIT) { sig[3] = 1; break; } }
-  if (peer_r) while (((volatile int*)sig)[1] < e) { if (++spins > FMPM_SYNC_SPIN_LIMIT) { sig[3] = 1; break; } }
+  if (peer_l) slab_wait((volatile int*)sig + 0, e, sig + 3);
+  if (peer_r) slab_wait((volatile int*)sig + 1, e, sig + 3);
   FMPM_SYSTEM_FENCE();
 }
 extern "C" int fmpm_slab_sync(FmpmHandle* h, void* stream) {
