@@ -376,3 +376,41 @@ def test_multi_rank_bench_arm_runs_on_the_emulated_device():
     line = json.loads(outs[0][0].strip().splitlines()[-1])
     assert line['n_gpus'] == 2 and line['value'] > 0 and line['e2e']['value'] > 0 and line['config']['g2p2g_fused'] is True
     assert 'neighbour handshake' in line['config']['parallelism'] and outs[1][0].strip() == ''
+
+
+def test_neighbour_handshake_gives_up_instead_of_hanging_when_a_peer_never_arrives():
+    """k_slab_sync with a neighbour that never posts its epoch: the wait must end by itself and raise the error word (on hardware a spinning
+    kernel that never ends would take the GPU down with it).  Built with a 0.2 s timeout instead of the product's 10 s."""
+    import ctypes as C
+    import subprocess
+    import time
+    from fluidlab_b200 import _lib
+    out = os.path.join(harness.EMU_DIR, '_build', 'libfluidmpm_emu_timeout.so')
+    src = os.path.join(harness.CSRC, 'fmpm_io.cu')
+    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+        subprocess.check_call(['/usr/bin/g++', '-std=c++20', '-O1', '-fPIC', '-shared', '-pthread', '-x', 'c++', '-I', harness.EMU_DIR, '-DFMPM_BUILD',
+                               '-DFMPM_SYNC_TIMEOUT_NS=200000000ULL'] + [os.path.join(harness.CSRC, s) for s in harness.SRCS] + ['-o', out])
+    L = C.CDLL(out)
+    for name, (res, args) in _lib._PROTOS.items():
+        fn = getattr(L, name); fn.restype = res; fn.argtypes = args
+    cfg = _lib.FmpmConfig()
+    cfg.n_grid, cfg.n_particles, cfg.max_substeps_local, cfg.n_substeps, cfg.n_materials = 16, 0, 10, 10, 1
+    h = C.c_void_p()
+    assert L.fmpm_create(C.byref(cfg), C.byref(h)) == 0
+    mine, silent_peer = np.zeros(8, np.int32), np.zeros(8, np.int32)
+    slab = _lib.FmpmSlab()
+    slab.enabled, slab.signal, slab.peer_signal_right = 1, mine.ctypes.data, silent_peer.ctypes.data
+    slab.right_lo, slab.right_hi = 4, 12
+    assert L.fmpm_set_slab(h, C.byref(slab)) == 0
+    t0 = time.perf_counter()
+    assert L.fmpm_slab_sync(h, None) == 0
+    dt = time.perf_counter() - t0
+    assert 0.15 < dt < 5.0, dt
+    assert mine[2] == 1 and silent_peer[0] == 1, 'the epoch must have been posted to the neighbour'
+    assert mine[3] == 1, 'the error word must be raised'
+    # and with a peer that has arrived the call returns at once without raising it
+    mine[3] = 0; mine[1] = 2
+    t0 = time.perf_counter()
+    assert L.fmpm_slab_sync(h, None) == 0
+    assert time.perf_counter() - t0 < 0.1 and mine[3] == 0 and mine[2] == 2
+    L.fmpm_destroy(h)
