@@ -138,6 +138,7 @@ _PROTOS = {
     "fmpm_substep_grad_stored": (_I, [vp, _I, _I, _I, vp]),
     "fmpm_substep_grad_scatter": (_I, [vp, _I, _I, vp]),
     "fmpm_substep_grad_finish": (_I, [vp, _I, _I, _I, vp]),
+    "fmpm_substep_grad_slab": (_I, [vp, _I, _I, _I, vp]),
     "fmpm_inject": (_I, [vp, _I, C.POINTER(FmpmInjector), C.POINTER(FmpmEffector), _I, _I, vp, vp]),
     "fmpm_substep_grad": (_I, [vp, _I, _I, _I, vp]),
     "fmpm_g2p_grad_scatter": (_I, [vp, _I, _I, vp]),

@@ -514,6 +514,17 @@ extern "C" int fmpm_substep_grad_finish(FmpmHandle* h, int f, int gin, int gout,
   if (grid_op_grad_impl(h, f, 1, -1, stream, fused)) return 1;
   return fmpm_particle_grad(h, f, gin, gout, stream);
 }
+int fmpm_slab_sync_impl(FmpmHandle* h, void* stream);   // fmpm_io.cu
+// one backward substep of an x-slab rank in ONE call (peer exchange + neighbour handshakes): recompute scatter, handshake, grid_op +
+// adjoint scatter (reducing into the neighbours' adjoint grids), handshake, grid_op.grad + particle side
+extern "C" int fmpm_substep_grad_slab(FmpmHandle* h, int f, int gin, int gout, void* stream) {
+  if (check_bound_b(h, "fmpm_substep_grad_slab")) return 1;
+  if (!h->slab.enabled || !h->slab.signal || !(h->slab.peer_ggv_left || h->slab.peer_ggv_right)) {
+    snprintf(h->err, sizeof(h->err), "fmpm_substep_grad_slab: needs the x-slab peer pointers of the adjoint grid and the handshake arrays"); return 1;
+  }
+  if (fmpm_p2g(h, f, 0, stream) || fmpm_slab_sync_impl(h, stream) || fmpm_substep_grad_scatter(h, f, gin, stream) || fmpm_slab_sync_impl(h, stream)) return 1;
+  return fmpm_substep_grad_finish(h, f, gin, gout, stream);
+}
 extern "C" int fmpm_inject_grad(FmpmHandle* h, int f, int gin, const FmpmInjector* inj, const FmpmEffector* e, int act_id,
                                 const void* inv, void* stream) {
   if (check_bound_b(h, "fmpm_inject_grad")) return 1;

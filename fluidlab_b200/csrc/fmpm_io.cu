@@ -105,7 +105,9 @@ __global__ void k_slab_sync(int* sig, int* peer_l, int* peer_r) {
   if (peer_r) slab_wait((volatile int*)sig + 1, e, sig + 3);
   FMPM_SYSTEM_FENCE();
 }
-extern "C" int fmpm_slab_sync(FmpmHandle* h, void* stream) {
+int fmpm_slab_sync_impl(FmpmHandle* h, void* stream);
+extern "C" int fmpm_slab_sync(FmpmHandle* h, void* stream) { return fmpm_slab_sync_impl(h, stream); }
+int fmpm_slab_sync_impl(FmpmHandle* h, void* stream) {
   if (!h) return 1;
   if (!h->slab.enabled || !h->slab.signal) { snprintf(h->err, sizeof(h->err), "fmpm_slab_sync: the handshake arrays were not set (FmpmSlab.signal)"); return 1; }
   FMPM_LAUNCH(k_slab_sync, 1, 32, 0, stream, (int*)h->slab.signal, (int*)h->slab.peer_signal_left, (int*)h->slab.peer_signal_right);

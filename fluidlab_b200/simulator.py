@@ -793,6 +793,13 @@ class MPMSimulator:
         self._ck(self._lib.fmpm_substep_grad_finish(self._h, f, gin, gout, self._stream()), 'fmpm_substep_grad_finish')
         self._gcur = gout
 
+    def slab_substep_grad_one_call(self, f):
+        """parts 1-3 with the neighbour handshakes in between, one library call (peer exchange + sync='signal')"""
+        self._ensure_grad_order(self._frame_ord[f])
+        gin, gout = self._gcur, 1 - self._gcur
+        self._ck(self._lib.fmpm_substep_grad_slab(self._h, f, gin, gout, self._stream()), 'fmpm_substep_grad_slab')
+        self._gcur = gout
+
     def read_grad_torch(self):
         """current adjoint frame in original particle order: dict of fresh device tensors x,v (N,3), C,F (N,3,3)."""
         N, dev, f32 = self.n_particles, self.device, torch.float32

@@ -457,6 +457,9 @@ class SlabMPMSimulator:
 
     def _substep_grad(self, f):
         sim = self.sim
+        if self.exchange == 'peer' and self.sync == 'signal':
+            sim.slab_substep_grad_one_call(f)
+            return
         sim.slab_substep_grad_p2g(f)
         if self.exchange == 'peer':
             self._sync_ranks()

@@ -224,6 +224,8 @@ int fmpm_substep_grad_stored(FmpmHandle* h, int f, int gin, int gout, void* stre
  *                  -> [ghost sum of the v_out-adjoint planes]    -> fmpm_substep_grad_finish  (grid_op.grad, accumulators cleared, particle side) */
 int fmpm_substep_grad_scatter(FmpmHandle* h, int f, int gin, void* stream);
 int fmpm_substep_grad_finish(FmpmHandle* h, int f, int gin, int gout, void* stream);
+/* the three steps above with the two neighbour handshakes (fmpm_slab_sync) in between, in one call; needs FmpmSlab.peer_ggv_* and .signal */
+int fmpm_substep_grad_slab(FmpmHandle* h, int f, int gin, int gout, void* stream);
 /* MPM:436-447 advect_grad for MAT_RIGID bodies: call BEFORE fmpm_substep_grad* / fmpm_g2p_grad_scatter of the same f (it rewrites
  * the x and v adjoints of rigid particles in gin in place; no-op without such bodies).  next_slot: int[N], slot in frame f+1 of the
  * particle in slot s of frame f, or NULL when both frames share one slot order (no cell sort between them). */
