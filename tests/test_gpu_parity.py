@@ -968,7 +968,7 @@ def test_cuda_matches_runs_of_the_real_reference_kernels(scene):
     assert np.array_equal(fr['x'][~u], d['ref_x'][~u])
 
 
-@pytest.mark.parametrize('exchange', ['peer', 'nccl'])
+@pytest.mark.parametrize('exchange', ['peer', 'nccl', 'peer-signal'])
 def test_slab_sharded_backward_matches_single_gpu(exchange):
     """2 ranks (nccl): SlabMPMSimulator.step_grad (ghost sums of the accumulator and of the v_out adjoint, migrate_grad) == the single-GPU
     gradient (tests/run_slab_gpu.py, SLAB_MODE=backward).  The same orchestration is checked on CPU against the oracle in
@@ -978,7 +978,7 @@ def test_slab_sharded_backward_matches_single_gpu(exchange):
         pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SLAB_MODE='backward', SLAB_EXCHANGE=exchange)
+    env = dict(os.environ, SLAB_MODE='backward', SLAB_EXCHANGE=exchange.split('-')[0], SLAB_SYNC='signal' if exchange.endswith('-signal') else 'barrier')
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                         '--master-port', '29547', os.path.join(root, 'tests', 'run_slab_gpu.py')], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and 'SLAB_GRAD_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
