@@ -66,3 +66,20 @@ for s_ in range(3): sf.step(s_,10*s_)
 sf.reset_grad(); sf._ensure_grad_buffers(); sf._gv[3].normal_(); sf._gq[3].normal_(); sf._gp[3].normal_()
 for s_ in (2,1,0): sf.step_grad(s_,10*s_)
 print('smoke ok', flush=True)
+
+# agent scenes (injectors, collectors, 6-DOF rigid SDF collider at grid + particle level, static collider, plastic material) and the
+# adjoint kernels on a multi-material cloud
+import reference_scene_cases as cases
+for name in ('latteart', 'jetbot', 'pouring', 'icecream'):
+    getattr(cases, f'run_{name}_case')(device='cpu')
+    print('scene ok', name, flush=True)
+cases.run_cloud_adjoint_case(device='cpu')
+print('cloud adjoint ok', flush=True)
+# grad-mode fused forward + backward
+s = MPMSimulator(dim=3, quality=n / 64, gravity=(0, -10, 0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+s.use_graphs = False; s.fuse_g2p2g = True
+s.setup_boundary(type='cube', lower=(0.3, 0.3, 0.3), upper=(0.7, 0.7, 0.7)); s.build(None, None, [], P)
+s.enable_grad(); s.step(None)
+s.reset_grad(); z9 = np.zeros((N, 3, 3), np.float32); s.set_grad(rng.randn(N, 3).astype(np.float32), np.zeros((N, 3), np.float32), z9, z9)
+s.step_grad(None)
+print('grad-mode fused ok', flush=True)
