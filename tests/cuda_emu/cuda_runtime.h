@@ -160,9 +160,17 @@ inline void run_block(Worker& wk, uint3 bid, dim3 block, dim3 grid, size_t smem,
     makecontext(&f.ctx, (void (*)())fiber_main, 0);
 #endif
   }
+  // Fibers only switch at barriers / warp collectives, so within a segment the threads of a block run one after the other in scheduler
+  // order.  CUEMU_SCHED=reverse (or =shuffle) changes that order: a kernel that is missing a __syncthreads / __syncwarp between a shared-memory
+  // write and another thread's read gives different results under different orders — the poor man's `compute-sanitizer --tool racecheck`.
+  static const int sched_mode = [] { const char* e = getenv("CUEMU_SCHED"); return !e ? 0 : (e[0] == 'r' ? 1 : 2); }();
+  std::vector<int> order(nt);
+  for (int t = 0; t < nt; t++) order[t] = sched_mode == 1 ? nt - 1 - t : t;
+  if (sched_mode == 2) { unsigned sd = 12345u + bid.x * 7919u + bid.y * 104729u; for (int t = nt - 1; t > 0; t--) { sd = sd * 1664525u + 1013904223u; std::swap(order[t], order[(sd >> 8) % (t + 1)]); } }
   for (;;) {
     bool progressed = false, all_done = true;
-    for (int t = 0; t < nt; t++) {
+    for (int oi = 0; oi < nt; oi++) {
+      const int t = order[oi];
 #ifdef CUEMU_FAST_SWITCH
       if (R.fib[t].state == RUN) { R.cur = t; cuemu_switch(&R.sched, R.fib[t].sp); progressed = true; }
 #else

