@@ -261,8 +261,11 @@ __global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const i
 // The scatter's warp-local key ranking (fmpm_scatter.cuh) absorbs the mismatch between the slot order (cells of the last sort)
 // and the cells of x[f+1].
 // =============================================================================================
+#ifndef G2P2G_MINB
+#define G2P2G_MINB P2G_MINB   // 96 registers at 5 CTAs of 4 warps; A/B other bounds with FMPM_DEFS=-DG2P2G_MINB=... (profiles/ab_variants.sh, PT_FUSED=1)
+#endif
 template <bool kWriteVC>
-__global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_g2p2g(const KParams P, const int f) {
+__global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KParams P, const int f) {
   __shared__ ScatterSmem smem[P2G_WARPS];
   static_assert(sizeof(((ScatterSmem*)0)->rec) >= 9 * G2P_ZMAX * sizeof(float4), "the gather tile is staged in the scatter records' storage");
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

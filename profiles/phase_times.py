@@ -62,6 +62,21 @@ if os.environ.get('PT_BWD'):
                 ts.append(e0.elapsed_time(e1) * 1e3)
         out[name] = float(np.median(ts))
     s.disable_grad()
+# the fused g2p(f) + p2g(f+1) kernel in isolation (PT_FUSED=1): grid_v of frame f in place, accumulator clear
+if os.environ.get('PT_FUSED'):
+    ts = []
+    for it in range(REP + 3):
+        s.phase('clear_grid', f); s.phase('p2g', f, 0); s.phase('grid_op', f, 1)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        s.phase('g2p2g', f)
+        e1.record(); torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        s.phase('grid_op', f + 1, 1)
+    out['g2p2g'] = float(np.median(ts))
+    s.fuse_g2p2g = True     # and the whole-step figure below takes the fused path
 # whole steps through the CUDA-graph path
 for _ in range(4):
     s.step(None)
