@@ -74,3 +74,13 @@ def test_product_never_imports_oracle():
             if fn.endswith(('.py', '.cu', '.cuh')):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src and 'liboracle' not in src, fn
+                # nor the CPU execution-model shim of tests/cuda_emu (test infrastructure: the product only ever loads the nvcc-built library)
+                assert 'import harness' not in src and 'libfluidmpm_emu' not in src and 'cuda_emu/harness' not in src, fn
+
+
+def test_product_library_path_is_the_nvcc_build_and_nothing_else_is_loaded_by_default():
+    from fluidlab_b200 import _lib
+    assert os.path.basename(_lib.LIB_PATH) == 'libfluidmpm.so' or 'FMPM_LIB' in os.environ
+    import subprocess
+    sym = subprocess.run(['nm', '-D', os.path.join(ROOT, 'fluidlab_b200', 'libfluidmpm.so')], capture_output=True, text=True).stdout
+    assert 'cuemu' not in sym, 'the shipped library must be the nvcc build (no host-emulation symbols)'
