@@ -348,6 +348,39 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
   window_flush_all(W, P.grid_pm);
 }
 
+// p2g of the few particles an injector has just activated in frame f (fused steps with an injector agent: the g2p2g kernel of the previous
+// substep ran before agent.act wrote them, so their contribution to the grid of frame f is added here — flux particles, plain vector
+// reductions, no window).  Same arithmetic as k_p2g for one particle; also writes F[f+1] and flags the touched blocks.
+__global__ void k_p2g_injected(const KParams P, const int f, const FmpmInjector inj, const int act_id, const int* __restrict__ inv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= inj.flux) return;
+  const int pid = ((const int*)inj.act_range)[act_id + i];
+  const int s = inv ? inv[pid] : pid;
+  PRaw R; p2g_load_raw(P, f, s, R);
+  PState st; p2g_unpack(R, st);
+  int b[3]; float fx[3];
+  if (!((st.meta & 1) && base_fx(P, st.x, b, fx))) { p2g_store_F(P, f + 1, s, st.F); return; }
+  const float4 mt = __ldg(P.mats + ((st.meta >> 8) & 0xff));
+  Constit K; constitutive(P, st, mt.x, mt.y, mt.z, __float_as_int(mt.w), K);
+  const float m = mt.z;
+  float w[3][3]; bspline(fx, w);
+  float B[9], q[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) B[k] = K.A.m[k] * P.dx;
+#pragma unroll
+  for (int k = 0; k < 3; k++) q[k] = m * st.v[k] - (B[k * 3] * fx[0] + B[k * 3 + 1] * fx[1] + B[k * 3 + 2] * fx[2]);
+  const int n = P.n, nb = P.nb;
+  for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) for (int c = 0; c < 3; c++) {
+    const float wt = w[a][0] * w[bb][1] * w[c][2];
+    const int gi = b[0] + a, gj = b[1] + bb, gk = b[2] + c;
+    const float4 v = make_float4(wt * (q[0] + B[0] * a + B[1] * bb + B[2] * c), wt * (q[1] + B[3] * a + B[4] * bb + B[5] * c),
+                                 wt * (q[2] + B[6] * a + B[7] * bb + B[8] * c), wt * m);
+    red_add_v4(P.grid_pm + (gi * n + gj) * n + gk, v);
+    P.blk_flags[((gi >> 3) * nb + (gj >> 3)) * nb + (gk >> 3)] = 1;
+  }
+  p2g_store_F(P, f + 1, s, K.Fn);
+}
+
 // =============================================================================================
 // injector act (agents/agent_injector.py:30-32 -> effectors/injector.py:80-105, 240-256)
 // =============================================================================================
@@ -507,6 +540,21 @@ static int g2p2g_store_impl(FmpmHandle* h, int f, void* stream) {
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p2g(store)");
   return 0;
 }
+// store-mode pieces for fused steps with an injector agent (the host interleaves agent.act between them)
+extern "C" int fmpm_clear_ring_slot(FmpmHandle* h, int f, void* stream) {
+  if (check_bound(h, "fmpm_clear_ring_slot") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_clear_ring_slot")) return 1;
+  if (!h->buf.grid_pm_ring || !h->buf.blk_list_ring) { snprintf(h->err, sizeof(h->err), "fmpm_clear_ring_slot: the per-frame grid ring was not bound"); return 1; }
+  KParams P = make_kparams(h, f);
+  const int nblk = P.nb * P.nb * P.nb;
+  const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  FMPM_LAUNCH(k_clear_blocks, grid, 256, 0, stream, P);
+  FMPM_CHECK_LAUNCH(h, "fmpm_clear_ring_slot");
+  return 0;
+}
+extern "C" int fmpm_g2p2g_store(FmpmHandle* h, int f, void* stream) { return g2p2g_store_impl(h, f, stream); }
+extern "C" int fmpm_p2g_store(FmpmHandle* h, int f, void* stream) { return fmpm_p2g_impl(h, f, 1, f, stream); }
+extern "C" int fmpm_grid_op_store(FmpmHandle* h, int f, void* stream) { return fmpm_grid_op_impl(h, f, 0, 0, f, stream); }
+extern "C" int fmpm_g2p_store(FmpmHandle* h, int f, void* stream) { return fmpm_g2p_impl(h, f, f, stream); }
 extern "C" int fmpm_substeps_fused_store(FmpmHandle* h, int f0, int n, void* stream) {
   if (check_bound(h, "fmpm_substeps_fused_store")) return 1;
   if (!h->buf.grid_pm_ring || !h->buf.grid_v_ring || !h->buf.blk_list_ring) {
@@ -572,6 +620,17 @@ extern "C" int fmpm_collect(FmpmHandle* h, int f, const FmpmCollector* c, void* 
   return 0;
 }
 
+// fused steps with an injector agent: scatter the particles that fmpm_inject(f-1, ...) has just activated in frame f (act_id = the injector's
+// counter BEFORE that injection).  Call after fmpm_g2p2g(f-1) + fmpm_inject(f-1) and before fmpm_grid_op(f).
+extern "C" int fmpm_p2g_injected(FmpmHandle* h, int f, const FmpmInjector* inj, int act_id, const void* inv, int ring_slot, void* stream) {
+  if (check_bound(h, "fmpm_p2g_injected") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_p2g_injected")) return 1;
+  if (!inj || act_id < 0 || act_id + inj->flux > inj->n_act_range) { snprintf(h->err, sizeof(h->err), "fmpm_p2g_injected: bad injector range"); return 1; }
+  if (h->slab.enabled) { snprintf(h->err, sizeof(h->err), "fmpm_p2g_injected: not available in x-slab mode"); return 1; }
+  KParams P = make_kparams(h, ring_slot);   // ring_slot >= 0: the accumulator / block flags of that slot of the per-frame ring (grad mode)
+  FMPM_LAUNCH(k_p2g_injected, (inj->flux + 31) / 32, 32, 0, stream, P, f, *inj, act_id, (const int*)inv);
+  FMPM_CHECK_LAUNCH(h, "fmpm_p2g_injected");
+  return 0;
+}
 extern "C" int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,
                            const void* inv, void* stream) {
   if (check_bound(h, "fmpm_inject") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_inject")) return 1;

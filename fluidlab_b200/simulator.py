@@ -419,6 +419,48 @@ class MPMSimulator:
             return False
         return (not self.grad_enabled) or self._storing()
 
+    def _can_fuse_injector(self):
+        """steps of a plain AgentInjector (LatteArt): the fused g2p2g kernels plus a tiny scatter of the newly injected particles; forward-only
+        and, in grad mode, the stored-grid path"""
+        if not (bool(getattr(self, 'fuse_g2p2g', False)) and not getattr(self, '_has_rigid_bodies', False)
+                and type(self.agent).__name__ == 'AgentInjector' and self.has_particles):
+            return False
+        return (not self.grad_enabled) or self._storing()
+
+    def _fused_step_with_injector(self):
+        """10 substeps with an injector agent (MPM:515-533 order: substep kernels, then agent.act writes frame f+1): p2g(f0), then per substep
+        grid_op(f) -> g2p2g(f) [g2p for the last] -> agent.act(f) -> scatter of the particles it activated into the grid of f+1.
+        Grad mode: the same with the per-frame grid ring (slot = frame; slot f+1 is cleared before g2p2g fills it, every frame is complete)."""
+        L, h, st = self._lib, self._h, self._stream
+        n, inj = self.n_substeps, self.agent.injector
+        store = self._storing()
+        f0 = self.cur_substep_local
+        if store:
+            self._ck(L.fmpm_clear_ring_slot(h, f0, st()), 'fmpm_clear_ring_slot')
+            self._ck(L.fmpm_p2g_store(h, f0, st()), 'fmpm_p2g_store')
+        else:
+            self._ck(L.fmpm_p2g(h, f0, 1, st()), 'fmpm_p2g')
+        for i in range(n):
+            f = f0 + i
+            last = i + 1 == n
+            if store:
+                self._ck(L.fmpm_grid_op_store(h, f, st()), 'fmpm_grid_op_store')
+                if last:
+                    self._ck(L.fmpm_g2p_store(h, f, st()), 'fmpm_g2p_store')
+                else:
+                    self._ck(L.fmpm_clear_ring_slot(h, f + 1, st()), 'fmpm_clear_ring_slot')
+                    self._ck(L.fmpm_g2p2g_store(h, f, st()), 'fmpm_g2p2g_store')
+            else:
+                self._ck(L.fmpm_grid_op(h, f, 1, st()), 'fmpm_grid_op')
+                self._ck(L.fmpm_g2p(h, f, st()) if last else L.fmpm_g2p2g(h, f, 0, st()), 'fmpm_g2p2g')
+            self._frame_ord[f + 1] = self._frame_ord[f]
+            self._ring_valid[f] = store
+            act_id = inj.act_id[f]
+            self.agent.act(f, self.cur_substep_global)
+            if not last:
+                self._ck(L.fmpm_p2g_injected(h, f + 1, C.byref(inj._inj), act_id, self._frame_ord[f + 1].inv_ptr(), (f + 1) if store else -1, st()), 'fmpm_p2g_injected')
+            self.cur_substep_global += 1
+
     def _fused_substeps(self, f0):
         if self._storing():
             self._ck(self._lib.fmpm_substeps_fused_store(self._h, f0, self.n_substeps, self._stream()), 'fmpm_substeps_fused_store')
@@ -649,6 +691,8 @@ class MPMSimulator:
             self.sort_frame(self.cur_substep_local)
         if self.use_graphs and is_none_action and self.has_particles and self._graph_substeps():
             self.cur_substep_global += self.n_substeps
+        elif not is_none_action and self._can_fuse_injector():
+            self._fused_step_with_injector()
         elif is_none_action and self.has_particles and self._can_fuse():
             f0 = self.cur_substep_local
             store = self._storing()

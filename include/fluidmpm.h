@@ -196,6 +196,15 @@ int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, 
 int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream);
 /* n substeps f0..f0+n-1: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1); frames f0 and f0+n are complete */
 int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream);
+/* fused steps with an injector agent (agents/agent_injector.py): after fmpm_g2p2g(f-1) and fmpm_inject(f-1, ...) the few newly activated
+ * particles of frame f are scattered separately, before fmpm_grid_op(f) */
+int fmpm_p2g_injected(FmpmHandle* h, int f, const FmpmInjector* inj, int act_id, const void* inv, int ring_slot, void* stream);   /* ring_slot: -1, or f in grad mode */
+/* the pieces of fmpm_substep_store / fmpm_substeps_fused_store one by one (ring slot = frame), for hosts that interleave agent kernels */
+int fmpm_clear_ring_slot(FmpmHandle* h, int f, void* stream);
+int fmpm_p2g_store(FmpmHandle* h, int f, void* stream);
+int fmpm_grid_op_store(FmpmHandle* h, int f, void* stream);
+int fmpm_g2p_store(FmpmHandle* h, int f, void* stream);
+int fmpm_g2p2g_store(FmpmHandle* h, int f, void* stream);       /* gathers from slot f, scatters into slot f+1 (cleared before), writes frame f+1 completely */
 /* the same in grad mode with per-frame grids (like fmpm_substep_store): every frame is written completely, slot f+1's grids are cleared and
  * refilled by the fused kernel: 148 B instead of 212 B per particle and substep, 3 launches instead of 4 */
 int fmpm_substeps_fused_store(FmpmHandle* h, int f0, int n, void* stream);

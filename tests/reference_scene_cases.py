@@ -169,3 +169,19 @@ def run_cloud_adjoint_case(device=None):
     for key, idx, fd in zip(FD['cloud_pick_key'], FD['cloud_pick_idx'], FD['cloud_fd']):
         an = float(g[str(key)].reshape(-1)[int(idx)])
         assert abs(an - fd) <= 2e-3 * scale, (str(key), int(idx), an, float(fd), scale)
+
+
+def run_latteart_fused_case(device=None):
+    """the LatteArt reference run again, stepped through the fused path (MPMSimulator.fuse_g2p2g with an AgentInjector: g2p2g kernels + the
+    separate scatter of the freshly injected particles)"""
+    from fluidlab_b200 import AgentInjector
+    d = np.load(os.path.join(G, 'reference_run_latteart.npz'))
+    s = _sim(d, device, (0.0, -20.0, 0.0), dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.34, 0.9)))
+    s.fuse_g2p2g = True
+    common = dict(max_substeps_local=int(d['T']), max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
+    agent = AgentInjector(**common)
+    agent.add_effector(type='Injector', params=dict(radius=0.0075, flux=int(d['flux']), init_pos=(0.5, 0.5, 0.5), action_dim=3, inject_v=(0.0, -3.0, 0.0),
+                                                    action_scale_p=(1.0, 1.0, 1.0), action_scale_v=(1.0, 1.0, 1.0), locally_random=True),
+                       mesh_cfg=None, boundary_cfg=dict(type='cylinder', xz_radius=0.12, xz_center=(0.5, 0.5), y_range=(0.55, 0.55)))
+    _drive(s, agent, agent.effectors[0], d)
+    assert s._can_fuse_injector()

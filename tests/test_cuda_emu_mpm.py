@@ -348,7 +348,7 @@ def test_slab_forward_with_g2p2g_fusion_on_the_emulated_device(exchange):
     assert out[0]['migrated'] > 0 and out[1]['migrated'] > 0
 
 
-@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream'])
+@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream', 'latteart_fused'])
 def test_agent_scenes_equal_runs_of_the_real_reference_agents(emu, scene):
     """product (real kernels on the emulated device) vs runs of the reference's own AgentInjector / AgentJetBot / AgentPouring / AgentIceCreamDynamic scenes; tests/reference_scene_cases.py"""
     import reference_scene_cases as cases
@@ -414,3 +414,65 @@ def test_neighbour_handshake_gives_up_instead_of_hanging_when_a_peer_never_arriv
     assert L.fmpm_slab_sync(h, None) == 0
     assert time.perf_counter() - t0 < 0.1 and mine[3] == 0 and mine[2] == 2
     L.fmpm_destroy(h)
+
+
+def test_latteart_forward_backward_with_fused_injector_steps(emu):
+    """TaichiEnv with an AgentInjector and the index-matched MILK loss (the call sequence of optimizer/solver.py:23-59), ring of 2 steps for a
+    3-step horizon (chunk checkpoint + re-simulation): with MPMSimulator.fuse_g2p2g the stored-grid forward runs g2p2g kernels + the separate
+    scatter of the freshly injected particles; loss and dLoss/dAction must equal the unfused run's and the fp64 oracle's"""
+    from fluidlab_b200 import TaichiEnv, LatteArtLoss, macros as M
+    n_grid, n_coffee, n_milk, flux, T, n_steps = 16, 400, 120, 2, 20, 3
+    rng = np.random.RandomState(21)
+    x = np.concatenate([np.tile(M.NOWHERE, (n_milk, 1)), rng.uniform((0.38, 0.36, 0.38), (0.62, 0.45, 0.62), size=(n_coffee, 3))])
+    mat = np.concatenate([np.full(n_milk, M.MILK), np.full(n_coffee, M.COFFEE)])
+    used = np.concatenate([np.zeros(n_milk), np.ones(n_coffee)]).astype(np.int32)
+    P = make_particles(x, mat, n_grid, used=used)
+    bnd = dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.34, 0.9))
+    ebnd = dict(type='cylinder', xz_radius=0.12, xz_center=(0.5, 0.5), y_range=(0.55, 0.55))
+    cfg = dict(type='AgentInjector', effectors=[dict(type='Injector', params=dict(radius=0.0075, flux=flux, init_pos=(0.5, 0.5, 0.5), action_dim=3, inject_v=(0.0, -3.0, 0.0),
+                                                                                 action_scale_p=(1.0, 1.0, 1.0), action_scale_v=(1.0, 1.0, 1.0), locally_random=True), boundary=ebnd)])
+    tgt = [rng.uniform(0.4, 0.6, size=x.shape).astype(np.float32) for _ in range(n_steps)]
+    actions = rng.uniform(-0.004, 0.004, size=(n_steps, 3)).astype(np.float32)
+    action_p = np.array([0.47, 0.55, 0.52], dtype=np.float32)
+    res = {}
+    for fuse in (False, True):
+        env = TaichiEnv(quality=n_grid / 64, max_substeps_local=T, gravity=(0.0, -20.0, 0.0), horizon=n_steps, ckpt_dest='cpu', device='cpu')
+        env.simulator.use_graphs, env.simulator.fuse_g2p2g = False, fuse
+        np.random.seed(5)
+        env.setup_agent(cfg)
+        env.particle_bodies.get = lambda: P
+        env.setup_boundary(**bnd)
+        env.setup_loss(loss_cls=LatteArtLoss, type='diff', target=tgt, weights={'chamfer': 1.0})
+        env.build()
+        rv = env.agent.effectors[0].random_vector_np
+        env.set_state(env.get_state()['state'], grad_enabled=True)
+        assert env.simulator._can_fuse_injector() == fuse
+        env.apply_agent_action_p(action_p)
+        for i in range(n_steps):
+            env.step(actions[i])
+        info = env.get_final_loss()
+        env.reset_grad(); env.get_final_loss_grad()
+        for i in range(n_steps - 1, -1, -1):
+            env.step_grad(actions[i])
+        env.apply_agent_action_p_grad(action_p)
+        res[fuse] = (info['loss'], env.agent.get_grad(n_steps))
+    o = orc.OracleSim(n_grid, P, gravity=(0, -20, 0), boundary=bnd, precision=64, max_substeps_local=T)
+    o.add_effector(type=1, action_dim=3, boundary=ebnd, radius=0.0075, flux=flux, inject_v=(0, -3, 0), inject_p=(0, 0, 0), locally_random=True, random_vector=rv,
+                   act_range=np.where(used == 0)[0], max_action_steps=n_steps + 1)
+    N = len(x)
+    o.enable_grad()
+    o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+    o.set_effector_state(0, 0, np.array([0.5, 0.5, 0.5, 1, 0, 0, 0, 0.0]))
+    o.apply_action_p(action_p)
+    total = 0.0
+    for i in range(n_steps):
+        o.step(actions[i]); total += o.loss_value(o.cur_substep_local, M.MILK, 1.0, tgt[i])
+    o.reset_grad()
+    for i in range(n_steps - 1, -1, -1):
+        o.loss_seed(o.cur_substep_local, M.MILK, 1.0, tgt[i]); o.step_grad(actions[i])
+    o.apply_action_p_grad()
+    og = o.get_action_grad(n_steps)
+    for fuse in (False, True):
+        loss, grad = res[fuse]
+        assert abs(loss - total) <= 1e-5 * abs(total), (fuse, loss, total)
+        assert np.abs(og).max() > 1e-3 and rel(grad, og) < 1e-4, (fuse, rel(grad, og))

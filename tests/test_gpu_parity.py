@@ -984,7 +984,7 @@ def test_slab_sharded_backward_matches_single_gpu(exchange):
     assert r.returncode == 0 and 'SLAB_GRAD_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream'])
+@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream', 'latteart_fused'])
 def test_cuda_matches_runs_of_the_real_reference_agents(scene):
     """the CUDA path against runs of the reference's own AgentInjector (LatteArt configuration in miniature), AgentJetBot (6-DOF injector +
     collector), AgentPouring (6-DOF Rigid SDF collider at grid and particle level + collector) and AgentIceCreamDynamic (BallInjector, gated
