@@ -386,8 +386,9 @@ def test_neighbour_handshake_gives_up_instead_of_hanging_when_a_peer_never_arriv
     import time
     from fluidlab_b200 import _lib
     out = os.path.join(harness.EMU_DIR, '_build', 'libfluidmpm_emu_timeout.so')
-    src = os.path.join(harness.CSRC, 'fmpm_io.cu')
-    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+    deps = [os.path.join(harness.CSRC, f) for f in os.listdir(harness.CSRC) if f.endswith(('.cu', '.cuh'))] + [os.path.join(harness.ROOT, 'include', 'fluidmpm.h'),
+                                                                                                              os.path.join(harness.EMU_DIR, 'cuda_runtime.h')]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(['/usr/bin/g++', '-std=c++20', '-O1', '-fPIC', '-shared', '-pthread', '-x', 'c++', '-I', harness.EMU_DIR, '-DFMPM_BUILD',
                                '-DFMPM_SYNC_TIMEOUT_NS=200000000ULL'] + [os.path.join(harness.CSRC, s) for s in harness.SRCS] + ['-o', out])
     L = C.CDLL(out)
