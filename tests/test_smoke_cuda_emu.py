@@ -22,13 +22,11 @@ EMU_DIR = os.path.join(ROOT, 'tests', 'cuda_emu')
 
 @pytest.fixture(scope='module')
 def emu():
-    out = os.path.join(EMU_DIR, '_build', 'libfsmk_emu.so')
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    src = os.path.join(ROOT, 'fluidlab_b200', 'csrc', 'fsmk_smoke.cu')
-    deps = [src, os.path.join(EMU_DIR, 'cuda_runtime.h'), os.path.join(ROOT, 'include', 'fluidsmoke.h'), os.path.join(ROOT, 'fluidlab_b200', 'csrc', 'fmpm_sdf.cuh')]
-    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(['/usr/bin/g++', '-std=c++20', '-O1', '-fPIC', '-shared', '-pthread', '-x', 'c++', '-I', EMU_DIR, src, '-o', out])
-    return _lib.attach_smoke_protos(C.CDLL(out))
+    """the whole product library built for the host (tests/cuda_emu/harness.py), smoke entry points attached"""
+    import sys
+    sys.path.insert(0, EMU_DIR)
+    import harness
+    return _lib.attach_smoke_protos(C.CDLL(harness.build_library()))
 
 
 class EmuSmoke:
