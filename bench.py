@@ -341,6 +341,42 @@ def main():
                  'frac': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9 / peak, 'p2g_ms': t_p2g, 'g2p_ms': t_g2p, 'grid_op_ms': t_gop,
                  'bytes': p2g_bytes + g2p_bytes, 'ms_by_steps_since_sort': sort_age}
 
+    # the fused path's own figure: mean launch time of k_g2p2g over a replay of the timed trajectory on the per-phase path.  One fused launch
+    # does the work SURVEY 8(d) counts for p2g + g2p of a substep (212 B x N_u + 28 B x G_t), so `achieved` uses that figure: the fraction is
+    # comparable with roofline_p2g_g2p.  (The bytes the fused kernel itself must move are fewer: 104 B x N_u + 28 B x G_t.)
+    roof_fused = None
+    if slab is None and args.fuse_g2p2g:
+        try:
+            evf = []
+            sim.cur_substep_global = 0
+            sim.set_state(0, init)
+            for i in range(W + K):
+                if sim.sort_every > 0 and sim.cur_step_global % sim.sort_every == 0:
+                    sim.sort_frame(sim.cur_substep_local)
+                f0 = sim.cur_substep_local
+                sim.phase('p2g', f0, 1)
+                for j in range(SUBSTEPS_PER_STEP):
+                    fj = f0 + j
+                    sim.phase('grid_op', fj, 1)
+                    if j + 1 < SUBSTEPS_PER_STEP:
+                        e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                        e[0].record(); sim.phase('g2p2g', fj); e[1].record()
+                        if i >= W:
+                            evf.append(e)
+                    else:
+                        sim.phase('g2p', fj)
+                    sim.cur_substep_global += 1
+                if sim.cur_substep_local == 0:
+                    sim.memory_to_cache()
+            torch.cuda.synchronize()
+            t_fused = float(np.mean([a.elapsed_time(b) for a, b in evf]))
+            pair_bytes = p2g_bytes + g2p_bytes
+            roof_fused = {'bound': 'hbm', 'kernel': 'k_g2p2g', 'achieved': pair_bytes / (t_fused * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                          'frac': pair_bytes / (t_fused * 1e-3) / 1e9 / peak, 'launch_ms': t_fused, 'algorithmic_bytes_per_launch': pair_bytes,
+                          'bytes_the_fused_kernel_moves': 104 * used + 28 * g_t, 'launches_timed': len(evf)}
+        except Exception as ex:
+            roof_fused = {'error': f'{type(ex).__name__}: {ex}'}
+
     # ------------------------------------------------------------------ forward+backward (BASELINE metric, second half)
     fb = None
     if args.bwd and world == 1:
@@ -474,7 +510,7 @@ def main():
                     'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},
             'gpu_launches': K * ((2 * SUBSTEPS_PER_STEP + 1) if args.fuse_g2p2g else SUBSTEPS_PER_STEP * 3) + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
             'e2e_obs_bridge': e2e_obs,
-            'roofline': roof, 'roofline_p2g_g2p': roof_pair,
+            'roofline': roof, 'roofline_p2g_g2p': roof_pair, 'roofline_g2p2g': roof_fused,
             'fwd_bwd': fb,
             'cpu_baseline': cpu,
         }
