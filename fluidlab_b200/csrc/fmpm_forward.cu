@@ -16,6 +16,7 @@
 //  * grid_op (MPM:380-398) also clears the momentum/mass accumulators for the next substep;
 //  * g2p fuses advect_used / process_unused_particles / g2p / advect_kernel (MPM:304-316, 400-426, 497-505).
 #include <cstdio>
+#include <cstring>
 #include "fmpm_common.cuh"
 
 #include "fmpm_scatter.cuh"
@@ -261,11 +262,20 @@ __global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const i
 // The scatter's warp-local key ranking (fmpm_scatter.cuh) absorbs the mismatch between the slot order (cells of the last sort)
 // and the cells of x[f+1].
 // =============================================================================================
+// collector boundary test of agents/agent_pouring.py:31-41 / agents/agent_jetbot.py:30-40 (boundaries.py:81-93, 128-134): true = the particle leaves
+__device__ __forceinline__ bool collector_takes(const FmpmCollector& c, const int meta, const float* x) {
+  const int row = (meta >> 8) & 0xff;
+  if (row >= 32 || !((c.row_mask >> row) & 1u)) return false;
+  if (c.boundary_type == 0) return x[0] > c.upper[0] || x[1] > c.upper[1] || x[2] > c.upper[2] || x[0] < c.lower[0] || x[1] < c.lower[1] || x[2] < c.lower[2];
+  const float rx = x[0] - c.cyl_center[0], rz = x[2] - c.cyl_center[1];
+  return x[1] > c.upper[1] || x[1] < c.lower[1] || sqrtf(rx * rx + rz * rz + FMPM_EPS) > c.cyl_radius;
+}
 #ifndef G2P2G_MINB
 #define G2P2G_MINB P2G_MINB   // 96 registers at 5 CTAs of 4 warps; A/B other bounds with FMPM_DEFS=-DG2P2G_MINB=... (profiles/ab_variants.sh, PT_FUSED=1)
 #endif
-template <bool kWriteVC>
-__global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KParams P, const int f) {
+// kAgent: particle-level agent.collide and the collector test are compiled in (scenes with a Rigid effector and / or a collector agent)
+template <bool kWriteVC, bool kAgent>
+__global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KParams P, const int f, const FmpmCollector col, const int has_col) {
   __shared__ ScatterSmem smem[P2G_WARPS];
   static_assert(sizeof(((ScatterSmem*)0)->rec) >= 9 * G2P_ZMAX * sizeof(float4), "the gather tile is staged in the scatter records' storage");
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -316,14 +326,22 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
         const int n = P.n;
         g2p_gather(fx, w, [&](int c) { return gv + ((c / 3) * n + (c % 3)) * n; }, st.v, st.C, c4);
       }
+      if (kAgent && P.col.has_rigid && P.col.collide_type != 1) {  // agent.collide at particle level (the default), MPM:419-422
+        const float xt[3] = {x[0] + P.dt * st.v[0], x[1] + P.dt * st.v[1], x[2] + P.dt * st.v[2]};
+        float o[3]; agent_collide<false>(P, f, xt, st.v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
+        st.v[0] = o[0]; st.v[1] = o[1]; st.v[2] = o[2];
+      }
 #pragma unroll
       for (int d = 0; d < 3; d++) st.x[d] = x[d] + P.dt * st.v[d];   // advect_kernel MPM:505
-      st.meta = meta;
+      // collector agents act on frame f+1 BEFORE its p2g (MPM:521): a particle that left is tagged (used bit off, bit 1 on), does not
+      // scatter, and the next substep's gather parks it — exactly what fmpm_collect(f+1) + k_p2g + k_g2p do on the unfused path
+      const bool taken = kAgent && has_col && collector_takes(col, meta, st.x);
+      st.meta = taken ? ((meta & ~1) | 2) : meta;
       // ---- p2g of frame f+1 (MPM:254-264, 331-378)
       int b1[3]; float fx1[3];
-      const bool ok1 = base_fx(P, st.x, b1, fx1);
-      if (kWriteVC || !ok1) store_A(P.pa, P, f + 1, s, st.x, meta, st.v, st.C);
-      else P.pa[pa_idx(P, f + 1, 0, s)] = make_float4(st.x[0], st.x[1], st.x[2], __int_as_float(meta));
+      const bool ok1 = !taken && base_fx(P, st.x, b1, fx1);
+      if (kWriteVC || !ok1) store_A(P.pa, P, f + 1, s, st.x, st.meta, st.v, st.C);
+      else P.pa[pa_idx(P, f + 1, 0, s)] = make_float4(st.x[0], st.x[1], st.x[2], __int_as_float(st.meta));
       if (ok1) {
         const float4 mt = __ldg(P.mats + ((meta >> 8) & 0xff));
         Constit K; constitutive(P, st, mt.x, mt.y, mt.z, __float_as_int(mt.w), K);
@@ -351,7 +369,8 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
 // p2g of the few particles an injector has just activated in frame f (fused steps with an injector agent: the g2p2g kernel of the previous
 // substep ran before agent.act wrote them, so their contribution to the grid of frame f is added here — flux particles, plain vector
 // reductions, no window).  Same arithmetic as k_p2g for one particle; also writes F[f+1] and flags the touched blocks.
-__global__ void k_p2g_injected(const KParams P, const int f, const FmpmInjector inj, const int act_id, const int* __restrict__ inv) {
+__global__ void k_p2g_injected(const KParams P, const int f, const FmpmInjector inj, const int act_id, const int* __restrict__ inv, const FmpmCollector col,
+                               const int has_col) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= inj.flux) return;
   const int pid = ((const int*)inj.act_range)[act_id + i];
@@ -359,6 +378,10 @@ __global__ void k_p2g_injected(const KParams P, const int f, const FmpmInjector 
   PRaw R; p2g_load_raw(P, f, s, R);
   PState st; p2g_unpack(R, st);
   int b[3]; float fx[3];
+  if ((st.meta & 1) && has_col && collector_takes(col, st.meta, st.x)) {   // fmpm_collect(f) would have tagged it before p2g(f)
+    P.pa[pa_idx(P, f, 0, s)].w = __int_as_float((st.meta & ~1) | 2);
+    p2g_store_F(P, f + 1, s, st.F); return;
+  }
   if (!((st.meta & 1) && base_fx(P, st.x, b, fx))) { p2g_store_F(P, f + 1, s, st.F); return; }
   const float4 mt = __ldg(P.mats + ((st.meta >> 8) & 0xff));
   Constit K; constitutive(P, st, mt.x, mt.y, mt.z, __float_as_int(mt.w), K);
@@ -423,6 +446,8 @@ static int check_bound(FmpmHandle* h, const char* name) {
   if (!h->bound) { snprintf(h->err, sizeof(h->err), "%s: fmpm_bind() has not been called", name); return 1; }
   return 0;
 }
+#define G2P2G_K(a, b) (k_g2p2g<a, b>)   /* a template-id with a comma cannot be a macro argument by itself */
+static FmpmCollector no_collector() { FmpmCollector c; memset(&c, 0, sizeof(c)); return c; }
 static int check_frame(FmpmHandle* h, int f, int maxf, const char* name) {
   if (f < 0 || f > maxf) { snprintf(h->err, sizeof(h->err), "%s: frame %d out of range [0,%d]", name, f, maxf); return 1; }
   return 0;
@@ -512,31 +537,38 @@ extern "C" int fmpm_substep_store(FmpmHandle* h, int f, void* stream) {
 }
 
 // g2p(f) fused with p2g(f+1): forward-only steps without agents, MAT_RIGID bodies or slabs (see k_g2p2g)
-extern "C" int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream) {
+static int g2p2g_impl(FmpmHandle* h, int f, int write_vc, const FmpmCollector* col, void* stream);
+extern "C" int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream) { return g2p2g_impl(h, f, write_vc, nullptr, stream); }
+extern "C" int fmpm_g2p2g_collect(FmpmHandle* h, int f, int write_vc, const FmpmCollector* col, void* stream) { return g2p2g_impl(h, f, write_vc, col, stream); }
+static int g2p2g_impl(FmpmHandle* h, int f, int write_vc, const FmpmCollector* col, void* stream) {
   if (check_bound(h, "fmpm_g2p2g") || check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_g2p2g")) return 1;
-  if (h->col.has_rigid || h->bodies.n_bodies > 0) {
-    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: not available with a rigid effector or MAT_RIGID bodies"); return 1;
+  if (h->bodies.n_bodies > 0) {
+    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: not available with MAT_RIGID bodies"); return 1;
   }
   KParams P = make_kparams(h, -1, f + 1);   // x-slab mode: the scatter goes to the accumulator / block flags / peers of substep parity f+1
   if (P.N == 0) return 0;
   const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
-  if (write_vc) FMPM_LAUNCH(k_g2p2g<true>, blocks, P2G_WARPS * 32, 0, stream, P, f);
-  else FMPM_LAUNCH(k_g2p2g<false>, blocks, P2G_WARPS * 32, 0, stream, P, f);
+  const FmpmCollector c = col ? *col : no_collector();
+  const bool agent = col != nullptr || (h->col.has_rigid && h->col.collide_type != 1);
+  if (write_vc) { if (agent) FMPM_LAUNCH(G2P2G_K(true, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0); else FMPM_LAUNCH(G2P2G_K(true, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0); }
+  else { if (agent) FMPM_LAUNCH(G2P2G_K(false, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0); else FMPM_LAUNCH(G2P2G_K(false, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0); }
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p2g");
   return 0;
 }
 // the same fusion in grad mode with per-frame grids (fmpm_substep_store): g2p gathers from ring slot f, p2g scatters into ring slot f+1, and
 // every frame is written completely (the backward pass reads x, v, C, F of every frame): 148 B instead of 212 B per particle and substep
-static int g2p2g_store_impl(FmpmHandle* h, int f, void* stream) {
+static int g2p2g_store_impl(FmpmHandle* h, int f, void* stream, const FmpmCollector* col = nullptr) {
   if (check_bound(h, "fmpm_g2p2g(store)") || check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_g2p2g(store)")) return 1;
-  if (h->col.has_rigid || h->bodies.n_bodies > 0 || h->slab.enabled) {
-    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: not available with a rigid effector, MAT_RIGID bodies or x-slabs"); return 1;
+  if (h->bodies.n_bodies > 0 || h->slab.enabled) {
+    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g(store): not available with MAT_RIGID bodies or x-slabs"); return 1;
   }
   KParams P = make_kparams(h, f + 1);            // scatter target: accumulator + block flags of slot f+1
   P.grid_v = make_kparams(h, f).grid_v;          // gather source: v_out of slot f
   if (P.N == 0) return 0;
   const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
-  FMPM_LAUNCH(k_g2p2g<true>, blocks, P2G_WARPS * 32, 0, stream, P, f);
+  const FmpmCollector c = col ? *col : no_collector();
+  if (col != nullptr || (h->col.has_rigid && h->col.collide_type != 1)) FMPM_LAUNCH(G2P2G_K(true, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0);
+  else FMPM_LAUNCH(G2P2G_K(true, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0);
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p2g(store)");
   return 0;
 }
@@ -551,7 +583,7 @@ extern "C" int fmpm_clear_ring_slot(FmpmHandle* h, int f, void* stream) {
   FMPM_CHECK_LAUNCH(h, "fmpm_clear_ring_slot");
   return 0;
 }
-extern "C" int fmpm_g2p2g_store(FmpmHandle* h, int f, void* stream) { return g2p2g_store_impl(h, f, stream); }
+extern "C" int fmpm_g2p2g_store(FmpmHandle* h, int f, const FmpmCollector* col, void* stream) { return g2p2g_store_impl(h, f, stream, col); }
 extern "C" int fmpm_p2g_store(FmpmHandle* h, int f, void* stream) { return fmpm_p2g_impl(h, f, 1, f, stream); }
 extern "C" int fmpm_grid_op_store(FmpmHandle* h, int f, void* stream) { return fmpm_grid_op_impl(h, f, 0, 0, f, stream); }
 extern "C" int fmpm_g2p_store(FmpmHandle* h, int f, void* stream) { return fmpm_g2p_impl(h, f, f, stream); }
@@ -622,12 +654,12 @@ extern "C" int fmpm_collect(FmpmHandle* h, int f, const FmpmCollector* c, void* 
 
 // fused steps with an injector agent: scatter the particles that fmpm_inject(f-1, ...) has just activated in frame f (act_id = the injector's
 // counter BEFORE that injection).  Call after fmpm_g2p2g(f-1) + fmpm_inject(f-1) and before fmpm_grid_op(f).
-extern "C" int fmpm_p2g_injected(FmpmHandle* h, int f, const FmpmInjector* inj, int act_id, const void* inv, int ring_slot, void* stream) {
+extern "C" int fmpm_p2g_injected(FmpmHandle* h, int f, const FmpmInjector* inj, int act_id, const void* inv, int ring_slot, const FmpmCollector* col, void* stream) {
   if (check_bound(h, "fmpm_p2g_injected") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_p2g_injected")) return 1;
   if (!inj || act_id < 0 || act_id + inj->flux > inj->n_act_range) { snprintf(h->err, sizeof(h->err), "fmpm_p2g_injected: bad injector range"); return 1; }
   if (h->slab.enabled) { snprintf(h->err, sizeof(h->err), "fmpm_p2g_injected: not available in x-slab mode"); return 1; }
   KParams P = make_kparams(h, ring_slot);   // ring_slot >= 0: the accumulator / block flags of that slot of the per-frame ring (grad mode)
-  FMPM_LAUNCH(k_p2g_injected, (inj->flux + 31) / 32, 32, 0, stream, P, f, *inj, act_id, (const int*)inv);
+  FMPM_LAUNCH(k_p2g_injected, (inj->flux + 31) / 32, 32, 0, stream, P, f, *inj, act_id, (const int*)inv, col ? *col : no_collector(), col ? 1 : 0);
   FMPM_CHECK_LAUNCH(h, "fmpm_p2g_injected");
   return 0;
 }

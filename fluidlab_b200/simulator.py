@@ -420,21 +420,26 @@ class MPMSimulator:
         return (not self.grad_enabled) or self._storing()
 
     def _can_fuse_injector(self):
-        """steps of a plain AgentInjector (LatteArt): the fused g2p2g kernels plus a tiny scatter of the newly injected particles; forward-only
-        and, in grad mode, the stored-grid path"""
-        if not (bool(getattr(self, 'fuse_g2p2g', False)) and not getattr(self, '_has_rigid_bodies', False)
-                and type(self.agent).__name__ == 'AgentInjector' and self.has_particles):
+        """steps WITH an agent: the fused g2p2g kernels (particle-level agent.collide and the collector's test compiled in where the agent has
+        them) plus a tiny scatter of the particles an injector activates; forward-only and, in grad mode, the stored-grid path.  Covers every
+        agent of agents.py; MAT_RIGID bodies (their advect pass needs complete frames) keep the unfused path."""
+        if not (bool(getattr(self, 'fuse_g2p2g', False)) and not getattr(self, '_has_rigid_bodies', False) and self.agent is not None and self.has_particles):
             return False
         return (not self.grad_enabled) or self._storing()
 
     def _fused_step_with_injector(self):
-        """10 substeps with an injector agent (MPM:515-533 order: substep kernels, then agent.act writes frame f+1): p2g(f0), then per substep
-        grid_op(f) -> g2p2g(f) [g2p for the last] -> agent.act(f) -> scatter of the particles it activated into the grid of f+1.
+        """10 substeps with an agent, in the reference's order (MPM:515-533: agent.act [collector part] -> substep kernels -> agent.act [injector
+        part writes frame f+1]): collect(f0), p2g(f0), then per substep grid_op(f) -> g2p2g(f) [collector test on the new position inside;
+        plain g2p for the last substep] -> agent.act(f) -> scatter of the particles it activated into the grid of f+1.
         Grad mode: the same with the per-frame grid ring (slot = frame; slot f+1 is cleared before g2p2g fills it, every frame is complete)."""
         L, h, st = self._lib, self._h, self._stream
-        n, inj = self.n_substeps, self.agent.injector
+        n = self.n_substeps
+        inj = getattr(self.agent, 'injector', None)
+        col = getattr(self.agent, '_collector', None)
+        colp = None if col is None else C.byref(col)
         store = self._storing()
         f0 = self.cur_substep_local
+        self.agent.collect(f0)
         if store:
             self._ck(L.fmpm_clear_ring_slot(h, f0, st()), 'fmpm_clear_ring_slot')
             self._ck(L.fmpm_p2g_store(h, f0, st()), 'fmpm_p2g_store')
@@ -449,16 +454,17 @@ class MPMSimulator:
                     self._ck(L.fmpm_g2p_store(h, f, st()), 'fmpm_g2p_store')
                 else:
                     self._ck(L.fmpm_clear_ring_slot(h, f + 1, st()), 'fmpm_clear_ring_slot')
-                    self._ck(L.fmpm_g2p2g_store(h, f, st()), 'fmpm_g2p2g_store')
+                    self._ck(L.fmpm_g2p2g_store(h, f, colp, st()), 'fmpm_g2p2g_store')
             else:
                 self._ck(L.fmpm_grid_op(h, f, 1, st()), 'fmpm_grid_op')
-                self._ck(L.fmpm_g2p(h, f, st()) if last else L.fmpm_g2p2g(h, f, 0, st()), 'fmpm_g2p2g')
+                self._ck(L.fmpm_g2p(h, f, st()) if last else L.fmpm_g2p2g_collect(h, f, 0, colp, st()), 'fmpm_g2p2g')
             self._frame_ord[f + 1] = self._frame_ord[f]
             self._ring_valid[f] = store
-            act_id = inj.act_id[f]
+            act_id = None if inj is None else inj.act_id[f]
             self.agent.act(f, self.cur_substep_global)
-            if not last:
-                self._ck(L.fmpm_p2g_injected(h, f + 1, C.byref(inj._inj), act_id, self._frame_ord[f + 1].inv_ptr(), (f + 1) if store else -1, st()), 'fmpm_p2g_injected')
+            if not last and inj is not None and inj.act_id[f + 1] != act_id:
+                self._ck(L.fmpm_p2g_injected(h, f + 1, C.byref(inj._inj), act_id, self._frame_ord[f + 1].inv_ptr(), (f + 1) if store else -1, colp, st()),
+                         'fmpm_p2g_injected')
             self.cur_substep_global += 1
 
     def _fused_substeps(self, f0):

@@ -191,20 +191,11 @@ int fmpm_substep(FmpmHandle* h, int f, void* stream);                  /* p2g, g
 int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, but the grids of frame f stay in ring slot f */
 /* forward-only fusion (no reference counterpart): g2p of frame f + p2g of frame f+1 in one kernel — v, C and x stay in registers
  * between the gather and the next scatter (104 B instead of 212 B per particle and substep).  write_vc = 0: v and C of frame f+1 are not
- * materialised.  Not available with a rigid effector or MAT_RIGID bodies.  x-slab mode: the scatter half behaves like fmpm_p2g(f+1)
+ * materialised.  Not available with MAT_RIGID bodies (their advect pass needs the complete frame).  x-slab mode: the scatter half behaves like fmpm_p2g(f+1)
  * (peer reductions into the neighbours' accumulators of parity f+1): synchronise the ranks before fmpm_grid_op(f+1). */
 int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream);
 /* n substeps f0..f0+n-1: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1); frames f0 and f0+n are complete */
 int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream);
-/* fused steps with an injector agent (agents/agent_injector.py): after fmpm_g2p2g(f-1) and fmpm_inject(f-1, ...) the few newly activated
- * particles of frame f are scattered separately, before fmpm_grid_op(f) */
-int fmpm_p2g_injected(FmpmHandle* h, int f, const FmpmInjector* inj, int act_id, const void* inv, int ring_slot, void* stream);   /* ring_slot: -1, or f in grad mode */
-/* the pieces of fmpm_substep_store / fmpm_substeps_fused_store one by one (ring slot = frame), for hosts that interleave agent kernels */
-int fmpm_clear_ring_slot(FmpmHandle* h, int f, void* stream);
-int fmpm_p2g_store(FmpmHandle* h, int f, void* stream);
-int fmpm_grid_op_store(FmpmHandle* h, int f, void* stream);
-int fmpm_g2p_store(FmpmHandle* h, int f, void* stream);
-int fmpm_g2p2g_store(FmpmHandle* h, int f, void* stream);       /* gathers from slot f, scatters into slot f+1 (cleared before), writes frame f+1 completely */
 /* the same in grad mode with per-frame grids (like fmpm_substep_store): every frame is written completely, slot f+1's grids are cleared and
  * refilled by the fused kernel: 148 B instead of 212 B per particle and substep, 3 launches instead of 4 */
 int fmpm_substeps_fused_store(FmpmHandle* h, int f0, int n, void* stream);
@@ -223,6 +214,20 @@ typedef struct FmpmCollector {
   unsigned int row_mask;             /* material-table rows that are collected (AgentPouring: all rows; AgentJetBot: the WATER rows) */
 } FmpmCollector;
 int fmpm_collect(FmpmHandle* h, int f, const FmpmCollector* c, void* stream);
+
+/* ---- g2p2g fusion with agents (declared here because they take an FmpmCollector) ---------------- */
+/* with a collector agent: the collector's test (fmpm_collect of frame f+1) is applied to the new position inside the kernel, before its scatter */
+int fmpm_g2p2g_collect(FmpmHandle* h, int f, int write_vc, const FmpmCollector* col, void* stream);
+/* fused steps with an injector agent (agents/agent_injector.py): after fmpm_g2p2g(f-1) and fmpm_inject(f-1, ...) the few newly activated
+ * particles of frame f are scattered separately, before fmpm_grid_op(f) */
+int fmpm_p2g_injected(FmpmHandle* h, int f, const FmpmInjector* inj, int act_id, const void* inv, int ring_slot, const FmpmCollector* col /* or NULL */,
+                      void* stream);   /* ring_slot: -1, or f in grad mode */
+/* the pieces of fmpm_substep_store / fmpm_substeps_fused_store one by one (ring slot = frame), for hosts that interleave agent kernels */
+int fmpm_clear_ring_slot(FmpmHandle* h, int f, void* stream);
+int fmpm_p2g_store(FmpmHandle* h, int f, void* stream);
+int fmpm_grid_op_store(FmpmHandle* h, int f, void* stream);
+int fmpm_g2p_store(FmpmHandle* h, int f, void* stream);
+int fmpm_g2p2g_store(FmpmHandle* h, int f, const FmpmCollector* col /* or NULL */, void* stream);       /* gathers from slot f, scatters into slot f+1 (cleared before), writes frame f+1 completely */
 
 /* ---- backward substep, MPM:535-552 ------------------------------------------------------------ */
 /* gin/gout in {0,1}: grad ping-pong index holding frame f+1 (in) and receiving frame f (out). */

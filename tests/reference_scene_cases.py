@@ -23,11 +23,15 @@ def _check(fr, d):
     assert np.array_equal(fr['x'][~u], d['ref_x'][~u]), 'parked particles differ'
 
 
+FUSE = [False]   # tests flip it to run the same scenes through the g2p2g path
+
+
 def _sim(d, device, gravity, bnd):
     from fluidlab_b200 import MPMSimulator
     s = MPMSimulator(dim=3, quality=int(d['n_grid']) / 64, gravity=gravity, horizon=10, max_substeps_local=int(d['T']), max_substeps_global=1000,
                      ckpt_dest='gpu' if device is None else 'cpu', device=device)
     s.setup_boundary(**bnd)
+    s.fuse_g2p2g = FUSE[0]
     return s
 
 
@@ -38,6 +42,7 @@ def _drive(s, agent, inj, d):
     agent.build(s)
     assert np.abs(inj.get_state(0)[:7] - d['init_state'][:7]).max() < 1e-6, 'init_pos / init_euler -> pose (effector.py:63-73)'
     agent.apply_action_p(d['action_p'])
+    assert s._can_fuse_injector() == FUSE[0]
     for a in d['actions']:
         s.step(a)
     f = s.cur_substep_local
@@ -97,6 +102,7 @@ def run_pouring_case(device=None):
     s.build(agent, None, [], P)
     agent.build(s)
     agent.apply_action_p(d['action_p'])
+    assert s._can_fuse_injector() == FUSE[0]
     for a in d['actions']:
         s.step(a)
     f = s.cur_substep_local
@@ -133,6 +139,7 @@ def run_icecream_case(device=None):
     s.build(agent, None, statics, P)
     agent.build(s)
     agent.apply_action_p(d['action_p'])
+    assert s._can_fuse_injector() == FUSE[0]
     for a in d['actions']:
         s.step(a)
     f = s.cur_substep_local
@@ -176,12 +183,19 @@ def run_latteart_fused_case(device=None):
     separate scatter of the freshly injected particles)"""
     from fluidlab_b200 import AgentInjector
     d = np.load(os.path.join(G, 'reference_run_latteart.npz'))
+    FUSE[0] = True
+    try:
+        return _latteart(d, device)
+    finally:
+        FUSE[0] = False
+
+
+def _latteart(d, device):
+    from fluidlab_b200 import AgentInjector
     s = _sim(d, device, (0.0, -20.0, 0.0), dict(type='cylinder', xz_radius=0.2, xz_center=(0.5, 0.5), y_range=(0.34, 0.9)))
-    s.fuse_g2p2g = True
     common = dict(max_substeps_local=int(d['T']), max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
     agent = AgentInjector(**common)
     agent.add_effector(type='Injector', params=dict(radius=0.0075, flux=int(d['flux']), init_pos=(0.5, 0.5, 0.5), action_dim=3, inject_v=(0.0, -3.0, 0.0),
                                                     action_scale_p=(1.0, 1.0, 1.0), action_scale_v=(1.0, 1.0, 1.0), locally_random=True),
                        mesh_cfg=None, boundary_cfg=dict(type='cylinder', xz_radius=0.12, xz_center=(0.5, 0.5), y_range=(0.55, 0.55)))
     _drive(s, agent, agent.effectors[0], d)
-    assert s._can_fuse_injector()

@@ -356,6 +356,18 @@ def test_agent_scenes_equal_runs_of_the_real_reference_agents(emu, scene):
     getattr(cases, f'run_{scene}_case')(device='cpu')
 
 
+@pytest.mark.parametrize('scene', ['jetbot', 'pouring', 'icecream'])
+def test_agent_scenes_through_the_fused_path_equal_the_reference_runs(emu, scene):
+    """the same reference runs with MPMSimulator.fuse_g2p2g: 6-DOF injector + collector (JetBot), Rigid SDF collider at grid and particle level +
+    collector (Pouring), BallInjector with inject_till + gated Rigid collider + Static collider (IceCream)"""
+    import reference_scene_cases as cases
+    cases.FUSE[0] = True
+    try:
+        getattr(cases, f'run_{scene}_case')(device='cpu')
+    finally:
+        cases.FUSE[0] = False
+
+
 def test_device_adjoint_equals_finite_differences_through_the_reference_forward(emu):
     import reference_scene_cases as cases
     cases.run_cloud_adjoint_case(device='cpu')

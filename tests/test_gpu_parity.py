@@ -1016,3 +1016,16 @@ def test_slab_sharded_forward_with_neighbour_handshake(fuse):
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                         '--master-port', '29551', os.path.join(root, 'tests', 'run_slab_gpu.py')], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and 'SLAB_PARITY_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize('scene', ['jetbot', 'pouring', 'icecream'])
+def test_cuda_fused_path_matches_runs_of_the_real_reference_agents(scene):
+    """the reference's AgentJetBot / AgentPouring / AgentIceCreamDynamic runs again through MPMSimulator.fuse_g2p2g (particle-level agent.collide
+    and the collector test inside k_g2p2g, freshly injected particles scattered by k_p2g_injected); verified on the CPU execution-model shim"""
+    _need_gpu()
+    import reference_scene_cases as cases
+    cases.FUSE[0] = True
+    try:
+        getattr(cases, f'run_{scene}_case')(device=None)
+    finally:
+        cases.FUSE[0] = False
