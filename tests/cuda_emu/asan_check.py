@@ -73,6 +73,11 @@ import reference_scene_cases as cases
 for name in ('latteart', 'jetbot', 'pouring', 'icecream'):
     getattr(cases, f'run_{name}_case')(device='cpu')
     print('scene ok', name, flush=True)
+cases.FUSE[0] = True          # the same scenes through the g2p2g path (kAgent kernels, k_p2g_injected)
+for name in ('latteart', 'jetbot', 'pouring', 'icecream'):
+    getattr(cases, f'run_{name}_case')(device='cpu')
+    print('fused scene ok', name, flush=True)
+cases.FUSE[0] = False
 cases.run_cloud_adjoint_case(device='cpu')
 print('cloud adjoint ok', flush=True)
 # grad-mode fused forward + backward
