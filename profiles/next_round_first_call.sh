@@ -16,6 +16,7 @@ python bench.py --fuse-g2p2g 1 > gpurun_out/${tag}_bench_fused.json 2> gpurun_ou
 python bench.py --fuse-g2p2g 1 --sort-every 2 --bwd 0 --no-cpu > gpurun_out/${tag}_bench_fused_sort2.json 2> /dev/null   # the fused scatter sees older cell orders: does a shorter sort period pay?
 # 3. smoke solver phase timings (50 and 500 Jacobi sweeps at 128^3)
 python profiles/smoke_times.py > gpurun_out/${tag}_smoke_times.json 2> gpurun_out/${tag}_smoke_times.err
+python profiles/c1_rollout_times.py > gpurun_out/${tag}_c1_rollout.json 2> gpurun_out/${tag}_c1_rollout.err
 # 4. launch list + full capture of the fused kernel
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_fused.csv python bench.py --steps 3 --warmup 3 --bwd 0 --no-cpu --fuse-g2p2g 1 > gpurun_out/${tag}_ncu_fused.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_g2p2g -s 40 -c 1 -f -o gpurun_out/${tag}_k_g2p2g python bench.py --steps 3 --warmup 3 --bwd 0 --no-cpu --fuse-g2p2g 1 > gpurun_out/${tag}_ncu_g2p2g.log 2>&1

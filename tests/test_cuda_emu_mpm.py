@@ -490,3 +490,11 @@ def test_latteart_forward_backward_with_fused_injector_steps(emu):
         loss, grad = res[fuse]
         assert abs(loss - total) <= 1e-5 * abs(total), (fuse, loss, total)
         assert np.abs(og).max() > 1e-3 and rel(grad, og) < 1e-4, (fuse, rel(grad, og))
+
+
+def test_c1_rollout_timing_script_runs_on_the_emulated_device(emu):
+    """profiles/c1_rollout_times.py (LatteArt rollouts with the fused path off / on, queued for the next GPU round) at a reduced size: script sanity"""
+    sys.path.insert(0, os.path.join(harness.ROOT, 'profiles'))
+    import c1_rollout_times
+    out = c1_rollout_times.run(device='cpu', n_steps=2, reps=1, sync=lambda: None, n_milk=300, quality=0.25, T=40)
+    assert out['plain']['n_particles'] == out['fused']['n_particles'] > 300 and out['fused']['substeps_per_s'] > 0
