@@ -32,7 +32,8 @@ def _oracle(d, iters=None, prec=32):
 
 def _field(d, iters=None):
     from fluidlab_b200 import smoke as smoke_mod, meshes, macros as M
-    dev = torch.device('cuda', 0)
+    emu = os.environ.get('FLUIDLAB_CUDA_EMU') == '1'      # development aid: conftest.py routes the library to the CPU execution-model shim
+    dev = torch.device('cpu') if emu else torch.device('cuda', 0)
     Tsub = 40
     z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
     air = types.SimpleNamespace(pos=z(Tsub + 1, 3), quat=z(Tsub + 1, 4), s=z(Tsub + 1), r=z(Tsub + 1), gpos=z(Tsub + 1, 3), gquat=z(Tsub + 1, 4), gs=z(Tsub + 1), gr=z(Tsub + 1),
@@ -45,7 +46,7 @@ def _field(d, iters=None):
         statics.add_static(file='x.obj', material=M.PILLAR, has_dynamics=True, sdf=dict(voxels=vox, T_mesh_to_voxels=T))
     agent = types.SimpleNamespace(aircon=air)
     import ctypes as C
-    sim = types.SimpleNamespace(max_steps_local=4, agent=agent, device=dev, statics=statics, _stream=lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    sim = types.SimpleNamespace(max_steps_local=4, agent=agent, device=dev, statics=statics, _stream=(lambda: None) if emu else (lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     sf = smoke_mod.SmokeField(dim=3, ckpt_dest='gpu', res=int(d['res']), dt=float(d['dt']), solver_iters=int(d['iters']) if iters is None else iters, q_dim=int(d['q_dim']))
     sf.lower_y, sf.higher_y = int(d['lower_y']), int(d['higher_y'])
     sf.build(sim, agent)
