@@ -79,7 +79,7 @@ def test_smoke_backward_matches_the_oracle_and_reference_finite_differences():
     d = np.load(os.path.join(GOLDEN, 'reference_smoke.npz'))
     fd = np.load(os.path.join(GOLDEN, 'reference_smoke_fd.npz'))
     sf, air = _field(d)
-    o = _oracle(d, prec=64)
+    o = _oracle(d, prec=32)     # float32 like the device; the float64 side of the pin is the finite-difference fixture below
     st0 = {k: d['st0_' + k] for k in ('v', 'v_tmp', 'div', 'p', 'q')}
     sf.set_state(0, st0); o.set_state(0, st0)
     for s in range(2):
