@@ -30,7 +30,6 @@ The orchestration talks to the local simulator only through `MPMSimulator`'s ste
 tests/test_slab_cpu.py drives this same code on CPU (gloo, world_size 2) with an oracle-backed stand-in and checks forward AND backward
 against the single-domain oracle.
 """
-import os
 import numpy as np
 import torch
 import torch.distributed as dist
