@@ -136,6 +136,7 @@ _PROTOS = {
     "fmpm_g2p2g_collect": (_I, [vp, _I, _I, C.POINTER(FmpmCollector), vp]),
     "fmpm_substeps_fused": (_I, [vp, _I, _I, vp]),
     "fmpm_p2g_injected": (_I, [vp, _I, C.POINTER(FmpmInjector), _I, vp, _I, C.POINTER(FmpmCollector), vp]),
+    "fmpm_p2g_rigid": (_I, [vp, _I, _I, C.POINTER(FmpmCollector), vp]),
     "fmpm_clear_ring_slot": (_I, [vp, _I, vp]),
     "fmpm_p2g_store": (_I, [vp, _I, vp]),
     "fmpm_grid_op_store": (_I, [vp, _I, vp]),

@@ -270,12 +270,18 @@ __device__ __forceinline__ bool collector_takes(const FmpmCollector& c, const in
   const float rx = x[0] - c.cyl_center[0], rz = x[2] - c.cyl_center[1];
   return x[1] > c.upper[1] || x[1] < c.lower[1] || sqrtf(rx * rx + rz * rz + FMPM_EPS) > c.cyl_radius;
 }
+// particle of a MAT_RIGID body (body id in meta bits 16..23, FmpmBodies.info = (first, material class) per body)
+__device__ __forceinline__ bool rigid_body_slot(const int meta, const int* __restrict__ info, const int nb) {
+  const int b = (meta >> 16) & 0xff;
+  return (meta & 1) && b < nb && __ldg(info + 2 * b + 1) == FMPM_MAT_RIGID;
+}
 #ifndef G2P2G_MINB
 #define G2P2G_MINB P2G_MINB   // 96 registers at 5 CTAs of 4 warps; A/B other bounds with FMPM_DEFS=-DG2P2G_MINB=... (profiles/ab_variants.sh, PT_FUSED=1)
 #endif
 // kAgent: particle-level agent.collide and the collector test are compiled in (scenes with a Rigid effector and / or a collector agent)
 template <bool kWriteVC, bool kAgent>
-__global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KParams P, const int f, const FmpmCollector col, const int has_col) {
+__global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KParams P, const int f, const FmpmCollector col, const int has_col,
+                                                                              const int* __restrict__ body_info, const int n_bodies) {
   __shared__ ScatterSmem smem[P2G_WARPS];
   static_assert(sizeof(((ScatterSmem*)0)->rec) >= 9 * G2P_ZMAX * sizeof(float4), "the gather tile is staged in the scatter records' storage");
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -335,11 +341,14 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
       for (int d = 0; d < 3; d++) st.x[d] = x[d] + P.dt * st.v[d];   // advect_kernel MPM:505
       // collector agents act on frame f+1 BEFORE its p2g (MPM:521): a particle that left is tagged (used bit off, bit 1 on), does not
       // scatter, and the next substep's gather parks it — exactly what fmpm_collect(f+1) + k_p2g + k_g2p do on the unfused path
-      const bool taken = kAgent && has_col && collector_takes(col, meta, st.x);
+      // a particle of a MAT_RIGID body: its position of frame f+1 is only final after the body's shape matching (fmpm_advect_rigid(f), MPM:428-505),
+      // so it leaves here with the complete provisional frame; k_p2g_rigid applies the collector test, scatters it and writes F[f+2] after that pass
+      const bool rigid = kAgent && body_info != nullptr && rigid_body_slot(meta, body_info, n_bodies);
+      const bool taken = kAgent && has_col && !rigid && collector_takes(col, meta, st.x);
       st.meta = taken ? ((meta & ~1) | 2) : meta;
       // ---- p2g of frame f+1 (MPM:254-264, 331-378)
       int b1[3]; float fx1[3];
-      const bool ok1 = !taken && base_fx(P, st.x, b1, fx1);
+      const bool ok1 = !taken && !rigid && base_fx(P, st.x, b1, fx1);
       if (kWriteVC || !ok1) store_A(P.pa, P, f + 1, s, st.x, st.meta, st.v, st.C);
       else P.pa[pa_idx(P, f + 1, 0, s)] = make_float4(st.x[0], st.x[1], st.x[2], __int_as_float(st.meta));
       if (ok1) {
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
         for (int i = 0; i < 3; i++) q[i] = m * st.v[i] - (B[i * 3] * fx1[0] + B[i * 3 + 1] * fx1[1] + B[i * 3 + 2] * fx1[2]);
         key = pack_key(b1);
         p2g_store_F(P, f + 2, s, K.Fn);
-      } else {
+      } else if (!rigid) {
         p2g_store_F(P, f + 2, s, st.F);
       }
     }
@@ -369,12 +378,8 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
 // p2g of the few particles an injector has just activated in frame f (fused steps with an injector agent: the g2p2g kernel of the previous
 // substep ran before agent.act wrote them, so their contribution to the grid of frame f is added here — flux particles, plain vector
 // reductions, no window).  Same arithmetic as k_p2g for one particle; also writes F[f+1] and flags the touched blocks.
-__global__ void k_p2g_injected(const KParams P, const int f, const FmpmInjector inj, const int act_id, const int* __restrict__ inv, const FmpmCollector col,
-                               const int has_col) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= inj.flux) return;
-  const int pid = ((const int*)inj.act_range)[act_id + i];
-  const int s = inv ? inv[pid] : pid;
+// one particle's p2g with plain vector reductions (no window): used for the few particles the fused steps handle outside k_g2p2g
+__device__ __forceinline__ void p2g_one_particle(const KParams& P, const int f, const int s, const FmpmCollector& col, const int has_col) {
   PRaw R; p2g_load_raw(P, f, s, R);
   PState st; p2g_unpack(R, st);
   int b[3]; float fx[3];
@@ -402,6 +407,22 @@ __global__ void k_p2g_injected(const KParams P, const int f, const FmpmInjector 
     P.blk_flags[((gi >> 3) * nb + (gj >> 3)) * nb + (gk >> 3)] = 1;
   }
   p2g_store_F(P, f + 1, s, K.Fn);
+}
+__global__ void k_p2g_injected(const KParams P, const int f, const FmpmInjector inj, const int act_id, const int* __restrict__ inv, const FmpmCollector col,
+                               const int has_col) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= inj.flux) return;
+  const int pid = ((const int*)inj.act_range)[act_id + i];
+  p2g_one_particle(P, f, inv ? inv[pid] : pid, col, has_col);
+}
+// particles of MAT_RIGID bodies in fused steps: k_g2p2g leaves their scatter out (their position of frame f is only final after the body's
+// shape matching, fmpm_advect_rigid(f-1)); this kernel adds it, after that pass and before grid_op(f)
+__global__ void __launch_bounds__(128) k_p2g_rigid(const KParams P, const int f, const int* __restrict__ body_info, const int n_bodies, const FmpmCollector col,
+                                                    const int has_col) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.N) return;
+  const int meta = __float_as_int(P.pa[pa_idx(P, f, 0, s)].w);
+  if (rigid_body_slot(meta, body_info, n_bodies)) p2g_one_particle(P, f, s, col, has_col);
 }
 
 // =============================================================================================
@@ -542,16 +563,15 @@ extern "C" int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream) { re
 extern "C" int fmpm_g2p2g_collect(FmpmHandle* h, int f, int write_vc, const FmpmCollector* col, void* stream) { return g2p2g_impl(h, f, write_vc, col, stream); }
 static int g2p2g_impl(FmpmHandle* h, int f, int write_vc, const FmpmCollector* col, void* stream) {
   if (check_bound(h, "fmpm_g2p2g") || check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_g2p2g")) return 1;
-  if (h->bodies.n_bodies > 0) {
-    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: not available with MAT_RIGID bodies"); return 1;
-  }
+  if (h->bodies.n_bodies > 0 && h->slab.enabled) { snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: MAT_RIGID bodies are not available in x-slab mode"); return 1; }
   KParams P = make_kparams(h, -1, f + 1);   // x-slab mode: the scatter goes to the accumulator / block flags / peers of substep parity f+1
   if (P.N == 0) return 0;
   const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
   const FmpmCollector c = col ? *col : no_collector();
-  const bool agent = col != nullptr || (h->col.has_rigid && h->col.collide_type != 1);
-  if (write_vc) { if (agent) FMPM_LAUNCH(G2P2G_K(true, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0); else FMPM_LAUNCH(G2P2G_K(true, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0); }
-  else { if (agent) FMPM_LAUNCH(G2P2G_K(false, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0); else FMPM_LAUNCH(G2P2G_K(false, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0); }
+  const int nbod = h->bodies.n_bodies; const int* binfo = nbod > 0 ? (const int*)h->bodies.info : nullptr;
+  const bool agent = col != nullptr || (h->col.has_rigid && h->col.collide_type != 1) || nbod > 0;
+  if (write_vc) { if (agent) FMPM_LAUNCH(G2P2G_K(true, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0, binfo, nbod); else FMPM_LAUNCH(G2P2G_K(true, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0, binfo, 0); }
+  else { if (agent) FMPM_LAUNCH(G2P2G_K(false, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0, binfo, nbod); else FMPM_LAUNCH(G2P2G_K(false, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0, binfo, 0); }
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p2g");
   return 0;
 }
@@ -559,16 +579,15 @@ static int g2p2g_impl(FmpmHandle* h, int f, int write_vc, const FmpmCollector* c
 // every frame is written completely (the backward pass reads x, v, C, F of every frame): 148 B instead of 212 B per particle and substep
 static int g2p2g_store_impl(FmpmHandle* h, int f, void* stream, const FmpmCollector* col = nullptr) {
   if (check_bound(h, "fmpm_g2p2g(store)") || check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_g2p2g(store)")) return 1;
-  if (h->bodies.n_bodies > 0 || h->slab.enabled) {
-    snprintf(h->err, sizeof(h->err), "fmpm_g2p2g(store): not available with MAT_RIGID bodies or x-slabs"); return 1;
-  }
+  if (h->slab.enabled) { snprintf(h->err, sizeof(h->err), "fmpm_g2p2g(store): not available in x-slab mode"); return 1; }
   KParams P = make_kparams(h, f + 1);            // scatter target: accumulator + block flags of slot f+1
   P.grid_v = make_kparams(h, f).grid_v;          // gather source: v_out of slot f
   if (P.N == 0) return 0;
   const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
   const FmpmCollector c = col ? *col : no_collector();
-  if (col != nullptr || (h->col.has_rigid && h->col.collide_type != 1)) FMPM_LAUNCH(G2P2G_K(true, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0);
-  else FMPM_LAUNCH(G2P2G_K(true, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0);
+  const int nbod = h->bodies.n_bodies; const int* binfo = nbod > 0 ? (const int*)h->bodies.info : nullptr;
+  if (col != nullptr || (h->col.has_rigid && h->col.collide_type != 1) || nbod > 0) FMPM_LAUNCH(G2P2G_K(true, true), blocks, P2G_WARPS * 32, 0, stream, P, f, c, col ? 1 : 0, binfo, nbod);
+  else FMPM_LAUNCH(G2P2G_K(true, false), blocks, P2G_WARPS * 32, 0, stream, P, f, c, 0, binfo, 0);
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p2g(store)");
   return 0;
 }
@@ -601,20 +620,26 @@ extern "C" int fmpm_substeps_fused_store(FmpmHandle* h, int f0, int n, void* str
     FMPM_LAUNCH(k_clear_blocks, grid, 256, 0, stream, P);   // previous occupant of slot f
     FMPM_CHECK_LAUNCH(h, "fmpm_substeps_fused_store(clear)");
     if (i == 0) { if (fmpm_p2g_impl(h, f, 1, f, stream)) return 1; }
-    else if (g2p2g_store_impl(h, f - 1, stream)) return 1;
+    else {
+      if (g2p2g_store_impl(h, f - 1, stream)) return 1;
+      if (h->bodies.n_bodies > 0 && (fmpm_advect_rigid_impl(h, f - 1, stream) || fmpm_p2g_rigid(h, f, f, nullptr, stream))) return 1;
+    }
     if (fmpm_grid_op_impl(h, f, 0, 0, f, stream)) return 1;
   }
-  return fmpm_g2p_impl(h, f0 + n - 1, f0 + n - 1, stream);
+  if (fmpm_g2p_impl(h, f0 + n - 1, f0 + n - 1, stream)) return 1;
+  return fmpm_advect_rigid_impl(h, f0 + n - 1, stream);
 }
 // n forward substeps f0 .. f0+n-1 with the inner g2p / p2g pairs fused: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1).
 // Frames f0 and f0+n are complete; the frames in between hold x, used and F only.  The grid must be clear on entry (as for fmpm_substep).
 extern "C" int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream) {
   if (n < 1) { if (h) snprintf(h->err, sizeof(h->err), "fmpm_substeps_fused: n must be >= 1"); return 1; }
   if (fmpm_p2g(h, f0, 1, stream)) return 1;
-  for (int i = 0; i + 1 < n; i++)
+  for (int i = 0; i + 1 < n; i++) {
     if (fmpm_grid_op(h, f0 + i, 1, stream) || fmpm_g2p2g(h, f0 + i, 0, stream)) return 1;
-  if (fmpm_grid_op(h, f0 + n - 1, 1, stream)) return 1;
-  return fmpm_g2p(h, f0 + n - 1, stream);
+    if (h->bodies.n_bodies > 0 && (fmpm_advect_rigid_impl(h, f0 + i, stream) || fmpm_p2g_rigid(h, f0 + i + 1, -1, nullptr, stream))) return 1;
+  }
+  if (fmpm_grid_op(h, f0 + n - 1, 1, stream) || fmpm_g2p(h, f0 + n - 1, stream)) return 1;
+  return fmpm_advect_rigid_impl(h, f0 + n - 1, stream);
 }
 
 extern "C" int fmpm_substep(FmpmHandle* h, int f, void* stream) {
@@ -661,6 +686,16 @@ extern "C" int fmpm_p2g_injected(FmpmHandle* h, int f, const FmpmInjector* inj, 
   KParams P = make_kparams(h, ring_slot);   // ring_slot >= 0: the accumulator / block flags of that slot of the per-frame ring (grad mode)
   FMPM_LAUNCH(k_p2g_injected, (inj->flux + 31) / 32, 32, 0, stream, P, f, *inj, act_id, (const int*)inv, col ? *col : no_collector(), col ? 1 : 0);
   FMPM_CHECK_LAUNCH(h, "fmpm_p2g_injected");
+  return 0;
+}
+// fused steps with MAT_RIGID bodies: scatter their particles of frame f (after fmpm_advect_rigid(f-1) fixed their positions), before fmpm_grid_op(f)
+extern "C" int fmpm_p2g_rigid(FmpmHandle* h, int f, int ring_slot, const FmpmCollector* col, void* stream) {
+  if (check_bound(h, "fmpm_p2g_rigid") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_p2g_rigid")) return 1;
+  if (h->bodies.n_bodies == 0) return 0;
+  KParams P = make_kparams(h, ring_slot);
+  if (P.N == 0) return 0;
+  FMPM_LAUNCH(k_p2g_rigid, (P.N + 127) / 128, 128, 0, stream, P, f, (const int*)h->bodies.info, h->bodies.n_bodies, col ? *col : no_collector(), col ? 1 : 0);
+  FMPM_CHECK_LAUNCH(h, "fmpm_p2g_rigid");
   return 0;
 }
 extern "C" int fmpm_inject(FmpmHandle* h, int f, const FmpmInjector* inj, const FmpmEffector* e, int act_id, int rand_row,

@@ -413,17 +413,18 @@ class MPMSimulator:
         return b.inv[ids.long()].to(torch.int32).contiguous()
 
     def _can_fuse(self):
-        """g2p2g fusion applies to steps without an agent or MAT_RIGID bodies: forward-only (fmpm_substeps_fused) and, in grad mode, the
-        stored-grid path (fmpm_substeps_fused_store); not the recompute path (csrc/fmpm_forward.cu: k_g2p2g)"""
-        if not bool(getattr(self, 'fuse_g2p2g', False)) or getattr(self, '_has_rigid_bodies', False) or self.agent is not None:
+        """g2p2g fusion of steps without an agent: forward-only (fmpm_substeps_fused) and, in grad mode, the stored-grid path
+        (fmpm_substeps_fused_store); not the recompute path (csrc/fmpm_forward.cu: k_g2p2g).  Particles of MAT_RIGID bodies go through
+        the gather half only; their scatter follows the body's shape matching (fmpm_advect_rigid -> fmpm_p2g_rigid)."""
+        if not bool(getattr(self, 'fuse_g2p2g', False)) or self.agent is not None:
             return False
         return (not self.grad_enabled) or self._storing()
 
     def _can_fuse_injector(self):
         """steps WITH an agent: the fused g2p2g kernels (particle-level agent.collide and the collector's test compiled in where the agent has
         them) plus a tiny scatter of the particles an injector activates; forward-only and, in grad mode, the stored-grid path.  Covers every
-        agent of agents.py; MAT_RIGID bodies (their advect pass needs complete frames) keep the unfused path."""
-        if not (bool(getattr(self, 'fuse_g2p2g', False)) and not getattr(self, '_has_rigid_bodies', False) and self.agent is not None and self.has_particles):
+        agent of agents.py, with or without MAT_RIGID bodies (their particles scatter after the body's shape matching: fmpm_p2g_rigid)."""
+        if not (bool(getattr(self, 'fuse_g2p2g', False)) and self.agent is not None and self.has_particles):
             return False
         return (not self.grad_enabled) or self._storing()
 
@@ -458,6 +459,10 @@ class MPMSimulator:
             else:
                 self._ck(L.fmpm_grid_op(h, f, 1, st()), 'fmpm_grid_op')
                 self._ck(L.fmpm_g2p(h, f, st()) if last else L.fmpm_g2p2g_collect(h, f, 0, colp, st()), 'fmpm_g2p2g')
+            if self._has_rigid_bodies:   # shape matching fixes x[f+1] of the bodies' particles (MPM:428-505), then their scatter of frame f+1
+                self._ck(L.fmpm_advect_rigid(h, f, st()), 'fmpm_advect_rigid')
+                if not last:
+                    self._ck(L.fmpm_p2g_rigid(h, f + 1, (f + 1) if store else -1, colp, st()), 'fmpm_p2g_rigid')
             self._frame_ord[f + 1] = self._frame_ord[f]
             self._ring_valid[f] = store
             act_id = None if inj is None else inj.act_id[f]

@@ -191,7 +191,7 @@ int fmpm_substep(FmpmHandle* h, int f, void* stream);                  /* p2g, g
 int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, but the grids of frame f stay in ring slot f */
 /* forward-only fusion (no reference counterpart): g2p of frame f + p2g of frame f+1 in one kernel — v, C and x stay in registers
  * between the gather and the next scatter (104 B instead of 212 B per particle and substep).  write_vc = 0: v and C of frame f+1 are not
- * materialised.  Not available with MAT_RIGID bodies (their advect pass needs the complete frame).  x-slab mode: the scatter half behaves like fmpm_p2g(f+1)
+ * materialised (particles of MAT_RIGID bodies always get the complete frame: fmpm_advect_rigid(f) reads it, then fmpm_p2g_rigid(f+1) scatters them).  x-slab mode: the scatter half behaves like fmpm_p2g(f+1)
  * (peer reductions into the neighbours' accumulators of parity f+1): synchronise the ranks before fmpm_grid_op(f+1). */
 int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream);
 /* n substeps f0..f0+n-1: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1); frames f0 and f0+n are complete */
@@ -227,6 +227,7 @@ int fmpm_clear_ring_slot(FmpmHandle* h, int f, void* stream);
 int fmpm_p2g_store(FmpmHandle* h, int f, void* stream);
 int fmpm_grid_op_store(FmpmHandle* h, int f, void* stream);
 int fmpm_g2p_store(FmpmHandle* h, int f, void* stream);
+int fmpm_p2g_rigid(FmpmHandle* h, int f, int ring_slot, const FmpmCollector* col /* or NULL */, void* stream);   /* fused steps with MAT_RIGID bodies: their particles' scatter of frame f, after fmpm_advect_rigid(f-1) */
 int fmpm_g2p2g_store(FmpmHandle* h, int f, const FmpmCollector* col /* or NULL */, void* stream);       /* gathers from slot f, scatters into slot f+1 (cleared before), writes frame f+1 completely */
 
 /* ---- backward substep, MPM:535-552 ------------------------------------------------------------ */

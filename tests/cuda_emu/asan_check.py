@@ -88,3 +88,18 @@ s.enable_grad(); s.step(None)
 s.reset_grad(); z9 = np.zeros((N, 3, 3), np.float32); s.set_grad(rng.randn(N, 3).astype(np.float32), np.zeros((N, 3), np.float32), z9, z9)
 s.step_grad(None)
 print('grad-mode fused ok', flush=True)
+# MAT_RIGID bodies through the fused steps (k_g2p2g gather half, fmpm_advect_rigid, k_p2g_rigid), forward-only and grad mode
+dr = np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_run_rigid_bodies.npz'))
+Pr = make_particles(dr['x0'], dr['mat'], int(dr['n_grid']))
+Pr['body_id'] = dr['body_id']; Pr['bodies'] = {'n': 4}
+for grad in (False, True):
+    s = MPMSimulator(dim=3, quality=int(dr['n_grid']) / 64, gravity=(0, -10, 0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+    s.use_graphs = False; s.fuse_g2p2g = True
+    s.setup_boundary(type='cylinder', xz_radius=float(dr['xz_radius']), xz_center=tuple(dr['xz_center']), y_range=tuple(dr['y_range'])); s.build(None, None, [], Pr)
+    if grad: s.enable_grad()
+    s.setframe(0, dr['x0'], dr['v0'], dr['C0'], dr['F0'], np.ones(len(dr['x0']), np.int32)); s.sort_frame(0)
+    s.step(None)
+    if grad:
+        Nr = len(dr['x0']); z9 = np.zeros((Nr, 3, 3), np.float32)
+        s.reset_grad(); s.set_grad(rng.randn(Nr, 3).astype(np.float32), np.zeros((Nr, 3), np.float32), z9, z9); s.step_grad(None)
+    print('rigid fused ok grad', grad, flush=True)

@@ -507,10 +507,10 @@ def test_gpu_marked_parity_tests_pass_on_the_shim():
     C5's 8M particles — but take minutes and tens of GB, so they are left to manual runs.)"""
     import subprocess
     sel = ('forward_phases or substep_grad_matches or state_io or dloss_daction_latteart or out_of_grid or library_error or ragged or no_used or reference_kernels '
-           'or reference_agents or fused_path or finite_differences or golden or smoke_forward or smoke_backward or real_reference_stack')
+           'or reference_agents or fused_path or finite_differences or golden or rigid_material_bodies or smoke_forward or smoke_backward or real_reference_stack')
     env = dict(os.environ, FLUIDLAB_CUDA_EMU='1')
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(HERE, 'test_gpu_parity.py'), os.path.join(HERE, 'test_golden.py'), os.path.join(HERE, 'test_zz_smoke_gpu.py'),
                         '-m', 'gpu', '-q', '-x', '-k', sel, '-p', 'no:cacheprovider'], capture_output=True, text=True, timeout=1500, env=env, cwd=harness.ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''
     assert r.returncode == 0 and ' passed' in tail and 'failed' not in tail, r.stdout[-3000:] + r.stderr[-1000:]
-    assert int(tail.split(' passed')[0].split()[-1]) >= 50, tail
+    assert int(tail.split(' passed')[0].split()[-1]) >= 56, tail

@@ -510,9 +510,11 @@ def _rigid_bodies_scene(rng, n_grid=32):
     return P, bid
 
 
-def test_rigid_material_bodies_forward_and_adjoint():
+@pytest.mark.parametrize('fuse', [False, True], ids=['unfused', 'g2p2g'])
+def test_rigid_material_bodies_forward_and_adjoint(fuse):
     """MAT_RIGID bodies (shape matching, MPM:449-505) and advect_grad (MPM:436-447, manual SVD adjoint :485-489): 20 substeps
-    forward over two cell-sort epochs (CUDA-graph path), then the adjoint back to frame 0, against the oracle."""
+    forward over two cell-sort epochs (CUDA-graph path), then the adjoint back to frame 0, against the oracle.  fuse: the g2p2g
+    steps, where the bodies' particles take the gather half only and scatter after the shape matching (fmpm_p2g_rigid)."""
     _need_gpu()
     from oracle import oracle as orc
     rng = np.random.RandomState(21)
@@ -524,12 +526,13 @@ def test_rigid_material_bodies_forward_and_adjoint():
         o.set_bodies(bid, 4)
     st = random_state(P, rng, amp_F=0.01, amp_C=2.0, amp_v=0.4)
     s.enable_grad()
+    s.fuse_g2p2g = fuse
     set_both(o64, s, st)
     o32.set_frame(0, st['x'], st['v'], st['C'], st['F'], st['used'])
     for f in range(n_sub):
         o64.substep(f); o32.substep(f)
     s.step(None); s.step(None)
-    assert s.cur_substep_local == n_sub
+    assert s.cur_substep_local == n_sub and s._can_fuse() == fuse
     r64, r32, got = o64.get_frame(n_sub), o32.get_frame(n_sub), s.get_state()
     for k, bar in (('x', 1e-5), ('v', 1e-4), ('F', 1e-5)):
         tol = max(bar, 3 * rel(r32[k], r64[k]))
@@ -930,12 +933,15 @@ def test_c3_latteart_two_material_fwd_bwd_full_size():
     assert rel(grad, g64) < 1e-4, (rel(grad, g64), grad, g64)
 
 
+@pytest.mark.parametrize('path', ['substep', 'g2p2g'])
 @pytest.mark.parametrize('scene', ['multimat', 'rigid_bodies', 'locked'])
-def test_cuda_matches_runs_of_the_real_reference_kernels(scene):
+def test_cuda_matches_runs_of_the_real_reference_kernels(scene, path):
     """tests/golden/reference_run_<scene>.npz hold particle states produced by the UNMODIFIED reference kernels executed on a NumPy emulation
     of the Taichi API (tests/golden/make_reference_run.py).  The CUDA path is compared with them directly (not through the oracle):
     every material class + cube walls + unused slots (12 substeps); two MAT_RIGID bodies + water + elastic in a cylinder (10 substeps);
-    transporting_env's boundary options (restitution + lock_dims=[2]) with water and a MAT_RIGID body hitting the walls (10 substeps)."""
+    transporting_env's boundary options (restitution + lock_dims=[2]) with water and a MAT_RIGID body hitting the walls (10 substeps).
+    path 'g2p2g': the same substeps through fmpm_substeps_fused (gather of f + scatter of f+1 in one kernel; the MAT_RIGID bodies' particles
+    scatter after their shape matching, fmpm_p2g_rigid)."""
     _need_gpu()
     import os
     from fluidlab_b200 import MPMSimulator
@@ -958,8 +964,13 @@ def test_cuda_matches_runs_of_the_real_reference_kernels(scene):
     s.build(None, None, [], P)
     s.setframe(0, d['x0'], d['v0'], d['C0'], d['F0'], used0)
     s.sort_frame(0)
-    for f in range(n_sub):
-        s.substep(f, True)
+    if path == 'g2p2g':
+        s._ck(s._lib.fmpm_substeps_fused(s._h, 0, n_sub, s._stream()), 'fmpm_substeps_fused')
+        for f in range(n_sub):
+            s._frame_ord[f + 1] = s._frame_ord[f]
+    else:
+        for f in range(n_sub):
+            s.substep(f, True)
     fr = s.readframe(n_sub)
     assert np.array_equal(fr['used'], d['ref_used'])
     u = fr['used'] != 0
