@@ -6,6 +6,7 @@ return that library instead of the nvcc-built libfluidmpm.so and (3) replaces th
 events, pinned memory, memory info) by no-ops, so `MPMSimulator(device='cpu')`, `TaichiEnv`, `SmokeField` and `SlabMPMSimulator` drive the
 real kernel code on CPU tensors.  Nothing here is reachable from the product; `disable()` undoes every patch."""
 import ctypes as C
+import hashlib
 import os
 import subprocess
 
@@ -19,13 +20,17 @@ _state = {}
 
 
 def build_library():
-    out = os.path.join(EMU_DIR, '_build', 'libfluidmpm_emu.so')
+    # CUEMU_CXXFLAGS: extra compiler flags, e.g. "-mfma -ffp-contract=fast" for a build that contracts a*b+c into FMAs as nvcc does
+    # (a second rounding variant of every kernel: parity bars that only hold for one instruction selection show up here, before the GPU)
+    extra = os.environ.get('CUEMU_CXXFLAGS', '').split()
+    tag = ('_' + hashlib.md5(' '.join(extra).encode()).hexdigest()[:8]) if extra else ''
+    out = os.path.join(EMU_DIR, '_build', f'libfluidmpm_emu{tag}.so')
     os.makedirs(os.path.dirname(out), exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))] + [os.path.join(EMU_DIR, 'cuda_runtime.h'),
             os.path.join(EMU_DIR, 'cub', 'device', 'device_radix_sort.cuh'), os.path.join(ROOT, 'include', 'fluidmpm.h'), os.path.join(ROOT, 'include', 'fluidsmoke.h')]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         tmp = out + f'.{os.getpid()}.tmp'
-        subprocess.check_call(['/usr/bin/g++', '-std=c++20', '-O1', '-fPIC', '-shared', '-pthread', '-x', 'c++', '-I', EMU_DIR, '-DFMPM_BUILD'] +
+        subprocess.check_call(['/usr/bin/g++', '-std=c++20', '-O1', '-fPIC', '-shared', '-pthread'] + extra + ['-x', 'c++', '-I', EMU_DIR, '-DFMPM_BUILD'] +
                               [os.path.join(CSRC, s) for s in SRCS] + ['-o', tmp])
         os.replace(tmp, out)
     return out

@@ -500,15 +500,20 @@ def test_c1_rollout_timing_script_runs_on_the_emulated_device(emu):
     assert out['plain']['n_particles'] == out['fused']['n_particles'] > 300 and out['fused']['substeps_per_s'] > 0
 
 
-def test_gpu_marked_parity_tests_pass_on_the_shim():
+@pytest.mark.parametrize('cxxflags', ['', '-O2 -mfma -ffp-contract=fast'], ids=['default', 'fma-contracted'])
+def test_gpu_marked_parity_tests_pass_on_the_shim(cxxflags):
     """the `-m gpu` parity tests THEMSELVES (tests/test_gpu_parity.py, test_golden.py, test_zz_smoke_gpu.py — the ones the B200 box runs), small
     scenes only, in a subprocess with FLUIDLAB_CUDA_EMU=1 (tests/conftest.py routes the library to the shim): whatever they assert about the
     kernels holds for the kernel code as written; what remains for the GPU is the hardware.  (The full-size ones pass on the shim too — up to
-    C5's 8M particles — but take minutes and tens of GB, so they are left to manual runs.)"""
+    C5's 8M particles — but take minutes and tens of GB, so they are left to manual runs.)
+    'fma-contracted': the same on a shim build that contracts a*b+c into FMAs the way nvcc does (CUEMU_CXXFLAGS, tests/cuda_emu/harness.py) — a second
+    rounding variant of every kernel, so a parity bar that only holds for one instruction selection fails here rather than on the GPU box."""
     import subprocess
+    if cxxflags and ' fma ' not in open('/proc/cpuinfo').read().replace('\n', ' '):
+        pytest.skip('host CPU has no FMA')
     sel = ('forward_phases or substep_grad_matches or state_io or dloss_daction_latteart or out_of_grid or library_error or ragged or no_used or reference_kernels '
            'or reference_agents or fused_path or finite_differences or golden or rigid_material_bodies or smoke_forward or smoke_backward or real_reference_stack')
-    env = dict(os.environ, FLUIDLAB_CUDA_EMU='1')
+    env = dict(os.environ, FLUIDLAB_CUDA_EMU='1', CUEMU_CXXFLAGS=cxxflags)
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(HERE, 'test_gpu_parity.py'), os.path.join(HERE, 'test_golden.py'), os.path.join(HERE, 'test_zz_smoke_gpu.py'),
                         '-m', 'gpu', '-q', '-x', '-k', sel, '-p', 'no:cacheprovider'], capture_output=True, text=True, timeout=1500, env=env, cwd=harness.ROOT)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''
