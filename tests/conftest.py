@@ -28,6 +28,19 @@ def pytest_configure(config):
         simulator.MPMSimulator.__init__ = emu_init
 
 
+# `-m gpu` tests written after round 1's GPU minutes were spent: verified on the CPU execution-model shim (tests/cuda_emu), never yet run on a
+# B200.  They are collected AFTER the hardware-validated ones, so that with `-x` a first-run surprise in a new path does not hide the state of
+# the paths that have already been measured.  Remove a pattern once its tests have passed on hardware.
+FIRST_HARDWARE_RUN_PENDING = ('g2p2g', '_fused', 'fused_path', 'reference_agents', 'finite_differences', 'neighbour_handshake', 'slab_sharded_backward', '-locked', 'locked-',
+                              'test_zz_smoke_gpu')
+
+
+def pytest_collection_modifyitems(config, items):
+    def pending(item):
+        return item.get_closest_marker('gpu') is not None and any(p in item.nodeid for p in FIRST_HARDWARE_RUN_PENDING)
+    items.sort(key=pending)   # stable: the order inside each group is unchanged
+
+
 def make_particles(x, mat_ids, n_grid, used=None, rho=None):
     """Particle dict in the format OracleSim / the CUDA simulator build() expect (MPM:136-175)."""
     from fluidlab_b200.macros import MU, LAMDA, RHO, MAT_CLASS
