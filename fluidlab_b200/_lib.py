@@ -111,6 +111,11 @@ class FsmkAircon(C.Structure):
 
 
 _I, _F, _U = C.c_int, C.c_float, C.c_uint
+class FmpmAdamCfg(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("lr", "beta_1", "beta_2", "epsilon", "bias_1", "bias_2", "clip_lo", "clip_hi")] + [
+        ("rows", C.c_int), ("cols", C.c_int), ("fix_dim_mask", C.c_uint), ("reserved", C.c_int)]
+
+
 _PROTOS = {
     "fmpm_set_bodies": (_I, [vp, C.POINTER(FmpmBodies)]),
     "fmpm_collect": (_I, [vp, _I, C.POINTER(FmpmCollector), vp]),
@@ -171,6 +176,7 @@ _PROTOS = {
     "fmpm_loss_chamfer": (_I, [vp, _I, vp, vp, _U, _F, vp, vp]),
     "fmpm_loss_chamfer_grad": (_I, [vp, _I, _I, vp, vp, _U, _F, vp]),
 }
+_PROTOS["fmpm_adam_step"] = (_I, [vp, C.POINTER(FmpmAdamCfg), vp, vp, vp, vp, vp, vp])
 EXPORTS = tuple(_PROTOS.keys())
 _SMOKE_PROTOS = {
     "fsmk_create": (_I, [C.POINTER(FsmkConfig), C.POINTER(vp)]),

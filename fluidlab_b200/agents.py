@@ -4,6 +4,7 @@ agents/agent_pouring.py / agents/agent_jetbot.py.  `collide` of injector agents 
 collision kernel is involved for them."""
 import ctypes as C
 import numpy as np
+import torch
 from . import _lib
 from .boundaries import create_boundary
 from .macros import WATER
@@ -84,6 +85,11 @@ class Agent:
     def get_grad(self, n):
         grads = [g for g in (e.get_action_grad(0, n) for e in self.effectors) if g is not None]
         return np.concatenate(grads, axis=1)
+
+    def get_grad_device(self, n):
+        """get_grad as a device tensor (float32 [n + 1, action_dim]): feeds optimizer.TrainablePolicy.optimize without leaving the GPU"""
+        grads = [g for g in (e.get_action_grad_device(0, n) for e in self.effectors) if g is not None]
+        return torch.cat(grads, dim=1).contiguous()
 
     def move(self, f):
         for e in self.effectors:
@@ -206,6 +212,9 @@ class AgentIceCreamDynamic(Agent):
 
     def get_grad(self, n):
         return self.rigid.get_action_grad(0, n)
+
+    def get_grad_device(self, n):
+        return self.rigid.get_action_grad_device(0, n).contiguous()
 
 
 class _Collector:

@@ -582,3 +582,48 @@ extern "C" int fmpm_loss_chamfer_grad(FmpmHandle* h, int f, int g, const void* i
   FMPM_CHECK_LAUNCH(h, "fmpm_loss_chamfer_grad");
   return 0;
 }
+
+// =============================================================================================
+// Adam on the composite action table (optimizer/optim.py:22-41, TrainablePolicy.optimize policies.py:152-164)
+// =============================================================================================
+// NumPy's evaluation order and dtypes: `(1 - beta) * grads` and `grads * grads` are float32 products (grads is float32, the Python scalar is
+// weak), everything that touches the float64 moment buffers is float64; each operation rounds once (the _rn intrinsics keep ptxas from
+// contracting a*b+c), so the table stays bit-identical to the reference's across iterations.
+#ifdef FMPM_HOST_EMU
+static inline double adam_dmul(double a, double b) { volatile double r = a * b; return r; }
+static inline double adam_dadd(double a, double b) { volatile double r = a + b; return r; }
+static inline float adam_fmul(float a, float b) { volatile float r = a * b; return r; }
+static inline double adam_ddiv(double a, double b) { return a / b; }
+static inline double adam_dsqrt(double a) { return sqrt(a); }
+#else
+__device__ __forceinline__ double adam_dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double adam_dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float adam_fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double adam_ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double adam_dsqrt(double a) { return __dsqrt_rn(a); }
+#endif
+__global__ void k_adam_step(const FmpmAdamCfg c, double* __restrict__ params, double* __restrict__ m, double* __restrict__ v, const float* __restrict__ grads,
+                            const unsigned char* __restrict__ trainable) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.rows * c.cols) return;
+  const int row = i / c.cols, col = i % c.cols;
+  float g = grads[i];
+  if ((trainable && !trainable[row]) || (col < 32 && ((c.fix_dim_mask >> col) & 1u))) g = 0.f;
+  const double m_t = adam_dadd(adam_dmul(c.beta_1, m[i]), (double)adam_fmul((float)(1.0 - c.beta_1), g));
+  const double v_t = adam_dadd(adam_dmul(c.beta_2, v[i]), (double)adam_fmul((float)(1.0 - c.beta_2), adam_fmul(g, g)));
+  m[i] = m_t; v[i] = v_t;
+  const double m_cap = adam_ddiv(m_t, c.bias_1), v_cap = adam_ddiv(v_t, c.bias_2);
+  double p = adam_dadd(params[i], -adam_ddiv(adam_dmul(c.lr, m_cap), adam_dadd(adam_dsqrt(v_cap), c.epsilon)));
+  if (row < c.rows - 1) p = p < c.clip_lo ? c.clip_lo : (p > c.clip_hi ? c.clip_hi : p);   // ndarray.clip: min(max(p, lo), hi)
+  params[i] = p;
+}
+extern "C" int fmpm_adam_step(FmpmHandle* h, const FmpmAdamCfg* c, void* params, void* m, void* v, const void* grads, const void* trainable, void* stream) {
+  if (!h) return 1;
+  if (!c || !params || !m || !v || !grads || c->rows < 1 || c->cols < 1 || c->cols > 32) {
+    snprintf(h->err, sizeof(h->err), "fmpm_adam_step: null buffer or bad shape (rows >= 1, 1 <= cols <= 32)"); return 1;
+  }
+  const int n = c->rows * c->cols;
+  FMPM_LAUNCH(k_adam_step, (n + 127) / 128, 128, 0, stream, *c, (double*)params, (double*)m, (double*)v, (const float*)grads, (const unsigned char*)trainable);
+  FMPM_CHECK_LAUNCH(h, "fmpm_adam_step");
+  return 0;
+}

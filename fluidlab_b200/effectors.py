@@ -128,6 +128,12 @@ class Effector:
             return grad
         return None
 
+    def get_action_grad_device(self, s, n):
+        """get_action_grad without the device->host copy: float32 [n + 1, action_dim] on the device (or None)"""
+        if self.action_dim > 0:
+            return torch.cat([self.action_buffer_grad[s:s + n, :self.action_dim], self.action_buffer_p_grad[None, :self.action_dim]], dim=0)
+        return None
+
     def move(self, f):
         pass  # folded into set_action (one kernel per step)
 

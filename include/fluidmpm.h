@@ -287,6 +287,20 @@ int fmpm_loss_chamfer(FmpmHandle* h, int f, const void* ids, const void* tgt, un
 int fmpm_loss_chamfer_grad(FmpmHandle* h, int f, int g, const void* ids, const void* tgt, unsigned int mrow_mask_lo,
                            float weight, void* stream);
 
+/* ---- trajectory optimiser step, fluidlab/optimizer/optim.py:22-41 + optimizer/policies.py:152-164 --- */
+/* One Adam update of the composite action table (rows = horizon + 1: the action_v rows, then action_p; cols = action_dim), resident on the
+ * device: params / m / v are double[rows*cols] (the reference keeps them in float64), grads is float[rows*cols] (agent.get_grad's dtype),
+ * trainable is unsigned char[rows] or NULL.  Rows with trainable == 0 and columns in fix_dim_mask see a zero gradient; the first rows-1 rows
+ * are clipped to [clip_lo, clip_hi] after the update (policies.py:158-164).  bias_1 / bias_2 = 1 - beta^(iter+1), computed by the caller.
+ * Every operation is rounded as NumPy rounds it (no contraction), so the result is bit-identical to the reference's. */
+typedef struct FmpmAdamCfg {
+  double lr, beta_1, beta_2, epsilon, bias_1, bias_2, clip_lo, clip_hi;
+  int rows, cols;
+  unsigned int fix_dim_mask;
+  int reserved;
+} FmpmAdamCfg;
+int fmpm_adam_step(FmpmHandle* h, const FmpmAdamCfg* cfg, void* params, void* m, void* v, const void* grads, const void* trainable, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ def pytest_configure(config):
 # B200.  They are collected AFTER the hardware-validated ones, so that with `-x` a first-run surprise in a new path does not hide the state of
 # the paths that have already been measured.  Remove a pattern once its tests have passed on hardware.
 FIRST_HARDWARE_RUN_PENDING = ('g2p2g', '_fused', 'fused_path', 'reference_agents', 'finite_differences', 'neighbour_handshake', 'slab_sharded_backward', '-locked', 'locked-',
-                              'test_zz_smoke_gpu')
+                              'test_zz_smoke_gpu', 'test_optimizer')
 
 
 def pytest_collection_modifyitems(config, items):

@@ -1,0 +1,52 @@
+"""Generates tests/golden/reference_optim.npz with the reference's OWN optimiser classes: Adam from fluidlab/optimizer/optim.py (loaded by
+path: it imports NumPy only) and TrainablePolicy from fluidlab/optimizer/policies.py (its class source is compiled on its own — the module
+imports input-device packages that are not installed).  Run in the build container (needs /root/reference); the fixture travels.
+
+    python tests/golden/make_reference_optim.py
+"""
+import ast
+import importlib.util
+import os
+import types
+import numpy as np
+
+REF = '/root/reference/fluidlab/optimizer'
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def reference_classes():
+    spec = importlib.util.spec_from_file_location('ref_optim', os.path.join(REF, 'optim.py'))
+    optim = importlib.util.module_from_spec(spec); spec.loader.exec_module(optim)
+    tree = ast.parse(open(os.path.join(REF, 'policies.py')).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'TrainablePolicy']
+    ns = {'np': np, 'Adam': optim.Adam}
+    exec(compile(ast.Module(body=cls, type_ignores=[]), 'policies.py', 'exec'), ns)
+    return optim.Adam, ns['TrainablePolicy']
+
+
+def main():
+    Adam, TrainablePolicy = reference_classes()
+    out = {}
+    for name, (H, D, fix_dim, frozen, lr) in dict(latteart=(12, 3, None, 0, 0.05), pouring=(9, 6, [1, 4], 3, 0.003)).items():
+        cfg = types.SimpleNamespace(type='Adam', lr=lr, beta_1=0.9, beta_2=0.999, epsilon=1e-8)
+        rng = types.SimpleNamespace(v=(-0.05, 0.05), p=(0.4, 0.6))
+        np.random.seed(7)
+        pol = TrainablePolicy(cfg, rng, D, H, (-0.1, 0.1), fix_dim=fix_dim)
+        pol.trainable[:frozen] = False
+        rs = np.random.RandomState(11)
+        n_iters = 6
+        grads = (rs.randn(n_iters, H + 1, D) * 10.0 ** rs.uniform(-4, 1, size=(n_iters, 1, 1))).astype(np.float32)
+        grads[2, 1] = 0.0                      # a zero gradient row: sqrt(v) + eps path
+        tables = [pol.comp_actions.copy()]
+        for it in range(n_iters):
+            pol.optimize(grads[it].copy(), {})
+            tables.append(pol.comp_actions.copy())
+        out.update({f'{name}_grads': grads, f'{name}_tables': np.stack(tables), f'{name}_trainable': pol.trainable.copy(),
+                    f'{name}_fix_dim': np.array([] if fix_dim is None else fix_dim, np.int32), f'{name}_lr': lr,
+                    f'{name}_m': pol.optim.momentum_buffer.copy(), f'{name}_v': pol.optim.v_buffer.copy()})
+    np.savez_compressed(os.path.join(HERE, 'reference_optim.npz'), beta_1=0.9, beta_2=0.999, epsilon=1e-8, action_range=np.array([-0.1, 0.1]), **out)
+    print('wrote reference_optim.npz', {k: v.shape for k, v in out.items() if hasattr(v, 'shape') and v.ndim > 0})
+
+
+if __name__ == '__main__':
+    main()
