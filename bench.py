@@ -439,6 +439,15 @@ def main():
             torch.cuda.empty_cache()
         except Exception as ex:   # an extra: never let it take the bench line down
             fb['whole_trajectory_ring'] = {'error': f'{type(ex).__name__}: {ex}'}
+        # the optimiser step that closes one solver iteration (optimizer/solver.py:62-67): Adam on LatteArt's 251 x 3 action table, on the device
+        try:
+            import types as _types
+            from fluidlab_b200.optimizer import Adam as _Adam
+            _ad = _Adam((251, 3), _types.SimpleNamespace(type='Adam', lr=0.05, beta_1=0.9, beta_2=0.999, epsilon=1e-8)); _ad.bind(sim)
+            _tab = torch.zeros((251, 3), dtype=torch.float64, device=dev); _gr = torch.randn((251, 3), dtype=torch.float32, device=dev)
+            fb['adam_step_ms'] = time_phase(lambda: _ad.step_device(_tab, _gr, clip=(-1.0, 1.0)))
+        except Exception as ex:
+            fb['adam_step_ms'] = {'error': f'{type(ex).__name__}: {ex}'}
 
     # ------------------------------------------------------------------ end to end through the public API with host buffers
     pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in init.items() if k in ('x', 'v', 'C', 'F', 'used')}

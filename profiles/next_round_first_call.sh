@@ -7,7 +7,8 @@
 set -x
 tag=${1:-r02a}
 mkdir -p gpurun_out
-# 1. the parity gate, incl. the tests that have never run on hardware (smoke solver, circulation stack, C5-from-rest, 'locked' reference run)
+# 1. the parity gate, incl. the tests that have never run on hardware (collected last, tests/conftest.py: smoke solver, circulation stack, reference
+#    agent scenes, g2p2g paths incl. MAT_RIGID bodies, device Adam, 'locked' reference run)
 timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/${tag}_pytest_gpu.log 2>&1
 tail -5 gpurun_out/${tag}_pytest_gpu.log
 # 2. bench: plain vs g2p2g-fused forward (same process conditions back to back); the line also carries e2e vs e2e_obs_bridge

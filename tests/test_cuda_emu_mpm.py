@@ -321,6 +321,7 @@ def test_bench_script_runs_end_to_end_on_the_emulated_device():
     assert line['roofline_g2p2g']['kernel'] == 'k_g2p2g' and line['roofline_g2p2g']['launches_timed'] == 2 * 9
     fb = line['fwd_bwd']
     assert fb['value'] > 0 and 'error' not in fb['whole_trajectory_ring'] and fb['whole_trajectory_ring']['max_substeps_local'] == 30
+    assert isinstance(fb['adam_step_ms'], float), fb['adam_step_ms']
     ob = line['e2e_obs_bridge']
     assert 'error' not in ob and ob['d2h_bytes_per_step'] < line['e2e']['d2h_bytes_per_step']
 
