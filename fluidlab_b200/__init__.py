@@ -12,4 +12,5 @@ from .effectors import Effector, Injector, BallInjector, Rigid, AirCon  # noqa: 
 from .smoke import SmokeField  # noqa: F401
 from .meshes import Static, Dynamic, Statics  # noqa: F401
 from .losses import Loss, ShapeMatchingLoss, LatteArtLoss, CirculationLoss  # noqa: F401
-from .optimizer import Adam, ActionsPolicy, TrainablePolicy, LatteArtPolicy, Solver, forward_backward  # noqa: F401
+from .optimizer import (Adam, ActionsPolicy, TrainablePolicy, LatteArtPolicy, LatteArtStirPolicy, IceCreamDynamicPolicy, IceCreamStaticPolicy,  # noqa: F401
+                        CirculationPolicy, PouringPolicy, TransportingPolicy, Solver, forward_backward)

@@ -140,8 +140,65 @@ class TrainablePolicy:  # policies.py:131-164
         self.actions_v = new[:-1]
 
 
+class _TaskPolicy(TrainablePolicy):
+    """The task policies of policies.py that differ from TrainablePolicy only by a rule table: which rows train, a gradient clip, and
+    learning-rate / freeze schedules keyed on loss_info['temporal_range'] (the loss's current horizon).  The scripted-phase policies
+    (Gathering*, Mixing: they read the effector's pose every step) stay with the reference's env layer."""
+    TRAINABLE = None        # None = every row; else slice bounds (start, stop) of the rows that train
+    GRAD_CLIP = None        # clip of the gradient before the update
+    LR_SCHEDULE = ()        # ((temporal_range >, lr factor), ...) first match wins
+    FREEZE_SCHEDULE = ()    # ((temporal_range >, freeze rows [:n]), ...) first match wins
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.TRAINABLE is not None:
+            self.trainable = np.full(self.comp_actions_shape[0], False)
+            self.trainable[slice(*self.TRAINABLE)] = True
+
+    def optimize(self, grads, loss_info=None):
+        if self.GRAD_CLIP is not None:
+            grads = grads.clamp(*self.GRAD_CLIP) if torch.is_tensor(grads) else np.clip(grads, *self.GRAD_CLIP)
+        super().optimize(grads, loss_info)
+        tr = (loss_info or {}).get('temporal_range', 0)
+        for above, factor in self.LR_SCHEDULE:
+            if tr > above:
+                self.optim.lr = self.optim.init_lr * factor
+                break
+        for above, n in self.FREEZE_SCHEDULE:
+            if tr > above:
+                self.trainable[:n] = False
+                break
+
+
 class LatteArtPolicy(TrainablePolicy):  # policies.py:167-169
     pass
+
+
+class LatteArtStirPolicy(_TaskPolicy):  # policies.py:172-192
+    LR_SCHEDULE = ((250, 0.2), (150, 0.5))
+    FREEZE_SCHEDULE = tuple((step, step - 100) for step in (400, 350, 300, 250, 200, 150, 100))
+
+
+class IceCreamDynamicPolicy(_TaskPolicy):  # policies.py:195-200
+    TRAINABLE = (169, -1)
+
+
+class IceCreamStaticPolicy(_TaskPolicy):  # policies.py:203-215
+    TRAINABLE = (None, -1)
+    GRAD_CLIP = (-1e5, 1e5)
+    LR_SCHEDULE = ((450, 0.1),)
+
+
+class CirculationPolicy(TrainablePolicy):  # policies.py:341-344
+    pass
+
+
+class PouringPolicy(TrainablePolicy):  # policies.py:357-359
+    pass
+
+
+class TransportingPolicy(_TaskPolicy):  # policies.py:362-366
+    TRAINABLE = (None, -1)
 
 
 def forward_backward(taichi_env, sim_state, policy, horizon_action, device_grad=True):

@@ -11,6 +11,7 @@ import types
 import numpy as np
 
 REF = '/root/reference/fluidlab/optimizer'
+TASK_POLICIES = ('LatteArtStirPolicy', 'IceCreamDynamicPolicy', 'IceCreamStaticPolicy', 'TransportingPolicy')
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -18,14 +19,14 @@ def reference_classes():
     spec = importlib.util.spec_from_file_location('ref_optim', os.path.join(REF, 'optim.py'))
     optim = importlib.util.module_from_spec(spec); spec.loader.exec_module(optim)
     tree = ast.parse(open(os.path.join(REF, 'policies.py')).read())
-    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'TrainablePolicy']
-    ns = {'np': np, 'Adam': optim.Adam}
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ('TrainablePolicy',) + TASK_POLICIES]
+    ns = {'np': np, 'Adam': optim.Adam, 'print': lambda *a, **k: None}
     exec(compile(ast.Module(body=cls, type_ignores=[]), 'policies.py', 'exec'), ns)
-    return optim.Adam, ns['TrainablePolicy']
+    return optim.Adam, ns['TrainablePolicy'], ns
 
 
 def main():
-    Adam, TrainablePolicy = reference_classes()
+    Adam, TrainablePolicy, ns = reference_classes()
     out = {}
     for name, (H, D, fix_dim, frozen, lr) in dict(latteart=(12, 3, None, 0, 0.05), pouring=(9, 6, [1, 4], 3, 0.003)).items():
         cfg = types.SimpleNamespace(type='Adam', lr=lr, beta_1=0.9, beta_2=0.999, epsilon=1e-8)
@@ -44,6 +45,21 @@ def main():
         out.update({f'{name}_grads': grads, f'{name}_tables': np.stack(tables), f'{name}_trainable': pol.trainable.copy(),
                     f'{name}_fix_dim': np.array([] if fix_dim is None else fix_dim, np.int32), f'{name}_lr': lr,
                     f'{name}_m': pol.optim.momentum_buffer.copy(), f'{name}_v': pol.optim.v_buffer.copy()})
+    # task policies (rule tables on loss_info['temporal_range']): horizon 180, temporal ranges that cross their lr / freeze thresholds
+    H, D = 180, 3
+    tranges = np.array([90, 120, 160, 210, 260, 460], np.int32)
+    rs = np.random.RandomState(5)
+    tgrads = (rs.randn(len(tranges), H + 1, D) * 10.0 ** rs.uniform(-2, 7, size=(len(tranges), 1, 1))).astype(np.float32)   # some beyond the 1e5 clip
+    for name in TASK_POLICIES:
+        cfg = types.SimpleNamespace(type='Adam', lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-8)
+        np.random.seed(9)
+        pol = ns[name](cfg, types.SimpleNamespace(v=(-0.05, 0.05), p=(0.4, 0.6)), D, H, (-0.1, 0.1), fix_dim=None)
+        tabs, lrs, trains = [pol.comp_actions.copy()], [], [pol.trainable.copy()]
+        for it, tr in enumerate(tranges):
+            pol.optimize(tgrads[it].copy(), {'temporal_range': int(tr)})
+            tabs.append(pol.comp_actions.copy()); lrs.append(pol.optim.lr); trains.append(pol.trainable.copy())
+        out.update({f'task_{name}_tables': np.stack(tabs), f'task_{name}_lr': np.array(lrs), f'task_{name}_trainable': np.stack(trains)})
+    out.update(task_grads=tgrads, task_tranges=tranges)
     np.savez_compressed(os.path.join(HERE, 'reference_optim.npz'), beta_1=0.9, beta_2=0.999, epsilon=1e-8, action_range=np.array([-0.1, 0.1]), **out)
     print('wrote reference_optim.npz', {k: v.shape for k, v in out.items() if hasattr(v, 'shape') and v.ndim > 0})
 

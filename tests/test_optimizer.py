@@ -68,6 +68,27 @@ def _check_product_against_golden(sim, name):
     assert pol.optim.iter == len(grads)
 
 
+TASKS = ('LatteArtStirPolicy', 'IceCreamDynamicPolicy', 'IceCreamStaticPolicy', 'TransportingPolicy')
+
+
+def _check_task_policy(sim, name):
+    """the rule-table policies against the reference's own classes: trainable rows, lr and freeze schedules over loss_info['temporal_range'],
+    IceCreamStatic's gradient clip; tables bit for bit"""
+    import fluidlab_b200
+    d = _golden()
+    tabs, lrs, trains = d[f'task_{name}_tables'], d[f'task_{name}_lr'], d[f'task_{name}_trainable']
+    H, D = tabs[0].shape[0] - 1, tabs[0].shape[1]
+    cfg = types.SimpleNamespace(type='Adam', lr=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-8)
+    pol = getattr(fluidlab_b200, name)(cfg, types.SimpleNamespace(v=(-0.05, 0.05), p=(0.4, 0.6)), D, H, (-0.1, 0.1), fix_dim=None, sim=sim)
+    pol.actions_v, pol.actions_p = tabs[0][:-1].copy(), tabs[0][-1].copy()
+    assert np.array_equal(pol.trainable, trains[0])
+    for it, tr in enumerate(d['task_tranges']):
+        g = d['task_grads'][it]
+        pol.optimize(g.copy() if it % 2 else torch.from_numpy(g).to(sim.device), {'temporal_range': int(tr)})
+        assert np.array_equal(pol.comp_actions, tabs[it + 1]), (name, it)
+        assert pol.optim.lr == lrs[it] and np.array_equal(pol.trainable, trains[it + 1]), (name, it)
+
+
 @pytest.fixture
 def emu():
     import harness
@@ -81,12 +102,25 @@ def test_device_adam_reproduces_the_reference_bit_for_bit_on_the_shim(emu, name)
     _check_product_against_golden(_tiny_sim('cpu'), name)
 
 
+@pytest.mark.parametrize('name', TASKS)
+def test_task_policies_equal_the_reference_classes_on_the_shim(emu, name):
+    _check_task_policy(_tiny_sim('cpu'), name)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', SCENES)
 def test_device_adam_reproduces_the_reference_bit_for_bit(name):
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     _check_product_against_golden(_tiny_sim(None), name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', TASKS)
+def test_task_policies_equal_the_reference_classes(name):
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    _check_task_policy(_tiny_sim(None), name)
 
 
 def _latteart_env(device):
