@@ -103,3 +103,12 @@ for grad in (False, True):
         Nr = len(dr['x0']); z9 = np.zeros((Nr, 3, 3), np.float32)
         s.reset_grad(); s.set_grad(rng.randn(Nr, 3).astype(np.float32), np.zeros((Nr, 3), np.float32), z9, z9); s.step_grad(None)
     print('rigid fused ok grad', grad, flush=True)
+# device Adam on a 251 x 3 table (trainable mask + fix_dim + clip)
+import types as _t
+from fluidlab_b200 import TrainablePolicy
+pol = TrainablePolicy(_t.SimpleNamespace(type='Adam', lr=0.05, beta_1=0.9, beta_2=0.999, epsilon=1e-8), _t.SimpleNamespace(v=(-0.05, 0.05), p=(0.4, 0.6)), 3, 250, (-0.1, 0.1),
+                      fix_dim=[1], sim=s)
+pol.trainable[:7] = False
+for _ in range(3):
+    pol.optimize(rng.randn(251, 3).astype(np.float32), {})
+print('adam ok', flush=True)
