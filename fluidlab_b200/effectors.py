@@ -20,6 +20,14 @@ def _xyzw_to_wxyz(q):
     return np.array([q[3], q[0], q[1], q[2]])
 
 
+class _HostField:
+    def __init__(self, val):
+        self._val = val
+
+    def to_numpy(self):
+        return self._val
+
+
 class Effector:
     state_dim = 7
 
@@ -103,6 +111,14 @@ class Effector:
         sim = self.sim
         a = self._stage_action(np.asarray(action, dtype=np.float32).reshape(-1))
         sim._ck(sim._lib.fmpm_effector_step(sim._h, C.byref(self._c), s, s_global, a.data_ptr(), sim._stream()), 'fmpm_effector_step')
+        self._latest_f = (s + 1) * n_substeps - 1     # update_latest_pos(f) of the step's last move (effector.py:146-152)
+
+    @property
+    def latest_pos(self):
+        """effector.py:58,150-152: position at the last moved substep, as an object with .to_numpy() -> float32 [1, 3] (zeros before any move)"""
+        f = getattr(self, '_latest_f', None)
+        val = np.zeros((1, 3), np.float32) if f is None else self.pos[f].detach().cpu().numpy().astype(np.float32)[None]
+        return _HostField(val)
 
     def set_action_grad(self, s, s_global, n_substeps, action):  # effector.py:270-274 (+ move_kernel.grad)
         assert s_global <= self.max_action_steps_global

@@ -142,8 +142,7 @@ class TrainablePolicy:  # policies.py:131-164
 
 class _TaskPolicy(TrainablePolicy):
     """The task policies of policies.py that differ from TrainablePolicy only by a rule table: which rows train, a gradient clip, and
-    learning-rate / freeze schedules keyed on loss_info['temporal_range'] (the loss's current horizon).  The scripted-phase policies
-    (Gathering*, Mixing: they read the effector's pose every step) stay with the reference's env layer."""
+    learning-rate / freeze schedules keyed on loss_info['temporal_range'] (the loss's current horizon)."""
     TRAINABLE = None        # None = every row; else slice bounds (start, stop) of the rows that train
     GRAD_CLIP = None        # clip of the gradient before the update
     LR_SCHEDULE = ()        # ((temporal_range >, lr factor), ...) first match wins
@@ -167,6 +166,80 @@ class _TaskPolicy(TrainablePolicy):
         for above, n in self.FREEZE_SCHEDULE:
             if tr > above:
                 self.trainable[:n] = False
+                break
+
+
+class _PhasedPolicy(TrainablePolicy):
+    """Gathering / GatheringO / Mixing (policies.py:218-339): the horizon is cut into periods; inside a period only the first phase trains, the
+    other phases are scripted in get_action_v(update=True) - lift by a fixed velocity, travel back towards a home position at the speed that
+    arrives at the phase's end (reads the effector's latest position), lower again."""
+    PHASES = ()          # phase end offsets inside one period; the last one is the period
+    LIFT = 0.008
+    KEEP_HEIGHT = True   # the travel-back phase keeps y
+    HOME = None          # None = actions_p
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        n, period = self.comp_actions_shape[0], self.PHASES[-1]
+        self.stage_step = list(self.PHASES)
+        self.trainable = np.full(n, False)
+        self.status = np.full(n, 0)
+        for i in range(self.horizon):
+            self.status[i] = int(np.searchsorted(np.asarray(self.PHASES), i % period, side='right'))
+            self.trainable[i] = self.status[i] == 0
+
+    def _script(self, i, agent):
+        raise NotImplementedError
+
+    def get_action_v(self, i, agent=None, update=False):
+        if update and self.status[i] != 0:
+            self.actions_v[i] = self._script(i, agent)
+        return self.actions_v[i]
+
+    def _travel_back(self, i, agent, end):
+        home = self.actions_p if self.HOME is None else np.array(self.HOME)
+        a = (home - agent.rigid.latest_pos.to_numpy()[0]) / (end - (i % self.PHASES[-1]))
+        if self.KEEP_HEIGHT:
+            a[1] = 0
+        return a
+
+
+class GatheringOPolicy(_PhasedPolicy):  # policies.py:262-303
+    PHASES = (50, 65, 105, 120)
+
+    def _script(self, i, agent):
+        st = self.status[i]
+        if st == 2:
+            return self._travel_back(i, agent, self.PHASES[2])
+        return np.array([0, self.LIFT if st == 1 else -self.LIFT, 0])
+
+
+class GatheringPolicy(GatheringOPolicy):  # policies.py:218-259
+    def optimize(self, grads, loss_info=None):
+        tr = (loss_info or {}).get('temporal_range', 0)
+        for step in (720, 600, 480, 360, 240, 120):
+            if tr > step:
+                self.freeze_till = tr - 120
+                self.trainable[:self.freeze_till] = False
+                break
+        super().optimize(grads, loss_info)
+
+
+class MixingPolicy(_PhasedPolicy):  # policies.py:306-339
+    PHASES = (50, 80)
+    KEEP_HEIGHT = False
+    HOME = (0.5, 0.73, 0.5)
+
+    def _script(self, i, agent):
+        return self._travel_back(i, agent, self.PHASES[1])
+
+    def optimize(self, grads, loss_info=None):
+        super().optimize(grads, loss_info)
+        tr = (loss_info or {}).get('temporal_range', 0)
+        for step in range(1920, 79, -80):
+            if tr > step:
+                self.freeze_till = tr - 160
+                self.trainable[:self.freeze_till] = False
                 break
 
 

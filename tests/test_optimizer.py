@@ -89,6 +89,48 @@ def _check_task_policy(sim, name):
         assert pol.optim.lr == lrs[it] and np.array_equal(pol.trainable, trains[it + 1]), (name, it)
 
 
+PHASED = ('GatheringPolicy', 'GatheringOPolicy', 'MixingPolicy')
+
+
+def _check_phased_policy(sim, name):
+    """Gathering / GatheringO / Mixing: status / trainable layout, the scripted phases of get_action_v(update=True) (reading agent.rigid.latest_pos),
+    freeze schedules and tables against the reference's own classes"""
+    import fluidlab_b200
+    sys.path.insert(0, os.path.join(HERE, 'golden'))
+    from make_reference_optim import fake_latest_pos
+    d = _golden()
+    scr, tabs, trains = d[f'phased_{name}_scripted'], d[f'phased_{name}_tables'], d[f'phased_{name}_trainable']
+    H, D = tabs[0].shape[0] - 1, tabs[0].shape[1]
+    cfg = types.SimpleNamespace(type='Adam', lr=0.002, beta_1=0.9, beta_2=0.999, epsilon=1e-8)
+    pol = getattr(fluidlab_b200, name)(cfg, types.SimpleNamespace(v=(-0.005, 0.005), p=(0.4, 0.6)), D, H, (-0.01, 0.01), fix_dim=None, sim=sim)
+    pol.actions_v, pol.actions_p = tabs[0][:-1].copy(), tabs[0][-1].copy()
+    assert np.array_equal(pol.status, d[f'phased_{name}_status']) and np.array_equal(pol.trainable, trains[0])
+    for it, tr in enumerate(d['phased_tranges']):
+        for i in range(H):
+            agent = types.SimpleNamespace(rigid=types.SimpleNamespace(latest_pos=types.SimpleNamespace(to_numpy=lambda it=it, i=i: fake_latest_pos(it, i))))
+            pol.get_action_v(i, agent=agent, update=True)
+        assert np.array_equal(pol.comp_actions, scr[it]), (name, it)
+        pol.optimize(d['phased_grads'][it].copy(), {'temporal_range': int(tr)})
+        assert np.array_equal(pol.comp_actions, tabs[it + 1]), (name, it)
+        assert np.array_equal(pol.trainable, trains[it + 1]) and pol.freeze_till == int(d[f'phased_{name}_freeze'][it]), (name, it)
+
+
+@pytest.mark.parametrize('name', PHASED)
+def test_scripted_phase_policies_equal_the_reference_classes_on_the_shim(emu, name):
+    _check_phased_policy(_tiny_sim('cpu'), name)
+
+
+def test_effector_latest_pos_follows_the_last_moved_substep(emu):
+    """effector.py:146-152: latest_pos = pos[f] of the step's last move; zeros before any move"""
+    env, n_steps = _latteart_env('cpu')
+    eff = env.agent.effectors[0]
+    assert np.array_equal(eff.latest_pos.to_numpy(), np.zeros((1, 3), np.float32))
+    env.set_state(env.get_state()['state'], grad_enabled=False)
+    env.step(np.array([0.004, 0.0, -0.002], np.float32))
+    n = env.simulator.n_substeps
+    assert np.array_equal(eff.latest_pos.to_numpy()[0], eff.get_state(n - 1)[:3]) and not np.array_equal(eff.get_state(n - 1)[:3], eff.get_state(0)[:3])
+
+
 @pytest.fixture
 def emu():
     import harness
