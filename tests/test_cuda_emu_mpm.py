@@ -520,3 +520,19 @@ def test_gpu_marked_parity_tests_pass_on_the_shim(cxxflags):
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''
     assert r.returncode == 0 and ' passed' in tail and 'failed' not in tail, r.stdout[-3000:] + r.stderr[-1000:]
     assert int(tail.split(' passed')[0].split()[-1]) >= 56, tail
+
+
+def test_graft_entry_smoke_runs_on_the_emulated_device(emu, monkeypatch):
+    """__graft_entry__.smoke() — the call the driver makes on cuda:0 before the bench — as written, on the shim (device checks patched only)"""
+    from fluidlab_b200 import simulator
+    init = simulator.MPMSimulator.__init__
+
+    def emu_init(self, *a, device=None, **k):
+        init(self, *a, device='cpu' if device is None else device, **k)
+        self.use_graphs = False
+    monkeypatch.setattr(simulator.MPMSimulator, '__init__', emu_init)
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+    import __graft_entry__ as g
+    g.smoke()
