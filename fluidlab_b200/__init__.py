@@ -13,4 +13,4 @@ from .smoke import SmokeField  # noqa: F401
 from .meshes import Static, Dynamic, Statics  # noqa: F401
 from .losses import Loss, ShapeMatchingLoss, LatteArtLoss, CirculationLoss  # noqa: F401
 from .optimizer import (Adam, ActionsPolicy, TrainablePolicy, LatteArtPolicy, LatteArtStirPolicy, IceCreamDynamicPolicy, IceCreamStaticPolicy,  # noqa: F401
-                        CirculationPolicy, PouringPolicy, TransportingPolicy, GatheringPolicy, GatheringOPolicy, MixingPolicy, Solver, forward_backward)
+                        CirculationPolicy, PouringPolicy, TransportingPolicy, GatheringPolicy, GatheringOPolicy, MixingPolicy, Solver, forward_backward, trainable_policy)

@@ -274,6 +274,12 @@ class TransportingPolicy(_TaskPolicy):  # policies.py:362-366
     TRAINABLE = (None, -1)
 
 
+def trainable_policy(taichi_env, policy_cls, optim_cfg, init_range, horizon_action, action_range, fix_dim=None):
+    """what every env's trainable_policy(optim_cfg, init_range) does (e.g. envs/latteart_env.py:97-101): the task's policy sized by the agent's
+    action_dim, already bound to the simulator that runs its update kernel"""
+    return policy_cls(optim_cfg, init_range, taichi_env.agent.action_dim, horizon_action, action_range, fix_dim=fix_dim, sim=taichi_env.simulator)
+
+
 def forward_backward(taichi_env, sim_state, policy, horizon_action, device_grad=True):
     """solver.py:23-59: one rollout with gradients -> (loss_info, dLoss/d(comp_actions)).  device_grad: return the gradient as a device tensor
     (agent.get_grad_device) so that policy.optimize consumes it without a round trip."""

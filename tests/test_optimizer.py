@@ -201,6 +201,10 @@ def test_solver_loop_equals_the_same_loop_with_the_oracle_optimiser(emu):
     def make_policy(*_):
         np.random.seed(3)
         return TrainablePolicy(ocfg, irange, 3, n_steps, (-0.02, 0.02), fix_dim=[1])
+    from fluidlab_b200 import trainable_policy
+    np.random.seed(3)
+    bound = trainable_policy(env, TrainablePolicy, ocfg, irange, n_steps, (-0.02, 0.02), fix_dim=[1])
+    assert bound._sim is env.simulator and np.array_equal(bound.comp_actions, make_policy().comp_actions)
     wrapper = types.SimpleNamespace(taichi_env=env, horizon=n_steps, horizon_action=n_steps, trainable_policy=make_policy)
     losses = []
     pol = Solver(wrapper, cfg=types.SimpleNamespace(optim=ocfg, init_range=irange, n_iters=4)).solve(callback=lambda it, info: losses.append(info['loss']))
