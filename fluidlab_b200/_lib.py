@@ -27,6 +27,7 @@ class FmpmConfig(C.Structure):
         ("lock_mask", C.c_int),
         ("n_materials", C.c_int),
         ("device", C.c_int),
+        ("scene_flags", C.c_int),
     ]
 
 
@@ -45,6 +46,7 @@ class FmpmBuffers(C.Structure):
         ("sort_tmp", vp), ("sort_tmp_bytes", C.c_ulonglong),
         ("blk_flags", vp), ("blk_list", vp), ("blk_count", vp),
         ("grid_pm_ring", vp), ("grid_v_ring", vp), ("blk_list_ring", vp), ("blk_count_ring", vp),
+        ("grid_pm3", vp), ("blk_flags3", vp),
     ]
 
 
@@ -94,6 +96,8 @@ class FmpmBodies(C.Structure):
 
 
 BODY_STATE_STRIDE, BODY_GRAD_STRIDE = 48, 32
+SCENE_ALL_LIQUID_MU0 = 1
+FWD_KFWD, FWD_LIQUID, FWD_INLINE, FWD_TMA = 1, 2, 4, 8
 
 
 # ---- include/fluidsmoke.h
@@ -140,6 +144,8 @@ _PROTOS = {
     "fmpm_g2p2g": (_I, [vp, _I, _I, vp]),
     "fmpm_g2p2g_collect": (_I, [vp, _I, _I, C.POINTER(FmpmCollector), vp]),
     "fmpm_substeps_fused": (_I, [vp, _I, _I, vp]),
+    "fmpm_fwd_path": (_I, [vp]),
+    "fmpm_set_fwd_mask": (_I, [vp, _I]),
     "fmpm_p2g_injected": (_I, [vp, _I, C.POINTER(FmpmInjector), _I, vp, _I, C.POINTER(FmpmCollector), vp]),
     "fmpm_p2g_rigid": (_I, [vp, _I, _I, C.POINTER(FmpmCollector), vp]),
     "fmpm_clear_ring_slot": (_I, [vp, _I, vp]),

@@ -26,6 +26,7 @@ struct FmpmHandle {
   bool bound;
   char err[512];
   int sm_count;
+  int fwd_mask;   // fmpm_set_fwd_mask
 };
 
 int fmpm_advect_rigid_impl(FmpmHandle* h, int f, void* stream);  // fmpm_rigid.cu; no-op without MAT_RIGID bodies
@@ -81,6 +82,12 @@ static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1, int 
     if (h->slab.peer_flags_right) P.peer_fr = (int*)h->slab.peer_flags_right + foff;
     P.gl_lo = h->slab.left_lo; P.gl_hi = h->slab.left_hi; P.gr_lo = h->slab.right_lo; P.gr_hi = h->slab.right_hi;
     P.peer_gl = (float4*)h->slab.peer_ggv_left; P.peer_gr = (float4*)h->slab.peer_ggv_right;
+  }
+  if (ring_slot <= -2 && h->buf.grid_pm3) {   // -2 - k: accumulator k of the triple-buffered forward path (k_fwd, kInline)
+    const int k = -2 - ring_slot;
+    const size_t nblk = (size_t)P.nb * P.nb * P.nb;
+    P.grid_pm = (float4*)h->buf.grid_pm3 + (size_t)k * P.G;
+    P.blk_flags = (int*)h->buf.blk_flags3 + (size_t)k * nblk;
   }
   if (ring_slot >= 0 && h->buf.grid_pm_ring) {
     const size_t nblk = (size_t)P.nb * P.nb * P.nb;

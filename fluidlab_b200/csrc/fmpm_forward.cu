@@ -375,6 +375,220 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
   window_flush_all(W, P.grid_pm);
 }
 
+// =============================================================================================
+// k_fwd: the forward-only substep kernel of agent-free scenes — g2p(f) [+ grid_op(f) inlined] + p2g(f+1) in ONE launch.
+//   kMat == 1  every particle is a mu = 0 liquid (WATER / MILK / COFFEE ...: BASELINE configs C1-C3, C5): no SVD code at all, and because
+//              F[f+1] = J^(1/3) I (MPM:358-359) the deformation gradient of the intermediate frames travels as the single float s = F22
+//              (plane pf8): F~ = (I + dt C) s is bit-identical to the general product with F = diag(s, s, s).  Intermediate frames then
+//              hold x + meta + s: 20 B in and 20 B out per particle and substep instead of the 212 B of p2g + g2p.
+//   kInline    grid_op (MPM:380-398: momentum -> velocity, gravity, domain boundary; scenes without SDF colliders at grid level) is
+//              evaluated while the warp stages its node footprint, straight from the (momentum, mass) accumulator: grid_v is never written
+//              or read and the substep is ONE launch.  The accumulator is triple-buffered by frame (f % 3): this launch gathers from buffer
+//              f % 3, scatters frame f+1 into (f+1) % 3 and clears the blocks of (f+2) % 3 that the launch before gathered from.
+// The footprint of a warp is the box of nodes its 32 particles touch, up to 4 x 4 node columns x 16 nodes (a fresh sort gives 3 x 3 x ~7;
+// the extra column in x and y absorbs the drift between two cell sorts), staged with coalesced 128-bit loads.
+// =============================================================================================
+#ifndef FWD_MINB
+#define FWD_MINB 5
+#endif
+#define FWD_TILE_COLS 16   // 4 x 4 node columns
+// grid_op of one node without SDF colliders (MPM:380-386,398): the same operations, in the same order, as k_grid_op
+__device__ __forceinline__ float4 grid_op_node(const KParams& P, const int i, const int j, const int k, const float4 pm) {
+  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pm.w > FMPM_EPS) {
+    const float inv_m = 1.f / pm.w;
+    float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
+    const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
+    float fac[3];
+    boundary_v(P, pos, v, fac);
+    out = make_float4(v[0], v[1], v[2], 0.f);
+  }
+  return out;
+}
+// the rare warp whose particles do not fit one footprint box (no cell sort yet, or a very old one): every lane gathers its own 27 nodes
+// from L2.  The node loop stays rolled so that the hot kernel stays small in the instruction cache.
+template <bool kInline>
+__device__ __forceinline__ void fwd_gather_unstaged(const KParams& P, const int* b, const float* fx, float* nv, float* nC) {
+  const int n = P.n;
+  const float4* gv = P.grid_v + ((b[0] * n + b[1]) * n + b[2]);
+  float v[3] = {0.f, 0.f, 0.f}, C[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int c = 0; c < 27; c++) {
+    const int i = c / 9, j = (c / 3) % 3, k = c % 3;
+    float4 g = gv[(i * n + j) * n + k];
+    if (kInline) g = grid_op_node(P, b[0] + i, b[1] + j, b[2] + k, g);
+    const float d[3] = {(float)i - fx[0], (float)j - fx[1], (float)k - fx[2]};
+    float wt = 1.f;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {   // quadratic B-spline weight of offset o = (i, j, k)[r] (bspline(), MPM:336), selected without indexing a local array
+      const int o = r == 0 ? i : (r == 1 ? j : k);
+      const float a = 1.5f - fx[r], bb = fx[r] - 1.0f, cc = fx[r] - 0.5f;
+      wt *= o == 0 ? 0.5f * a * a : (o == 1 ? 0.75f - bb * bb : 0.5f * cc * cc);
+    }
+    const float gvv[3] = {g.x, g.y, g.z};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      v[r] += wt * gvv[r];
+#pragma unroll
+      for (int q = 0; q < 3; q++) C[r * 3 + q] += wt * gvv[r] * d[q];
+    }
+  }
+  const float c4 = 4.f * P.inv_dx;
+#pragma unroll
+  for (int r = 0; r < 3; r++) nv[r] = v[r];
+#pragma unroll
+  for (int r = 0; r < 9; r++) nC[r] = c4 * C[r];
+}
+template <int kMat, bool kInline>
+__global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams P, const int f, float4* __restrict__ clr, int* __restrict__ clr_flags, const int full) {
+  __shared__ ScatterSmem smem[P2G_WARPS];
+  static_assert(sizeof(((ScatterSmem*)0)->rec) >= FWD_TILE_COLS * 16 * sizeof(float4), "the gather tile is staged in the scatter records' storage");
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  ScatterSmem& S = smem[wib];
+  float4* tile = S.rec;   // gather tile first, scatter records afterwards (a __syncwarp separates the two uses)
+  const long long gw = (long long)blockIdx.x * P2G_WARPS + wib;
+  // ---- clear duty (kInline): one warp per flagged 8^3-node block of the accumulator that the previous launch gathered from
+  if (kInline && clr != nullptr) {
+    const int nb = P.nb, nblk = nb * nb * nb, n = P.n;
+    const long long nwarps = (long long)gridDim.x * P2G_WARPS;
+    for (long long blk = gw; blk < nblk; blk += nwarps) {
+      if (clr_flags[blk] != 0) {   // warp-uniform
+        const int bx = (int)(blk / (nb * nb)), by = (int)((blk / nb) % nb), bz = (int)(blk % nb);
+#pragma unroll 4
+        for (int r = 0; r < 16; r++) {
+          const int t = lane + r * 32;
+          const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+          clr[(i * n + j) * n + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) clr_flags[blk] = 0;
+      }
+    }
+  }
+  const long long slot0 = gw * 32;
+  if (slot0 >= P.N) return;   // warp-uniform
+  const long long sl = slot0 + lane;
+  const long long rem = (long long)P.N - slot0;
+  const int cnt = rem < 32 ? (int)rem : 32;
+  const bool inrange = sl < P.N;
+  const int s = (int)sl;
+  Window W; window_init(W, lane, P.n, P.blk_flags);
+  window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);   // x-slab mode: like k_p2g
+  // ---- particle loads: x + meta of frame f, F[f+1] (written by the p2g / k_fwd of frame f)
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 f0 = make_float4(1.f, 0.f, 0.f, 0.f), f1 = make_float4(1.f, 0.f, 0.f, 0.f); float f8 = 1.f;
+  if (inrange) {
+    a0 = P2G_LD(&P.pa[pa_idx(P, f, 0, s)]);
+    f8 = P2G_LD(&P.pf8[pf8_idx(P, f + 1, s)]);
+    if (kMat != 1) { f0 = P2G_LD(&P.pf[pf_idx(P, f + 1, 0, s)]); f1 = P2G_LD(&P.pf[pf_idx(P, f + 1, 1, s)]); }
+  }
+  const int meta = __float_as_int(a0.w);
+  const float x[3] = {a0.x, a0.y, a0.z};
+  int b[3]; float fx[3];
+  const bool ok = inrange && (meta & 1) && base_fx(P, x, b, fx);
+  // ---- footprint box of the warp
+  const int bx0 = __reduce_min_sync(SC_FULL, ok ? b[0] : 0x7fffffff), bx1 = __reduce_max_sync(SC_FULL, ok ? b[0] : -1);
+  const int by0 = __reduce_min_sync(SC_FULL, ok ? b[1] : 0x7fffffff), by1 = __reduce_max_sync(SC_FULL, ok ? b[1] : -1);
+  const int bz0 = __reduce_min_sync(SC_FULL, ok ? b[2] : 0x7fffffff), bz1 = __reduce_max_sync(SC_FULL, ok ? b[2] : -1);
+  const int nx = bx1 - bx0 + 3, ny = by1 - by0 + 3, nz = bz1 - bz0 + 3;
+  const bool any = bx1 >= 0;
+  const bool staged = any && nx <= 4 && ny <= 4 && nz <= 16;
+  const int tzs = nz <= 8 ? 3 : 4;   // rows of 8 or 16 nodes
+  if (staged) {
+    const int n = P.n, tot = FWD_TILE_COLS << tzs;
+    for (int t = lane; t < tot; t += 32) {
+      const int iz = t & ((1 << tzs) - 1), c = t >> tzs, iy = c & 3, ix = c >> 2;
+      if (ix >= nx) break;   // warp-uniform from the first lane on: the remaining columns lie outside the box
+      if (iy < ny && iz < nz) {
+        const int gi = bx0 + ix, gj = by0 + iy, gk = bz0 + iz;
+        float4 g = P.grid_v[(gi * n + gj) * n + gk];
+        if (kInline) g = grid_op_node(P, gi, gj, gk, g);
+        tile[t] = g;
+      }
+    }
+    __syncwarp();
+  }
+  int key = -1;
+  float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, m = 0.f;
+  float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  if (inrange) {
+    PState st;
+    if (!ok) {  // unused (MPM:309-316) or frozen: the whole state is carried over unchanged (these slots always hold complete frames)
+      if (meta & 2) { a0.x = a0.y = a0.z = FMPM_NOWHERE; a0.w = __int_as_float(meta & ~3); }
+      if (kMat == 1) { f0 = P.pf[pf_idx(P, f + 1, 0, s)]; f1 = P.pf[pf_idx(P, f + 1, 1, s)]; }
+      P.pa[pa_idx(P, f + 1, 0, s)] = a0;
+      P.pa[pa_idx(P, f + 1, 1, s)] = P.pa[pa_idx(P, f, 1, s)];
+      P.pa[pa_idx(P, f + 1, 2, s)] = P.pa[pa_idx(P, f, 2, s)];
+      P.pa[pa_idx(P, f + 1, 3, s)] = P.pa[pa_idx(P, f, 3, s)];
+      P.pf[pf_idx(P, f + 2, 0, s)] = f0; P.pf[pf_idx(P, f + 2, 1, s)] = f1; P.pf8[pf8_idx(P, f + 2, s)] = f8;
+    } else {
+      // ---- g2p of frame f (MPM:400-426) + advect (MPM:497-505)
+      bspline(fx, w);
+      const float c4 = 4.f * P.inv_dx;
+      if (staged) {
+        const float4* t0 = tile + ((((b[0] - bx0) << 2) + (b[1] - by0)) << tzs) + (b[2] - bz0);
+        g2p_gather_v(fx, w, [&](int c) { const float4* p = t0 + ((((c / 3) << 2) + (c % 3)) << tzs); Col3 r; r.g0 = p[0]; r.g1 = p[1]; r.g2 = p[2]; return r; }, st.v, st.C, c4);
+      } else {
+        fwd_gather_unstaged<kInline>(P, b, fx, st.v, st.C.m);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; d++) st.x[d] = x[d] + P.dt * st.v[d];
+      st.meta = meta;
+      // ---- p2g of frame f+1 (MPM:254-264, 331-378)
+      int b1[3]; float fx1[3];
+      const bool ok1 = base_fx(P, st.x, b1, fx1);
+      if (full || !ok1) store_A(P.pa, P, f + 1, s, st.x, meta, st.v, st.C);
+      else P.pa[pa_idx(P, f + 1, 0, s)] = make_float4(st.x[0], st.x[1], st.x[2], a0.w);
+      if (ok1) {
+        const float4 mt = __ldg(P.mats + ((meta >> 8) & 0xff));
+        m = mt.z;
+        float Bm[9];   // affine = k_stress * stress + m C  (MPM:344), times dx
+        if (kMat == 1) {
+          float Ft[9];
+#pragma unroll
+          for (int i = 0; i < 9; i++) Ft[i] = (P.dt * st.C.m[i] + ((i % 4 == 0) ? 1.f : 0.f)) * f8;   // (I + dt C) F with F = f8 I
+          const float J = Ft[0] * (Ft[4] * Ft[8] - Ft[5] * Ft[7]) - Ft[1] * (Ft[3] * Ft[8] - Ft[5] * Ft[6]) + Ft[2] * (Ft[3] * Ft[7] - Ft[4] * Ft[6]);
+          const float iso = mt.y * J * (J - 1.f);
+#pragma unroll
+          for (int i = 0; i < 9; i++) Bm[i] = (P.k_stress * ((i % 4 == 0) ? iso : 0.f) + m * st.C.m[i]) * P.dx;
+          float sn = (J > 0.f) ? cbrtf(J) : __int_as_float(0x7fc00000);   // pow(J, 1/3): NaN for J < 0 like the reference
+          if (J == 0.f) sn = 0.f;
+          if (full) {
+            __stcs(&P.pf[pf_idx(P, f + 2, 0, s)], make_float4(sn, 0.f, 0.f, 0.f));
+            __stcs(&P.pf[pf_idx(P, f + 2, 1, s)], make_float4(sn, 0.f, 0.f, 0.f));
+          }
+          __stcs(&P.pf8[pf8_idx(P, f + 2, s)], sn);
+        } else {
+          st.F.m[0] = f0.x; st.F.m[1] = f0.y; st.F.m[2] = f0.z; st.F.m[3] = f0.w; st.F.m[4] = f1.x; st.F.m[5] = f1.y; st.F.m[6] = f1.z; st.F.m[7] = f1.w; st.F.m[8] = f8;
+          Constit K; constitutive(P, st, mt.x, mt.y, mt.z, __float_as_int(mt.w), K);
+#pragma unroll
+          for (int i = 0; i < 9; i++) Bm[i] = K.A.m[i] * P.dx;
+          p2g_store_F(P, f + 2, s, K.Fn);
+        }
+        bspline(fx1, w);
+#pragma unroll
+        for (int i = 0; i < 9; i++) B[i] = Bm[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) q[i] = m * st.v[i] - (B[i * 3] * fx1[0] + B[i * 3 + 1] * fx1[1] + B[i * 3 + 2] * fx1[2]);
+        key = pack_key(b1);
+      } else {   // left the grid: frozen from now on, with the complete state (F = f8 I for kMat == 1)
+        if (kMat == 1) { f0 = make_float4(f8, 0.f, 0.f, 0.f); f1 = f0; }
+        P.pf[pf_idx(P, f + 2, 0, s)] = f0; P.pf[pf_idx(P, f + 2, 1, s)] = f1; P.pf8[pf8_idx(P, f + 2, s)] = f8;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) w[i][j] = 0.f;
+      }
+    }
+  }
+  __syncwarp();   // every lane is done with the gather tile before the scatter staging is written
+  const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
+  __syncwarp();
+  window_consume(W, S, cnt, starts, P.grid_pm);
+  __syncwarp();
+  window_flush_all(W, P.grid_pm);
+}
+
 // p2g of the few particles an injector has just activated in frame f (fused steps with an injector agent: the g2p2g kernel of the previous
 // substep ran before agent.act wrote them, so their contribution to the grid of frame f is added here — flux particles, plain vector
 // reductions, no window).  Same arithmetic as k_p2g for one particle; also writes F[f+1] and flags the touched blocks.
@@ -468,6 +682,7 @@ static int check_bound(FmpmHandle* h, const char* name) {
   return 0;
 }
 #define G2P2G_K(a, b) (k_g2p2g<a, b>)   /* a template-id with a comma cannot be a macro argument by itself */
+#define G2P2G_K2(k, a, b) (k<a, b>)
 static FmpmCollector no_collector() { FmpmCollector c; memset(&c, 0, sizeof(c)); return c; }
 static int check_frame(FmpmHandle* h, int f, int maxf, const char* name) {
   if (f < 0 || f > maxf) { snprintf(h->err, sizeof(h->err), "%s: frame %d out of range [0,%d]", name, f, maxf); return 1; }
@@ -629,13 +844,74 @@ extern "C" int fmpm_substeps_fused_store(FmpmHandle* h, int f0, int n, void* str
   if (fmpm_g2p_impl(h, f0 + n - 1, f0 + n - 1, stream)) return 1;
   return fmpm_advect_rigid_impl(h, f0 + n - 1, stream);
 }
-// n forward substeps f0 .. f0+n-1 with the inner g2p / p2g pairs fused: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1).
-// Frames f0 and f0+n are complete; the frames in between hold x, used and F only.  The grid must be clear on entry (as for fmpm_substep).
+// ---- k_fwd dispatch --------------------------------------------------------------------------------------------
+enum { FWD_KFWD = 1, FWD_LIQUID = 2, FWD_INLINE = 4, FWD_TMA = 8 };
+// what fmpm_substeps_fused may use for this handle: k_fwd needs an agent-free scene without MAT_RIGID bodies; the inlined grid_op also
+// needs the triple-buffered accumulators, no SDF collider at grid level and no x-slab peers (their ghost exchange is per parity buffer)
+static int fwd_path(const FmpmHandle* h) {
+  int p = 0;
+  const bool agent = (h->col.has_rigid != 0) || h->bodies.n_bodies > 0;
+  if (!agent) {
+    p |= FWD_KFWD;
+    if (h->cfg.scene_flags & FMPM_SCENE_ALL_LIQUID_MU0) p |= FWD_LIQUID;
+    if (h->buf.grid_pm3 && h->buf.blk_flags3 && h->col.n_statics == 0 && !h->slab.enabled) p |= FWD_INLINE;
+  }
+  p &= h->fwd_mask;
+  if (!(p & FWD_KFWD)) p = 0;
+  return p;
+}
+extern "C" int fmpm_fwd_path(FmpmHandle* h) { return h ? fwd_path(h) : 0; }
+extern "C" int fmpm_set_fwd_mask(FmpmHandle* h, int mask) { if (!h) return 1; h->fwd_mask = mask; return 0; }
+
+// one k_fwd launch: g2p(f) + p2g(f+1).  acc < 0: plain accumulator / grid_v (grid_op ran before); acc >= 0: inlined grid_op, frame f lives in
+// accumulator acc % 3
+static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream) {
+  if (check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_substeps_fused(k_fwd)")) return 1;
+  const bool inl = (path & FWD_INLINE) != 0, liq = (path & FWD_LIQUID) != 0;
+  KParams P = inl ? make_kparams(h, -2 - ((f + 1) % 3)) : make_kparams(h, -1, f + 1);   // scatter target: accumulator + block flags of frame f+1
+  float4* clr = nullptr; int* clr_flags = nullptr;
+  if (inl) {
+    const KParams Ps = make_kparams(h, -2 - (f % 3)), Pc = make_kparams(h, -2 - ((f + 2) % 3));
+    P.grid_v = Ps.grid_pm;   // gather source: the (momentum, mass) accumulator of frame f
+    clr = Pc.grid_pm; clr_flags = Pc.blk_flags;
+  }
+  if (P.N == 0) return 0;
+  const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
+  if (liq) { if (inl) FMPM_LAUNCH(G2P2G_K2(k_fwd, 1, true), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full); else FMPM_LAUNCH(G2P2G_K2(k_fwd, 1, false), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full); }
+  else { if (inl) FMPM_LAUNCH(G2P2G_K2(k_fwd, 0, true), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full); else FMPM_LAUNCH(G2P2G_K2(k_fwd, 0, false), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full); }
+  FMPM_CHECK_LAUNCH(h, "fmpm_substeps_fused(k_fwd)");
+  return 0;
+}
+static int clear_blocks_launch(FmpmHandle* h, const KParams& P, void* stream) {
+  const int nblk = P.nb * P.nb * P.nb;
+  const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  FMPM_LAUNCH(k_clear_blocks, grid, 256, 0, stream, P);
+  FMPM_CHECK_LAUNCH(h, "fmpm_substeps_fused(clear)");
+  return 0;
+}
+// n forward substeps f0 .. f0+n-1 with the inner g2p / p2g pairs fused.  Frames f0 and f0+n are complete; the frames in between hold x, used
+// and F only (all-liquid scenes: x, used and F22).  The grid must be clear on entry (as for fmpm_substep) and is clear on return.
+//   round-1 path            p2g(f0), [grid_op, k_g2p2g] x (n-1), grid_op, g2p(f0+n-1)
+//   k_fwd                   p2g(f0), [grid_op, k_fwd]   x (n-1), grid_op, g2p(f0+n-1)
+//   k_fwd + inlined grid_op p2g(f0), k_fwd x (n-1), grid_op, clear, g2p(f0+n-1)          (accumulators f % 3)
 extern "C" int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream) {
   if (n < 1) { if (h) snprintf(h->err, sizeof(h->err), "fmpm_substeps_fused: n must be >= 1"); return 1; }
+  if (check_bound(h, "fmpm_substeps_fused")) return 1;
+  const int path = fwd_path(h);
+  if (path & FWD_INLINE) {
+    if (fmpm_p2g_impl(h, f0, 1, -2 - (f0 % 3), stream)) return 1;
+    for (int i = 0; i + 1 < n; i++)
+      if (fwd_launch(h, f0 + i, path, i + 2 == n, stream)) return 1;
+    const int fl = f0 + n - 1;
+    if (fmpm_grid_op_impl(h, fl, 1, 0, -2 - (fl % 3), stream)) return 1;        // consumes and clears the accumulator of the last frame
+    if (n >= 2 && clear_blocks_launch(h, make_kparams(h, -2 - ((fl + 2) % 3)), stream)) return 1;   // the one the last k_fwd gathered from
+    return fmpm_g2p(h, fl, stream);
+  }
   if (fmpm_p2g(h, f0, 1, stream)) return 1;
   for (int i = 0; i + 1 < n; i++) {
-    if (fmpm_grid_op(h, f0 + i, 1, stream) || fmpm_g2p2g(h, f0 + i, 0, stream)) return 1;
+    if (fmpm_grid_op(h, f0 + i, 1, stream)) return 1;
+    if (path & FWD_KFWD) { if (fwd_launch(h, f0 + i, path, i + 2 == n, stream)) return 1; }
+    else if (fmpm_g2p2g(h, f0 + i, 0, stream)) return 1;
     if (h->bodies.n_bodies > 0 && (fmpm_advect_rigid_impl(h, f0 + i, stream) || fmpm_p2g_rigid(h, f0 + i + 1, -1, nullptr, stream))) return 1;
   }
   if (fmpm_grid_op(h, f0 + n - 1, 1, stream) || fmpm_g2p(h, f0 + n - 1, stream)) return 1;

@@ -6,7 +6,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include "fmpm_common.cuh"
 
-#define FMPM_ABI_VERSION 1
+#define FMPM_ABI_VERSION 2
 
 extern "C" int fmpm_abi_version(void) { return FMPM_ABI_VERSION; }
 
@@ -14,7 +14,7 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
   if (!cfg || !out) return 1;
   FmpmHandle* h = new (std::nothrow) FmpmHandle();
   if (!h) return 1;
-  h->cfg = *cfg; h->bound = false; h->err[0] = 0; h->sm_count = 148;
+  h->cfg = *cfg; h->bound = false; h->err[0] = 0; h->sm_count = 148; h->fwd_mask = ~0;
   memset(&h->buf, 0, sizeof(h->buf));
   memset(&h->col, 0, sizeof(h->col));
   memset(&h->slab, 0, sizeof(h->slab));

@@ -15,7 +15,6 @@
 #include <cuda_runtime.h>
 
 #define SC_FULL 0xffffffffu
-#define SC_WSTR 33
 
 #ifdef FMPM_HOST_EMU   // host build of the CUDA execution-model tests (tests/cuda_emu/): no PTX there
 __device__ __forceinline__ void red_add_v4(float4* addr, const float4& v) { atomicAdd(&addr->x, v.x); atomicAdd(&addr->y, v.y); atomicAdd(&addr->z, v.z); atomicAdd(&addr->w, v.w); }
@@ -42,12 +41,14 @@ __device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
 }
 #endif
 
-#define SC_REC 10
+#define SC_REC 9           // float4 records per particle: 36-word stride, so the 128-bit stores of lane = particle are bank-conflict free
+#define SC_WQ 7            // float4 per particle of stencil weights (27 + 1 pad): 28-word stride, conflict free as well
 struct __align__(16) ScatterSmem {
-  // per particle: nine Q_ab = (q + a*B[:,0] + b*B[:,1], m) for the (a,b) node columns of the stencil, then (B02,B12,B22,0):
+  // per particle: nine Q_ab = (q + a*B[:,0] + b*B[:,1], m) for the (a,b) node columns of the stencil and b2 = (B02,B12,B22,0):
   // a lane (a,b,c) needs only Q_ab + c*B[:,2], i.e. 2 LDS.128 + 1 LDS and 4 FFMA2 per particle
   float4 rec[32 * SC_REC];
-  float w[27 * SC_WSTR + 5];   // w[node*33 + particle]: conflict-free for lane=particle stores and lane=node loads
+  float4 b2[32];
+  float4 w[32 * SC_WQ];      // ((float*)w)[particle*28 + node]: lane = particle writes 7 x STS.128, lane = node reads consecutive words
   int key[32];
 };
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ void window_init(Window& W, const int lane, const int
   const int a = L / 9, b = (L / 3) % 3, c = L % 3;
   W.oa = (float)a; W.ob = (float)b; W.oc = (float)c; W.a = a; W.b = b; W.c = c;
   W.lane_valid = lane < 27;
-  W.wrow = L * SC_WSTR; W.qidx = a * 3 + b;
+  W.wrow = L; W.qidx = a * 3 + b;
   W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
   W.cur_key = -1; W.node = 0;
   W.n = n; W.nb = n >> 3; W.flags = flags;
@@ -130,50 +131,71 @@ __device__ __forceinline__ void window_move(Window& W, const int key, float4* __
 }
 
 // lane = particle.  key < 0: the particle contributes nothing (unused / out of grid / beyond N).
-// The 32 records are staged in ascending key order (stable counting rank inside the warp, one warp-uniform pass per distinct
-// key), so the node-mode pass sees every cell of the warp as ONE run even when the global cell sort is a few substeps old
-// (particles that changed cell since the last sort would otherwise split their neighbours' runs: each split costs a 27-node
-// flush).  With a fresh sort rank == lane.  Returns the mask of staged positions at which a new cell run starts.
+// The 32 records are staged in ascending key order (stable rank inside the warp), so the node-mode pass sees every cell of the warp as
+// ONE run even when the global cell sort is a few substeps old (particles that changed cell since the last sort would otherwise split
+// their neighbours' runs: each split costs a 27-node flush).  Warps whose keys are already non-decreasing (always the case right after a
+// sort) take a 6-instruction path: rank == lane.  Otherwise MATCH.ANY groups equal keys and one short warp-uniform loop over the group
+// leaders counts, per lane, the particles with a smaller key.  Returns the mask of staged positions at which a new cell run starts.
 // ALL 32 lanes must call.
+__device__ __forceinline__ unsigned scatter_rank(const int lane, const int key, const int carry_key, int& rank) {
+  const int skey = key >= 0 ? key : 0x7fffffff;   // particles without a cell go last and add zeros to the last run
+  const int prev = __shfl_up_sync(SC_FULL, skey, 1);
+  const bool valid = key >= 0;
+  if (__ballot_sync(SC_FULL, lane > 0 && prev > skey) == 0u) {   // warp-uniform
+    rank = lane;
+    return __ballot_sync(SC_FULL, valid && (lane == 0 ? skey != carry_key : skey != prev));
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned same = __match_any_sync(SC_FULL, skey);
+  const bool leader = (same & lt) == 0u;
+  unsigned leaders = __ballot_sync(SC_FULL, leader);
+  int less = 0;
+  while (leaders != 0u) {   // warp-uniform: one pass per distinct key
+    const int L = __ffs(leaders) - 1;
+    leaders &= leaders - 1u;
+    const int k = __shfl_sync(SC_FULL, skey, L);
+    const unsigned g = __shfl_sync(SC_FULL, same, L);
+    if (k < skey) less += __popc(g);
+  }
+  rank = less + __popc(same & lt);
+  // a run starts at position `less` of every distinct valid key, except when the smallest key continues the window's current cell
+  const bool st = leader && valid && !(less == 0 && skey == carry_key);
+  return __reduce_or_sync(SC_FULL, st ? (1u << less) : 0u);
+}
 __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int lane, const int key, const int carry_key, const float* q,
                                                     const float* B, const float m, const float w[3][3]) {
+  int rank;
+  const unsigned starts = scatter_rank(lane, key, carry_key, rank);
   const bool valid = key >= 0;
-  const int skey = valid ? key : 0x7fffffff;   // particles without a cell go last and add zeros to the last run
-  const unsigned lt = (1u << lane) - 1u;
-  unsigned remaining = SC_FULL, starts = 0u;
-  int base = 0, rank = 0, prevk = carry_key, mykey = carry_key;
-  while (remaining != 0u) {   // warp-uniform: ascending distinct keys
-    const bool pend = (remaining >> lane) & 1u;
-    const int kmin = __reduce_min_sync(SC_FULL, pend ? skey : 0x7fffffff);
-    const unsigned grp = __ballot_sync(SC_FULL, pend && skey == kmin);
-    if (kmin != 0x7fffffff) {
-      if (kmin != prevk) starts |= 1u << base;
-      prevk = kmin;
-    }
-    if (pend && skey == kmin) { rank = base + __popc(grp & lt); mykey = prevk; }
-    base += __popc(grp);
-    remaining &= ~grp;
-  }
+  // Q_ab = q + a*B[:,0] + b*B[:,1] in packed (x,y) / (z,m) pairs
+  const float2 c0a = make_float2(B[0], B[3]), c0b = make_float2(B[6], 0.f);
+  const float2 c1a = make_float2(B[1], B[4]), c1b = make_float2(B[7], 0.f);
+  float4* rec = S.rec + rank * SC_REC;
 #pragma unroll
   for (int a = 0; a < 3; a++) {
-    const float fa = (float)a;
-    const float qa0 = fmaf(fa, B[0], q[0]), qa1 = fmaf(fa, B[3], q[1]), qa2 = fmaf(fa, B[6], q[2]);
+    const float2 fa = make_float2((float)a, (float)a);
+    const float2 qa01 = ffma2(fa, c0a, make_float2(q[0], q[1])), qa2m = ffma2(fa, c0b, make_float2(q[2], m));
 #pragma unroll
     for (int b = 0; b < 3; b++) {
-      const float fb = (float)b;
-      S.rec[rank * SC_REC + a * 3 + b] = make_float4(fmaf(fb, B[1], qa0), fmaf(fb, B[4], qa1), fmaf(fb, B[7], qa2), m);
+      const float2 fb = make_float2((float)b, (float)b);
+      const float2 r01 = ffma2(fb, c1a, qa01), r2m = ffma2(fb, c1b, qa2m);
+      rec[a * 3 + b] = make_float4(r01.x, r01.y, r2m.x, r2m.y);
     }
   }
-  S.rec[rank * SC_REC + 9] = make_float4(B[2], B[5], B[8], 0.f);
+  S.b2[rank] = make_float4(B[2], B[5], B[8], 0.f);
+  float wn[28];
 #pragma unroll
   for (int a = 0; a < 3; a++)
 #pragma unroll
     for (int b = 0; b < 3; b++) {
       const float wab = valid ? w[a][0] * w[b][1] : 0.f;
 #pragma unroll
-      for (int c = 0; c < 3; c++) S.w[(a * 9 + b * 3 + c) * SC_WSTR + rank] = valid ? wab * w[c][2] : 0.f;
+      for (int c = 0; c < 3; c++) wn[a * 9 + b * 3 + c] = wab * w[c][2];   // w is all-zero for particles without a cell
     }
-  S.key[rank] = mykey;
+  wn[27] = 0.f;
+#pragma unroll
+  for (int k = 0; k < SC_WQ; k++) S.w[rank * SC_WQ + k] = make_float4(wn[4 * k], wn[4 * k + 1], wn[4 * k + 2], wn[4 * k + 3]);
+  S.key[rank] = key;
   return starts;
 }
 
@@ -183,14 +205,15 @@ __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int la
 __device__ __forceinline__ void window_consume(Window& W, const ScatterSmem& S, const int cnt, const unsigned starts, float4* __restrict__ grid) {
   const float2 oc2 = make_float2(W.oc, W.oc);
   const int ngroups = (cnt + 3) >> 2;
+  const float* wf = reinterpret_cast<const float*>(S.w) + W.wrow;
 #pragma unroll 1
   for (int g = 0; g < ngroups; g++) {
     float2 t01[4], t2m[4], w2[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int p = g * 4 + u;
-      const float4 Q = S.rec[p * SC_REC + W.qidx], B2 = S.rec[p * SC_REC + 9];
-      const float w = S.w[W.wrow + p];
+      const float4 Q = S.rec[p * SC_REC + W.qidx], B2 = S.b2[p];
+      const float w = wf[p * (4 * SC_WQ)];
       w2[u] = make_float2(w, w);
       t01[u] = ffma2(make_float2(B2.x, B2.y), oc2, make_float2(Q.x, Q.y));
       t2m[u] = ffma2(make_float2(B2.z, B2.w), oc2, make_float2(Q.z, Q.w));
@@ -241,9 +264,10 @@ __device__ __forceinline__ void footprint_load(const float4* __restrict__ grid, 
 
 // Separable evaluation of  v' = sum w g,  C' = 4 inv_dx sum w g (o - fx)^T  (MPM:409-416): reduce the three nodes of a
 // z-column first (G0 = sum_k wz g, G1 = sum_k wz (k - fz) g), then fold the 9 columns in.  Packed FFMA2 throughout.
-// `col(c)` returns a pointer to the three consecutive v_out nodes of stencil column c = i*3+j for this particle.
+// `col3(c)` returns (by value) the three consecutive v_out nodes of stencil column c = i*3+j for this particle.
+struct Col3 { float4 g0, g1, g2; };
 template <class ColFn>
-__device__ __forceinline__ void g2p_gather(const float* fx, const float w[3][3], ColFn col, float* nv, Mat3& nC, const float c4) {
+__device__ __forceinline__ void g2p_gather_v(const float* fx, const float w[3][3], ColFn col3, float* nv, Mat3& nC, const float c4) {
   const float2 wz0 = make_float2(w[0][2], w[0][2]), wz1 = make_float2(w[1][2], w[1][2]), wz2 = make_float2(w[2][2], w[2][2]);
   const float wd0 = w[0][2] * (0.f - fx[2]), wd1 = w[1][2] * (1.f - fx[2]), wd2 = w[2][2] * (2.f - fx[2]);
   const float2 wzd0 = make_float2(wd0, wd0), wzd1 = make_float2(wd1, wd1), wzd2 = make_float2(wd2, wd2);
@@ -254,8 +278,8 @@ __device__ __forceinline__ void g2p_gather(const float* fx, const float w[3][3],
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      const float4* c = col(i * 3 + j);
-      const float4 g0 = c[0], g1 = c[1], g2 = c[2];
+      const Col3 c = col3(i * 3 + j);
+      const float4 g0 = c.g0, g1 = c.g1, g2 = c.g2;
       float2 G0xy = fmul2(make_float2(g0.x, g0.y), wz0); G0xy = ffma2(make_float2(g1.x, g1.y), wz1, G0xy); G0xy = ffma2(make_float2(g2.x, g2.y), wz2, G0xy);
       float2 G1xy = fmul2(make_float2(g0.x, g0.y), wzd0); G1xy = ffma2(make_float2(g1.x, g1.y), wzd1, G1xy); G1xy = ffma2(make_float2(g2.x, g2.y), wzd2, G1xy);
       float2 Gz = fmul2(make_float2(g0.z, g0.z), wzz0); Gz = ffma2(make_float2(g1.z, g1.z), wzz1, Gz); Gz = ffma2(make_float2(g2.z, g2.z), wzz2, Gz);  // (G0_z, G1_z)
@@ -273,5 +297,10 @@ __device__ __forceinline__ void g2p_gather(const float* fx, const float w[3][3],
   nC.m[0] = c4 * c00_10.x; nC.m[1] = c4 * c01_11.x; nC.m[2] = c4 * c02_12.x;
   nC.m[3] = c4 * c00_10.y; nC.m[4] = c4 * c01_11.y; nC.m[5] = c4 * c02_12.y;
   nC.m[6] = c4 * c20_21.x; nC.m[7] = c4 * c20_21.y; nC.m[8] = c4 * v2c22.y;
+}
+// `col(c)` returns a pointer to the three consecutive v_out nodes of stencil column c
+template <class ColFn>
+__device__ __forceinline__ void g2p_gather(const float* fx, const float w[3][3], ColFn col, float* nv, Mat3& nC, const float c4) {
+  g2p_gather_v(fx, w, [&](int c) { const float4* p = col(c); Col3 r; r.g0 = p[0]; r.g1 = p[1]; r.g2 = p[2]; return r; }, nv, nC, c4);
 }
 

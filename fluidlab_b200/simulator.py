@@ -180,6 +180,9 @@ class MPMSimulator:
         self._blk_flags = torch.zeros((nblk,), dtype=i32, device=dev)
         self._blk_list = torch.zeros((nblk,), dtype=i32, device=dev)
         self._blk_count = torch.zeros((1,), dtype=i32, device=dev)
+        # forward-only fused substeps with grid_op inlined (csrc/fmpm_forward.cu: k_fwd): three accumulators + their block flags
+        self._grid_pm3 = torch.zeros((3, G, 4), dtype=f32, device=dev)
+        self._blk_flags3 = torch.zeros((3, nblk), dtype=i32, device=dev)
         self._ga = self._gf = self._gf8 = self._ggrid_v = self._ggrid_pm = None
         self._pm_ring = self._v_ring = self._blk_list_ring = self._blk_count_ring = None
         self._ring_valid = [False] * T
@@ -200,11 +203,16 @@ class MPMSimulator:
         cfg.restitution = b.restitution; cfg.lock_mask = b.lock_mask
         cfg.n_materials = len(uniq)
         cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        # every table row a mu = 0 liquid (WATER / MILK / COFFEE ...): the fused forward substeps carry F = J^(1/3) I as one float (MPM:358-359)
+        all_liquid = all(int(table[r]['cls']) == 200 and float(table[r]['mu']) == 0.0 for r in range(len(uniq)))
+        cfg.scene_flags = _lib.SCENE_ALL_LIQUID_MU0 if all_liquid else 0
         h = C.c_void_p()
         rc = lib.fmpm_create(C.byref(cfg), C.byref(h))
         self._h = h
         self._ck(rc, 'fmpm_create')
         self._sort_tmp = torch.empty((int(lib.fmpm_sort_workspace_bytes(h)),), dtype=torch.uint8, device=dev)
+        if os.environ.get('FMPM_FWD_MASK'):   # A/B of the forward kernels (profiles/): bit 0 k_fwd, 1 liquid specialisation, 2 inlined grid_op, 3 TMA tiles
+            self._ck(lib.fmpm_set_fwd_mask(h, int(os.environ['FMPM_FWD_MASK'])), 'fmpm_set_fwd_mask')
         self._bind()
         if self._has_rigid_bodies:
             self._body_info = torch.from_numpy(self._body_info_np).to(dev)
@@ -237,6 +245,7 @@ class MPMSimulator:
         b.blk_flags, b.blk_list, b.blk_count = p(self._blk_flags), p(self._blk_list), p(self._blk_count)
         b.grid_pm_ring, b.grid_v_ring = p(self._pm_ring), p(self._v_ring)
         b.blk_list_ring, b.blk_count_ring = p(self._blk_list_ring), p(self._blk_count_ring)
+        b.grid_pm3, b.blk_flags3 = p(getattr(self, '_grid_pm3', None)), p(getattr(self, '_blk_flags3', None))
         self._ck(self._lib.fmpm_bind(self._h, C.byref(b)), 'fmpm_bind')
 
     def register_colliders(self):

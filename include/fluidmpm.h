@@ -64,7 +64,11 @@ typedef struct {
   int lock_mask;          /* bit d: lock_dims contains d */
   int n_materials;        /* rows in the material table */
   int device;             /* CUDA device ordinal */
+  int scene_flags;        /* FMPM_SCENE_* bits: what the host knows about the whole particle set (0 = nothing assumed) */
 } FmpmConfig;
+/* every row of the material table is a MAT_LIQUID with mu == 0 (WATER, MILK, COFFEE, ...: macros.py:131-201): the forward-only fused
+ * substeps then skip the SVD entirely and carry F = J^(1/3) I (MPM:358-359) as one float per particle between step boundaries */
+#define FMPM_SCENE_ALL_LIQUID_MU0 1
 
 /* one row per distinct (material, rho): replaces particles_i.{mu,lam,mass,mat_cls} (MPM:96-103,170-175) */
 typedef struct { float mu, lam, mass; int cls; } FmpmMaterial;
@@ -87,6 +91,11 @@ typedef struct {
    * fmpm_substep_store(f) leaves the (momentum, mass) and v_out grids of frame f in slot f; fmpm_substep_grad_stored(f) reads them.
    * The reference keeps a grid per frame too (MPM:117), 56 B/node dense; here 32 B/node and only touched blocks are rewritten. */
   void* grid_pm_ring; void* grid_v_ring; void* blk_list_ring; void* blk_count_ring;
+  /* optional (both NULL = off): three (momentum, mass) accumulators float4[3][G] + their block flags int[3][(n_grid/8)^3], all zero.
+   * With them fmpm_substeps_fused evaluates grid_op inside the fused gather / scatter kernel (one launch per substep; scenes without SDF
+   * colliders at grid level): the launch of frame f gathers from accumulator f % 3, scatters frame f+1 into (f+1) % 3 and clears (f+2) % 3.
+   * All three are clear again when fmpm_substeps_fused returns. */
+  void* grid_pm3; void* blk_flags3;
 } FmpmBuffers;
 
 /* effector pose chain, fluidlab/fluidengine/effectors/effector.py:34-51 (fields), :157-161 (move_kernel),
@@ -196,6 +205,11 @@ int fmpm_substep_store(FmpmHandle* h, int f, void* stream);            /* same, 
 int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream);
 /* n substeps f0..f0+n-1: p2g(f0), [grid_op, g2p2g] x (n-1), grid_op, g2p(f0+n-1); frames f0 and f0+n are complete */
 int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream);
+/* which kernels fmpm_substeps_fused uses for this handle (bit 0: k_fwd instead of k_g2p2g, bit 1: all-liquid specialisation, bit 2: grid_op
+ * inlined with the triple-buffered accumulators, bit 3: footprint tiles staged by TMA); `mask` clears bits for A/B measurements
+ * (fmpm_set_fwd_mask(h, 0) = the round-1 path: grid_op + k_g2p2g).  Default mask: all bits set. */
+int fmpm_fwd_path(FmpmHandle* h);
+int fmpm_set_fwd_mask(FmpmHandle* h, int mask);
 /* the same in grad mode with per-frame grids (like fmpm_substep_store): every frame is written completely, slot f+1's grids are cleared and
  * refilled by the fused kernel: 148 B instead of 212 B per particle and substep, 3 launches instead of 4 */
 int fmpm_substeps_fused_store(FmpmHandle* h, int f0, int n, void* stream);

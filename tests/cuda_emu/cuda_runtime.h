@@ -242,6 +242,12 @@ template <class T> static inline T __reduce_min_sync(unsigned mask, T x) {
 template <class T> static inline T __reduce_max_sync(unsigned mask, T x) {
   return cuemu_collective(x, [&](auto get, int) { T m = x; for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) m = std::max(m, get(l)); return m; });
 }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned x) {
+  return cuemu_collective(x, [&](auto get, int) { unsigned m = 0; for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) m |= get(l); return m; });
+}
+template <class T> static inline unsigned __match_any_sync(unsigned mask, T x) {
+  return cuemu_collective(x, [&](auto get, int) { unsigned m = 0; for (int l = 0; l < 32; l++) if (((mask >> l) & 1u) && get(l) == x) m |= 1u << l; return m; });
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 template <class T> static inline T __ldcs(const T* p) { return *p; }

@@ -536,3 +536,13 @@ def test_graft_entry_smoke_runs_on_the_emulated_device(emu, monkeypatch):
     monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
     import __graft_entry__ as g
     g.smoke()
+
+
+@pytest.mark.parametrize('liquid,boundary,sort_every', [(False, 'cube', 1), (True, 'cube', 1), (True, 'cylinder', 0), (False, 'cylinder', 2)],
+                         ids=['multimat', 'liquid', 'liquid-cyl-unsorted', 'multimat-cyl-sort2'])
+def test_every_forward_path_of_fmpm_substeps_fused_equals_the_plain_substeps_and_the_oracle(emu, liquid, boundary, sort_every):
+    """k_fwd (g2p + [grid_op] + p2g in one kernel) with each feature switched on in turn — all-liquid specialisation (F carried as one float
+    between step boundaries), grid_op inlined over the triple-buffered accumulators — against the plain substeps and the fp64 oracle
+    (tests/fwd_path_case.py; the same body runs on a B200 in tests/test_gpu_parity.py)."""
+    import fwd_path_case
+    fwd_path_case.run('cpu', liquid, [0, 1, 3, 5, 7] if liquid else [0, 1, 5], boundary=boundary, sort_every=sort_every)

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f'{name} declared in include/fluidmpm.h but not exported'
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert L.fmpm_abi_version() == 1
+    assert L.fmpm_abi_version() == 2
     hdr = open(os.path.join(ROOT, 'include', 'fluidsmoke.h')).read()
     declared = set(re.findall(r'\b(fsmk_[a-z0-9_]+)\s*\(', hdr))
     for name in sorted(declared):
