@@ -85,14 +85,34 @@ class ClockSampler:
                 'samples': len(self.samples)}
 
 
+def host_cores():
+    """cores this process may run on (cgroup / affinity aware)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def oracle_lib_all_cores():
+    """the CPU oracle with ALL host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which round 1's reference arm inherited at N > 1
+    (cpu_baseline.cores = 1).  Threads are pinned one per core (the unpinned runs swung 3x between hosts); the OpenMP runtime reads the binding
+    variables when liboracle.so is loaded, so they are set before that."""
+    os.environ.setdefault('OMP_PROC_BIND', 'spread')
+    os.environ.setdefault('OMP_PLACES', 'cores')
+    os.environ['OMP_NUM_THREADS'] = str(host_cores())
+    from oracle import oracle as orc
+    L = orc.lib()
+    L.orc_set_threads(host_cores())
+    return orc, L
+
+
 def cpu_baseline_run(n_particles, max_seconds=15.0, max_substeps=60, threads=None):
     """Time the CPU oracle (restatement of mpm_simulator.py:515-533, fp32, OpenMP) on the same workload."""
     from conftest import make_particles
-    from oracle import oracle as orc
     from fluidlab_b200 import macros as M
     wp = workload_particles(n_particles)
     P = make_particles(wp['x'], M.WATER, 64 * QUALITY)
-    L = orc.lib()
+    orc, L = oracle_lib_all_cores()
     if threads:
         L.orc_set_threads(int(threads))
     cores = L.orc_get_max_threads()
@@ -107,20 +127,40 @@ def cpu_baseline_run(n_particles, max_seconds=15.0, max_substeps=60, threads=Non
                        'C++/OpenMP restatement of the reference algorithm (Taichi ti.cpu is not installable)')
 
 
+def slab_layout(world, rank, N):
+    """the multi-GPU arm's workload: one water body on a 256^3 grid cut into `world` x-slabs of N particles each (weak scaling)"""
+    from fluidlab_b200.slab import slab_bounds
+    q = 4; n = 64 * q; dx = 1.0 / n; slab_w = 24
+    bounds = slab_bounds(32, 32 + slab_w * world, world)
+    lo = ((bounds[rank] - 0.5) * dx, 0.30, 0.36); hi = ((bounds[rank + 1] - 0.5) * dx, 0.30 + 72 * dx, 0.36 + 72 * dx)
+    return q, bounds, lo, hi
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path = oracle port, all host threads; each bench step is a bounded sample of
-    ONE substep of the workload (a full 10-substep step at 1M particles takes ~10 s of CPU)."""
+    """--impl reference: the reference's CPU path = the oracle port on all host cores, on the workload the repo arm runs at this N: C2 at N = 1, the
+    N-slab water body on the 256^3 grid at N > 1 (rank 0 alone computes it; the other ranks exit).  Each bench step is a bounded sample of ONE
+    substep (a 10-substep step of 1M particles is seconds of CPU).  `value` uses the repo arm's unit: 1M-particle substeps/s = N x global substeps/s."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from conftest import make_particles
-    from oracle import oracle as orc
     from fluidlab_b200 import macros as M
-    wp = workload_particles(N_PARTICLES)
-    P = make_particles(wp['x'], M.WATER, 64 * QUALITY)
-    L = orc.lib()
+    orc, L = oracle_lib_all_cores()
+    world = max(1, args.gpus)
+    if world == 1:
+        wp = workload_particles(N_PARTICLES)
+        n_grid, x = 64 * QUALITY, wp['x']
+        workload = 'C2 water block free fall, 1M particles, 128^3 grid, forward'
+    else:
+        xs = []
+        for r in range(world):
+            q, _, lo, hi = slab_layout(world, r, N_PARTICLES)
+            xs.append(workload_particles(N_PARTICLES, seed=r, lo=lo, hi=hi)['x'])
+        n_grid, x = 64 * q, np.concatenate(xs)
+        workload = f'C2-weak: {world} x {N_PARTICLES} water particles as x-slabs of one body, 256^3 grid, forward (the repo arm\'s workload at {world} GPUs)'
+    P = make_particles(x, M.WATER, n_grid)
     cores = L.orc_get_max_threads()
-    o = orc.OracleSim(64 * QUALITY, P, gravity=GRAVITY, max_substeps_local=2, precision=32)
+    o = orc.OracleSim(n_grid, P, gravity=GRAVITY, max_substeps_local=2, precision=32)
     for _ in range(max(1, min(args.warmup, 2))):
         o.substep(0)
     K = max(1, min(args.steps, 20))
@@ -128,13 +168,14 @@ def run_reference(args):
     for i in range(K):
         o.substep(i % 2)
     dt = time.perf_counter() - t0
-    val = K / dt
+    val = world * K / dt
     line = {'metric': 'mpm_substeps_per_s_fwd', 'value': val, 'unit': 'substeps/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': args.warmup,
             'ms_per_step': 1e3 * dt / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'impl': 'reference',
-            'config': {'workload': 'C2 water block free fall, 1M particles, 128^3 grid, forward', 'step': '1 substep (bounded sample)'},
+            'config': {'workload': workload, 'step': '1 substep (bounded sample)', 'same_config_as_repo_arm': True},
             'cpu_baseline': {'value': val, 'unit': 'substeps/s', 'cores': int(cores), 'kind': 'port',
-                             'sample': f'{K} forward substeps, full workload, C++/OpenMP restatement of the reference (Taichi not installable)'},
+                             'sample': f'{K} forward substeps of the full workload ({len(x)} particles, {n_grid}^3 grid), threads pinned one per core; '
+                                       'C++/OpenMP restatement of the reference (Taichi not installable)'},
             'e2e': {'value': val, 'unit': 'substeps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -148,8 +189,9 @@ def main():
     ap.add_argument('--particles', type=int, default=N_PARTICLES)
     ap.add_argument('--bwd', type=int, default=1, help='also time forward+backward (extra keys)')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--fuse-g2p2g', type=int, default=0, help='1: forward steps use fmpm_substeps_fused (inner g2p / p2g pairs in one kernel; verified on the CPU '
-                    'execution-model shim, not yet measured on a B200 — A/B it against the default before switching)')
+    ap.add_argument('--min-seconds', type=float, default=1.0, help='minimum length of the timed region (the K steps are repeated)')
+    ap.add_argument('--fuse-g2p2g', type=int, default=1, help='1 (default, measured faster: profiles/README.md): forward steps use fmpm_substeps_fused (the gather of substep f and the '
+                    'scatter of f+1 in one kernel, k_fwd); 0: the plain p2g / grid_op / g2p substeps')
     ap.add_argument('--sort-every', type=int, default=4, help='cell-sort period in steps (measured with the warp-local key ranking: 1 -> 7.14k, 2 -> 7.43k, 4 -> 7.60k, 8 -> 7.44k substeps/s)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -177,16 +219,25 @@ def main():
         parts = workload_particles(N, seed=rank)
         sim.build(None, None, [], parts)
         sim.fuse_g2p2g = bool(args.fuse_g2p2g)
-        step_fn = lambda: sim.step(None)
+        # The block falls 0.25 of the domain: free fall lasts ~110 steps (SURVEY.md 8d times 1,000 substeps after 100 warm-up).  Longer timed regions
+        # replay that episode: every EPISODE steps the initial state is restored from a device-side copy INSIDE the timed region (~0.1 % of the time).
+        EPISODE = 100
+        _cnt1 = [0]
+        _init1 = [None]
+
+        def step_fn():
+            if _init1[0] is not None and _cnt1[0] and _cnt1[0] % EPISODE == 0:
+                sim.cur_substep_global = 0
+                sim.set_state(0, _init1[0])
+            _cnt1[0] += 1
+            sim.step(None)
         workload = f'C2 water block free fall, {N} particles, 128^3 grid, fp32, forward (BASELINE.json configs[1])'
         parallelism = 'single GPU'
     else:
         # weak scaling: the C2 block (same particle count and ~8 particles/cell per GPU) laid out as x-slabs of one global
         # water body on a 256^3 grid; ghost planes of the (momentum, mass) grid are summed between neighbours every substep.
-        from fluidlab_b200.slab import SlabMPMSimulator, slab_bounds
-        q = 4; n = 64 * q; dx = 1.0 / n; slab_w = 24
-        bounds = slab_bounds(32, 32 + slab_w * world, world)
-        lo = ((bounds[rank] - 0.5) * dx, 0.30, 0.36); hi = ((bounds[rank + 1] - 0.5) * dx, 0.30 + 72 * dx, 0.36 + 72 * dx)
+        from fluidlab_b200.slab import SlabMPMSimulator
+        q, bounds, lo, hi = slab_layout(world, rank, N)
         parts = workload_particles(N, seed=rank, lo=lo, hi=hi)
         slab = SlabMPMSimulator(q, GRAVITY, parts, gid=np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1), max_substeps_local=T, device=dev,
                                 exchange=os.environ.get('SLAB_EXCHANGE', 'peer'), sync=os.environ.get('SLAB_SYNC', 'barrier'))
@@ -214,6 +265,8 @@ def main():
         else:
             parallelism = (f'{world} x-slabs; NCCL pair all-reduce of {slab.ghost.bytes_per_exchange()} B of ghost planes per rank per substep; per-step migration')
     init = sim.get_state()
+    if slab is None:
+        _init1[0] = {k: v.clone() for k, v in sim.readframe_torch(0).items()}
     def barrier():
         if world > 1:
             dist.barrier()
@@ -230,14 +283,24 @@ def main():
     for _ in range(W):
         step_fn()
     barrier()
+    # the timed region is `reps` x K steps, reps chosen (from one untimed probe of K steps, agreed across ranks) so that it lasts >= --min-seconds
+    # and covers >= 1,000 substeps whatever --steps is (round 1's 20-step region was 29 ms)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(K):
+        step_fn()
+    p1.record(); barrier()
+    probe_ms = max_over_ranks(p0.elapsed_time(p1))
+    reps = max(1, int(np.ceil(args.min_seconds * 1e3 / max(probe_ms, 1e-3))), int(np.ceil(1000 / (K * SUBSTEPS_PER_STEP))))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as cs:
         e0.record()
-        for _ in range(K):
+        for _ in range(K * reps):
             step_fn()
         e1.record()
         barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms = ms_total / reps            # per K steps
     clocks = cs.summary()
     value = world * K * SUBSTEPS_PER_STEP / (ms * 1e-3)
 
@@ -330,10 +393,16 @@ def main():
     peak, peak_src = peaks()
     p2g_bytes = 136 * used + 16 * g_t            # p2g particle bytes + accumulated grid write-back
     g2p_bytes = 76 * used + 12 * g_t             # g2p(+advect)
-    traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tp) and world == 1 and N == N_PARTICLES:
-        traffic = json.load(open(tp)).get('k_p2g')  # from the committed ncu --set full capture of this same workload
+    def traffic_of(kernel):
+        """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures of this same workload"""
+        for name in ('r02_traffic.json', 'r01_traffic.json'):
+            tp = os.path.join(ROOT, 'profiles', name)
+            if os.path.exists(tp) and world == 1 and N == N_PARTICLES:
+                v = json.load(open(tp)).get(kernel)
+                if v is not None:
+                    return v
+        return None
+    traffic = traffic_of('k_p2g')
     roof = {'bound': 'hbm', 'kernel': 'k_p2g', 'achieved': p2g_bytes / (t_p2g * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
             'frac': p2g_bytes / (t_p2g * 1e-3) / 1e9 / peak, 'traffic': traffic, 'peak_source': peak_src,
             'algorithmic_bytes_per_launch': p2g_bytes, 'launch_ms': t_p2g, 'n_used': used, 'touched_nodes': g_t, 'timing': timing_note}
@@ -341,39 +410,56 @@ def main():
                  'frac': (p2g_bytes + g2p_bytes) / ((t_p2g + t_g2p) * 1e-3) / 1e9 / peak, 'p2g_ms': t_p2g, 'g2p_ms': t_g2p, 'grid_op_ms': t_gop,
                  'bytes': p2g_bytes + g2p_bytes, 'ms_by_steps_since_sort': sort_age}
 
-    # the fused path's own figure: mean launch time of k_g2p2g over a replay of the timed trajectory on the per-phase path.  One fused launch
-    # does the work SURVEY 8(d) counts for p2g + g2p of a substep (212 B x N_u + 28 B x G_t), so `achieved` uses that figure: the fraction is
-    # comparable with roofline_p2g_g2p.  (The bytes the fused kernel itself must move are fewer: 104 B x N_u + 28 B x G_t.)
+    # The fused path's own figures: the timed trajectory replayed launch by launch (fmpm_p2g, then [fmpm_grid_op, fmpm_fwd_step] x 9, fmpm_grid_op,
+    # fmpm_g2p: exactly what fmpm_substeps_fused enqueues) with CUDA events around every launch.  One fused launch does the work SURVEY 8(d)
+    # counts for p2g + g2p of a substep (212 B x N_u + 28 B x G_t), so `achieved` uses that figure and the fraction is comparable with
+    # roofline_p2g_g2p; the bytes the kernel itself moves are fewer and stated.  Event-bracketed launches read a few per cent longer than the
+    # same launches inside the CUDA graph of the timed region (round 1's verdict: 153.9 vs 145.3 us per substep), so every launch time is
+    # also given scaled by graph substep time / replayed substep time (`launch_ms`, used for `frac`; the raw mean is `launch_ms_events`).
     roof_fused = None
     if slab is None and args.fuse_g2p2g:
         try:
-            evf = []
+            L_, h_, st_ = sim._lib, sim._h, sim._stream
+            path = int(L_.fmpm_fwd_path(h_))
+            ev = lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            e_fused, e_gop, e_p2g, e_g2p, e_step = [], [], [], [], []
             sim.cur_substep_global = 0
             sim.set_state(0, init)
             for i in range(W + K):
+                es = ev(); es[0].record()
                 if sim.sort_every > 0 and sim.cur_step_global % sim.sort_every == 0:
                     sim.sort_frame(sim.cur_substep_local)
                 f0 = sim.cur_substep_local
-                sim.phase('p2g', f0, 1)
+                e = ev(); e[0].record(); sim.phase('p2g', f0, 1); e[1].record(); e_p2g.append(e)
                 for j in range(SUBSTEPS_PER_STEP):
                     fj = f0 + j
-                    sim.phase('grid_op', fj, 1)
+                    e = ev(); e[0].record(); sim.phase('grid_op', fj, 1); e[1].record(); e_gop.append(e)
+                    e = ev(); e[0].record()
                     if j + 1 < SUBSTEPS_PER_STEP:
-                        e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                        e[0].record(); sim.phase('g2p2g', fj); e[1].record()
-                        if i >= W:
-                            evf.append(e)
+                        sim._ck(L_.fmpm_fwd_step(h_, fj, int(j + 2 == SUBSTEPS_PER_STEP), st_()), 'fmpm_fwd_step'); e[1].record(); e_fused.append(e)
                     else:
-                        sim.phase('g2p', fj)
+                        sim.phase('g2p', fj); e[1].record(); e_g2p.append(e)
+                    sim._frame_ord[fj + 1] = sim._frame_ord[fj]
                     sim.cur_substep_global += 1
+                es[1].record(); e_step.append(es)
                 if sim.cur_substep_local == 0:
                     sim.memory_to_cache()
             torch.cuda.synchronize()
-            t_fused = float(np.mean([a.elapsed_time(b) for a, b in evf]))
+            mean = lambda evs: float(np.mean([a.elapsed_time(b) for a, b in evs[W * (len(evs) // (W + K)):]]))
+            t_fused, t_gop_f, t_p2g_f, t_g2p_f, t_step = mean(e_fused), mean(e_gop), mean(e_p2g), mean(e_g2p), mean(e_step)
+            scale = min(1.0, (ms / K) / t_step)     # CUDA-graph step of the timed region / event-bracketed replay of the same step
             pair_bytes = p2g_bytes + g2p_bytes
-            roof_fused = {'bound': 'hbm', 'kernel': 'k_g2p2g', 'achieved': pair_bytes / (t_fused * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                          'frac': pair_bytes / (t_fused * 1e-3) / 1e9 / peak, 'launch_ms': t_fused, 'algorithmic_bytes_per_launch': pair_bytes,
-                          'bytes_the_fused_kernel_moves': 104 * used + 28 * g_t, 'launches_timed': len(evf)}
+            liquid = bool(path & 2)
+            moved = (40 if liquid else 104) * used + 28 * g_t
+            kname = ('k_fwd<all-liquid>' if liquid else 'k_fwd') if path & 1 else 'k_g2p2g'
+            roof_fused = {'bound': 'hbm', 'kernel': kname, 'fwd_path': path, 'achieved': pair_bytes / (t_fused * scale * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                          'frac': pair_bytes / (t_fused * scale * 1e-3) / 1e9 / peak, 'launch_ms': t_fused * scale, 'launch_ms_events': t_fused,
+                          'event_to_graph_scale': scale, 'algorithmic_bytes_per_launch': pair_bytes, 'bytes_the_fused_kernel_moves': moved,
+                          'traffic': traffic_of('k_fwd' if path & 1 else 'k_g2p2g'),
+                          'peak_source': peak_src, 'n_used': used, 'touched_nodes': g_t, 'launches_timed': len(e_fused) * K // (W + K),
+                          'other_launches_ms': {'first_p2g': t_p2g_f * scale, 'grid_op': t_gop_f * scale, 'last_g2p': t_g2p_f * scale},
+                          'substep_ms_graph': ms / K / SUBSTEPS_PER_STEP, 'substep_ms_events': t_step / SUBSTEPS_PER_STEP,
+                          'timing': 'mean over the fused launches of a launch-by-launch replay of the timed trajectory, scaled to the CUDA-graph step time'}
         except Exception as ex:
             roof_fused = {'error': f'{type(ex).__name__}: {ex}'}
 
@@ -507,6 +593,7 @@ def main():
         cpu = None if args.no_cpu else cpu_baseline_run(N)
         line = {
             'metric': 'mpm_substeps_per_s_fwd', 'value': value, 'unit': 'substeps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'timed_steps': K * reps, 'timed_region_ms': ms_total,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': workload,
                        'substeps_per_step': SUBSTEPS_PER_STEP, 'dt': 2e-4, 'gravity': GRAVITY, 'max_substeps_local': T,
@@ -519,7 +606,8 @@ def main():
                     'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},
             'gpu_launches': K * ((2 * SUBSTEPS_PER_STEP + 1) if args.fuse_g2p2g else SUBSTEPS_PER_STEP * 3) + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
             'e2e_obs_bridge': e2e_obs,
-            'roofline': roof, 'roofline_p2g_g2p': roof_pair, 'roofline_g2p2g': roof_fused,
+            'roofline': roof_fused if (roof_fused and 'frac' in roof_fused) else roof,
+            'roofline_unfused_p2g': roof, 'roofline_p2g_g2p': roof_pair, 'roofline_fused': roof_fused,
             'fwd_bwd': fb,
             'cpu_baseline': cpu,
         }

@@ -144,6 +144,7 @@ _PROTOS = {
     "fmpm_g2p2g": (_I, [vp, _I, _I, vp]),
     "fmpm_g2p2g_collect": (_I, [vp, _I, _I, C.POINTER(FmpmCollector), vp]),
     "fmpm_substeps_fused": (_I, [vp, _I, _I, vp]),
+    "fmpm_fwd_step": (_I, [vp, _I, _I, vp]),
     "fmpm_fwd_path": (_I, [vp]),
     "fmpm_set_fwd_mask": (_I, [vp, _I]),
     "fmpm_p2g_injected": (_I, [vp, _I, C.POINTER(FmpmInjector), _I, vp, _I, C.POINTER(FmpmCollector), vp]),

@@ -153,7 +153,8 @@ class AgentRigid(Agent):
         assert isinstance(self.effectors[0], Rigid)
         self.rigid = self.effectors[0]
         assert self.rigid.mesh is not None, 'Rigid effector without a mesh'
-        sim.register_colliders()
+        if sim.has_particles:   # a particle-free scene (e.g. smoke only) has no MPM handle to register colliders with
+            sim.register_colliders()
 
 
 class AgentIceCreamDynamic(Agent):
@@ -174,7 +175,8 @@ class AgentIceCreamDynamic(Agent):
         self.rigid = self.effectors[1]
         self.injector.set_act_range(sim.get_used(0))
         self.injector.finalize()
-        sim.register_colliders()
+        if sim.has_particles:   # a particle-free scene (e.g. smoke only) has no MPM handle to register colliders with
+            sim.register_colliders()
 
     def act(self, f, f_global):
         if f_global < self.inject_till:

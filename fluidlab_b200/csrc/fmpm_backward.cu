@@ -34,15 +34,16 @@ __device__ __forceinline__ void load_grad(const KParams& P, int g, int s, GState
 // =============================================================================================
 // g2p.grad, grid side:  gv_out[i] += w_i * (gv + 4 inv_dx * gC' (o - fx)),  gv = gv' + dt * gx'
 // =============================================================================================
+template <bool kSlab>
 __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParams P, const int f, const int gin) {
   __shared__ ScatterSmem smem[SC_WARPS];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wib = __shfl_sync(SC_FULL, (int)(threadIdx.x >> 5), 0);   // broadcast: dependent code is compiled warp-uniform
   ScatterSmem& S = smem[wib];
   const long long gw = (long long)blockIdx.x * SC_WARPS + wib;
   const long long slot0 = gw * (32 * SC_ROUNDS);
   if (slot0 >= P.N) return;
   Window W; window_init(W, lane, P.n, nullptr);
-  window_set_slab(W, P.peer_gl, P.peer_gr, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, nullptr, nullptr);   // x-slab backward: ghost planes also go to the neighbour
+  if (kSlab) window_set_slab(W, P.peer_gl, P.peer_gr, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, nullptr, nullptr);   // x-slab backward: ghost planes also go to the neighbour
 #pragma unroll 1
   for (int r = 0; r < SC_ROUNDS; r++) {
     const long long rem = (long long)P.N - (slot0 + r * 32);
@@ -70,10 +71,10 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
     }
     const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, 0.f, w);
     __syncwarp();
-    window_consume(W, S, cnt, starts, P.ggrid_v);
+    window_consume2<kSlab>(W, S, cnt, starts, P.ggrid_v);
     __syncwarp();
   }
-  window_flush_all(W, P.ggrid_v);
+  window_flush_all2<kSlab>(W, P.ggrid_v);
 }
 
 // =============================================================================================
@@ -423,7 +424,8 @@ static int g2p_grad_scatter_impl(FmpmHandle* h, int f, int gin, int dense_zero, 
   if (P.N == 0) return 0;
   const long long warps = ((long long)P.N + 32 * SC_ROUNDS - 1) / (32 * SC_ROUNDS);
   const int blocks = (int)((warps + SC_WARPS - 1) / SC_WARPS);
-  FMPM_LAUNCH(k_g2p_grad_scatter, blocks, SC_WARPS * 32, 0, stream, P, f, gin);
+  if (h->slab.enabled) FMPM_LAUNCH(k_g2p_grad_scatter<true>, blocks, SC_WARPS * 32, 0, stream, P, f, gin);
+  else FMPM_LAUNCH(k_g2p_grad_scatter<false>, blocks, SC_WARPS * 32, 0, stream, P, f, gin);
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p_grad_scatter");
   return 0;
 }

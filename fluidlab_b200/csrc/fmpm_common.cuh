@@ -27,6 +27,8 @@ struct FmpmHandle {
   char err[512];
   int sm_count;
   int fwd_mask;   // fmpm_set_fwd_mask
+  int fwd_stride; // 1: no CTA -> slot-block permutation in the lazy-grid_op k_fwd (FMPM_FWD_STRIDE=1)
+  int use_pdl;    // programmatic dependent launch of the forward chain (FMPM_PDL=0 switches it off)
 };
 
 int fmpm_advect_rigid_impl(FmpmHandle* h, int f, void* stream);  // fmpm_rigid.cu; no-op without MAT_RIGID bodies
@@ -45,6 +47,7 @@ struct KParams {
   float4* grid_pm; float4* grid_v; float4* ggrid_v; float4* ggrid_pm;
   const float4* mats;  // (mu, lam, mass, cls-as-int-bits)
   int* blk_flags; int* blk_list; int* blk_count; int nb;  // sparse grid: 8^3-node blocks
+  int* epoch;   // launch epoch of the lazy grid_op (k_fwd, kInline): bumped by the p2g that opens a fused step, see fmpm_forward.cu
   CollidersDev col;
   // x-slab mode: neighbours' accumulators (peer memory over NVLink) and the node-plane ranges shared with them
   float4* peer_l; float4* peer_r; int gl_lo, gl_hi, gr_lo, gr_hi;
@@ -70,6 +73,7 @@ static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1, int 
   P.mats = (const float4*)h->buf.materials;
   P.col = h->col;
   P.blk_flags = (int*)h->buf.blk_flags; P.blk_list = (int*)h->buf.blk_list; P.blk_count = (int*)h->buf.blk_count; P.nb = c.n_grid / 8;
+  P.epoch = nullptr;
   P.peer_l = P.peer_r = nullptr; P.gl_lo = P.gl_hi = P.gr_lo = P.gr_hi = 0; P.peer_fl = P.peer_fr = nullptr; P.peer_gl = P.peer_gr = nullptr;
   if (h->slab.enabled) {  // accumulator double-buffered by substep parity; peers use the same parity
     const size_t off = (size_t)(parity & 1) * P.G;
@@ -88,6 +92,7 @@ static inline KParams make_kparams(const FmpmHandle* h, int ring_slot = -1, int 
     const size_t nblk = (size_t)P.nb * P.nb * P.nb;
     P.grid_pm = (float4*)h->buf.grid_pm3 + (size_t)k * P.G;
     P.blk_flags = (int*)h->buf.blk_flags3 + (size_t)k * nblk;
+    P.epoch = (int*)h->buf.blk_count;   // (a reserved word of FmpmBuffers: int[1], zero-initialised by the caller)
   }
   if (ring_slot >= 0 && h->buf.grid_pm_ring) {
     const size_t nblk = (size_t)P.nb * P.nb * P.nb;
@@ -275,15 +280,15 @@ __device__ __forceinline__ void store_A(float4* __restrict__ base, const KParams
 // the grid (the reference has no bounds check there; such particles are frozen here instead of corrupting memory).
 __device__ __forceinline__ bool base_fx(const KParams& P, const float* x, int* b, float* fx) {
   bool ok = true;
+  const float tmax = (float)(P.n - 2);
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     float g = x[d] * P.inv_dx;
     float t = g - 0.5f;
-    ok = ok && (t > -1.0f) && (t < (float)(P.n - 2));
+    ok = ok && (t > -1.0f) && (t < tmax);   // then 0 <= (int)t <= n - 3: the whole 3x3x3 stencil is inside the grid (false for NaN)
     int bi = (int)t;  // cast(int): truncation toward zero
     b[d] = bi; fx[d] = g - (float)bi;
   }
-  ok = ok && b[0] >= 0 && b[1] >= 0 && b[2] >= 0 && b[0] <= P.n - 3 && b[1] <= P.n - 3 && b[2] <= P.n - 3;
   return ok;
 }
 __device__ __forceinline__ void bspline(const float* fx, float w[3][3]) {
@@ -373,10 +378,29 @@ __device__ __forceinline__ void constitutive(const KParams& P, const PState& st,
 // kernel bodies and the host launch logic run under `pytest -m "not gpu"` (tests/test_cuda_emu_*.py).  nvcc never sees that header.
 #ifdef FMPM_HOST_EMU
 #define FMPM_LAUNCH(kern, grid, block, smem, stream, ...) cuemu::launch(dim3(grid), dim3(block), smem, [&]() { kern(__VA_ARGS__); })
+#define FMPM_LAUNCH_PDL(pdl, kern, grid, block, smem, stream, ...) FMPM_LAUNCH(kern, grid, block, smem, stream, __VA_ARGS__)
 #define FMPM_DYN_SMEM(type, name) type* name = (type*)cuemu::dyn_smem()
+__device__ __forceinline__ void fmpm_pdl_trigger() {}
+__device__ __forceinline__ void fmpm_pdl_wait() {}
 #else
 #define FMPM_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define FMPM_DYN_SMEM(type, name) extern __shared__ type name[]
+// Programmatic dependent launch (the forward substep is a chain of short kernels: p2g, [grid_op, k_fwd] x 9, grid_op, g2p).  A kernel of the
+// chain lets its successor's CTAs become resident as soon as all of its own CTAs have started (fmpm_pdl_trigger at the top), so the launch
+// latency and the tail of the grid are filled with the successor's prologue; the successor touches NO global memory before fmpm_pdl_wait,
+// which returns once the predecessor grid has completed and its writes are visible.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void fmpm_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void fmpm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... Params, class... Args>
+static inline void fmpm_launch_pdl(const bool pdl, void (*kern)(Params...), const int grid, const int block, const size_t smem, void* stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<Params>(args)...);
+}
+#define FMPM_LAUNCH_PDL(pdl, kern, grid, block, smem, stream, ...) fmpm_launch_pdl(pdl, kern, grid, block, smem, stream, __VA_ARGS__)
 #endif
 
 #define FMPM_CHECK_LAUNCH(h, name)                                                        \

@@ -90,16 +90,19 @@ __device__ __forceinline__ void p2g_unpack(const PRaw& R, PState& st) {
   st.F.m[4] = R.f1.x; st.F.m[5] = R.f1.y; st.F.m[6] = R.f1.z; st.F.m[7] = R.f1.w; st.F.m[8] = R.f8;
 }
 
-template <bool kWriteF>
+template <bool kWriteF, bool kSlab>
 __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams P, const int f) {
   __shared__ ScatterSmem smem[P2G_WARPS];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wib = __shfl_sync(SC_FULL, (int)(threadIdx.x >> 5), 0);   // broadcast: dependent code is compiled warp-uniform
   ScatterSmem& S = smem[wib];
+  fmpm_pdl_trigger();
   const long long gw = (long long)blockIdx.x * P2G_WARPS + wib;
   const long long slot0 = gw * (32 * P2G_ROUNDS);
   if (slot0 >= P.N) return;
-  Window W; window_init(W, lane, P.n, P.blk_flags);
-  window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);
+  Window W; window_init(W, lane, P.n, nullptr);   // blocks are flagged once per round (flag_box), not by the window
+  fmpm_pdl_wait();
+  if (P.epoch != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *P.epoch += 16;   // opens a fused step with lazy grid_op: fresh tags for its k_fwd launches
+  if (kSlab) window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);
   PRaw R; p2g_load_raw(P, f, slot0 + lane, R);
 #pragma unroll 1
   for (int r = 0; r < P2G_ROUNDS; r++) {
@@ -113,12 +116,13 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
     int key = -1;
     float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, m = 0.f;
     float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    int b[3] = {0, 0, 0}; bool ok = false;
     if (sl < P.N) {
       const int s = (int)sl;
       PState st; p2g_unpack(R, st);
-      int b[3]; float fx[3];
+      float fx[3];
       const bool used = st.meta & 1;
-      const bool ok = used && base_fx(P, st.x, b, fx);
+      ok = used && base_fx(P, st.x, b, fx);
       if (ok) {
         const float4 mt = __ldg(P.mats + ((st.meta >> 8) & 0xff));
         Constit K; constitutive(P, st, mt.x, mt.y, mt.z, __float_as_int(mt.w), K);
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
         p2g_store_F(P, f + 1, s, st.F);  // process_unused_particles (MPM:316) / frozen out-of-grid particle
       }
     }
+    flag_box<kSlab>(W, P.blk_flags, lane, ok, b);
     const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
     // software pipelining: the next round's 100 B/particle are in flight while this round is scattered
 #if P2G_PREFETCH == 1
@@ -143,10 +148,10 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
     if (r + 1 < P2G_ROUNDS) p2g_prefetch_l2(P, f, sl + 32);
 #endif
     __syncwarp();
-    window_consume(W, S, cnt, starts, P.grid_pm);
+    window_consume2<kSlab>(W, S, cnt, starts, P.grid_pm);
     __syncwarp();
   }
-  window_flush_all(W, P.grid_pm);
+  window_flush_all2<kSlab>(W, P.grid_pm);
 }
 
 // =============================================================================================
@@ -156,32 +161,29 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
 // MPM:380-398 on the active blocks; optionally clears the (momentum, mass) accumulators for the next substep
 // and zeroes the v_out adjoint of the same blocks (backward pass).
 __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, const int clear_pm, const int zero_ggv, const int reset_flags) {
+  // one CTA per 8^3-node block: CTAs of unflagged blocks leave after one broadcast load, the others make ONE memory round trip (r02e: the
+  // round-1 version — flag compaction through shared memory, two barriers, a block loop — took 10.6 us for 4 MB, 5.8 barrier stalls per issue)
   const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
-  // this CTA owns blocks blockIdx.x + q*gridDim.x; their flags are fetched in parallel (thread q reads flag q) and the CTA
-  // then walks the flagged ones (nblk / gridDim.x <= 256 for every supported grid)
-  __shared__ int s_act[256];
-  __shared__ int s_n;
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  {
-    const int blk = blockIdx.x + threadIdx.x * gridDim.x;
-    if (blk < nblk && P.blk_flags[blk] != 0) s_act[atomicAdd(&s_n, 1)] = blk;
-  }
-  __syncthreads();
-  const int n_act = s_n;
-  for (int ai = 0; ai < n_act; ai++) {
-    const int blk = s_act[ai];
+  fmpm_pdl_trigger();
+  fmpm_pdl_wait();
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    if (P.blk_flags[blk] == 0) continue;   // CTA-uniform
     const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+    float4 pm[2]; int g[2], ci[2], cj[2], ck[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const int t = threadIdx.x + r * 256;
-      const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
-      const int g = (i * n + j) * n + k;
-      const float4 pm = P.grid_pm[g];
+      ci[r] = bx * 8 + (t >> 6); cj[r] = by * 8 + ((t >> 3) & 7); ck[r] = bz * 8 + (t & 7);
+      g[r] = (ci[r] * n + cj[r]) * n + ck[r];
+      pm[r] = P.grid_pm[g[r]];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int i = ci[r], j = cj[r], k = ck[r];
       float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pm.w > FMPM_EPS) {
-        const float inv_m = 1.f / pm.w;
-        float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
+      if (pm[r].w > FMPM_EPS) {
+        const float inv_m = 1.f / pm[r].w;
+        float v[3] = {inv_m * pm[r].x + P.dt * P.gx, inv_m * pm[r].y + P.dt * P.gy, inv_m * pm[r].z + P.dt * P.gz};
         const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
         for (int si = 0; si < P.col.n_statics; si++) {  // statics[i].collide, MPM:388-390
           float o[3]; sdf_collide<false>(P.col.statics[si], false, nullptr, nullptr, nullptr, nullptr, P.dt, pos, v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -195,11 +197,13 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, c
         boundary_v(P, pos, v, fac);
         out = make_float4(v[0], v[1], v[2], 0.f);
       }
-      P.grid_v[g] = out;
-      if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (zero_ggv) P.ggrid_v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      P.grid_v[g[r]] = out;
+      if (clear_pm && (pm[r].w != 0.f || pm[r].x != 0.f || pm[r].y != 0.f || pm[r].z != 0.f)) P.grid_pm[g[r]] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zero_ggv) P.ggrid_v[g[r]] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (reset_flags && threadIdx.x == 0) P.blk_flags[blk] = 0;
+    // every thread has read the flag above (the loads of this iteration precede the barrier-free reset only in program order of thread 0, so
+    // the reset is delayed until the whole CTA passed the flag test)
+    if (reset_flags) { __syncthreads(); if (threadIdx.x == 0) P.blk_flags[blk] = 0; }
   }
 }
 
@@ -213,6 +217,8 @@ __global__ void __launch_bounds__(G2P_WARPS * 32) k_g2p(const KParams P, const i
   __shared__ float4 tiles[G2P_WARPS][9 * G2P_ZMAX];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   float4* tile = tiles[threadIdx.x >> 5];
+  fmpm_pdl_trigger();
+  fmpm_pdl_wait();
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s < P.N) a0 = P.pa[pa_idx(P, f, 0, s)];
   const int meta = __float_as_int(a0.w);
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
                                                                               const int* __restrict__ body_info, const int n_bodies) {
   __shared__ ScatterSmem smem[P2G_WARPS];
   static_assert(sizeof(((ScatterSmem*)0)->rec) >= 9 * G2P_ZMAX * sizeof(float4), "the gather tile is staged in the scatter records' storage");
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wib = __shfl_sync(SC_FULL, (int)(threadIdx.x >> 5), 0);   // broadcast: dependent code is compiled warp-uniform
   ScatterSmem& S = smem[wib];
   float4* tile = S.rec;   // gather tile first, scatter records afterwards (a __syncwarp separates the two uses)
   const long long slot0 = ((long long)blockIdx.x * P2G_WARPS + wib) * 32;
@@ -292,8 +298,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
   const long long sl = slot0 + lane;
   const long long rem = (long long)P.N - slot0;
   const int cnt = rem < 32 ? (int)rem : 32;
-  Window W; window_init(W, lane, P.n, P.blk_flags);
-  window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);   // x-slab mode: like k_p2g
+  Window W; window_init(W, lane, P.n, nullptr);   // blocks are flagged once per warp (flag_box); x-slab forward steps use k_fwd
   // ---- g2p of frame f (MPM:304-316, 400-426, 497-505)
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (sl < P.N) a0 = P2G_LD(&P.pa[pa_idx(P, f, 0, (int)sl)]);
@@ -304,6 +309,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
   Footprint fp = footprint_of(ok, b);
   if (fp.staged) footprint_load(P.grid_v, P.n, fp, tile);
   int key = -1;
+  int b1[3] = {0, 0, 0}; bool ok1 = false;
   float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, m = 0.f;
   float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
   if (sl < P.N) {
@@ -347,8 +353,8 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
       const bool taken = kAgent && has_col && !rigid && collector_takes(col, meta, st.x);
       st.meta = taken ? ((meta & ~1) | 2) : meta;
       // ---- p2g of frame f+1 (MPM:254-264, 331-378)
-      int b1[3]; float fx1[3];
-      const bool ok1 = !taken && !rigid && base_fx(P, st.x, b1, fx1);
+      float fx1[3];
+      ok1 = !taken && !rigid && base_fx(P, st.x, b1, fx1);
       if (kWriteVC || !ok1) store_A(P.pa, P, f + 1, s, st.x, st.meta, st.v, st.C);
       else P.pa[pa_idx(P, f + 1, 0, s)] = make_float4(st.x[0], st.x[1], st.x[2], __int_as_float(st.meta));
       if (ok1) {
@@ -367,12 +373,12 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
       }
     }
   }
+  flag_box<false>(W, P.blk_flags, lane, ok1, b1);
   __syncwarp();   // every lane is done with the gather tile before the scatter staging is written
   const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
   __syncwarp();
-  window_consume(W, S, cnt, starts, P.grid_pm);
-  __syncwarp();
-  window_flush_all(W, P.grid_pm);
+  window_consume2<false>(W, S, cnt, starts, P.grid_pm);
+  window_flush_all2<false>(W, P.grid_pm);
 }
 
 // =============================================================================================
@@ -392,31 +398,49 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
 #define FWD_MINB 5
 #endif
 #define FWD_TILE_COLS 16   // 4 x 4 node columns
-// grid_op of one node without SDF colliders (MPM:380-386,398): the same operations, in the same order, as k_grid_op
-__device__ __forceinline__ float4 grid_op_node(const KParams& P, const int i, const int j, const int k, const float4 pm) {
+// grid_op of one node without SDF colliders (MPM:380-386,398): the same operations, in the same order, as k_grid_op.
+// interior: the caller knows that no boundary condition can act on this node (then boundary_v would multiply by 1: skipped)
+__device__ __forceinline__ float4 grid_op_node(const KParams& P, const int i, const int j, const int k, const float4 pm, const bool interior = false) {
   float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pm.w > FMPM_EPS) {
     const float inv_m = 1.f / pm.w;
     float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
-    const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
-    float fac[3];
-    boundary_v(P, pos, v, fac);
+    if (!interior) {
+      const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
+      float fac[3];
+      boundary_v(P, pos, v, fac);
+    }
     out = make_float4(v[0], v[1], v[2], 0.f);
   }
   return out;
 }
+// true when no node of the box [i0,i1] x [j0,j1] x [k0,k1] can be touched by the domain boundary (boundaries.py:39-63,106-120): the cube's
+// walls / the cylinder's caps and mantle lie strictly outside it and no dimension is locked.  Conservative, warp-uniform.
+__device__ __forceinline__ bool box_is_interior(const KParams& P, const int i0, const int i1, const int j0, const int j1, const int k0, const int k1) {
+  if (P.lock_mask != 0) return false;
+  const float x0 = (float)i0 * P.dx, x1 = (float)i1 * P.dx, y0 = (float)j0 * P.dx, y1 = (float)j1 * P.dx, z0 = (float)k0 * P.dx, z1 = (float)k1 * P.dx;
+  if (P.boundary_type == 0)
+    return x0 > P.lo[0] && x1 < P.hi[0] && y0 > P.lo[1] && y1 < P.hi[1] && z0 > P.lo[2] && z1 < P.hi[2];
+  const float ax = fmaxf(fabsf(x0 - P.cyl_cx), fabsf(x1 - P.cyl_cx)), az = fmaxf(fabsf(z0 - P.cyl_cz), fabsf(z1 - P.cyl_cz));
+  return y0 >= P.lo[1] && y1 <= P.hi[1] && sqrtf(ax * ax + az * az + FMPM_EPS) < 0.999f * P.cyl_r;
+}
 // the rare warp whose particles do not fit one footprint box (no cell sort yet, or a very old one): every lane gathers its own 27 nodes
 // from L2.  The node loop stays rolled so that the hot kernel stays small in the instruction cache.
 template <bool kInline>
-__device__ __forceinline__ void fwd_gather_unstaged(const KParams& P, const int* b, const float* fx, float* nv, float* nC) {
+__device__ __forceinline__ void fwd_gather_unstaged(const KParams& P, const float4* __restrict__ pms, const int tagf, const int* b, const float* fx, float* nv, float* nC) {
   const int n = P.n;
-  const float4* gv = P.grid_v + ((b[0] * n + b[1]) * n + b[2]);
+  const int cell = (b[0] * n + b[1]) * n + b[2];
   float v[3] = {0.f, 0.f, 0.f}, C[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
   for (int c = 0; c < 27; c++) {
     const int i = c / 9, j = (c / 3) % 3, k = c % 3;
-    float4 g = gv[(i * n + j) * n + k];
-    if (kInline) g = grid_op_node(P, b[0] + i, b[1] + j, b[2] + k, g);
+    const int node = cell + (i * n + j) * n + k;
+    float4 g = kInline ? __ldcg(&P.grid_v[node]) : P.grid_v[node];
+    if (kInline && __float_as_int(g.w) != tagf) {   // lazy grid_op, see k_fwd
+      g = grid_op_node(P, b[0] + i, b[1] + j, b[2] + k, pms[node]);
+      g.w = __int_as_float(tagf);
+      P.grid_v[node] = g;
+    }
     const float d[3] = {(float)i - fx[0], (float)j - fx[1], (float)k - fx[2]};
     float wt = 1.f;
 #pragma unroll
@@ -439,14 +463,25 @@ __device__ __forceinline__ void fwd_gather_unstaged(const KParams& P, const int*
 #pragma unroll
   for (int r = 0; r < 9; r++) nC[r] = c4 * C[r];
 }
-template <int kMat, bool kInline>
-__global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams P, const int f, float4* __restrict__ clr, int* __restrict__ clr_flags, const int full) {
+// kInline (lazy grid_op): P.grid_v is a CACHE of v_out whose w component carries the tag (launch epoch) of the substep it was computed for;
+// pms is the (momentum, mass) accumulator of frame f.  A node whose cached tag is not this launch's tag is converted on the spot
+// (grid_op_node) and written back with the tag in ONE 16-byte store, so each node is converted by the first warp that needs it (plus the
+// few that race with it: they store identical values) instead of by every warp that stages it.  `stride` permutes the CTA -> slot-block
+// map (an odd prime not dividing the grid size): neighbouring slot blocks — which share their nodes — then run in different waves.
+template <int kMat, bool kInline, bool kSlab>
+__global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams P, const int f, float4* __restrict__ clr, int* __restrict__ clr_flags, const int full,
+                                                                            const float4* __restrict__ pms, const int tag_off, const int stride) {
   __shared__ ScatterSmem smem[P2G_WARPS];
   static_assert(sizeof(((ScatterSmem*)0)->rec) >= FWD_TILE_COLS * 16 * sizeof(float4), "the gather tile is staged in the scatter records' storage");
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wib = __shfl_sync(SC_FULL, (int)(threadIdx.x >> 5), 0);   // broadcast: dependent code is compiled warp-uniform
   ScatterSmem& S = smem[wib];
   float4* tile = S.rec;   // gather tile first, scatter records afterwards (a __syncwarp separates the two uses)
   const long long gw = (long long)blockIdx.x * P2G_WARPS + wib;
+  const long long gws = (long long)((blockIdx.x * (unsigned)stride) % gridDim.x) * P2G_WARPS + wib;   // the slot block this warp works on (32-bit: the host checks blocks * stride < 2^32)
+  fmpm_pdl_trigger();
+  Window W; window_init(W, lane, P.n, nullptr);   // blocks are flagged once per warp (flag_box), not by the window
+  fmpm_pdl_wait();
+  const int tagf = kInline ? (*P.epoch + tag_off) : 0;
   // ---- clear duty (kInline): one warp per flagged 8^3-node block of the accumulator that the previous launch gathered from
   if (kInline && clr != nullptr) {
     const int nb = P.nb, nblk = nb * nb * nb, n = P.n;
@@ -465,22 +500,26 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
       }
     }
   }
-  const long long slot0 = gw * 32;
+  const long long slot0 = gws * 32;
   if (slot0 >= P.N) return;   // warp-uniform
   const long long sl = slot0 + lane;
   const long long rem = (long long)P.N - slot0;
   const int cnt = rem < 32 ? (int)rem : 32;
   const bool inrange = sl < P.N;
   const int s = (int)sl;
-  Window W; window_init(W, lane, P.n, P.blk_flags);
-  window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);   // x-slab mode: like k_p2g
+  if (kSlab) window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);   // x-slab mode: like k_p2g
+  // plane pointers of this slot: frame f / f+1 of the state planes, frame f+1 / f+2 of F
+  const size_t Ns = (size_t)P.N;
+  float4* const pa_f = P.pa + (size_t)f * 4 * Ns + s; float4* const pa_n = pa_f + 4 * Ns;
+  float4* const pf_r = P.pf + (size_t)(f + 1) * 2 * Ns + s; float4* const pf_w = pf_r + 2 * Ns;
+  float* const p8_r = P.pf8 + (size_t)(f + 1) * Ns + s; float* const p8_w = p8_r + Ns;
   // ---- particle loads: x + meta of frame f, F[f+1] (written by the p2g / k_fwd of frame f)
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 f0 = make_float4(1.f, 0.f, 0.f, 0.f), f1 = make_float4(1.f, 0.f, 0.f, 0.f); float f8 = 1.f;
   if (inrange) {
-    a0 = P2G_LD(&P.pa[pa_idx(P, f, 0, s)]);
-    f8 = P2G_LD(&P.pf8[pf8_idx(P, f + 1, s)]);
-    if (kMat != 1) { f0 = P2G_LD(&P.pf[pf_idx(P, f + 1, 0, s)]); f1 = P2G_LD(&P.pf[pf_idx(P, f + 1, 1, s)]); }
+    a0 = P2G_LD(pa_f);
+    f8 = P2G_LD(p8_r);
+    if (kMat != 1) { f0 = P2G_LD(pf_r); f1 = P2G_LD(pf_r + Ns); }
   }
   const int meta = __float_as_int(a0.w);
   const float x[3] = {a0.x, a0.y, a0.z};
@@ -496,31 +535,49 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
   const int tzs = nz <= 8 ? 3 : 4;   // rows of 8 or 16 nodes
   if (staged) {
     const int n = P.n, tot = FWD_TILE_COLS << tzs;
-    for (int t = lane; t < tot; t += 32) {
-      const int iz = t & ((1 << tzs) - 1), c = t >> tzs, iy = c & 3, ix = c >> 2;
-      if (ix >= nx) break;   // warp-uniform from the first lane on: the remaining columns lie outside the box
-      if (iy < ny && iz < nz) {
-        const int gi = bx0 + ix, gj = by0 + iy, gk = bz0 + iz;
-        float4 g = P.grid_v[(gi * n + gj) * n + gk];
-        if (kInline) g = grid_op_node(P, gi, gj, gk, g);
-        tile[t] = g;
+    // four rows of 32 slots per batch: all loads of a batch are issued before the first use (one exposed L2 latency per batch)
+#pragma unroll 1
+    for (int t0 = 0; t0 < tot; t0 += 128) {
+      if (((t0 >> tzs) >> 2) >= nx) break;   // warp-uniform: the remaining columns lie outside the box
+      float4 g[4]; bool act[4]; int gi[4], gj[4], gk[4];
+      bool stale = false;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = t0 + u * 32 + lane;
+        const int iz = t & ((1 << tzs) - 1), c = t >> tzs, iy = c & 3, ix = c >> 2;
+        act[u] = ix < nx && iy < ny && iz < nz;
+        gi[u] = bx0 + ix; gj[u] = by0 + iy; gk[u] = bz0 + iz;
+        if (act[u]) g[u] = kInline ? __ldcg(&P.grid_v[(gi[u] * n + gj[u]) * n + gk[u]]) : P.grid_v[(gi[u] * n + gj[u]) * n + gk[u]];
+        if (kInline) stale = stale || (act[u] && __float_as_int(g[u].w) != tagf);
       }
+      if (kInline && __any_sync(SC_FULL, stale)) {   // warp-uniform; false for most warps once the first toucher of a node has converted it
+        const bool interior = box_is_interior(P, bx0, bx0 + nx - 1, by0, by0 + ny - 1, bz0, bz0 + nz - 1);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (act[u] && __float_as_int(g[u].w) != tagf) {
+            const int node = (gi[u] * n + gj[u]) * n + gk[u];
+            g[u] = grid_op_node(P, gi[u], gj[u], gk[u], pms[node], interior);
+            g[u].w = __int_as_float(tagf);
+            P.grid_v[node] = g[u];   // v_out and its tag in one 16-byte store
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (act[u]) tile[t0 + u * 32 + lane] = g[u];
     }
     __syncwarp();
   }
   int key = -1;
+  int b1[3] = {0, 0, 0}; bool ok1 = false;
   float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, m = 0.f;
   float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
   if (inrange) {
     PState st;
     if (!ok) {  // unused (MPM:309-316) or frozen: the whole state is carried over unchanged (these slots always hold complete frames)
       if (meta & 2) { a0.x = a0.y = a0.z = FMPM_NOWHERE; a0.w = __int_as_float(meta & ~3); }
-      if (kMat == 1) { f0 = P.pf[pf_idx(P, f + 1, 0, s)]; f1 = P.pf[pf_idx(P, f + 1, 1, s)]; }
-      P.pa[pa_idx(P, f + 1, 0, s)] = a0;
-      P.pa[pa_idx(P, f + 1, 1, s)] = P.pa[pa_idx(P, f, 1, s)];
-      P.pa[pa_idx(P, f + 1, 2, s)] = P.pa[pa_idx(P, f, 2, s)];
-      P.pa[pa_idx(P, f + 1, 3, s)] = P.pa[pa_idx(P, f, 3, s)];
-      P.pf[pf_idx(P, f + 2, 0, s)] = f0; P.pf[pf_idx(P, f + 2, 1, s)] = f1; P.pf8[pf8_idx(P, f + 2, s)] = f8;
+      if (kMat == 1) { f0 = pf_r[0]; f1 = pf_r[Ns]; }
+      pa_n[0] = a0; pa_n[Ns] = pa_f[Ns]; pa_n[2 * Ns] = pa_f[2 * Ns]; pa_n[3 * Ns] = pa_f[3 * Ns];
+      pf_w[0] = f0; pf_w[Ns] = f1; *p8_w = f8;
     } else {
       // ---- g2p of frame f (MPM:400-426) + advect (MPM:497-505)
       bspline(fx, w);
@@ -528,17 +585,25 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
       if (staged) {
         const float4* t0 = tile + ((((b[0] - bx0) << 2) + (b[1] - by0)) << tzs) + (b[2] - bz0);
         g2p_gather_v(fx, w, [&](int c) { const float4* p = t0 + ((((c / 3) << 2) + (c % 3)) << tzs); Col3 r; r.g0 = p[0]; r.g1 = p[1]; r.g2 = p[2]; return r; }, st.v, st.C, c4);
-      } else {
-        fwd_gather_unstaged<kInline>(P, b, fx, st.v, st.C.m);
+      } else if (kInline) {
+        fwd_gather_unstaged<kInline>(P, pms, tagf, b, fx, st.v, st.C.m);
+      } else {   // warps that straddle two z-columns (1 in 16 at 8 particles per cell) or are not cell-sorted: 27 gathers per lane from L2
+        const float4* gv = P.grid_v + ((b[0] * P.n + b[1]) * P.n + b[2]);
+        const int n = P.n;
+        g2p_gather(fx, w, [&](int c) { return gv + ((c / 3) * n + (c % 3)) * n; }, st.v, st.C, c4);
       }
 #pragma unroll
       for (int d = 0; d < 3; d++) st.x[d] = x[d] + P.dt * st.v[d];
       st.meta = meta;
       // ---- p2g of frame f+1 (MPM:254-264, 331-378)
-      int b1[3]; float fx1[3];
-      const bool ok1 = base_fx(P, st.x, b1, fx1);
-      if (full || !ok1) store_A(P.pa, P, f + 1, s, st.x, meta, st.v, st.C);
-      else P.pa[pa_idx(P, f + 1, 0, s)] = make_float4(st.x[0], st.x[1], st.x[2], a0.w);
+      float fx1[3];
+      ok1 = base_fx(P, st.x, b1, fx1);
+      pa_n[0] = make_float4(st.x[0], st.x[1], st.x[2], a0.w);
+      if (full || !ok1) {
+        pa_n[Ns] = make_float4(st.v[0], st.v[1], st.v[2], st.C.m[0]);
+        pa_n[2 * Ns] = make_float4(st.C.m[1], st.C.m[2], st.C.m[3], st.C.m[4]);
+        pa_n[3 * Ns] = make_float4(st.C.m[5], st.C.m[6], st.C.m[7], st.C.m[8]);
+      }
       if (ok1) {
         const float4 mt = __ldg(P.mats + ((meta >> 8) & 0xff));
         m = mt.z;
@@ -553,17 +618,15 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
           for (int i = 0; i < 9; i++) Bm[i] = (P.k_stress * ((i % 4 == 0) ? iso : 0.f) + m * st.C.m[i]) * P.dx;
           float sn = (J > 0.f) ? cbrtf(J) : __int_as_float(0x7fc00000);   // pow(J, 1/3): NaN for J < 0 like the reference
           if (J == 0.f) sn = 0.f;
-          if (full) {
-            __stcs(&P.pf[pf_idx(P, f + 2, 0, s)], make_float4(sn, 0.f, 0.f, 0.f));
-            __stcs(&P.pf[pf_idx(P, f + 2, 1, s)], make_float4(sn, 0.f, 0.f, 0.f));
-          }
-          __stcs(&P.pf8[pf8_idx(P, f + 2, s)], sn);
+          if (full) { __stcs(pf_w, make_float4(sn, 0.f, 0.f, 0.f)); __stcs(pf_w + Ns, make_float4(sn, 0.f, 0.f, 0.f)); }
+          __stcs(p8_w, sn);
         } else {
           st.F.m[0] = f0.x; st.F.m[1] = f0.y; st.F.m[2] = f0.z; st.F.m[3] = f0.w; st.F.m[4] = f1.x; st.F.m[5] = f1.y; st.F.m[6] = f1.z; st.F.m[7] = f1.w; st.F.m[8] = f8;
           Constit K; constitutive(P, st, mt.x, mt.y, mt.z, __float_as_int(mt.w), K);
 #pragma unroll
           for (int i = 0; i < 9; i++) Bm[i] = K.A.m[i] * P.dx;
-          p2g_store_F(P, f + 2, s, K.Fn);
+          __stcs(pf_w, make_float4(K.Fn.m[0], K.Fn.m[1], K.Fn.m[2], K.Fn.m[3])); __stcs(pf_w + Ns, make_float4(K.Fn.m[4], K.Fn.m[5], K.Fn.m[6], K.Fn.m[7]));
+          __stcs(p8_w, K.Fn.m[8]);
         }
         bspline(fx1, w);
 #pragma unroll
@@ -573,7 +636,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
         key = pack_key(b1);
       } else {   // left the grid: frozen from now on, with the complete state (F = f8 I for kMat == 1)
         if (kMat == 1) { f0 = make_float4(f8, 0.f, 0.f, 0.f); f1 = f0; }
-        P.pf[pf_idx(P, f + 2, 0, s)] = f0; P.pf[pf_idx(P, f + 2, 1, s)] = f1; P.pf8[pf8_idx(P, f + 2, s)] = f8;
+        pf_w[0] = f0; pf_w[Ns] = f1; *p8_w = f8;
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -581,12 +644,12 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
       }
     }
   }
+  flag_box<kSlab>(W, P.blk_flags, lane, ok1, b1);
   __syncwarp();   // every lane is done with the gather tile before the scatter staging is written
   const unsigned starts = scatter_publish(S, lane, key, W.cur_key, q, B, m, w);
   __syncwarp();
-  window_consume(W, S, cnt, starts, P.grid_pm);
-  __syncwarp();
-  window_flush_all(W, P.grid_pm);
+  window_consume2<kSlab>(W, S, cnt, starts, P.grid_pm);
+  window_flush_all2<kSlab>(W, P.grid_pm);
 }
 
 // p2g of the few particles an injector has just activated in frame f (fused steps with an injector agent: the g2p2g kernel of the previous
@@ -683,6 +746,7 @@ static int check_bound(FmpmHandle* h, const char* name) {
 }
 #define G2P2G_K(a, b) (k_g2p2g<a, b>)   /* a template-id with a comma cannot be a macro argument by itself */
 #define G2P2G_K2(k, a, b) (k<a, b>)
+#define FWD_K(a, b, c) (k_fwd<a, b, c>)
 static FmpmCollector no_collector() { FmpmCollector c; memset(&c, 0, sizeof(c)); return c; }
 static int check_frame(FmpmHandle* h, int f, int maxf, const char* name) {
   if (f < 0 || f > maxf) { snprintf(h->err, sizeof(h->err), "%s: frame %d out of range [0,%d]", name, f, maxf); return 1; }
@@ -703,8 +767,9 @@ int fmpm_p2g_impl(FmpmHandle* h, int f, int write_F, int ring_slot, void* stream
   if (P.N == 0) return 0;
   const long long warps = ((long long)P.N + 32 * P2G_ROUNDS - 1) / (32 * P2G_ROUNDS);
   const int blocks = (int)((warps + P2G_WARPS - 1) / P2G_WARPS);
-  if (write_F) FMPM_LAUNCH(k_p2g<true>, blocks, P2G_WARPS * 32, 0, stream, P, f);
-  else FMPM_LAUNCH(k_p2g<false>, blocks, P2G_WARPS * 32, 0, stream, P, f);
+  const bool pdl = h->use_pdl != 0;
+  if (h->slab.enabled) { if (write_F) FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, true, true), blocks, P2G_WARPS * 32, 0, stream, P, f); else FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, false, true), blocks, P2G_WARPS * 32, 0, stream, P, f); }
+  else { if (write_F) FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, true, false), blocks, P2G_WARPS * 32, 0, stream, P, f); else FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, false, false), blocks, P2G_WARPS * 32, 0, stream, P, f); }
   FMPM_CHECK_LAUNCH(h, "fmpm_p2g");
   return 0;
 }
@@ -716,11 +781,10 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring
   if (!P.blk_flags) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block flags were not bound"); return 1; }
   if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
   const int nblk = P.nb * P.nb * P.nb;
-  int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
-  if ((nblk + grid - 1) / grid > 256) grid = (nblk + 255) / 256;  // keep <= 256 blocks per CTA (parallel flag fetch)
+  const int grid = nblk < 65536 ? nblk : 65536;   // one CTA per sparse block (a grid-stride loop covers grids beyond 320^3)
   // the flags are consumed (reset) here only when nothing later in the substep needs them: plain forward substeps
   const int reset_flags = (clear_pm && ring_slot < 0) ? 1 : 0;
-  FMPM_LAUNCH(k_grid_op, grid, 256, 0, stream, P, f, clear_pm, zero_ggv, reset_flags);
+  FMPM_LAUNCH_PDL(h->use_pdl != 0, k_grid_op, grid, 256, 0, stream, P, f, clear_pm, zero_ggv, reset_flags);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op");
   return 0;
 }
@@ -732,7 +796,7 @@ int fmpm_g2p_impl(FmpmHandle* h, int f, int ring_slot, void* stream) {
   if (check_bound(h, "fmpm_g2p") || check_frame(h, f, h->cfg.max_substeps_local - 1, "fmpm_g2p")) return 1;
   KParams P = make_kparams(h, ring_slot);
   if (P.N == 0) return 0;
-  FMPM_LAUNCH(k_g2p, (P.N + G2P_WARPS * 32 - 1) / (G2P_WARPS * 32), G2P_WARPS * 32, 0, stream, P, f);
+  FMPM_LAUNCH_PDL(h->use_pdl != 0, k_g2p, (P.N + G2P_WARPS * 32 - 1) / (G2P_WARPS * 32), G2P_WARPS * 32, 0, stream, P, f);
   FMPM_CHECK_LAUNCH(h, "fmpm_g2p");
   return 0;
 }
@@ -772,6 +836,26 @@ extern "C" int fmpm_substep_store(FmpmHandle* h, int f, void* stream) {
   return fmpm_advect_rigid_impl(h, f, stream);
 }
 
+// ---- k_fwd dispatch --------------------------------------------------------------------------------------------
+enum { FWD_KFWD = 1, FWD_LIQUID = 2, FWD_INLINE = 4, FWD_TMA = 8 };
+// what fmpm_substeps_fused may use for this handle: k_fwd needs an agent-free scene without MAT_RIGID bodies; the inlined grid_op also
+// needs the triple-buffered accumulators, no SDF collider at grid level and no x-slab peers (their ghost exchange is per parity buffer)
+static int fwd_path(const FmpmHandle* h) {
+  int p = 0;
+  const bool agent = (h->col.has_rigid != 0) || h->bodies.n_bodies > 0;
+  if (!agent) {
+    p |= FWD_KFWD;
+    if (h->cfg.scene_flags & FMPM_SCENE_ALL_LIQUID_MU0) p |= FWD_LIQUID;
+    if (h->buf.grid_pm3 && h->buf.blk_flags3 && h->col.n_statics == 0 && !h->slab.enabled) p |= FWD_INLINE;
+  }
+  p &= h->fwd_mask;
+  if (!(p & FWD_KFWD)) p = 0;
+  return p;
+}
+extern "C" int fmpm_fwd_path(FmpmHandle* h) { return h ? fwd_path(h) : 0; }
+extern "C" int fmpm_set_fwd_mask(FmpmHandle* h, int mask) { if (!h) return 1; h->fwd_mask = mask; return 0; }
+
+static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream, int tag_f0 = 0);
 // g2p(f) fused with p2g(f+1): forward-only steps without agents, MAT_RIGID bodies or slabs (see k_g2p2g)
 static int g2p2g_impl(FmpmHandle* h, int f, int write_vc, const FmpmCollector* col, void* stream);
 extern "C" int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream) { return g2p2g_impl(h, f, write_vc, nullptr, stream); }
@@ -779,6 +863,10 @@ extern "C" int fmpm_g2p2g_collect(FmpmHandle* h, int f, int write_vc, const Fmpm
 static int g2p2g_impl(FmpmHandle* h, int f, int write_vc, const FmpmCollector* col, void* stream) {
   if (check_bound(h, "fmpm_g2p2g") || check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_g2p2g")) return 1;
   if (h->bodies.n_bodies > 0 && h->slab.enabled) { snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: MAT_RIGID bodies are not available in x-slab mode"); return 1; }
+  // agent-free scenes (and every x-slab scene): k_fwd, general-material instantiation with complete F planes (the callers of this phase-level
+  // entry point own the step structure; the lean all-liquid frames are only used inside fmpm_substeps_fused / fmpm_substeps_slab)
+  if (col == nullptr && (fwd_path(h) & FWD_KFWD)) return fwd_launch(h, f, FWD_KFWD, write_vc, stream);
+  if (h->slab.enabled) { snprintf(h->err, sizeof(h->err), "fmpm_g2p2g: agents / colliders are not available in x-slab mode"); return 1; }
   KParams P = make_kparams(h, -1, f + 1);   // x-slab mode: the scatter goes to the accumulator / block flags / peers of substep parity f+1
   if (P.N == 0) return 0;
   const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
@@ -844,44 +932,42 @@ extern "C" int fmpm_substeps_fused_store(FmpmHandle* h, int f0, int n, void* str
   if (fmpm_g2p_impl(h, f0 + n - 1, f0 + n - 1, stream)) return 1;
   return fmpm_advect_rigid_impl(h, f0 + n - 1, stream);
 }
-// ---- k_fwd dispatch --------------------------------------------------------------------------------------------
-enum { FWD_KFWD = 1, FWD_LIQUID = 2, FWD_INLINE = 4, FWD_TMA = 8 };
-// what fmpm_substeps_fused may use for this handle: k_fwd needs an agent-free scene without MAT_RIGID bodies; the inlined grid_op also
-// needs the triple-buffered accumulators, no SDF collider at grid level and no x-slab peers (their ghost exchange is per parity buffer)
-static int fwd_path(const FmpmHandle* h) {
-  int p = 0;
-  const bool agent = (h->col.has_rigid != 0) || h->bodies.n_bodies > 0;
-  if (!agent) {
-    p |= FWD_KFWD;
-    if (h->cfg.scene_flags & FMPM_SCENE_ALL_LIQUID_MU0) p |= FWD_LIQUID;
-    if (h->buf.grid_pm3 && h->buf.blk_flags3 && h->col.n_statics == 0 && !h->slab.enabled) p |= FWD_INLINE;
-  }
-  p &= h->fwd_mask;
-  if (!(p & FWD_KFWD)) p = 0;
-  return p;
-}
-extern "C" int fmpm_fwd_path(FmpmHandle* h) { return h ? fwd_path(h) : 0; }
-extern "C" int fmpm_set_fwd_mask(FmpmHandle* h, int mask) { if (!h) return 1; h->fwd_mask = mask; return 0; }
-
 // one k_fwd launch: g2p(f) + p2g(f+1).  acc < 0: plain accumulator / grid_v (grid_op ran before); acc >= 0: inlined grid_op, frame f lives in
 // accumulator acc % 3
-static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream) {
+static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream, int tag_f0) {
   if (check_frame(h, f, h->cfg.max_substeps_local - 2, "fmpm_substeps_fused(k_fwd)")) return 1;
   const bool inl = (path & FWD_INLINE) != 0, liq = (path & FWD_LIQUID) != 0;
   KParams P = inl ? make_kparams(h, -2 - ((f + 1) % 3)) : make_kparams(h, -1, f + 1);   // scatter target: accumulator + block flags of frame f+1
-  float4* clr = nullptr; int* clr_flags = nullptr;
+  float4* clr = nullptr; int* clr_flags = nullptr; const float4* pms = nullptr;
   if (inl) {
     const KParams Ps = make_kparams(h, -2 - (f % 3)), Pc = make_kparams(h, -2 - ((f + 2) % 3));
-    P.grid_v = Ps.grid_pm;   // gather source: the (momentum, mass) accumulator of frame f
+    pms = Ps.grid_pm;   // the (momentum, mass) accumulator of frame f; P.grid_v is the tagged v_out cache
     clr = Pc.grid_pm; clr_flags = Pc.blk_flags;
   }
   if (P.N == 0) return 0;
   const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
-  if (liq) { if (inl) FMPM_LAUNCH(G2P2G_K2(k_fwd, 1, true), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full); else FMPM_LAUNCH(G2P2G_K2(k_fwd, 1, false), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full); }
-  else { if (inl) FMPM_LAUNCH(G2P2G_K2(k_fwd, 0, true), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full); else FMPM_LAUNCH(G2P2G_K2(k_fwd, 0, false), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full); }
+  int stride = 1;   // CTA -> slot-block permutation (lazy grid_op): an odd prime that does not divide the grid size
+  if (inl && h->fwd_stride != 1) {
+    static const int primes[] = {1021, 1031, 2053, 509, 257};
+    for (int k = 0; k < 5 && stride == 1; k++) if (blocks > primes[k] && blocks % primes[k] != 0 && (long long)blocks * primes[k] < (1LL << 32)) stride = primes[k];
+  }
+  const int tag_off = f - tag_f0;
+  const bool slab = h->slab.enabled != 0;   // (never together with the inlined grid_op, see fwd_path)
+#define FWD_GO(a, b, c) FMPM_LAUNCH_PDL(h->use_pdl != 0, FWD_K(a, b, c), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full, pms, tag_off, stride)
+  if (liq) { if (inl) FWD_GO(1, true, false); else if (slab) FWD_GO(1, false, true); else FWD_GO(1, false, false); }
+  else { if (inl) FWD_GO(0, true, false); else if (slab) FWD_GO(0, false, true); else FWD_GO(0, false, false); }
+#undef FWD_GO
   FMPM_CHECK_LAUNCH(h, "fmpm_substeps_fused(k_fwd)");
   return 0;
 }
+// one fused substep (g2p(f) + p2g(f+1)) with whatever the scene allows short of the inlined grid_op: x-slab steps (fmpm_substeps_slab)
+int fmpm_fwd_step_impl(FmpmHandle* h, int f, int full, void* stream) {
+  if (check_bound(h, "fmpm_fwd_step")) return 1;
+  const int path = fwd_path(h) & ~FWD_INLINE;
+  if (path & FWD_KFWD) return fwd_launch(h, f, path, full, stream);
+  return fmpm_g2p2g(h, f, 0, stream);
+}
+extern "C" int fmpm_fwd_step(FmpmHandle* h, int f, int full, void* stream) { return fmpm_fwd_step_impl(h, f, full, stream); }
 static int clear_blocks_launch(FmpmHandle* h, const KParams& P, void* stream) {
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
@@ -901,7 +987,7 @@ extern "C" int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream) {
   if (path & FWD_INLINE) {
     if (fmpm_p2g_impl(h, f0, 1, -2 - (f0 % 3), stream)) return 1;
     for (int i = 0; i + 1 < n; i++)
-      if (fwd_launch(h, f0 + i, path, i + 2 == n, stream)) return 1;
+      if (fwd_launch(h, f0 + i, path, i + 2 == n, stream, f0)) return 1;
     const int fl = f0 + n - 1;
     if (fmpm_grid_op_impl(h, fl, 1, 0, -2 - (fl % 3), stream)) return 1;        // consumes and clears the accumulator of the last frame
     if (n >= 2 && clear_blocks_launch(h, make_kparams(h, -2 - ((fl + 2) % 3)), stream)) return 1;   // the one the last k_fwd gathered from

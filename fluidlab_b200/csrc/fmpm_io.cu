@@ -1,6 +1,7 @@
 // fmpm_io.cu — handle management, frame ring io, cell sort, grad permutation, effector pose chain and the
 // index-matched shape loss of libfluidmpm.so.  Reference semantics cited per entry point in include/fluidmpm.h.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <cub/device/device_radix_sort.cuh>
@@ -15,6 +16,8 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
   FmpmHandle* h = new (std::nothrow) FmpmHandle();
   if (!h) return 1;
   h->cfg = *cfg; h->bound = false; h->err[0] = 0; h->sm_count = 148; h->fwd_mask = ~0;
+  { const char* e = getenv("FMPM_FWD_STRIDE"); h->fwd_stride = (e && e[0] == '1' && e[1] == 0) ? 1 : 0; }
+  { const char* e = getenv("FMPM_PDL"); h->use_pdl = (e && e[0] == '0') ? 0 : 1; }
   memset(&h->buf, 0, sizeof(h->buf));
   memset(&h->col, 0, sizeof(h->col));
   memset(&h->slab, 0, sizeof(h->slab));
@@ -114,6 +117,7 @@ int fmpm_slab_sync_impl(FmpmHandle* h, void* stream) {
   FMPM_CHECK_LAUNCH(h, "fmpm_slab_sync");
   return 0;
 }
+int fmpm_fwd_step_impl(FmpmHandle* h, int f, int full, void* stream);   // fmpm_forward.cu: k_fwd (or k_g2p2g) with everything the scene allows
 extern "C" int fmpm_substeps_slab(FmpmHandle* h, int f0, int n, int fuse, void* stream) {
   if (!h) return 1;
   if (n < 1) { snprintf(h->err, sizeof(h->err), "fmpm_substeps_slab: n must be >= 1"); return 1; }
@@ -121,7 +125,7 @@ extern "C" int fmpm_substeps_slab(FmpmHandle* h, int f0, int n, int fuse, void* 
     const int f = f0 + i;
     if (!(fuse && i > 0) && fmpm_p2g(h, f, 1, stream)) return 1;    // fused: the previous substep's g2p2g scattered frame f already
     if (fmpm_slab_sync(h, stream) || fmpm_grid_op(h, f, 1, stream)) return 1;
-    if (fuse && i + 1 < n) { if (fmpm_g2p2g(h, f, 0, stream)) return 1; }
+    if (fuse && i + 1 < n) { if (fmpm_fwd_step_impl(h, f, i + 2 == n, stream)) return 1; }   // the last fused substep completes F[f+2] (all-liquid scenes)
     else if (fmpm_g2p(h, f, stream)) return 1;
   }
   return 0;

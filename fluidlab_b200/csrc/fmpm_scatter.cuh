@@ -41,6 +41,14 @@ __device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
 }
 #endif
 
+// the same under a per-lane predicate: one predicated REDG, no branch / convergence barrier around the flush
+#ifdef FMPM_HOST_EMU
+__device__ __forceinline__ void red_add_v4_if(const bool p, float4* addr, const float4& v) { if (p) red_add_v4(addr, v); }
+#else
+__device__ __forceinline__ void red_add_v4_if(const bool p, float4* addr, const float4& v) {
+  asm volatile("{\n\t.reg .pred pr;\n\tsetp.ne.s32 pr, %5, 0;\n\t@pr red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)p) : "memory");
+}
+#endif
 #define SC_REC 9           // float4 records per particle: 36-word stride, so the 128-bit stores of lane = particle are bank-conflict free
 #define SC_WQ 7            // float4 per particle of stencil weights (27 + 1 pad): 28-word stride, conflict free as well
 struct __align__(16) ScatterSmem {
@@ -67,7 +75,7 @@ struct Window {
 };
 __device__ __forceinline__ void window_init(Window& W, const int lane, const int n, int* flags) {
   const int L = lane < 27 ? lane : 26;
-  const int a = L / 9, b = (L / 3) % 3, c = L % 3;
+  const int a = (L >= 9) + (L >= 18), r = L - 9 * a, b = (r >= 3) + (r >= 6), c = r - 3 * b;   // L = 9 a + 3 b + c without integer divisions
   W.oa = (float)a; W.ob = (float)b; W.oc = (float)c; W.a = a; W.b = b; W.c = c;
   W.lane_valid = lane < 27;
   W.wrow = L; W.qidx = a * 3 + b;
@@ -132,35 +140,30 @@ __device__ __forceinline__ void window_move(Window& W, const int key, float4* __
 
 // lane = particle.  key < 0: the particle contributes nothing (unused / out of grid / beyond N).
 // The 32 records are staged in ascending key order (stable rank inside the warp), so the node-mode pass sees every cell of the warp as
-// ONE run even when the global cell sort is a few substeps old (particles that changed cell since the last sort would otherwise split
-// their neighbours' runs: each split costs a 27-node flush).  Warps whose keys are already non-decreasing (always the case right after a
-// sort) take a 6-instruction path: rank == lane.  Otherwise MATCH.ANY groups equal keys and one short warp-uniform loop over the group
-// leaders counts, per lane, the particles with a smaller key.  Returns the mask of staged positions at which a new cell run starts.
+// ONE run, and the cells of a z-column one after the other (the window then only shifts by one plane), even when the global cell sort is
+// a few substeps old: in falling water half of a warp's particles have crossed into the next column down before the next sort, and an
+// order of first appearance (measured, r02c) would alternate between the two columns — a 27-node flush per run.  MATCH.ANY groups equal
+// keys; one short warp-uniform loop over the group leaders counts, per lane, the particles in smaller cells.
+// Returns the mask of staged positions at which a new cell run starts.
 // ALL 32 lanes must call.
 __device__ __forceinline__ unsigned scatter_rank(const int lane, const int key, const int carry_key, int& rank) {
-  const int skey = key >= 0 ? key : 0x7fffffff;   // particles without a cell go last and add zeros to the last run
-  const int prev = __shfl_up_sync(SC_FULL, skey, 1);
   const bool valid = key >= 0;
-  if (__ballot_sync(SC_FULL, lane > 0 && prev > skey) == 0u) {   // warp-uniform
-    rank = lane;
-    return __ballot_sync(SC_FULL, valid && (lane == 0 ? skey != carry_key : skey != prev));
-  }
+  const int skey = valid ? key : 0x7fffffff;   // particles without a cell go last (callers consume the first `cnt` staged positions only)
   const unsigned lt = (1u << lane) - 1u;
-  const unsigned same = __match_any_sync(SC_FULL, skey);
+  const unsigned same = __match_any_sync(SC_FULL, skey);   // MATCH.ANY: the lanes that share my cell
   const bool leader = (same & lt) == 0u;
+  const int gsz = __popc(same);
   unsigned leaders = __ballot_sync(SC_FULL, leader);
   int less = 0;
-  while (leaders != 0u) {   // warp-uniform: one pass per distinct key
+  while (leaders != 0u) {   // warp-uniform: one pass per distinct cell of the warp (4 ... 10)
     const int L = __ffs(leaders) - 1;
     leaders &= leaders - 1u;
-    const int k = __shfl_sync(SC_FULL, skey, L);
-    const unsigned g = __shfl_sync(SC_FULL, same, L);
-    if (k < skey) less += __popc(g);
+    const int k = __shfl_sync(SC_FULL, skey, L), n = __shfl_sync(SC_FULL, gsz, L);
+    less += k < skey ? n : 0;
   }
   rank = less + __popc(same & lt);
-  // a run starts at position `less` of every distinct valid key, except when the smallest key continues the window's current cell
-  const bool st = leader && valid && !(less == 0 && skey == carry_key);
-  return __reduce_or_sync(SC_FULL, st ? (1u << less) : 0u);
+  // every valid cell starts a run, except when the smallest one continues the cell the window is already on
+  return __reduce_or_sync(SC_FULL, (leader && valid && !(less == 0 && skey == carry_key)) ? (1u << less) : 0u);
 }
 __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int lane, const int key, const int carry_key, const float* q,
                                                     const float* B, const float m, const float w[3][3]) {
@@ -170,7 +173,8 @@ __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int la
   // Q_ab = q + a*B[:,0] + b*B[:,1] in packed (x,y) / (z,m) pairs
   const float2 c0a = make_float2(B[0], B[3]), c0b = make_float2(B[6], 0.f);
   const float2 c1a = make_float2(B[1], B[4]), c1b = make_float2(B[7], 0.f);
-  float4* rec = S.rec + rank * SC_REC;
+  // (stored as 64-bit halves: an FFMA2 result is a register PAIR, a 128-bit store would first need four MOVs into an aligned quad)
+  float2* rec = reinterpret_cast<float2*>(S.rec + rank * SC_REC);
 #pragma unroll
   for (int a = 0; a < 3; a++) {
     const float2 fa = make_float2((float)a, (float)a);
@@ -178,8 +182,8 @@ __device__ __forceinline__ unsigned scatter_publish(ScatterSmem& S, const int la
 #pragma unroll
     for (int b = 0; b < 3; b++) {
       const float2 fb = make_float2((float)b, (float)b);
-      const float2 r01 = ffma2(fb, c1a, qa01), r2m = ffma2(fb, c1b, qa2m);
-      rec[a * 3 + b] = make_float4(r01.x, r01.y, r2m.x, r2m.y);
+      rec[2 * (a * 3 + b)] = ffma2(fb, c1a, qa01);
+      rec[2 * (a * 3 + b) + 1] = ffma2(fb, c1b, qa2m);
     }
   }
   S.b2[rank] = make_float4(B[2], B[5], B[8], 0.f);
@@ -230,6 +234,121 @@ __device__ __forceinline__ void window_consume(Window& W, const ScatterSmem& S, 
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Lean variants (the ncu source page of the round-1 fused kernel charged 29 % of its 58 M warp instructions to the window moves of the
+// four-way unrolled group loop above — more than to the node loop itself): (1) the window no longer flags sparse-grid blocks, the kernel
+// flags the blocks of the warp's stencil box once (flag_box); (2) the x-slab peer reductions are compiled in only where asked (kSlab);
+// (3) the staged particles are consumed RUN BY RUN: one copy of the move code, then the run's particles four at a time plus a remainder.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool kSlab>
+__device__ __forceinline__ void window_flush_node2(const Window& W, const bool pred, float4* __restrict__ grid, const float4& v) {
+  red_add_v4_if(pred, grid + W.node, v);
+  if (kSlab) {
+    red_add_v4_if(pred && W.peer_r != nullptr && W.plane >= W.gr_lo && W.plane < W.gr_hi, W.peer_r + W.node, v);
+    red_add_v4_if(pred && W.peer_l != nullptr && W.plane >= W.gl_lo && W.plane < W.gl_hi, W.peer_l + W.node, v);
+  }
+}
+template <bool kSlab>
+__device__ __forceinline__ void window_move2(Window& W, const int key, float4* __restrict__ grid) {
+  const float4 v = make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y);
+  const bool open = W.cur_key >= 0;
+  if (open && key == W.cur_key + 1) {  // next cell of the same z-column: plane c=0 is complete, shift the other two
+    window_flush_node2<kSlab>(W, W.lane_valid && W.c == 0, grid, v);
+    float4 t;
+    t.x = __shfl_down_sync(SC_FULL, v.x, 1); t.y = __shfl_down_sync(SC_FULL, v.y, 1);
+    t.z = __shfl_down_sync(SC_FULL, v.z, 1); t.w = __shfl_down_sync(SC_FULL, v.w, 1);
+    const bool z = (W.c == 2) || !W.lane_valid;
+    W.acc01 = z ? make_float2(0.f, 0.f) : make_float2(t.x, t.y);
+    W.acc2m = z ? make_float2(0.f, 0.f) : make_float2(t.z, t.w);
+    W.node += 1; W.cur_key = key;
+    return;
+  }
+  window_flush_node2<kSlab>(W, open && W.lane_valid, grid, v);
+  W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
+  const int i = (key >> 20) + W.a, j = ((key >> 10) & 1023) + W.b, k = (key & 1023) + W.c;
+  W.node = (i * W.n + j) * W.n + k; W.plane = i;
+  W.cur_key = key;
+}
+template <bool kSlab>
+__device__ __forceinline__ void window_flush_all2(Window& W, float4* __restrict__ grid) {
+  window_flush_node2<kSlab>(W, W.cur_key >= 0 && W.lane_valid, grid, make_float4(W.acc01.x, W.acc01.y, W.acc2m.x, W.acc2m.y));
+  W.acc01 = make_float2(0.f, 0.f); W.acc2m = make_float2(0.f, 0.f);
+  W.cur_key = -1;
+}
+template <bool kSlab>
+__device__ __forceinline__ void window_consume2(Window& W, const ScatterSmem& S, const int cnt, const unsigned starts, float4* __restrict__ grid) {
+  if (starts == 0u && W.cur_key < 0) return;   // nothing staged and nothing open (a warp of unused slots)
+  const float2 oc2 = make_float2(W.oc, W.oc);
+  // running pointers: every LDS of the loop is [pointer + immediate]
+  const float* wf = reinterpret_cast<const float*>(S.w) + W.wrow;
+  const float4* rq = S.rec + W.qidx;
+  const float4* rb = S.b2;
+  const int* kp = S.key;
+  const int ngroups = (cnt + 3) >> 2;
+  // fixed groups of four, software-pipelined: the 12 LDS of group g+1 are issued before group g is accumulated, so the shared-memory
+  // latency overlaps the FFMA2 chains of the same warp (r02e: short-scoreboard stalls were the largest entry, 2.05 per issue)
+  float4 Qn[4], Bn[4]; float wn[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) { Qn[u] = rq[u * SC_REC]; Bn[u] = rb[u]; wn[u] = wf[u * (4 * SC_WQ)]; }
+  unsigned st = starts;
+#pragma unroll 1
+  for (int g = ngroups; g > 0; g--) {   // warp-uniform trip count
+    float2 t01[4], t2m[4], w2[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      w2[u] = make_float2(wn[u], wn[u]);
+      t01[u] = ffma2(make_float2(Bn[u].x, Bn[u].y), oc2, make_float2(Qn[u].x, Qn[u].y));
+      t2m[u] = ffma2(make_float2(Bn[u].z, Bn[u].w), oc2, make_float2(Qn[u].z, Qn[u].w));
+    }
+    if (g > 1) {   // prefetch the next group (the staging area holds 32 records: 8 groups)
+      rq += 4 * SC_REC; rb += 4; wf += 16 * SC_WQ;
+#pragma unroll
+      for (int u = 0; u < 4; u++) { Qn[u] = rq[u * SC_REC]; Bn[u] = rb[u]; wn[u] = wf[u * (4 * SC_WQ)]; }
+    }
+    const unsigned sb = st & 15u;   // warp-uniform (starts comes out of a warp reduction)
+    st >>= 4;
+    if (sb == 0u) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) { W.acc01 = ffma2(w2[u], t01[u], W.acc01); W.acc2m = ffma2(w2[u], t2m[u], W.acc2m); }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if ((sb >> u) & 1u) window_move2<kSlab>(W, kp[u], grid);
+        W.acc01 = ffma2(w2[u], t01[u], W.acc01); W.acc2m = ffma2(w2[u], t2m[u], W.acc2m);
+      }
+    }
+    kp += 4;
+  }
+}
+// flag the 8^3-node blocks that the stencils of the warp's particles (bases b, valid where ok) can touch: the blocks of the box
+// [min b, max b + 2] per axis (a superset is harmless: flagged blocks are only visited).  ALL 32 lanes must call.
+template <bool kSlab>
+__device__ __forceinline__ void flag_one(const Window& W, int* __restrict__ flags, const int X, const int Y, const int Z) {
+  const int blk = (X * W.nb + Y) * W.nb + Z;
+  flags[blk] = 1;
+  if (kSlab) {   // the neighbour must visit (and later clear) the blocks this rank reduces into over NVLink
+    if (W.peer_fr != nullptr && X * 8 + 7 >= W.gr_lo && X * 8 < W.gr_hi) W.peer_fr[blk] = 1;
+    if (W.peer_fl != nullptr && X * 8 + 7 >= W.gl_lo && X * 8 < W.gl_hi) W.peer_fl[blk] = 1;
+  }
+}
+template <bool kSlab>
+__device__ __forceinline__ void flag_box(const Window& W, int* __restrict__ flags, const int lane, const bool ok, const int* b) {
+  const int x1 = __reduce_max_sync(SC_FULL, ok ? b[0] : -1);
+  if (x1 < 0) return;   // warp-uniform
+  const int x0 = __reduce_min_sync(SC_FULL, ok ? b[0] : 0x7fffffff);
+  const int y0 = __reduce_min_sync(SC_FULL, ok ? b[1] : 0x7fffffff), y1 = __reduce_max_sync(SC_FULL, ok ? b[1] : -1);
+  const int z0 = __reduce_min_sync(SC_FULL, ok ? b[2] : 0x7fffffff), z1 = __reduce_max_sync(SC_FULL, ok ? b[2] : -1);
+  const int X0 = x0 >> 3, Y0 = y0 >> 3, Z0 = z0 >> 3, ex = ((x1 + 2) >> 3) - X0, ey = ((y1 + 2) >> 3) - Y0, ez = ((z1 + 2) >> 3) - Z0;
+  if ((ex | ey | ez) <= 1) {   // the usual case (a cell-sorted warp spans a few cells): at most 2 x 2 x 2 blocks, one predicated store per lane
+    const int dx = lane & 1, dy = (lane >> 1) & 1, dz = (lane >> 2) & 1;
+    if (lane < 8 && dx <= ex && dy <= ey && dz <= ez) flag_one<kSlab>(W, flags, X0 + dx, Y0 + dy, Z0 + dz);
+    return;
+  }
+  for (int X = X0; X <= X0 + ex; X++)
+    for (int Y = Y0; Y <= Y0 + ey; Y++)
+      for (int t = lane; t <= ez; t += 32) flag_one<kSlab>(W, flags, X, Y, Z0 + t);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

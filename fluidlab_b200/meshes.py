@@ -12,6 +12,7 @@ import torch
 from scipy.spatial.transform import Rotation
 
 from .boundaries import _tup
+from . import macros as _macros
 from .macros import FRICTION, DTYPE_NP
 
 
@@ -29,7 +30,8 @@ class Mesh:
                  softness=0, has_dynamics=False, sdf=None, assets_dir=None):
         self.pos, self.euler, self.scale = _tup(pos), _tup(euler), _tup(scale)
         self.raw_file, self.sdf_res = file, sdf_res
-        self.material = eval(material) if isinstance(material, str) else material
+        # the reference's yaml configs name the collider material as a string (`material: PLATE`, configs/macros.py:19-30); resolve it in macros
+        self.material = getattr(_macros, material) if isinstance(material, str) else material
         self.has_dynamics = has_dynamics
         self.softness = float(softness)
         self.friction = 0.0

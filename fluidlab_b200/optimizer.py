@@ -132,8 +132,11 @@ class TrainablePolicy:  # policies.py:131-164
         trainable = torch.from_numpy(np.ascontiguousarray(self.trainable, dtype=np.uint8)).to(dev)
         mask = 0
         if self.fix_dim is not None:
-            for d in np.atleast_1d(self.fix_dim):
-                mask |= 1 << int(d)
+            ncol = int(self.comp_actions_shape[-1])
+            assert ncol <= 32, 'fix_dim_mask covers at most 32 action columns'
+            for d in np.atleast_1d(self.fix_dim):   # the reference's `grads[:, fix_dim] = 0` takes negative indices too
+                assert -ncol <= int(d) < ncol, f'fix_dim {d} out of range for {ncol} action columns'
+                mask |= 1 << (int(d) % ncol)
         self.optim.step_device(self._table, g, trainable=trainable, fix_dim_mask=mask, clip=self.action_range)
         new = self._table.cpu().numpy()
         self.actions_p = new[-1]

@@ -82,7 +82,9 @@ class MPMSimulator:
         self.has_particles = False
         self.sort_every = int(sort_every)  # cell-sort period in steps (0 = never)
         self.use_graphs = True             # replay the 10 substeps of an agent-free step as one CUDA graph per local step index
-        self.store_grids = True            # grad mode: keep each ring frame's forward grid in HBM instead of recomputing it in the backward
+        self.store_grids = 'auto'          # grad mode: keep each ring frame's forward grid in HBM instead of recomputing it in the backward:
+                                           # True (raise if the ring does not fit), False, or 'auto' (if it fits); the choice made is `grids_stored`
+        self.grids_stored = None
         self.fuse_g2p2g = False            # forward-only agent-free steps: inner g2p / p2g pairs fused (fmpm_substeps_fused).  Verified on the
                                            # CPU execution-model shim, NOT yet measured on a B200: opt-in until it is
         if device is None:
@@ -281,7 +283,11 @@ class MPMSimulator:
             T = self.max_substeps_local
             need = T * G * 32
             free, _ = torch.cuda.mem_get_info(dev)
-            if self.store_grids and need < 0.35 * free:
+            fits = need < 0.35 * free
+            if self.store_grids is True and not fits:
+                raise RuntimeError(f'store_grids=True: the per-frame grid ring needs {need / 2**30:.1f} GiB, only {free / 2**30:.1f} GiB are free (use "auto" or False)')
+            self.grids_stored = bool(self.store_grids) and fits
+            if self.grids_stored:
                 nblk = (self.n_grid // 8) ** 3
                 self._pm_ring = torch.zeros((T, G, 4), dtype=f32, device=dev)
                 self._v_ring = torch.zeros((T, G, 4), dtype=f32, device=dev)
@@ -515,7 +521,11 @@ class MPMSimulator:
                         for i in range(self.n_substeps):
                             self._ck(fn(self._h, f0 + i, self._stream()), 'fmpm_substep')
                 self._graphs[key] = g
-            except Exception:
+            except _lib.FmpmError:
+                raise   # a library error inside the capture is a real bug, not "graphs unavailable"
+            except RuntimeError as ex:   # stream capture unsupported / invalidated: fall back to per-substep launches, and say so once
+                import warnings
+                warnings.warn(f'MPMSimulator: CUDA-graph capture failed ({ex}); falling back to per-substep launches')
                 self.use_graphs = False
                 return False
         g.replay()

@@ -9,7 +9,7 @@ import sys
 def row(path):
     txt = open(path).read().strip().splitlines()
     d = json.loads(txt[-1])
-    r, rp, rf = d.get('roofline') or {}, d.get('roofline_p2g_g2p') or {}, d.get('roofline_g2p2g') or {}
+    r, rp, rf = d.get('roofline') or {}, d.get('roofline_p2g_g2p') or {}, (d.get('roofline_fused') or d.get('roofline_g2p2g') or {})
     fb = d.get('fwd_bwd') or {}
     ring = (fb.get('whole_trajectory_ring') or {}).get('value')
     ob = (d.get('e2e_obs_bridge') or {}).get('value')

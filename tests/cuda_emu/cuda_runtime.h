@@ -251,6 +251,8 @@ template <class T> static inline unsigned __match_any_sync(unsigned mask, T x) {
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 template <class T> static inline T __ldcs(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 static inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_relaxed); }

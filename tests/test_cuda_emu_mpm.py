@@ -318,7 +318,9 @@ def test_bench_script_runs_end_to_end_on_the_emulated_device():
     assert line['metric'] == 'mpm_substeps_per_s_fwd' and line['warmup'] >= 3 and line['value'] > 0 and line['e2e']['value'] > 0
     assert line['config']['g2p2g_fused'] is True and line['gpu_launches'] == 2 * 21 + 2
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'}
-    assert line['roofline_g2p2g']['kernel'] == 'k_g2p2g' and line['roofline_g2p2g']['launches_timed'] == 2 * 9
+    rf = line['roofline_fused']
+    assert 'error' not in rf and rf['kernel'].startswith('k_fwd') and rf['launches_timed'] == 2 * 9 and line['roofline']['kernel'] == rf['kernel']
+    assert line['timed_steps'] >= 2 and line['timed_steps'] % 2 == 0
     fb = line['fwd_bwd']
     assert fb['value'] > 0 and 'error' not in fb['whole_trajectory_ring'] and fb['whole_trajectory_ring']['max_substeps_local'] == 30
     assert isinstance(fb['adam_step_ms'], float), fb['adam_step_ms']

@@ -1040,3 +1040,65 @@ def test_cuda_fused_path_matches_runs_of_the_real_reference_agents(scene):
         getattr(cases, f'run_{scene}_case')(device=None)
     finally:
         cases.FUSE[0] = False
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('liquid,boundary,sort_every', [(False, 'cube', 1), (True, 'cube', 1), (True, 'cylinder', 0), (False, 'cylinder', 2), (True, 'cube', 3)],
+                         ids=['multimat', 'liquid', 'liquid-cyl-unsorted', 'multimat-cyl-sort2', 'liquid-sort3'])
+def test_every_forward_path_of_fmpm_substeps_fused(liquid, boundary, sort_every):
+    """k_fwd (g2p + [grid_op] + p2g in one kernel) with each feature switched on in turn — all-liquid specialisation (F carried as one float
+    between step boundaries), grid_op inlined over the triple-buffered accumulators — against the plain p2g / grid_op / g2p substeps and the
+    fp64 oracle; a larger cloud than the shim's run of the same body (tests/fwd_path_case.py) so that many warps and blocks are involved."""
+    _need_gpu()
+    import fwd_path_case
+    fwd_path_case.run(None, liquid, [0, 1, 3, 5, 7] if liquid else [0, 1, 5], boundary=boundary, sort_every=sort_every, n=32, N=20000, steps=3 if sort_every == 3 else 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('path', ['fused', 'plain'])
+def test_c2_full_size_state_parity_vs_the_oracle(path):
+    """BASELINE.json configs[1] at FULL size against the oracle itself (round 1 only had conservation invariants there): C2 = 1M WATER
+    particles, 128^3, free fall from rest, 30 substeps (3 steps, two cell sorts, the CUDA-graph step path) through the default forward path
+    (fused: k_fwd, all-liquid specialisation) and through the plain p2g / grid_op / g2p substeps, vs the fp32 oracle (the reference's
+    arithmetic): x, F <= 1e-5, v <= 1e-5 relative (north star).  Then one backward substep at full size vs the fp64 oracle (<= 1e-4)."""
+    _need_gpu()
+    from oracle import oracle as orc
+    rs = np.random.RandomState(0)
+    n_grid, N, n_steps = 128, 1_000_000, 3
+    x = rs.uniform((0.25, 0.30, 0.25), (0.75, 0.54, 0.75), size=(N, 3))
+    P = make_particles(x, M.WATER, n_grid)
+    o, s = build_pair(P, n_grid, T=50, precision=32, sort_every=2)
+    s.fuse_g2p2g = path == 'fused'
+    for _ in range(n_steps):
+        s.step(None)
+    assert (int(s._lib.fmpm_fwd_path(s._h)) & 3) == 3 and s._can_fuse() == (path == 'fused')
+    for f in range(10 * n_steps):
+        o.substep(f)
+    got, ref = s.get_state(), o.get_frame(10 * n_steps)
+    assert int(got['used'].sum()) == N
+    for k, bar in (('x', 1e-5), ('F', 1e-5), ('v', 1e-5)):
+        assert rel(got[k], ref[k]) < bar, (k, rel(got[k], ref[k]))
+    if path == 'plain':
+        return
+    # ---- one backward substep at full size: adjoint of frame 30 (the complete frame the three steps ended on) from a smooth adjoint of frame 31,
+    # vs the fp64 oracle on the same fp32 state
+    o64 = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), max_substeps_local=2, precision=64)
+    f_last = 10 * n_steps
+    s.enable_grad()
+    st = s.readframe(f_last)
+    o64.set_frame(0, st['x'], st['v'], st['C'], st['F'], st['used'])
+    s.cur_substep_global = f_last
+    s.substep(f_last, True); o64.substep(0)
+    s.cur_substep_global = f_last + 1
+    tp = 2 * np.pi
+    g = dict(x=np.stack([np.sin(tp * x[:, 1] * 2), np.cos(tp * x[:, 2] * 3), np.sin(tp * x[:, 0] * 2)], 1).astype(np.float32),
+             v=np.stack([np.cos(tp * x[:, 0] * 3), np.sin(tp * x[:, 1] * 2), np.cos(tp * x[:, 2])], 1).astype(np.float32) * 1e-3,
+             C=np.zeros((N, 3, 3), np.float32), F=np.zeros((N, 3, 3), np.float32))
+    o64.reset_grad(); o64.set_grad_frame(1, g['x'], g['v'], g['C'], g['F'])
+    s.reset_grad(); s.set_grad(g['x'], g['v'], g['C'], g['F'])
+    o64.substep_grad(0)
+    s.cur_substep_global = f_last
+    s.substep_grad(f_last, True)
+    og, gg = o64.get_grad_frame(0), s.get_grad()
+    for k in ('x', 'v', 'C', 'F'):
+        assert rel(gg[k], og[k]) < 1e-4, (k, rel(gg[k], og[k]))
