@@ -94,16 +94,32 @@ def host_cores():
 
 
 def oracle_lib_all_cores():
-    """the CPU oracle with ALL host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which round 1's reference arm inherited at N > 1
-    (cpu_baseline.cores = 1).  Threads are pinned one per core (the unpinned runs swung 3x between hosts); the OpenMP runtime reads the binding
-    variables when liboracle.so is loaded, so they are set before that."""
-    os.environ.setdefault('OMP_PROC_BIND', 'spread')
-    os.environ.setdefault('OMP_PLACES', 'cores')
+    """the CPU oracle, free to use ALL host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which round 1's reference arm inherited at
+    N > 1 (cpu_baseline.cores = 1).  The thread count actually used is tuned per host by `tune_threads` (more threads are not always faster: the
+    scatter's atomics and NUMA placement make the 128-thread run of a 128-core box 3x slower than its 32-thread run)."""
     os.environ['OMP_NUM_THREADS'] = str(host_cores())
     from oracle import oracle as orc
     L = orc.lib()
     L.orc_set_threads(host_cores())
     return orc, L
+
+
+def tune_threads(L, o, probe=2):
+    """fastest OpenMP thread count for this host among {all, 1/2, 1/4, 1/8 of the cores, 16, 8}: `probe` substeps each (the reference arm gets the
+    CPU's best configuration; SURVEY.md 8d: the speed-up target is against the faster CPU number)"""
+    n = host_cores()
+    best = (None, 0.0)
+    for t in sorted({n, max(1, n // 2), max(1, n // 4), max(1, n // 8), min(n, 16), min(n, 8)}, reverse=True):
+        L.orc_set_threads(t)
+        o.substep(0)
+        t0 = time.perf_counter()
+        for i in range(probe):
+            o.substep(i % 2)
+        r = probe / (time.perf_counter() - t0)
+        if r > best[1]:
+            best = (t, r)
+    L.orc_set_threads(best[0])
+    return best[0]
 
 
 def cpu_baseline_run(n_particles, max_seconds=15.0, max_substeps=60, threads=None):
@@ -113,17 +129,16 @@ def cpu_baseline_run(n_particles, max_seconds=15.0, max_substeps=60, threads=Non
     wp = workload_particles(n_particles)
     P = make_particles(wp['x'], M.WATER, 64 * QUALITY)
     orc, L = oracle_lib_all_cores()
-    if threads:
-        L.orc_set_threads(int(threads))
-    cores = L.orc_get_max_threads()
     o = orc.OracleSim(64 * QUALITY, P, gravity=GRAVITY, max_substeps_local=2, precision=32)
     o.substep(0)  # warm-up (page faults, thread pool)
+    cores = int(threads) if threads else tune_threads(L, o)
+    L.orc_set_threads(cores)
     t0, n = time.perf_counter(), 0
     while n < max_substeps and (time.perf_counter() - t0) < max_seconds:
         o.substep(n % 2); n += 1
     dt = time.perf_counter() - t0
-    return dict(value=n / dt, unit='substeps/s', cores=int(cores), kind='port',
-                sample=f'{n} forward substeps of the full workload ({n_particles} particles, {64 * QUALITY}^3 grid) in {dt:.1f}s; '
+    return dict(value=n / dt, unit='substeps/s', cores=int(cores), kind='port', host_threads_available=host_cores(),
+                sample=f'{n} forward substeps of the full workload ({n_particles} particles, {64 * QUALITY}^3 grid) in {dt:.1f}s with {cores} threads (fastest of 6 counts probed); '
                        'C++/OpenMP restatement of the reference algorithm (Taichi ti.cpu is not installable)')
 
 
@@ -134,6 +149,26 @@ def slab_layout(world, rank, N):
     bounds = slab_bounds(32, 32 + slab_w * world, world)
     lo = ((bounds[rank] - 0.5) * dx, 0.30, 0.36); hi = ((bounds[rank + 1] - 0.5) * dx, 0.30 + 72 * dx, 0.36 + 72 * dx)
     return q, bounds, lo, hi
+
+
+C5_N, C5_LO, C5_HI = 8_000_000, (0.10, 0.20, 0.10), (0.90, 0.42, 0.90)   # WATER, ~8.4 particles per cell at 256^3
+
+
+def c5_shard(world, rank, n=C5_N):
+    """BASELINE.json configs[4]: the 8M-particle water body on the 256^3 grid; rank r of `world` gets the particles whose stencil-centre plane lies
+    in its x-slab (slabs of equal width over the body's 206 planes, boundaries on multiples of 8).  Returns (quality, bounds, particle dict, global ids)."""
+    from fluidlab_b200 import macros as M
+    from fluidlab_b200.slab import slab_bounds
+    q, ng = 4, 256
+    x = np.random.RandomState(0).uniform(C5_LO, C5_HI, size=(n, 3))
+    bounds = slab_bounds(24, 232, world) if world > 1 else [24, 232]
+    cp = (x[:, 0] * ng - 0.5).astype(np.int32) + 1
+    lo = bounds[rank] if rank > 0 else -10 ** 6
+    hi = bounds[rank + 1] if rank < world - 1 else 10 ** 6
+    mine = np.where((cp >= lo) & (cp < hi))[0]
+    parts = dict(x=x[mine], mat=np.full(len(mine), M.WATER, dtype=np.int32), used=np.ones(len(mine), dtype=np.int32), rho=np.full(len(mine), M.RHO[M.WATER]),
+                 body_id=np.zeros(len(mine), dtype=np.int32), bodies={'n': 1})
+    return q, bounds, parts, mine
 
 
 def run_reference(args):
@@ -159,10 +194,10 @@ def run_reference(args):
         n_grid, x = 64 * q, np.concatenate(xs)
         workload = f'C2-weak: {world} x {N_PARTICLES} water particles as x-slabs of one body, 256^3 grid, forward (the repo arm\'s workload at {world} GPUs)'
     P = make_particles(x, M.WATER, n_grid)
-    cores = L.orc_get_max_threads()
     o = orc.OracleSim(n_grid, P, gravity=GRAVITY, max_substeps_local=2, precision=32)
     for _ in range(max(1, min(args.warmup, 2))):
         o.substep(0)
+    cores = tune_threads(L, o)
     K = max(1, min(args.steps, 20))
     t0 = time.perf_counter()
     for i in range(K):
@@ -174,7 +209,7 @@ def run_reference(args):
             'impl': 'reference',
             'config': {'workload': workload, 'step': '1 substep (bounded sample)', 'same_config_as_repo_arm': True},
             'cpu_baseline': {'value': val, 'unit': 'substeps/s', 'cores': int(cores), 'kind': 'port',
-                             'sample': f'{K} forward substeps of the full workload ({len(x)} particles, {n_grid}^3 grid), threads pinned one per core; '
+                             'sample': f'{K} forward substeps of the full workload ({len(x)} particles, {n_grid}^3 grid), {cores} of {host_cores()} host threads (the fastest of 6 thread counts probed); '
                                        'C++/OpenMP restatement of the reference (Taichi not installable)'},
             'e2e': {'value': val, 'unit': 'substeps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -189,6 +224,8 @@ def main():
     ap.add_argument('--particles', type=int, default=N_PARTICLES)
     ap.add_argument('--bwd', type=int, default=1, help='also time forward+backward (extra keys)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help="weak (default): 1M particles per GPU (C2 at N = 1; N x-slabs of one body on a 256^3 grid at N > 1); "
+                    "strong: BASELINE.json configs[4] — C5, 8M water particles on a 256^3 grid, sharded into N x-slabs (N = 1: one GPU holds it all)")
     ap.add_argument('--min-seconds', type=float, default=1.0, help='minimum length of the timed region (the K steps are repeated)')
     ap.add_argument('--fuse-g2p2g', type=int, default=1, help='1 (default, measured faster: profiles/README.md): forward steps use fmpm_substeps_fused (the gather of substep f and the '
                     'scatter of f+1 in one kernel, k_fwd); 0: the plain p2g / grid_op / g2p substeps')
@@ -213,15 +250,23 @@ def main():
     T = 50
     N = args.particles
     slab = None
+    strong = args.scaling == 'strong'
+    if strong:
+        T = 20   # 8M particles x 21 frames x 100 B = 17 GB per GPU at N = 1
+        args.bwd, args.no_cpu = 0, True   # the strong-scaling arm is an extra: forward throughput + e2e only
     if world == 1:
-        sim = MPMSimulator(dim=3, quality=QUALITY, gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T, max_substeps_global=10 ** 7,
+        if strong:
+            q5, _, parts, _ = c5_shard(1, 0, args.particles if args.particles != N_PARTICLES else C5_N)
+            N = len(parts['x'])
+        sim = MPMSimulator(dim=3, quality=q5 if strong else QUALITY, gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T, max_substeps_global=10 ** 7,
                            ckpt_dest='gpu', device=dev, sort_every=args.sort_every)
-        parts = workload_particles(N, seed=rank)
+        if not strong:
+            parts = workload_particles(N, seed=rank)
         sim.build(None, None, [], parts)
         sim.fuse_g2p2g = bool(args.fuse_g2p2g)
         # The block falls 0.25 of the domain: free fall lasts ~110 steps (SURVEY.md 8d times 1,000 substeps after 100 warm-up).  Longer timed regions
         # replay that episode: every EPISODE steps the initial state is restored from a device-side copy INSIDE the timed region (~0.1 % of the time).
-        EPISODE = 100
+        EPISODE = 30 if strong else 100   # C5: the reference's fixed dt is only stable for ~700 substeps of water at 256^3
         _cnt1 = [0]
         _init1 = [None]
 
@@ -231,16 +276,22 @@ def main():
                 sim.set_state(0, _init1[0])
             _cnt1[0] += 1
             sim.step(None)
-        workload = f'C2 water block free fall, {N} particles, 128^3 grid, fp32, forward (BASELINE.json configs[1])'
+        workload = (f'C5 water body, {N} particles, 256^3 grid, fp32, forward (BASELINE.json configs[4], strong scaling: the whole body on one GPU)' if strong else
+                    f'C2 water block free fall, {N} particles, 128^3 grid, fp32, forward (BASELINE.json configs[1])')
         parallelism = 'single GPU'
     else:
         # weak scaling: the C2 block (same particle count and ~8 particles/cell per GPU) laid out as x-slabs of one global
         # water body on a 256^3 grid; ghost planes of the (momentum, mass) grid are summed between neighbours every substep.
         from fluidlab_b200.slab import SlabMPMSimulator
-        q, bounds, lo, hi = slab_layout(world, rank, N)
-        parts = workload_particles(N, seed=rank, lo=lo, hi=hi)
-        slab = SlabMPMSimulator(q, GRAVITY, parts, gid=np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1), max_substeps_local=T, device=dev,
-                                exchange=os.environ.get('SLAB_EXCHANGE', 'peer'), sync=os.environ.get('SLAB_SYNC', 'barrier'))
+        if strong:
+            q, bounds, parts, gid5 = c5_shard(world, rank, args.particles if args.particles != N_PARTICLES else C5_N)
+            N = len(parts['x'])
+        else:
+            q, bounds, lo, hi = slab_layout(world, rank, N)
+            parts = workload_particles(N, seed=rank, lo=lo, hi=hi)
+        slab = SlabMPMSimulator(q, GRAVITY, parts, gid=gid5 if strong else np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1) + 1024, max_substeps_local=T, device=dev,
+                                exchange=os.environ.get('SLAB_EXCHANGE', 'peer'), sync=os.environ.get('SLAB_SYNC', 'signal'), sort_every=args.sort_every,
+                                halo=int(os.environ.get('SLAB_HALO', '4')))
         sim = slab.sim
         sim.fuse_g2p2g = bool(args.fuse_g2p2g)   # x-slab mode: the fused kernel's scatter half reduces frame f+1's ghost planes into the neighbour
         # the reference's fixed dt = 2e-4 is unstable for water at 256^3 beyond ~700 substeps (profiles/check_stability_256.py,
@@ -255,8 +306,10 @@ def main():
                 sim.set_state(0, _init_dev); slab.gid.copy_(_gid0)
             _cnt[0] += 1
             slab.step()
-        workload = (f'C2-weak: {N} water particles per GPU (~8/cell) as {world} x-slabs of one body, 256^3 grid, fp32, forward; value counts '
-                    f'1M-particle substeps (global substeps/s = value / n_gpus)')
+        workload = ((f'C5 water body, {C5_N if args.particles == N_PARTICLES else args.particles} particles, 256^3 grid, fp32, forward, sharded into {world} x-slabs (BASELINE.json '
+                     f'configs[4], strong scaling); value = substeps/s of the WHOLE body') if strong else
+                    (f'C2-weak: {N} water particles per GPU (~8/cell) as {world} x-slabs of one body, 256^3 grid, fp32, forward; value counts '
+                     f'1M-particle substeps (global substeps/s = value / n_gpus)'))
         if slab.exchange == 'peer':
             sync_txt = ('one neighbour handshake per substep inside the library, the whole step in one call' if slab.sync == 'signal'
                         else 'one device-side signal-pad barrier per substep')
@@ -302,7 +355,7 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms = ms_total / reps            # per K steps
     clocks = cs.summary()
-    value = world * K * SUBSTEPS_PER_STEP / (ms * 1e-3)
+    value = (1 if strong else world) * K * SUBSTEPS_PER_STEP / (ms * 1e-3)
 
     # ------------------------------------------------------------------ per-kernel timing (roofline)
     f = sim.cur_substep_local
@@ -561,7 +614,7 @@ def main():
         episode()
     b.record(); barrier()
     e2e_ms = max_over_ranks(max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3))
-    e2e_val = world * n_ep * EP * SUBSTEPS_PER_STEP / (e2e_ms * 1e-3)
+    e2e_val = (1 if strong else world) * n_ep * EP * SUBSTEPS_PER_STEP / (e2e_ms * 1e-3)
 
     # the same episodes with the observation assembled on the device (MPMSimulator.get_obs_RL): FluidEnv._get_obs keeps
     # ~200 particles per body, so the per-step D2H shrinks from 28 B x N to a few KB.  Reported as an EXTRA key; `e2e` stays the full-state API.
@@ -594,7 +647,7 @@ def main():
         line = {
             'metric': 'mpm_substeps_per_s_fwd', 'value': value, 'unit': 'substeps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'timed_steps': K * reps, 'timed_region_ms': ms_total,
-            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': workload,
                        'substeps_per_step': SUBSTEPS_PER_STEP, 'dt': 2e-4, 'gravity': GRAVITY, 'max_substeps_local': T,
                        'cell_sort_every_steps': args.sort_every,

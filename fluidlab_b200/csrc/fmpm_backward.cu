@@ -244,6 +244,9 @@ __device__ __forceinline__ Mat3 constitutive_grad(const KParams& P, const Consti
 }
 
 #define PG_WARPS 4
+#ifndef PG_MINB_LIQUID
+#define PG_MINB_LIQUID 4   // all-liquid instantiation: 128 registers, 12 B of spills (5 CTAs/SM = 96 registers would spill 372 B)
+#endif
 #ifndef PG_MINB
 #define PG_MINB 4   // <=128 registers (16 warps/SM) with ~200 B of L1-resident spills: 164 us -> 121 us at 1M particles
 #endif
@@ -312,7 +315,10 @@ __device__ __forceinline__ void adjoint_gather(const float* fx, const float w[3]
   gfx[2] = sgz - (Mg.m[2] * vp[0] + Mg.m[5] * vp[1] + Mg.m[8] * vp[2]) - (Ma.m[2] * gvp[0] + Ma.m[5] * gvp[1] + Ma.m[8] * gvp[2]);
 }
 
-__global__ void __launch_bounds__(PG_WARPS * 32, PG_MINB) k_particle_grad(const KParams P, const int f, const int gin, const int gout) {
+// kMat == 1: every particle is a mu = 0 liquid (FmpmConfig.scene_flags): no SVD and no SVD adjoint in the instruction stream, the constitutive
+// adjoint is gJ * cof(F~) (+ the J^(1/3) term of F[f+1])
+template <int kMat>
+__global__ void __launch_bounds__(PG_WARPS * 32, kMat == 1 ? PG_MINB_LIQUID : PG_MINB) k_particle_grad(const KParams P, const int f, const int gin, const int gout) {
   __shared__ float4 tiles[PG_WARPS][2][9 * G2P_ZMAX];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   float4* tg = tiles[threadIdx.x >> 5][0];
@@ -335,7 +341,18 @@ __global__ void __launch_bounds__(PG_WARPS * 32, PG_MINB) k_particle_grad(const 
   load_F(P.pf, P.pf8, P, f, s, st.F);
   const float4 mt = __ldg(P.mats + ((st.meta >> 8) & 0xff));
   const float mu = mt.x, lam = mt.y, m = mt.z; const int cls = __float_as_int(mt.w);
-  Constit K; constitutive(P, st, mu, lam, m, cls, K);
+  Constit K;
+  if (kMat == 1) {   // F~ = (I + dt C) F, J = det F~, affine = k_stress * lam J (J - 1) I + m C   (MPM:254-258, 339-344 with mu = 0)
+    Mat3 IdC0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) IdC0.m[i] = P.dt * st.C.m[i] + ((i % 4 == 0) ? 1.f : 0.f);
+    K.Ft = m3_mul(IdC0, st.F); K.need_svd = false; K.J = m3_det(K.Ft);
+    const float iso = lam * K.J * (K.J - 1.f);
+#pragma unroll
+    for (int i = 0; i < 9; i++) K.A.m[i] = P.k_stress * ((i % 4 == 0) ? iso : 0.f) + m * st.C.m[i];
+  } else {
+    constitutive(P, st, mu, lam, m, cls, K);
+  }
   float w[3][3], dw[3][3]; bspline(fx, w); bspline_d(fx, dw);
   float gxin[3], gve[3], mv[3];
   Mat3 Mg, Ma;
@@ -366,7 +383,19 @@ __global__ void __launch_bounds__(PG_WARPS * 32, PG_MINB) k_particle_grad(const 
 #pragma unroll
   for (int k = 0; k < 3; k++) { ox[k] = gxin[k] + P.inv_dx * gfx[k]; ov[k] = m * gvp[k]; }
   Mat3 gFn; load_F(P.gf, P.gf8, P, gin, s, gFn);
-  Mat3 gFt = constitutive_grad(P, K, mu, lam, cls, gA, gFn);
+  Mat3 gFt;
+  if (kMat == 1) {   // constitutive_grad with need_svd == false, cls == MAT_LIQUID
+    const float trP = P.k_stress * m3_trace(gA);
+    float gJ = lam * (2.f * K.J - 1.f) * trP;
+    const float cb = cbrtf(K.J);
+    gJ += (1.f / 3.f) * (cb / K.J) * m3_trace(gFn);
+    const float* a = K.Ft.m;
+    gFt.m[0] = gJ * (a[4] * a[8] - a[5] * a[7]); gFt.m[1] = gJ * (a[5] * a[6] - a[3] * a[8]); gFt.m[2] = gJ * (a[3] * a[7] - a[4] * a[6]);
+    gFt.m[3] = gJ * (a[2] * a[7] - a[1] * a[8]); gFt.m[4] = gJ * (a[0] * a[8] - a[2] * a[6]); gFt.m[5] = gJ * (a[1] * a[6] - a[0] * a[7]);
+    gFt.m[6] = gJ * (a[1] * a[5] - a[2] * a[4]); gFt.m[7] = gJ * (a[2] * a[3] - a[0] * a[5]); gFt.m[8] = gJ * (a[0] * a[4] - a[1] * a[3]);
+  } else {
+    gFt = constitutive_grad(P, K, mu, lam, cls, gA, gFn);
+  }
   // compute_F_tmp.grad (MPM:546): gC += dt * gFt F^T ; gF += (I + dt C)^T gFt ; plus gC += m * gA
   Mat3 oC = m3_add(m3_scale(gA, m), m3_scale(m3_mul_nt(gFt, st.F), P.dt));
   Mat3 IdC;
@@ -444,7 +473,8 @@ static int particle_grad_impl(FmpmHandle* h, int f, int gin, int gout, int ring_
   if (check_bound_b(h, "fmpm_particle_grad")) return 1;
   KParams P = make_kparams(h, ring_slot);
   if (P.N == 0) return 0;
-  FMPM_LAUNCH(k_particle_grad, (P.N + PG_WARPS * 32 - 1) / (PG_WARPS * 32), PG_WARPS * 32, 0, stream, P, f, gin, gout);
+  if (h->cfg.scene_flags & FMPM_SCENE_ALL_LIQUID_MU0) FMPM_LAUNCH(k_particle_grad<1>, (P.N + PG_WARPS * 32 - 1) / (PG_WARPS * 32), PG_WARPS * 32, 0, stream, P, f, gin, gout);
+  else FMPM_LAUNCH(k_particle_grad<0>, (P.N + PG_WARPS * 32 - 1) / (PG_WARPS * 32), PG_WARPS * 32, 0, stream, P, f, gin, gout);
   FMPM_CHECK_LAUNCH(h, "fmpm_particle_grad");
   return 0;
 }

@@ -17,7 +17,17 @@ struct CollidersDev {
   float y_min;
 };
 
+#ifdef FMPM_HOST_EMU
+struct CUtensorMap_st { alignas(64) unsigned long long opaque[16]; };
+typedef CUtensorMap_st CUtensorMap;
+#define __grid_constant__
+#else
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched from the driver at run time, no link dependency on libcuda)
+#endif
+
 struct FmpmHandle {
+  CUtensorMap tm_gv8, tm_gv16;   // TMA descriptors of grid_v as a (4, n, n, n) float tensor with boxes (4, 8 | 16, 4, 4): the footprint tile of k_fwd
+  int tma_ok;                    // 0: descriptors not available (encoder missing / FMPM_TMA=0): k_fwd stages its tile with LDG + STS
   FmpmConfig cfg;
   FmpmBuffers buf;
   CollidersDev col;
@@ -389,6 +399,26 @@ __device__ __forceinline__ void fmpm_pdl_wait() {}
 // chain lets its successor's CTAs become resident as soon as all of its own CTAs have started (fmpm_pdl_trigger at the top), so the launch
 // latency and the tail of the grid are filled with the successor's prologue; the successor touches NO global memory before fmpm_pdl_wait,
 // which returns once the predecessor grid has completed and its writes are visible.  Both are no-ops in a launch without the attribute.
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: one elected lane arms the warp's mbarrier with the byte count and issues the tile copy, every
+// lane then waits on the barrier's phase.  The wait is bounded: a descriptor that never completes traps instead of hanging the GPU.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, const unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, const unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, unsigned long long* bar, const int c0, const int c1, const int c2, const int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, const unsigned phase) {
+  unsigned done = 0;
+  for (int it = 0; it < (1 << 22) && !done; it++)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  if (!done) __trap();
+}
 __device__ __forceinline__ void fmpm_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fmpm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 template <class... Params, class... Args>

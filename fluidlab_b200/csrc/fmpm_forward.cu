@@ -161,29 +161,36 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
 // MPM:380-398 on the active blocks; optionally clears the (momentum, mass) accumulators for the next substep
 // and zeroes the v_out adjoint of the same blocks (backward pass).
 __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, const int clear_pm, const int zero_ggv, const int reset_flags) {
-  // one CTA per 8^3-node block: CTAs of unflagged blocks leave after one broadcast load, the others make ONE memory round trip (r02e: the
-  // round-1 version — flag compaction through shared memory, two barriers, a block loop — took 10.6 us for 4 MB, 5.8 barrier stalls per issue)
   const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
+  // this CTA owns blocks blockIdx.x + q*gridDim.x; their flags are fetched in parallel (thread q reads flag q) and the CTA
+  // then walks the flagged ones (nblk / gridDim.x <= 256 for every supported grid)
+  // (A one-CTA-per-block variant without shared memory or barriers was measured slower, r02f: 12.7 us against 10.6 us — 4096 tiny CTAs cost
+  // more to schedule than the flag compaction below.)
+  __shared__ int s_act[256];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
   fmpm_pdl_trigger();
   fmpm_pdl_wait();
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    if (P.blk_flags[blk] == 0) continue;   // CTA-uniform
+  __syncthreads();
+  {
+    const int blk = blockIdx.x + threadIdx.x * gridDim.x;
+    if (blk < nblk && P.blk_flags[blk] != 0) s_act[atomicAdd(&s_n, 1)] = blk;
+  }
+  __syncthreads();
+  const int n_act = s_n;
+  for (int ai = 0; ai < n_act; ai++) {
+    const int blk = s_act[ai];
     const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
-    float4 pm[2]; int g[2], ci[2], cj[2], ck[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const int t = threadIdx.x + r * 256;
-      ci[r] = bx * 8 + (t >> 6); cj[r] = by * 8 + ((t >> 3) & 7); ck[r] = bz * 8 + (t & 7);
-      g[r] = (ci[r] * n + cj[r]) * n + ck[r];
-      pm[r] = P.grid_pm[g[r]];
-    }
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const int i = ci[r], j = cj[r], k = ck[r];
+      const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+      const int g = (i * n + j) * n + k;
+      const float4 pm = P.grid_pm[g];
       float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pm[r].w > FMPM_EPS) {
-        const float inv_m = 1.f / pm[r].w;
-        float v[3] = {inv_m * pm[r].x + P.dt * P.gx, inv_m * pm[r].y + P.dt * P.gy, inv_m * pm[r].z + P.dt * P.gz};
+      if (pm.w > FMPM_EPS) {
+        const float inv_m = 1.f / pm.w;
+        float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
         const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
         for (int si = 0; si < P.col.n_statics; si++) {  // statics[i].collide, MPM:388-390
           float o[3]; sdf_collide<false>(P.col.statics[si], false, nullptr, nullptr, nullptr, nullptr, P.dt, pos, v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -197,13 +204,11 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, c
         boundary_v(P, pos, v, fac);
         out = make_float4(v[0], v[1], v[2], 0.f);
       }
-      P.grid_v[g[r]] = out;
-      if (clear_pm && (pm[r].w != 0.f || pm[r].x != 0.f || pm[r].y != 0.f || pm[r].z != 0.f)) P.grid_pm[g[r]] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (zero_ggv) P.ggrid_v[g[r]] = make_float4(0.f, 0.f, 0.f, 0.f);
+      P.grid_v[g] = out;
+      if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zero_ggv) P.ggrid_v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // every thread has read the flag above (the loads of this iteration precede the barrier-free reset only in program order of thread 0, so
-    // the reset is delayed until the whole CTA passed the flag test)
-    if (reset_flags) { __syncthreads(); if (threadIdx.x == 0) P.blk_flags[blk] = 0; }
+    if (reset_flags && threadIdx.x == 0) P.blk_flags[blk] = 0;
   }
 }
 
@@ -470,8 +475,10 @@ __device__ __forceinline__ void fwd_gather_unstaged(const KParams& P, const floa
 // map (an odd prime not dividing the grid size): neighbouring slot blocks — which share their nodes — then run in different waves.
 template <int kMat, bool kInline, bool kSlab>
 __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams P, const int f, float4* __restrict__ clr, int* __restrict__ clr_flags, const int full,
-                                                                            const float4* __restrict__ pms, const int tag_off, const int stride) {
+                                                                            const float4* __restrict__ pms, const int tag_off, const int stride,
+                                                                            const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm16, const int use_tma) {
   __shared__ ScatterSmem smem[P2G_WARPS];
+  __shared__ unsigned long long tbar[P2G_WARPS];   // one mbarrier per warp: completion of its TMA footprint tile
   static_assert(sizeof(((ScatterSmem*)0)->rec) >= FWD_TILE_COLS * 16 * sizeof(float4), "the gather tile is staged in the scatter records' storage");
   const int lane = threadIdx.x & 31, wib = __shfl_sync(SC_FULL, (int)(threadIdx.x >> 5), 0);   // broadcast: dependent code is compiled warp-uniform
   ScatterSmem& S = smem[wib];
@@ -533,6 +540,21 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
   const bool any = bx1 >= 0;
   const bool staged = any && nx <= 4 && ny <= 4 && nz <= 16;
   const int tzs = nz <= 8 ? 3 : 4;   // rows of 8 or 16 nodes
+#ifndef FMPM_HOST_EMU
+  const bool tma = !kInline && use_tma && staged;   // warp-uniform
+  if (tma) {
+    // The 3x3x3 neighbourhoods of the warp's particles as ONE TMA tile: cp.async.bulk.tensor.4d copies the box (4 components, 8 | 16 nodes in z,
+    // 4 in y, 4 in x) at (0, bz0, by0, bx0) of grid_v into the warp's tile (out-of-range nodes arrive as zeros) and completes on the warp's
+    // mbarrier; the lanes meanwhile go on with the particle-side arithmetic and wait just before the gather.
+    if (lane == 0) {
+      mbar_init(&tbar[wib], 1);
+      mbar_expect_tx(&tbar[wib], (unsigned)((FWD_TILE_COLS << tzs) * sizeof(float4)));
+      tma_load_4d(tile, tzs == 3 ? &tm8 : &tm16, &tbar[wib], 0, bz0, by0, bx0);
+    }
+  } else
+#else
+  const bool tma = false;
+#endif
   if (staged) {
     const int n = P.n, tot = FWD_TILE_COLS << tzs;
     // four rows of 32 slots per batch: all loads of a batch are issued before the first use (one exposed L2 latency per batch)
@@ -567,6 +589,9 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
     }
     __syncwarp();
   }
+#ifndef FMPM_HOST_EMU
+  if (tma) __syncwarp();   // the warp's mbarrier was initialised by lane 0
+#endif
   int key = -1;
   int b1[3] = {0, 0, 0}; bool ok1 = false;
   float q[3] = {0.f, 0.f, 0.f}, B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, m = 0.f;
@@ -582,6 +607,9 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
       // ---- g2p of frame f (MPM:400-426) + advect (MPM:497-505)
       bspline(fx, w);
       const float c4 = 4.f * P.inv_dx;
+#ifndef FMPM_HOST_EMU
+      if (tma) mbar_wait(&tbar[wib], 0);   // the tile has landed (every gathering lane waits; the others meet them at the __syncwarp before the staging)
+#endif
       if (staged) {
         const float4* t0 = tile + ((((b[0] - bx0) << 2) + (b[1] - by0)) << tzs) + (b[2] - bz0);
         g2p_gather_v(fx, w, [&](int c) { const float4* p = t0 + ((((c / 3) << 2) + (c % 3)) << tzs); Col3 r; r.g0 = p[0]; r.g1 = p[1]; r.g2 = p[2]; return r; }, st.v, st.C, c4);
@@ -781,7 +809,8 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring
   if (!P.blk_flags) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block flags were not bound"); return 1; }
   if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
   const int nblk = P.nb * P.nb * P.nb;
-  const int grid = nblk < 65536 ? nblk : 65536;   // one CTA per sparse block (a grid-stride loop covers grids beyond 320^3)
+  int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  if ((nblk + grid - 1) / grid > 256) grid = (nblk + 255) / 256;  // keep <= 256 blocks per CTA (parallel flag fetch)
   // the flags are consumed (reset) here only when nothing later in the substep needs them: plain forward substeps
   const int reset_flags = (clear_pm && ring_slot < 0) ? 1 : 0;
   FMPM_LAUNCH_PDL(h->use_pdl != 0, k_grid_op, grid, 256, 0, stream, P, f, clear_pm, zero_ggv, reset_flags);
@@ -846,6 +875,7 @@ static int fwd_path(const FmpmHandle* h) {
   if (!agent) {
     p |= FWD_KFWD;
     if (h->cfg.scene_flags & FMPM_SCENE_ALL_LIQUID_MU0) p |= FWD_LIQUID;
+    if (h->tma_ok) p |= FWD_TMA;
     if (h->buf.grid_pm3 && h->buf.blk_flags3 && h->col.n_statics == 0 && !h->slab.enabled) p |= FWD_INLINE;
   }
   p &= h->fwd_mask;
@@ -953,7 +983,8 @@ static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream, in
   }
   const int tag_off = f - tag_f0;
   const bool slab = h->slab.enabled != 0;   // (never together with the inlined grid_op, see fwd_path)
-#define FWD_GO(a, b, c) FMPM_LAUNCH_PDL(h->use_pdl != 0, FWD_K(a, b, c), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full, pms, tag_off, stride)
+  const int use_tma = (h->tma_ok && (path & FWD_TMA) && !inl) ? 1 : 0;
+#define FWD_GO(a, b, c) FMPM_LAUNCH_PDL(h->use_pdl != 0, FWD_K(a, b, c), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full, pms, tag_off, stride, h->tm_gv8, h->tm_gv16, use_tma)
   if (liq) { if (inl) FWD_GO(1, true, false); else if (slab) FWD_GO(1, false, true); else FWD_GO(1, false, false); }
   else { if (inl) FWD_GO(0, true, false); else if (slab) FWD_GO(0, false, true); else FWD_GO(0, false, false); }
 #undef FWD_GO

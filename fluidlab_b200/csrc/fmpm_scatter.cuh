@@ -51,7 +51,7 @@ __device__ __forceinline__ void red_add_v4_if(const bool p, float4* addr, const 
 #endif
 #define SC_REC 9           // float4 records per particle: 36-word stride, so the 128-bit stores of lane = particle are bank-conflict free
 #define SC_WQ 7            // float4 per particle of stencil weights (27 + 1 pad): 28-word stride, conflict free as well
-struct __align__(16) ScatterSmem {
+struct __align__(128) ScatterSmem {   // 128-byte aligned: `rec` doubles as the destination of the TMA footprint tile (k_fwd)
   // per particle: nine Q_ab = (q + a*B[:,0] + b*B[:,1], m) for the (a,b) node columns of the stencil and b2 = (B02,B12,B22,0):
   // a lane (a,b,c) needs only Q_ab + c*B[:,2], i.e. 2 LDS.128 + 1 LDS and 4 FFMA2 per particle
   float4 rec[32 * SC_REC];

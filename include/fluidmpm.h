@@ -207,7 +207,8 @@ int fmpm_g2p2g(FmpmHandle* h, int f, int write_vc, void* stream);
 int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream);
 /* which kernels fmpm_substeps_fused uses for this handle (bit 0: k_fwd instead of k_g2p2g, bit 1: all-liquid specialisation, bit 2: grid_op
  * inlined with the triple-buffered accumulators, bit 3: footprint tiles staged by TMA); `mask` clears bits for A/B measurements
- * (fmpm_set_fwd_mask(h, 0) = the round-1 path: grid_op + k_g2p2g).  Default mask: all bits set. */
+ * (fmpm_set_fwd_mask(h, 0) = the round-1 path: grid_op + k_g2p2g).  Default mask: everything except bit 2 (the in-kernel grid_op was measured
+ * slower than the separate k_grid_op launch on a B200, profiles/README.md; fmpm_set_fwd_mask(h, 7) switches it on). */
 /* ONE fused substep of the sequence above: g2p(f) + p2g(f+1) with the kernel fmpm_substeps_fused would pick (grid_op NOT inlined: run
  * fmpm_grid_op(f) before).  full != 0: frame f+1 and F[f+2] are written completely (the last fused substep of a step); full == 0: all-liquid
  * scenes write x, used and F22 only.  For hosts that interleave their own work between the substeps, and for per-kernel timing. */

@@ -3,7 +3,7 @@
 
 fmpm_substeps_fused picks its kernels from what the scene allows (fmpm_fwd_path); FMPM_FWD_MASK / fmpm_set_fwd_mask switch features off:
     0  round-1 path (grid_op + k_g2p2g)        1  k_fwd                      3  k_fwd, all-liquid specialisation (F carried as one float)
-    5  k_fwd + inlined grid_op (one launch per substep, triple-buffered accumulators)       7  all of them
+    5  k_fwd + lazy in-kernel grid_op (one launch per substep, triple-buffered accumulators)       7  both      + 8: footprint tile by TMA (9, 11)
 Every mask must reproduce the plain p2g / grid_op / g2p substeps and the fp64 oracle."""
 import numpy as np
 
@@ -44,7 +44,8 @@ def run(device, liquid, masks, boundary='cube', n=16, N=330, sort_every=1, steps
         if mask is not None:
             s._ck(s._lib.fmpm_set_fwd_mask(s._h, int(mask)), 'fmpm_set_fwd_mask')
             path = int(s._lib.fmpm_fwd_path(s._h))
-            assert path == (mask & (7 if liquid else 5)) if (mask & 1) else path == 0, (mask, path)
+            assert (path & 7) == (mask & (7 if liquid else 5)) if (mask & 1) else path == 0, (mask, path)
+            assert (path & 8) in (0, mask & 8)   # bit 3: the footprint tile arrives by TMA (a GPU with the driver's tensor-map encoder; never on the CPU shim)
         st = s.get_state(); st['v'][:] = v0; st['F'][:] = F0; st['C'][:] = C0; s.set_state(0, st)
         for _ in range(steps):
             s.step(None)

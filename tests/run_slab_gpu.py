@@ -105,6 +105,21 @@ def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
             ref.step_grad(None)
         g = ref.get_grad()
         rel = lambda a, b: float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
+        if os.environ.get('SLAB_SELFCHECK', '0') == '1':
+            # conditioning of the test itself: the same single-GPU gradient again with another summation order (no cell sort, recompute path)
+            ref2 = MPMSimulator(dim=3, quality=q, gravity=(0.0, -10.0, 0.0), horizon=1000, max_substeps_local=20, max_substeps_global=10 ** 6, ckpt_dest='gpu', device=dev, sort_every=0)
+            ref2.store_grids = False
+            ref2.build(None, None, [], parts(np.arange(Ntot)))
+            s0 = ref2.get_state(); s0['v'][:] = v0; ref2.set_state(0, s0)
+            ref2.enable_grad()
+            for _ in range(n_steps):
+                ref2.step(None)
+            xT2 = ref2.get_state()['x']
+            ref2.reset_grad(); ref2.set_grad(2.0 * (xT2 - tgt.cpu().numpy()), np.zeros((Ntot, 3), np.float32), z9, z9)
+            for _ in range(n_steps):
+                ref2.step_grad(None)
+            g2 = ref2.get_grad()
+            print('selfcheck single-GPU vs single-GPU (unsorted, recompute path): ' + ' '.join(f'g{k}={rel(g2[k], g[k]):.2e}' for k in ('x', 'v', 'C', 'F')) + f' xT={rel(xT2, xT):.2e}')
         assert len(got['gid']) == Ntot and np.array_equal(got['gid'], np.arange(Ntot)), 'particles lost or duplicated'
         errs = {k: rel(got[k], g[k]) for k in ('x', 'v', 'C', 'F')}
         print(f'slab backward world={world} exchange={exchange}: migrated={int(migrated[0].item())} at {int(migrated[1].item())} (rank, step) pairs; rel err ' +
