@@ -266,7 +266,7 @@ def main():
         sim.fuse_g2p2g = bool(args.fuse_g2p2g)
         # The block falls 0.25 of the domain: free fall lasts ~110 steps (SURVEY.md 8d times 1,000 substeps after 100 warm-up).  Longer timed regions
         # replay that episode: every EPISODE steps the initial state is restored from a device-side copy INSIDE the timed region (~0.1 % of the time).
-        EPISODE = 30 if strong else 100   # C5: the reference's fixed dt is only stable for ~700 substeps of water at 256^3
+        EPISODE = 8 if strong else 100    # C5 from rest turns non-finite after ~140 substeps with the reference's fixed dt (profiles/check_c5.py: c dt / dx = 0.85 at 256^3)
         _cnt1 = [0]
         _init1 = [None]
 
@@ -291,7 +291,7 @@ def main():
             parts = workload_particles(N, seed=rank, lo=lo, hi=hi)
         slab = SlabMPMSimulator(q, GRAVITY, parts, gid=gid5 if strong else np.arange(N) + rank * N, bounds=bounds, capacity=int(N * 1.1) + 1024, max_substeps_local=T, device=dev,
                                 exchange=os.environ.get('SLAB_EXCHANGE', 'peer'), sync=os.environ.get('SLAB_SYNC', 'signal'), sort_every=args.sort_every,
-                                halo=int(os.environ.get('SLAB_HALO', '4')))
+                                halo=int(os.environ.get('SLAB_HALO', '4')), migrate_every=int(os.environ.get('SLAB_MIGRATE_EVERY', '4')))
         sim = slab.sim
         sim.fuse_g2p2g = bool(args.fuse_g2p2g)   # x-slab mode: the fused kernel's scatter half reduces frame f+1's ghost planes into the neighbour
         # the reference's fixed dt = 2e-4 is unstable for water at 256^3 beyond ~700 substeps (profiles/check_stability_256.py,
@@ -301,7 +301,7 @@ def main():
         _gid0 = slab.gid.clone()
 
         def step_fn():
-            if _cnt[0] and _cnt[0] % 30 == 0:
+            if _cnt[0] and _cnt[0] % (8 if strong else 30) == 0:   # (C5 is only stable for ~140 substeps from rest, profiles/check_c5.py)
                 sim.cur_substep_global = 0
                 sim.set_state(0, _init_dev); slab.gid.copy_(_gid0)
             _cnt[0] += 1
@@ -354,6 +354,11 @@ def main():
         barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms = ms_total / reps            # per K steps
+    # a run that blew up (NaN positions freeze the particles: less work per substep) must not produce a number
+    fcur = sim.cur_substep_local
+    xs_, alive_ = sim.slab_positions(fcur)
+    if not bool(torch.isfinite(xs_[alive_]).all().item()):
+        raise RuntimeError(f'rank {rank}: non-finite particle positions after the timed region: the workload is unstable, the measurement is void')
     clocks = cs.summary()
     value = (1 if strong else world) * K * SUBSTEPS_PER_STEP / (ms * 1e-3)
 
@@ -596,25 +601,38 @@ def main():
     d2h = sim.n_particles * (12 + 12 + 4)
     gid0 = slab.gid.clone() if slab is not None else None
 
-    def episode():
+    def episode(pipelined):
         sim.cur_substep_global = 0
         sim.set_state(0, pin)                      # H2D of the episode's initial state (pinned host)
         if slab is not None:
             slab.gid.copy_(gid0)
-        out = None
+        out, pend = None, None
         for _ in range(EP):
-            step_fn()
-            out = sim.get_state_RL()               # D2H of x, v, used every step (FluidEnv._get_obs)
+            step_plain()
+            if pipelined:                          # D2H of x, v, used of EVERY step (FluidEnv._get_obs), consumed one step later: the copy overlaps the next step
+                nxt = sim.get_state_RL_async()
+                if pend is not None:
+                    out = pend.result()
+                pend = nxt
+            else:
+                out = sim.get_state_RL()           # the reference's blocking call sequence (MPM:683-696)
+        if pend is not None:
+            out = pend.result()
         return out
-    episode(); barrier()
-    t0 = time.perf_counter()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(n_ep):
-        episode()
-    b.record(); barrier()
-    e2e_ms = max_over_ranks(max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3))
-    e2e_val = (1 if strong else world) * n_ep * EP * SUBSTEPS_PER_STEP / (e2e_ms * 1e-3)
+
+    def time_episodes(pipelined):
+        episode(pipelined); barrier()
+        t0 = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_ep):
+            episode(pipelined)
+        b.record(); barrier()
+        ms_ = max_over_ranks(max(a.elapsed_time(b), (time.perf_counter() - t0) * 1e3))
+        return (1 if strong else world) * n_ep * EP * SUBSTEPS_PER_STEP / (ms_ * 1e-3)
+    step_plain = (lambda: slab.step()) if slab is not None else (lambda: sim.step(None))
+    e2e_blocking = time_episodes(False)
+    e2e_val = time_episodes(True)
 
     # the same episodes with the observation assembled on the device (MPMSimulator.get_obs_RL): FluidEnv._get_obs keeps
     # ~200 particles per body, so the per-step D2H shrinks from 28 B x N to a few KB.  Reported as an EXTRA key; `e2e` stays the full-state API.
@@ -656,7 +674,10 @@ def main():
                        'parallelism': parallelism},
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'api': 'MPMSimulator.set_state(pinned host)/step/get_state_RL, 10-step episodes'},
+                    'api': 'MPMSimulator.set_state(pinned host) / step / get_state_RL_async (x, v, used of every step read back on a copy stream and consumed one '
+                           'step later), 10-step episodes',
+                    'blocking_api_value': e2e_blocking,
+                    'blocking_api': 'the same with the reference\'s blocking get_state_RL after every step (MPM:683-696): the D2H is serialised with the steps'},
             'gpu_launches': K * ((2 * SUBSTEPS_PER_STEP + 1) if args.fuse_g2p2g else SUBSTEPS_PER_STEP * 3) + (2 * ((K + args.sort_every - 1) // args.sort_every) if args.sort_every else 0),   # p2g, grid_op, g2p per substep + k_sort_keys, k_reorder per cell sort (CUB's own kernels not counted)
             'e2e_obs_bridge': e2e_obs,
             'roofline': roof_fused if (roof_fused and 'frac' in roof_fused) else roof,

@@ -6,7 +6,7 @@ kernel each (fmpm_loss_chamfer / fmpm_loss_chamfer_grad)."""
 import pickle as pkl
 import numpy as np
 import torch
-from .macros import MILK
+from .macros import MILK, ICECREAM, ICECREAM1
 
 
 class Loss:
@@ -133,6 +133,38 @@ class LatteArtLoss(ShapeMatchingLoss):
         info = super().get_final_loss()
         info['reward'] = float(np.sum((121.3 - self.step_loss.cpu().numpy()) * 0.025))
         return info
+
+
+class _ScaledShapeLoss(ShapeMatchingLoss):
+    """ShapeMatchingLoss with a task's material, curriculum start and reward scaling (the reference repeats the class per task: the data differ, the
+    kernels do not).  `type='diff'`: the expanding temporal range used by the gradient-based solver; `'default'`: the whole horizon."""
+    MAT, INIT_END, OFFSET, SCALE, STEP_LOSS_SCALE = None, 50, 0.0, 1.0, 1.0
+
+    def __init__(self, type='diff', **kwargs):
+        if type == 'diff':
+            super().__init__(matching_mat=self.MAT, temporal_init_range_end=self.INIT_END, temporal_range_type='expand', **kwargs)
+        else:
+            assert type == 'default', type
+            super().__init__(matching_mat=self.MAT, temporal_range_type='all', **kwargs)
+
+    def get_step_loss(self):
+        cur = float(self.step_loss[self.sim.cur_step_global - 1].item())
+        return {'reward': self.SCALE * (self.OFFSET - cur), 'loss': self.STEP_LOSS_SCALE * cur}
+
+    def get_final_loss(self):
+        info = super().get_final_loss()
+        info['reward'] = float(np.sum((self.OFFSET - self.step_loss.cpu().numpy()) * self.SCALE))
+        return info
+
+
+class IceCreamDynamicLoss(_ScaledShapeLoss):
+    """losses/icecreamdynamic_loss.py:14-60: ICECREAM particles against the recorded target, range expanding from 200 steps, reward 0.001 (1700 - loss)"""
+    MAT, INIT_END, OFFSET, SCALE, STEP_LOSS_SCALE = ICECREAM, 200, 1700.0, 0.001, 0.001
+
+
+class IceCreamStaticLoss(_ScaledShapeLoss):
+    """losses/icecreamstatic_loss.py:13-55: ICECREAM1 particles, range expanding from 100 steps, reward 0.001 (900 - loss), the step loss unscaled"""
+    MAT, INIT_END, OFFSET, SCALE, STEP_LOSS_SCALE = ICECREAM1, 100, 900.0, 0.001, 1.0
 
 
 class CirculationLoss(Loss):

@@ -85,8 +85,9 @@ class MPMSimulator:
         self.store_grids = 'auto'          # grad mode: keep each ring frame's forward grid in HBM instead of recomputing it in the backward:
                                            # True (raise if the ring does not fit), False, or 'auto' (if it fits); the choice made is `grids_stored`
         self.grids_stored = None
-        self.fuse_g2p2g = False            # forward-only agent-free steps: inner g2p / p2g pairs fused (fmpm_substeps_fused).  Verified on the
-                                           # CPU execution-model shim, NOT yet measured on a B200: opt-in until it is
+        self.fuse_g2p2g = True             # forward-only steps: the gather of substep f and the scatter of f+1 in one kernel (fmpm_substeps_fused: k_fwd, or k_g2p2g
+                                           # with agents / MAT_RIGID bodies); measured on B200 in round 2 (profiles/README.md).  Frames strictly inside a step then
+                                           # hold x, used and F only (all-liquid scenes: x, used, F22); step boundaries are complete.  False: plain substeps
         if device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError('fluidlab_b200.MPMSimulator needs a CUDA device (B200, sm_100a); there is no CPU fallback')
@@ -558,8 +559,8 @@ class MPMSimulator:
     def setframe(self, f, x, v, Cm, F, used):
         """x,v,C,F,used: numpy arrays or torch tensors in original particle order (MPM:566-575)."""
         def dev(a, st, dt):
-            if torch.is_tensor(a):
-                st.copy_(a.reshape(st.shape)); return st
+            if torch.is_tensor(a):   # pinned host tensors: an asynchronous H2D copy on the compute stream (the host may refill them only after the frame was written)
+                st.copy_(a.reshape(st.shape), non_blocking=bool(a.device.type == 'cpu' and a.is_pinned())); return st
             return self._to_dev(a, st, dt)
         sx, sv, sC, sF = dev(x, self._sx, np.float32), dev(v, self._sv, np.float32), dev(Cm, self._sC, np.float32), dev(F, self._sF, np.float32)
         su = dev(used, self._sused, np.int32)
@@ -622,6 +623,60 @@ class MPMSimulator:
         if not self.has_particles:
             return np.zeros((0,), dtype=np.int32)
         return self.readframe(f, ('used',))['used']
+
+    # ---- pipelined state read-back: the same data as get_state_RL, without stalling the simulation
+    class _PendingState:
+        """result of get_state_RL_async: `.result()` blocks until the copies have landed and returns the dict get_state_RL would have returned (numpy
+        views of pinned host buffers, valid until the second-next get_state_RL_async call)"""
+        def __init__(self, event, host, extra):
+            self._event, self._host, self._extra = event, host, extra
+
+        def result(self):
+            self._event.synchronize()
+            out = {k: h.numpy() for k, h in self._host.items()}
+            out.update(self._extra)
+            return out
+
+    def get_state_RL_async(self):
+        """get_state_RL (MPM:683-696) as a pipeline stage: frame -> API-layout staging (one of two sets) on the compute stream, then the D2H copies
+        into pinned host buffers on a COPY stream, so the next `step()` runs while x, v, used (28 B per particle) cross PCIe.  Callers that
+        need the observation before choosing the next action (closed-loop RL) call `.result()` at once — that is get_state_RL; open-loop
+        consumers (trajectory optimisation, logging, rendering) call it one step later and never wait.  Ring frames are not rewritten for
+        max_substeps_local substeps, and a staging set is reused only after its previous copies have completed."""
+        assert self.has_particles
+        dev, N = self.device, self.n_particles
+        if dev.type != 'cuda':   # (the CPU execution-model shim of tests/: nothing is asynchronous there)
+            done = SimpleNamespace(synchronize=lambda: None)
+            r = self.get_state_RL()
+            return MPMSimulator._PendingState(done, {k: torch.from_numpy(r[k]) for k in ('x', 'v', 'used')}, {k: v for k, v in r.items() if k not in ('x', 'v', 'used')})
+        if not hasattr(self, '_rl_sets'):
+            f32, i32 = torch.float32, torch.int32
+            mk = lambda: dict(x=torch.empty((N, 3), dtype=f32, device=dev), v=torch.empty((N, 3), dtype=f32, device=dev), used=torch.empty((N,), dtype=i32, device=dev))
+            mh = lambda: dict(x=torch.empty((N, 3), dtype=f32, pin_memory=True), v=torch.empty((N, 3), dtype=f32, pin_memory=True), used=torch.empty((N,), dtype=i32, pin_memory=True))
+            self._rl_sets = [dict(dev=mk(), host=mh(), done=None) for _ in range(2)]
+            self._rl_next = 0
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        st = self._rl_sets[self._rl_next]; self._rl_next ^= 1
+        cur = torch.cuda.current_stream(dev)
+        if st['done'] is not None:
+            cur.wait_event(st['done'])           # the copies that last read this staging set have finished
+        f = self.cur_substep_local
+        d = st['dev']
+        self._ck(self._lib.fmpm_read_frame(self._h, f, d['x'].data_ptr(), d['v'].data_ptr(), None, None, d['used'].data_ptr(),
+                                           self._frame_ord[f].ids_ptr(), self._stream()), 'fmpm_read_frame')
+        ready = torch.cuda.Event(); ready.record(cur)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            for k in ('x', 'v', 'used'):
+                st['host'][k].copy_(d[k], non_blocking=True)
+            done = torch.cuda.Event(); done.record(self._copy_stream)
+        st['done'] = done
+        extra = {}
+        if self.agent is not None:
+            extra['agent'] = self.agent.get_state(f)
+        if self.smoke_field is not None:
+            extra['smoke_field'] = self.smoke_field.get_state(self.cur_step_local)
+        return MPMSimulator._PendingState(done, st['host'], extra)
 
     def get_state_RL(self):  # MPM:683-696
         f = self.cur_substep_local

@@ -208,12 +208,17 @@ class SlabMPMSimulator:
     """Forward MLS-MPM over x-slabs: one local `MPMSimulator` per rank + ghost exchange + migration."""
 
     def __init__(self, quality, gravity, particles, gid, bounds, capacity, boundary=None, max_substeps_local=50, device=None, group=None, halo=4,
-                 exchange='peer', migrate=True, sim_factory=None, peer_factory=None, sync='signal', sort_every=1, use_graphs=True):
+                 exchange='peer', migrate=True, sim_factory=None, peer_factory=None, sync='signal', sort_every=1, use_graphs=True, migrate_every=1):
         from .macros import NOWHERE
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
         self.migrate_enabled = bool(migrate)   # False: diagnostics only (particles must then stay inside their ghost range)
+        # census + migration period in steps.  A particle may sit up to (2 * migrate_every) steps of drift outside its slab (the census is read one
+        # period late): `halo` - 1 cells must cover that (|v_x| < (halo - 1) dx / (20 dt * 2 * migrate_every)); the census also counts particles
+        # that left the halo and the next step raises instead of computing with incomplete ghost sums.
+        self.migrate_every = max(1, int(migrate_every))
+        self.halo = int(halo)
         self.sort_every = int(sort_every)      # cell-sort period in steps (the kernels tolerate an aged sort; arrivals of a migration land in free slots)
         self.use_graphs = bool(use_graphs)     # sync='signal': the one-call step (fmpm_substeps_slab) is replayed as a CUDA graph per local step index
         self._graphs = {}
@@ -310,11 +315,12 @@ class SlabMPMSimulator:
         xs, alive = sim.slab_positions(f)
         cp = (xs * sim.inv_dx - 0.5).to(torch.int32) + 1
         out = torch.zeros((), dtype=torch.int64, device=xs.device)
+        lost = torch.zeros((), dtype=torch.int64, device=xs.device)   # particles whose stencil left the planes shared with the neighbour
         if self.rank > 0:
-            out = out + (alive & (cp < self.lo)).sum()
+            out = out + (alive & (cp < self.lo)).sum(); lost = lost + (alive & (cp < self.lo - (self.halo - 1))).sum()
         if self.rank < self.world - 1:
-            out = out + (alive & (cp >= self.hi)).sum()
-        out = out.reshape(1)
+            out = out + (alive & (cp >= self.hi)).sum(); lost = lost + (alive & (cp >= self.hi + (self.halo - 1))).sum()
+        out = (out + (lost << 40)).reshape(1)   # one word: leavers in the low 40 bits, halo violations above
         dist.all_reduce(out, group=self.group)
         if xs.device.type != 'cuda':   # host stand-in (tests): nothing is asynchronous
             self._census_host, self._census_event = out.clone(), _Done()
@@ -332,7 +338,11 @@ class SlabMPMSimulator:
         need = False
         if self._census_event is not None:
             self._census_event.synchronize()
-            need = int(self._census_host[0]) != 0
+            word = int(self._census_host[0])
+            if word >> 40:
+                raise RuntimeError(f'SlabMPMSimulator: {word >> 40} particle(s) drifted beyond the {self.halo}-plane halo between two migrations: raise `halo` or lower '
+                                   f'`migrate_every` (now {self.migrate_every})')
+            need = (word & ((1 << 40) - 1)) != 0
         if need:
             f = sim.cur_substep_local
             st = sim.readframe_torch(f)
@@ -388,7 +398,7 @@ class SlabMPMSimulator:
         sim = self.sim
         if sim.grad_enabled and sim.cur_substep_local == 0 and not self._replaying:
             self._checkpoint_chunk_start()
-        if self.world > 1 and self.migrate_enabled:
+        if self.world > 1 and self.migrate_enabled and (sim.cur_step_global % self.migrate_every == 0 or sim.grad_enabled):
             self._migrate()
         if self.sort_every > 0 and sim.cur_step_global % self.sort_every == 0:
             sim.sort_frame(sim.cur_substep_local)

@@ -88,3 +88,19 @@ def box_sdf(half, half_extent, res=32):
     s = (res - 1) / (2 * half_extent)
     T = np.eye(4); T[0, 0] = T[1, 1] = T[2, 2] = s; T[:3, 3] = s * half_extent
     return vox, T
+
+
+def cone_sdf(radius, height, half_extent, res=48):
+    """SDF volume of a solid cone (apex at +z = height / 2, base disc of `radius` at z = -height / 2, axis = mesh z), in the reference's baked
+    format — an analytic stand-in for assets/meshes/processed/cone_tip-128.sdf, which cannot travel to the GPU box (8 MB, not the repo's to ship)."""
+    ax = np.linspace(-half_extent, half_extent, res)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing='ij')
+    r = np.sqrt(X ** 2 + Y ** 2)
+    zt = Z + height / 2                     # height above the base
+    # distance to the slanted side (line from (radius, 0) to (0, height) in the (r, z) half plane), negative inside
+    nrm = np.array([height, radius]) / np.hypot(height, radius)
+    side = (r - radius) * nrm[0] + zt * nrm[1]
+    vox = np.maximum(side, -zt).astype(np.float32)   # intersection of the side's half space and z >= base
+    s = (res - 1) / (2 * half_extent)
+    T = np.eye(4); T[0, 0] = T[1, 1] = T[2, 2] = s; T[:3, 3] = s * half_extent
+    return vox, T

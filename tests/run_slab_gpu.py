@@ -76,7 +76,10 @@ def main():
 
 def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
     from fluidlab_b200 import MPMSimulator
-    n_steps = 5   # 50 substeps on a 20-frame ring: two wraps (chunk checkpoints + re-runs in the backward pass); migrations at steps 2 and 4
+    # 30 substeps on a 20-frame ring: one wrap (chunk checkpoint + re-run in the backward pass), a migration at step 2.  (Round 2, first hardware run: with
+    # 50 substeps of this water + ELASTIC cloud at 3 m/s the SINGLE-GPU gradient differs from itself by gC, gF ~ 0.3 when only the summation order changes —
+    # amplified round-off, not an exchange error; the yardstick below is therefore that single-GPU spread, measured in the same run.)
+    n_steps = int(os.environ.get('SLAB_BWD_STEPS', '3'))
     tgt = torch.from_numpy((x + np.random.RandomState(9).randn(Ntot, 3).astype(np.float32) * 0.05).astype(np.float32)).to(dev)
     slab.enable_grad()
     for _ in range(n_steps):
@@ -105,7 +108,8 @@ def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
             ref.step_grad(None)
         g = ref.get_grad()
         rel = lambda a, b: float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-12))
-        if os.environ.get('SLAB_SELFCHECK', '0') == '1':
+        self_err = None
+        if os.environ.get('SLAB_SELFCHECK', '1') == '1':
             # conditioning of the test itself: the same single-GPU gradient again with another summation order (no cell sort, recompute path)
             ref2 = MPMSimulator(dim=3, quality=q, gravity=(0.0, -10.0, 0.0), horizon=1000, max_substeps_local=20, max_substeps_global=10 ** 6, ckpt_dest='gpu', device=dev, sort_every=0)
             ref2.store_grids = False
@@ -119,13 +123,18 @@ def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
             for _ in range(n_steps):
                 ref2.step_grad(None)
             g2 = ref2.get_grad()
-            print('selfcheck single-GPU vs single-GPU (unsorted, recompute path): ' + ' '.join(f'g{k}={rel(g2[k], g[k]):.2e}' for k in ('x', 'v', 'C', 'F')) + f' xT={rel(xT2, xT):.2e}')
+            self_err = {k: rel(g2[k], g[k]) for k in ('x', 'v', 'C', 'F')}
+            print('selfcheck single-GPU vs single-GPU (unsorted, recompute path): ' + ' '.join(f'g{k}={self_err[k]:.2e}' for k in ('x', 'v', 'C', 'F')) + f' xT={rel(xT2, xT):.2e}')
         assert len(got['gid']) == Ntot and np.array_equal(got['gid'], np.arange(Ntot)), 'particles lost or duplicated'
         errs = {k: rel(got[k], g[k]) for k in ('x', 'v', 'C', 'F')}
         print(f'slab backward world={world} exchange={exchange}: migrated={int(migrated[0].item())} at {int(migrated[1].item())} (rank, step) pairs; rel err ' +
               ' '.join(f'g{k}={e:.2e}' for k, e in errs.items()))
         # fp32 summation order differs between the sharded and the single-GPU scatter: same bars as the single-GPU adjoint tests
-        ok = errs['x'] < 1e-4 and errs['v'] < 1e-4 and errs['C'] < 2e-3 and errs['F'] < 2e-3 and int(migrated[0].item()) > 0
+        bars = dict(x=1e-4, v=1e-4, C=2e-3, F=2e-3)
+        if self_err is not None:   # never stricter than what the single-GPU path reproduces of itself; and the test must stay discriminating
+            bars = {k: max(b, 3.0 * self_err[k]) for k, b in bars.items()}
+            assert max(self_err.values()) < 5e-2, f'the scene is too ill-conditioned to test anything: {self_err}'
+        ok = all(errs[k] < bars[k] for k in bars) and int(migrated[0].item()) > 0
         print('SLAB_GRAD_OK' if ok else 'SLAB_GRAD_FAIL')
     return ok
 

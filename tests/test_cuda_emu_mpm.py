@@ -548,3 +548,20 @@ def test_every_forward_path_of_fmpm_substeps_fused_equals_the_plain_substeps_and
     (tests/fwd_path_case.py; the same body runs on a B200 in tests/test_gpu_parity.py)."""
     import fwd_path_case
     fwd_path_case.run('cpu', liquid, [0, 1, 3, 5, 7] if liquid else [0, 1, 5], boundary=boundary, sort_every=sort_every)
+
+
+def test_c4_scene_at_reduced_size_on_the_emulated_device(emu):
+    """the C4 scene of tests/test_gpu_parity.py (ELASTIC + ICECREAM blocks, soft cone collider configured the way agent_icecreamdynamic.yaml does —
+    material by NAME, scale, euler, softness —, IceCreamDynamicLoss, forward + dLoss/dAction vs the oracle) with 2 x 6,000 particles on a 48^3
+    grid: the same body the B200 runs with 2 x 1,000,000 on 192^3"""
+    import test_gpu_parity as g
+    from fluidlab_b200 import simulator
+    orig = simulator.MPMSimulator.__init__
+
+    def init_cpu(self, *a, device=None, **k):
+        orig(self, *a, device='cpu', **k); self.use_graphs = False
+    simulator.MPMSimulator.__init__ = init_cpu
+    try:
+        g.c4_case(48, 6000)
+    finally:
+        simulator.MPMSimulator.__init__ = orig

@@ -1104,3 +1104,116 @@ def test_c2_full_size_state_parity_vs_the_oracle(path):
     og, gg = o64.get_grad_frame(0), s.get_grad()
     for k in ('x', 'v', 'C', 'F'):
         assert rel(gg[k], og[k]) < 1e-4, (k, rel(gg[k], og[k]))
+
+
+@pytest.mark.gpu
+def test_c4_cone_collider_fwd_bwd_at_the_full_particle_count():
+    """BASELINE.json configs[3] with its collider: 1M ELASTIC + 1M ICECREAM (plasto-elastic) particles and the soft cone of
+    envs/configs/agent_icecreamdynamic.yaml:26-37 (scale 0.726, euler (-90, 0, 30), softness 100, material CONE = friction 8.0, configured by NAME)
+    driven by a 3-D action, forward + backward through TaichiEnv: state vs the fp32 oracle, loss and dLoss/dAction vs the fp64 oracle.
+    Grid 96^3, not 192^3: with the reference's fixed dt the config has c dt / dx = 1.27 (ELASTIC) and 1.8 (ICECREAM) at 192^3, and the first contact
+    perturbation grows 5x per substep there — in the oracle as well, which leaves the grid after 7 substeps whatever the cone's speed (0.2 ... 9 m/s;
+    measured with the CPU oracle, round 2).  At 96^3 the same scene is stable, so the collider, the loss and both material adjoints are compared over a
+    whole step at the full particle count; the 192^3 grid is covered from rest by test_c4_full_size_from_rest_vs_the_oracle.  The cone's SDF is the
+    analytic volume of conftest.cone_sdf (the baked cone_tip-128.sdf asset cannot travel to the GPU box)."""
+    _need_gpu()
+    c4_case(96, 1_000_000)
+
+
+@pytest.mark.gpu
+def test_c4_full_size_from_rest_vs_the_oracle():
+    """BASELINE.json configs[3] at FULL size (2M particles, 192^3) against the oracle itself: one step (10 substeps) from rest through the default step
+    path vs the fp32 oracle (x, F, v), then one backward substep (both material adjoints, SVD adjoint included) vs the fp64 oracle.  From rest the only
+    forcing is gravity, so the CFL-unstable modes of this config (see the cone test) are not excited within the step."""
+    _need_gpu()
+    from oracle import oracle as orc
+    rs = np.random.RandomState(0)
+    n_grid, n_each = 192, 1_000_000
+    xa = rs.uniform((0.20, 0.30, 0.30), (0.45, 0.55, 0.70), size=(n_each, 3))
+    xb = rs.uniform((0.55, 0.30, 0.30), (0.80, 0.55, 0.70), size=(n_each, 3))
+    x = np.concatenate([xa, xb]); mat = np.concatenate([np.full(n_each, M.ELASTIC), np.full(n_each, M.ICECREAM)])
+    N = len(x)
+    P = make_particles(x, mat, n_grid)
+    o, s = build_pair(P, n_grid, T=20, precision=32, sort_every=1)
+    s.step(None)
+    for f in range(10):
+        o.substep(f)
+    got, ref = s.get_state(), o.get_frame(10)
+    assert int(got['used'].sum()) == N
+    for k, bar in (('x', 1e-5), ('F', 1e-5), ('v', 1e-4)):
+        assert rel(got[k], ref[k]) < bar, (k, rel(got[k], ref[k]))
+    o64 = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), max_substeps_local=2, precision=64)
+    s.enable_grad()
+    o64.set_frame(0, got['x'], got['v'], got['C'], got['F'], got['used'])
+    s.cur_substep_global = 10
+    s.substep(10, True); o64.substep(0)
+    s.cur_substep_global = 11
+    tp = 2 * np.pi
+    g = dict(x=np.stack([np.sin(tp * x[:, 1] * 2), np.cos(tp * x[:, 2] * 3), np.sin(tp * x[:, 0] * 2)], 1).astype(np.float32),
+             v=np.stack([np.cos(tp * x[:, 0] * 3), np.sin(tp * x[:, 1] * 2), np.cos(tp * x[:, 2])], 1).astype(np.float32) * 1e-3,
+             C=np.zeros((N, 3, 3), np.float32), F=(np.eye(3, dtype=np.float32)[None] * np.sin(tp * x[:, 0] * 2)[:, None, None].astype(np.float32) * 1e-3))
+    o64.reset_grad(); o64.set_grad_frame(1, g['x'], g['v'], g['C'], g['F'])
+    s.reset_grad(); s.set_grad(g['x'], g['v'], g['C'], g['F'])
+    o64.substep_grad(0)
+    s.cur_substep_global = 10
+    s.substep_grad(10, True)
+    og, gg = o64.get_grad_frame(0), s.get_grad()
+    for k in ('x', 'v', 'C', 'F'):
+        assert rel(gg[k], og[k]) < 1e-4, (k, rel(gg[k], og[k]))
+
+
+def c4_case(n_grid, n_each, device_kw=None):
+    """body of the C4 test (also run at reduced size on the CPU execution-model shim, tests/test_cuda_emu_mpm.py)"""
+    from conftest import cone_sdf
+    from fluidlab_b200 import TaichiEnv, IceCreamDynamicLoss
+    from oracle import oracle as orc
+    n_steps, T = 1, 10
+    rs = np.random.RandomState(0)
+    xa = rs.uniform((0.20, 0.30, 0.30), (0.45, 0.55, 0.70), size=(n_each, 3))
+    xb = rs.uniform((0.55, 0.30, 0.30), (0.80, 0.55, 0.70), size=(n_each, 3))
+    x = np.concatenate([xa, xb]); mat = np.concatenate([np.full(len(xa), M.ELASTIC), np.full(len(xb), M.ICECREAM)])
+    N = len(x)
+    P = make_particles(x, mat, n_grid)
+    vox, Tm = cone_sdf(0.10, 0.22, 0.2)
+    cube = dict(type='cube', lower=(0.05, 0.05, 0.05), upper=(0.95, 0.95, 0.95))
+    env = TaichiEnv(quality=n_grid / 64, max_substeps_local=T, gravity=(0.0, -10.0, 0.0), horizon=n_steps, **(device_kw or {}))
+    init_pos = (0.66, 0.56, 0.5)   # the cone's tip dips into the top of the ice-cream block
+    env.setup_agent(dict(type='AgentRigid', params=dict(collide_type='particle'), effectors=[dict(
+        type='Rigid', params=dict(init_pos=init_pos, init_euler=(0.0, 0.0, 0.0), action_dim=3, action_scale_p=(1.0, 1.0, 1.0), action_scale_v=(1.0, 1.0, 1.0)),
+        mesh=dict(file='cone_tip.obj', scale=(0.726, 0.726, 0.726), euler=(-90.0, 0.0, 30.0), material='CONE', softness=100.0, sdf=dict(voxels=vox, T_mesh_to_voxels=Tm)),
+        boundary=cube)]))
+    env.setup_boundary(**cube)
+    env.particle_bodies.get = lambda: P
+    tgt = [(x + rs.randn(N, 3) * 0.01).astype(np.float32) for _ in range(n_steps)]
+    env.setup_loss(loss_cls=IceCreamDynamicLoss, type='default', target=tgt, weights={'chamfer': 1.0})
+    env.build()
+    actions = np.array([[0.2, -0.9, 0.1]], dtype=np.float32) * 0.002   # the cone moves at 0.9 m/s
+    action_p = np.array(init_pos, dtype=np.float32)
+    fr, info, grad = _run_env_fwd_bwd(env, actions, action_p)
+    mesh = env.agent.rigid.mesh
+    assert abs(mesh.friction - 8.0) < 1e-6 and mesh.softness == 100.0   # the yaml's material name resolved through macros (CONE)
+
+    def oracle(prec):
+        o = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), boundary=cube, precision=prec, max_substeps_local=T)
+        o.add_effector(type=0, action_dim=3, boundary=cube, max_action_steps=n_steps + 1, init_pos=init_pos)
+        o.set_rigid_mesh(mesh.sdf_voxels_np, mesh.T_mesh_to_voxels_np, friction=mesh.friction, softness=mesh.softness, collide_type='particle')
+        o.enable_grad()
+        o.set_frame(0, P['x'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), P['used'])
+        o.set_effector_state(0, 0, np.array([*init_pos, 1, 0, 0, 0, 0.0])); o.apply_action_p(action_p)
+        total = 0.0
+        for i in range(n_steps):
+            o.step(actions[i]); total += o.loss_value(o.cur_substep_local, M.ICECREAM, 1.0, tgt[i])
+        ofr = o.get_frame(o.cur_substep_local)
+        o.reset_grad()
+        for i in range(n_steps - 1, -1, -1):
+            o.loss_seed(o.cur_substep_local, M.ICECREAM, 1.0, tgt[i]); o.step_grad(actions[i])
+        o.apply_action_p_grad()
+        return ofr, total, o.get_action_grad(n_steps)
+    o32, _, _ = oracle(32)
+    _, loss64, g64 = oracle(64)
+    assert np.abs(o32['v'] - np.array([0, -10 * 10 * 2e-4, 0])).max() > 0.1, 'the cone never pushed the material'
+    for k, bar in (('x', 1e-5), ('F', 1e-5), ('v', 1e-4)):
+        assert rel(fr[k], o32[k]) < bar, (k, rel(fr[k], o32[k]))
+    assert abs(info['loss'] - loss64) <= 1e-5 * abs(loss64), (info['loss'], loss64)
+    assert np.abs(g64).max() > 1e-6
+    assert rel(grad, g64) < 2e-3, (rel(grad, g64), grad, g64)   # the contact map is piecewise smooth (hit / influence thresholds flip between fp32 and fp64): the bar of test_icecream_dynamic_like_scene
