@@ -313,10 +313,13 @@ def main():
         if slab.exchange == 'peer':
             sync_txt = ('one neighbour handshake per substep inside the library, the whole step in one call' if slab.sync == 'signal'
                         else 'one device-side signal-pad barrier per substep')
-            parallelism = (f'{world} x-slabs; ghost-plane reduction fused into p2g (vector REDs into the neighbour grid over NVLink peer memory, '
-                           f'parity double-buffered), {sync_txt}, no data-path collective; per-step migration')
+            ghost_txt = ('ghost-plane reduction PULLED by grid_op (it adds the neighbours\' partial sums of the 2 x halo ghost planes, read over NVLink peer memory after the '
+                         'handshake; the scatter stays local; ghost blocks cleared one handshake later)' if slab.pull else
+                         'ghost-plane reduction fused into p2g (vector REDs into the neighbour grid over NVLink peer memory)')
+            parallelism = (f'{world} x-slabs, halo {slab.halo}; {ghost_txt}, accumulators double-buffered by substep parity, {sync_txt}, no data-path collective; '
+                           f'census + migration every {slab.migrate_every} step(s)')
         else:
-            parallelism = (f'{world} x-slabs; NCCL pair all-reduce of {slab.ghost.bytes_per_exchange()} B of ghost planes per rank per substep; per-step migration')
+            parallelism = (f'{world} x-slabs; NCCL pair all-reduce of {slab.ghost.bytes_per_exchange()} B of ghost planes per rank per substep; census + migration every {slab.migrate_every} step(s)')
     init = sim.get_state()
     if slab is None:
         _init1[0] = {k: v.clone() for k, v in sim.readframe_torch(0).items()}

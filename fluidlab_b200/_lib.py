@@ -129,6 +129,7 @@ _PROTOS = {
     "fmpm_set_slab": (_I, [vp, C.POINTER(FmpmSlab)]),
     "fmpm_slab_sync": (_I, [vp, vp]),
     "fmpm_substeps_slab": (_I, [vp, _I, _I, _I, vp]),
+    "fmpm_set_slab_pull": (_I, [vp, _I]),
     "fmpm_create": (_I, [C.POINTER(FmpmConfig), C.POINTER(vp)]),
     "fmpm_destroy": (None, [vp]),
     "fmpm_bind": (_I, [vp, C.POINTER(FmpmBuffers)]),

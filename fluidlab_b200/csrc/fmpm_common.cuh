@@ -39,6 +39,8 @@ struct FmpmHandle {
   int fwd_mask;   // fmpm_set_fwd_mask
   int fwd_stride; // 1: no CTA -> slot-block permutation in the lazy-grid_op k_fwd (FMPM_FWD_STRIDE=1)
   int use_pdl;    // programmatic dependent launch of the forward chain (FMPM_PDL=0 switches it off)
+  int slab_pull_ok;   // x-slab forward steps: grid_op reads the neighbours' ghost planes instead of p2g pushing them (FMPM_SLAB_PULL=0: push form)
+  int slab_pull;      // set by fmpm_substeps_slab around its launches: the scatter kernels stay local, grid_op is k_grid_op_pull
 };
 
 int fmpm_advect_rigid_impl(FmpmHandle* h, int f, void* stream);  // fmpm_rigid.cu; no-op without MAT_RIGID bodies

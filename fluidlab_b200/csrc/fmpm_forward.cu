@@ -160,6 +160,27 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_MINB) k_p2g(const KParams 
 // =============================================================================================
 // MPM:380-398 on the active blocks; optionally clears the (momentum, mass) accumulators for the next substep
 // and zeroes the v_out adjoint of the same blocks (backward pass).
+// v_out of one node from its (momentum, mass) sum: MPM:380-398 with SDF colliders and the agent's grid-level collision
+__device__ __forceinline__ float4 grid_op_node_full(const KParams& P, const int f, const int i, const int j, const int k, const float4 pm) {
+  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pm.w > FMPM_EPS) {
+    const float inv_m = 1.f / pm.w;
+    float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
+    const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
+    for (int si = 0; si < P.col.n_statics; si++) {  // statics[i].collide, MPM:388-390
+      float o[3]; sdf_collide<false>(P.col.statics[si], false, nullptr, nullptr, nullptr, nullptr, P.dt, pos, v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
+      v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
+    }
+    if (P.col.has_rigid && P.col.collide_type >= 1) {  // agent.collide at grid level, MPM:393-395
+      float o[3]; agent_collide<false>(P, f, pos, v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
+      v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
+    }
+    float fac[3];
+    boundary_v(P, pos, v, fac);
+    out = make_float4(v[0], v[1], v[2], 0.f);
+  }
+  return out;
+}
 __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, const int clear_pm, const int zero_ggv, const int reset_flags) {
   const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
   // this CTA owns blocks blockIdx.x + q*gridDim.x; their flags are fetched in parallel (thread q reads flag q) and the CTA
@@ -187,28 +208,82 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, c
       const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
       const int g = (i * n + j) * n + k;
       const float4 pm = P.grid_pm[g];
-      float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pm.w > FMPM_EPS) {
-        const float inv_m = 1.f / pm.w;
-        float v[3] = {inv_m * pm.x + P.dt * P.gx, inv_m * pm.y + P.dt * P.gy, inv_m * pm.z + P.dt * P.gz};
-        const float pos[3] = {(float)i * P.dx, (float)j * P.dx, (float)k * P.dx};
-        for (int si = 0; si < P.col.n_statics; si++) {  // statics[i].collide, MPM:388-390
-          float o[3]; sdf_collide<false>(P.col.statics[si], false, nullptr, nullptr, nullptr, nullptr, P.dt, pos, v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
-          v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
-        }
-        if (P.col.has_rigid && P.col.collide_type >= 1) {  // agent.collide at grid level, MPM:393-395
-          float o[3]; agent_collide<false>(P, f, pos, v, o, nullptr, nullptr, nullptr, nullptr, nullptr);
-          v[0] = o[0]; v[1] = o[1]; v[2] = o[2];
-        }
-        float fac[3];
-        boundary_v(P, pos, v, fac);
-        out = make_float4(v[0], v[1], v[2], 0.f);
-      }
-      P.grid_v[g] = out;
+      P.grid_v[g] = grid_op_node_full(P, f, i, j, k, pm);
       if (clear_pm && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f)) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (zero_ggv) P.ggrid_v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (reset_flags && threadIdx.x == 0) P.blk_flags[blk] = 0;
+  }
+}
+
+// ---- x-slab forward steps, PULL form of the ghost reduction (fmpm_substeps_slab) -------------------------------------------------------------
+// The push form (k_p2g / k_fwd with kSlab: every vector reduction on a ghost plane issued a second time into the neighbour's accumulator over
+// NVLink) doubles the scatter's reductions on 2 * halo planes per slab boundary — two thirds of ALL reductions for the 24-plane slabs of the
+// 8-GPU bench (round 2: 29.2 k substeps/s with halo 4 against 35.2 k with halo 2).  Here the scatter stays local (kSlab = false) and grid_op,
+// which already runs after the neighbour handshake, READS the neighbour's partial sums of the ghost planes over NVLink: 2 * halo planes of
+// active nodes x 16 B per boundary and substep instead.  own + peer is one commutative addition, so both ranks compute bit-identical ghost
+// nodes.  Clearing: the neighbour reads this rank's ghost planes during ITS grid_op(f), so blocks that hold ghost planes (and their flags)
+// are left as they are and cleared one handshake later — by grid_op(f+1), on the other parity buffer (`Po`) — when the neighbour's
+// grid_op(f) is known to be complete; fmpm_substeps_slab ends with one more handshake and a k_clear_blocks of the last parity.
+__device__ __forceinline__ float4 ld_peer_v4(const float4* p) {
+#ifdef FMPM_HOST_EMU
+  return *p;
+#else
+  float4 v;   // never through L1: the line may be there from the previous substep
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ int ld_peer_flag(const int* p) { return *(const volatile int*)p; }
+__global__ void __launch_bounds__(256) k_grid_op_pull(const KParams P, const int f, float4* __restrict__ pm_other, int* __restrict__ flags_other) {
+  const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
+  __shared__ int s_act[256];
+  __shared__ int s_clr[256];
+  __shared__ int s_n, s_nc;
+  if (threadIdx.x == 0) { s_n = 0; s_nc = 0; }
+  __syncthreads();
+  {
+    const int blk = blockIdx.x + threadIdx.x * gridDim.x;
+    if (blk < nblk) {
+      const int x0 = (blk / (nb * nb)) * 8;
+      int act = P.blk_flags[blk];
+      if (P.peer_fl != nullptr && x0 < P.gl_hi && x0 + 8 > P.gl_lo) act |= ld_peer_flag(P.peer_fl + blk);
+      if (P.peer_fr != nullptr && x0 < P.gr_hi && x0 + 8 > P.gr_lo) act |= ld_peer_flag(P.peer_fr + blk);
+      if (act != 0) s_act[atomicAdd(&s_n, 1)] = blk;
+      if (flags_other[blk] != 0) s_clr[atomicAdd(&s_nc, 1)] = blk;   // ghost blocks of the previous substep: every neighbour has read them by now
+    }
+  }
+  __syncthreads();
+  const int n_act = s_n, n_clr = s_nc;
+  for (int ai = 0; ai < n_act; ai++) {
+    const int blk = s_act[ai];
+    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+    const int x0 = bx * 8;
+    const bool gl = P.peer_l != nullptr && x0 < P.gl_hi && x0 + 8 > P.gl_lo, gr = P.peer_r != nullptr && x0 < P.gr_hi && x0 + 8 > P.gr_lo;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int t = threadIdx.x + r * 256;
+      const int i = x0 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+      const int g = (i * n + j) * n + k;
+      float4 pm = P.grid_pm[g];
+      const bool clr = !(gl || gr) && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f);
+      if (gl && i >= P.gl_lo && i < P.gl_hi) { const float4 q = ld_peer_v4(P.peer_l + g); pm.x += q.x; pm.y += q.y; pm.z += q.z; pm.w += q.w; }
+      if (gr && i >= P.gr_lo && i < P.gr_hi) { const float4 q = ld_peer_v4(P.peer_r + g); pm.x += q.x; pm.y += q.y; pm.z += q.z; pm.w += q.w; }
+      P.grid_v[g] = grid_op_node_full(P, f, i, j, k, pm);
+      if (clr) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (!(gl || gr) && threadIdx.x == 0) P.blk_flags[blk] = 0;
+  }
+  for (int ci = 0; ci < n_clr; ci++) {
+    const int blk = s_clr[ci];
+    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int t = threadIdx.x + r * 256;
+      const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+      pm_other[(i * n + j) * n + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (threadIdx.x == 0) flags_other[blk] = 0;
   }
 }
 
@@ -796,7 +871,7 @@ int fmpm_p2g_impl(FmpmHandle* h, int f, int write_F, int ring_slot, void* stream
   const long long warps = ((long long)P.N + 32 * P2G_ROUNDS - 1) / (32 * P2G_ROUNDS);
   const int blocks = (int)((warps + P2G_WARPS - 1) / P2G_WARPS);
   const bool pdl = h->use_pdl != 0;
-  if (h->slab.enabled) { if (write_F) FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, true, true), blocks, P2G_WARPS * 32, 0, stream, P, f); else FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, false, true), blocks, P2G_WARPS * 32, 0, stream, P, f); }
+  if (h->slab.enabled && !h->slab_pull) { if (write_F) FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, true, true), blocks, P2G_WARPS * 32, 0, stream, P, f); else FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, false, true), blocks, P2G_WARPS * 32, 0, stream, P, f); }
   else { if (write_F) FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, true, false), blocks, P2G_WARPS * 32, 0, stream, P, f); else FMPM_LAUNCH_PDL(pdl, G2P2G_K2(k_p2g, false, false), blocks, P2G_WARPS * 32, 0, stream, P, f); }
   FMPM_CHECK_LAUNCH(h, "fmpm_p2g");
   return 0;
@@ -813,6 +888,12 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring
   if ((nblk + grid - 1) / grid > 256) grid = (nblk + 255) / 256;  // keep <= 256 blocks per CTA (parallel flag fetch)
   // the flags are consumed (reset) here only when nothing later in the substep needs them: plain forward substeps
   const int reset_flags = (clear_pm && ring_slot < 0) ? 1 : 0;
+  if (h->slab_pull) {   // fmpm_substeps_slab, pull form: ghost planes read from the neighbours, the other parity's ghost blocks cleared
+    const KParams Po = make_kparams(h, -1, f + 1);
+    FMPM_LAUNCH(k_grid_op_pull, grid, 256, 0, stream, P, f, Po.grid_pm, Po.blk_flags);
+    FMPM_CHECK_LAUNCH(h, "fmpm_grid_op(pull)");
+    return 0;
+  }
   FMPM_LAUNCH_PDL(h->use_pdl != 0, k_grid_op, grid, 256, 0, stream, P, f, clear_pm, zero_ggv, reset_flags);
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op");
   return 0;
@@ -982,7 +1063,7 @@ static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream, in
     for (int k = 0; k < 5 && stride == 1; k++) if (blocks > primes[k] && blocks % primes[k] != 0 && (long long)blocks * primes[k] < (1LL << 32)) stride = primes[k];
   }
   const int tag_off = f - tag_f0;
-  const bool slab = h->slab.enabled != 0;   // (never together with the inlined grid_op, see fwd_path)
+  const bool slab = h->slab.enabled != 0 && !h->slab_pull;   // (never together with the inlined grid_op, see fwd_path; pull form: local scatter)
   const int use_tma = (h->tma_ok && (path & FWD_TMA) && !inl) ? 1 : 0;
 #define FWD_GO(a, b, c) FMPM_LAUNCH_PDL(h->use_pdl != 0, FWD_K(a, b, c), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full, pms, tag_off, stride, h->tm_gv8, h->tm_gv16, use_tma)
   if (liq) { if (inl) FWD_GO(1, true, false); else if (slab) FWD_GO(1, false, true); else FWD_GO(1, false, false); }
@@ -999,7 +1080,7 @@ int fmpm_fwd_step_impl(FmpmHandle* h, int f, int full, void* stream) {
   return fmpm_g2p2g(h, f, 0, stream);
 }
 extern "C" int fmpm_fwd_step(FmpmHandle* h, int f, int full, void* stream) { return fmpm_fwd_step_impl(h, f, full, stream); }
-static int clear_blocks_launch(FmpmHandle* h, const KParams& P, void* stream) {
+int fmpm_clear_blocks_launch(FmpmHandle* h, const KParams& P, void* stream) {
   const int nblk = P.nb * P.nb * P.nb;
   const int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
   FMPM_LAUNCH(k_clear_blocks, grid, 256, 0, stream, P);
@@ -1021,7 +1102,7 @@ extern "C" int fmpm_substeps_fused(FmpmHandle* h, int f0, int n, void* stream) {
       if (fwd_launch(h, f0 + i, path, i + 2 == n, stream, f0)) return 1;
     const int fl = f0 + n - 1;
     if (fmpm_grid_op_impl(h, fl, 1, 0, -2 - (fl % 3), stream)) return 1;        // consumes and clears the accumulator of the last frame
-    if (n >= 2 && clear_blocks_launch(h, make_kparams(h, -2 - ((fl + 2) % 3)), stream)) return 1;   // the one the last k_fwd gathered from
+    if (n >= 2 && fmpm_clear_blocks_launch(h, make_kparams(h, -2 - ((fl + 2) % 3)), stream)) return 1;   // the one the last k_fwd gathered from
     return fmpm_g2p(h, fl, stream);
   }
   if (fmpm_p2g(h, f0, 1, stream)) return 1;

@@ -18,6 +18,7 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
   h->cfg = *cfg; h->bound = false; h->err[0] = 0; h->sm_count = 148; h->fwd_mask = ~4;   // the lazy in-kernel grid_op (bit 2) is opt-in: measured slower than the separate k_grid_op launch (r02h: 119.6 vs 106.0 us per substep)
   { const char* e = getenv("FMPM_FWD_STRIDE"); h->fwd_stride = (e && e[0] == '1' && e[1] == 0) ? 1 : 0; }
   { const char* e = getenv("FMPM_PDL"); h->use_pdl = (e && e[0] == '0') ? 0 : 1; }
+  h->slab_pull_ok = 0; h->slab_pull = 0;   // fmpm_set_slab_pull
   memset(&h->buf, 0, sizeof(h->buf));
   memset(&h->col, 0, sizeof(h->col));
   memset(&h->slab, 0, sizeof(h->slab));
@@ -118,17 +119,36 @@ int fmpm_slab_sync_impl(FmpmHandle* h, void* stream) {
   return 0;
 }
 int fmpm_fwd_step_impl(FmpmHandle* h, int f, int full, void* stream);   // fmpm_forward.cu: k_fwd (or k_g2p2g) with everything the scene allows
+int fmpm_clear_blocks_launch(FmpmHandle* h, const KParams& P, void* stream);   // fmpm_forward.cu
+// pull form of the ghost reduction (k_grid_op_pull, fmpm_forward.cu) when every neighbour's accumulator and flags are peer-addressable and the
+// two ghost ranges of this slab do not overlap; otherwise the push form (kSlab scatter kernels)
+extern "C" int fmpm_set_slab_pull(FmpmHandle* h, int on) { if (!h) return 1; h->slab_pull_ok = on ? 1 : 0; return 0; }
+static bool slab_can_pull(const FmpmHandle* h) {
+  const FmpmSlab& s = h->slab;
+  if (!h->slab_pull_ok || !s.enabled) return false;
+  if (!s.peer_pm_left && !s.peer_pm_right) return false;
+  if ((s.peer_pm_left && !s.peer_flags_left) || (s.peer_pm_right && !s.peer_flags_right)) return false;
+  if (s.peer_pm_left && s.peer_pm_right && s.left_hi > s.right_lo) return false;
+  return true;
+}
 extern "C" int fmpm_substeps_slab(FmpmHandle* h, int f0, int n, int fuse, void* stream) {
   if (!h) return 1;
   if (n < 1) { snprintf(h->err, sizeof(h->err), "fmpm_substeps_slab: n must be >= 1"); return 1; }
-  for (int i = 0; i < n; i++) {
+  h->slab_pull = slab_can_pull(h) ? 1 : 0;
+  int rc = 0;
+  for (int i = 0; i < n && !rc; i++) {
     const int f = f0 + i;
-    if (!(fuse && i > 0) && fmpm_p2g(h, f, 1, stream)) return 1;    // fused: the previous substep's g2p2g scattered frame f already
-    if (fmpm_slab_sync(h, stream) || fmpm_grid_op(h, f, 1, stream)) return 1;
-    if (fuse && i + 1 < n) { if (fmpm_fwd_step_impl(h, f, i + 2 == n, stream)) return 1; }   // the last fused substep completes F[f+2] (all-liquid scenes)
-    else if (fmpm_g2p(h, f, stream)) return 1;
+    if (!(fuse && i > 0)) rc = fmpm_p2g(h, f, 1, stream);    // fused: the previous substep's g2p2g scattered frame f already
+    if (!rc) rc = fmpm_slab_sync(h, stream) || fmpm_grid_op(h, f, 1, stream);
+    if (rc) break;
+    if (fuse && i + 1 < n) rc = fmpm_fwd_step_impl(h, f, i + 2 == n, stream);   // the last fused substep completes F[f+2] (all-liquid scenes)
+    else rc = fmpm_g2p(h, f, stream);
   }
-  return 0;
+  if (!rc && h->slab_pull) {   // the ghost blocks of the last substep: cleared once the neighbours are known to have read them
+    rc = fmpm_slab_sync(h, stream) || fmpm_clear_blocks_launch(h, make_kparams(h, -1, f0 + n - 1), stream);
+  }
+  h->slab_pull = 0;
+  return rc ? 1 : 0;
 }
 
 static int sort_bits(const FmpmHandle* h) {

@@ -255,6 +255,7 @@ class SlabMPMSimulator:
         #            (round 1's measured path: 59 % weak-scaling efficiency at 8 GPUs).
         assert sync in ('barrier', 'signal')
         self.sync = sync if exchange == 'peer' else 'barrier'
+        self.pull = False
         if self.exchange == 'peer':
             self._setup_peer(halo)
         self._census_host = None
@@ -304,6 +305,13 @@ class SlabMPMSimulator:
             slab.peer_signal_right = int(sptrs[self.rank + 1])
             slab.right_lo, slab.right_hi = hi - halo, hi + halo
         sim._ck(sim._lib.fmpm_set_slab(sim._h, C.byref(slab)), 'fmpm_set_slab')
+        # forward steps of the one-call path: PULL form of the ghost reduction (grid_op reads the neighbours' partial sums of the ghost planes; the
+        # scatter kernels stay local) — decided from the bounds every rank knows, so all ranks take the same form: no slab narrower than its two
+        # ghost ranges.  FMPM_SLAB_PULL=0: the push form (every ghost-plane reduction issued a second time over NVLink).
+        import os
+        widths = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
+        self.pull = bool(self.sync == 'signal' and min(widths) >= 2 * halo and os.environ.get('FMPM_SLAB_PULL', '1') != '0')
+        sim._ck(sim._lib.fmpm_set_slab_pull(sim._h, int(self.pull)), 'fmpm_set_slab_pull')
         if sim.device.type == 'cuda':
             torch.cuda.synchronize(sim.device)
         dist.barrier(group=self.group)

@@ -168,6 +168,12 @@ int  fmpm_slab_sync(FmpmHandle* h, void* stream);     /* one tiny kernel: post e
 /* the forward substeps f0..f0+n-1 of one x-slab rank in ONE call (no host round trip per phase; CUDA-graph capturable): per substep
  * p2g (or, with fuse != 0, the previous substep's g2p2g) -> fmpm_slab_sync -> grid_op -> g2p / g2p2g.  Needs the handshake arrays. */
 int  fmpm_substeps_slab(FmpmHandle* h, int f0, int n, int fuse, void* stream);
+/* on != 0: fmpm_substeps_slab uses the PULL form of the ghost reduction — the scatter kernels reduce into this rank's accumulator only and
+ * grid_op, after the handshake, adds the neighbours' partial sums of the ghost planes read over NVLink (2 * halo planes of active nodes per
+ * boundary instead of a second vector reduction for every scatter on those planes); the ghost blocks are cleared one handshake later, and the
+ * call ends with one more handshake.  Needs peer_pm_* and peer_flags_*, disjoint ghost ranges, and the SAME setting on every rank (the ranks
+ * handshake n + 1 times per call instead of n).  Default off (push form); the phase-level entry points always use the push form. */
+int  fmpm_set_slab_pull(FmpmHandle* h, int on);
 
 /* MAT_RIGID bodies: rigidity enforcement by shape matching (MPM:177-201 body structs, MPM:428-505 advect).
  * The body id of a particle travels in bits 16..23 of its meta word: pass mrow[p] = material_row | (body_id << 8) to

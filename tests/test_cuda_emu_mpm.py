@@ -125,7 +125,7 @@ class ShmPeers:
         self.dist.barrier(group=self.group)
 
 
-def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='barrier'):
+def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='barrier', pull=True):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     torch.set_num_threads(1)
@@ -134,22 +134,25 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='bar
         harness.enable()
         from fluidlab_b200 import MPMSimulator, macros as M
         from fluidlab_b200.slab import SlabMPMSimulator, slab_bounds, centre_plane
+        os.environ['FMPM_SLAB_PULL'] = '1' if pull else '0'
         rng = np.random.RandomState(21)
-        n, Ntot, n_steps = 32, 700, 5
-        x = rng.uniform((0.32, 0.36, 0.36), (0.68, 0.54, 0.64), size=(Ntot, 3)).astype(np.float32)
+        n, Ntot, n_steps = 16 * world, 700, 5          # two ranks: 32^3; three ranks (a middle slab with two neighbours): 48^3
+        quality = n / 64
+        x = rng.uniform((0.32, 0.36, 0.36) if world == 2 else (0.22, 0.36, 0.36), (0.68, 0.54, 0.64) if world == 2 else (0.78, 0.54, 0.64), size=(Ntot, 3)).astype(np.float32)
         v0 = np.where(x[:, 1:2] < 0.45, np.array([[6.0, 0.0, 0.5]]), np.array([[-6.0, 0.3, 0.0]])).astype(np.float32) + (rng.randn(Ntot, 3) * 0.2).astype(np.float32)
         mat = np.where(x[:, 2] < 0.5, M.WATER, M.ELASTIC).astype(np.int32)
         F0 = (np.eye(3)[None] + rng.randn(Ntot, 3, 3) * 0.04).astype(np.float32)
         tgt = torch.from_numpy((x + rng.randn(Ntot, 3) * 0.05).astype(np.float32))
-        bounds = slab_bounds(0, 32, world)
+        bounds = slab_bounds(0, n, world)
         cp = centre_plane(torch.from_numpy(x), float(n)).numpy()
         mine = np.where((cp >= bounds[rank]) & (cp < bounds[rank + 1]))[0]
 
         def parts(idx):
             return dict(x=x[idx], mat=mat[idx], used=np.ones(len(idx), np.int32), rho=np.array([M.RHO[m] for m in mat[idx]]), body_id=np.zeros(len(idx), np.int32), bodies={'n': 1})
-        slab = SlabMPMSimulator(0.5, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=len(mine) + 300, max_substeps_local=20, device='cpu', halo=4,
+        slab = SlabMPMSimulator(quality, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=len(mine) + 300, max_substeps_local=20, device='cpu', halo=4,
                                 exchange=exchange, peer_factory=ShmPeers, sync=sync)
         assert slab.exchange == exchange and (slab.sync == sync or exchange != 'peer')
+        assert slab.pull == (exchange == 'peer' and sync == 'signal' and pull)   # pull form of the ghost reduction: the one-call forward steps
         slab.sim.use_graphs = False
         st = slab.sim.get_state()
         st['v'][:len(mine)] = v0[mine]; st['F'][:len(mine)] = F0[mine]
@@ -160,8 +163,11 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='bar
                 slab.step()
             out = dict(fwd=slab.gather_state(), migrated=slab.n_migrated)
             assert not slab.sync_error()
+            if exchange == 'peer':   # both parity accumulators and their block flags are clean between steps, ghost blocks included (pull form: deferred clears)
+                dist.barrier()
+                assert float(slab.sim._grid_pm.abs().max()) == 0.0 and int(slab.sim._blk_flags.abs().max()) == 0
             if rank == 0:
-                ref = MPMSimulator(dim=3, quality=0.5, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+                ref = MPMSimulator(dim=3, quality=quality, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
                 ref.use_graphs = False
                 ref.build(None, None, [], parts(np.arange(Ntot)))
                 s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
@@ -185,7 +191,7 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='bar
         assert not slab.sync_error()
         out = dict(fwd=fwd, grad=grad, migrated=slab.n_migrated, rec=sorted(slab._records))
         if rank == 0:   # the single-domain reference: the same product on the same emulated device
-            ref = MPMSimulator(dim=3, quality=0.5, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+            ref = MPMSimulator(dim=3, quality=quality, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
             ref.use_graphs = False
             ref.build(None, None, [], parts(np.arange(Ntot)))
             s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
@@ -335,21 +341,24 @@ def test_circulation_stack_equals_a_run_of_the_real_reference_stack(emu):
     run_reference_stack_case(device='cpu')
 
 
-@pytest.mark.parametrize('exchange', ['peer', 'nccl', 'peer-signal'])
+@pytest.mark.parametrize('exchange', ['peer', 'nccl', 'peer-signal', 'peer-signal-push', 'peer-signal-3ranks', 'peer-signal-push-3ranks'])
 def test_slab_forward_with_g2p2g_fusion_on_the_emulated_device(exchange):
-    """x-slabs + g2p2g: the fused kernel's scatter half reduces the ghost planes of frame f+1 into the neighbour's accumulator (peer) or the
-    all-reduce follows it (nccl); 5 steps with migrations and two ring wraps against the single-domain (unfused) product"""
+    """x-slabs + the fused forward kernel: 5 steps with migrations and two ring wraps against the single-domain (unfused) product.
+    peer / peer-signal-push: the scatter half reduces the ghost planes of frame f+1 into the neighbour's accumulator (push form); nccl: the
+    all-reduce follows it; peer-signal: the one-call step with the PULL form (local scatter, grid_op adds the neighbours' ghost planes, deferred
+    ghost clears, n + 1 handshakes); -3ranks: a middle slab with two neighbours"""
     import torch.multiprocessing as mp
     mgr = mp.Manager(); ret = mgr.dict()
-    sync = 'signal' if exchange.endswith('-signal') else 'barrier'   # 'signal': the whole step is ONE library call (fmpm_substeps_slab)
-    mp.spawn(_slab_worker, args=(2, _free_port(), ret, exchange.split('-')[0], True, sync), nprocs=2, join=True)
+    sync = 'signal' if '-signal' in exchange else 'barrier'   # 'signal': the whole step is ONE library call (fmpm_substeps_slab)
+    world = 3 if exchange.endswith('3ranks') else 2
+    mp.spawn(_slab_worker, args=(world, _free_port(), ret, exchange.split('-')[0], True, sync, '-push' not in exchange), nprocs=world, join=True)
     out = dict(ret)
     ref_s = out[0]['ref_state']
-    for r in (0, 1):
+    for r in range(world):
         fwd = out[r]['fwd']
         assert np.array_equal(fwd['gid'], np.arange(700)), 'particles lost or duplicated'
         assert rel(fwd['x'], ref_s['x']) < 1e-5 and rel(fwd['F'], ref_s['F']) < 1e-5 and rel(fwd['v'], ref_s['v']) < 1e-4
-    assert out[0]['migrated'] > 0 and out[1]['migrated'] > 0
+    assert all(out[r]['migrated'] > 0 for r in range(world))
 
 
 @pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream', 'latteart_fused'])

