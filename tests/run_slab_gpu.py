@@ -30,6 +30,9 @@ def main():
     x = rng.uniform((0.2, 0.3, 0.3), (0.8, 0.5, 0.7), size=(Ntot, 3)).astype(np.float32)
     v0 = np.tile(np.array([3.0, 0.0, 0.5], dtype=np.float32), (Ntot, 1))  # 3 m/s along x: ~0.4 cells per step -> migration
     mat = np.where(x[:, 2] < 0.5, M.WATER, M.ELASTIC).astype(np.int32)
+    # F0 away from the identity: at F = I the SVD adjoint of the ELASTIC half is degenerate (equal singular values) and the backward test below would
+    # measure amplified round-off (round 2, hardware: single-GPU gC / gF differ by 0.25 from THEMSELVES when only the summation order changes)
+    F0 = (np.eye(3)[None] + rng.randn(Ntot, 3, 3) * (0.04 if os.environ.get('SLAB_MODE', 'forward') == 'backward' else 0.0)).astype(np.float32)
     bounds = slab_bounds(0, 64, world) if world > 2 else slab_bounds(8, 56, world)
     cp = centre_plane(torch.from_numpy(x), float(n)).numpy()
     lo = bounds[rank] if rank > 0 else -10 ** 6
@@ -43,10 +46,10 @@ def main():
                             exchange=exchange, sync=os.environ.get('SLAB_SYNC', 'barrier'))
     slab.sim.fuse_g2p2g = bool(int(os.environ.get('SLAB_FUSE', '0')))   # forward mode only: g2p(f) + p2g(f+1) fused
     st = slab.sim.get_state()
-    st['v'][:len(mine)] = v0[mine]
+    st['v'][:len(mine)] = v0[mine]; st['F'][:len(mine)] = F0[mine]
     slab.sim.set_state(0, st)
     if os.environ.get('SLAB_MODE', 'forward') == 'backward':
-        ok = backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange)
+        ok = backward_parity(slab, rank, world, dev, q, parts, x, v0, F0, Ntot, exchange)
         dist.barrier()
         dist.destroy_process_group()
         sys.exit(0 if ok else 1)
@@ -59,7 +62,7 @@ def main():
     if rank == 0:
         ref = MPMSimulator(dim=3, quality=q, gravity=(0.0, -10.0, 0.0), horizon=1000, max_substeps_local=20, max_substeps_global=10 ** 6, ckpt_dest='gpu', device=dev)
         ref.build(None, None, [], parts(np.arange(Ntot)))
-        s0 = ref.get_state(); s0['v'][:] = v0; ref.set_state(0, s0)
+        s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
         for _ in range(n_steps):
             ref.step(None)
         r = ref.get_state()
@@ -74,7 +77,7 @@ def main():
     sys.exit(0 if ok else 1)
 
 
-def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
+def backward_parity(slab, rank, world, dev, q, parts, x, v0, F0, Ntot, exchange):
     from fluidlab_b200 import MPMSimulator
     # 30 substeps on a 20-frame ring: one wrap (chunk checkpoint + re-run in the backward pass), a migration at step 2.  (Round 2, first hardware run: with
     # 50 substeps of this water + ELASTIC cloud at 3 m/s the SINGLE-GPU gradient differs from itself by gC, gF ~ 0.3 when only the summation order changes —
@@ -96,7 +99,7 @@ def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
     if rank == 0:
         ref = MPMSimulator(dim=3, quality=q, gravity=(0.0, -10.0, 0.0), horizon=1000, max_substeps_local=20, max_substeps_global=10 ** 6, ckpt_dest='gpu', device=dev)
         ref.build(None, None, [], parts(np.arange(Ntot)))
-        s0 = ref.get_state(); s0['v'][:] = v0; ref.set_state(0, s0)
+        s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
         ref.enable_grad()
         for _ in range(n_steps):
             ref.step(None)
@@ -114,7 +117,7 @@ def backward_parity(slab, rank, world, dev, q, parts, x, v0, Ntot, exchange):
             ref2 = MPMSimulator(dim=3, quality=q, gravity=(0.0, -10.0, 0.0), horizon=1000, max_substeps_local=20, max_substeps_global=10 ** 6, ckpt_dest='gpu', device=dev, sort_every=0)
             ref2.store_grids = False
             ref2.build(None, None, [], parts(np.arange(Ntot)))
-            s0 = ref2.get_state(); s0['v'][:] = v0; ref2.set_state(0, s0)
+            s0 = ref2.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref2.set_state(0, s0)
             ref2.enable_grad()
             for _ in range(n_steps):
                 ref2.step(None)
