@@ -28,11 +28,10 @@ def pytest_configure(config):
         simulator.MPMSimulator.__init__ = emu_init
 
 
-# `-m gpu` tests written after round 1's GPU minutes were spent: verified on the CPU execution-model shim (tests/cuda_emu), never yet run on a
-# B200.  They are collected AFTER the hardware-validated ones, so that with `-x` a first-run surprise in a new path does not hide the state of
-# the paths that have already been measured.  Remove a pattern once its tests have passed on hardware.
-FIRST_HARDWARE_RUN_PENDING = ('g2p2g', '_fused', 'fused_path', 'reference_agents', 'finite_differences', 'neighbour_handshake', 'slab_sharded_backward', '-locked', 'locked-',
-                              'test_zz_smoke_gpu', 'test_optimizer')
+# `-m gpu` tests that have not yet passed on a B200 are collected AFTER the hardware-validated ones, so that with `-x` a first-run surprise in a new
+# path does not hide the state of the paths that have already been measured.  Remove a pattern once its tests have passed on hardware.  (Round 2:
+# everything round 1 had left here has run green on hardware — profiles/README.md, r02n / r02u / r02v; the two C4 tests were re-conditioned after r02n.)
+FIRST_HARDWARE_RUN_PENDING = ('test_c4_',)
 
 
 def pytest_collection_modifyitems(config, items):
