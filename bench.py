@@ -215,8 +215,104 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_config(args):
+    """--config C3 | C4: BASELINE.json configs[2] / configs[3] through the reference-facing TaichiEnv API (tests/baseline_scenes.py builds the same scenes the
+    parity tests compare with the oracle): forward substeps/s, forward + backward substep pairs/s (loss + dLoss/dAction, chunk re-simulation included) and
+    an end-to-end figure with host actions and a get_state_RL read-back per step.  An extra to the C2 line: the driver's line stays the default config."""
+    import torch
+    from baseline_scenes import c3_env, c4_env
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    if args.config == 'C3':
+        n_steps = max(1, min(args.steps, 50)) if args.steps != 100 else 10   # SURVEY 8d C3: 50-step horizon; default 10 steps = 100 substeps = two T = 50 chunks
+        env, actions, action_p = c3_env(n_steps, T=50, device_kw=dict(device=dev), scale=1.0 if args.particles == N_PARTICLES else args.particles / 262_144)
+        workload = (f'C3 LatteArt two-material ({env.simulator.n_particles} slots: COFFEE in the cup + parked MILK, Injector flux 8, cylinder boundary), 128^3 grid, fp32, {n_steps} steps x 10 substeps, '
+                    'T = 50 ring, LatteArtLoss, dLoss/dAction (BASELINE.json configs[2])')
+    else:
+        n_steps = 1
+        small = args.particles != N_PARTICLES   # (script checks on the CPU execution-model shim: fewer particles on a coarser grid)
+        env, actions, action_p = c4_env(n_steps=n_steps, n_grid=32 if small else 192, n_each=args.particles // 2 if small else 1_000_000, T=10, device_kw=dict(device=dev))
+        workload = (f'C4 IceCream elastic + plasto-elastic, 2 x {env.simulator.n_particles // 2} particles, {env.simulator.n_grid}^3 grid, fp32, soft cone collider '
+                    '(agent_icecreamdynamic.yaml:26-37) evaluated per particle but hovering above the blocks (no contact: dLoss/dAction is ~0; with the reference\'s fixed dt a '
+                    'contact perturbation grows 5x per substep at 192^3, see tests/test_gpu_parity.py c4_case), 1 step x 10 substeps from rest per repetition, '
+                    'IceCreamDynamicLoss, forward + backward (BASELINE.json configs[3])')
+    sim = env.simulator
+    st0 = env.get_state()['state']
+    n_sub = n_steps * SUBSTEPS_PER_STEP
+
+    def fwd(grad):
+        env.set_state(st0, grad_enabled=grad)
+        env.apply_agent_action_p(action_p)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n_steps):
+            env.step(actions[i])
+        b.record()
+        return a, b
+
+    def fwd_bwd():
+        a, _ = fwd(True)
+        env.get_final_loss()
+        env.reset_grad(); env.get_final_loss_grad()
+        for i in range(n_steps - 1, -1, -1):
+            env.step_grad(actions[i])
+        env.apply_agent_action_p_grad(action_p)
+        b = torch.cuda.Event(enable_timing=True); b.record()
+        return a, b
+
+    def timed(fn, min_ms):
+        for _ in range(max(args.warmup, 3) if n_steps == 1 else 2):
+            fn()
+        torch.cuda.synchronize()
+        tot, reps = 0.0, 0
+        while reps == 0 or (tot < min_ms and reps < 2000):
+            a, b = fn(); torch.cuda.synchronize()
+            tot += a.elapsed_time(b); reps += 1
+        return tot / reps, reps
+    with ClockSampler(0) as cs:
+        ms_f, reps_f = timed(lambda: fwd(False), args.min_seconds * 1e3)
+    clocks = cs.summary()
+    ms_fb, reps_fb = timed(fwd_bwd, args.min_seconds * 1e3)
+    grad = env.agent.get_grad(n_steps)
+    x_ = sim.get_x()
+    if not (np.isfinite(x_).all() and np.isfinite(grad).all()):
+        raise RuntimeError(f'{args.config}: non-finite state / gradient after the timed region: the measurement is void')
+    # end to end: host actions in, x / v / used of every step out (get_state_RL), set_state from host at every episode start
+    d2h = sim.n_particles * 28
+    h2d = sum(np.asarray(v).nbytes for k, v in st0.items() if k in ('x', 'v', 'C', 'F', 'used')) / n_steps
+
+    def episode():
+        env.set_state(st0, grad_enabled=False)
+        env.apply_agent_action_p(action_p)
+        for i in range(n_steps):
+            env.step(actions[i])
+            out = env.get_state_RL()
+        return out
+    episode(); torch.cuda.synchronize()
+    t0, n_ep = time.perf_counter(), 0
+    while n_ep == 0 or time.perf_counter() - t0 < args.min_seconds:
+        episode(); n_ep += 1
+    torch.cuda.synchronize()
+    e2e = n_ep * n_sub / (time.perf_counter() - t0)
+    line = {'metric': 'mpm_substeps_per_s_fwd', 'value': n_sub / (ms_f * 1e-3), 'unit': 'substeps/s', 'n_gpus': 1, 'steps': n_steps, 'warmup': max(args.warmup, 3),
+            'timed_steps': n_steps * reps_f, 'ms_per_step': ms_f / n_steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload, 'substeps_per_step': SUBSTEPS_PER_STEP, 'dt': 2e-4, 'n_particle_slots': int(sim.n_particles),
+                       'api': 'TaichiEnv.set_state / apply_agent_action_p / step(action) [/ get_final_loss / reset_grad / get_final_loss_grad / step_grad / apply_agent_action_p_grad]; '
+                              'device time of the step loop (CUDA events), set_state outside the timed region',
+                       'l2_policy': 'inputs larger than L2 (100 B x particle slots per frame, walked frame by frame)', 'parallelism': 'single GPU'},
+            'clocks': clocks,
+            'fwd_bwd': {'value': n_sub / (ms_fb * 1e-3), 'unit': 'substeps/s (each = 1 forward + 1 backward substep; loss, loss gradient and chunk re-simulation included)',
+                        'ms_per_pass': ms_fb, 'passes_timed': reps_fb, 'dloss_daction_absmax': float(np.abs(grad).max())},
+            'e2e': {'value': e2e, 'unit': 'substeps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'api': 'TaichiEnv.set_state(host) / step(host action) / get_state_RL (blocking D2H of x, v, used every step)'},
+            'gpu_launches': None}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--config', default='C2', choices=['C2', 'C3', 'C4'], help='C2 (default): BASELINE.json configs[1], the line the metric is quoted on; C3 / C4: configs[2] / configs[3] '
+                    'through TaichiEnv (forward, forward + backward, e2e) as an extra line; C5 is --scaling strong')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
@@ -233,6 +329,8 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.config != 'C2':
+        return run_config(args)
 
     import torch
     import torch.distributed as dist
@@ -566,22 +664,33 @@ def main():
             sim2.fuse_g2p2g = bool(args.fuse_g2p2g)
             tgt2, mask2 = tgt, sim2.material_row_mask(fluidlab_b200.macros.WATER)
 
+            mid = [None]
+
             def fwd_bwd2():
                 sim2.set_state(0, init); sim2.enable_grad()
                 for _ in range(nfb):
                     sim2.step(None)
                 sim2.reset_grad()
                 sim2.add_x_grad_chamfer(tgt2, mask2, 1.0)
+                mid[0] = torch.cuda.Event(enable_timing=True); mid[0].record()
                 for _ in range(nfb):
                     sim2.step_grad(None)
             fwd_bwd2(); barrier()
-            runs2 = []
+            runs2, bwd2 = [], []
             for _ in range(3):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); fwd_bwd2(); b.record(); barrier()
-                runs2.append(a.elapsed_time(b))
+                runs2.append(a.elapsed_time(b)); bwd2.append(mid[0].elapsed_time(b))
             fb['whole_trajectory_ring'] = {'value': nfb * SUBSTEPS_PER_STEP / (float(np.median(runs2)) * 1e-3), 'unit': 'substeps/s (1 forward + 1 backward substep each, no re-simulation)',
                                            'max_substeps_local': T2, 'runs_ms': runs2, 'stored_grids': sim2._pm_ring is not None}
+            # the backward substep against SURVEY 8(d)'s byte count for it (432 B x N_u + 156 B x G_t: k_g2p_grad_scatter + k_grid_op_grad +
+            # k_particle_grad, forward grids kept in the ring): mean device time of a backward substep over the nfb x 10 of the pass above
+            t_bs = float(np.median(bwd2)) / (nfb * SUBSTEPS_PER_STEP)
+            bwd_bytes = 432 * used + 156 * g_t
+            fb['roofline_bwd'] = {'bound': 'hbm', 'kernels': 'k_g2p_grad_scatter + k_grid_op_grad + k_particle_grad (+ the sparse clear of the adjoint grid)',
+                                  'achieved': bwd_bytes / (t_bs * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': bwd_bytes / (t_bs * 1e-3) / 1e9 / peak,
+                                  'backward_substep_ms': t_bs, 'algorithmic_bytes_per_substep': bwd_bytes,
+                                  'timing': f'device time of the {nfb * SUBSTEPS_PER_STEP} backward substeps of the whole-trajectory pass (CUDA events), median of 3'}
             del sim2
             torch.cuda.empty_cache()
         except Exception as ex:   # an extra: never let it take the bench line down

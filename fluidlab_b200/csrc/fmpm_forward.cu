@@ -548,8 +548,10 @@ __device__ __forceinline__ void fwd_gather_unstaged(const KParams& P, const floa
 // (grid_op_node) and written back with the tag in ONE 16-byte store, so each node is converted by the first warp that needs it (plus the
 // few that race with it: they store identical values) instead of by every warp that stages it.  `stride` permutes the CTA -> slot-block
 // map (an odd prime not dividing the grid size): neighbouring slot blocks — which share their nodes — then run in different waves.
+// frame bases of one k_fwd launch, computed on the host (in the kernel the 64-bit products f * 4 * N ... were ~20 per-lane instructions per warp)
+struct FwdFrames { float4* pa_f; float4* pa_n; float4* pf_r; float4* pf_w; float* p8_r; float* p8_w; };
 template <int kMat, bool kInline, bool kSlab>
-__global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams P, const int f, float4* __restrict__ clr, int* __restrict__ clr_flags, const int full,
+__global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams P, const FwdFrames FR, const int f, float4* __restrict__ clr, int* __restrict__ clr_flags, const int full,
                                                                             const float4* __restrict__ pms, const int tag_off, const int stride,
                                                                             const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm16, const int use_tma) {
   __shared__ ScatterSmem smem[P2G_WARPS];
@@ -559,7 +561,9 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
   ScatterSmem& S = smem[wib];
   float4* tile = S.rec;   // gather tile first, scatter records afterwards (a __syncwarp separates the two uses)
   const long long gw = (long long)blockIdx.x * P2G_WARPS + wib;
-  const long long gws = (long long)((blockIdx.x * (unsigned)stride) % gridDim.x) * P2G_WARPS + wib;   // the slot block this warp works on (32-bit: the host checks blocks * stride < 2^32)
+  // the slot block this warp works on; only the lazy grid_op permutes the CTA -> slot-block map (32-bit: the host checks blocks * stride < 2^32) —
+  // elsewhere the identity is compiled in (the modulo was 23 instructions per warp, r02k source view)
+  const long long gws = kInline ? (long long)((blockIdx.x * (unsigned)stride) % gridDim.x) * P2G_WARPS + wib : gw;
   fmpm_pdl_trigger();
   Window W; window_init(W, lane, P.n, nullptr);   // blocks are flagged once per warp (flag_box), not by the window
   fmpm_pdl_wait();
@@ -592,9 +596,15 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
   if (kSlab) window_set_slab(W, P.peer_l, P.peer_r, P.gl_lo, P.gl_hi, P.gr_lo, P.gr_hi, P.peer_fl, P.peer_fr);   // x-slab mode: like k_p2g
   // plane pointers of this slot: frame f / f+1 of the state planes, frame f+1 / f+2 of F
   const size_t Ns = (size_t)P.N;
+#ifdef FWD_DEVICE_PTRS   // A/B (profiles/ab_variants.sh): the round-2 r02k form, frame offsets computed per lane in the kernel
   float4* const pa_f = P.pa + (size_t)f * 4 * Ns + s; float4* const pa_n = pa_f + 4 * Ns;
   float4* const pf_r = P.pf + (size_t)(f + 1) * 2 * Ns + s; float4* const pf_w = pf_r + 2 * Ns;
   float* const p8_r = P.pf8 + (size_t)(f + 1) * Ns + s; float* const p8_w = p8_r + Ns;
+#else
+  float4* const pa_f = FR.pa_f + s; float4* const pa_n = FR.pa_n + s;
+  float4* const pf_r = FR.pf_r + s; float4* const pf_w = FR.pf_w + s;
+  float* const p8_r = FR.p8_r + s; float* const p8_w = FR.p8_w + s;
+#endif
   // ---- particle loads: x + meta of frame f, F[f+1] (written by the p2g / k_fwd of frame f)
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 f0 = make_float4(1.f, 0.f, 0.f, 0.f), f1 = make_float4(1.f, 0.f, 0.f, 0.f); float f8 = 1.f;
@@ -1063,9 +1073,16 @@ static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream, in
     for (int k = 0; k < 5 && stride == 1; k++) if (blocks > primes[k] && blocks % primes[k] != 0 && (long long)blocks * primes[k] < (1LL << 32)) stride = primes[k];
   }
   const int tag_off = f - tag_f0;
+  FwdFrames FR;   // frame f / f+1 of the state planes, frame f+1 / f+2 of F
+  {
+    const size_t Ns = (size_t)P.N;
+    FR.pa_f = P.pa + (size_t)f * 4 * Ns; FR.pa_n = FR.pa_f + 4 * Ns;
+    FR.pf_r = P.pf + (size_t)(f + 1) * 2 * Ns; FR.pf_w = FR.pf_r + 2 * Ns;
+    FR.p8_r = P.pf8 + (size_t)(f + 1) * Ns; FR.p8_w = FR.p8_r + Ns;
+  }
   const bool slab = h->slab.enabled != 0 && !h->slab_pull;   // (never together with the inlined grid_op, see fwd_path; pull form: local scatter)
   const int use_tma = (h->tma_ok && (path & FWD_TMA) && !inl) ? 1 : 0;
-#define FWD_GO(a, b, c) FMPM_LAUNCH_PDL(h->use_pdl != 0, FWD_K(a, b, c), blocks, P2G_WARPS * 32, 0, stream, P, f, clr, clr_flags, full, pms, tag_off, stride, h->tm_gv8, h->tm_gv16, use_tma)
+#define FWD_GO(a, b, c) FMPM_LAUNCH_PDL(h->use_pdl != 0, FWD_K(a, b, c), blocks, P2G_WARPS * 32, 0, stream, P, FR, f, clr, clr_flags, full, pms, tag_off, stride, h->tm_gv8, h->tm_gv16, use_tma)
   if (liq) { if (inl) FWD_GO(1, true, false); else if (slab) FWD_GO(1, false, true); else FWD_GO(1, false, false); }
   else { if (inl) FWD_GO(0, true, false); else if (slab) FWD_GO(0, false, true); else FWD_GO(0, false, false); }
 #undef FWD_GO
