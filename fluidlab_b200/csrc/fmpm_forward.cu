@@ -477,6 +477,13 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
 #ifndef FWD_MINB
 #define FWD_MINB 5
 #endif
+#ifndef FWD_PERSIST
+#define FWD_PERSIST 0   // 1: persistent warps — sm_count x FWD_MINB CTAs, every warp claims 32-slot chunks from a global counter (P.blk_list[0]) until none is
+                        // left: no CTA turnover, and the tail of the grid shrinks from a partial wave of CTAs to one chunk.  Not with the lazy grid_op (kInline).
+#endif
+#ifndef FWD_WARPS
+#define FWD_WARPS P2G_WARPS   // warps per CTA of k_fwd (A/B: -DFWD_WARPS=3 -DFWD_MINB=7 ...)
+#endif
 #define FWD_TILE_COLS 16   // 4 x 4 node columns
 // grid_op of one node without SDF colliders (MPM:380-386,398): the same operations, in the same order, as k_grid_op.
 // interior: the caller knows that no boundary condition can act on this node (then boundary_v would multiply by 1: skipped)
@@ -551,19 +558,19 @@ __device__ __forceinline__ void fwd_gather_unstaged(const KParams& P, const floa
 // frame bases of one k_fwd launch, computed on the host (in the kernel the 64-bit products f * 4 * N ... were ~20 per-lane instructions per warp)
 struct FwdFrames { float4* pa_f; float4* pa_n; float4* pf_r; float4* pf_w; float* p8_r; float* p8_w; };
 template <int kMat, bool kInline, bool kSlab>
-__global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams P, const FwdFrames FR, const int f, float4* __restrict__ clr, int* __restrict__ clr_flags, const int full,
+__global__ void __launch_bounds__(FWD_WARPS * 32, FWD_MINB) k_fwd(const KParams P, const FwdFrames FR, const int f, float4* __restrict__ clr, int* __restrict__ clr_flags, const int full,
                                                                             const float4* __restrict__ pms, const int tag_off, const int stride,
                                                                             const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm16, const int use_tma) {
-  __shared__ ScatterSmem smem[P2G_WARPS];
-  __shared__ unsigned long long tbar[P2G_WARPS];   // one mbarrier per warp: completion of its TMA footprint tile
+  __shared__ ScatterSmem smem[FWD_WARPS];
+  __shared__ unsigned long long tbar[FWD_WARPS];   // one mbarrier per warp: completion of its TMA footprint tile
   static_assert(sizeof(((ScatterSmem*)0)->rec) >= FWD_TILE_COLS * 16 * sizeof(float4), "the gather tile is staged in the scatter records' storage");
   const int lane = threadIdx.x & 31, wib = __shfl_sync(SC_FULL, (int)(threadIdx.x >> 5), 0);   // broadcast: dependent code is compiled warp-uniform
   ScatterSmem& S = smem[wib];
   float4* tile = S.rec;   // gather tile first, scatter records afterwards (a __syncwarp separates the two uses)
-  const long long gw = (long long)blockIdx.x * P2G_WARPS + wib;
+  const long long gw = (long long)blockIdx.x * FWD_WARPS + wib;
   // the slot block this warp works on; only the lazy grid_op permutes the CTA -> slot-block map (32-bit: the host checks blocks * stride < 2^32) —
   // elsewhere the identity is compiled in (the modulo was 23 instructions per warp, r02k source view)
-  const long long gws = kInline ? (long long)((blockIdx.x * (unsigned)stride) % gridDim.x) * P2G_WARPS + wib : gw;
+  const long long gws = kInline ? (long long)((blockIdx.x * (unsigned)stride) % gridDim.x) * FWD_WARPS + wib : gw;
   fmpm_pdl_trigger();
   Window W; window_init(W, lane, P.n, nullptr);   // blocks are flagged once per warp (flag_box), not by the window
   fmpm_pdl_wait();
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
   // ---- clear duty (kInline): one warp per flagged 8^3-node block of the accumulator that the previous launch gathered from
   if (kInline && clr != nullptr) {
     const int nb = P.nb, nblk = nb * nb * nb, n = P.n;
-    const long long nwarps = (long long)gridDim.x * P2G_WARPS;
+    const long long nwarps = (long long)gridDim.x * FWD_WARPS;
     for (long long blk = gw; blk < nblk; blk += nwarps) {
       if (clr_flags[blk] != 0) {   // warp-uniform
         const int bx = (int)(blk / (nb * nb)), by = (int)((blk / nb) % nb), bz = (int)(blk % nb);
@@ -586,8 +593,28 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
       }
     }
   }
-  const long long slot0 = gws * 32;
+  constexpr bool kPersist = FWD_PERSIST && !kInline && (kMat == 1 || FWD_PERSIST >= 2);   // (the general instantiation spills 250 B inside the loop: FWD_PERSIST=2 to force it)
+  unsigned tph = 0;   // phase of the warp's mbarrier (it completes once per TMA tile)
+#ifndef FMPM_HOST_EMU
+  if (kPersist && use_tma) {
+    if (lane == 0) mbar_init(&tbar[wib], 1);
+    __syncwarp();
+  }
+#endif
+#if FWD_PERSIST
+  for (;;) {
+#endif
+  long long slot0 = gws * 32;
+  if (kPersist) {   // claim the next chunk of 32 slots
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(P.blk_list, 1);
+    slot0 = (long long)__shfl_sync(SC_FULL, chunk, 0) * 32;
+  }
+#if FWD_PERSIST
+  if (slot0 >= P.N) break;    // warp-uniform
+#else
   if (slot0 >= P.N) return;   // warp-uniform
+#endif
   const long long sl = slot0 + lane;
   const long long rem = (long long)P.N - slot0;
   const int cnt = rem < 32 ? (int)rem : 32;
@@ -632,7 +659,8 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
     // 4 in y, 4 in x) at (0, bz0, by0, bx0) of grid_v into the warp's tile (out-of-range nodes arrive as zeros) and completes on the warp's
     // mbarrier; the lanes meanwhile go on with the particle-side arithmetic and wait just before the gather.
     if (lane == 0) {
-      mbar_init(&tbar[wib], 1);
+      if (!kPersist) mbar_init(&tbar[wib], 1);
+      else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile overwrites the previous chunk's scatter records (generic-proxy stores)
       mbar_expect_tx(&tbar[wib], (unsigned)((FWD_TILE_COLS << tzs) * sizeof(float4)));
       tma_load_4d(tile, tzs == 3 ? &tm8 : &tm16, &tbar[wib], 0, bz0, by0, bx0);
     }
@@ -693,7 +721,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
       bspline(fx, w);
       const float c4 = 4.f * P.inv_dx;
 #ifndef FMPM_HOST_EMU
-      if (tma) mbar_wait(&tbar[wib], 0);   // the tile has landed (every gathering lane waits; the others meet them at the __syncwarp before the staging)
+      if (tma) mbar_wait(&tbar[wib], tph);   // the tile has landed (every gathering lane waits; the others meet them at the __syncwarp before the staging)
 #endif
       if (staged) {
         const float4* t0 = tile + ((((b[0] - bx0) << 2) + (b[1] - by0)) << tzs) + (b[2] - bz0);
@@ -763,6 +791,16 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, FWD_MINB) k_fwd(const KParams 
   __syncwarp();
   window_consume2<kSlab>(W, S, cnt, starts, P.grid_pm);
   window_flush_all2<kSlab>(W, P.grid_pm);
+#if FWD_PERSIST
+  if (!kPersist) break;
+  if (tma) tph ^= 1u;
+  __syncwarp();   // the staging area is the next chunk's gather tile
+  }
+  if (kPersist && lane == 0) {   // the last warp out resets the chunk counter for the next launch (every other warp has left its loop by then)
+    const int done = atomicAdd(P.blk_list + 1, 1);
+    if (done == (int)(gridDim.x * FWD_WARPS) - 1) { P.blk_list[0] = 0; P.blk_list[1] = 0; }
+  }
+#endif
 }
 
 // p2g of the few particles an injector has just activated in frame f (fused steps with an injector agent: the g2p2g kernel of the previous
@@ -1066,7 +1104,14 @@ static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream, in
     clr = Pc.grid_pm; clr_flags = Pc.blk_flags;
   }
   if (P.N == 0) return 0;
-  const int blocks = (int)(((long long)P.N + 32 * P2G_WARPS - 1) / (32 * P2G_WARPS));
+  int blocks = (int)(((long long)P.N + 32 * FWD_WARPS - 1) / (32 * FWD_WARPS));
+#if FWD_PERSIST
+  if (!inl && (liq || FWD_PERSIST >= 2)) {   // persistent warps: one resident set of CTAs, chunks claimed from P.blk_list[0] (a reserved, zero-initialised buffer of FmpmBuffers)
+    if (!P.blk_list) { snprintf(h->err, sizeof(h->err), "fmpm_substeps_fused(k_fwd): blk_list (the chunk counter of the persistent kernel) was not bound"); return 1; }
+    const int resident = h->sm_count * FWD_MINB;
+    if (blocks > resident) blocks = resident;
+  }
+#endif
   int stride = 1;   // CTA -> slot-block permutation (lazy grid_op): an odd prime that does not divide the grid size
   if (inl && h->fwd_stride != 1) {
     static const int primes[] = {1021, 1031, 2053, 509, 257};
@@ -1082,7 +1127,7 @@ static int fwd_launch(FmpmHandle* h, int f, int path, int full, void* stream, in
   }
   const bool slab = h->slab.enabled != 0 && !h->slab_pull;   // (never together with the inlined grid_op, see fwd_path; pull form: local scatter)
   const int use_tma = (h->tma_ok && (path & FWD_TMA) && !inl) ? 1 : 0;
-#define FWD_GO(a, b, c) FMPM_LAUNCH_PDL(h->use_pdl != 0, FWD_K(a, b, c), blocks, P2G_WARPS * 32, 0, stream, P, FR, f, clr, clr_flags, full, pms, tag_off, stride, h->tm_gv8, h->tm_gv16, use_tma)
+#define FWD_GO(a, b, c) FMPM_LAUNCH_PDL(h->use_pdl != 0, FWD_K(a, b, c), blocks, FWD_WARPS * 32, 0, stream, P, FR, f, clr, clr_flags, full, pms, tag_off, stride, h->tm_gv8, h->tm_gv16, use_tma)
   if (liq) { if (inl) FWD_GO(1, true, false); else if (slab) FWD_GO(1, false, true); else FWD_GO(1, false, false); }
   else { if (inl) FWD_GO(0, true, false); else if (slab) FWD_GO(0, false, true); else FWD_GO(0, false, false); }
 #undef FWD_GO
