@@ -322,6 +322,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help="weak (default): 1M particles per GPU (C2 at N = 1; N x-slabs of one body on a 256^3 grid at N > 1); "
                     "strong: BASELINE.json configs[4] — C5, 8M water particles on a 256^3 grid, sharded into N x-slabs (N = 1: one GPU holds it all)")
+    ap.add_argument('--slab-shape', type=int, default=0, help='diagnostic (N = 1 only): run ONE slab of the `--gpus SLAB_SHAPE` weak-scaling workload (1M particles as a 24-plane slab on '
+                    'the 256^3 grid, 10 % spare slots) alone on one GPU through the single-GPU path — the per-GPU cost of that workload without any exchange')
     ap.add_argument('--min-seconds', type=float, default=1.0, help='minimum length of the timed region (the K steps are repeated)')
     ap.add_argument('--fuse-g2p2g', type=int, default=1, help='1 (default, measured faster: profiles/README.md): forward steps use fmpm_substeps_fused (the gather of substep f and the '
                     'scatter of f+1 in one kernel, k_fwd); 0: the plain p2g / grid_op / g2p substeps')
@@ -356,15 +358,24 @@ def main():
         if strong:
             q5, _, parts, _ = c5_shard(1, 0, args.particles if args.particles != N_PARTICLES else C5_N)
             N = len(parts['x'])
-        sim = MPMSimulator(dim=3, quality=q5 if strong else QUALITY, gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T, max_substeps_global=10 ** 7,
+        sim = MPMSimulator(dim=3, quality=q5 if strong else (4 if args.slab_shape else QUALITY), gravity=GRAVITY, horizon=max(K + W + 4, 100) * 4, max_substeps_local=T, max_substeps_global=10 ** 7,
                            ckpt_dest='gpu', device=dev, sort_every=args.sort_every)
-        if not strong:
+        if args.slab_shape:
+            from fluidlab_b200 import macros as M_
+            _, _, lo_, hi_ = slab_layout(args.slab_shape, 0, N)
+            parts = workload_particles(N, seed=0, lo=lo_, hi=hi_)
+            pad = int(N * 0.1) + 1024
+            parts = dict(x=np.concatenate([parts['x'], np.tile(np.array(M_.NOWHERE, dtype=np.float64), (pad, 1))]), mat=np.concatenate([parts['mat'], np.full(pad, M_.WATER, np.int32)]),
+                         used=np.concatenate([parts['used'], np.zeros(pad, np.int32)]), rho=np.concatenate([parts['rho'], np.full(pad, M_.RHO[M_.WATER])]),
+                         body_id=np.zeros(N + pad, dtype=np.int32), bodies={'n': 1})
+            args.bwd, args.no_cpu = 0, True
+        elif not strong:
             parts = workload_particles(N, seed=rank)
         sim.build(None, None, [], parts)
         sim.fuse_g2p2g = bool(args.fuse_g2p2g)
         # The block falls 0.25 of the domain: free fall lasts ~110 steps (SURVEY.md 8d times 1,000 substeps after 100 warm-up).  Longer timed regions
         # replay that episode: every EPISODE steps the initial state is restored from a device-side copy INSIDE the timed region (~0.1 % of the time).
-        EPISODE = 8 if strong else 100    # C5 from rest turns non-finite after ~140 substeps with the reference's fixed dt (profiles/check_c5.py: c dt / dx = 0.85 at 256^3)
+        EPISODE = 8 if strong else (30 if args.slab_shape else 100)    # C5 from rest turns non-finite after ~140 substeps with the reference's fixed dt (profiles/check_c5.py: c dt / dx = 0.85 at 256^3)
         _cnt1 = [0]
         _init1 = [None]
 
@@ -376,6 +387,9 @@ def main():
             sim.step(None)
         workload = (f'C5 water body, {N} particles, 256^3 grid, fp32, forward (BASELINE.json configs[4], strong scaling: the whole body on one GPU)' if strong else
                     f'C2 water block free fall, {N} particles, 128^3 grid, fp32, forward (BASELINE.json configs[1])')
+        if args.slab_shape:
+            workload = (f'DIAGNOSTIC: one slab of the {args.slab_shape}-GPU weak-scaling workload alone ({N} water particles as a 24-plane slab on the 256^3 grid, 10 % spare slots), '
+                        'single-GPU path, no exchange')
         parallelism = 'single GPU'
     else:
         # weak scaling: the C2 block (same particle count and ~8 particles/cell per GPU) laid out as x-slabs of one global

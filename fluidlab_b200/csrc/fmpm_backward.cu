@@ -23,6 +23,23 @@
 #define SC_ROUNDS 4   // 1 / 2 rounds: no gain for this kernel (A/B in profiles/README.md)
 #endif
 
+#ifndef BWD_PREFETCH
+#define BWD_PREFETCH 1   // L2 prefetch of the planes a backward kernel reads late (the adjoint of frame f+1, F): r02x ncu — k_particle_grad waits 3.3 issue slots per
+                         // instruction on long-scoreboard stalls at 14 resident warps per SM, its second batch of loads is issued after the footprint staging
+#endif
+// one 128-byte line per 8 lanes of a float4 plane (the warp's 32 slots are 512 contiguous bytes), lane 0 for a float plane
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef FMPM_HOST_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+__device__ __forceinline__ void prefetch_planes4(const float4* base, const KParams& P, const int g, const int nplanes, const int s) {
+  if (BWD_PREFETCH && (threadIdx.x & 7) == 0)
+    for (int k = 0; k < nplanes; k++) prefetch_l2(base + ((size_t)g * nplanes + k) * (size_t)P.N + s);
+}
+__device__ __forceinline__ void prefetch_plane1(const float* base, const KParams& P, const int g, const int s) {
+  if (BWD_PREFETCH && (threadIdx.x & 31) == 0) prefetch_l2(base + (size_t)g * (size_t)P.N + s);
+}
 // grads in a ping-pong buffer g (0/1): same planar layout as the state ring with frame index g
 struct GState { float x[3], v[3]; Mat3 C, F; };
 __device__ __forceinline__ void load_grad(const KParams& P, int g, int s, GState& G) {
@@ -35,7 +52,7 @@ __device__ __forceinline__ void load_grad(const KParams& P, int g, int s, GState
 // g2p.grad, grid side:  gv_out[i] += w_i * (gv + 4 inv_dx * gC' (o - fx)),  gv = gv' + dt * gx'
 // =============================================================================================
 template <bool kSlab>
-__global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParams P, const int f, const int gin) {
+__global__ void __launch_bounds__(SC_WARPS * 32, 6) k_g2p_grad_scatter(const KParams P, const int f, const int gin) {
   __shared__ ScatterSmem smem[SC_WARPS];
   const int lane = threadIdx.x & 31, wib = __shfl_sync(SC_FULL, (int)(threadIdx.x >> 5), 0);   // broadcast: dependent code is compiled warp-uniform
   ScatterSmem& S = smem[wib];
@@ -55,6 +72,11 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
     float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     if (sl < P.N) {
       const int s = (int)sl;
+      if (r == 0) prefetch_planes4(P.ga, P, gin, 4, s);
+      if (r + 1 < SC_ROUNDS && sl + 32 < P.N) {   // the next round's first loads are in L2 by the time this round's node loop is done
+        if (BWD_PREFETCH && (threadIdx.x & 7) == 0) prefetch_l2(P.pa + pa_idx(P, f, 0, s + 32));
+        prefetch_planes4(P.ga, P, gin, 4, s + 32);
+      }
       const float4 a0 = P.pa[pa_idx(P, f, 0, s)];
       const float x[3] = {a0.x, a0.y, a0.z};
       int b[3]; float fx[3];
@@ -324,7 +346,11 @@ __global__ void __launch_bounds__(PG_WARPS * 32, kMat == 1 ? PG_MINB_LIQUID : PG
   float4* tg = tiles[threadIdx.x >> 5][0];
   float4* ta = tiles[threadIdx.x >> 5][1];
   PState st; st.meta = 0; st.x[0] = st.x[1] = st.x[2] = 0.f;
-  if (s < P.N) load_A(P.pa, P, f, s, st);
+  if (s < P.N) {
+    load_A(P.pa, P, f, s, st);
+    prefetch_planes4(P.pf, P, f, 2, s); prefetch_plane1(P.pf8, P, f, s);   // read after the footprint staging: F[f], then the adjoint of frame f+1
+    prefetch_planes4(P.ga, P, gin, 4, s); prefetch_planes4(P.gf, P, gin, 2, s); prefetch_plane1(P.gf8, P, gin, s);
+  }
   int b[3]; float fx[3];
   const bool ok = (s < P.N) && (st.meta & 1) && base_fx(P, st.x, b, fx);
   const Footprint fp = footprint_of(ok, b);

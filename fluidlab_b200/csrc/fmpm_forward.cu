@@ -475,14 +475,14 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
 // the extra column in x and y absorbs the drift between two cell sorts), staged with coalesced 128-bit loads.
 // =============================================================================================
 #ifndef FWD_MINB
-#define FWD_MINB 5
+#define FWD_MINB 7   // with FWD_WARPS 3: 21 warps per SM at <= 96 registers
 #endif
 #ifndef FWD_PERSIST
-#define FWD_PERSIST 0   // 1: persistent warps — sm_count x FWD_MINB CTAs, every warp claims 32-slot chunks from a global counter (P.blk_list[0]) until none is
+#define FWD_PERSIST 0   // (measured r02x: 110.9 us per substep against 104.3 — the loop costs more instructions and spills than the CTA turnover it saves)  1: persistent warps — sm_count x FWD_MINB CTAs, every warp claims 32-slot chunks from a global counter (P.blk_list[0]) until none is
                         // left: no CTA turnover, and the tail of the grid shrinks from a partial wave of CTAs to one chunk.  Not with the lazy grid_op (kInline).
 #endif
 #ifndef FWD_WARPS
-#define FWD_WARPS P2G_WARPS   // warps per CTA of k_fwd (A/B: -DFWD_WARPS=3 -DFWD_MINB=7 ...)
+#define FWD_WARPS 3   // warps per CTA of k_fwd.  r02x A/B at C2 (us per substep, whole step): 1 warp x 20 CTAs 104.3, 2 x 10 103.0, 3 x 7 101.2, 4 x 5 104.3, 5 x 4 105.3
 #endif
 #define FWD_TILE_COLS 16   // 4 x 4 node columns
 // grid_op of one node without SDF colliders (MPM:380-386,398): the same operations, in the same order, as k_grid_op.
@@ -511,6 +511,29 @@ __device__ __forceinline__ bool box_is_interior(const KParams& P, const int i0, 
   const float ax = fmaxf(fabsf(x0 - P.cyl_cx), fabsf(x1 - P.cyl_cx)), az = fmaxf(fabsf(z0 - P.cyl_cz), fabsf(z1 - P.cyl_cz));
   return y0 >= P.lo[1] && y1 <= P.hi[1] && sqrtf(ax * ax + az * az + FMPM_EPS) < 0.999f * P.cyl_r;
 }
+// lazy grid_op: a node's v_out and its tag travel in ONE 16-byte access, which the GPU performs as a single transaction.  The host build of the execution-model
+// tests has no such guarantee (a float4 copy may be four moves: a reader could pair a fresh tag with stale components), so there the tag is written last
+// and read first, with the ordering x86-TSO provides once the compiler is kept from reordering.
+__device__ __forceinline__ float4 ld_tagged(const float4* p) {
+#ifdef FMPM_HOST_EMU
+  float4 g;
+  g.w = *(const volatile float*)&p->w;
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  g.x = *(const volatile float*)&p->x; g.y = *(const volatile float*)&p->y; g.z = *(const volatile float*)&p->z;
+  return g;
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void st_tagged(float4* p, const float4& g) {
+#ifdef FMPM_HOST_EMU
+  *(volatile float*)&p->x = g.x; *(volatile float*)&p->y = g.y; *(volatile float*)&p->z = g.z;
+  __atomic_thread_fence(__ATOMIC_RELEASE);
+  *(volatile float*)&p->w = g.w;
+#else
+  *p = g;
+#endif
+}
 // the rare warp whose particles do not fit one footprint box (no cell sort yet, or a very old one): every lane gathers its own 27 nodes
 // from L2.  The node loop stays rolled so that the hot kernel stays small in the instruction cache.
 template <bool kInline>
@@ -522,11 +545,11 @@ __device__ __forceinline__ void fwd_gather_unstaged(const KParams& P, const floa
   for (int c = 0; c < 27; c++) {
     const int i = c / 9, j = (c / 3) % 3, k = c % 3;
     const int node = cell + (i * n + j) * n + k;
-    float4 g = kInline ? __ldcg(&P.grid_v[node]) : P.grid_v[node];
+    float4 g = kInline ? ld_tagged(&P.grid_v[node]) : P.grid_v[node];
     if (kInline && __float_as_int(g.w) != tagf) {   // lazy grid_op, see k_fwd
       g = grid_op_node(P, b[0] + i, b[1] + j, b[2] + k, pms[node]);
       g.w = __int_as_float(tagf);
-      P.grid_v[node] = g;
+      st_tagged(&P.grid_v[node], g);
     }
     const float d[3] = {(float)i - fx[0], (float)j - fx[1], (float)k - fx[2]};
     float wt = 1.f;
@@ -682,7 +705,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, FWD_MINB) k_fwd(const KParams 
         const int iz = t & ((1 << tzs) - 1), c = t >> tzs, iy = c & 3, ix = c >> 2;
         act[u] = ix < nx && iy < ny && iz < nz;
         gi[u] = bx0 + ix; gj[u] = by0 + iy; gk[u] = bz0 + iz;
-        if (act[u]) g[u] = kInline ? __ldcg(&P.grid_v[(gi[u] * n + gj[u]) * n + gk[u]]) : P.grid_v[(gi[u] * n + gj[u]) * n + gk[u]];
+        if (act[u]) g[u] = kInline ? ld_tagged(&P.grid_v[(gi[u] * n + gj[u]) * n + gk[u]]) : P.grid_v[(gi[u] * n + gj[u]) * n + gk[u]];
         if (kInline) stale = stale || (act[u] && __float_as_int(g[u].w) != tagf);
       }
       if (kInline && __any_sync(SC_FULL, stale)) {   // warp-uniform; false for most warps once the first toucher of a node has converted it
@@ -693,7 +716,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, FWD_MINB) k_fwd(const KParams 
             const int node = (gi[u] * n + gj[u]) * n + gk[u];
             g[u] = grid_op_node(P, gi[u], gj[u], gk[u], pms[node], interior);
             g[u].w = __int_as_float(tagf);
-            P.grid_v[node] = g[u];   // v_out and its tag in one 16-byte store
+            st_tagged(&P.grid_v[node], g[u]);   // v_out and its tag in one 16-byte store
           }
       }
 #pragma unroll
