@@ -66,7 +66,7 @@ class FmpmInjector(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("flux", C.c_int), ("radius", C.c_float),
         ("inject_v", C.c_float * 3), ("inject_p", C.c_float * 3),
-        ("random_vector", vp), ("act_range", vp), ("n_act_range", C.c_int),
+        ("random_vector", vp), ("act_range", vp), ("n_act_range", C.c_int), ("randomize_inject_v", C.c_int),
     ]
 
 

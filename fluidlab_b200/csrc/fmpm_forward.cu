@@ -900,6 +900,11 @@ __global__ void k_inject(const KParams P, const int f, const FmpmInjector inj, c
 #pragma unroll
     for (int k = 0; k < 3; k++) x[k] = (rv[k] * 2.f - 1.f) * inj.radius + pos[k] + ipr[k];
     quat_rot(quat, inj.inject_v, v);
+    if (inj.randomize_inject_v) {   // injector.py:96-97; a constant of the pose: the adjoint (k_inject_grad) is unchanged
+      const float nv2 = 2.f * sqrtf(inj.inject_v[0] * inj.inject_v[0] + inj.inject_v[1] * inj.inject_v[1] + inj.inject_v[2] * inj.inject_v[2]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) v[k] += (rv[k] * 2.f - 1.f) * nv2;
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < 3; k++) { x[k] = rv[k] + pos[k]; v[k] = inj.inject_v[k]; }

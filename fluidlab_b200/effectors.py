@@ -192,8 +192,7 @@ class Injector(Effector):
     def __init__(self, radius=1.0, flux=1, inject_v=(0.0, 0.0, 0.0), inject_p=(0.0, 0.0, 0.0), randomize_inject_v=False,
                  locally_random=False, **kwargs):
         super().__init__(**kwargs)
-        if randomize_inject_v:
-            raise NotImplementedError('randomize_inject_v (injector.py:96-97) is not used by any shipped env and is not built')
+        self.randomize_inject_v = bool(randomize_inject_v)   # injector.py:96-97 (Injector.act only; BallInjector.act ignores it, :240-256)
         self.radius = radius
         self.n_particles = flux
         self.locally_random = locally_random
@@ -223,6 +222,7 @@ class Injector(Effector):
         inj.kind, inj.flux, inj.radius = self.kind, int(self.n_particles), float(self.radius)
         inj.inject_v = (C.c_float * 3)(*[float(x) for x in self.inject_v]); inj.inject_p = (C.c_float * 3)(*[float(x) for x in self.inject_p])
         inj.random_vector = self._random_vector.data_ptr(); inj.act_range = self._act_range.data_ptr(); inj.n_act_range = len(self.act_range_np)
+        inj.randomize_inject_v = int(self.randomize_inject_v and self.kind == 1)
         self._inj = inj
 
     def act(self, f, f_global):  # injector.py:80-105

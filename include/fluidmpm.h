@@ -119,6 +119,7 @@ typedef struct {
   const void* random_vector; /* float[random_length*flux*3] */
   const void* act_range;     /* int[n_act_range], original particle ids */
   int n_act_range;
+  int randomize_inject_v;    /* injector.py:96-97 (Injector only): v += (2 random_vector - 1) * |inject_v| * 2 */
 } FmpmInjector;
 
 /* SDF mesh colliders: fluidlab/fluidengine/meshes/static.py:26-104 (Static.collide, applied in grid_op MPM:388-390) and

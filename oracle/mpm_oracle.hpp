@@ -167,7 +167,7 @@ struct EffectorCfg {
   // own boundary (effector.py:63 setup_boundary)
   int boundary_type; double b_lower[3], b_upper[3]; double cyl_center[2], cyl_radius;
   // injector
-  double radius; int flux; double inject_v[3], inject_p[3]; int locally_random; int random_length;
+  double radius; int flux; double inject_v[3], inject_p[3]; int locally_random; int random_length; int randomize_inject_v;
   int max_action_steps;
 };
 
@@ -773,6 +773,10 @@ template <class R> struct Sim {
         R iv[3] = {(R)ec.inject_v[0], (R)ec.inject_v[1], (R)ec.inject_v[2]}, ivr[3];
         quat_rotate(&e.quat[f * 4], iv, ivr);
         for (int k = 0; k < 3; k++) v[q * 3 + k] = ivr[k];
+        if (ec.randomize_inject_v) {   // injector.py:96-97: + (random_vector * 2 - 1) * inject_v.norm() * 2.0 (no pose dependence: agent_act_grad is unchanged)
+          const R nv = std::sqrt(iv[0] * iv[0] + iv[1] * iv[1] + iv[2] * iv[2]);
+          for (int k = 0; k < 3; k++) v[q * 3 + k] = ivr[k] + (rv[k] * R(2) - R(1)) * nv * R(2);
+        }
       } else {
         for (int k = 0; k < 3; k++) { x[q * 3 + k] = rv[k] + e.pos[f * 3 + k]; v[q * 3 + k] = (R)ec.inject_v[k]; }
       }

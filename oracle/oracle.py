@@ -42,7 +42,7 @@ class EffectorCfg(C.Structure):
         ("boundary_type", C.c_int), ("b_lower", C.c_double * 3), ("b_upper", C.c_double * 3),
         ("cyl_center", C.c_double * 2), ("cyl_radius", C.c_double),
         ("radius", C.c_double), ("flux", C.c_int), ("inject_v", C.c_double * 3), ("inject_p", C.c_double * 3),
-        ("locally_random", C.c_int), ("random_length", C.c_int),
+        ("locally_random", C.c_int), ("random_length", C.c_int), ("randomize_inject_v", C.c_int),
         ("max_action_steps", C.c_int),
     ]
 
@@ -193,7 +193,7 @@ class OracleSim:
     # ---- agent (single effector agents: AgentInjector / plain pose chain)
     def add_effector(self, type=0, action_dim=3, scale_v=(1, 1, 1), scale_p=(1, 1, 1), boundary=None, radius=0.0, flux=0,
                      inject_v=(0, 0, 0), inject_p=(0, 0, 0), locally_random=True, random_vector=None, act_range=None,
-                     max_action_steps=1000, init_pos=(0.5, 0.5, 0.5), init_quat=(1, 0, 0, 0)):
+                     max_action_steps=1000, init_pos=(0.5, 0.5, 0.5), init_quat=(1, 0, 0, 0), randomize_inject_v=False):
         ec = EffectorCfg()
         ec.type, ec.action_dim = type, action_dim
         sv = list(scale_v) + [1.0] * (6 - len(scale_v)); sp = list(scale_p) + [1.0] * (6 - len(scale_p))
@@ -204,7 +204,7 @@ class OracleSim:
         ec.cyl_center = (C.c_double * 2)(*bf["cyl_center"]); ec.cyl_radius = bf["cyl_radius"]
         ec.radius, ec.flux = radius, flux
         ec.inject_v = (C.c_double * 3)(*inject_v); ec.inject_p = (C.c_double * 3)(*inject_p)
-        ec.locally_random = int(locally_random)
+        ec.locally_random = int(locally_random); ec.randomize_inject_v = int(randomize_inject_v)
         rv = _d(random_vector) if random_vector is not None else np.zeros((1, max(flux, 1), 3))
         ec.random_length = rv.shape[0]
         ec.max_action_steps = max_action_steps

@@ -121,7 +121,7 @@ def scene_rigid_bodies(R):
 
 
 # ---------------------------------------------------------------------------------------------------------------- scene 3
-def scene_jetbot(R):
+def scene_jetbot(R, randomize_inject_v=False):
     """the real AgentJetBot (agents/agent_jetbot.py): a 6-DOF Injector whose pose is driven through Agent.set_action -> set_velocity ->
     move_kernel (quaternion chain), injecting WATER into a pool, plus the collector; 3 steps through MPMSimulator.step"""
     from fluidlab_b200 import macros as M
@@ -138,7 +138,7 @@ def scene_jetbot(R):
     np.random.seed(31)
     agent = R['agents'].AgentJetBot(collector_boundary=cbnd, **common)
     agent.add_effector(type='Injector', params=dict(radius=0.015, flux=flux, init_pos=(0.58, 0.55, 0.5), init_euler=(20.0, 35.0, -10.0), inject_v=(-3.0, 0.0, 0.0),
-                                                     inject_p=(-0.07, 0.0, 0.0), action_dim=6, action_scale_p=(1.0,) * 6, action_scale_v=(1.0, 1.0, 1.0, 5.0, 5.0, 5.0)),
+                                                     inject_p=(-0.07, 0.0, 0.0), randomize_inject_v=randomize_inject_v, action_dim=6, action_scale_p=(1.0,) * 6, action_scale_v=(1.0, 1.0, 1.0, 5.0, 5.0, 5.0)),
                        mesh_cfg=None, boundary_cfg=ebnd)
     S = R['sim'].MPMSimulator(dim=3, quality=n_grid / 64, gravity=(0.0, -10.0, 0.0), horizon=10, max_substeps_local=T, max_substeps_global=1000, ckpt_dest='cpu')
     S.setup_boundary(**bnd)
@@ -318,7 +318,7 @@ def scene_icecream(R):
 def main():
     R = load_reference()
     patch_mesh_io(R)
-    for name, fn in (('multimat', scene_multimat), ('rigid_bodies', scene_rigid_bodies), ('locked', scene_locked), ('jetbot', scene_jetbot), ('latteart', scene_latteart), ('pouring', scene_pouring),
+    for name, fn in (('multimat', scene_multimat), ('rigid_bodies', scene_rigid_bodies), ('locked', scene_locked), ('jetbot', scene_jetbot), ('jetbot_randv', lambda R_: scene_jetbot(R_, randomize_inject_v=True)), ('latteart', scene_latteart), ('pouring', scene_pouring),
                      ('icecream', scene_icecream)):
         d = fn(R)
         np.savez_compressed(os.path.join(HERE, f'reference_run_{name}.npz'), **d)

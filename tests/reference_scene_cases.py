@@ -64,19 +64,25 @@ def run_latteart_case(device=None):
     _drive(s, agent, agent.effectors[0], d)
 
 
-def run_jetbot_case(device=None):
+def run_jetbot_case(device=None, randv=False):
     """AgentJetBot: a 6-DOF Injector (rotated pose, pose chain with quaternions) injecting WATER into a pool + the collector, 3 steps"""
     from fluidlab_b200 import AgentJetBot
-    d = np.load(os.path.join(G, 'reference_run_jetbot.npz'))
+    d = np.load(os.path.join(G, 'reference_run_jetbot_randv.npz' if randv else 'reference_run_jetbot.npz'))   # randv: Injector(randomize_inject_v=True), injector.py:96-97
     cube = lambda lo, hi: dict(type='cube', lower=tuple(lo), upper=tuple(hi))
     s = _sim(d, device, (0.0, -10.0, 0.0), cube(d['b_lower'], d['b_upper']))
     common = dict(max_substeps_local=int(d['T']), max_substeps_global=1000, max_action_steps_global=20, ckpt_dest='cpu')
     agent = AgentJetBot(collector_boundary=cube(d['c_lower'], d['c_upper']), **common)
     agent.add_effector(type='Injector', params=dict(radius=0.015, flux=int(d['flux']), init_pos=(0.58, 0.55, 0.5), init_euler=(20.0, 35.0, -10.0), inject_v=(-3.0, 0.0, 0.0),
-                                                    inject_p=(-0.07, 0.0, 0.0), action_dim=6, action_scale_p=(1.0,) * 6, action_scale_v=(1.0, 1.0, 1.0, 5.0, 5.0, 5.0)),
+                                                    inject_p=(-0.07, 0.0, 0.0), randomize_inject_v=randv, action_dim=6, action_scale_p=(1.0,) * 6, action_scale_v=(1.0, 1.0, 1.0, 5.0, 5.0, 5.0)),
                        mesh_cfg=None, boundary_cfg=cube(d['e_lower'], d['e_upper']))
     _drive(s, agent, agent.effectors[0], d)
     assert int(d['ref_used'].sum()) < int(d['used0'].sum()) + int(d['flux']) * 10 * int(d['n_steps']), 'the reference run collected nothing'
+
+
+def run_jetbot_randv_case(device=None):
+    """the AgentJetBot scene with Injector(randomize_inject_v=True): every injected particle's velocity gets (2 random_vector - 1) * |inject_v| * 2 on top of the
+    rotated inject_v (effectors/injector.py:96-97); a run of the reference's own class"""
+    run_jetbot_case(device, randv=True)
 
 
 def run_pouring_case(device=None):

@@ -361,14 +361,14 @@ def test_slab_forward_with_g2p2g_fusion_on_the_emulated_device(exchange):
     assert all(out[r]['migrated'] > 0 for r in range(world))
 
 
-@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream', 'latteart_fused'])
+@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'jetbot_randv', 'pouring', 'icecream', 'latteart_fused'])
 def test_agent_scenes_equal_runs_of_the_real_reference_agents(emu, scene):
     """product (real kernels on the emulated device) vs runs of the reference's own AgentInjector / AgentJetBot / AgentPouring / AgentIceCreamDynamic scenes; tests/reference_scene_cases.py"""
     import reference_scene_cases as cases
     getattr(cases, f'run_{scene}_case')(device='cpu')
 
 
-@pytest.mark.parametrize('scene', ['jetbot', 'pouring', 'icecream'])
+@pytest.mark.parametrize('scene', ['jetbot', 'jetbot_randv', 'pouring', 'icecream'])
 def test_agent_scenes_through_the_fused_path_equal_the_reference_runs(emu, scene):
     """the same reference runs with MPMSimulator.fuse_g2p2g: 6-DOF injector + collector (JetBot), Rigid SDF collider at grid and particle level +
     collector (Pouring), BallInjector with inject_till + gated Rigid collider + Static collider (IceCream)"""

@@ -997,7 +997,7 @@ def test_slab_sharded_backward_matches_single_gpu(exchange):
     assert r.returncode == 0 and 'SLAB_GRAD_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'pouring', 'icecream', 'latteart_fused'])
+@pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'jetbot_randv', 'pouring', 'icecream', 'latteart_fused'])
 def test_cuda_matches_runs_of_the_real_reference_agents(scene):
     """the CUDA path against runs of the reference's own AgentInjector (LatteArt configuration in miniature), AgentJetBot (6-DOF injector +
     collector), AgentPouring (6-DOF Rigid SDF collider at grid and particle level + collector) and AgentIceCreamDynamic (BallInjector, gated
@@ -1031,7 +1031,7 @@ def test_slab_sharded_forward_with_neighbour_handshake(fuse):
     assert r.returncode == 0 and 'SLAB_PARITY_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize('scene', ['jetbot', 'pouring', 'icecream'])
+@pytest.mark.parametrize('scene', ['jetbot', 'jetbot_randv', 'pouring', 'icecream'])
 def test_cuda_fused_path_matches_runs_of_the_real_reference_agents(scene):
     """the reference's AgentJetBot / AgentPouring / AgentIceCreamDynamic runs again through MPMSimulator.fuse_g2p2g (particle-level agent.collide
     and the collector test inside k_g2p2g, freshly injected particles scattered by k_p2g_injected); verified on the CPU execution-model shim"""

@@ -81,14 +81,15 @@ def test_boundary_restitution_and_lock_dims(prec):
     check(fr, d)
 
 
+@pytest.mark.parametrize('randv', [False, True], ids=['plain', 'randomize_inject_v'])
 @pytest.mark.parametrize('prec', [32, 64])
-def test_agent_jetbot_6dof_injector_and_collector(prec):
-    d = np.load(os.path.join(G, 'reference_run_jetbot.npz'))
+def test_agent_jetbot_6dof_injector_and_collector(prec, randv):
+    d = np.load(os.path.join(G, 'reference_run_jetbot_randv.npz' if randv else 'reference_run_jetbot.npz'))   # randv: Injector(randomize_inject_v=True), injector.py:96-97
     N = len(d['x0'])
     P = make_particles(d['x0'], d['mat'], int(d['n_grid']), used=d['used0'])
     o = orc.OracleSim(int(d['n_grid']), P, gravity=(0, -10, 0), boundary=cube(d['b_lower'], d['b_upper']), precision=prec, max_substeps_local=int(d['T']))
     o.add_effector(type=1, action_dim=6, scale_v=(1, 1, 1, 5, 5, 5), boundary=cube(d['e_lower'], d['e_upper']), radius=0.015, flux=int(d['flux']), inject_v=(-3.0, 0, 0),
-                   inject_p=(-0.07, 0, 0), locally_random=False, random_vector=d['random_vector'], act_range=np.where(d['used0'] == 0)[0], max_action_steps=20)
+                   inject_p=(-0.07, 0, 0), locally_random=False, random_vector=d['random_vector'], act_range=np.where(d['used0'] == 0)[0], max_action_steps=20, randomize_inject_v=randv)
     o.set_collector(cube(d['c_lower'], d['c_upper']), mat=M.WATER)
     o.set_frame(0, d['x0'], np.zeros((N, 3)), np.zeros((N, 3, 3)), np.tile(np.eye(3), (N, 1, 1)), d['used0'])
     o.set_effector_state(0, 0, np.concatenate([d['init_state'][:7], [0.0]])); o.apply_action_p(d['action_p'])
