@@ -41,6 +41,7 @@ struct FmpmHandle {
   int use_pdl;    // programmatic dependent launch of the forward chain (FMPM_PDL=0 switches it off)
   int slab_pull_ok;   // x-slab forward steps: grid_op reads the neighbours' ghost planes instead of p2g pushing them (FMPM_SLAB_PULL=0: push form)
   int slab_pull;      // set by fmpm_substeps_slab around its launches: the scatter kernels stay local, grid_op is k_grid_op_pull
+  int slab_fsync;     // pull form: the neighbour handshake runs INSIDE k_grid_op_pull (FMPM_SLAB_FSYNC=0: the separate k_slab_sync launch before it)
 };
 
 int fmpm_advect_rigid_impl(FmpmHandle* h, int f, void* stream);  // fmpm_rigid.cu; no-op without MAT_RIGID bodies
@@ -434,6 +435,26 @@ static inline void fmpm_launch_pdl(const bool pdl, void (*kern)(Params...), cons
 }
 #define FMPM_LAUNCH_PDL(pdl, kern, grid, block, smem, stream, ...) fmpm_launch_pdl(pdl, kern, grid, block, smem, stream, __VA_ARGS__)
 #endif
+
+// ---- neighbour handshake of the x-slab steps (k_slab_sync in fmpm_io.cu, and fused into k_grid_op_pull in fmpm_forward.cu)
+#ifdef FMPM_HOST_EMU
+#include <chrono>
+#define FMPM_SYSTEM_FENCE() std::atomic_thread_fence(std::memory_order_seq_cst)
+static inline unsigned long long fmpm_now_ns() { return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#else
+#define FMPM_SYSTEM_FENCE() __threadfence_system()
+__device__ __forceinline__ unsigned long long fmpm_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+#ifndef FMPM_SYNC_TIMEOUT_NS
+#define FMPM_SYNC_TIMEOUT_NS 10000000000ULL   // 10 s: ranks enter a step together (the migration census is a collective), real skews are microseconds
+#endif
+__device__ __forceinline__ void slab_wait(volatile int* slot, const int e, int* err) {
+  if (*slot >= e) return;
+  const unsigned long long t0 = fmpm_now_ns();
+  while (*slot < e) {
+    if (fmpm_now_ns() - t0 > FMPM_SYNC_TIMEOUT_NS) { *err = 1; return; }   // never hang the GPU on a peer that stopped
+  }
+}
 
 #define FMPM_CHECK_LAUNCH(h, name)                                                        \
   do {                                                                                    \

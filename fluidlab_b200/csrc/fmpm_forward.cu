@@ -235,55 +235,94 @@ __device__ __forceinline__ float4 ld_peer_v4(const float4* p) {
 #endif
 }
 __device__ __forceinline__ int ld_peer_flag(const int* p) { return *(const volatile int*)p; }
-__global__ void __launch_bounds__(256) k_grid_op_pull(const KParams P, const int f, float4* __restrict__ pm_other, int* __restrict__ flags_other) {
+// Handshake inside the launch (sig != nullptr; round 2, r02y: the separate one-thread k_slab_sync launch + a grid_op that could not start before both
+// neighbours had arrived cost ~20 us per substep at 2 GPUs): block 0 posts this rank's epoch E = sig[2] + 1 to the neighbours (sig[2] is only advanced by
+// the LAST block of this launch, so every block reads the same E), the blocks first convert the nodes no neighbour contributes to, and only then wait
+// for the neighbours' epochs — once — before they read peer flags / peer ghost planes and clear the other parity's ghost blocks.
+__device__ __forceinline__ void grid_op_pull_block(const KParams& P, const int f, const int blk, const bool ghost) {
+  const int n = P.n, nb = P.nb;
+  const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+  const int x0 = bx * 8;
+  const bool gl = ghost && P.peer_l != nullptr && x0 < P.gl_hi && x0 + 8 > P.gl_lo, gr = ghost && P.peer_r != nullptr && x0 < P.gr_hi && x0 + 8 > P.gr_lo;
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int t = threadIdx.x + r * 256;
+    const int i = x0 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+    const int g = (i * n + j) * n + k;
+    float4 pm = P.grid_pm[g];
+    const bool clr = !(gl || gr) && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f);
+    if (gl && i >= P.gl_lo && i < P.gl_hi) { const float4 q = ld_peer_v4(P.peer_l + g); pm.x += q.x; pm.y += q.y; pm.z += q.z; pm.w += q.w; }
+    if (gr && i >= P.gr_lo && i < P.gr_hi) { const float4 q = ld_peer_v4(P.peer_r + g); pm.x += q.x; pm.y += q.y; pm.z += q.z; pm.w += q.w; }
+    P.grid_v[g] = grid_op_node_full(P, f, i, j, k, pm);
+    if (clr) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (!(gl || gr) && threadIdx.x == 0) P.blk_flags[blk] = 0;
+}
+__global__ void __launch_bounds__(256) k_grid_op_pull(const KParams P, const int f, float4* __restrict__ pm_other, int* __restrict__ flags_other,
+                                                      int* sig, int* psig_l, int* psig_r) {
   const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
   __shared__ int s_act[256];
+  __shared__ int s_gho[256];
   __shared__ int s_clr[256];
-  __shared__ int s_n, s_nc;
-  if (threadIdx.x == 0) { s_n = 0; s_nc = 0; }
+  __shared__ int s_n, s_ng, s_nc;
+  if (threadIdx.x == 0) { s_n = 0; s_ng = 0; s_nc = 0; }
+  const int E = sig ? ((volatile int*)sig)[2] + 1 : 0;
+  if (sig && blockIdx.x == 0 && threadIdx.x == 0) {   // my scatter of frame f (the kernels before this one) is complete: tell the neighbours
+    FMPM_SYSTEM_FENCE();
+    if (psig_l) ((volatile int*)psig_l)[1] = E;   // I am my left neighbour's RIGHT neighbour
+    if (psig_r) ((volatile int*)psig_r)[0] = E;
+    FMPM_SYSTEM_FENCE();
+  }
   __syncthreads();
   {
     const int blk = blockIdx.x + threadIdx.x * gridDim.x;
     if (blk < nblk) {
       const int x0 = (blk / (nb * nb)) * 8;
+      const bool ghost = (P.peer_fl != nullptr && x0 < P.gl_hi && x0 + 8 > P.gl_lo) || (P.peer_fr != nullptr && x0 < P.gr_hi && x0 + 8 > P.gr_lo);
+      if (ghost) s_gho[atomicAdd(&s_ng, 1)] = blk;                       // its flags (mine | the neighbour's) are read after the handshake
+      else if (P.blk_flags[blk] != 0) s_act[atomicAdd(&s_n, 1)] = blk;
+      if (flags_other[blk] != 0) s_clr[atomicAdd(&s_nc, 1)] = blk;      // ghost blocks of the previous substep: cleared after the handshake
+    }
+  }
+  __syncthreads();
+  const int n_act = s_n, n_gho = s_ng, n_clr = s_nc;
+  for (int ai = 0; ai < n_act; ai++) grid_op_pull_block(P, f, s_act[ai], false);
+  if (n_gho > 0 || n_clr > 0) {
+    if (sig && threadIdx.x == 0) {
+      if (psig_l) slab_wait((volatile int*)sig + 0, E, sig + 3);
+      if (psig_r) slab_wait((volatile int*)sig + 1, E, sig + 3);
+      FMPM_SYSTEM_FENCE();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (threadIdx.x < n_gho) {   // (n_gho <= 256: one candidate per thread at most)
+      const int blk = s_gho[threadIdx.x];
+      const int x0 = (blk / (nb * nb)) * 8;
       int act = P.blk_flags[blk];
       if (P.peer_fl != nullptr && x0 < P.gl_hi && x0 + 8 > P.gl_lo) act |= ld_peer_flag(P.peer_fl + blk);
       if (P.peer_fr != nullptr && x0 < P.gr_hi && x0 + 8 > P.gr_lo) act |= ld_peer_flag(P.peer_fr + blk);
       if (act != 0) s_act[atomicAdd(&s_n, 1)] = blk;
-      if (flags_other[blk] != 0) s_clr[atomicAdd(&s_nc, 1)] = blk;   // ghost blocks of the previous substep: every neighbour has read them by now
+    }
+    __syncthreads();
+    const int n_act2 = s_n;
+    for (int ai = 0; ai < n_act2; ai++) grid_op_pull_block(P, f, s_act[ai], true);
+    for (int ci = 0; ci < n_clr; ci++) {
+      const int blk = s_clr[ci];
+      const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const int t = threadIdx.x + r * 256;
+        const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
+        pm_other[(i * n + j) * n + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (threadIdx.x == 0) flags_other[blk] = 0;
     }
   }
-  __syncthreads();
-  const int n_act = s_n, n_clr = s_nc;
-  for (int ai = 0; ai < n_act; ai++) {
-    const int blk = s_act[ai];
-    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
-    const int x0 = bx * 8;
-    const bool gl = P.peer_l != nullptr && x0 < P.gl_hi && x0 + 8 > P.gl_lo, gr = P.peer_r != nullptr && x0 < P.gr_hi && x0 + 8 > P.gr_lo;
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const int t = threadIdx.x + r * 256;
-      const int i = x0 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
-      const int g = (i * n + j) * n + k;
-      float4 pm = P.grid_pm[g];
-      const bool clr = !(gl || gr) && (pm.w != 0.f || pm.x != 0.f || pm.y != 0.f || pm.z != 0.f);
-      if (gl && i >= P.gl_lo && i < P.gl_hi) { const float4 q = ld_peer_v4(P.peer_l + g); pm.x += q.x; pm.y += q.y; pm.z += q.z; pm.w += q.w; }
-      if (gr && i >= P.gr_lo && i < P.gr_hi) { const float4 q = ld_peer_v4(P.peer_r + g); pm.x += q.x; pm.y += q.y; pm.z += q.z; pm.w += q.w; }
-      P.grid_v[g] = grid_op_node_full(P, f, i, j, k, pm);
-      if (clr) P.grid_pm[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (!(gl || gr) && threadIdx.x == 0) P.blk_flags[blk] = 0;
-  }
-  for (int ci = 0; ci < n_clr; ci++) {
-    const int blk = s_clr[ci];
-    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const int t = threadIdx.x + r * 256;
-      const int i = bx * 8 + (t >> 6), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t & 7);
-      pm_other[(i * n + j) * n + k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (threadIdx.x == 0) flags_other[blk] = 0;
+  if (sig && threadIdx.x == 0) {   // the last block out advances the epoch for the next handshake (sig[4]: blocks done)
+    FMPM_SYSTEM_FENCE();
+    const int done = atomicAdd(sig + 4, 1);
+    if (done == (int)gridDim.x - 1) { sig[4] = 0; ((volatile int*)sig)[2] = E; }
   }
 }
 
@@ -966,7 +1005,13 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring
   const int reset_flags = (clear_pm && ring_slot < 0) ? 1 : 0;
   if (h->slab_pull) {   // fmpm_substeps_slab, pull form: ghost planes read from the neighbours, the other parity's ghost blocks cleared
     const KParams Po = make_kparams(h, -1, f + 1);
-    FMPM_LAUNCH(k_grid_op_pull, grid, 256, 0, stream, P, f, Po.grid_pm, Po.blk_flags);
+    int* sig = h->slab_fsync ? (int*)h->slab.signal : nullptr;   // handshake inside the launch (fmpm_substeps_slab then skips its k_slab_sync)
+    if (sig) {   // blocks that wait for a neighbour must not keep later blocks (with neighbour-independent work) off the SMs: one resident wave (78 registers x 256)
+      const int resident = h->sm_count * 3;
+      if (grid > resident && (nblk + resident - 1) / resident <= 256) grid = resident;
+    }
+    FMPM_LAUNCH(k_grid_op_pull, grid, 256, 0, stream, P, f, Po.grid_pm, Po.blk_flags, sig, sig ? (int*)h->slab.peer_signal_left : nullptr,
+                sig ? (int*)h->slab.peer_signal_right : nullptr);
     FMPM_CHECK_LAUNCH(h, "fmpm_grid_op(pull)");
     return 0;
   }

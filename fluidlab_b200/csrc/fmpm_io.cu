@@ -19,6 +19,7 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
   { const char* e = getenv("FMPM_FWD_STRIDE"); h->fwd_stride = (e && e[0] == '1' && e[1] == 0) ? 1 : 0; }
   { const char* e = getenv("FMPM_PDL"); h->use_pdl = (e && e[0] == '0') ? 0 : 1; }
   h->slab_pull_ok = 0; h->slab_pull = 0;   // fmpm_set_slab_pull
+  { const char* e = getenv("FMPM_SLAB_FSYNC"); h->slab_fsync = (e && e[0] == '0') ? 0 : 1; }
   memset(&h->buf, 0, sizeof(h->buf));
   memset(&h->col, 0, sizeof(h->col));
   memset(&h->slab, 0, sizeof(h->slab));
@@ -79,24 +80,7 @@ extern "C" int fmpm_set_slab(FmpmHandle* h, const FmpmSlab* s) {
 // neighbour handshake of the x-slab mode: epochs in peer-addressable memory.  A rank posts e = ++epoch into its neighbours' slots (after a
 // system-scope fence: its peer reductions of the kernels before are visible first) and waits until both neighbours posted >= e.  The spin
 // is bounded IN TIME (globaltimer): a rank that never arrives (a crashed peer) raises the error flag instead of hanging the GPU.
-#ifdef FMPM_HOST_EMU
-#include <chrono>
-#define FMPM_SYSTEM_FENCE() std::atomic_thread_fence(std::memory_order_seq_cst)
-static inline unsigned long long fmpm_now_ns() { return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-#else
-#define FMPM_SYSTEM_FENCE() __threadfence_system()
-__device__ __forceinline__ unsigned long long fmpm_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#endif
-#ifndef FMPM_SYNC_TIMEOUT_NS
-#define FMPM_SYNC_TIMEOUT_NS 10000000000ULL   // 10 s: ranks enter a step together (the migration census is a collective), real skews are microseconds
-#endif
-__device__ __forceinline__ void slab_wait(volatile int* slot, const int e, int* err) {
-  if (*slot >= e) return;
-  const unsigned long long t0 = fmpm_now_ns();
-  while (*slot < e) {
-    if (fmpm_now_ns() - t0 > FMPM_SYNC_TIMEOUT_NS) { *err = 1; return; }   // never hang the GPU on a peer that stopped
-  }
-}
+// (FMPM_SYSTEM_FENCE, fmpm_now_ns, slab_wait: fmpm_common.cuh — k_grid_op_pull runs the same handshake inside the grid_op launch)
 __global__ void k_slab_sync(int* sig, int* peer_l, int* peer_r) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int e = sig[2] + 1;
@@ -139,7 +123,7 @@ extern "C" int fmpm_substeps_slab(FmpmHandle* h, int f0, int n, int fuse, void* 
   for (int i = 0; i < n && !rc; i++) {
     const int f = f0 + i;
     if (!(fuse && i > 0)) rc = fmpm_p2g(h, f, 1, stream);    // fused: the previous substep's g2p2g scattered frame f already
-    if (!rc) rc = fmpm_slab_sync(h, stream) || fmpm_grid_op(h, f, 1, stream);
+    if (!rc) rc = ((h->slab_pull && h->slab_fsync) ? 0 : fmpm_slab_sync(h, stream)) || fmpm_grid_op(h, f, 1, stream);   // pull form: the handshake runs inside k_grid_op_pull
     if (rc) break;
     if (fuse && i + 1 < n) rc = fmpm_fwd_step_impl(h, f, i + 2 == n, stream);   // the last fused substep completes F[f+2] (all-liquid scenes)
     else rc = fmpm_g2p(h, f, stream);
