@@ -24,8 +24,9 @@
 #endif
 
 #ifndef BWD_PREFETCH
-#define BWD_PREFETCH 1   // L2 prefetch of the planes a backward kernel reads late (the adjoint of frame f+1, F): r02x ncu — k_particle_grad waits 3.3 issue slots per
-                         // instruction on long-scoreboard stalls at 14 resident warps per SM, its second batch of loads is issued after the footprint staging
+#define BWD_PREFETCH 1   // L2 prefetch of the planes k_particle_grad reads late (the adjoint of frame f+1, F): r02x ncu — it waits 3.3 issue slots per instruction on
+                         // long-scoreboard stalls at 14 resident warps per SM and issues its second batch of loads after the footprint staging.  r02z A/B: 110.1 us with
+                         // the prefetch, 114.1 without; the same in k_g2p_grad_scatter cost registers and time (85.8 against 79.5 us) and was taken out again
 #endif
 // one 128-byte line per 8 lanes of a float4 plane (the warp's 32 slots are 512 contiguous bytes), lane 0 for a float plane
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -52,7 +53,7 @@ __device__ __forceinline__ void load_grad(const KParams& P, int g, int s, GState
 // g2p.grad, grid side:  gv_out[i] += w_i * (gv + 4 inv_dx * gC' (o - fx)),  gv = gv' + dt * gx'
 // =============================================================================================
 template <bool kSlab>
-__global__ void __launch_bounds__(SC_WARPS * 32, 6) k_g2p_grad_scatter(const KParams P, const int f, const int gin) {
+__global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParams P, const int f, const int gin) {
   __shared__ ScatterSmem smem[SC_WARPS];
   const int lane = threadIdx.x & 31, wib = __shfl_sync(SC_FULL, (int)(threadIdx.x >> 5), 0);   // broadcast: dependent code is compiled warp-uniform
   ScatterSmem& S = smem[wib];
@@ -72,11 +73,6 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 6) k_g2p_grad_scatter(const KPa
     float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     if (sl < P.N) {
       const int s = (int)sl;
-      if (r == 0) prefetch_planes4(P.ga, P, gin, 4, s);
-      if (r + 1 < SC_ROUNDS && sl + 32 < P.N) {   // the next round's first loads are in L2 by the time this round's node loop is done
-        if (BWD_PREFETCH && (threadIdx.x & 7) == 0) prefetch_l2(P.pa + pa_idx(P, f, 0, s + 32));
-        prefetch_planes4(P.ga, P, gin, 4, s + 32);
-      }
       const float4 a0 = P.pa[pa_idx(P, f, 0, s)];
       const float x[3] = {a0.x, a0.y, a0.z};
       int b[3]; float fx[3];

@@ -450,6 +450,7 @@ __device__ __forceinline__ unsigned long long fmpm_now_ns() { unsigned long long
 #endif
 __device__ __forceinline__ void slab_wait(volatile int* slot, const int e, int* err) {
   if (*slot >= e) return;
+  if (*(volatile int*)err) return;   // a handshake already timed out: fail fast from here on (the host reads the flag, SlabMPMSimulator.sync_error)
   const unsigned long long t0 = fmpm_now_ns();
   while (*slot < e) {
     if (fmpm_now_ns() - t0 > FMPM_SYNC_TIMEOUT_NS) { *err = 1; return; }   // never hang the GPU on a peer that stopped
