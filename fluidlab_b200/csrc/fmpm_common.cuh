@@ -41,7 +41,7 @@ struct FmpmHandle {
   int use_pdl;    // programmatic dependent launch of the forward chain (FMPM_PDL=0 switches it off)
   int slab_pull_ok;   // x-slab forward steps: grid_op reads the neighbours' ghost planes instead of p2g pushing them (FMPM_SLAB_PULL=0: push form)
   int slab_pull;      // set by fmpm_substeps_slab around its launches: the scatter kernels stay local, grid_op is k_grid_op_pull
-  int slab_fsync;     // pull form: the neighbour handshake runs INSIDE k_grid_op_pull (FMPM_SLAB_FSYNC=0: the separate k_slab_sync launch before it)
+  int slab_fsync;     // pull form, opt-in (FMPM_SLAB_FSYNC=1): the neighbour handshake runs INSIDE k_grid_op_pull instead of in a k_slab_sync launch before it
 };
 
 int fmpm_advect_rigid_impl(FmpmHandle* h, int f, void* stream);  // fmpm_rigid.cu; no-op without MAT_RIGID bodies

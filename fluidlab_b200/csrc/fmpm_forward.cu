@@ -235,8 +235,8 @@ __device__ __forceinline__ float4 ld_peer_v4(const float4* p) {
 #endif
 }
 __device__ __forceinline__ int ld_peer_flag(const int* p) { return *(const volatile int*)p; }
-// Handshake inside the launch (sig != nullptr; round 2, r02y: the separate one-thread k_slab_sync launch + a grid_op that could not start before both
-// neighbours had arrived cost ~20 us per substep at 2 GPUs): block 0 posts this rank's epoch E = sig[2] + 1 to the neighbours (sig[2] is only advanced by
+// Handshake inside the launch (sig != nullptr; opt-in, FMPM_SLAB_FSYNC=1 — parity green on 2 GPUs but 2 % SLOWER than the separate one-thread k_slab_sync launch,
+// r02v: 16.2 k against 16.6 k substeps/s; the one resident wave of 444 fat blocks it needs costs the neighbour-independent part more than the launch it saves): block 0 posts this rank's epoch E = sig[2] + 1 to the neighbours (sig[2] is only advanced by
 // the LAST block of this launch, so every block reads the same E), the blocks first convert the nodes no neighbour contributes to, and only then wait
 // for the neighbours' epochs — once — before they read peer flags / peer ghost planes and clear the other parity's ghost blocks.
 __device__ __forceinline__ void grid_op_pull_block(const KParams& P, const int f, const int blk, const bool ghost) {

@@ -19,7 +19,7 @@ extern "C" int fmpm_create(const FmpmConfig* cfg, FmpmHandle** out) {
   { const char* e = getenv("FMPM_FWD_STRIDE"); h->fwd_stride = (e && e[0] == '1' && e[1] == 0) ? 1 : 0; }
   { const char* e = getenv("FMPM_PDL"); h->use_pdl = (e && e[0] == '0') ? 0 : 1; }
   h->slab_pull_ok = 0; h->slab_pull = 0;   // fmpm_set_slab_pull
-  { const char* e = getenv("FMPM_SLAB_FSYNC"); h->slab_fsync = (e && e[0] == '0') ? 0 : 1; }
+  { const char* e = getenv("FMPM_SLAB_FSYNC"); h->slab_fsync = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured r02v (2 GPUs) 16.2 k substeps/s against 16.6 k with the separate k_slab_sync launch
   memset(&h->buf, 0, sizeof(h->buf));
   memset(&h->col, 0, sizeof(h->col));
   memset(&h->slab, 0, sizeof(h->slab));
