@@ -19,6 +19,9 @@
 #include "fmpm_sdf.cuh"
 
 #define SC_WARPS 4
+#ifndef SC_AHEAD
+#define SC_AHEAD 0   // > 0: L2 prefetch of the first plane of the CTA SC_AHEAD CTAs further on
+#endif
 #ifndef SC_ROUNDS
 #define SC_ROUNDS 4   // 1 / 2 rounds: no gain for this kernel (A/B in profiles/README.md)
 #endif
@@ -28,12 +31,7 @@
                          // long-scoreboard stalls at 14 resident warps per SM and issues its second batch of loads after the footprint staging.  r02z A/B: 110.1 us with
                          // the prefetch, 114.1 without; the same in k_g2p_grad_scatter cost registers and time (85.8 against 79.5 us) and was taken out again
 #endif
-// one 128-byte line per 8 lanes of a float4 plane (the warp's 32 slots are 512 contiguous bytes), lane 0 for a float plane
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-#ifndef FMPM_HOST_EMU
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
+// one 128-byte line per 8 lanes of a float4 plane (the warp's 32 slots are 512 contiguous bytes), lane 0 for a float plane (prefetch_l2: fmpm_common.cuh)
 __device__ __forceinline__ void prefetch_planes4(const float4* base, const KParams& P, const int g, const int nplanes, const int s) {
   if (BWD_PREFETCH && (threadIdx.x & 7) == 0)
     for (int k = 0; k < nplanes; k++) prefetch_l2(base + ((size_t)g * nplanes + k) * (size_t)P.N + s);
@@ -73,6 +71,10 @@ __global__ void __launch_bounds__(SC_WARPS * 32) k_g2p_grad_scatter(const KParam
     float w[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     if (sl < P.N) {
       const int s = (int)sl;
+#if SC_AHEAD > 0
+      if (r == 0 && sl + (long long)SC_AHEAD * SC_WARPS * 32 * SC_ROUNDS < P.N && (threadIdx.x & 7) == 0)
+        prefetch_l2(P.pa + pa_idx(P, f, 0, s + SC_AHEAD * SC_WARPS * 32 * SC_ROUNDS));
+#endif
       const float4 a0 = P.pa[pa_idx(P, f, 0, s)];
       const float x[3] = {a0.x, a0.y, a0.z};
       int b[3]; float fx[3];
@@ -262,6 +264,9 @@ __device__ __forceinline__ Mat3 constitutive_grad(const KParams& P, const Consti
 }
 
 #define PG_WARPS 4
+#ifndef PG_AHEAD
+#define PG_AHEAD 0   // > 0: L2 prefetch of the state planes of the CTA PG_AHEAD CTAs further on (A/B: 148 x 4 = 592)
+#endif
 #ifndef PG_MINB_LIQUID
 #define PG_MINB_LIQUID 4   // all-liquid instantiation: 128 registers, 12 B of spills (5 CTAs/SM = 96 registers would spill 372 B)
 #endif
@@ -346,6 +351,9 @@ __global__ void __launch_bounds__(PG_WARPS * 32, kMat == 1 ? PG_MINB_LIQUID : PG
     load_A(P.pa, P, f, s, st);
     prefetch_planes4(P.pf, P, f, 2, s); prefetch_plane1(P.pf8, P, f, s);   // read after the footprint staging: F[f], then the adjoint of frame f+1
     prefetch_planes4(P.ga, P, gin, 4, s); prefetch_planes4(P.gf, P, gin, 2, s); prefetch_plane1(P.gf8, P, gin, s);
+#if PG_AHEAD > 0
+    if ((long long)s + (long long)PG_AHEAD * PG_WARPS * 32 < P.N) prefetch_planes4(P.pa, P, f, 4, s + PG_AHEAD * PG_WARPS * 32);   // the first loads of the CTA that takes this one's place
+#endif
   }
   int b[3]; float fx[3];
   const bool ok = (s < P.N) && (st.meta & 1) && base_fx(P, st.x, b, fx);

@@ -436,6 +436,11 @@ static inline void fmpm_launch_pdl(const bool pdl, void (*kern)(Params...), cons
 #define FMPM_LAUNCH_PDL(pdl, kern, grid, block, smem, stream, ...) fmpm_launch_pdl(pdl, kern, grid, block, smem, stream, __VA_ARGS__)
 #endif
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef FMPM_HOST_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 // ---- neighbour handshake of the x-slab steps (k_slab_sync in fmpm_io.cu, and fused into k_grid_op_pull in fmpm_forward.cu)
 #ifdef FMPM_HOST_EMU
 #include <chrono>

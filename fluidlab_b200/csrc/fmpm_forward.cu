@@ -181,6 +181,9 @@ __device__ __forceinline__ float4 grid_op_node_full(const KParams& P, const int 
   }
   return out;
 }
+#ifndef GOP_PER_SM
+#define GOP_PER_SM 8   // CTAs of k_grid_op per SM (one resident wave of 256-thread CTAs)
+#endif
 __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, const int clear_pm, const int zero_ggv, const int reset_flags) {
   const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
   // this CTA owns blocks blockIdx.x + q*gridDim.x; their flags are fetched in parallel (thread q reads flag q) and the CTA
@@ -213,6 +216,42 @@ __global__ void __launch_bounds__(256) k_grid_op(const KParams P, const int f, c
       if (zero_ggv) P.ggrid_v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (reset_flags && threadIdx.x == 0) P.blk_flags[blk] = 0;
+  }
+}
+
+// Warp-per-block variant (GOP_WARP=1, A/B): no shared memory, no block barrier — every warp owns the flags gw, gw + n_warps, ...; a flagged block is 16 nodes per
+// lane, converted four at a time (four independent 128-bit loads in flight per lane, rows of 8 nodes = 128 contiguous bytes).
+#ifndef GOP_WARP
+#define GOP_WARP 0
+#endif
+__global__ void __launch_bounds__(256) k_grid_op_warp(const KParams P, const int f, const int clear_pm, const int zero_ggv, const int reset_flags) {
+  const int n = P.n, nb = P.nb, nblk = nb * nb * nb;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+  fmpm_pdl_trigger();
+  fmpm_pdl_wait();
+  for (int blk = gw; blk < nblk; blk += nw) {
+    if (P.blk_flags[blk] == 0) continue;   // warp-uniform
+    const int bx = blk / (nb * nb), by = (blk / nb) % nb, bz = blk % nb;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 16; r0 += 4) {
+      float4 pm[4]; int g[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = lane + (r0 + u) * 32;
+        g[u] = ((bx * 8 + (t >> 6)) * n + by * 8 + ((t >> 3) & 7)) * n + bz * 8 + (t & 7);
+        pm[u] = P.grid_pm[g[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = lane + (r0 + u) * 32;
+        P.grid_v[g[u]] = grid_op_node_full(P, f, bx * 8 + (t >> 6), by * 8 + ((t >> 3) & 7), bz * 8 + (t & 7), pm[u]);
+        if (clear_pm && (pm[u].w != 0.f || pm[u].x != 0.f || pm[u].y != 0.f || pm[u].z != 0.f)) P.grid_pm[g[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (zero_ggv) P.ggrid_v[g[u]] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncwarp();
+    if (reset_flags && lane == 0) P.blk_flags[blk] = 0;
   }
 }
 
@@ -516,6 +555,9 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
 #ifndef FWD_MINB
 #define FWD_MINB 7   // with FWD_WARPS 3: 21 warps per SM at <= 96 registers
 #endif
+#ifndef FWD_AHEAD
+#define FWD_AHEAD 0   // > 0: L2 prefetch of the particle lines of the CTA FWD_AHEAD CTAs further on (A/B: 148 x 8 = 1184)
+#endif
 #ifndef FWD_PERSIST
 #define FWD_PERSIST 0   // (measured r02x: 110.9 us per substep against 104.3 — the loop costs more instructions and spills than the CTA turnover it saves)  1: persistent warps — sm_count x FWD_MINB CTAs, every warp claims 32-slot chunks from a global counter (P.blk_list[0]) until none is
                         // left: no CTA turnover, and the tail of the grid shrinks from a partial wave of CTAs to one chunk.  Not with the lazy grid_op (kInline).
@@ -702,6 +744,17 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, FWD_MINB) k_fwd(const KParams 
     f8 = P2G_LD(p8_r);
     if (kMat != 1) { f0 = P2G_LD(pf_r); f1 = P2G_LD(pf_r + Ns); }
   }
+#if FWD_AHEAD > 0
+  {   // CTAs are dispatched in index order: the one that takes this CTA's place is ~FWD_AHEAD CTAs further on.  Its x / F lines go to L2 now, so that its
+      // first loads (the one DRAM latency nothing overlaps: long scoreboard 1.7 per issue, r02z) are L2 hits.  One 128-byte line per 8 lanes.
+    const long long ahead = (long long)FWD_AHEAD * FWD_WARPS * 32;
+    if (sl + ahead < P.N) {
+      if ((lane & 7) == 0) prefetch_l2(pa_f + ahead);
+      if (lane == 0) prefetch_l2(p8_r + ahead);
+      if (kMat != 1 && (lane & 7) == 0) { prefetch_l2(pf_r + ahead); prefetch_l2(pf_r + Ns + ahead); }
+    }
+  }
+#endif
   const int meta = __float_as_int(a0.w);
   const float x[3] = {a0.x, a0.y, a0.z};
   int b[3]; float fx[3];
@@ -999,7 +1052,7 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring
   if (!P.blk_flags) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: sparse-grid block flags were not bound"); return 1; }
   if (zero_ggv && !P.ggrid_v) { snprintf(h->err, sizeof(h->err), "fmpm_grid_op: gradient grids were not bound"); return 1; }
   const int nblk = P.nb * P.nb * P.nb;
-  int grid = nblk < h->sm_count * 8 ? nblk : h->sm_count * 8;
+  int grid = nblk < h->sm_count * GOP_PER_SM ? nblk : h->sm_count * GOP_PER_SM;
   if ((nblk + grid - 1) / grid > 256) grid = (nblk + 255) / 256;  // keep <= 256 blocks per CTA (parallel flag fetch)
   // the flags are consumed (reset) here only when nothing later in the substep needs them: plain forward substeps
   const int reset_flags = (clear_pm && ring_slot < 0) ? 1 : 0;
@@ -1015,7 +1068,15 @@ int fmpm_grid_op_impl(FmpmHandle* h, int f, int clear_pm, int zero_ggv, int ring
     FMPM_CHECK_LAUNCH(h, "fmpm_grid_op(pull)");
     return 0;
   }
+#if GOP_WARP
+  {
+    int gridw = (nblk + 7) / 8;
+    if (gridw > h->sm_count * 8) gridw = h->sm_count * 8;
+    FMPM_LAUNCH_PDL(h->use_pdl != 0, k_grid_op_warp, gridw, 256, 0, stream, P, f, clear_pm, zero_ggv, reset_flags);
+  }
+#else
   FMPM_LAUNCH_PDL(h->use_pdl != 0, k_grid_op, grid, 256, 0, stream, P, f, clear_pm, zero_ggv, reset_flags);
+#endif
   FMPM_CHECK_LAUNCH(h, "fmpm_grid_op");
   return 0;
 }
