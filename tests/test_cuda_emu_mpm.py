@@ -332,6 +332,23 @@ def test_bench_script_runs_end_to_end_on_the_emulated_device():
     assert isinstance(fb['adam_step_ms'], float), fb['adam_step_ms']
     ob = line['e2e_obs_bridge']
     assert 'error' not in ob and ob['d2h_bytes_per_step'] < line['e2e']['d2h_bytes_per_step']
+    rb = fb['roofline_bwd']
+    assert rb['frac'] > 0 and rb['backward_substep_ms'] > 0 and rb['algorithmic_bytes_per_substep'] == 432 * line['roofline']['n_used'] + 156 * line['roofline']['touched_nodes']
+
+
+@pytest.mark.parametrize('cfg,extra', [('C3', ['--particles', '6000', '--steps', '6']), ('C4', ['--particles', '6000'])])
+def test_bench_config_arms_run_on_the_emulated_device(cfg, extra):
+    """`bench.py --config C3 | C4` (BASELINE configs[2] / configs[3] through TaichiEnv: forward, forward + backward with dLoss/dAction, e2e) at a few thousand
+    particles on the shim: the SCRIPT and the scenes of tests/baseline_scenes.py; numbers meaningless.  C3 with 6 steps crosses the T = 50 ring boundary once."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'cuda_emu', 'run_bench_emu.py'), '--config', cfg, '--min-seconds', '0'] + extra, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line['metric'] == 'mpm_substeps_per_s_fwd' and line['value'] > 0 and line['fwd_bwd']['value'] > 0 and line['e2e']['value'] > 0
+    assert cfg in line['config']['workload'] and line['e2e']['d2h_bytes_per_step'] == 28 * line['config']['n_particle_slots']
+    if cfg == 'C3':
+        assert line['fwd_bwd']['dloss_daction_absmax'] > 0
 
 
 def test_circulation_stack_equals_a_run_of_the_real_reference_stack(emu):
