@@ -600,8 +600,14 @@ class MPMSimulator:
 
     def set_state(self, f_global, state):  # MPM:633-644
         f = self.f_global_to_f_local(f_global)
+        staged = isinstance(state, MPMSimulator._StagedState)
+        if staged and self.device.type == 'cuda':   # uploaded earlier on the copy stream (stage_state_async): order the frame write after that upload
+            torch.cuda.current_stream(self.device).wait_event(state.ready)
         if self.has_particles:
             self.setframe(f, state['x'], state['v'], state['C'], state['F'], state['used'])
+        if staged and self.device.type == 'cuda':   # its device buffers may be refilled once this frame write has run
+            ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(self.device))
+            state.slot['consumed'] = ev
         if self.agent is not None:
             self.agent.set_state(f, state['agent'])
         if self.smoke_field is not None:
@@ -623,6 +629,44 @@ class MPMSimulator:
         if not self.has_particles:
             return np.zeros((0,), dtype=np.int32)
         return self.readframe(f, ('used',))['used']
+
+    # ---- pipelined state upload: set_state's H2D copies taken off the compute stream
+    class _StagedState(dict):
+        """result of stage_state_async: the state dict set_state takes, with x, v, C, F, used already on (or on their way to) the device"""
+        ready = None
+        slot = None
+
+    def stage_state_async(self, state):
+        """Start uploading a host state (the dict get_state returns; pinned tensors make the copies asynchronous) into one of two device staging sets on
+        a COPY stream and return at once: a later `set_state(f, staged)` writes the frame from those buffers, so the 100 B per particle of an episode's
+        initial state cross PCIe while the previous episode is still stepping (envs reset to states they know in advance).  The returned dict
+        is valid until the second-next stage_state_async call."""
+        assert self.has_particles
+        dev, N = self.device, self.n_particles
+        keys = (('x', (N, 3), torch.float32), ('v', (N, 3), torch.float32), ('C', (N, 3, 3), torch.float32), ('F', (N, 3, 3), torch.float32), ('used', (N,), torch.int32))
+        out = MPMSimulator._StagedState({k: v for k, v in state.items() if k not in ('x', 'v', 'C', 'F', 'used')})
+        if dev.type != 'cuda':   # (the CPU execution-model shim of tests/: nothing is asynchronous there)
+            for k, shp, dt in keys:
+                out[k] = torch.as_tensor(np.asarray(state[k]) if not torch.is_tensor(state[k]) else state[k]).to(dt).reshape(shp).clone()
+            out.slot = {'consumed': None}
+            return out
+        if not hasattr(self, '_stage_sets'):
+            self._stage_sets = [dict(dev={k: torch.empty(shp, dtype=dt, device=dev) for k, shp, dt in keys}, consumed=None) for _ in range(2)]
+            self._stage_next = 0
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        st = self._stage_sets[self._stage_next]; self._stage_next ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            if st['consumed'] is not None:
+                self._copy_stream.wait_event(st['consumed'])   # the frame write that last read this set has run
+            for k, shp, dt in keys:
+                a = state[k]
+                a = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+                st['dev'][k].copy_(a.reshape(shp), non_blocking=bool(a.device.type == 'cpu' and a.is_pinned()))
+            ready = torch.cuda.Event(); ready.record(self._copy_stream)
+        out.update(st['dev'])
+        out.ready, out.slot = ready, st
+        return out
 
     # ---- pipelined state read-back: the same data as get_state_RL, without stalling the simulation
     class _PendingState:
@@ -655,7 +699,8 @@ class MPMSimulator:
             mh = lambda: dict(x=torch.empty((N, 3), dtype=f32, pin_memory=True), v=torch.empty((N, 3), dtype=f32, pin_memory=True), used=torch.empty((N,), dtype=i32, pin_memory=True))
             self._rl_sets = [dict(dev=mk(), host=mh(), done=None) for _ in range(2)]
             self._rl_next = 0
-            self._copy_stream = torch.cuda.Stream(device=dev)
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
         st = self._rl_sets[self._rl_next]; self._rl_next ^= 1
         cur = torch.cuda.current_stream(dev)
         if st['done'] is not None:

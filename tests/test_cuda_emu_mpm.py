@@ -591,3 +591,9 @@ def test_c4_scene_at_reduced_size_on_the_emulated_device(emu):
         g.c4_case(48, 6000)
     finally:
         simulator.MPMSimulator.__init__ = orig
+
+
+def test_staged_state_upload_equals_blocking_set_state_on_the_emulated_device(emu):
+    """stage_state_async + set_state vs set_state (tests/test_gpu_parity.py: staged_upload_case) on the shim: the host logic of the staging sets"""
+    import test_gpu_parity as g
+    g.staged_upload_case(device='cpu')

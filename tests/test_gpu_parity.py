@@ -1265,3 +1265,60 @@ def test_device_side_observation_and_render_bridge():
     r = sim.get_state_render_device(sim.cur_substep_local)
     x_dl = torch.utils.dlpack.from_dlpack(torch.utils.dlpack.to_dlpack(r.x))
     assert x_dl.is_cuda and np.array_equal(x_dl.cpu().numpy(), state['x']) and np.array_equal(r.used.cpu().numpy(), state['used'])
+
+
+def staged_upload_case(device=None):
+    """body of the staged-upload test (also run on the CPU execution-model shim): episodes whose initial state arrives through stage_state_async (uploaded on a copy
+    stream while the previous episode is still stepping, double-buffered) end in exactly the states the blocking set_state gives; three episodes with DIFFERENT
+    initial states, so a staging set that was refilled too early or consumed too late would show."""
+    from fluidlab_b200 import MPMSimulator
+    rs = np.random.RandomState(5)
+    n_grid, N = 32, 6000
+    x = rs.uniform((0.3, 0.3, 0.3), (0.7, 0.55, 0.7), size=(N, 3))
+    P = make_particles(x, M.WATER, n_grid)
+    kw = dict(dim=3, quality=n_grid / 64, gravity=(0.0, -10.0, 0.0), horizon=100, max_substeps_local=20, max_substeps_global=10 ** 6, ckpt_dest='gpu')
+    if device is not None:
+        kw['device'] = device
+    sims = [MPMSimulator(**kw) for _ in range(2)]
+    for s in sims:
+        s.build(None, None, [], P)
+    base = sims[0].get_state()
+    inits = []
+    for e in range(3):
+        st = {k: np.array(v, copy=True) for k, v in base.items()}
+        st['v'] = (rs.randn(N, 3) * 0.5).astype(np.float32)
+        st['x'] = (st['x'] + rs.randn(N, 3).astype(np.float32) * 1e-3).astype(np.float32)
+        inits.append(st)
+    pin = lambda st: {k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory() if torch.cuda.is_available() and device is None else torch.from_numpy(np.ascontiguousarray(v)))
+                      for k, v in st.items()}
+    pinned = [pin(st) for st in inits]
+    a, b = sims
+    want = []
+    for e in range(3):                       # blocking uploads
+        a.cur_substep_global = 0
+        a.set_state(0, inits[e])
+        for _ in range(2):
+            a.step(None)
+        want.append(a.get_state())
+    got = []
+    staged = b.stage_state_async(pinned[0])
+    for e in range(3):                       # staged uploads: episode e+1's state is on its way while episode e steps
+        b.cur_substep_global = 0
+        b.set_state(0, staged)
+        if e + 1 < 3:
+            staged = b.stage_state_async(pinned[e + 1])
+        for _ in range(2):
+            b.step(None)
+        got.append(b.get_state())
+    for e in range(3):   # (two runs of the same path differ in the order of the scatter's reductions: compared at the parity bar, not bit for bit)
+        assert np.array_equal(got[e]['used'], want[e]['used'])
+        for k, bar in (('x', 1e-6), ('v', 1e-4), ('C', 1e-3), ('F', 1e-5)):
+            assert rel(got[e][k], want[e][k]) < bar, (e, k, rel(got[e][k], want[e][k]))
+    assert rel(want[0]['v'], want[1]['v']) > 0.1, 'the episodes must differ'
+
+
+@pytest.mark.gpu
+def test_staged_state_upload_equals_blocking_set_state():
+    """MPMSimulator.stage_state_async + set_state (the e2e path of bench.py) against the blocking set_state"""
+    _need_gpu()
+    staged_upload_case()
