@@ -268,7 +268,7 @@ __device__ __forceinline__ Mat3 constitutive_grad(const KParams& P, const Consti
 #define PG_AHEAD 0   // > 0: L2 prefetch of the state planes of the CTA PG_AHEAD CTAs further on (A/B: 148 x 4 = 592)
 #endif
 #ifndef PG_MINB_LIQUID
-#define PG_MINB_LIQUID 4   // all-liquid instantiation: 128 registers, 12 B of spills (5 CTAs/SM = 96 registers would spill 372 B)
+#define PG_MINB_LIQUID 4   // all-liquid instantiation: 128 registers, 12 B of spills.  r02last A/B (backward substep): 3 / 4 / 5 CTAs per SM = 207.5 / 204.7 / 207.3 us
 #endif
 #ifndef PG_MINB
 #define PG_MINB 4   // <=128 registers (16 warps/SM) with ~200 B of L1-resident spills: 164 us -> 121 us at 1M particles

@@ -30,8 +30,8 @@ def pytest_configure(config):
 
 # `-m gpu` tests that have not yet passed on a B200 are collected AFTER the hardware-validated ones, so that with `-x` a first-run surprise in a new
 # path does not hide the state of the paths that have already been measured.  Remove a pattern once its tests have passed on hardware.  (Round 2:
-# everything round 1 had left here has run green on hardware — profiles/README.md, r02n / r02u / r02v; the two C4 tests were re-conditioned after r02n.)
-FIRST_HARDWARE_RUN_PENDING = ('test_c4_',)
+# everything round 1 had left here has run green on hardware — profiles/README.md; the re-conditioned C4 tests and the staged-upload test in r02x / r02final.)
+FIRST_HARDWARE_RUN_PENDING = ()
 
 
 def pytest_collection_modifyitems(config, items):
