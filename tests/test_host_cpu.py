@@ -84,3 +84,33 @@ def test_product_library_path_is_the_nvcc_build_and_nothing_else_is_loaded_by_de
     import subprocess
     sym = subprocess.run(['nm', '-D', os.path.join(ROOT, 'fluidlab_b200', 'libfluidmpm.so')], capture_output=True, text=True).stdout
     assert 'cuemu' not in sym, 'the shipped library must be the nvcc build (no host-emulation symbols)'
+
+
+def test_ctypes_structs_match_the_c_headers(tmp_path):
+    """every struct the host passes by value / by pointer through the C ABI: sizeof and the offset of every field as gcc lays them out from include/*.h must equal
+    what fluidlab_b200/_lib.py declares with ctypes (a field added on one side only — e.g. FmpmInjector.randomize_inject_v — would shift everything after it)."""
+    import ctypes as C
+    import subprocess
+    from fluidlab_b200 import _lib
+    names = ['FmpmConfig', 'FmpmMaterial', 'FmpmBuffers', 'FmpmEffector', 'FmpmInjector', 'FmpmSdfMesh', 'FmpmColliders', 'FmpmSlab', 'FmpmCollector', 'FmpmBodies',
+             'FmpmAdamCfg', 'FsmkConfig', 'FsmkBuffers', 'FsmkAircon']
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fluidmpm.h"', '#include "fluidsmoke.h"', 'int main(void) {']
+    for n in names:
+        cls = getattr(_lib, n)
+        lines.append(f'  printf("{n} %zu", sizeof({n}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({n}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == len(names)
+    for n, line in zip(names, out):
+        tok = line.split()
+        cls = getattr(_lib, n)
+        assert tok[0] == n and int(tok[1]) == C.sizeof(cls), (n, int(tok[1]), C.sizeof(cls))
+        for (fname, _), off in zip(cls._fields_, tok[2:]):
+            assert getattr(cls, fname).offset == int(off), (n, fname, getattr(cls, fname).offset, int(off))
