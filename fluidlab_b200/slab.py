@@ -208,7 +208,7 @@ class SlabMPMSimulator:
     """Forward MLS-MPM over x-slabs: one local `MPMSimulator` per rank + ghost exchange + migration."""
 
     def __init__(self, quality, gravity, particles, gid, bounds, capacity, boundary=None, max_substeps_local=50, device=None, group=None, halo=4,
-                 exchange='peer', migrate=True, sim_factory=None, peer_factory=None, sync='signal', sort_every=1, use_graphs=True, migrate_every=1):
+                 exchange='peer', migrate=True, sim_factory=None, peer_factory=None, sync='signal', sort_every=1, use_graphs=True, migrate_every=1, statics=None):
         from .macros import NOWHERE
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -236,7 +236,9 @@ class SlabMPMSimulator:
                                     max_substeps_global=10 ** 7, ckpt_dest='gpu', device=device, sort_every=1)
             if boundary is not None:
                 self.sim.setup_boundary(**boundary)
-            self.sim.build(None, None, [], P)
+            # static SDF colliders (meshes/static.py, applied in grid_op MPM:388-390): every rank evaluates them on the nodes it converts, shared planes included —
+            # no pose, no exchange; Rigid effectors / agents and MAT_RIGID bodies stay single-GPU
+            self.sim.build(None, None, statics if statics is not None else [], P)
         else:   # tests: a stand-in with MPMSimulator's step-level methods and slab_* hooks (tests/test_slab_cpu.py)
             self.sim = sim_factory(quality=quality, gravity=gravity, particles=P, boundary=boundary, max_substeps_local=max_substeps_local)
             exchange = 'nccl' if exchange == 'peer' else exchange   # "nccl" = the all-reduce exchange, whatever the backend

@@ -125,7 +125,7 @@ class ShmPeers:
         self.dist.barrier(group=self.group)
 
 
-def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='barrier', pull=True):
+def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='barrier', pull=True, with_static=False):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     torch.set_num_threads(1)
@@ -149,8 +149,29 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='bar
 
         def parts(idx):
             return dict(x=x[idx], mat=mat[idx], used=np.ones(len(idx), np.int32), rho=np.array([M.RHO[m] for m in mat[idx]]), body_id=np.zeros(len(idx), np.int32), bodies={'n': 1})
+
+        def statics():   # a static box collider (meshes/static.py) across the slab boundary, in the way of the falling cloud
+            if not with_static:
+                return []
+            from conftest import box_sdf
+            from fluidlab_b200 import Statics
+            bv, bT = box_sdf((0.3, 0.04, 0.3), 0.4)
+            s = Statics()
+            s.add_static(file='box.obj', material=M.CUP, has_dynamics=True, pos=(0.5, 0.36, 0.5), sdf=dict(voxels=bv, T_mesh_to_voxels=bT))
+            return s
         slab = SlabMPMSimulator(quality, (0.0, -10.0, 0.0), parts(mine), gid=mine, bounds=bounds, capacity=len(mine) + 300, max_substeps_local=20, device='cpu', halo=4,
-                                exchange=exchange, peer_factory=ShmPeers, sync=sync)
+                                exchange=exchange, peer_factory=ShmPeers, sync=sync, statics=statics())
+
+        def static_effect(x_with):   # how far the single-domain run WITHOUT the collider ends from the one with it (rank 0, with_static only)
+            if not with_static:
+                return 0.0
+            r0 = MPMSimulator(dim=3, quality=quality, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
+            r0.use_graphs = False
+            r0.build(None, None, [], parts(np.arange(Ntot)))
+            s0 = r0.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; r0.set_state(0, s0)
+            for _ in range(n_steps):
+                r0.step(None)
+            return float(np.abs(r0.get_state()['x'] - x_with).max())
         assert slab.exchange == exchange and (slab.sync == sync or exchange != 'peer')
         assert slab.pull == (exchange == 'peer' and sync == 'signal' and pull)   # pull form of the ghost reduction: the one-call forward steps
         slab.sim.use_graphs = False
@@ -169,12 +190,12 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='bar
             if rank == 0:
                 ref = MPMSimulator(dim=3, quality=quality, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
                 ref.use_graphs = False
-                ref.build(None, None, [], parts(np.arange(Ntot)))
+                ref.build(None, None, statics(), parts(np.arange(Ntot)))
                 s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
                 for _ in range(n_steps):
                     ref.step(None)
                 r = ref.get_state()
-                out.update(ref_state={k: r[k] for k in ('x', 'v', 'F')})
+                out.update(ref_state={k: r[k] for k in ('x', 'v', 'F')}, static_effect=static_effect(r['x']))
             ret[rank] = out
             return
         slab.enable_grad()
@@ -193,7 +214,7 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='bar
         if rank == 0:   # the single-domain reference: the same product on the same emulated device
             ref = MPMSimulator(dim=3, quality=quality, gravity=(0.0, -10.0, 0.0), horizon=50, max_substeps_local=20, max_substeps_global=1000, ckpt_dest='cpu', device='cpu')
             ref.use_graphs = False
-            ref.build(None, None, [], parts(np.arange(Ntot)))
+            ref.build(None, None, statics(), parts(np.arange(Ntot)))
             s0 = ref.get_state(); s0['v'][:] = v0; s0['F'][:] = F0; ref.set_state(0, s0)
             ref.enable_grad()
             for _ in range(n_steps):
@@ -204,7 +225,7 @@ def _slab_worker(rank, world, port, ret, exchange='nccl', fused=False, sync='bar
             ref.set_grad(2.0 * (r['x'] - tgt.numpy()), np.zeros((Ntot, 3), np.float32), z9, z9)
             for _ in range(n_steps):
                 ref.step_grad(None)
-            out.update(ref_state={k: r[k] for k in ('x', 'v', 'F')}, ref_grad=ref.get_grad())
+            out.update(ref_state={k: r[k] for k in ('x', 'v', 'F')}, ref_grad=ref.get_grad(), static_effect=static_effect(r['x']))
         ret[rank] = out
     finally:
         dist.destroy_process_group()
@@ -376,6 +397,27 @@ def test_slab_forward_with_g2p2g_fusion_on_the_emulated_device(exchange):
         assert np.array_equal(fwd['gid'], np.arange(700)), 'particles lost or duplicated'
         assert rel(fwd['x'], ref_s['x']) < 1e-5 and rel(fwd['F'], ref_s['F']) < 1e-5 and rel(fwd['v'], ref_s['v']) < 1e-4
     assert all(out[r]['migrated'] > 0 for r in range(world))
+
+
+@pytest.mark.parametrize('mode', ['forward-fused', 'backward'])
+def test_slab_with_a_static_sdf_collider_matches_the_single_domain_run(mode):
+    """x-slabs + a static SDF collider (meshes/static.py:26-104, applied in grid_op MPM:388-390) that straddles the slab boundary: every rank evaluates it on the nodes
+    it converts (shared planes included, from identical ghost sums), so the sharded run — forward through the one-call pull-form steps, and forward + backward with
+    dL/d(x0, v0, C0, F0) — equals the single-domain run with the same collider; and the collider must have acted (the cloud falls onto the box)."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager(); ret = mgr.dict()
+    fused = mode == 'forward-fused'
+    mp.spawn(_slab_worker, args=(2, _free_port(), ret, 'peer', fused, 'signal', True, True), nprocs=2, join=True)
+    out = dict(ret)
+    ref_s = out[0]['ref_state']
+    assert out[0]['static_effect'] > 1e-3, 'the collider must change the run'
+    for r in (0, 1):
+        fwd = out[r]['fwd']
+        assert np.array_equal(fwd['gid'], np.arange(700)), 'particles lost or duplicated'
+        assert rel(fwd['x'], ref_s['x']) < 1e-5 and rel(fwd['F'], ref_s['F']) < 1e-5 and rel(fwd['v'], ref_s['v']) < 1e-4
+        if not fused:
+            errs = {k: rel(out[r]['grad'][k], out[0]['ref_grad'][k].astype(np.float64)) for k in 'xvCF'}
+            assert errs['x'] < 1e-4 and errs['v'] < 1e-4 and errs['C'] < 2e-3 and errs['F'] < 2e-3, errs
 
 
 @pytest.mark.parametrize('scene', ['latteart', 'jetbot', 'jetbot_randv', 'pouring', 'icecream', 'latteart_fused'])
