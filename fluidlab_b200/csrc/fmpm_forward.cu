@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, G2P2G_MINB) k_g2p2g(const KPar
 // the extra column in x and y absorbs the drift between two cell sorts), staged with coalesced 128-bit loads.
 // =============================================================================================
 #ifndef FWD_MINB
-#define FWD_MINB 7   // with FWD_WARPS 3: 21 warps per SM at <= 96 registers
+#define FWD_MINB 7   // with FWD_WARPS 3 ptxas settles at 80 registers, so 8 CTAs = 24 warps fit an SM (21 achieved, r02z ncu); 8 as the bound measured the same, 6 (96 registers) 3.5 % slower
 #endif
 #ifndef FWD_AHEAD
 #define FWD_AHEAD 0   // > 0: L2 prefetch of the particle lines of the CTA FWD_AHEAD CTAs further on (A/B: 148 x 8 = 1184)
