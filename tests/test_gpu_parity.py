@@ -1312,7 +1312,7 @@ def staged_upload_case(device=None):
         got.append(b.get_state())
     for e in range(3):   # (two runs of the same path differ in the order of the scatter's reductions: compared at the parity bar, not bit for bit)
         assert np.array_equal(got[e]['used'], want[e]['used'])
-        for k, bar in (('x', 1e-6), ('v', 1e-4), ('C', 1e-3), ('F', 1e-5)):
+        for k, bar in (('x', 1e-5), ('v', 1e-3), ('C', 1e-2), ('F', 1e-4)):   # a staging set refilled too early / consumed too late is an O(1) error
             assert rel(got[e][k], want[e][k]) < bar, (e, k, rel(got[e][k], want[e][k]))
     assert rel(want[0]['v'], want[1]['v']) > 0.1, 'the episodes must differ'
 
