@@ -324,6 +324,7 @@ def main():
                     "strong: BASELINE.json configs[4] — C5, 8M water particles on a 256^3 grid, sharded into N x-slabs (N = 1: one GPU holds it all)")
     ap.add_argument('--slab-shape', type=int, default=0, help='diagnostic (N = 1 only): run ONE slab of the `--gpus SLAB_SHAPE` weak-scaling workload (1M particles as a 24-plane slab on '
                     'the 256^3 grid, 10 % spare slots) alone on one GPU through the single-GPU path — the per-GPU cost of that workload without any exchange')
+    ap.add_argument('--min-substeps', type=int, default=1000, help='minimum number of substeps in the timed region (SURVEY.md 8d: >= 1,000)')
     ap.add_argument('--min-seconds', type=float, default=1.0, help='minimum length of the timed region (the K steps are repeated)')
     ap.add_argument('--fuse-g2p2g', type=int, default=1, help='1 (default, measured faster: profiles/README.md): forward steps use fmpm_substeps_fused (the gather of substep f and the '
                     'scatter of f+1 in one kernel, k_fwd); 0: the plain p2g / grid_op / g2p substeps')
@@ -459,7 +460,7 @@ def main():
         step_fn()
     p1.record(); barrier()
     probe_ms = max_over_ranks(p0.elapsed_time(p1))
-    reps = max(1, int(np.ceil(args.min_seconds * 1e3 / max(probe_ms, 1e-3))), int(np.ceil(1000 / (K * SUBSTEPS_PER_STEP))))
+    reps = max(1, int(np.ceil(args.min_seconds * 1e3 / max(probe_ms, 1e-3))), int(np.ceil(args.min_substeps / (K * SUBSTEPS_PER_STEP))))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as cs:
         e0.record()

@@ -336,7 +336,7 @@ def test_bench_script_runs_end_to_end_on_the_emulated_device():
     numbers are meaningless here."""
     import json
     import subprocess
-    r = subprocess.run([sys.executable, os.path.join(HERE, 'cuda_emu', 'run_bench_emu.py'), '--particles', '1200', '--steps', '2', '--warmup', '1', '--no-cpu', '--fuse-g2p2g', '1'], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'cuda_emu', 'run_bench_emu.py'), '--particles', '1200', '--steps', '2', '--warmup', '1', '--no-cpu', '--fuse-g2p2g', '1', '--min-seconds', '0', '--min-substeps', '40'], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e',
@@ -357,7 +357,7 @@ def test_bench_script_runs_end_to_end_on_the_emulated_device():
     assert rb['frac'] > 0 and rb['backward_substep_ms'] > 0 and rb['algorithmic_bytes_per_substep'] == 432 * line['roofline']['n_used'] + 156 * line['roofline']['touched_nodes']
 
 
-@pytest.mark.parametrize('cfg,extra', [('C3', ['--particles', '6000', '--steps', '6']), ('C4', ['--particles', '6000'])])
+@pytest.mark.parametrize('cfg,extra', [('C3', ['--particles', '3000', '--steps', '6']), ('C4', ['--particles', '6000'])])
 def test_bench_config_arms_run_on_the_emulated_device(cfg, extra):
     """`bench.py --config C3 | C4` (BASELINE configs[2] / configs[3] through TaichiEnv: forward, forward + backward with dLoss/dAction, e2e) at a few thousand
     particles on the shim: the SCRIPT and the scenes of tests/baseline_scenes.py; numbers meaningless.  C3 with 6 steps crosses the T = 50 ring boundary once."""
@@ -454,7 +454,7 @@ def test_multi_rank_bench_arm_runs_on_the_emulated_device():
     for r in (0, 1):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), SLAB_SYNC='signal')
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, 'cuda_emu', 'run_bench_emu.py'), '--gpus', '2', '--particles', '3000', '--steps', '2', '--warmup', '1',
-                                       '--no-cpu', '--bwd', '0', '--fuse-g2p2g', '1'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
+                                       '--no-cpu', '--bwd', '0', '--fuse-g2p2g', '1', '--min-seconds', '0', '--min-substeps', '40'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
     outs = [p.communicate(timeout=900) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs[0][1][-2000:] + outs[1][1][-2000:]
     line = json.loads(outs[0][0].strip().splitlines()[-1])
